@@ -1,0 +1,69 @@
+/* include/bc_host.h — host side of the drop-in: the reference's run set-up (format file, conversion CSVs,
+ * error caps), FASTQ ingest + packing into bc_batch, and the count/merged/enrichment CSV writers, as a C API
+ * over the C++ implementation in ngs-barcode-count_b200/csrc/host/.  It replaces, for this path only:
+ *   SequenceFormat::parse_format_file      info.rs:215-310
+ *   BarcodeConversions::*                  info.rs:364-456
+ *   MaxSeqErrors::new                      info.rs:490-543
+ *   input::read_fastq                      input.rs:24-148   (records -> packed pinned batches instead of a deque)
+ *   WriteFiles::write_counts_files         output.rs:74-485
+ * The compute itself goes through include/bc_b200.h; nothing here decodes a read on the CPU.
+ */
+#ifndef BC_HOST_H
+#define BC_HOST_H
+
+#include "bc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bch_run bch_run;
+
+/* arguments.rs:6-20, the part that shapes the path.  Negative max_err_* = flag not given (20 % default). */
+typedef struct {
+    const char *format_path;            /* --sequence-format (required) */
+    const char *sample_barcodes_path;   /* --sample-barcodes or NULL */
+    const char *counted_barcodes_path;  /* --counted-barcodes or NULL */
+    int max_errors_counted_barcode;
+    int max_errors_sample;
+    int max_errors_constant;
+    float min_quality;                  /* --min-quality */
+    uint32_t max_read_len;              /* longest read to expect (0: 2 x template length, at least 160) */
+} bch_args;
+
+/* Parses the three input files and derives the caps; on failure returns NULL and writes the message. */
+bch_run *bch_open(const bch_args *args, char *err, int errlen);
+void bch_close(bch_run *run);
+/* The configuration to hand to bc_create (owned by `run`). */
+const bc_config *bch_config(const bch_run *run);
+/* "-FORMAT-" and "-BARCODE INFO-" blocks as the reference prints them (info.rs:313-335, 618-659). */
+const char *bch_describe(const bch_run *run);
+uint32_t bch_barcode_num(const bch_run *run);
+/* reference DNA / ID of a slot's i-th barcode (NULL when out of range) */
+const char *bch_ref_dna(const bch_run *run, uint32_t slot, uint32_t i);
+const char *bch_ref_name(const bch_run *run, uint32_t slot, uint32_t i);
+
+/* Packs n reads (text) into caller-provided batch arrays sized with bc_plane_stride / bc_qual_stride.
+ * quals may be NULL (then qual_out is not touched).  Reads longer than max_read_len give BC_EINVAL; a quality
+ * string whose length differs from its sequence gives BC_EINVAL.  threads <= 1 packs on the calling thread. */
+int bch_pack(uint32_t max_read_len, uint32_t n, const char *const *seqs, const char *const *quals, uint32_t *planes_out,
+             uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
+/* Same, for reads given as one '\n'-separated text block each (convenient from ctypes). */
+int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, const char *qual_lines, uint32_t *planes_out,
+                   uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
+
+/* input::read_fastq replacement: streams a .fastq / .fastq.gz file through pinned double-buffered batches of
+ * `batch_reads` reads into ctx (bc_submit).  threads = host threads used for packing.  Returns BC_OK and the
+ * number of records. */
+int bch_count_fastq(bch_run *run, bc_ctx *ctx, const char *fastq_path, unsigned threads, uint32_t batch_reads,
+                    uint64_t *total_reads, char *err, int errlen);
+
+/* WriteFiles::write_counts_files: per-sample count CSVs, merged CSV, Single/Double enrichment CSVs, same names
+ * and layout as the reference; rows are written sorted.  names_out receives the '\n'-joined file names. */
+int bch_write_counts(bch_run *run, bc_ctx *ctx, const char *output_dir, const char *prefix, int merge_output, int enrich,
+                     char *names_out, int names_len, char *err, int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BC_HOST_H */

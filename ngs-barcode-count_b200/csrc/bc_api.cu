@@ -1,0 +1,1029 @@
+// bc_api.cu — the C ABI of include/bc_b200.h: context, device tables, staging, finish/enrichment.
+// No CPU fallback lives here: every compute entry point launches the kernels of bc_kernels.cu or fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bc_b200.h"
+#include "bc_kernels.h"
+
+using namespace bc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Staging {
+    uint32_t* planes = nullptr;
+    uint16_t* read_len = nullptr;
+    uint8_t* qual = nullptr;
+    uint64_t cap_reads = 0;
+    cudaEvent_t free_ev = nullptr;    // recorded on the main stream after the last kernel that read the buffer
+    cudaEvent_t copied_ev = nullptr;  // recorded on the copy stream after the H2D copies
+};
+
+struct KeyField {
+    int slot;        // index into cfg.slots
+    uint32_t shift;  // first bit in the full key (UMI field at bit 0)
+    uint32_t bits;
+    bool raw;
+};
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    int kind;
+};
+
+}  // namespace
+
+struct bc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = true;
+    DevCfg cfg{};
+    std::vector<KeyField> fields;      // per slot, scheme order
+    std::vector<int> counted_slots;    // slot indices of counted barcodes in order
+    int sample_slot = -1, umi_slot = -1;
+    uint32_t max_read_len = 0, W = 0, plane_stride = 0, qual_stride = 0;
+    bool quality_on = false;
+    // reference accelerators
+    uint4* d_refs = nullptr;
+    uint16_t* d_tables = nullptr;
+    unsigned long long* d_hash_keys = nullptr;
+    uint32_t* d_hash_idx = nullptr;
+    DevAux aux{};
+    // main table
+    DevTable table{};
+    unsigned long long table_capacity = 0;
+    unsigned long long entries_upper = 0;  // host-side upper bound of occupied entries
+    unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 1 (last = table entries)
+    // staging for host batches
+    Staging staging[2];
+    int cur = 0;
+    bool copies_pending = false;
+    // scratch for the test hooks
+    // cached final rows (device) for enrich / export
+    unsigned long long *d_row_lo = nullptr, *d_row_hi = nullptr, *d_row_cnt = nullptr, *d_row_n = nullptr;
+    unsigned long long n_rows = 0;
+    bool rows_valid = false;
+    // profiling
+    bool profiling = false;
+    std::vector<ProfEvent> prof_events;
+    bc_profile prof{};
+    std::string err;
+};
+
+namespace {
+
+int fail(bc_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(ctx, BC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                            \
+    } while (0)
+
+unsigned long long pow2_at_least(unsigned long long v) {
+    unsigned long long p = 1024;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+uint32_t bits_for(uint32_t n) {  // bits to hold indices 0..n-1, at least 1
+    uint32_t b = 1;
+    while ((1ull << b) < n) b++;
+    return b;
+}
+
+void free_table(DevTable& t) {
+    if (t.keys64) cudaFree(t.keys64);
+    if (t.keys128) cudaFree(t.keys128);
+    if (t.counts) cudaFree(t.counts);
+    t.keys64 = nullptr;
+    t.keys128 = nullptr;
+    t.counts = nullptr;
+}
+
+// kind: 0 dense (capacity = number of counters), 1 hash+counts, 2 hash set
+int alloc_table(bc_ctx* ctx, DevTable& t, int kind, int wide, unsigned long long capacity, unsigned long long* n_entries) {
+    t = DevTable{};
+    t.kind = kind;
+    t.wide = wide;
+    t.n_entries = n_entries;
+    if (kind == 0) {
+        t.cap_mask = capacity;
+        CK(ctx, cudaMalloc(&t.counts, capacity * sizeof(unsigned long long)));
+        CK(ctx, cudaMemsetAsync(t.counts, 0, capacity * sizeof(unsigned long long), ctx->stream));
+        return BC_OK;
+    }
+    t.cap_mask = capacity - 1;
+    if (wide) {
+        CK(ctx, cudaMalloc(&t.keys128, capacity * sizeof(ulonglong2)));
+        CK(ctx, cudaMemsetAsync(t.keys128, 0xFF, capacity * sizeof(ulonglong2), ctx->stream));
+    } else {
+        CK(ctx, cudaMalloc(&t.keys64, capacity * sizeof(unsigned long long)));
+        CK(ctx, cudaMemsetAsync(t.keys64, 0xFF, capacity * sizeof(unsigned long long), ctx->stream));
+    }
+    if (kind == 1) {
+        CK(ctx, cudaMalloc(&t.counts, capacity * sizeof(unsigned long long)));
+        CK(ctx, cudaMemsetAsync(t.counts, 0, capacity * sizeof(unsigned long long), ctx->stream));
+    }
+    return BC_OK;
+}
+
+struct ProfScope {  // CUDA events around one launch, only while profiling is on
+    bc_ctx* ctx;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(bc_ctx* c, int k) : ctx(c), kind(k) {
+        ctx->prof.launches[kind]++;
+        if (ctx->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->prof_events.push_back({a, b, kind});
+        }
+    }
+};
+
+void drain_profile(bc_ctx* ctx) {
+    for (ProfEvent& p : ctx->prof_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->prof.ms[p.kind] += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->prof_events.clear();
+}
+
+void drop_rows(bc_ctx* ctx) {
+    if (ctx->d_row_lo) cudaFree(ctx->d_row_lo);
+    if (ctx->d_row_hi) cudaFree(ctx->d_row_hi);
+    if (ctx->d_row_cnt) cudaFree(ctx->d_row_cnt);
+    ctx->d_row_lo = ctx->d_row_hi = ctx->d_row_cnt = nullptr;
+    ctx->n_rows = 0;
+    ctx->rows_valid = false;
+}
+
+// Smallest integer sum S with fl32(fl32(S) / fl32(len)) >= min_quality: the reference's f32 mean test
+// (parse.rs:352-355) as an exact integer threshold (Q12).  255*len+1 when no sum passes.
+uint32_t quality_threshold(uint32_t len, float min_quality) {
+    const uint32_t top = 255u * len;
+    for (uint32_t s = 0; s <= top; s++) {
+        volatile float avg = static_cast<float>(s) / static_cast<float>(len);
+        if (!(avg < min_quality)) return s;
+    }
+    return top + 1;
+}
+
+int validate_batch(bc_ctx* ctx, const bc_batch* b) {
+    if (!b) return fail(ctx, BC_EINVAL, "batch is NULL");
+    if (b->n_reads == 0) return BC_OK;
+    if (!b->planes || !b->read_len) return fail(ctx, BC_EINVAL, "batch.planes / batch.read_len is NULL");
+    if (b->plane_stride != ctx->plane_stride)
+        return fail(ctx, BC_EINVAL, "batch.plane_stride %u != %u (bc_plane_stride(max_read_len))", b->plane_stride, ctx->plane_stride);
+    if (ctx->quality_on) {
+        if (!b->qual) return fail(ctx, BC_EINVAL, "min_quality > 0 but batch.qual is NULL");
+        if (b->qual_stride != ctx->qual_stride)
+            return fail(ctx, BC_EINVAL, "batch.qual_stride %u != %u (bc_qual_stride(max_read_len))", b->qual_stride, ctx->qual_stride);
+    }
+    if (b->location != BC_LOC_HOST && b->location != BC_LOC_DEVICE) return fail(ctx, BC_EINVAL, "batch.location");
+    return BC_OK;
+}
+
+// Make the batch visible to the kernels: device batches are used in place, host batches go through the
+// double-buffered staging on the copy stream (H2D of batch i+1 overlaps the kernels of batch i).
+int stage_batch(bc_ctx* ctx, const bc_batch* b, BatchView* view) {
+    view->n_reads = b->n_reads;
+    view->plane_stride = ctx->plane_stride;
+    view->qual_stride = ctx->qual_stride;
+    view->W = ctx->W;
+    const bool want_qual = ctx->quality_on;
+    if (b->location == BC_LOC_DEVICE) {
+        view->planes = b->planes;
+        view->read_len = b->read_len;
+        view->qual = want_qual ? b->qual : nullptr;
+        return BC_OK;
+    }
+    Staging& s = ctx->staging[ctx->cur];
+    ctx->cur ^= 1;
+    if (!s.free_ev) {
+        CK(ctx, cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&s.copied_ev, cudaEventDisableTiming));
+    }
+    if (s.cap_reads < b->n_reads) {
+        CK(ctx, cudaEventSynchronize(s.free_ev));
+        if (s.planes) cudaFree(s.planes);
+        if (s.read_len) cudaFree(s.read_len);
+        if (s.qual) cudaFree(s.qual);
+        s.planes = nullptr; s.read_len = nullptr; s.qual = nullptr;
+        // round the tile count up so tile-granular staging never reads past the allocation
+        const uint64_t cap = ((uint64_t)b->n_reads + kTile - 1) / kTile * kTile;
+        CK(ctx, cudaMalloc(&s.planes, cap * ctx->plane_stride * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&s.read_len, cap * sizeof(uint16_t)));
+        if (want_qual) CK(ctx, cudaMalloc(&s.qual, cap * ctx->qual_stride));
+        s.cap_reads = cap;
+    }
+    CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, s.free_ev, 0));
+    const size_t pb = (size_t)b->n_reads * ctx->plane_stride * sizeof(uint32_t);
+    const size_t lb = (size_t)b->n_reads * sizeof(uint16_t);
+    const size_t qb = want_qual ? (size_t)b->n_reads * ctx->qual_stride : 0;
+    CK(ctx, cudaMemcpyAsync(s.planes, b->planes, pb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(ctx, cudaMemcpyAsync(s.read_len, b->read_len, lb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (want_qual) CK(ctx, cudaMemcpyAsync(s.qual, b->qual, qb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(ctx, cudaEventRecord(s.copied_ev, ctx->copy_stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, s.copied_ev, 0));
+    ctx->prof.h2d_bytes += pb + lb + qb;
+    ctx->copies_pending = true;
+    view->planes = s.planes;
+    view->read_len = s.read_len;
+    view->qual = s.qual;
+    // the caller records s.free_ev after its kernels
+    return 1;  // staged
+}
+
+int release_staging(bc_ctx* ctx, int staged) {
+    if (staged == 1) {
+        Staging& s = ctx->staging[ctx->cur ^ 1];
+        CK(ctx, cudaEventRecord(s.free_ev, ctx->stream));
+    }
+    return BC_OK;
+}
+
+// keep the load factor of the hash kinds <= 0.5 (entries are bounded by reads submitted)
+int ensure_capacity(bc_ctx* ctx, unsigned long long incoming) {
+    if (ctx->table.kind == 0) return BC_OK;
+    ctx->entries_upper += incoming;
+    if (2 * ctx->entries_upper <= ctx->table_capacity) return BC_OK;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long n = 0;
+    CK(ctx, cudaMemcpy(&n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
+    ctx->entries_upper = n + incoming;
+    unsigned long long cap = ctx->table_capacity;
+    while (2 * ctx->entries_upper > cap) cap <<= 1;
+    if (cap == ctx->table_capacity) return BC_OK;
+    DevTable bigger;
+    int rc = alloc_table(ctx, bigger, ctx->table.kind, ctx->table.wide, cap, ctx->table.n_entries);
+    if (rc != BC_OK) return rc;
+    {
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_rehash(ctx->table, bigger, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    free_table(ctx->table);
+    ctx->table = bigger;
+    ctx->table_capacity = cap;
+    return BC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t bc_plane_words(uint32_t max_read_len) { return (max_read_len + 31) / 32; }
+uint32_t bc_plane_stride(uint32_t max_read_len) { return (3 * bc_plane_words(max_read_len)) | 1u; }
+uint32_t bc_qual_stride(uint32_t max_read_len) { return (((max_read_len + 3) / 4) | 1u) * 4; }
+
+const char* bc_last_error(const bc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void bc_destroy(bc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    drain_profile(ctx);
+    drop_rows(ctx);
+    if (ctx->d_row_n) cudaFree(ctx->d_row_n);
+    free_table(ctx->table);
+    for (Staging& s : ctx->staging) {
+        if (s.planes) cudaFree(s.planes);
+        if (s.read_len) cudaFree(s.read_len);
+        if (s.qual) cudaFree(s.qual);
+        if (s.free_ev) cudaEventDestroy(s.free_ev);
+        if (s.copied_ev) cudaEventDestroy(s.copied_ev);
+    }
+    if (ctx->d_refs) cudaFree(ctx->d_refs);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_hash_keys) cudaFree(ctx->d_hash_keys);
+    if (ctx->d_hash_idx) cudaFree(ctx->d_hash_idx);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, BC_EINVAL, "cfg / out is NULL");
+    *out = nullptr;
+    if (cfg->abi_version != BC_ABI_VERSION) return fail(nullptr, BC_EINVAL, "abi_version %u != %u", cfg->abi_version, BC_ABI_VERSION);
+    const uint32_t L = cfg->template_len;
+    if (L == 0 || L > BC_MAX_TEMPLATE) return fail(nullptr, BC_EUNSUPPORTED, "template length %u outside 1..%d", L, BC_MAX_TEMPLATE);
+    if (cfg->max_read_len < L || cfg->max_read_len > BC_MAX_READ_LEN)
+        return fail(nullptr, BC_EUNSUPPORTED, "max_read_len %u outside %u..%d", cfg->max_read_len, L, BC_MAX_READ_LEN);
+    if (cfg->n_slots > BC_MAX_SLOTS) return fail(nullptr, BC_EUNSUPPORTED, "more than %d barcodes", BC_MAX_SLOTS);
+    if (cfg->region_len > L) return fail(nullptr, BC_EINVAL, "region_codes longer than the template");
+    if (!cfg->template_chars || (cfg->region_len && !cfg->region_codes)) return fail(nullptr, BC_EINVAL, "template / region pointers");
+
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0)
+        return fail(nullptr, BC_ECUDA, "no usable CUDA device (%s); this library has no CPU path", cudaGetErrorString(ce));
+    if (device < 0 || device >= n_dev) return fail(nullptr, BC_EINVAL, "device %d of %d", device, n_dev);
+
+    bc_ctx* ctx = new bc_ctx();
+    ctx->device = device;
+#define CKC(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess) {                                                                               \
+            int rc_ = fail(nullptr, BC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            bc_destroy(ctx);                                                                                   \
+            return rc_;                                                                                        \
+        }                                                                                                      \
+    } while (0)
+#define FAILC(code, ...)                              \
+    do {                                              \
+        int rc_ = fail(nullptr, code, __VA_ARGS__);   \
+        bc_destroy(ctx);                              \
+        return rc_;                                   \
+    } while (0)
+
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+
+    DevCfg& d = ctx->cfg;
+    d.L = L;
+    d.TW = (L + 31) / 32;
+    d.n_slots = cfg->n_slots;
+    d.max_const_err = cfg->max_const_err;
+    ctx->max_read_len = cfg->max_read_len;
+    ctx->W = bc_plane_words(cfg->max_read_len);
+    ctx->plane_stride = bc_plane_stride(cfg->max_read_len);
+    ctx->qual_stride = bc_qual_stride(cfg->max_read_len);
+    ctx->quality_on = cfg->min_quality > 0.0f;
+
+    // ---- template planes (info.rs:283-299): barcode positions are free, 'N' outside barcodes is format-N
+    std::vector<int> owner(L, -1);
+    for (uint32_t s = 0; s < cfg->n_slots; s++) {
+        const bc_slot& S = cfg->slots[s];
+        if (S.kind != 'S' && S.kind != 'B' && S.kind != 'R') FAILC(BC_EINVAL, "slot %u: kind must be 'S', 'B' or 'R'", s);
+        if (S.len == 0 || (uint32_t)S.offset + S.len > L) FAILC(BC_EINVAL, "slot %u lies outside the template", s);
+        if (S.len > BC_MAX_REF_LEN) FAILC(BC_EUNSUPPORTED, "slot %u: barcodes longer than %d bases", s, BC_MAX_REF_LEN);
+        for (uint32_t p = S.offset; p < (uint32_t)S.offset + S.len; p++) {
+            if (owner[p] >= 0) FAILC(BC_EINVAL, "slots %d and %u overlap", owner[p], s);
+            owner[p] = (int)s;
+        }
+        if (S.kind == 'S') {
+            if (ctx->sample_slot >= 0) FAILC(BC_EINVAL, "two sample barcodes (the reference rejects this too, info.rs:308)");
+            ctx->sample_slot = (int)s;
+        } else if (S.kind == 'R') {
+            if (ctx->umi_slot >= 0) FAILC(BC_EINVAL, "two random barcodes (the reference rejects this too, info.rs:308)");
+            if (S.n_ref) FAILC(BC_EINVAL, "the random barcode cannot have a reference set");
+            ctx->umi_slot = (int)s;
+        } else {
+            ctx->counted_slots.push_back((int)s);
+        }
+    }
+    for (uint32_t p = 0; p < L; p++) {
+        const char ch = cfg->template_chars[p];
+        const uint32_t w = p >> 5, bit = 1u << (p & 31);
+        if (owner[p] >= 0) continue;
+        switch (ch) {
+            case 'A': d.t_cm[w] |= bit; break;
+            case 'C': d.t_cm[w] |= bit; d.t_lo[w] |= bit; break;
+            case 'G': d.t_cm[w] |= bit; d.t_hi[w] |= bit; break;
+            case 'T': d.t_cm[w] |= bit; d.t_lo[w] |= bit; d.t_hi[w] |= bit; break;
+            case 'N': d.t_fn[w] |= bit; d.has_fn = 1; break;
+            default:
+                FAILC(BC_EUNSUPPORTED, "template position %u holds '%c': only upper-case A/C/G/T/N constants are supported "
+                      "(lower case never matches in the reference's repair step, Q11)", p, ch);
+        }
+    }
+
+    // ---- quality runs (parse.rs:340-374): maximal runs of one region code; a non-constant run is tested only when
+    // another code follows it inside the walked range (Q8); format-N shortens the code string (Q9)
+    if (ctx->quality_on) {
+        uint32_t i = 0;
+        while (i < cfg->region_len) {
+            uint32_t j = i;
+            while (j < cfg->region_len && cfg->region_codes[j] == cfg->region_codes[i]) j++;
+            if (cfg->region_codes[i] != 'C' && j < cfg->region_len) {
+                if (d.n_qruns == kMaxQRuns) FAILC(BC_EUNSUPPORTED, "more than %d quality-tested runs", kMaxQRuns);
+                d.qruns[d.n_qruns++] = DevQRun{(uint16_t)i, (uint16_t)(j - i), quality_threshold(j - i, cfg->min_quality)};
+            }
+            i = j;
+        }
+    }
+
+    // ---- processing order (parse.rs:451, 483, 512) and key layout: [UMI | counted 1..k | sample]
+    {
+        uint32_t n = 0;
+        if (ctx->sample_slot >= 0) d.order[n++] = (uint8_t)ctx->sample_slot;
+        for (int s : ctx->counted_slots) d.order[n++] = (uint8_t)s;
+        if (ctx->umi_slot >= 0) d.order[n++] = (uint8_t)ctx->umi_slot;
+    }
+    ctx->fields.resize(cfg->n_slots);
+    uint32_t shift = 0;
+    auto add_field = [&](int s) {
+        const bc_slot& S = cfg->slots[s];
+        const bool raw = S.n_ref == 0;
+        const uint32_t bits = raw ? 3u * S.len : bits_for(S.n_ref);
+        ctx->fields[s] = KeyField{s, shift, bits, raw};
+        d.slots[s].key_shift = (uint16_t)shift;
+        d.slots[s].key_bits = (uint16_t)bits;
+        shift += bits;
+    };
+    if (ctx->umi_slot >= 0) {
+        add_field(ctx->umi_slot);
+        d.has_umi = 1;
+        d.umi_bits = shift;
+    }
+    for (int s : ctx->counted_slots) add_field(s);
+    if (ctx->sample_slot >= 0) add_field(ctx->sample_slot);
+    if (shift > BC_MAX_KEY_BITS)
+        FAILC(BC_EUNSUPPORTED, "packed key needs %u bits (> %d): too many / too long raw barcodes", shift, BC_MAX_KEY_BITS);
+    d.key_bits = shift;
+    d.wide = shift > 63;
+
+    // ---- reference sets -> {lo,hi,nm,len} words, direct tables, exact-match hashes
+    std::vector<uint4> refs;
+    std::vector<unsigned long long> hkeys;
+    std::vector<uint32_t> hidx;
+    size_t table_u16 = 0;
+    for (uint32_t s = 0; s < cfg->n_slots; s++) {
+        const bc_slot& S = cfg->slots[s];
+        DevSlot& D = d.slots[s];
+        D.offset = S.offset;
+        D.len = S.len;
+        D.max_err = S.max_err;
+        D.kind = S.kind;
+        D.n_ref = S.n_ref;
+        D.mode = MODE_RAW;
+        if (S.n_ref == 0) continue;
+        if (!S.ref_seqs) FAILC(BC_EINVAL, "slot %u: ref_seqs is NULL", s);
+        D.ref_off = (uint32_t)refs.size();
+        bool any_exactable = false;
+        for (uint32_t i = 0; i < S.n_ref; i++) {
+            const char* r = S.ref_seqs[i];
+            const size_t rl = r ? strlen(r) : 0;
+            if (rl > BC_MAX_REF_LEN) FAILC(BC_EUNSUPPORTED, "slot %u: reference barcode %u longer than %d bases", s, i, BC_MAX_REF_LEN);
+            uint4 v = make_uint4(0, 0, 0, (uint32_t)rl);
+            for (size_t p = 0; p < rl; p++) {
+                const uint32_t bit = 1u << p;
+                switch (r[p]) {
+                    case 'A': break;
+                    case 'C': v.x |= bit; break;
+                    case 'G': v.y |= bit; break;
+                    case 'T': v.x |= bit; v.y |= bit; break;
+                    case 'N': v.z |= bit; break;
+                    default: FAILC(BC_EUNSUPPORTED, "slot %u: reference barcode '%s' holds a character outside ACGTN", s, r);
+                }
+            }
+            if (rl == S.len && v.z == 0) any_exactable = true;
+            refs.push_back(v);
+        }
+        if (S.len <= 10 && S.n_ref < 0xFFFFu) {
+            D.mode = MODE_TABLE;
+            D.aux_off = (uint32_t)table_u16;
+            table_u16 += (size_t)1 << (2 * S.len);
+        } else if (any_exactable) {
+            D.mode = MODE_HASH;
+            const unsigned long long cap = pow2_at_least(2ull * S.n_ref);
+            D.aux_off = (uint32_t)hkeys.size();
+            D.aux_mask = (uint32_t)(cap - 1);
+            hkeys.resize(hkeys.size() + cap, 0ull);
+            hidx.resize(hidx.size() + cap, kFail);
+            for (uint32_t i = 0; i < S.n_ref; i++) {
+                const uint4 v = refs[D.ref_off + i];
+                if (v.w != S.len || v.z != 0) continue;
+                const unsigned long long k = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+                unsigned long long h = mix64(k) & D.aux_mask;
+                while (hidx[D.aux_off + h] != kFail && hkeys[D.aux_off + h] != k) h = (h + 1) & D.aux_mask;
+                hkeys[D.aux_off + h] = k;
+                hidx[D.aux_off + h] = i;  // identical strings cannot repeat in a set; the last one wins like a map insert
+            }
+        } else {
+            D.mode = MODE_SCAN;
+        }
+    }
+    if (!refs.empty()) {
+        CKC(cudaMalloc(&ctx->d_refs, refs.size() * sizeof(uint4)));
+        CKC(cudaMemcpyAsync(ctx->d_refs, refs.data(), refs.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!hkeys.empty()) {
+        CKC(cudaMalloc(&ctx->d_hash_keys, hkeys.size() * sizeof(unsigned long long)));
+        CKC(cudaMalloc(&ctx->d_hash_idx, hidx.size() * sizeof(uint32_t)));
+        CKC(cudaMemcpyAsync(ctx->d_hash_keys, hkeys.data(), hkeys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaMemcpyAsync(ctx->d_hash_idx, hidx.data(), hidx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (table_u16) CKC(cudaMalloc(&ctx->d_tables, table_u16 * sizeof(uint16_t)));
+    ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx};
+    for (uint32_t s = 0; s < cfg->n_slots; s++) {
+        if (d.slots[s].mode != MODE_TABLE) continue;
+        ctx->prof.launches[BC_K_OTHER]++;
+        CKC(launch_build_table(d.slots[s], ctx->aux, ctx->d_tables + d.slots[s].aux_off, ctx->stream));
+    }
+    CKC(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+
+    // ---- counters and the main table
+    CKC(cudaMalloc(&ctx->d_counters, (BC_N_COUNTERS + 1) * sizeof(unsigned long long)));
+    CKC(cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
+    CKC(cudaMalloc(&ctx->d_row_n, sizeof(unsigned long long)));
+    const unsigned long long hint = expected_reads ? expected_reads : (1ull << 20);
+    int rc;
+    if (!d.has_umi && d.key_bits <= 27) {
+        ctx->table_capacity = 1ull << d.key_bits;
+        rc = alloc_table(ctx, ctx->table, 0, 0, ctx->table_capacity, ctx->d_counters + BC_N_COUNTERS);
+    } else {
+        ctx->table_capacity = pow2_at_least(2 * hint);
+        rc = alloc_table(ctx, ctx->table, d.has_umi ? 2 : 1, d.wide, ctx->table_capacity, ctx->d_counters + BC_N_COUNTERS);
+    }
+    if (rc != BC_OK) {
+        g_create_error = ctx->err;
+        bc_destroy(ctx);
+        return rc;
+    }
+    CKC(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return BC_OK;
+#undef CKC
+#undef FAILC
+}
+
+int bc_set_stream(bc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return BC_OK;
+}
+
+static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const DecodeOut& out, const RouteOut& route,
+                      unsigned long long* counters) {
+    int rc = validate_batch(ctx, batch);
+    if (rc != BC_OK) return rc;
+    if (batch->n_reads == 0) return BC_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (flags & F_INSERT) {
+        rc = ensure_capacity(ctx, batch->n_reads);
+        if (rc != BC_OK) return rc;
+        ctx->rows_valid = false;
+    }
+    BatchView view{};
+    const int staged = stage_batch(ctx, batch, &view);
+    if (staged < 0) return staged;
+    {
+        ProfScope p(ctx, BC_K_DECODE);
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, flags, ctx->stream));
+    }
+    return release_staging(ctx, staged);
+}
+
+int bc_submit(bc_ctx* ctx, const bc_batch* batch) {
+    if (!ctx) return BC_EINVAL;
+    return run_decode(ctx, batch, F_INSERT, DecodeOut{}, RouteOut{}, ctx->d_counters);
+}
+
+int bc_sync(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->copies_pending = false;
+    return BC_OK;
+}
+
+int bc_wait_copies(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copies_pending = false;
+    return BC_OK;
+}
+
+int bc_get_counters(bc_ctx* ctx, uint64_t out[BC_N_COUNTERS]) {
+    if (!ctx || !out) return BC_EINVAL;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    unsigned long long h[BC_N_COUNTERS];
+    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    ctx->prof.d2h_bytes += sizeof h;
+    for (int i = 0; i < BC_N_COUNTERS; i++) out[i] = h[i];
+    return BC_OK;
+}
+
+static int decode_hook(bc_ctx* ctx, const bc_batch* batch, int flags, uint8_t* status, int16_t* offset, uint8_t* repaired,
+                       int32_t* slot_index, uint64_t* key_lo, uint64_t* key_hi) {
+    if (!ctx || !batch) return BC_EINVAL;
+    const size_t n = batch->n_reads;
+    if (n == 0) return BC_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    DecodeOut d{};
+    const size_t ns = n * ctx->cfg.n_slots;
+    auto cleanup = [&]() {
+        if (d.status) cudaFree(d.status);
+        if (d.offset) cudaFree(d.offset);
+        if (d.repaired) cudaFree(d.repaired);
+        if (d.slot_index) cudaFree(d.slot_index);
+        if (d.key_lo) cudaFree(d.key_lo);
+        if (d.key_hi) cudaFree(d.key_hi);
+    };
+#define CKH(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            cleanup();                                                                                             \
+            return fail(ctx, BC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);       \
+        }                                                                                                          \
+    } while (0)
+    if (status) CKH(cudaMalloc(&d.status, n));
+    if (offset) CKH(cudaMalloc(&d.offset, n * sizeof(int16_t)));
+    if (repaired) CKH(cudaMalloc(&d.repaired, n));
+    if (slot_index && ns) {
+        CKH(cudaMalloc(&d.slot_index, ns * sizeof(int32_t)));
+        CKH(cudaMemsetAsync(d.slot_index, 0xFF, ns * sizeof(int32_t), ctx->stream));
+    }
+    if (key_lo) CKH(cudaMalloc(&d.key_lo, n * sizeof(unsigned long long)));
+    if (key_hi) CKH(cudaMalloc(&d.key_hi, n * sizeof(unsigned long long)));
+    int rc = run_decode(ctx, batch, flags | F_EMIT, d, RouteOut{}, nullptr);
+    if (rc != BC_OK) {
+        cleanup();
+        return rc;
+    }
+    CKH(cudaStreamSynchronize(ctx->stream));
+    if (status) CKH(cudaMemcpy(status, d.status, n, cudaMemcpyDeviceToHost));
+    if (offset) CKH(cudaMemcpy(offset, d.offset, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    if (repaired) CKH(cudaMemcpy(repaired, d.repaired, n, cudaMemcpyDeviceToHost));
+    if (slot_index && ns) CKH(cudaMemcpy(slot_index, d.slot_index, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (key_lo) CKH(cudaMemcpy(key_lo, d.key_lo, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (key_hi) CKH(cudaMemcpy(key_hi, d.key_hi, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+#undef CKH
+    cleanup();
+    return BC_OK;
+}
+
+int bc_locate_only(bc_ctx* ctx, const bc_batch* batch, bc_locate_out* out) {
+    if (!out) return BC_EINVAL;
+    return decode_hook(ctx, batch, F_LOCATE_ONLY, out->status, out->offset, out->repaired, nullptr, nullptr, nullptr);
+}
+
+int bc_decode_only(bc_ctx* ctx, const bc_batch* batch, bc_decode_out* out) {
+    if (!out) return BC_EINVAL;
+    return decode_hook(ctx, batch, 0, out->status, out->offset, out->repaired, out->slot_index, out->key_lo, out->key_hi);
+}
+
+// ---------------------------------------------------------------------------------------------- finish / enrich
+
+void bc_table_free(bc_table* t) {
+    if (!t) return;
+    free(t->key_lo);
+    free(t->key_hi);
+    free(t->count);
+    free(t->mask);
+    memset(t, 0, sizeof *t);
+}
+
+static int rows_to_host(bc_ctx* ctx, const unsigned long long* lo, const unsigned long long* hi, const unsigned long long* cnt,
+                        unsigned long long n, uint32_t mask, bool with_mask, bc_table* t) {
+    const uint64_t old = t->n_rows;
+    const uint64_t tot = old + n;
+    if (tot == 0) return BC_OK;
+    t->key_lo = (uint64_t*)realloc(t->key_lo, tot * sizeof(uint64_t));
+    t->key_hi = (uint64_t*)realloc(t->key_hi, tot * sizeof(uint64_t));
+    t->count = (uint64_t*)realloc(t->count, tot * sizeof(uint64_t));
+    if (with_mask) t->mask = (uint32_t*)realloc(t->mask, tot * sizeof(uint32_t));
+    if (!t->key_lo || !t->key_hi || !t->count || (with_mask && !t->mask)) return fail(ctx, BC_ENOMEM, "host rows");
+    if (n) {
+        CK(ctx, cudaMemcpy(t->key_lo + old, lo, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CK(ctx, cudaMemcpy(t->key_hi + old, hi, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CK(ctx, cudaMemcpy(t->count + old, cnt, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        ctx->prof.d2h_bytes += 3 * n * sizeof(uint64_t);
+    }
+    if (with_mask)
+        for (uint64_t i = old; i < tot; i++) t->mask[i] = mask;
+    t->n_rows = tot;
+    return BC_OK;
+}
+
+// table -> compact device rows
+static int compact_rows(bc_ctx* ctx, const DevTable& t, unsigned long long upper, unsigned long long** lo,
+                        unsigned long long** hi, unsigned long long** cnt, unsigned long long* n) {
+    *lo = *hi = *cnt = nullptr;
+    const unsigned long long cap = upper ? upper : 1;
+    CK(ctx, cudaMalloc(lo, cap * sizeof(unsigned long long)));
+    CK(ctx, cudaMalloc(hi, cap * sizeof(unsigned long long)));
+    CK(ctx, cudaMalloc(cnt, cap * sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_FINISH);
+        CK(ctx, launch_compact(t, *lo, *hi, *cnt, ctx->d_row_n, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(n, ctx->d_row_n, sizeof *n, cudaMemcpyDeviceToHost));
+    return BC_OK;
+}
+
+static int build_rows(bc_ctx* ctx) {
+    if (ctx->rows_valid) return BC_OK;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    drop_rows(ctx);
+    unsigned long long h[BC_N_COUNTERS + 1];
+    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    const unsigned long long entries = h[BC_N_COUNTERS];
+    if (ctx->table.kind == 0) {
+        // at most one row per counted read, at most one per counter
+        unsigned long long upper = h[BC_CNT_MATCHED] < ctx->table_capacity ? h[BC_CNT_MATCHED] : ctx->table_capacity;
+        rc = compact_rows(ctx, ctx->table, upper, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
+    } else if (ctx->table.kind == 1) {
+        rc = compact_rows(ctx, ctx->table, entries, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
+    } else {
+        // UMI set -> number of distinct random barcodes per key (output.rs:265-270)
+        unsigned long long* d_n = nullptr;
+        CK(ctx, cudaMalloc(&d_n, sizeof(unsigned long long)));
+        CK(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
+        DevTable grouped;
+        const int wide = (ctx->cfg.key_bits - ctx->cfg.umi_bits) > 63;
+        rc = alloc_table(ctx, grouped, 1, wide, pow2_at_least(2 * (entries ? entries : 1)), d_n);
+        if (rc == BC_OK) {
+            {
+                ProfScope p(ctx, BC_K_FINISH);
+                cudaError_t e = launch_group(ctx->table, ctx->cfg.umi_bits, grouped, ctx->stream);
+                if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_group: %s", cudaGetErrorString(e));
+            }
+            unsigned long long keys = 0;
+            if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "group sync");
+            if (rc == BC_OK && cudaMemcpy(&keys, d_n, sizeof keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "group count");
+            if (rc == BC_OK) rc = compact_rows(ctx, grouped, keys, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
+        }
+        free_table(grouped);
+        cudaFree(d_n);
+    }
+    if (rc != BC_OK) return rc;
+    ctx->rows_valid = true;
+    return BC_OK;
+}
+
+int bc_finish(bc_ctx* ctx, bc_table* rows) {
+    if (!ctx || !rows) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    memset(rows, 0, sizeof *rows);
+    int rc = build_rows(ctx);
+    if (rc != BC_OK) return rc;
+    return rows_to_host(ctx, ctx->d_row_lo, ctx->d_row_hi, ctx->d_row_cnt, ctx->n_rows, 0, false, rows);
+}
+
+// key mask keeping the sample field and the counted barcodes listed in `keep` (bit k = k-th counted barcode)
+static void marginal_mask(const bc_ctx* ctx, uint32_t keep, Key* mask, uint32_t* kept_bits) {
+    Key m{0, 0};
+    uint32_t bits = 0;
+    auto add = [&](const KeyField& f) {
+        const uint32_t sh = f.shift - ctx->cfg.umi_bits;
+        for (uint32_t b = sh; b < sh + f.bits; b++) {
+            if (b < 64) m.lo |= 1ull << b;
+            else m.hi |= 1ull << (b - 64);
+        }
+        bits += f.bits;
+    };
+    for (size_t k = 0; k < ctx->counted_slots.size(); k++)
+        if (keep & (1u << k)) add(ctx->fields[ctx->counted_slots[k]]);
+    if (ctx->sample_slot >= 0) add(ctx->fields[ctx->sample_slot]);
+    *mask = m;
+    *kept_bits = bits;
+}
+
+static int one_marginal(bc_ctx* ctx, uint32_t keep, bc_table* out) {
+    Key mask;
+    uint32_t kept_bits;
+    marginal_mask(ctx, keep, &mask, &kept_bits);
+    unsigned long long cap = pow2_at_least(2 * (ctx->n_rows ? ctx->n_rows : 1));
+    if (kept_bits < 40 && (2ull << kept_bits) < cap) cap = pow2_at_least(2ull << kept_bits);
+    unsigned long long* d_n = nullptr;
+    CK(ctx, cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
+    DevTable t;
+    const int wide = (ctx->cfg.key_bits - ctx->cfg.umi_bits) > 63;
+    int rc = alloc_table(ctx, t, 1, wide, cap, d_n);
+    unsigned long long *lo = nullptr, *hi = nullptr, *cnt = nullptr, n = 0;
+    if (rc == BC_OK) {
+        {
+            ProfScope p(ctx, BC_K_FINISH);
+            cudaError_t e = launch_marginal(ctx->d_row_lo, ctx->d_row_hi, ctx->d_row_cnt, ctx->n_rows, mask, t, ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_marginal: %s", cudaGetErrorString(e));
+        }
+        unsigned long long keys = 0;
+        if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "marginal sync");
+        if (rc == BC_OK && cudaMemcpy(&keys, d_n, sizeof keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "marginal count");
+        if (rc == BC_OK) rc = compact_rows(ctx, t, keys, &lo, &hi, &cnt, &n);
+        if (rc == BC_OK) rc = rows_to_host(ctx, lo, hi, cnt, n, keep, true, out);
+    }
+    if (lo) cudaFree(lo);
+    if (hi) cudaFree(hi);
+    if (cnt) cudaFree(cnt);
+    free_table(t);
+    cudaFree(d_n);
+    return rc;
+}
+
+int bc_enrich(bc_ctx* ctx, bc_table* singles, bc_table* doubles) {
+    if (!ctx || !singles) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    memset(singles, 0, sizeof *singles);
+    if (doubles) memset(doubles, 0, sizeof *doubles);
+    int rc = build_rows(ctx);
+    if (rc != BC_OK) return rc;
+    const uint32_t k = (uint32_t)ctx->counted_slots.size();
+    for (uint32_t a = 0; a < k; a++) {  // info.rs:840-866
+        rc = one_marginal(ctx, 1u << a, singles);
+        if (rc != BC_OK) return rc;
+    }
+    if (doubles) {
+        for (uint32_t a = 0; a + 1 < k; a++)  // info.rs:869-904
+            for (uint32_t b = a + 1; b < k; b++) {
+                rc = one_marginal(ctx, (1u << a) | (1u << b), doubles);
+                if (rc != BC_OK) return rc;
+            }
+    }
+    return BC_OK;
+}
+
+int bc_key_decode(const bc_ctx* ctx, uint64_t key_lo, uint64_t key_hi, uint32_t mask, int with_umi, int32_t* idx_out,
+                  char* str_out, uint32_t str_stride) {
+    if (!ctx || !idx_out) return BC_EINVAL;
+    auto get_bits = [&](uint32_t shift, uint32_t bits) -> uint64_t {
+        if (bits == 0) return 0;
+        uint64_t v;
+        if (shift >= 64) v = key_hi >> (shift - 64);
+        else v = (key_lo >> shift) | (shift ? (key_hi << (64 - shift)) : 0);
+        return bits >= 64 ? v : (v & ((1ull << bits) - 1));
+    };
+    const uint32_t drop = with_umi ? 0 : ctx->cfg.umi_bits;
+    for (uint32_t s = 0; s < ctx->cfg.n_slots; s++) {
+        idx_out[s] = -1;
+        if (str_out) str_out[(size_t)s * str_stride] = 0;
+        const KeyField& f = ctx->fields[s];
+        const DevSlot& D = ctx->cfg.slots[s];
+        if ((int)s == ctx->umi_slot && !with_umi) continue;
+        if (D.kind == 'B' && mask) {
+            uint32_t k = 0;
+            for (; k < ctx->counted_slots.size(); k++)
+                if (ctx->counted_slots[k] == (int)s) break;
+            if (!(mask & (1u << k))) continue;
+        }
+        const uint32_t sh = f.shift - drop;
+        if (!f.raw) {
+            idx_out[s] = (int32_t)get_bits(sh, f.bits);
+        } else if (str_out) {
+            if (str_stride < (uint32_t)D.len + 1) return BC_EINVAL;
+            const uint32_t lo = (uint32_t)get_bits(sh, D.len), hi = (uint32_t)get_bits(sh + D.len, D.len),
+                           nm = (uint32_t)get_bits(sh + 2 * D.len, D.len);
+            char* o = str_out + (size_t)s * str_stride;
+            for (uint32_t p = 0; p < D.len; p++) {
+                const uint32_t b = 1u << p;
+                o[p] = (nm & b) ? 'N' : "ACGT"[((lo & b) ? 1 : 0) | ((hi & b) ? 2 : 0)];
+            }
+            o[D.len] = 0;
+        }
+    }
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU
+
+int bc_decode_route(bc_ctx* ctx, const bc_batch* batch, uint32_t n_ranks, bc_record* dev_buckets, uint64_t bucket_capacity,
+                    uint32_t* dev_bucket_counts) {
+    if (!ctx || !batch || !dev_buckets || !dev_bucket_counts || n_ranks == 0) return BC_EINVAL;
+    if (bucket_capacity < batch->n_reads)
+        return fail(ctx, BC_EINVAL, "bucket_capacity %llu < n_reads %u: a bucket must be able to hold the whole batch",
+                    (unsigned long long)bucket_capacity, batch->n_reads);
+    RouteOut r{reinterpret_cast<Key*>(dev_buckets), bucket_capacity, dev_bucket_counts, n_ranks};
+    return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+}
+
+int bc_insert_records(bc_ctx* ctx, const bc_record* dev_records, uint64_t n) {
+    if (!ctx || (!dev_records && n)) return BC_EINVAL;
+    if (n == 0) return BC_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_capacity(ctx, n);
+    if (rc != BC_OK) return rc;
+    ctx->rows_valid = false;
+    ProfScope p(ctx, BC_K_INSERT);
+    CK(ctx, launch_insert(ctx->table, nullptr, nullptr, reinterpret_cast<const Key*>(dev_records), nullptr, n, ctx->d_counters, ctx->stream));
+    return BC_OK;
+}
+
+int bc_export_rows(bc_ctx* ctx, uint64_t** dev_key_lo, uint64_t** dev_key_hi, uint64_t** dev_count, uint64_t* n_rows) {
+    if (!ctx || !dev_key_lo || !dev_key_hi || !dev_count || !n_rows) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = build_rows(ctx);
+    if (rc != BC_OK) return rc;
+    *dev_key_lo = reinterpret_cast<uint64_t*>(ctx->d_row_lo);
+    *dev_key_hi = reinterpret_cast<uint64_t*>(ctx->d_row_hi);
+    *dev_count = reinterpret_cast<uint64_t*>(ctx->d_row_cnt);
+    *n_rows = ctx->n_rows;
+    return BC_OK;
+}
+
+// Adds (key, count) rows — keys WITHOUT the random barcode — into this rank's table.  Only meaningful for
+// schemes without a random barcode (with one, de-duplication is routed per record, see bc_decode_route).
+int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_key_hi, const uint64_t* dev_count, uint64_t n_rows) {
+    if (!ctx) return BC_EINVAL;
+    if (ctx->cfg.has_umi) return fail(ctx, BC_ESTATE, "bc_import_rows: scheme has a random barcode; route records instead");
+    if (n_rows == 0) return BC_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_capacity(ctx, n_rows);
+    if (rc != BC_OK) return rc;
+    ctx->rows_valid = false;
+    ProfScope p(ctx, BC_K_INSERT);
+    CK(ctx, launch_insert(ctx->table, reinterpret_cast<const unsigned long long*>(dev_key_lo),
+                          reinterpret_cast<const unsigned long long*>(dev_key_hi), nullptr,
+                          reinterpret_cast<const unsigned long long*>(dev_count), n_rows, nullptr, ctx->stream));
+    return BC_OK;
+}
+
+int bc_add_counters(bc_ctx* ctx, const uint64_t add[BC_N_COUNTERS]) {
+    if (!ctx || !add) return BC_EINVAL;
+    uint64_t cur[BC_N_COUNTERS];
+    int rc = bc_get_counters(ctx, cur);
+    if (rc != BC_OK) return rc;
+    unsigned long long h[BC_N_COUNTERS];
+    for (int i = 0; i < BC_N_COUNTERS; i++) h[i] = cur[i] + add[i];
+    CK(ctx, cudaMemcpy(ctx->d_counters, h, sizeof h, cudaMemcpyHostToDevice));
+    return BC_OK;
+}
+
+int bc_reset(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    drop_rows(ctx);
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
+    const unsigned long long cap = ctx->table_capacity;
+    if (ctx->table.kind == 0) {
+        CK(ctx, cudaMemsetAsync(ctx->table.counts, 0, cap * sizeof(unsigned long long), ctx->stream));
+    } else {
+        if (ctx->table.wide) CK(ctx, cudaMemsetAsync(ctx->table.keys128, 0xFF, cap * sizeof(ulonglong2), ctx->stream));
+        else CK(ctx, cudaMemsetAsync(ctx->table.keys64, 0xFF, cap * sizeof(unsigned long long), ctx->stream));
+        if (ctx->table.counts) CK(ctx, cudaMemsetAsync(ctx->table.counts, 0, cap * sizeof(unsigned long long), ctx->stream));
+    }
+    ctx->entries_upper = 0;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- measurement
+
+int bc_set_profiling(bc_ctx* ctx, int on) {
+    if (!ctx) return BC_EINVAL;
+    ctx->profiling = on != 0;
+    return BC_OK;
+}
+
+int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
+    if (!ctx || !out) return BC_EINVAL;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    drain_profile(ctx);
+    unsigned long long n = 0;
+    CK(ctx, cudaMemcpy(&n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
+    ctx->prof.table_capacity = ctx->table_capacity;
+    ctx->prof.table_entries = n;
+    ctx->prof.key_bits = ctx->cfg.key_bits;
+    ctx->prof.wide_keys = ctx->table.wide;
+    ctx->prof.dense_table = ctx->table.kind == 0;
+    *out = ctx->prof;
+    return BC_OK;
+}
+
+int bc_reset_profile(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    drain_profile(ctx);
+    ctx->prof = bc_profile{};
+    return BC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// bc_device.cuh — device-side layout of the run configuration, packed keys and the open-addressing tables.
+// sm_100a only.  Semantics follow SURVEY.md §3.3 (P1-P9, Q1-Q22); citations are file:line into the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bc {
+
+constexpr int kTile = 128;          // reads per CTA tile == threads per CTA
+constexpr int kMaxTW = 8;           // template words (BC_MAX_TEMPLATE / 32)
+constexpr int kMaxSlots = 16;
+constexpr int kMaxQRuns = 32;
+constexpr uint32_t kFail = 0xFFFFFFFFu;
+
+enum SlotMode : uint8_t { MODE_RAW = 0, MODE_TABLE = 1, MODE_HASH = 2, MODE_SCAN = 3 };
+
+struct DevSlot {
+    uint16_t offset, len, max_err;
+    uint8_t kind;        // 'S' 'B' 'R'
+    uint8_t mode;        // SlotMode
+    uint32_t n_ref;
+    uint32_t ref_off;    // first uint4 {lo,hi,nm,len} of this slot in the reference array
+    uint32_t aux_off;    // TABLE: first u16 of the 4^len lookup; HASH: first entry of the exact-match hash
+    uint32_t aux_mask;   // HASH: capacity-1
+    uint16_t key_shift;  // first key bit of this slot's field
+    uint16_t key_bits;   // index bits, or 3*len for raw fields ([lo:len][hi:len][nm:len])
+};
+
+struct DevQRun {
+    uint16_t off, len;   // position in the region walk (relative to the quality start) and length
+    uint32_t thresh;     // low quality iff sum of (q-33)&0xFF over the run < thresh  (parse.rs:352-355, Q12)
+};
+
+struct DevCfg {
+    uint32_t L, TW, n_slots, n_qruns, max_const_err, has_fn;
+    uint32_t has_umi, umi_bits, key_bits, wide;
+    uint32_t t_lo[kMaxTW], t_hi[kMaxTW], t_cm[kMaxTW], t_fn[kMaxTW];
+    DevSlot slots[kMaxSlots];
+    uint8_t order[kMaxSlots];  // sample first, then counted barcodes in order, then the random barcode
+    DevQRun qruns[kMaxQRuns];
+};
+
+struct Key {
+    unsigned long long lo, hi;
+};
+
+struct BatchView {
+    const uint32_t* planes;
+    const uint16_t* read_len;
+    const uint8_t* qual;  // nullptr when the quality filter is off
+    uint32_t n_reads, plane_stride, qual_stride, W;
+};
+
+// Main table.  kind: 0 dense counts (index = key), 1 hash with counts, 2 hash set (UMI mode, no counts).
+struct DevTable {
+    unsigned long long* keys64;   // narrow keys
+    ulonglong2* keys128;          // wide keys
+    unsigned long long* counts;   // dense / hash-with-counts
+    unsigned long long cap_mask;  // capacity - 1 (hash) ; capacity (dense)
+    unsigned long long* n_entries;
+    int kind;
+    int wide;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ unsigned long long hash_key(Key k) { return mix64(k.lo ^ mix64(k.hi + 0x9e3779b97f4a7c15ULL)); }
+
+__device__ __forceinline__ void key_or(Key& k, unsigned long long v, uint32_t shift) {
+    if (shift < 64) {
+        k.lo |= v << shift;
+        if (shift) k.hi |= v >> (64 - shift);
+    } else {
+        k.hi |= v << (shift - 64);
+    }
+}
+__device__ __forceinline__ Key key_shr(Key k, uint32_t s) {
+    if (s == 0) return k;
+    Key r;
+    if (s < 64) {
+        r.lo = (k.lo >> s) | (k.hi << (64 - s));
+        r.hi = k.hi >> s;
+    } else {
+        r.lo = k.hi >> (s - 64);
+        r.hi = 0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2* addr, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n"
+        ".reg .b128 c, v, o;\n"
+        "mov.b128 c, {%2, %3};\n"
+        "mov.b128 v, {%4, %5};\n"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n"
+        "mov.b128 {%0, %1}, o;\n"
+        "}\n"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+constexpr unsigned long long kEmpty = ~0ULL;
+
+// Find-or-claim the slot of `key`.  Returns the slot index; *is_new tells whether this call claimed it.
+// Load factor is kept <= 0.5 by the host, so linear probing terminates quickly.
+__device__ __forceinline__ unsigned long long table_find_or_insert(const DevTable& t, Key key, bool* is_new) {
+    unsigned long long h = hash_key(key) & t.cap_mask;
+    if (!t.wide) {
+        for (;;) {
+            unsigned long long cur = t.keys64[h];
+            if (cur == key.lo) { *is_new = false; return h; }
+            if (cur == kEmpty) {
+                unsigned long long old = atomicCAS(&t.keys64[h], kEmpty, key.lo);
+                if (old == kEmpty) { *is_new = true; return h; }
+                if (old == key.lo) { *is_new = false; return h; }
+            }
+            h = (h + 1) & t.cap_mask;
+        }
+    } else {
+        const ulonglong2 empty = make_ulonglong2(kEmpty, kEmpty);
+        const ulonglong2 mine = make_ulonglong2(key.lo, key.hi);
+        for (;;) {
+            ulonglong2 old = cas128(&t.keys128[h], empty, mine);
+            if (old.x == kEmpty && old.y == kEmpty) { *is_new = true; return h; }
+            if (old.x == key.lo && old.y == key.hi) { *is_new = false; return h; }
+            h = (h + 1) & t.cap_mask;
+        }
+    }
+}
+
+// One read's contribution (info.rs:735-808).  Returns true when the read is "matched", false when it is a
+// duplicate (only possible in UMI/set mode: info.rs:780-791).  *is_new reports a newly claimed hash slot so the
+// caller can aggregate the entry count per CTA instead of hammering one global counter.
+__device__ __forceinline__ bool table_count(const DevTable& t, Key key, unsigned long long add, bool* is_new) {
+    *is_new = false;
+    if (t.kind == 0) {
+        atomicAdd(&t.counts[key.lo], add);
+        return true;
+    }
+    unsigned long long h = table_find_or_insert(t, key, is_new);
+    if (t.kind == 1) {
+        atomicAdd(&t.counts[h], add);
+        return true;
+    }
+    return *is_new;
+}
+
+}  // namespace bc

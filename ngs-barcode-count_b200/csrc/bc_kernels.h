@@ -1,0 +1,62 @@
+// bc_kernels.h — host-callable launchers of the sm_100a kernels (defined in bc_kernels.cu).
+#pragma once
+#include "bc_device.cuh"
+
+namespace bc {
+
+struct DecodeOut {  // all optional (test hooks / decode_only)
+    uint8_t* status;
+    int16_t* offset;
+    uint8_t* repaired;
+    int32_t* slot_index;
+    unsigned long long* key_lo;
+    unsigned long long* key_hi;
+};
+
+struct RouteOut {  // multi-GPU: matched (key,UMI) records bucketed by owner rank instead of inserted
+    Key* buckets;
+    unsigned long long capacity;  // records per bucket
+    uint32_t* counts;             // [n_ranks]
+    uint32_t n_ranks;
+};
+
+struct DevAux {  // reference sets and their accelerators
+    const uint4* refs;                    // {lo, hi, nm, len} per reference barcode
+    const uint16_t* tables;               // 4^len direct lookups (MODE_TABLE)
+    const unsigned long long* hash_keys;  // exact-match hash (MODE_HASH): lo | hi << 32
+    const uint32_t* hash_idx;
+};
+
+enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8 };
+
+// counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
+cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, int flags,
+                          cudaStream_t stream);
+
+// fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
+cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t* table, cudaStream_t stream);
+
+// inserts n keys (count `add` each, or counts[i]) into `table`; bumps matched/duplicates when counters != nullptr
+cudaError_t launch_insert(const DevTable& table, const unsigned long long* key_lo, const unsigned long long* key_hi,
+                          const Key* records, const unsigned long long* counts, unsigned long long n,
+                          unsigned long long* counters, cudaStream_t stream);
+
+// UMI set -> per-key counts: for every occupied entry of `set`, dst[key >> umi_bits] += 1
+cudaError_t launch_group(const DevTable& set, uint32_t umi_bits, const DevTable& dst, cudaStream_t stream);
+
+// occupied entries of `t` (dense: non-zero counts) appended to the row arrays; *n_rows is a device counter
+cudaError_t launch_compact(const DevTable& t, unsigned long long* key_lo, unsigned long long* key_hi,
+                           unsigned long long* count, unsigned long long* n_rows, cudaStream_t stream);
+
+// dst[key & mask] += count over the rows
+cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned long long* key_hi,
+                            const unsigned long long* count, unsigned long long n_rows, Key mask, const DevTable& dst,
+                            cudaStream_t stream);
+
+// move every entry of `src` (hash kinds) into `dst`
+cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);
+
+size_t decode_smem_bytes(const BatchView& batch);
+
+}  // namespace bc

@@ -1,0 +1,797 @@
+// bc_host.cpp — host side of the drop-in (include/bc_host.h): scheme/CSV set-up, FASTQ ingest + packing,
+// CSV writers.  Index based: barcodes are reference indices or packed raw keys end to end; strings appear
+// only when files are read and written.  No read is decoded here — that is the GPU library's job.
+#include "../../../include/bc_host.h"
+
+#include <cuda_runtime_api.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+std::string slurp(const std::string& path, const char* verb) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw Error(std::string(verb) + " " + path);
+    std::ostringstream ss;
+    ss << in.rdbuf();
+    return ss.str();
+}
+
+// text -> lines without terminators ("\n" and "\r\n"), no phantom last line
+std::vector<std::string> text_lines(const std::string& text) {
+    std::vector<std::string> lines;
+    size_t start = 0;
+    while (start < text.size()) {
+        size_t end = text.find('\n', start);
+        size_t stop = end == std::string::npos ? text.size() : end;
+        size_t len = stop - start;
+        if (len && text[stop - 1] == '\r') len--;
+        lines.emplace_back(text, start, len);
+        if (end == std::string::npos) break;
+        start = end + 1;
+    }
+    return lines;
+}
+
+std::vector<std::string> csv_fields(const std::string& line) {
+    std::vector<std::string> f;
+    std::string cur;
+    for (char c : line) {
+        if (c == ',') {
+            f.push_back(cur);
+            cur.clear();
+        } else {
+            cur.push_back(c);
+        }
+    }
+    f.push_back(cur);
+    return f;
+}
+
+struct SlotInfo {
+    char kind;  // 'S' 'B' 'R'
+    uint16_t offset, len;
+    std::vector<std::string> dna, name;        // reference barcodes in first-seen order (empty: raw)
+    std::vector<const char*> dna_ptrs;
+    std::unordered_map<std::string, size_t> pos;  // DNA -> index
+};
+
+}  // namespace
+
+struct bch_run {
+    std::string format_string, regions_string;
+    uint16_t constant_len = 0;
+    std::vector<SlotInfo> slots;  // template order
+    std::vector<int> counted;     // slot indices of {n} barcodes, in order
+    int sample_slot = -1, random_slot = -1;
+    bool have_sample_file = false, have_counted_file = false;
+    uint16_t max_constant = 0, max_sample = 0;
+    std::vector<uint16_t> max_counted, counted_sizes;
+    float min_quality = 0.f;
+    bc_config cfg{};
+    std::string description;
+};
+
+namespace {
+
+// ---- scheme file: tokens {n} [n] (n), runs of N, runs of ACGT; everything else is ignored; lines starting with
+// '#' are comments and the remaining lines are joined without a separator (info.rs:218-233)
+void parse_scheme(bch_run& run, const std::string& text) {
+    std::string body;
+    for (const std::string& line : text_lines(text))
+        if (line.empty() || line[0] != '#') body += line;
+    auto digit = [](char c) { return c >= '0' && c <= '9'; };
+    size_t i = 0;
+    const size_t n = body.size();
+    while (i < n) {
+        const char c = body[i];
+        if (c == '{' || c == '[' || c == '(') {
+            const char closer = c == '{' ? '}' : c == '[' ? ']' : ')';
+            size_t j = i + 1;
+            unsigned long value = 0;
+            while (j < n && digit(body[j])) {
+                value = value * 10 + (unsigned long)(body[j] - '0');
+                if (value > 65535) throw Error("scheme: barcode length does not fit 16 bits");
+                j++;
+            }
+            if (j == i + 1 || j >= n || body[j] != closer) {
+                i++;
+                continue;
+            }
+            SlotInfo s;
+            s.kind = c == '{' ? 'B' : c == '[' ? 'S' : 'R';
+            s.offset = (uint16_t)run.format_string.size();
+            s.len = (uint16_t)value;
+            const int idx = (int)run.slots.size();
+            if (s.kind == 'S') {
+                if (run.sample_slot >= 0) throw Error("scheme: more than one sample barcode [n] (the reference's regex rejects a duplicate group too)");
+                run.sample_slot = idx;
+            } else if (s.kind == 'R') {
+                if (run.random_slot >= 0) throw Error("scheme: more than one random barcode (n) (the reference's regex rejects a duplicate group too)");
+                run.random_slot = idx;
+            } else {
+                run.counted.push_back(idx);
+                run.counted_sizes.push_back(s.len);
+            }
+            run.slots.push_back(s);
+            run.format_string.append(value, 'N');
+            run.regions_string.append(value, s.kind);
+            i = j + 1;
+        } else if (c == 'N' || c == 'n') {
+            size_t j = i;
+            while (j < n && (body[j] == 'N' || body[j] == 'n')) {
+                if (body[j] == 'n') throw Error("scheme: lower-case 'n' is not supported (upper-case N only)");
+                j++;
+            }
+            run.format_string.append(j - i, 'N');  // no region code for format-N (info.rs:287-295)
+            i = j;
+        } else if (strchr("ACGTacgt", c)) {
+            size_t j = i;
+            while (j < n && strchr("ACGTacgt", body[j]) && body[j] != '\0') {
+                if (body[j] >= 'a')
+                    throw Error("scheme: lower-case constants are not supported: the reference upper-cases them for the regex but "
+                                "not for the repair step (info.rs:298-299), which makes such schemes ill-defined");
+                j++;
+            }
+            run.format_string.append(body, i, j - i);
+            run.regions_string.append(j - i, 'C');
+            run.constant_len = (uint16_t)(run.constant_len + (j - i));
+            i = j;
+        } else {
+            i++;
+        }
+    }
+    if (run.counted.empty()) throw Error("scheme: no counted barcode {n}");
+}
+
+// ---- conversion CSVs (info.rs:364-433): header skipped, comma split, no trimming; a later duplicate DNA
+// replaces the earlier ID
+void add_ref(SlotInfo& s, const std::string& dna, const std::string& id) {
+    auto it = s.pos.find(dna);
+    if (it != s.pos.end()) {
+        s.name[it->second] = id;
+        return;
+    }
+    s.pos.emplace(dna, s.dna.size());
+    s.dna.push_back(dna);
+    s.name.push_back(id);
+}
+
+void load_samples(bch_run& run, const std::string& path) {
+    if (run.sample_slot < 0)
+        throw Error("--sample-barcodes given but the scheme has no sample barcode [n]: the reference silently drops every count in "
+                    "that configuration (info.rs:762-766); refusing to run it");
+    std::vector<std::string> lines = text_lines(slurp(path, "Failed to open"));
+    SlotInfo& s = run.slots[run.sample_slot];
+    for (size_t i = 1; i < lines.size(); i++) {
+        std::vector<std::string> f = csv_fields(lines[i]);
+        if (f.size() >= 2) add_ref(s, f[0], f[1]);
+        else add_ref(s, "", "");
+    }
+    run.have_sample_file = !s.dna.empty();
+}
+
+void load_counted(bch_run& run, const std::string& path) {
+    std::vector<std::string> lines = text_lines(slurp(path, "Failed to read"));
+    std::vector<bool> seen(run.counted.size(), false);
+    for (size_t i = 1; i < lines.size(); i++) {
+        std::vector<std::string> f = csv_fields(lines[i]);
+        std::string dna, id, num;
+        if (f.size() >= 3) {
+            dna = f[0];
+            id = f[1];
+            num = f[2];
+        }
+        size_t p = (!num.empty() && num[0] == '+') ? 1 : 0;
+        bool numeric = p < num.size();
+        for (size_t q = p; q < num.size() && numeric; q++) numeric = num[q] >= '0' && num[q] <= '9';
+        if (!numeric) throw Error("Third column of barcode file contains something other than an integer: " + num);
+        const unsigned long long k = std::stoull(num.substr(p));
+        if (k == 0 || k > run.counted.size())
+            throw Error("barcode file: barcode number " + num + " is outside 1.." + std::to_string(run.counted.size()));
+        seen[k - 1] = true;
+        add_ref(run.slots[run.counted[k - 1]], dna, id);
+    }
+    std::string missing;
+    for (size_t k = 0; k < seen.size(); k++)
+        if (!seen[k]) missing += (missing.empty() ? "" : ", ") + std::to_string(k);
+    if (!missing.empty()) throw Error("Barcode conversion file missing barcode numers [" + missing + "] in the third column");
+    run.have_counted_file = true;
+}
+
+std::string shortest_float(float v) {
+    char buf[64];
+    for (int p = 1; p <= 9; p++) {
+        snprintf(buf, sizeof buf, "%.*g", p, (double)v);
+        if (strtof(buf, nullptr) == v) break;
+    }
+    return buf;
+}
+
+std::string list_u16(const std::vector<uint16_t>& v) {
+    std::string s = "[";
+    for (size_t i = 0; i < v.size(); i++) s += (i ? ", " : "") + std::to_string(v[i]);
+    return s + "]";
+}
+
+void describe(bch_run& run) {
+    std::string key;
+    std::string seen;
+    for (char c : run.regions_string) {
+        if (seen.find(c) != std::string::npos) continue;
+        seen.push_back(c);
+        if (c == 'S') key += "\nS: Sample barcode";
+        else if (c == 'B') key += "\nB: Counted barcode";
+        else if (c == 'C') key += "\nC: Constant region";
+        else if (c == 'R') key += "\nR: Random barcode";
+    }
+    std::string d = "-FORMAT-\n" + run.format_string + "\n" + run.regions_string + key + "\n\n";
+    const std::string bar = "--------------------------------------------------------------\n";
+    d += "-BARCODE INFO-\nConstant region size: " + std::to_string(run.constant_len) +
+         "\nMaximum mismatches allowed per sequence: " + std::to_string(run.max_constant) + "\n" + bar;
+    d += "Sample barcode size: " + std::to_string(run.sample_slot >= 0 ? run.slots[run.sample_slot].len : 0) +
+         "\nMaximum mismatches allowed per sequence: " + std::to_string(run.max_sample) + "\n" + bar;
+    if (run.counted_sizes.size() > 1)
+        d += "Barcode sizes: " + list_u16(run.counted_sizes) + "\nMaximum mismatches allowed per barcode sequence: " +
+             list_u16(run.max_counted) + "\n";
+    else
+        d += "Barcode size: " + std::to_string(run.counted_sizes[0]) + "\nMaximum mismatches allowed per barcode sequence: " +
+             std::to_string(run.max_counted[0]) + "\n";
+    d += bar + "Minimum allowed average read quality score per barcode: " + shortest_float(run.min_quality) + "\n";
+    run.description = d;
+}
+
+// ---- packing ------------------------------------------------------------------------------------------------
+
+struct BaseLut {
+    uint8_t code[256];  // 0..3 = A C G T, 4 = N, 5 = anything else
+    BaseLut() {
+        memset(code, 5, sizeof code);
+        code[(unsigned char)'A'] = 0;
+        code[(unsigned char)'C'] = 1;
+        code[(unsigned char)'G'] = 2;
+        code[(unsigned char)'T'] = 3;
+        code[(unsigned char)'N'] = 4;
+    }
+};
+const BaseLut kLut;
+
+// one read -> three bit planes + length word (+ quality bytes)
+inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W, uint32_t* planes, uint16_t* read_len,
+                     uint8_t* qual_out, uint32_t qual_stride) {
+    uint32_t* lo = planes;
+    uint32_t* hi = planes + W;
+    uint32_t* nm = planes + 2 * W;
+    bool other = false;
+    uint32_t w = 0;
+    for (uint32_t base = 0; base < len; base += 32, w++) {
+        const uint32_t m = std::min(32u, len - base);
+        uint32_t l = 0, h = 0, x = 0;
+        for (uint32_t b = 0; b < m; b++) {
+            const uint8_t c = kLut.code[(unsigned char)seq[base + b]];
+            l |= (uint32_t)(c & 1u) << b;
+            h |= (uint32_t)((c >> 1) & 1u) << b;
+            x |= (uint32_t)(c >> 2) << b;      // N or other
+            other |= c == 5;
+        }
+        lo[w] = l & ~x;
+        hi[w] = h & ~x;
+        nm[w] = x;
+    }
+    for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
+    if (3 * W != ((3 * W) | 1u)) planes[3 * W] = 0;  // pad word of an even record
+    *read_len = (uint16_t)(len | (other ? BC_READ_UNSUPPORTED : 0u));
+    if (qual_out) {
+        memcpy(qual_out, qual, len);
+        memset(qual_out + len, '!', qual_stride - len);
+    }
+}
+
+struct ReadRef {
+    const char* seq;
+    const char* qual;
+    uint32_t len, qlen;
+};
+
+int pack_refs(uint32_t max_read_len, const std::vector<ReadRef>& reads, size_t first, size_t count, uint32_t* planes,
+              uint16_t* read_len, uint8_t* qual, unsigned threads) {
+    const uint32_t W = bc_plane_words(max_read_len), ps = bc_plane_stride(max_read_len), qs = bc_qual_stride(max_read_len);
+    std::atomic<int> bad{0};
+    auto work = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) {
+            const ReadRef& r = reads[first + i];
+            if (r.len > max_read_len || r.len > 0x7FFF || (qual && r.qlen != r.len)) {
+                bad = 1;
+                continue;
+            }
+            pack_one(r.seq, r.len, r.qual, W, planes + i * ps, read_len + i, qual ? qual + i * qs : nullptr, qs);
+        }
+    };
+    if (threads <= 1 || count < 4096) {
+        work(0, count);
+    } else {
+        std::vector<std::thread> pool;
+        const size_t per = (count + threads - 1) / threads;
+        for (unsigned t = 0; t < threads; t++) {
+            const size_t a = std::min(count, t * per), b = std::min(count, a + per);
+            if (a < b) pool.emplace_back(work, a, b);
+        }
+        for (auto& th : pool) th.join();
+    }
+    return bad ? BC_EINVAL : BC_OK;
+}
+
+// ---- FASTQ streaming: big blocks through zlib's gz layer (plain files pass through; concatenated gzip members
+// are walked like flate2's MultiGzDecoder, input.rs:63), records split in place
+struct FastqStream {
+    gzFile gz = nullptr;
+    std::vector<char> buf;
+    size_t have = 0;      // valid bytes in buf
+    bool eof = false;
+    FastqStream(const std::string& path, size_t block_bytes) {
+        auto ends = [&](const char* suf) {
+            const size_t k = strlen(suf);
+            return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
+        };
+        if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
+            throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
+        gz = gzopen(path.c_str(), "rb");
+        if (!gz) throw Error("Failed to open file: " + path);
+        gzbuffer(gz, 4u << 20);
+        buf.resize(std::min<size_t>(std::max<size_t>(block_bytes, 16u << 20), 1u << 30));
+    }
+    ~FastqStream() {
+        if (gz) gzclose(gz);
+    }
+    // Appends whole records to `out` (pointers into buf, valid until the next call).  Returns false at the end.
+    bool next_block(std::vector<ReadRef>& out, size_t max_records) {
+        out.clear();
+        if (eof && have == 0) return false;
+        while (!eof && have < buf.size()) {
+            const int got = gzread(gz, buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, 1u << 30));
+            if (got < 0) throw Error("gzread failed (corrupt input?)");
+            if (got == 0) {
+                eof = true;
+                break;
+            }
+            have += (size_t)got;
+        }
+        size_t pos = 0, consumed = 0;
+        while (out.size() < max_records) {
+            const char* line[4];
+            uint32_t len[4];
+            size_t p = pos;
+            int k = 0;
+            for (; k < 4; k++) {
+                const char* nl = (const char*)memchr(buf.data() + p, '\n', have - p);
+                size_t end;
+                if (nl) end = (size_t)(nl - buf.data());
+                else if (eof && k == 3 && p < have) end = have;  // last line without '\n'
+                else break;
+                size_t l = end - p;
+                if (l && buf[end - 1] == '\r') l--;
+                line[k] = buf.data() + p;
+                len[k] = (uint32_t)l;
+                p = nl ? end + 1 : end;
+            }
+            if (k < 4) break;
+            out.push_back(ReadRef{line[1], line[3], len[1], len[3]});
+            pos = p;
+            consumed = p;
+        }
+        pending_shift = consumed;
+        if (out.empty()) {
+            if (eof) {
+                have = 0;  // trailing partial record (fewer than 4 lines) is dropped, as the reference never posts it
+                return false;
+            }
+            if (have == buf.size()) throw Error("FASTQ record longer than the block buffer");
+        }
+        return true;
+    }
+    size_t pending_shift = 0;
+    void release_block() {  // call once the records of the last block are packed
+        if (pending_shift) {
+            memmove(buf.data(), buf.data() + pending_shift, have - pending_shift);
+            have -= pending_shift;
+            pending_shift = 0;
+        }
+    }
+};
+
+struct PinnedBatch {
+    uint32_t* planes = nullptr;
+    uint16_t* read_len = nullptr;
+    uint8_t* qual = nullptr;
+    ~PinnedBatch() {
+        if (planes) cudaFreeHost(planes);
+        if (read_len) cudaFreeHost(read_len);
+        if (qual) cudaFreeHost(qual);
+    }
+    void alloc(uint32_t n, uint32_t max_read_len, bool with_qual) {
+        if (cudaHostAlloc((void**)&planes, (size_t)n * bc_plane_stride(max_read_len) * 4, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&read_len, (size_t)n * 2, cudaHostAllocDefault) != cudaSuccess ||
+            (with_qual && cudaHostAlloc((void**)&qual, (size_t)n * bc_qual_stride(max_read_len), cudaHostAllocDefault) != cudaSuccess))
+            throw Error("cudaHostAlloc failed for the pinned batch buffers");
+    }
+};
+
+// ---- output ---------------------------------------------------------------------------------------------------
+
+std::string join(const std::vector<std::string>& v) {
+    std::string s;
+    for (size_t i = 0; i < v.size(); i++) s += (i ? "," : "") + v[i];
+    return s;
+}
+
+struct DecodedRow {
+    std::string sample;           // sample DNA (file sample: reference DNA; raw: captured DNA; none: "barcode")
+    std::vector<std::string> dna; // per counted barcode ("" when absent in an enrichment row)
+    std::vector<std::string> out; // what is written: ID when a counted file exists, DNA otherwise
+    uint64_t count;
+};
+
+void decode_rows(const bch_run& run, const bc_ctx* ctx, const bc_table& t, std::vector<DecodedRow>& rows) {
+    const uint32_t ns = (uint32_t)run.slots.size();
+    const uint32_t stride = BC_MAX_REF_LEN + 1;
+    std::vector<int32_t> idx(ns);
+    std::vector<char> str((size_t)ns * stride);
+    rows.resize(t.n_rows);
+    for (uint64_t r = 0; r < t.n_rows; r++) {
+        const uint32_t mask = t.mask ? t.mask[r] : 0;
+        if (bc_key_decode(ctx, t.key_lo[r], t.key_hi[r], mask, 0, idx.data(), str.data(), stride) != BC_OK)
+            throw Error("bc_key_decode failed");
+        DecodedRow& d = rows[r];
+        d.count = t.count[r];
+        if (run.sample_slot < 0) d.sample = "barcode";
+        else if (run.have_sample_file) d.sample = run.slots[run.sample_slot].dna.at((size_t)idx[run.sample_slot]);
+        else d.sample = str.data() + (size_t)run.sample_slot * stride;
+        d.dna.resize(run.counted.size());
+        d.out.resize(run.counted.size());
+        for (size_t k = 0; k < run.counted.size(); k++) {
+            const int s = run.counted[k];
+            if (mask && !(mask & (1u << k))) continue;  // column left empty (info.rs:847-856, 881-893)
+            if (run.have_counted_file) {
+                d.dna[k] = run.slots[s].dna.at((size_t)idx[s]);
+                d.out[k] = run.slots[s].name.at((size_t)idx[s]);
+            } else {
+                d.dna[k] = d.out[k] = str.data() + (size_t)s * stride;
+            }
+        }
+    }
+}
+
+void write_text(const std::string& dir, const std::string& name, const std::string& text, std::vector<std::string>& names) {
+    std::string path = dir;
+    if (!path.empty() && path.back() != '/') path.push_back('/');
+    path += name;
+    std::ofstream out(path, std::ios::binary);
+    if (!out) throw Error("cannot create " + path);
+    out << text;
+    names.push_back(name);
+}
+
+}  // namespace
+
+extern "C" {
+
+bch_run* bch_open(const bch_args* args, char* err, int errlen) {
+    auto report = [&](const std::string& m) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
+    };
+    if (!args || !args->format_path) {
+        report("format_path is required");
+        return nullptr;
+    }
+    bch_run* run = new bch_run();
+    try {
+        parse_scheme(*run, slurp(args->format_path, "Failed to open"));
+        if (args->sample_barcodes_path) load_samples(*run, args->sample_barcodes_path);
+        if (args->counted_barcodes_path) load_counted(*run, args->counted_barcodes_path);
+        // caps (info.rs:499-532): flag value, else a fifth of the length, rounded down
+        if (run->sample_slot >= 0)
+            run->max_sample = args->max_errors_sample >= 0 ? (uint16_t)args->max_errors_sample : (uint16_t)(run->slots[run->sample_slot].len / 5);
+        for (uint16_t sz : run->counted_sizes)
+            run->max_counted.push_back(args->max_errors_counted_barcode >= 0 ? (uint16_t)args->max_errors_counted_barcode : (uint16_t)(sz / 5));
+        run->max_constant = args->max_errors_constant >= 0 ? (uint16_t)args->max_errors_constant : (uint16_t)(run->constant_len / 5);
+        run->min_quality = args->min_quality;
+
+        bc_config& c = run->cfg;
+        c.abi_version = BC_ABI_VERSION;
+        c.template_chars = run->format_string.c_str();
+        c.template_len = (uint32_t)run->format_string.size();
+        c.region_codes = run->regions_string.c_str();
+        c.region_len = (uint32_t)run->regions_string.size();
+        if (run->slots.size() > BC_MAX_SLOTS) throw Error("scheme: more than " + std::to_string(BC_MAX_SLOTS) + " barcodes");
+        c.n_slots = (uint32_t)run->slots.size();
+        size_t counted_k = 0;
+        for (size_t s = 0; s < run->slots.size(); s++) {
+            SlotInfo& S = run->slots[s];
+            for (const std::string& d : S.dna) S.dna_ptrs.push_back(d.c_str());
+            bc_slot& o = c.slots[s];
+            o.kind = (uint8_t)S.kind;
+            o.offset = S.offset;
+            o.len = S.len;
+            o.max_err = S.kind == 'S' ? run->max_sample : S.kind == 'B' ? run->max_counted[counted_k++] : 0;
+            o.n_ref = (uint32_t)S.dna.size();
+            o.ref_seqs = S.dna_ptrs.empty() ? nullptr : S.dna_ptrs.data();
+        }
+        c.max_const_err = run->max_constant;
+        c.min_quality = run->min_quality;
+        c.max_read_len = args->max_read_len ? args->max_read_len : std::max<uint32_t>(160, 2 * c.template_len);
+        describe(*run);
+        return run;
+    } catch (const std::exception& e) {
+        report(e.what());
+        delete run;
+        return nullptr;
+    }
+}
+
+void bch_close(bch_run* run) { delete run; }
+const bc_config* bch_config(const bch_run* run) { return run ? &run->cfg : nullptr; }
+const char* bch_describe(const bch_run* run) { return run ? run->description.c_str() : ""; }
+uint32_t bch_barcode_num(const bch_run* run) { return run ? (uint32_t)run->counted.size() : 0; }
+const char* bch_ref_dna(const bch_run* run, uint32_t slot, uint32_t i) {
+    if (!run || slot >= run->slots.size() || i >= run->slots[slot].dna.size()) return nullptr;
+    return run->slots[slot].dna[i].c_str();
+}
+const char* bch_ref_name(const bch_run* run, uint32_t slot, uint32_t i) {
+    if (!run || slot >= run->slots.size() || i >= run->slots[slot].name.size()) return nullptr;
+    return run->slots[slot].name[i].c_str();
+}
+
+int bch_pack(uint32_t max_read_len, uint32_t n, const char* const* seqs, const char* const* quals, uint32_t* planes_out,
+             uint16_t* read_len_out, uint8_t* qual_out, unsigned threads) {
+    if (!seqs || !planes_out || !read_len_out || (qual_out && !quals)) return BC_EINVAL;
+    std::vector<ReadRef> refs(n);
+    for (uint32_t i = 0; i < n; i++)
+        refs[i] = ReadRef{seqs[i], quals ? quals[i] : nullptr, (uint32_t)strlen(seqs[i]), quals ? (uint32_t)strlen(quals[i]) : 0u};
+    return pack_refs(max_read_len, refs, 0, n, planes_out, read_len_out, quals ? qual_out : nullptr, threads);
+}
+
+int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char* seq_lines, const char* qual_lines, uint32_t* planes_out,
+                   uint16_t* read_len_out, uint8_t* qual_out, unsigned threads) {
+    if (!seq_lines || !planes_out || !read_len_out || (qual_out && !qual_lines)) return BC_EINVAL;
+    std::vector<ReadRef> refs;
+    refs.reserve(n);
+    const char* s = seq_lines;
+    const char* q = qual_lines;
+    for (uint32_t i = 0; i < n; i++) {
+        const char* se = strchr(s, '\n');
+        const uint32_t sl = se ? (uint32_t)(se - s) : (uint32_t)strlen(s);
+        ReadRef r{s, nullptr, sl, 0};
+        if (q) {
+            const char* qe = strchr(q, '\n');
+            r.qual = q;
+            r.qlen = qe ? (uint32_t)(qe - q) : (uint32_t)strlen(q);
+            q = qe ? qe + 1 : q + r.qlen;
+        }
+        refs.push_back(r);
+        s = se ? se + 1 : s + sl;
+    }
+    return pack_refs(max_read_len, refs, 0, n, planes_out, read_len_out, qual_lines ? qual_out : nullptr, threads);
+}
+
+int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads,
+                    uint64_t* total_reads, char* err, int errlen) {
+    auto report = [&](const std::string& m) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
+    };
+    if (!run || !ctx || !fastq_path) return BC_EINVAL;
+    if (batch_reads == 0) batch_reads = 1u << 20;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    try {
+        const uint32_t mrl = run->cfg.max_read_len;
+        const bool with_qual = run->min_quality > 0.0f;
+        PinnedBatch pinned[2];
+        pinned[0].alloc(batch_reads, mrl, with_qual);
+        pinned[1].alloc(batch_reads, mrl, with_qual);
+        FastqStream in(fastq_path, (size_t)batch_reads * (2 * (size_t)mrl + 64));
+        std::vector<ReadRef> block;
+        uint64_t total = 0;
+        int cur = 0;
+        int in_flight = 0;  // submits since the last sync; each pinned buffer is reused every second submit
+        while (in.next_block(block, batch_reads)) {
+            if (block.empty()) {
+                in.release_block();
+                continue;
+            }
+            if (in_flight == 2) {  // the buffer we are about to overwrite was handed to the submit before last
+                if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+                in_flight = 0;
+            }
+            PinnedBatch& p = pinned[cur];
+            if (pack_refs(mrl, block, 0, block.size(), p.planes, p.read_len, with_qual ? p.qual : nullptr, threads) != BC_OK)
+                throw Error("FASTQ record " + std::to_string(total) + "+: read longer than max_read_len (" + std::to_string(mrl) +
+                            ") or quality/sequence length mismatch");
+            bc_batch b{};
+            b.n_reads = (uint32_t)block.size();
+            b.plane_stride = bc_plane_stride(mrl);
+            b.qual_stride = bc_qual_stride(mrl);
+            b.location = BC_LOC_HOST;
+            b.planes = p.planes;
+            b.read_len = p.read_len;
+            b.qual = with_qual ? p.qual : nullptr;
+            if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
+            total += block.size();
+            in.release_block();
+            cur ^= 1;
+            in_flight++;
+        }
+        if (bc_sync(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+        if (total_reads) *total_reads = total;
+        return BC_OK;
+    } catch (const std::exception& e) {
+        report(e.what());
+        return BC_EINVAL;
+    }
+}
+
+int bch_write_counts(bch_run* run, bc_ctx* ctx, const char* output_dir, const char* prefix, int merge_output, int enrich,
+                     char* names_out, int names_len, char* err, int errlen) {
+    auto report = [&](const std::string& m) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
+    };
+    if (!run || !ctx) return BC_EINVAL;
+    bc_table full{}, singles{}, doubles{};
+    try {
+        const std::string dir = output_dir ? output_dir : "./";
+        const std::string pre = prefix ? prefix : "";
+        const size_t nb = run->counted.size();
+        bool merge = merge_output != 0;
+        bool do_enrich = enrich != 0 && nb >= 2;  // main.rs:22-25
+        if (bc_finish(ctx, &full) != BC_OK) throw Error(bc_last_error(ctx));
+        std::vector<DecodedRow> rows;
+        decode_rows(*run, ctx, full, rows);
+
+        // sample list and its order (output.rs:77-97): with a sample file every listed sample gets files (Q16) and the
+        // order is by sample ID; otherwise the samples seen, ordered by DNA for reproducibility
+        std::vector<std::string> samples, sample_names;
+        if (run->have_sample_file) {
+            const SlotInfo& S = run->slots[run->sample_slot];
+            std::vector<size_t> order(S.dna.size());
+            for (size_t i = 0; i < order.size(); i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return S.name[a] < S.name[b]; });
+            for (size_t i : order) {
+                samples.push_back(S.dna[i]);
+                sample_names.push_back(S.name[i]);
+            }
+        } else if (run->sample_slot >= 0) {
+            std::set<std::string> seen;
+            for (const DecodedRow& r : rows) seen.insert(r.sample);
+            for (const std::string& s : seen) {
+                samples.push_back(s);
+                sample_names.push_back(s);
+            }
+        } else {
+            samples.push_back("barcode");
+            sample_names.push_back("barcode");
+        }
+        std::unordered_map<std::string, size_t> sample_pos;
+        for (size_t i = 0; i < samples.size(); i++) sample_pos[samples[i]] = i;
+
+        std::string header = nb > 1 ? "Barcode_1" : "Barcode";  // output.rs:184-196
+        for (size_t k = 1; k < nb; k++) header += ",Barcode_" + std::to_string(k + 1);
+        if (merge && samples.size() == 1) {  // output.rs:105-110
+            fprintf(stderr, "Merged file cannot be created without multiple sample barcodes\n");
+            merge = false;
+        }
+        std::string merged_header = header;
+        for (const std::string& nme : sample_names) merged_header += "," + nme;
+        merged_header += "\n";
+
+        std::vector<std::string> names;
+        std::set<std::string> compounds_written;  // one set across Full / Single / Double, as output.rs:39
+
+        // generic emitter for one family of tables (Full, Single or Double): per-sample files + merged file
+        auto emit = [&](const std::vector<DecodedRow>& src, bool full_type, const std::string& descriptor) {
+            // per sample: written-key -> count ; merged: code -> (written, per-sample counts)
+            struct Merged {
+                std::string written;
+                std::vector<uint64_t> counts;
+            };
+            std::vector<std::map<std::string, uint64_t>> per_sample_enriched(samples.size());
+            std::vector<std::vector<std::string>> per_sample_lines(samples.size());
+            std::map<std::string, Merged> merged;
+            for (const DecodedRow& r : src) {
+                auto sp = sample_pos.find(r.sample);
+                if (sp == sample_pos.end()) continue;
+                const size_t si = sp->second;
+                const std::string written = join(r.out);
+                if (full_type) {
+                    per_sample_lines[si].push_back(written + "," + std::to_string(r.count));
+                    if (merge) {
+                        Merged& m = merged[join(r.dna)];  // keyed by the DNA code (output.rs:292)
+                        if (m.counts.empty()) {
+                            m.written = written;
+                            m.counts.assign(samples.size(), 0);
+                        }
+                        m.counts[si] += r.count;
+                    }
+                } else {
+                    per_sample_enriched[si][written] += r.count;  // keyed by what is written: IDs merge (Q20)
+                }
+            }
+            if (!full_type) {
+                for (size_t si = 0; si < samples.size(); si++)
+                    for (const auto& kv : per_sample_enriched[si]) {
+                        per_sample_lines[si].push_back(kv.first + "," + std::to_string(kv.second));
+                        if (merge) {
+                            Merged& m = merged[kv.first];
+                            if (m.counts.empty()) {
+                                m.written = kv.first;
+                                m.counts.assign(samples.size(), 0);
+                            }
+                            m.counts[si] += kv.second;
+                        }
+                    }
+            }
+            for (size_t si = 0; si < samples.size(); si++) {
+                std::sort(per_sample_lines[si].begin(), per_sample_lines[si].end());
+                std::string text = header + ",Count\n";
+                for (const std::string& l : per_sample_lines[si]) text += l + "\n";
+                write_text(dir, pre + "_" + sample_names[si] + "_counts" + (descriptor.empty() ? "" : "." + descriptor) + ".csv", text, names);
+            }
+            if (merge) {
+                std::vector<std::string> lines;
+                for (const auto& kv : merged) {
+                    if (!compounds_written.insert(kv.first).second) continue;
+                    std::string l = kv.second.written;
+                    for (uint64_t c : kv.second.counts) l += "," + std::to_string(c);
+                    lines.push_back(l);
+                }
+                std::sort(lines.begin(), lines.end());
+                std::string text = merged_header;
+                for (const std::string& l : lines) text += l + "\n";
+                write_text(dir, pre + "_counts.all" + (descriptor.empty() ? "" : "." + descriptor) + ".csv", text, names);
+            }
+        };
+
+        emit(rows, true, "");
+        if (do_enrich) {
+            if (bc_enrich(ctx, &singles, nb > 2 ? &doubles : nullptr) != BC_OK) throw Error(bc_last_error(ctx));
+            std::vector<DecodedRow> srows, drows;
+            decode_rows(*run, ctx, singles, srows);
+            emit(srows, false, "Single");
+            if (nb > 2) {  // output.rs:176-178
+                decode_rows(*run, ctx, doubles, drows);
+                emit(drows, false, "Double");
+            }
+        }
+        if (names_out && names_len > 0) {
+            std::string joined;
+            for (const std::string& n : names) joined += n + "\n";
+            snprintf(names_out, (size_t)names_len, "%s", joined.c_str());
+        }
+        bc_table_free(&full);
+        bc_table_free(&singles);
+        bc_table_free(&doubles);
+        return (int)names.size();
+    } catch (const std::exception& e) {
+        bc_table_free(&full);
+        bc_table_free(&singles);
+        bc_table_free(&doubles);
+        report(e.what());
+        return BC_EINVAL;
+    }
+}
+
+}  // extern "C"

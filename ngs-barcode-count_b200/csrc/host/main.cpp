@@ -1,0 +1,183 @@
+// main.cpp — `barcode-count` for B200: the reference's command line (arguments.rs:27-124) over the GPU path.
+// Same flags, same input files, same output CSV set; the per-read work runs in the CUDA library (bc_b200.h).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <thread>
+
+#include "../../../include/bc_host.h"
+
+static void usage() {
+    fprintf(stderr,
+            "NGS-Barcode-Count (B200 decode-and-count path)\n"
+            "Counts barcodes located in sequencing data\n\n"
+            "USAGE:\n    barcode-count [FLAGS] [OPTIONS] --fastq <fastq> --sequence-format <format_file>\n\n"
+            "FLAGS:\n"
+            "    -e, --enrich          Create output files of enrichment for single and double synthons/barcodes\n"
+            "    -m, --merge-output    Merge sample output counts into a single file\n"
+            "    -h, --help\n    -V, --version\n\n"
+            "OPTIONS:\n"
+            "    -c, --counted-barcodes <barcode_file>    Counted barcodes file\n"
+            "    -o, --output-dir <dir>                   Directory to output the counts to [default: ./]\n"
+            "    -f, --fastq <fastq>                      FastQ file\n"
+            "    -q, --sequence-format <format_file>      Sequence format file\n"
+            "        --max-errors-counted-barcode <n>     Maximimum number of sequence errors allowed within each counted barcode\n"
+            "        --max-errors-constant <n>            Maximimum number of sequence errors allowed within constant region\n"
+            "        --max-errors-sample <n>              Maximimum number of sequence errors allowed within sample barcode\n"
+            "        --min-quality <min>                  Minimum average read quality score per barcode [default: 0]\n"
+            "    -p, --prefix <prefix>                    File prefix name [default: today's date]\n"
+            "    -s, --sample-barcodes <sample_file>      Sample barcodes file\n"
+            "    -t, --threads <threads>                  Number of host threads (FASTQ parse + pack)\n"
+            "        --device <n>                         CUDA device [default: 0]\n"
+            "        --max-read-length <n>                Longest read in the FASTQ [default: max(160, 2 x scheme length)]\n"
+            "        --batch-reads <n>                    Reads per GPU batch [default: 1048576]\n");
+}
+
+static std::string thousands(unsigned long long v) {
+    std::string d = std::to_string(v), out;
+    for (size_t i = 0; i < d.size(); i++) {
+        out.push_back(d[i]);
+        const size_t left = d.size() - 1 - i;
+        if (left && left % 3 == 0) out.push_back(',');
+    }
+    return out;
+}
+
+static std::string hms(double secs) {
+    const long ms = (long)(secs * 1000.0 + 0.5);
+    char buf[96];
+    snprintf(buf, sizeof buf, "%ld hours, %ld minutes, %ld.%03ld seconds", ms / 3600000, (ms / 60000) % 60, (ms / 1000) % 60, ms % 1000);
+    return buf;
+}
+
+int main(int argc, char** argv) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string fastq, format, samples, counted, outdir = "./", prefix;
+    int max_b = -1, max_s = -1, max_c = -1, device = 0;
+    float min_quality = 0.f;
+    bool merge = false, enrich = false;
+    unsigned threads = std::thread::hardware_concurrency();
+    unsigned max_read_len = 0, batch_reads = 1u << 20;
+    {
+        char buf[32];
+        const time_t now = time(nullptr);
+        strftime(buf, sizeof buf, "%Y-%m-%d", localtime(&now));
+        prefix = buf;
+    }
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> const char* {
+            if (i + 1 >= argc) {
+                fprintf(stderr, "error: The argument '%s' requires a value but none was supplied\n", a.c_str());
+                exit(2);
+            }
+            return argv[++i];
+        };
+        auto num = [&](const char* what) -> int {
+            const char* v = val();
+            char* end = nullptr;
+            const long x = strtol(v, &end, 10);
+            if (!*v || *end || x < 0 || x > 65535) {
+                fprintf(stderr, "Error: Unable to convert %s to an integer\n", what);
+                exit(1);
+            }
+            return (int)x;
+        };
+        if (a == "-f" || a == "--fastq") fastq = val();
+        else if (a == "-q" || a == "--sequence-format") format = val();
+        else if (a == "-s" || a == "--sample-barcodes") samples = val();
+        else if (a == "-c" || a == "--counted-barcodes") counted = val();
+        else if (a == "-t" || a == "--threads") threads = (unsigned)num("threads");
+        else if (a == "-o" || a == "--output-dir") outdir = val();
+        else if (a == "-p" || a == "--prefix") prefix = val();
+        else if (a == "-m" || a == "--merge-output") merge = true;
+        else if (a == "-e" || a == "--enrich") enrich = true;
+        else if (a == "--max-errors-counted-barcode") max_b = num("maximum barcode errors");
+        else if (a == "--max-errors-sample") max_s = num("maximum sample errors");
+        else if (a == "--max-errors-constant") max_c = num("maximum constant errors");
+        else if (a == "--min-quality") {
+            const char* v = val();
+            char* end = nullptr;
+            min_quality = strtof(v, &end);
+            if (!*v || *end) {
+                fprintf(stderr, "Error: Unable to convert min score to a float\n");
+                return 1;
+            }
+        } else if (a == "--device") device = num("device");
+        else if (a == "--max-read-length") max_read_len = (unsigned)num("max read length");
+        else if (a == "--batch-reads") batch_reads = (unsigned)strtoul(val(), nullptr, 10);
+        else if (a == "-h" || a == "--help") { usage(); return 0; }
+        else if (a == "-V" || a == "--version") { printf("NGS-Barcode-Count 0.11.1-b200\n"); return 0; }
+        else {
+            fprintf(stderr, "error: Found argument '%s' which wasn't expected\n", a.c_str());
+            usage();
+            return 2;
+        }
+    }
+    if (fastq.empty() || format.empty()) {
+        fprintf(stderr, "error: The following required arguments were not provided:\n    --fastq <fastq>\n    --sequence-format <format_file>\n");
+        return 2;
+    }
+    char err[2048] = "";
+    bch_args args{};
+    args.format_path = format.c_str();
+    args.sample_barcodes_path = samples.empty() ? nullptr : samples.c_str();
+    args.counted_barcodes_path = counted.empty() ? nullptr : counted.c_str();
+    args.max_errors_counted_barcode = max_b;
+    args.max_errors_sample = max_s;
+    args.max_errors_constant = max_c;
+    args.min_quality = min_quality;
+    args.max_read_len = max_read_len;
+    bch_run* run = bch_open(&args, err, sizeof err);
+    if (!run) {
+        fprintf(stderr, "Error: %s\n", err);
+        return 1;
+    }
+    printf("%s\n", bch_describe(run));
+    if (enrich && bch_barcode_num(run) < 2) {  // main.rs:22-25
+        fprintf(stderr, "Fewer than 2 counted barcodes.  Too few for barcode enrichment.  Argument flag is ignored\n");
+        enrich = false;
+    }
+    bc_ctx* ctx = nullptr;
+    if (bc_create(bch_config(run), device, 0, &ctx) != BC_OK) {
+        fprintf(stderr, "Error: %s\n", bc_last_error(nullptr));
+        bch_close(run);
+        return 1;
+    }
+    uint64_t total = 0;
+    if (bch_count_fastq(run, ctx, fastq.c_str(), threads, batch_reads, &total, err, sizeof err) != BC_OK) {
+        fprintf(stderr, "Error: %s\n", err);
+        bc_destroy(ctx);
+        bch_close(run);
+        return 1;
+    }
+    uint64_t c[BC_N_COUNTERS] = {0};
+    bc_get_counters(ctx, c);
+    printf("Total sequences:             %s\n", thousands(total).c_str());
+    printf("Correctly matched sequences: %s\nConstant region mismatches:  %s\nSample barcode mismatches:   %s\n"
+           "Counted barcode mismatches:  %s\nDuplicates:                  %s\nLow quality barcodes:        %s\n",
+           thousands(c[BC_CNT_MATCHED]).c_str(), thousands(c[BC_CNT_CONSTANT]).c_str(), thousands(c[BC_CNT_SAMPLE]).c_str(),
+           thousands(c[BC_CNT_COUNTED]).c_str(), thousands(c[BC_CNT_DUPLICATES]).c_str(), thousands(c[BC_CNT_LOW_QUALITY]).c_str());
+    if (c[BC_CNT_UNSUPPORTED])
+        fprintf(stderr, "WARNING: %s reads hold characters outside A/C/G/T/N and were not decoded (the reference treats such "
+                        "characters as plain mismatching symbols)\n", thousands(c[BC_CNT_UNSUPPORTED]).c_str());
+    const auto t1 = std::chrono::steady_clock::now();
+    printf("\nCompute time: %s\n\n-WRITING COUNTS-\n", hms(std::chrono::duration<double>(t1 - t0).count()).c_str());
+    static char names[1 << 20];
+    const int nfiles = bch_write_counts(run, ctx, outdir.c_str(), prefix.c_str(), merge, enrich, names, sizeof names, err, sizeof err);
+    if (nfiles < 0) {
+        fprintf(stderr, "Error: %s\n", err);
+        bc_destroy(ctx);
+        bch_close(run);
+        return 1;
+    }
+    printf("%s", names);
+    const auto t2 = std::chrono::steady_clock::now();
+    printf("\nTotal time: %s\n", hms(std::chrono::duration<double>(t2 - t0).count()).c_str());
+    bc_destroy(ctx);
+    bch_close(run);
+    return 0;
+}
