@@ -1,0 +1,11 @@
+"""Import shim: the package directory is `ngs-barcode-count_b200/` (hyphens are not importable), so
+`import ngs_barcode_count_b200` loads it from there."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ngs-barcode-count_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA decode-and-count path, called through the C ABI (include/bc_b200.h, bc_host.h), against
+the committed golden fixtures (tests/golden/, produced by the Python mirror of the reference) and against the CPU
+oracle (oracle/) on seeded random inputs.  Bit-exact: per-read status / offset / repaired flag / decoded barcodes,
+the outcome counters and the canonical CSV set must all be equal."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import ngs_barcode_count_b200 as bc
+from helpers import (GOLDEN, Oracle, assert_same_csv_set, golden_cases, load_golden, read_csv_dir, read_fastq)
+
+pytestmark = pytest.mark.gpu
+
+ORACLE_TO_GPU_STATUS = {"matched": "matched", "duplicate": "matched", "constant_region": "constant_region",
+                        "low_quality": "low_quality", "sample_barcode": "sample_barcode", "barcode": "barcode"}
+
+
+def make_run(paths, fl, **kw):
+    return bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"],
+                  max_barcode=fl["max_barcode"], max_sample=fl["max_sample"], max_constant=fl["max_constant"], **kw)
+
+
+def decoded_strings(run, ctr, lo, hi):
+    """(sample, 'b1,b2,..', random) of one matched read, as the oracle reports them."""
+    per_slot = ctr.key_decode(lo, hi, with_umi=True)
+    sample, counted, rnd = "barcode", [], None
+    for s in range(run.n_slots):
+        kind = chr(run.slot(s).kind)
+        if kind == "S":
+            sample = per_slot[s]
+        elif kind == "B":
+            counted.append(per_slot[s])
+        else:
+            rnd = per_slot[s]
+    return sample, ",".join(counted), rnd
+
+
+def check_reads_against(run, ctr, reads, outcomes):
+    batch = run.pack([r[0] for r in reads], [r[1] for r in reads])
+    got = ctr.decode_only(batch)
+    st, off, rep = ctr.locate_only(batch)
+    for i, want in enumerate(outcomes):
+        g_status = bc.STATUS_NAMES[got["status"][i]]
+        assert g_status == ORACLE_TO_GPU_STATUS[want["status"]], (i, g_status, want, reads[i][0])
+        located = want["offset"] >= 0
+        assert (st[i] == 0) == located, (i, want)
+        assert off[i] == want["offset"] and bool(rep[i]) == want["repaired"], (i, off[i], rep[i], want)
+        assert got["offset"][i] == want["offset"] and bool(got["repaired"][i]) == want["repaired"], (i, want)
+        if want["status"] in ("matched", "duplicate"):
+            assert decoded_strings(run, ctr, got["key_lo"][i], got["key_hi"][i]) == (
+                want["sample"], want["barcodes"], want["random"]), (i, want)
+    return batch
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_per_read_and_csv(case, tmp_path):
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run)
+    reads = read_fastq(paths["fastq"])
+    batch = check_reads_against(run, ctr, reads, exp["outcomes"])
+    # hooks do not count
+    assert sum(ctr.counters().values()) == 0
+    # count in three uneven batches (the last one a single read), then compare counters and files
+    n = batch.n
+    for a, b in ((0, n // 3), (n // 3, n - 1), (n - 1, n)):
+        ctr.submit(batch.slice(a, b))
+    c = ctr.counters()
+    assert c.pop("unsupported") == 0
+    assert c == exp["counters"]
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+    # reset clears everything; a second pass gives the same answer
+    ctr.reset()
+    assert sum(ctr.counters().values()) == 0
+    ctr.submit(batch)
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_fastq_ingest_small_batches(case, tmp_path):
+    """bch_count_fastq (the read_fastq replacement) with batches far smaller than the file: pinned double
+    buffering, staging reuse and table growth are all exercised."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run)
+    total = ctr.count_fastq(paths["fastq"], threads=2, batch_reads=37)
+    assert total == len(exp["outcomes"])
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+
+
+@pytest.mark.parametrize("case", ["example", "crispr", "del3_umi", "lineage_raw"])
+@pytest.mark.parametrize("gz", [False, True])
+def test_cli_drop_in(case, gz, tmp_path):
+    """The `barcode-count` binary with the reference's flags writes the reference's CSV set."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    fastq = paths["fastq"]
+    if gz:
+        import gzip
+        fastq = str(tmp_path / "reads.fastq.gz")
+        data = open(paths["fastq"], "rb").read()
+        half = data.find(b"\n@", len(data) // 2) + 1
+        with open(fastq, "wb") as f:  # two concatenated gzip members (MultiGzDecoder, input.rs:63)
+            f.write(gzip.compress(data[:half]))
+            f.write(gzip.compress(data[half:]))
+    out = tmp_path / "out"
+    out.mkdir()
+    cmd = [bc.CLI_PATH, "--fastq", fastq, "--sequence-format", paths["fmt"], "--output-dir", str(out), "--prefix", "golden",
+           "--threads", "2", "--min-quality", str(fl["min_quality"])]
+    if paths["samples"]:
+        cmd += ["--sample-barcodes", paths["samples"]]
+    if paths["counted"]:
+        cmd += ["--counted-barcodes", paths["counted"]]
+    if fl["merge"]:
+        cmd.append("--merge-output")
+    if fl["enrich"]:
+        cmd.append("--enrich")
+    for flag, key in (("--max-errors-counted-barcode", "max_barcode"), ("--max-errors-sample", "max_sample"),
+                      ("--max-errors-constant", "max_constant")):
+        if fl[key] is not None:
+            cmd += [flag, str(fl[key])]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert_same_csv_set(read_csv_dir(str(out), "golden"), exp["files"])
+    c = exp["counters"]
+    assert f"Correctly matched sequences: {c['matched']:,}" in r.stdout
+    assert f"Constant region mismatches:  {c['constant_region']:,}" in r.stdout
+    assert f"Duplicates:                  {c['duplicates']:,}" in r.stdout
+
+
+# ---- hand-derived vectors on the reference's example files ------------------------------
+SAMPLE, C1, B1, C2, B2, C3, B3, C4, UMI, C5 = ("AGCATACGGG", "AGCTACGAATCG", "CAGAGA", "TGGA", "ATGAAA", "TGGA",
+                                               "GATAGC", "ACTAGAT", "ACGTACGT", "TAGA")
+G1 = SAMPLE + C1 + B1 + C2 + B2 + C3 + B3 + C4 + UMI + C5
+ROW = "CAGAGAC,ATGAAAT,GATAGCT"
+EX = os.path.join(GOLDEN, "example")
+
+
+def example(min_quality=0.0):
+    run = bc.Run(os.path.join(EX, "scheme.txt"), os.path.join(EX, "samples.csv"), os.path.join(EX, "barcodes.csv"),
+                 min_quality=min_quality)
+    return run, bc.Counter(run)
+
+
+def one(run, ctr, seq, qual=None):
+    qual = qual or "I" * len(seq)
+    got = ctr.decode_only(run.pack([seq], [qual]))
+    status = bc.STATUS_NAMES[got["status"][0]]
+    strings = decoded_strings(run, ctr, got["key_lo"][0], got["key_hi"][0]) if status == "matched" else None
+    return status, int(got["offset"][0]), bool(got["repaired"][0]), strings
+
+
+def test_hand_vectors():
+    run, ctr = example()
+    assert one(run, ctr, G1 + "A") == ("matched", 0, False, ("AGCATAC", ROW, UMI))  # G1
+    assert one(run, ctr, G1.replace(B1, "CAGTGA", 1) + "A")[3][1] == ROW  # G3: d=1 corrected
+    assert one(run, ctr, G1.replace(B1, "CTGTGA", 1) + "A")[0] == "barcode"  # G4: d=2 rejected
+    assert one(run, ctr, "AACATAC" + G1[7:] + "A")[0] == "sample_barcode"  # G5: tie
+    bad = G1.replace(C1, "AGCTACGTATCG", 1)
+    assert one(run, ctr, "TTTTT" + bad + "A") == ("matched", 5, True, ("AGCATAC", ROW, UMI))  # G6
+    assert one(run, ctr, "TTTTT" + bad)[0] == "constant_region"  # G7 (Q3): last offset not repaired
+    assert one(run, ctr, "TTTTT" + G1)[:3] == ("matched", 5, False)  # ... but matched exactly there
+    assert one(run, ctr, bad)[0] == "constant_region"  # R == L
+    assert one(run, ctr, G1.replace(C1, "AGCTANGAATCG", 1) + "A") == ("matched", 0, True, ("AGCATAC", ROW, UMI))  # G8
+    assert one(run, ctr, G1[:40])[0] == "constant_region"  # shorter than the scheme (Q4 fenced off)
+    assert one(run, ctr, G1.replace("G", "g", 1) + "A")[0] == "unsupported"
+    # G2: UMI duplicate through the counting path
+    b = run.pack([G1 + "A", G1 + "A", G1 + "C"])
+    ctr.submit(b)
+    c = ctr.counters()
+    assert (c["matched"], c["duplicates"]) == (1, 2)
+    rows = ctr.finish()
+    assert list(rows["count"]) == [1]
+
+
+def test_quality_window_after_repair_q6():
+    read = "TTTTT" + G1.replace(C1, "AGCTACGTATCG", 1) + "A"
+    run, ctr = example(min_quality=20.0)
+    assert one(run, ctr, read, "#" * 10 + "I" * (len(read) - 10))[0] == "low_quality"
+    assert one(run, ctr, read, "I" * 5 + "#" * 4 + "I" * (len(read) - 9))[0] == "matched"
+
+
+def test_empty_batch_and_empty_table(tmp_path):
+    run, ctr = example()
+    ctr.submit(run.pack([]))
+    assert sum(ctr.counters().values()) == 0
+    assert ctr.finish()["count"].size == 0
+    names = ctr.write_counts(str(tmp_path), "t", merge=True, enrich=True)
+    files = read_csv_dir(str(tmp_path), "t")
+    assert files["t_Sample_name_1_counts.csv"] == ["Barcode_1,Barcode_2,Barcode_3,Count"]  # Q16
+    assert "t_counts.all.csv" in names
+
+
+# ---- seeded random schemes and reads against the oracle ---------------------------------------------------------
+def rand_dna(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def mutate(rng, s, p_sub, p_n):
+    out = []
+    for ch in s:
+        u = rng.random()
+        if u < p_n:
+            out.append("N")
+        elif u < p_n + p_sub:
+            out.append(rng.choice("ACGT"))
+        else:
+            out.append(ch)
+    return "".join(out)
+
+
+def random_case(rng, tmp_path, idx):
+    """A random scheme with its conversion files and reads; exercises ties, N, raw slots, mixed lengths."""
+    pieces, kinds = [], []
+    n_counted = rng.randint(1, 3)
+    layout = ["S"] * rng.randint(0, 1) + ["B"] * n_counted + ["R"] * rng.randint(0, 1)
+    rng.shuffle(layout)
+    scheme = ""
+    slot_lens = []
+    for k, kind in enumerate(layout):
+        if k > 0 or rng.random() < 0.8:
+            if k == 0 or rng.random() < 0.85:  # sometimes two barcodes touch
+                c = rand_dna(rng, rng.randint(3, 14))
+                scheme += c
+        ln = rng.choice([4, 5, 6, 8, 10, 12, 16, 20] if kind != "R" else [4, 6, 8, 10, 12])
+        slot_lens.append(ln)
+        scheme += {"S": "[%d]", "B": "{%d}", "R": "(%d)"}[kind] % ln
+    if rng.random() < 0.8:
+        scheme += rand_dna(rng, rng.randint(3, 12))
+    if not any(ch in "ACGT" for ch in scheme):
+        scheme = "ACGTTGCA" + scheme
+    fmt = tmp_path / f"scheme{idx}.txt"
+    fmt.write_text(scheme + "\n")
+    # reference sets: close neighbours on purpose so that ties and corrections happen
+    def make_set(ln, n):
+        base = [rand_dna(rng, ln) for _ in range(max(1, n // 3))]
+        out = set(base)
+        while len(out) < n:
+            out.add(mutate(rng, rng.choice(base), 0.25, 0.0))
+        return sorted(out)
+    samples_path = counted_path = None
+    sample_set, counted_sets = None, None
+    if "S" in layout and rng.random() < 0.7:
+        ln = slot_lens[layout.index("S")]
+        sample_set = make_set(ln, rng.randint(2, 12))
+        samples_path = tmp_path / f"samples{idx}.csv"
+        samples_path.write_text("Barcode,Sample_ID\n" + "".join(f"{d},S{j}\n" for j, d in enumerate(sample_set)))
+    if rng.random() < 0.75:
+        counted_sets = []
+        lines = ["Barcode,Barcode_ID,Barcode_Number"]
+        for k, s in enumerate(i for i, kd in enumerate(layout) if kd == "B"):
+            st = make_set(slot_lens[s], rng.randint(2, 40))
+            counted_sets.append(st)
+            lines += [f"{d},B{k}_{j},{k + 1}" for j, d in enumerate(st)]
+        counted_path = tmp_path / f"counted{idx}.csv"
+        counted_path.write_text("\n".join(lines) + "\n")
+    # template instance builder
+    import re
+    tokens = re.findall(r"\{\d+\}|\[\d+\]|\(\d+\)|[ACGT]+", scheme)
+    L = sum(int(t[1:-1]) if t[0] in "{[(" else len(t) for t in tokens)
+    reads = []
+    R = L + rng.randint(1, 40)
+    for _ in range(600):
+        body, k = "", 0
+        for t in tokens:
+            if t[0] == "[":
+                body += rng.choice(sample_set) if sample_set and rng.random() < 0.9 else rand_dna(rng, int(t[1:-1]))
+            elif t[0] == "{":
+                st = counted_sets[k] if counted_sets else None
+                body += rng.choice(st) if st and rng.random() < 0.9 else rand_dna(rng, int(t[1:-1]))
+                k += 1
+            elif t[0] == "(":
+                body += rand_dna(rng, int(t[1:-1]), "ACGGT")
+            else:
+                body += t
+        u = rng.random()
+        if u < 0.08:
+            seq = rand_dna(rng, R)
+        else:
+            start = rng.randint(0, R - L)
+            seq = rand_dna(rng, start) + mutate(rng, body, rng.choice([0.0, 0.01, 0.04]), rng.choice([0.0, 0.01])) + rand_dna(rng, R - L - start)
+            if rng.random() < 0.05:
+                seq = seq[:rng.randint(max(1, L - 5), R)]  # ragged lengths, some shorter than the scheme
+        qual = "".join(chr(33 + max(2, min(40, int(rng.gauss(30, 8))))) for _ in seq)
+        reads.append((seq, qual))
+    return dict(fmt=str(fmt), samples=str(samples_path) if samples_path else None,
+                counted=str(counted_path) if counted_path else None), reads, len(layout) - layout.count("R") - layout.count("S")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_schemes_against_oracle(seed, tmp_path):
+    rng = random.Random(1000 + seed)
+    paths, reads, n_counted = random_case(rng, tmp_path, seed)
+    min_q = rng.choice([0.0, 0.0, 20.0, 27.5])
+    caps = dict(max_barcode=rng.choice([None, None, 0, 2]), max_sample=rng.choice([None, None, 1]),
+                max_constant=rng.choice([None, None, 1, 4]))
+    merge, enrich = rng.random() < 0.5, rng.random() < 0.6
+    o_dir, g_dir = tmp_path / "o", tmp_path / "g"
+    o_dir.mkdir()
+    g_dir.mkdir()
+    orc = Oracle(paths["fmt"], paths["samples"], paths["counted"], min_quality=min_q, merge=merge, enrich=enrich,
+                 outdir=str(o_dir), prefix="p", **caps)
+    # the fenced-off reference behaviour (Q4: reads shorter than the scheme underflow in the reference) is
+    # defined by the oracle as constant_region_error, like the GPU path
+    outcomes = [orc.process(s, q) for s, q in reads]
+    run = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=min_q, **caps)
+    ctr = bc.Counter(run)
+    batch = check_reads_against(run, ctr, reads, outcomes)
+    ctr.submit(batch)
+    c = ctr.counters()
+    assert c.pop("unsupported") == 0
+    assert c == orc.counters()
+    orc.write_files()
+    ctr.write_counts(str(g_dir), "p", merge=merge, enrich=enrich and n_counted >= 2)
+    assert_same_csv_set(read_csv_dir(str(g_dir), "p"), read_csv_dir(str(o_dir), "p"))
+
+
+def test_device_resident_batch_and_caller_stream():
+    import torch
+    exp, paths = load_golden("del3_umi")
+    run = make_run(paths, exp["flags"])
+    ctr = bc.Counter(run)
+    stream = torch.cuda.Stream()
+    ctr.set_stream(stream.cuda_stream)
+    reads = read_fastq(paths["fastq"])
+    dev = run.pack([r[0] for r in reads], [r[1] for r in reads]).to_device()
+    with torch.cuda.stream(stream):
+        ctr.submit(dev)
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    assert ctr.profile()["h2d_bytes"] == 0
+
+
+def test_table_growth_and_many_keys():
+    """Raw 30-mer keys + UMI: 126-bit records, tables start tiny (expected_reads=0 -> growth by rehash)."""
+    exp, paths = load_golden("lineage_raw")
+    run = make_run(paths, exp["flags"])
+    rng = random.Random(7)
+    reads = read_fastq(paths["fastq"])
+    tmpl = [r for r, o in zip(reads, exp["outcomes"]) if o["status"] == "matched" and not o["repaired"]][0][0]
+    off = [o for o in exp["outcomes"] if o["status"] == "matched" and not o["repaired"]][0]["offset"]
+    seqs, want = [], {}
+    n = 6000
+    for i in range(n):
+        key, umi = rand_dna(rng, 30), rand_dna(rng, 12)
+        s = tmpl[:off + 20] + key + tmpl[off + 50:off + 60] + umi + tmpl[off + 72:]
+        reps = rng.randint(1, 3)
+        for _ in range(reps):
+            seqs.append(s)
+        want[key] = want.get(key, 0) + 1
+    ctr = bc.Counter(run, expected_reads=0)
+    batch = run.pack(seqs)
+    for a in range(0, batch.n, 1000):
+        ctr.submit(batch.slice(a, min(batch.n, a + 1000)))
+    c = ctr.counters()
+    assert c["matched"] == n and c["duplicates"] == len(seqs) - n
+    rows = ctr.finish()
+    got = {}
+    for lo, hi, cnt in zip(rows["key_lo"], rows["key_hi"], rows["count"]):
+        got[ctr.key_decode(lo, hi)[0]] = int(cnt)
+    assert got == want
