@@ -1,0 +1,71 @@
+"""The synthetic workloads (bench tooling): barcode-set construction and host generator on the CPU, and on the GPU the
+device generator against the host one plus oracle parity of the whole job on every BASELINE.json workload."""
+import numpy as np
+import pytest
+
+import ngs_barcode_count_b200 as bc
+from ngs_barcode_count_b200 import synth
+from helpers import Oracle, assert_same_csv_set, read_csv_dir
+
+
+def test_hamming_sets_have_distance_3():
+    rng = np.random.default_rng(5)
+    w = synth.hamming_code_words(8, 1024, rng)
+    assert len({bytes(x) for x in w}) == 1024
+    d = (w[:, None, :] != w[None, :, :]).sum(-1)
+    np.fill_diagonal(d, 99)
+    assert d.min() == 3
+    g = synth.hamming_code_words(20, 80_000, rng)
+    assert len({bytes(x) for x in g}) == 80_000
+    sub = g[rng.permutation(80_000)[:1500]]
+    d = (sub[:, None, :] != sub[None, :, :]).sum(-1)
+    np.fill_diagonal(d, 99)
+    assert d.min() >= 3
+
+
+@pytest.mark.parametrize("name", ["example", "crispr", "del3", "lineage"])
+def test_host_generator_is_deterministic_and_well_formed(name, tmp_path):
+    wl = synth.Workload(name, str(tmp_path / name), reads=10_000)
+    a = wl.generate_fastq(100, 300, threads=1).tobytes()
+    b = wl.generate_fastq(0, 1000, threads=3).tobytes()
+    assert len(a) == wl.fastq_bytes(100, 300) and len(b) == wl.fastq_bytes(0, 1000)
+    lines = b.decode().split("\n")
+    assert lines[-1] == "" and len(lines) == 4001
+    assert a.decode().split("\n")[:4] == lines[400:404]  # read 100 is the same whatever the range / thread count
+    for i in range(0, 4000, 4):
+        assert lines[i] == f"@r{i // 4}" and lines[i + 2] == "+"
+        assert len(lines[i + 1]) == wl.read_len == len(lines[i + 3])
+        assert set(lines[i + 1]) <= set("ACGTN")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["example", "crispr", "del3", "lineage"])
+def test_device_generator_equals_host_and_job_equals_oracle(name, tmp_path):
+    import torch
+    n = 20_000
+    wl = synth.Workload(name, str(tmp_path / name), reads=n)
+    run = wl.run(bc)
+    text = wl.generate_fastq(0, n, threads=4).tobytes().decode().split("\n")
+    seqs, quals = text[1::4], text[3::4]
+    host = run.pack(seqs, quals)
+    dev = wl.generate_device(run, 0, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.planes.cpu().numpy().view(np.uint32), host.planes)
+    assert np.array_equal(dev.read_len.cpu().numpy().view(np.uint16), host.read_len)
+    if run.quality_on:
+        assert np.array_equal(dev.qual.cpu().numpy(), host.qual)
+    # whole job on the device batch vs the oracle on the text
+    ctr = bc.Counter(run, expected_reads=n)
+    ctr.submit(dev)
+    got = ctr.counters()
+    o_dir, g_dir = tmp_path / "o", tmp_path / "g"
+    o_dir.mkdir()
+    g_dir.mkdir()
+    orc = Oracle(wl.fmt, wl.samples, wl.counted, min_quality=wl.min_quality, merge=wl.merge, enrich=wl.enrich,
+                 outdir=str(o_dir), prefix="p")
+    orc.process_block(seqs, quals)
+    assert got.pop("unsupported") == 0 and got == orc.counters()
+    assert got["matched"] > n // 2
+    orc.write_files()
+    ctr.write_counts(str(g_dir), "p", merge=wl.merge, enrich=wl.enrich)
+    assert_same_csv_set(read_csv_dir(str(g_dir), "p"), read_csv_dir(str(o_dir), "p"))
