@@ -55,7 +55,14 @@ struct bc_ctx {
     uint16_t* d_tables = nullptr;
     unsigned long long* d_hash_keys = nullptr;
     uint32_t* d_hash_idx = nullptr;
+    unsigned long long* d_half = nullptr;
+    DevDeep* d_deep = nullptr;
+    uint32_t* d_csr = nullptr;
     DevAux aux{};
+    // reads of the batch in flight whose barcode step needs a search (filled by k_decode, drained by k_resolve)
+    uint2* d_def_items = nullptr;
+    uint32_t* d_def_count = nullptr;
+    uint64_t def_cap = 0;
     // main table
     DevTable table{};
     unsigned long long table_capacity = 0;
@@ -325,6 +332,11 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_hash_keys) cudaFree(ctx->d_hash_keys);
     if (ctx->d_hash_idx) cudaFree(ctx->d_hash_idx);
+    if (ctx->d_half) cudaFree(ctx->d_half);
+    if (ctx->d_deep) cudaFree(ctx->d_deep);
+    if (ctx->d_csr) cudaFree(ctx->d_csr);
+    if (ctx->d_def_items) cudaFree(ctx->d_def_items);
+    if (ctx->d_def_count) cudaFree(ctx->d_def_count);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -420,6 +432,18 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         }
     }
 
+    {  // locate prefilter: the template word with the most constant bases
+        int bestw = 0, bestc = -1;
+        for (uint32_t w = 0; w < d.TW; w++) {
+            const int c = __builtin_popcount(d.t_cm[w]);
+            if (c > bestc) {
+                bestc = c;
+                bestw = (int)w;
+            }
+        }
+        d.pivot = (uint32_t)bestw;
+    }
+
     // ---- quality runs (parse.rs:340-374): maximal runs of one region code; a non-constant run is tested only when
     // another code follows it inside the walked range (Q8); format-N shortens the code string (Q9)
     if (ctx->quality_on) {
@@ -469,6 +493,9 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     std::vector<uint4> refs;
     std::vector<unsigned long long> hkeys;
     std::vector<uint32_t> hidx;
+    std::vector<unsigned long long> half;
+    std::vector<DevDeep> deep;
+    std::vector<uint32_t> csr;
     size_t table_u16 = 0;
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         const bc_slot& S = cfg->slots[s];
@@ -482,7 +509,7 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         if (S.n_ref == 0) continue;
         if (!S.ref_seqs) FAILC(BC_EINVAL, "slot %u: ref_seqs is NULL", s);
         D.ref_off = (uint32_t)refs.size();
-        bool any_exactable = false;
+        bool any_exactable = false, indexable = true;
         for (uint32_t i = 0; i < S.n_ref; i++) {
             const char* r = S.ref_seqs[i];
             const size_t rl = r ? strlen(r) : 0;
@@ -500,6 +527,7 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
                 }
             }
             if (rl == S.len && v.z == 0) any_exactable = true;
+            else indexable = false;
             refs.push_back(v);
         }
         if (S.len <= 10 && S.n_ref < 0xFFFFu) {
@@ -522,6 +550,57 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
                 hkeys[D.aux_off + h] = k;
                 hidx[D.aux_off + h] = i;  // identical strings cannot repeat in a set; the last one wins like a map insert
             }
+            if (indexable) {
+                // half index: every reference within distance 1 of a query shares one of its halves
+                D.has_half = 1;
+                D.half_len0 = (uint16_t)(S.len / 2);
+                D.half_off = (uint32_t)half.size();
+                D.half_mask = (uint32_t)(cap - 1);
+                half.resize(half.size() + 2 * cap, kEmpty);
+                for (uint32_t i = 0; i < S.n_ref; i++) {
+                    const uint4 v = refs[D.ref_off + i];
+                    for (int hh = 0; hh < 2; hh++) {
+                        const uint32_t pos0 = hh ? D.half_len0 : 0u, hl = hh ? (uint32_t)S.len - D.half_len0 : (uint32_t)D.half_len0;
+                        const uint32_t hm = hl >= 32 ? 0xFFFFFFFFu : ((1u << hl) - 1u);
+                        const uint32_t key = ((v.x >> pos0) & hm) | (((v.y >> pos0) & hm) << 16);
+                        uint32_t x = key;  // mix32 of bc_kernels.cu
+                        x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+                        size_t pos = x & D.half_mask;
+                        unsigned long long* tab = half.data() + D.half_off + (hh ? cap : 0);
+                        while (tab[pos] != kEmpty) pos = (pos + 1) & D.half_mask;
+                        tab[pos] = (unsigned long long)key | ((unsigned long long)i << 32);
+                    }
+                }
+                // block index: max_err+1 blocks, bucketed by (up to) the first kMaxBlockKey bases of each block
+                const uint32_t P = (uint32_t)S.max_err + 1u;
+                if (P <= (uint32_t)kMaxBlocks && S.len / P >= 3 && S.n_ref >= 256) {
+                    DevDeep dd{};
+                    D.n_blocks = (uint8_t)P;
+                    D.deep_off = (uint32_t)deep.size();
+                    for (uint32_t p = 0; p < P; p++) {
+                        const uint32_t b0 = p * S.len / P, b1 = (p + 1) * S.len / P;
+                        const uint32_t kl = std::min<uint32_t>(b1 - b0, kMaxBlockKey);
+                        dd.key_pos[p] = (uint8_t)b0;
+                        dd.key_len[p] = (uint8_t)kl;
+                        const uint32_t nb = 1u << (2 * kl), km = (1u << kl) - 1u;
+                        dd.start_off[p] = (uint32_t)csr.size();
+                        csr.resize(csr.size() + nb + 1, 0u);
+                        dd.ids_off[p] = (uint32_t)csr.size();
+                        csr.resize(csr.size() + S.n_ref, 0u);
+                        uint32_t* start = csr.data() + dd.start_off[p];
+                        uint32_t* ids = csr.data() + dd.ids_off[p];
+                        auto bucket = [&](uint32_t i) {
+                            const uint4 v = refs[D.ref_off + i];
+                            return ((v.x >> b0) & km) | (((v.y >> b0) & km) << kl);
+                        };
+                        for (uint32_t i = 0; i < S.n_ref; i++) start[bucket(i) + 1]++;
+                        for (uint32_t b = 0; b < nb; b++) start[b + 1] += start[b];
+                        std::vector<uint32_t> fill(start, start + nb);
+                        for (uint32_t i = 0; i < S.n_ref; i++) ids[fill[bucket(i)]++] = i;
+                    }
+                    deep.push_back(dd);
+                }
+            }
         } else {
             D.mode = MODE_SCAN;
         }
@@ -536,8 +615,19 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         CKC(cudaMemcpyAsync(ctx->d_hash_keys, hkeys.data(), hkeys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
         CKC(cudaMemcpyAsync(ctx->d_hash_idx, hidx.data(), hidx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (!half.empty()) {
+        CKC(cudaMalloc(&ctx->d_half, half.size() * sizeof(unsigned long long)));
+        CKC(cudaMemcpyAsync(ctx->d_half, half.data(), half.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!deep.empty()) {
+        CKC(cudaMalloc(&ctx->d_deep, deep.size() * sizeof(DevDeep)));
+        CKC(cudaMemcpyAsync(ctx->d_deep, deep.data(), deep.size() * sizeof(DevDeep), cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaMalloc(&ctx->d_csr, csr.size() * sizeof(uint32_t)));
+        CKC(cudaMemcpyAsync(ctx->d_csr, csr.data(), csr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (table_u16) CKC(cudaMalloc(&ctx->d_tables, table_u16 * sizeof(uint16_t)));
-    ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx};
+    CKC(cudaMalloc(&ctx->d_def_count, sizeof(uint32_t)));
+    ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx, ctx->d_half, ctx->d_deep, ctx->d_csr};
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         if (d.slots[s].mode != MODE_TABLE) continue;
         ctx->prof.launches[BC_K_OTHER]++;
@@ -594,9 +684,22 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     BatchView view{};
     const int staged = stage_batch(ctx, batch, &view);
     if (staged < 0) return staged;
+    if (ctx->def_cap < batch->n_reads) {  // worst case every read of the batch is deferred
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_def_items) cudaFree(ctx->d_def_items);
+        ctx->d_def_items = nullptr;
+        CK(ctx, cudaMalloc(&ctx->d_def_items, (size_t)batch->n_reads * sizeof(uint2)));
+        ctx->def_cap = batch->n_reads;
+    }
+    const Deferred deferred{ctx->d_def_items, ctx->d_def_count};
+    CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, flags, ctx->stream));
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, deferred, flags, ctx->stream));
+    }
+    if (!(flags & F_LOCATE_ONLY)) {
+        ProfScope p(ctx, BC_K_SCAN);
+        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, deferred, flags, ctx->stream));
     }
     return release_staging(ctx, staged);
 }

@@ -14,6 +14,10 @@ constexpr uint32_t kFail = 0xFFFFFFFFu;
 
 enum SlotMode : uint8_t { MODE_RAW = 0, MODE_TABLE = 1, MODE_HASH = 2, MODE_SCAN = 3 };
 
+constexpr int kMaxBlocks = 8;       // pigeonhole blocks of the deep index (max_err + 1 <= kMaxBlocks)
+constexpr int kMaxBlockKey = 8;     // bases of a block that form its bucket key (4^8 buckets)
+constexpr uint32_t kHalfProbeCap = 24;
+
 struct DevSlot {
     uint16_t offset, len, max_err;
     uint8_t kind;        // 'S' 'B' 'R'
@@ -24,6 +28,20 @@ struct DevSlot {
     uint32_t aux_mask;   // HASH: capacity-1
     uint16_t key_shift;  // first key bit of this slot's field
     uint16_t key_bits;   // index bits, or 3*len for raw fields ([lo:len][hi:len][nm:len])
+    // Exact pruned search for long barcodes (every reference as long as the slot and N-free):
+    //  half index  — two hashes keyed by the first / second half of the barcode; holds every reference within
+    //                Hamming distance 1 of a query (one of the halves is then error-free)
+    //  block index — max_err+1 blocks; a reference within max_err of the query agrees with it on a whole block
+    uint8_t has_half, n_blocks;
+    uint16_t half_len0;          // bases in the first half
+    uint32_t half_off, half_mask;  // two tables of half_mask+1 u64 entries {key32, id32} each, at half_off and half_off+cap
+    uint32_t deep_off;           // index of this slot's DevDeep descriptor
+};
+
+struct DevDeep {  // block index of one slot (global memory, read by k_resolve only)
+    uint8_t key_pos[kMaxBlocks], key_len[kMaxBlocks];  // bucket key = bases [key_pos, key_pos+key_len) of the barcode
+    uint32_t start_off[kMaxBlocks];                    // first of 4^key_len + 1 u32 bucket starts (CSR) in `csr`
+    uint32_t ids_off[kMaxBlocks];                      // first of n_ref u32 reference ids in `csr`
 };
 
 struct DevQRun {
@@ -33,6 +51,7 @@ struct DevQRun {
 
 struct DevCfg {
     uint32_t L, TW, n_slots, n_qruns, max_const_err, has_fn;
+    uint32_t pivot;  // template word with the most constant bases: the locate prefilter looks at it alone
     uint32_t has_umi, umi_bits, key_bits, wide;
     uint32_t t_lo[kMaxTW], t_hi[kMaxTW], t_cm[kMaxTW], t_fn[kMaxTW];
     DevSlot slots[kMaxSlots];

@@ -21,28 +21,69 @@ __device__ __forceinline__ uint32_t plane_bits(const uint32_t* p, uint32_t W, ui
     return __funnelshift_r(a, b, s);
 }
 
-// parse.rs:553-593 over a slot's reference set, with the exact-membership short cut of parse.rs:457,489 folded
-// in: an identical reference wins outright; otherwise the unique minimum within max_err, compared over the
-// shorter of the two lengths, N on either side never counting (Q5, Q10).
+// ---- TMA (bulk async copy) + mbarrier, raw PTX ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- fix_error (parse.rs:553-593) pieces -------------------------------------------------------------------
+struct Best {  // unique-minimum tracker: smallest distance, how many references reach it, one of them
+    uint32_t d, cnt, arg, exact;
+};
+__device__ __forceinline__ void best_add(Best& b, uint32_t d, uint32_t i) {
+    if (d < b.d) {
+        b.d = d;
+        b.cnt = 1;
+        b.arg = i;
+    } else if (d == b.d) {
+        b.cnt++;
+    }
+}
+// distance of a query to one reference: compared over the shorter of the two, N on either side never counts (Q10)
+__device__ __forceinline__ uint32_t ref_dist(uint4 r, uint32_t blo, uint32_t bhi, uint32_t bnm, uint32_t len, uint32_t lm) {
+    const uint32_t m = r.w < len ? lenmask(r.w) : lm;
+    return __popc(((blo ^ r.x) | (bhi ^ r.y)) & ~bnm & ~r.z & m);
+}
+__device__ __forceinline__ bool ref_same(uint4 r, uint32_t blo, uint32_t bhi, uint32_t bnm, uint32_t len) {
+    return r.w == len && r.x == blo && r.y == bhi && r.z == bnm;
+}
+
+// One thread, whole reference set (table building only): exact membership wins (parse.rs:457,489), otherwise the
+// unique minimum within max_err (Q5).
 __device__ __forceinline__ uint32_t scan_refs(const uint4* __restrict__ refs, uint32_t n_ref, uint32_t blo, uint32_t bhi,
                                               uint32_t bnm, uint32_t len, uint32_t max_err) {
-    uint32_t best = max_err + 1, cnt = 0, arg = kFail, exact = kFail;
+    Best b{max_err + 1, 0, kFail, kFail};
     const uint32_t lm = lenmask(len);
     for (uint32_t i = 0; i < n_ref; i++) {
-        uint4 r = __ldg(&refs[i]);
-        uint32_t m = r.w < len ? lenmask(r.w) : lm;
-        uint32_t d = __popc(((blo ^ r.x) | (bhi ^ r.y)) & ~bnm & ~r.z & m);
-        if (r.w == len && r.x == blo && r.y == bhi && r.z == bnm) exact = i;
-        if (d < best) {
-            best = d;
-            cnt = 1;
-            arg = i;
-        } else if (d == best) {
-            cnt++;
-        }
+        const uint4 r = __ldg(&refs[i]);
+        if (ref_same(r, blo, bhi, bnm, len)) b.exact = i;
+        best_add(b, ref_dist(r, blo, bhi, bnm, len, lm), i);
     }
-    if (exact != kFail) return exact;
-    return (cnt == 1 && best <= max_err) ? arg : kFail;
+    if (b.exact != kFail) return b.exact;
+    return (b.cnt == 1 && b.d <= max_err) ? b.arg : kFail;
 }
 
 __device__ __forceinline__ uint32_t hash_exact(const DevAux& aux, const DevSlot& S, uint32_t blo, uint32_t bhi) {
@@ -56,122 +97,251 @@ __device__ __forceinline__ uint32_t hash_exact(const DevAux& aux, const DevSlot&
     }
 }
 
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+// Half index probe for an N-free query that missed the exact lookup.  Every reference within distance 1 agrees
+// with the query on its first or on its second half, so it sits in one of the two probe chains.  Returns
+//   0 resolved: *idx is the unique reference at distance 1, or kFail when several tie at distance 1 (Q5) or the cap is 0
+//   1 nothing within distance 1: the caller needs the block index (distance 2..max_err) -> defer
+enum { HALF_RESOLVED = 0, HALF_DEEPER = 1 };
+__device__ __forceinline__ int half_probe(const DevAux& aux, const DevSlot& S, uint32_t blo, uint32_t bhi, uint32_t* idx) {
+    const uint32_t lm = lenmask(S.len);
+    const uint32_t cap = S.half_mask + 1;
+    Best b{2, 0, kFail, kFail};
+    bool overflow = false;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t pos0 = h ? S.half_len0 : 0u;
+        const uint32_t hl = h ? (uint32_t)S.len - S.half_len0 : (uint32_t)S.half_len0;
+        const uint32_t hm = lenmask(hl);
+        const uint32_t key = ((blo >> pos0) & hm) | (((bhi >> pos0) & hm) << 16);
+        const unsigned long long* tab = aux.half + S.half_off + (h ? cap : 0u);
+        uint32_t p = mix32(key) & S.half_mask;
+        uint32_t probes = 0;
+        for (;; probes++) {
+            const unsigned long long e = __ldg(&tab[p]);
+            if (e == kEmpty) break;
+            if (probes == kHalfProbeCap) {
+                overflow = true;
+                break;
+            }
+            if ((uint32_t)e == key) {
+                const uint32_t id = (uint32_t)(e >> 32);
+                const uint4 r = __ldg(&aux.refs[S.ref_off + id]);
+                best_add(b, __popc(((blo ^ r.x) | (bhi ^ r.y)) & lm), id);
+            }
+            p = (p + 1) & S.half_mask;
+        }
+    }
+    if (overflow) return HALF_DEEPER;  // a crowded chain was cut short: let the block index decide
+    if (b.d <= 1) {                    // exact was a miss, so this is distance 1
+        *idx = (b.cnt == 1 && S.max_err >= 1) ? b.arg : kFail;
+        return HALF_RESOLVED;
+    }
+    if (S.max_err <= 1) {
+        *idx = kFail;
+        return HALF_RESOLVED;
+    }
+    return HALF_DEEPER;
+}
+
+// ---- K1: locate (parse.rs:89-96, 151-163, 287-313) ----------------------------------------------------------
+// Two predicates per window (Q1): the regex's exact test (a read N in a constant fails, format-N needs ACGT) and
+// the repair's masked Hamming distance (N on either side is a wildcard).  Leftmost exact window wins (P1);
+// otherwise the unique minimum over offsets [0, R-L) within the cap (P2, Q3, Q5).
+// Every window is first looked at through ONE template word (the pivot: the word with the most constant bases):
+// a window whose pivot word alone already has more than max_const_err mismatches can be neither exact nor within
+// the cap, so only the survivors (typically just the true offset) get the full-width test.
+template <int TW>
+__device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, const uint32_t* hi, const uint32_t* nm,
+                                       const uint32_t W, const int len, int* off_out, bool* repaired_out) {
+    const int L = cfg.L;
+    const int nwin = len - L + 1;  // <= 0: read shorter than the scheme (Q4) -> constant-region error
+    const uint32_t kp = cfg.pivot;
+    const uint32_t p_lo = cfg.t_lo[kp], p_hi = cfg.t_hi[kp], p_cm = cfg.t_cm[kp];
+    const uint32_t maxc = cfg.max_const_err;
+    uint32_t best = maxc + 1, cnt = 0;
+    int arg = -1, first_exact = -1;
+    for (int c = 0; (c << 5) < nwin && first_exact < 0; c++) {
+        const uint32_t j = c + kp;
+        const uint32_t al = j < W ? lo[j] : 0u, bl = j + 1 < W ? lo[j + 1] : 0u;
+        const uint32_t ah = j < W ? hi[j] : 0u, bh = j + 1 < W ? hi[j + 1] : 0u;
+        const uint32_t an = j < W ? nm[j] : 0u, bn = j + 1 < W ? nm[j + 1] : 0u;
+        uint32_t cand = 0;
+#pragma unroll
+        for (int s = 0; s < 32; s++) {
+            const uint32_t wl = __funnelshift_r(al, bl, s);
+            const uint32_t wh = __funnelshift_r(ah, bh, s);
+            const uint32_t wn = __funnelshift_r(an, bn, s);
+            const uint32_t x = (((wl ^ p_lo) | (wh ^ p_hi)) & p_cm) & ~wn;
+            if ((uint32_t)__popc(x) <= maxc) cand |= 1u << s;
+        }
+        const int rem = nwin - (c << 5);
+        if (rem < 32) cand &= (1u << rem) - 1u;
+        while (cand) {
+            const int s = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int o = (c << 5) + s;
+            uint32_t d = 0, e = 0;
+#pragma unroll
+            for (int k = 0; k < TW; k++) {
+                const uint32_t wl = plane_bits(lo, W, o + (k << 5));
+                const uint32_t wh = plane_bits(hi, W, o + (k << 5));
+                const uint32_t wn = plane_bits(nm, W, o + (k << 5));
+                const uint32_t x = ((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k];
+                e |= x | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
+                d += __popc(x & ~wn);
+            }
+            if (e == 0) {
+                first_exact = o;
+                break;
+            }
+            if (o < nwin - 1) {
+                if (d < best) {
+                    best = d;
+                    cnt = 1;
+                    arg = o;
+                } else if (d == best) {
+                    cnt++;
+                }
+            }
+        }
+    }
+    int off = -1;
+    bool repaired = false;
+    if (first_exact >= 0) {
+        off = first_exact;
+    } else if (cnt == 1 && best <= maxc) {
+        off = arg;
+        repaired = true;
+        if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
+            uint32_t bad = 0;
+#pragma unroll
+            for (int k = 0; k < TW; k++) bad |= plane_bits(nm, W, off + (k << 5)) & cfg.t_fn[k];
+            if (bad) {
+                off = -1;
+                repaired = false;
+            }
+        }
+    }
+    *off_out = off;
+    *repaired_out = repaired;
+}
+
+struct SlotBits {
+    uint32_t lo, hi, nm;
+};
+__device__ __forceinline__ SlotBits slot_bits(const uint32_t* lo, const uint32_t* hi, const uint32_t* nm, uint32_t W,
+                                              uint32_t pos, uint32_t len) {
+    const uint32_t m = lenmask(len);
+    SlotBits b;
+    b.nm = plane_bits(nm, W, pos) & m;
+    b.lo = plane_bits(lo, W, pos) & m & ~b.nm;
+    b.hi = plane_bits(hi, W, pos) & m & ~b.nm;
+    return b;
+}
+__device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBits& b) {
+    // raw key (N kept as its own symbol, Q14): field = [lo:len][hi:len][nm:len]
+    key_or(key, b.lo, S.key_shift);
+    key_or(key, b.hi, S.key_shift + S.len);
+    key_or(key, b.nm, S.key_shift + 2 * S.len);
+}
+
+// K3 for one matched read: count it (info.rs:735-808) or, multi-GPU with a random barcode, hand it to its owner rank
+__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const DevTable& table, const RouteOut& route, int flags,
+                                              Key key, bool* is_new) {
+    if (flags & F_INSERT) return table_count(table, key, 1ULL, is_new) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
+    if (flags & F_ROUTE) {
+        const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
+        const uint32_t slot = atomicAdd(&route.counts[owner], 1u);
+        if (slot < route.capacity) route.buckets[owner * route.capacity + slot] = key;
+        return -2;  // outcome is decided by the owner rank
+    }
+    return BC_ST_MATCHED;
+}
+
+constexpr int kDeferred = -3;  // thread-local status: the read went to the deferred list (k_resolve finishes it)
+
+// k_decode: one thread per read, kTile reads per CTA.  The tile's packed planes / qualities / lengths are contiguous
+// in global memory and land in shared memory through three TMA bulk copies signalled on one mbarrier.
 template <int TW>
 __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg cfg, const BatchView batch,
                                                   const DevAux aux, const DevTable table,
                                                   unsigned long long* __restrict__ counters, const DecodeOut out,
-                                                  const RouteOut route, const int flags) {
-    extern __shared__ uint32_t smem[];
+                                                  const RouteOut route, const Deferred deferred, const int flags) {
+    extern __shared__ __align__(128) uint32_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned int s_cnt[BC_N_COUNTERS + 1];
 
     const uint32_t tid = threadIdx.x;
     const unsigned long long base = (unsigned long long)blockIdx.x * kTile;
-    const uint32_t n_tile = min((unsigned long long)kTile, batch.n_reads - base);
+    const uint32_t n_tile = (uint32_t)min((unsigned long long)kTile, batch.n_reads - base);
     const uint32_t W = batch.W;
     uint32_t* s_pl = smem;
     uint8_t* s_q = reinterpret_cast<uint8_t*>(smem + kTile * batch.plane_stride);
+    uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (batch.qual ? kTile * batch.qual_stride : 0u));
 
     if (tid < BC_N_COUNTERS + 1) s_cnt[tid] = 0;
-    // stage the tile: both arrays are contiguous per tile, so this is a straight coalesced copy
     {
-        const uint32_t* g = batch.planes + base * batch.plane_stride;
-        const uint32_t nw = n_tile * batch.plane_stride;
-        for (uint32_t i = tid; i < nw; i += kTile) s_pl[i] = __ldg(g + i);
-        if (batch.qual) {
-            const uint32_t* gq = reinterpret_cast<const uint32_t*>(batch.qual + base * batch.qual_stride);
-            uint32_t* sq = reinterpret_cast<uint32_t*>(s_q);
-            const uint32_t nq = n_tile * (batch.qual_stride >> 2);
-            for (uint32_t i = tid; i < nq; i += kTile) sq[i] = __ldg(gq + i);
+        const uint32_t* g_pl = batch.planes + base * batch.plane_stride;
+        const uint8_t* g_q = batch.qual ? batch.qual + base * batch.qual_stride : nullptr;
+        const uint16_t* g_len = batch.read_len + base;
+        const uint32_t b_pl = n_tile * batch.plane_stride * 4u, b_q = g_q ? n_tile * batch.qual_stride : 0u, b_len = n_tile * 2u;
+        const bool bulk = (((b_pl | b_q | b_len) & 15u) == 0) &&
+                          ((((unsigned long long)g_pl | (unsigned long long)g_q | (unsigned long long)g_len) & 15ull) == 0);
+        if (bulk) {  // uniform per CTA
+            if (tid == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, b_pl + b_q + b_len);
+                bulk_g2s(s_pl, g_pl, b_pl, &s_bar);
+                if (b_q) bulk_g2s(s_q, g_q, b_q, &s_bar);
+                bulk_g2s(s_len, g_len, b_len, &s_bar);
+            }
+            mbar_wait(&s_bar, 0);
+        } else {  // ragged last tile / unaligned caller buffers: plain cooperative copy
+            for (uint32_t i = tid; i < n_tile * batch.plane_stride; i += kTile) s_pl[i] = __ldg(g_pl + i);
+            if (g_q) {
+                const uint32_t* gq = reinterpret_cast<const uint32_t*>(g_q);
+                uint32_t* sq = reinterpret_cast<uint32_t*>(s_q);
+                for (uint32_t i = tid; i < n_tile * (batch.qual_stride >> 2); i += kTile) sq[i] = __ldg(gq + i);
+            }
+            if (tid < n_tile) s_len[tid] = g_len[tid];
+            __syncthreads();
         }
     }
-    __syncthreads();
 
     int status = -1;  // -1: thread has no read
     bool is_new = false;
+    int off = -1;
+    bool repaired = false;
     if (tid < n_tile) {
         const uint32_t* lo = s_pl + tid * batch.plane_stride;
         const uint32_t* hi = lo + W;
         const uint32_t* nm = hi + W;
-        const uint32_t rl = batch.read_len[base + tid];
-        const int len = rl & 0x7FFF;
-        const int L = cfg.L;
-        int off = -1;
-        bool repaired = false;
+        const uint32_t rl = s_len[tid];
         Key key{0, 0};
-
         if (rl & BC_READ_UNSUPPORTED) {
             status = BC_ST_UNSUPPORTED;
         } else {
-            // ---- K1: locate.  One pass over the windows computes both predicates (Q1): the exact test of the
-            // regex (a read N in a constant fails, format-N needs ACGT) and the masked Hamming distance of the
-            // repair (N on either side is a wildcard).  Leftmost exact window wins (P1); otherwise the unique
-            // minimum over offsets [0, R-L) within the cap (P2, Q3, Q5).
-            const int nwin = len - L + 1;  // <= 0: read shorter than the scheme (Q4) -> constant-region error
-            uint32_t best = cfg.max_const_err + 1, cnt = 0;
-            int arg = -1, first_exact = -1;
-            const int nchunks = (nwin + 31) >> 5;
-            for (int c = 0; c < nchunks && first_exact < 0; c++) {
-                uint32_t pl[TW + 1], ph[TW + 1], pn[TW + 1];
-#pragma unroll
-                for (int k = 0; k <= TW; k++) {
-                    const bool in = (uint32_t)(c + k) < W;
-                    pl[k] = in ? lo[c + k] : 0u;
-                    ph[k] = in ? hi[c + k] : 0u;
-                    pn[k] = in ? nm[c + k] : 0u;
-                }
-                const int smax = min(32, nwin - (c << 5));
-                for (int s = 0; s < smax; s++) {
-                    uint32_t d = 0, e = 0;
-#pragma unroll
-                    for (int k = 0; k < TW; k++) {
-                        const uint32_t wl = __funnelshift_r(pl[k], pl[k + 1], s);
-                        const uint32_t wh = __funnelshift_r(ph[k], ph[k + 1], s);
-                        const uint32_t wn = __funnelshift_r(pn[k], pn[k + 1], s);
-                        const uint32_t x = ((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k];
-                        e |= x | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
-                        d += __popc(x & ~wn);
-                    }
-                    const int o = (c << 5) + s;
-                    if (e == 0) {
-                        first_exact = o;
-                        break;
-                    }
-                    if (o < nwin - 1) {
-                        if (d < best) {
-                            best = d;
-                            cnt = 1;
-                            arg = o;
-                        } else if (d == best) {
-                            cnt++;
-                        }
-                    }
-                }
-            }
-            int qstart = 0;
-            if (first_exact >= 0) {
-                off = first_exact;
-                qstart = off;
-            } else if (cnt == 1 && best <= cfg.max_const_err) {
-                off = arg;
-                repaired = true;
-                qstart = 0;  // Q6: the repaired sequence starts at 0, the quality string is not re-aligned
-                if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
-                    uint32_t bad = 0;
-#pragma unroll
-                    for (int k = 0; k < TW; k++) bad |= plane_bits(nm, W, off + (k << 5)) & cfg.t_fn[k];
-                    if (bad) off = -1;
-                }
-            }
+            locate<TW>(cfg, lo, hi, nm, W, (int)(rl & 0x7FFF), &off, &repaired);
             if (off < 0) {
                 status = BC_ST_CONSTANT;
-                repaired = false;
             } else if (flags & F_LOCATE_ONLY) {
                 status = BC_ST_MATCHED;
             } else {
                 status = BC_ST_MATCHED;
-                // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12)
+                // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
+                // Q6: after a repair the quality string is read from 0, not from the repaired offset.
                 if (cfg.n_qruns) {
-                    const uint8_t* q = s_q + tid * batch.qual_stride + qstart;
+                    const uint8_t* q = s_q + tid * batch.qual_stride + (repaired ? 0 : off);
                     for (uint32_t r = 0; r < cfg.n_qruns; r++) {
                         const DevQRun run = cfg.qruns[r];
                         uint32_t sum = 0;
@@ -182,31 +352,34 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         }
                     }
                 }
-                // ---- K2b: barcode correction, sample first then counted barcodes in order (parse.rs:448-507)
+                // ---- K2b: barcode correction, sample first then counted barcodes in order (parse.rs:448-507).
+                // Fast paths only: anything that needs a search over the reference set goes to k_resolve.
                 if (status == BC_ST_MATCHED) {
                     for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
                         const uint32_t si = cfg.order[oi];
                         const DevSlot& S = cfg.slots[si];
-                        const uint32_t pos = off + S.offset;
-                        const uint32_t m = lenmask(S.len);
-                        const uint32_t bnm = plane_bits(nm, W, pos) & m;
-                        const uint32_t blo = plane_bits(lo, W, pos) & m & ~bnm;
-                        const uint32_t bhi = plane_bits(hi, W, pos) & m & ~bnm;
+                        const SlotBits b = slot_bits(lo, hi, nm, W, off + S.offset, S.len);
                         if (S.mode == MODE_RAW) {
-                            // raw key (N kept as its own symbol, Q14): field = [lo:len][hi:len][nm:len]
-                            key_or(key, blo, S.key_shift);
-                            key_or(key, bhi, S.key_shift + S.len);
-                            key_or(key, bnm, S.key_shift + 2 * S.len);
-                            if (out.slot_index) out.slot_index[(base + tid) * cfg.n_slots + si] = -1;
+                            key_raw(key, S, b);
                             continue;
                         }
                         uint32_t idx = kFail;
-                        if (bnm == 0 && S.mode == MODE_TABLE) {
-                            const uint32_t v = __ldg(&aux.tables[S.aux_off + (blo | (bhi << S.len))]);
+                        bool defer = false;
+                        if (b.nm != 0 || S.mode == MODE_SCAN) {
+                            defer = true;
+                        } else if (S.mode == MODE_TABLE) {
+                            const uint32_t v = __ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]);
                             idx = v == 0xFFFFu ? kFail : v;
-                        } else {
-                            if (bnm == 0 && S.mode == MODE_HASH) idx = hash_exact(aux, S, blo, bhi);
-                            if (idx == kFail) idx = scan_refs(aux.refs + S.ref_off, S.n_ref, blo, bhi, bnm, S.len, S.max_err);
+                        } else {  // MODE_HASH
+                            idx = hash_exact(aux, S, b.lo, b.hi);
+                            if (idx == kFail) {
+                                if (!S.has_half) defer = true;
+                                else defer = half_probe(aux, S, b.lo, b.hi, &idx) == HALF_DEEPER;
+                            }
+                        }
+                        if (defer) {
+                            status = kDeferred;
+                            break;
                         }
                         if (out.slot_index) out.slot_index[(base + tid) * cfg.n_slots + si] = (int32_t)idx;
                         if (idx == kFail) {
@@ -216,20 +389,10 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         key_or(key, idx, S.key_shift);
                     }
                 }
-                // ---- K3: count (info.rs:735-808)
-                if (status == BC_ST_MATCHED) {
-                    if (flags & F_INSERT) {
-                        if (!table_count(table, key, 1ULL, &is_new)) status = BC_ST_DUPLICATE;
-                    } else if (flags & F_ROUTE) {
-                        const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
-                        const uint32_t slot = atomicAdd(&route.counts[owner], 1u);
-                        if (slot < route.capacity) route.buckets[owner * route.capacity + slot] = key;
-                        status = -2;  // outcome is decided by the owner rank
-                    }
-                }
+                if (status == BC_ST_MATCHED) status = count_or_route(cfg, table, route, flags, key, &is_new);
             }
         }
-        if (flags & F_EMIT) {
+        if (status != kDeferred && (flags & F_EMIT)) {
             const unsigned long long i = base + tid;
             if (out.status) out.status[i] = (uint8_t)status;
             if (out.offset) out.offset[i] = (int16_t)off;
@@ -239,9 +402,22 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
         }
     }
 
+    // ---- deferred reads: one warp-aggregated append per warp
+    const int lane = tid & 31;
+    {
+        const unsigned dm = __ballot_sync(0xFFFFFFFFu, status == kDeferred);
+        if (dm) {
+            const int leader = __ffs(dm) - 1;
+            uint32_t at = 0;
+            if (lane == leader) at = atomicAdd(deferred.count, (uint32_t)__popc(dm));
+            at = __shfl_sync(0xFFFFFFFFu, at, leader);
+            if (status == kDeferred)
+                deferred.items[at + __popc(dm & ((1u << lane) - 1u))] =
+                    make_uint2((uint32_t)(base + tid), (uint32_t)off | (repaired ? 0x10000u : 0u));
+        }
+    }
     // ---- outcome counters (info.rs:60-127): warp-aggregated, one global atomic per counter per CTA
     if (counters) {
-        const int lane = tid & 31;
 #pragma unroll
         for (int st = 0; st < BC_N_COUNTERS; st++) {
             const unsigned b = __ballot_sync(0xFFFFFFFFu, status == st);
@@ -261,12 +437,161 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     }
 }
 
-size_t decode_smem_bytes(const BatchView& b) { return (size_t)kTile * (b.plane_stride * 4u + (b.qual ? b.qual_stride : 0u)); }
+// ---- k_resolve: one WARP per deferred read.  Redoes the barcode step of that read (parse.rs:439-524) with the
+// searches done cooperatively: lanes share the candidates of the block index (or, when a slot has none, the whole
+// reference set) and reduce to (minimum distance, how many reach it, which one) — fix_error's unique-minimum rule.
+__device__ __forceinline__ uint32_t warp_best(Best b, uint32_t max_err) {
+    uint32_t dmin = b.d;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dmin = min(dmin, __shfl_xor_sync(0xFFFFFFFFu, dmin, o));
+    uint32_t cnt = b.d == dmin ? b.cnt : 0u;
+    uint32_t arg = b.d == dmin && b.cnt ? b.arg : kFail;
+    uint32_t exact = b.exact;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        arg = min(arg, __shfl_xor_sync(0xFFFFFFFFu, arg, o));
+        exact = min(exact, __shfl_xor_sync(0xFFFFFFFFu, exact, o));
+    }
+    if (exact != kFail) return exact;
+    return (cnt == 1 && dmin <= max_err) ? arg : kFail;
+}
+
+__device__ __forceinline__ uint32_t warp_scan_all(const DevAux& aux, const DevSlot& S, const SlotBits& q, int lane) {
+    Best b{S.max_err + 1u, 0, kFail, kFail};
+    const uint32_t lm = lenmask(S.len);
+    const uint4* refs = aux.refs + S.ref_off;
+    for (uint32_t i = lane; i < S.n_ref; i += 32) {
+        const uint4 r = __ldg(&refs[i]);
+        if (ref_same(r, q.lo, q.hi, q.nm, S.len)) b.exact = i;
+        best_add(b, ref_dist(r, q.lo, q.hi, q.nm, S.len, lm), i);
+    }
+    return warp_best(b, S.max_err);
+}
+
+// Block index: every reference within max_err of the query (N positions of the query never count) agrees with it
+// on all non-N bases of at least one of the max_err+1 blocks, hence on that block's key bases; it is then found in
+// the bucket of one completion of the key's N positions.  A reference is counted at the FIRST block it agrees on.
+__device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const DevSlot& S, const SlotBits& q, int lane) {
+    const DevDeep& D = aux.deep[S.deep_off];
+    Best b{S.max_err + 1u, 0, kFail, kFail};
+    const uint32_t lm = lenmask(S.len);
+    const uint4* refs = aux.refs + S.ref_off;
+    for (uint32_t p = 0; p < S.n_blocks; p++) {
+        const uint32_t kpos = D.key_pos[p], kl = D.key_len[p], km = lenmask(kl);
+        const uint32_t qlo = (q.lo >> kpos) & km, qhi = (q.hi >> kpos) & km, qn = (q.nm >> kpos) & km;
+        const uint32_t t = __popc(qn);  // <= 2 (checked by the caller)
+        const uint32_t n1 = qn ? (uint32_t)__ffs(qn) - 1u : 0u;
+        const uint32_t n2 = t > 1 ? 31u - (uint32_t)__clz(qn) : 0u;
+        const uint32_t* start = aux.csr + D.start_off[p];
+        const uint32_t* ids = aux.csr + D.ids_off[p];
+        for (uint32_t comp = 0; comp < (1u << (2 * t)); comp++) {
+            uint32_t vlo = qlo, vhi = qhi;
+            if (t >= 1) {
+                vlo |= (comp & 1u) << n1;
+                vhi |= ((comp >> 1) & 1u) << n1;
+            }
+            if (t >= 2) {
+                vlo |= ((comp >> 2) & 1u) << n2;
+                vhi |= ((comp >> 3) & 1u) << n2;
+            }
+            const uint32_t bucket = vlo | (vhi << kl);
+            const uint32_t a = __ldg(&start[bucket]), e = __ldg(&start[bucket + 1]);
+            for (uint32_t j = a + lane; j < e; j += 32) {
+                const uint32_t id = __ldg(&ids[j]);
+                const uint4 r = __ldg(&refs[id]);
+                const uint32_t diff = ((q.lo ^ r.x) | (q.hi ^ r.y)) & ~q.nm & lm;
+                bool earlier = false;
+                for (uint32_t pp = 0; pp < p; pp++)
+                    earlier |= (diff & (lenmask(D.key_len[pp]) << D.key_pos[pp])) == 0;
+                if (!earlier) best_add(b, __popc(diff), id);
+            }
+        }
+    }
+    return warp_best(b, S.max_err);
+}
+
+__global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg cfg, const BatchView batch, const DevAux aux,
+                                                 const DevTable table, unsigned long long* __restrict__ counters,
+                                                 const DecodeOut out, const RouteOut route, const Deferred deferred,
+                                                 const int flags) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = *deferred.count;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t W = batch.W;
+    unsigned long long c_matched = 0, c_dup = 0, c_sample = 0, c_counted = 0, c_new = 0;  // lane 0 only
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
+        const uint2 item = deferred.items[w];
+        const unsigned long long ri = item.x;
+        const int off = (int)(item.y & 0xFFFFu);
+        const uint32_t* lo = batch.planes + ri * batch.plane_stride;
+        const uint32_t* hi = lo + W;
+        const uint32_t* nm = hi + W;
+        int status = BC_ST_MATCHED;
+        Key key{0, 0};
+        for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
+            const uint32_t si = cfg.order[oi];
+            const DevSlot& S = cfg.slots[si];
+            const SlotBits b = slot_bits(lo, hi, nm, W, off + S.offset, S.len);  // lane-uniform
+            if (S.mode == MODE_RAW) {
+                key_raw(key, S, b);
+                continue;
+            }
+            uint32_t idx = kFail;
+            bool search = true;
+            if (b.nm == 0 && S.mode == MODE_TABLE) {
+                const uint32_t v = __ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]);
+                idx = v == 0xFFFFu ? kFail : v;
+                search = false;  // the table already holds the result of the full search
+            } else if (b.nm == 0 && S.mode == MODE_HASH) {
+                idx = hash_exact(aux, S, b.lo, b.hi);
+                search = idx == kFail;
+            }
+            if (search) {
+                if (S.n_blocks && __popc(b.nm) <= 2) idx = warp_scan_blocks(aux, S, b, lane);
+                else idx = warp_scan_all(aux, S, b, lane);
+            }
+            if (lane == 0 && out.slot_index) out.slot_index[ri * cfg.n_slots + si] = (int32_t)idx;
+            if (idx == kFail) {
+                status = S.kind == 'S' ? BC_ST_SAMPLE : BC_ST_COUNTED;
+                break;
+            }
+            key_or(key, idx, S.key_shift);
+        }
+        if (lane == 0) {
+            bool is_new = false;
+            if (status == BC_ST_MATCHED) status = count_or_route(cfg, table, route, flags, key, &is_new);
+            c_matched += status == BC_ST_MATCHED;
+            c_dup += status == BC_ST_DUPLICATE;
+            c_sample += status == BC_ST_SAMPLE;
+            c_counted += status == BC_ST_COUNTED;
+            c_new += is_new;
+            if (flags & F_EMIT) {
+                if (out.status) out.status[ri] = (uint8_t)status;
+                if (out.offset) out.offset[ri] = (int16_t)off;
+                if (out.repaired) out.repaired[ri] = (item.y >> 16) & 1u;
+                if (out.key_lo) out.key_lo[ri] = key.lo;
+                if (out.key_hi) out.key_hi[ri] = key.hi;
+            }
+        }
+    }
+    if (lane == 0 && counters) {
+        if (c_matched) atomicAdd(&counters[BC_CNT_MATCHED], c_matched);
+        if (c_dup) atomicAdd(&counters[BC_CNT_DUPLICATES], c_dup);
+        if (c_sample) atomicAdd(&counters[BC_CNT_SAMPLE], c_sample);
+        if (c_counted) atomicAdd(&counters[BC_CNT_COUNTED], c_counted);
+        if (c_new && table.n_entries) atomicAdd(table.n_entries, c_new);
+    }
+}
+
+size_t decode_smem_bytes(const BatchView& b) {
+    return (size_t)kTile * (b.plane_stride * 4u + (b.qual ? b.qual_stride : 0u) + 2u);
+}
 
 template <int TW>
 static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
-                                    unsigned long long* counters, const DecodeOut& out, const RouteOut& route, int flags,
-                                    cudaStream_t stream) {
+                                    unsigned long long* counters, const DecodeOut& out, const RouteOut& route,
+                                    const Deferred& deferred, int flags, cudaStream_t stream) {
     const size_t smem = decode_smem_bytes(batch);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -275,25 +600,38 @@ static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, c
         configured = smem;
     }
     const unsigned grid = (batch.n_reads + kTile - 1) / kTile;
-    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, table, counters, out, route, flags);
+    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, table, counters, out, route, deferred, flags);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, int flags,
-                          cudaStream_t stream) {
+                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
+                          int flags, cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     switch (cfg.TW) {
-        case 1: return launch_decode_tw<1>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 2: return launch_decode_tw<2>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 3: return launch_decode_tw<3>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 4: return launch_decode_tw<4>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 5: return launch_decode_tw<5>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 6: return launch_decode_tw<6>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 7: return launch_decode_tw<7>(cfg, batch, aux, table, counters, out, route, flags, stream);
-        case 8: return launch_decode_tw<8>(cfg, batch, aux, table, counters, out, route, flags, stream);
+        case 1: return launch_decode_tw<1>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 2: return launch_decode_tw<2>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 3: return launch_decode_tw<3>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 4: return launch_decode_tw<4>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 5: return launch_decode_tw<5>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 6: return launch_decode_tw<6>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 7: return launch_decode_tw<7>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 8: return launch_decode_tw<8>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// deferred reads of the batch just decoded (their number is read on the device: no host round trip)
+cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
+                           int flags, cudaStream_t stream) {
+    if (batch.n_reads == 0) return cudaSuccess;
+    unsigned long long warps = batch.n_reads;  // at most one warp per read of the batch
+    unsigned grid = (unsigned)((warps + 3) / 4);
+    const unsigned cap = 148u * 16u;  // persistent warps stride over the list
+    if (grid > cap) grid = cap;
+    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, table, counters, out, route, deferred, flags);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------

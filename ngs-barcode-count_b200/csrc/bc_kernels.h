@@ -25,14 +25,25 @@ struct DevAux {  // reference sets and their accelerators
     const uint16_t* tables;               // 4^len direct lookups (MODE_TABLE)
     const unsigned long long* hash_keys;  // exact-match hash (MODE_HASH): lo | hi << 32
     const uint32_t* hash_idx;
+    const unsigned long long* half;       // half index: {key32, id32} entries, kEmpty = free
+    const DevDeep* deep;                  // block index descriptors
+    const uint32_t* csr;                  // block index buckets: starts and reference ids
+};
+
+struct Deferred {  // reads whose barcode step needs a search: {read index, offset | repaired << 16}
+    uint2* items;
+    uint32_t* count;
 };
 
 enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8 };
 
 // counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, int flags,
-                          cudaStream_t stream);
+                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
+                          int flags, cudaStream_t stream);
+cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
+                           int flags, cudaStream_t stream);
 
 // fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
 cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t* table, cudaStream_t stream);

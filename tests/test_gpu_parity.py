@@ -372,3 +372,49 @@ def test_table_growth_and_many_keys():
     for lo, hi, cnt in zip(rows["key_lo"], rows["key_hi"], rows["count"]):
         got[ctr.key_decode(lo, hi)[0]] = int(cnt)
     assert got == want
+
+
+@pytest.mark.parametrize("blen,max_err,n_ref", [(20, None, 700), (20, 1, 300), (20, 7, 400), (16, 2, 5000), (12, None, 900),
+                                                (24, 5, 260), (11, 0, 300), (20, None, 100)])
+def test_long_barcode_search_paths(blen, max_err, n_ref, tmp_path):
+    """Barcodes longer than the direct-table limit: exact hash, half index (distance 1), block index (distance 2..cap,
+    N wildcards expanded) and the whole-set fallback (3+ N, small sets) must all reproduce fix_error exactly —
+    including ties at the minimum, which the engineered near-duplicate references provoke."""
+    rng = random.Random(blen * 1000 + n_ref + (max_err or 0))
+    refs = set()
+    while len(refs) < n_ref * 2 // 3:
+        refs.add(rand_dna(rng, blen))
+    base = sorted(refs)
+    while len(refs) < n_ref:  # close neighbours: distance 1..3 from an existing reference
+        r = list(rng.choice(base))
+        for pos in rng.sample(range(blen), rng.randint(1, 3)):
+            r[pos] = rng.choice("ACGT")
+        refs.add("".join(r))
+    # a crowded half: many references sharing their first half
+    head = rand_dna(rng, blen // 2)
+    for _ in range(40):
+        refs.add(head + rand_dna(rng, blen - blen // 2))
+    refs = sorted(refs)
+    fmt = tmp_path / "scheme.txt"
+    fmt.write_text("ACGTACGTACGG{%d}TTGACAGTCA\n" % blen)
+    counted = tmp_path / "counted.csv"
+    counted.write_text("Barcode,ID,N\n" + "".join(f"{d},id{i},1\n" for i, d in enumerate(refs)))
+    reads = []
+    for i in range(3000):
+        b = list(rng.choice(refs))
+        for pos in rng.sample(range(blen), rng.choice([0, 1, 1, 1, 2, 2, 3, 4, 5, 6])):
+            b[pos] = rng.choice("ACGT")
+        for pos in rng.sample(range(blen), rng.choice([0, 0, 0, 1, 1, 2, 3])):
+            b[pos] = "N"
+        seq = rand_dna(rng, rng.randint(0, 6)) + "ACGTACGTACGG" + "".join(b) + "TTGACAGTCA" + rand_dna(rng, rng.randint(1, 6))
+        reads.append((seq, "I" * len(seq)))
+    orc = Oracle(str(fmt), None, str(counted), max_barcode=max_err)
+    outcomes = [orc.process(s, q) for s, q in reads]
+    assert sum(o["status"] == "matched" for o in outcomes) > 100
+    run = bc.Run(str(fmt), None, str(counted), max_barcode=max_err)
+    ctr = bc.Counter(run)
+    batch = check_reads_against(run, ctr, reads, outcomes)
+    ctr.submit(batch)
+    c = ctr.counters()
+    assert c.pop("unsupported") == 0 and c == orc.counters()
+    assert ctr.profile()["launches"]["scan"] >= 1
