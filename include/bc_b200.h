@@ -165,13 +165,17 @@ int bc_locate_only(bc_ctx *ctx, const bc_batch *batch, bc_locate_out *out);
 int bc_decode_only(bc_ctx *ctx, const bc_batch *batch, bc_decode_out *out);
 
 /* A table of (key, count) rows in host memory, owned by the library until bc_table_free.  `mask` (enrichment
- * tables only) has bit k set when counted barcode k is part of the row. */
+ * tables only) has bit k set when counted barcode k is part of the row.  key_hi is NULL when every key fits 64
+ * bits.  The rows of bc_finish live in pinned memory owned by the ctx (flags has BC_TABLE_BORROWED): they stay
+ * valid until the next bc_finish / bc_destroy on that ctx, and bc_table_free only clears the struct. */
+#define BC_TABLE_BORROWED 1u
 typedef struct {
     uint64_t n_rows;
     uint64_t *key_lo;
     uint64_t *key_hi;
     uint64_t *count;
     uint32_t *mask;
+    uint32_t flags;
 } bc_table;
 void bc_table_free(bc_table *t);
 

@@ -59,7 +59,7 @@ class bc_decode_out(C.Structure):
 
 class bc_table(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("key_lo", C.POINTER(C.c_uint64)), ("key_hi", C.POINTER(C.c_uint64)),
-                ("count", C.POINTER(C.c_uint64)), ("mask", C.POINTER(C.c_uint32))]
+                ("count", C.POINTER(C.c_uint64)), ("mask", C.POINTER(C.c_uint32)), ("flags", C.c_uint32)]
 
 
 class bc_profile(C.Structure):
@@ -322,7 +322,8 @@ class Counter:
     def _table(self, t):
         n = int(t.n_rows)
         get = lambda p, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt).copy() if n and p else np.zeros(0, dt)
-        rows = dict(key_lo=get(t.key_lo, np.uint64), key_hi=get(t.key_hi, np.uint64), count=get(t.count, np.uint64),
+        rows = dict(key_lo=get(t.key_lo, np.uint64), key_hi=get(t.key_hi, np.uint64) if t.key_hi else np.zeros(n, np.uint64),
+                    count=get(t.count, np.uint64),
                     mask=get(t.mask, np.uint32) if t.mask else None)
         lib().bc_table_free(C.byref(t))
         return rows
@@ -331,6 +332,15 @@ class Counter:
         t = bc_table()
         self._ck(lib().bc_finish(self.h, C.byref(t)), "bc_finish")
         return self._table(t)
+
+    def finish_view(self):
+        """bc_finish without copying: (n_rows, key_lo, key_hi or None, count) as numpy views of the ctx-owned pinned
+        rows, valid until the next finish on this Counter."""
+        t = bc_table()
+        self._ck(lib().bc_finish(self.h, C.byref(t)), "bc_finish")
+        n = int(t.n_rows)
+        view = lambda p: np.ctypeslib.as_array(p, shape=(n,)) if n and p else np.zeros(0, np.uint64)
+        return n, view(t.key_lo), (view(t.key_hi) if t.key_hi else None), view(t.count)
 
     def enrich(self, doubles=True):
         s, d = bc_table(), bc_table()
@@ -368,7 +378,7 @@ class Counter:
         return lo.value, hi.value, cnt.value, int(n.value)
 
     def import_rows(self, lo, hi, cnt, n):
-        self._ck(lib().bc_import_rows(self.h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()),
+        self._ck(lib().bc_import_rows(self.h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()) if hi is not None else None,
                                       C.c_void_p(cnt.data_ptr()), n), "bc_import_rows")
 
     # ---- measurement ----

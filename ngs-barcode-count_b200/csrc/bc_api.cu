@@ -1,5 +1,6 @@
 // bc_api.cu — the C ABI of include/bc_b200.h: context, device tables, staging, finish/enrichment.
 // No CPU fallback lives here: every compute entry point launches the kernels of bc_kernels.cu or fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -63,20 +64,21 @@ struct bc_ctx {
     uint2* d_def_items = nullptr;
     uint32_t* d_def_count = nullptr;
     uint64_t def_cap = 0;
-    // main table
-    DevTable table{};
-    unsigned long long table_capacity = 0;
-    unsigned long long entries_upper = 0;  // host-side upper bound of occupied entries
-    unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 1 (last = table entries)
+    // counting state: map (key -> count) and, with a random barcode, the (key, UMI) set
+    Tables tables{};
+    unsigned long long entries_upper = 0;  // host-side upper bound of entries added to either table
+    unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 2 (then: map entries, set entries)
     // staging for host batches
     Staging staging[2];
     int cur = 0;
     bool copies_pending = false;
     // scratch for the test hooks
-    // cached final rows (device) for enrich / export
+    // final rows: device buffers (grow-only, reused by every finish / export) and their pinned host mirror
     unsigned long long *d_row_lo = nullptr, *d_row_hi = nullptr, *d_row_cnt = nullptr, *d_row_n = nullptr;
-    unsigned long long n_rows = 0;
+    unsigned long long row_cap = 0, n_rows = 0;
     bool rows_valid = false;
+    uint64_t *h_row_lo = nullptr, *h_row_hi = nullptr, *h_row_cnt = nullptr;
+    unsigned long long h_row_cap = 0;
     // profiling
     bool profiling = false;
     std::vector<ProfEvent> prof_events;
@@ -116,42 +118,6 @@ uint32_t bits_for(uint32_t n) {  // bits to hold indices 0..n-1, at least 1
     return b;
 }
 
-void free_table(DevTable& t) {
-    if (t.keys64) cudaFree(t.keys64);
-    if (t.keys128) cudaFree(t.keys128);
-    if (t.counts) cudaFree(t.counts);
-    t.keys64 = nullptr;
-    t.keys128 = nullptr;
-    t.counts = nullptr;
-}
-
-// kind: 0 dense (capacity = number of counters), 1 hash+counts, 2 hash set
-int alloc_table(bc_ctx* ctx, DevTable& t, int kind, int wide, unsigned long long capacity, unsigned long long* n_entries) {
-    t = DevTable{};
-    t.kind = kind;
-    t.wide = wide;
-    t.n_entries = n_entries;
-    if (kind == 0) {
-        t.cap_mask = capacity;
-        CK(ctx, cudaMalloc(&t.counts, capacity * sizeof(unsigned long long)));
-        CK(ctx, cudaMemsetAsync(t.counts, 0, capacity * sizeof(unsigned long long), ctx->stream));
-        return BC_OK;
-    }
-    t.cap_mask = capacity - 1;
-    if (wide) {
-        CK(ctx, cudaMalloc(&t.keys128, capacity * sizeof(ulonglong2)));
-        CK(ctx, cudaMemsetAsync(t.keys128, 0xFF, capacity * sizeof(ulonglong2), ctx->stream));
-    } else {
-        CK(ctx, cudaMalloc(&t.keys64, capacity * sizeof(unsigned long long)));
-        CK(ctx, cudaMemsetAsync(t.keys64, 0xFF, capacity * sizeof(unsigned long long), ctx->stream));
-    }
-    if (kind == 1) {
-        CK(ctx, cudaMalloc(&t.counts, capacity * sizeof(unsigned long long)));
-        CK(ctx, cudaMemsetAsync(t.counts, 0, capacity * sizeof(unsigned long long), ctx->stream));
-    }
-    return BC_OK;
-}
-
 struct ProfScope {  // CUDA events around one launch, only while profiling is on
     bc_ctx* ctx;
     int kind;
@@ -182,13 +148,60 @@ void drain_profile(bc_ctx* ctx) {
     ctx->prof_events.clear();
 }
 
+void free_table(DevTable& t) {
+    if (t.data) cudaFree(t.data);
+    t.data = nullptr;
+}
+
+size_t table_bytes(const DevTable& t) { return (size_t)t.cap * table_stride(t.kind, t.wide) * sizeof(unsigned long long); }
+
+int clear_table(bc_ctx* ctx, DevTable& t) {
+    if (!t.data) return BC_OK;
+    if (t.kind == 1) {  // {key = empty, count = 0} slots: one pass of 16-byte stores
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_clear_map(t, ctx->stream));
+    } else {
+        CK(ctx, cudaMemsetAsync(t.data, t.kind == 0 ? 0 : 0xFF, table_bytes(t), ctx->stream));
+    }
+    return BC_OK;
+}
+
+// kind: 0 dense (cap = number of counters), 1 hash map, 2 hash set
+int alloc_table(bc_ctx* ctx, DevTable& t, int kind, int wide, unsigned long long cap, unsigned long long* n_entries) {
+    t = DevTable{};
+    t.kind = kind;
+    t.wide = wide;
+    t.cap = cap;
+    t.n_entries = n_entries;
+    CK(ctx, cudaMalloc(&t.data, table_bytes(t)));
+    return clear_table(ctx, t);
+}
+
+// slots for `entries` keys at load factor <= 0.6
+unsigned long long slots_for(unsigned long long entries) {
+    const unsigned long long c = entries + entries * 2 / 3 + 1024;
+    return c;
+}
+
 void drop_rows(bc_ctx* ctx) {
+    ctx->n_rows = 0;
+    ctx->rows_valid = false;
+}
+
+int reserve_rows(bc_ctx* ctx, unsigned long long n, bool wide) {
+    if (n <= ctx->row_cap && (!wide || ctx->d_row_hi)) return BC_OK;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_row_lo) cudaFree(ctx->d_row_lo);
     if (ctx->d_row_hi) cudaFree(ctx->d_row_hi);
     if (ctx->d_row_cnt) cudaFree(ctx->d_row_cnt);
     ctx->d_row_lo = ctx->d_row_hi = ctx->d_row_cnt = nullptr;
-    ctx->n_rows = 0;
-    ctx->rows_valid = false;
+    ctx->row_cap = 0;
+    const unsigned long long cap = std::max<unsigned long long>(n + n / 8, 1024);
+    CK(ctx, cudaMalloc(&ctx->d_row_lo, cap * sizeof(unsigned long long)));
+    CK(ctx, cudaMalloc(&ctx->d_row_cnt, cap * sizeof(unsigned long long)));
+    if (wide) CK(ctx, cudaMalloc(&ctx->d_row_hi, cap * sizeof(unsigned long long)));
+    ctx->row_cap = cap;
+    return BC_OK;
 }
 
 // Smallest integer sum S with fl32(fl32(S) / fl32(len)) >= min_quality: the reference's f32 mean test
@@ -276,30 +289,38 @@ int release_staging(bc_ctx* ctx, int staged) {
     return BC_OK;
 }
 
-// keep the load factor of the hash kinds <= 0.5 (entries are bounded by reads submitted)
-int ensure_capacity(bc_ctx* ctx, unsigned long long incoming) {
-    if (ctx->table.kind == 0) return BC_OK;
-    ctx->entries_upper += incoming;
-    if (2 * ctx->entries_upper <= ctx->table_capacity) return BC_OK;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    unsigned long long n = 0;
-    CK(ctx, cudaMemcpy(&n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
-    ctx->entries_upper = n + incoming;
-    unsigned long long cap = ctx->table_capacity;
-    while (2 * ctx->entries_upper > cap) cap <<= 1;
-    if (cap == ctx->table_capacity) return BC_OK;
+int grow_table(bc_ctx* ctx, DevTable& t, unsigned long long need_entries) {
+    if (t.kind == 0 || !t.data) return BC_OK;
+    if (slots_for(need_entries) <= t.cap) return BC_OK;
+    unsigned long long cap = t.cap;
+    while (cap < slots_for(need_entries)) cap *= 2;
     DevTable bigger;
-    int rc = alloc_table(ctx, bigger, ctx->table.kind, ctx->table.wide, cap, ctx->table.n_entries);
+    int rc = alloc_table(ctx, bigger, t.kind, t.wide, cap, t.n_entries);
     if (rc != BC_OK) return rc;
     {
         ProfScope p(ctx, BC_K_OTHER);
-        CK(ctx, launch_rehash(ctx->table, bigger, ctx->stream));
+        CK(ctx, launch_rehash(t, bigger, ctx->stream));
     }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    free_table(ctx->table);
-    ctx->table = bigger;
-    ctx->table_capacity = cap;
+    free_table(t);
+    t = bigger;
     return BC_OK;
+}
+
+// keep the load factor of the hash tables <= 0.6 (entries are bounded by the reads submitted so far)
+int ensure_capacity(bc_ctx* ctx, unsigned long long incoming) {
+    Tables& T = ctx->tables;
+    if (T.map.kind == 0 && !T.has_set) return BC_OK;
+    ctx->entries_upper += incoming;
+    const unsigned long long smallest = std::min(T.map.kind ? T.map.cap : ~0ull, T.has_set ? T.set.cap : ~0ull);
+    if (slots_for(ctx->entries_upper) <= smallest) return BC_OK;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long n[2] = {0, 0};
+    CK(ctx, cudaMemcpy(n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
+    ctx->entries_upper = std::max(n[0], n[1]) + incoming;
+    int rc = grow_table(ctx, T.map, n[0] + incoming);
+    if (rc == BC_OK && T.has_set) rc = grow_table(ctx, T.set, n[1] + incoming);
+    return rc;
 }
 
 }  // namespace
@@ -318,9 +339,15 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drain_profile(ctx);
-    drop_rows(ctx);
+    if (ctx->d_row_lo) cudaFree(ctx->d_row_lo);
+    if (ctx->d_row_hi) cudaFree(ctx->d_row_hi);
+    if (ctx->d_row_cnt) cudaFree(ctx->d_row_cnt);
+    if (ctx->h_row_lo) cudaFreeHost(ctx->h_row_lo);
+    if (ctx->h_row_hi) cudaFreeHost(ctx->h_row_hi);
+    if (ctx->h_row_cnt) cudaFreeHost(ctx->h_row_cnt);
     if (ctx->d_row_n) cudaFree(ctx->d_row_n);
-    free_table(ctx->table);
+    free_table(ctx->tables.map);
+    free_table(ctx->tables.set);
     for (Staging& s : ctx->staging) {
         if (s.planes) cudaFree(s.planes);
         if (s.read_len) cudaFree(s.read_len);
@@ -635,19 +662,19 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     }
     CKC(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
 
-    // ---- counters and the main table
-    CKC(cudaMalloc(&ctx->d_counters, (BC_N_COUNTERS + 1) * sizeof(unsigned long long)));
-    CKC(cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
+    // ---- counters and the tables
+    CKC(cudaMalloc(&ctx->d_counters, (BC_N_COUNTERS + 2) * sizeof(unsigned long long)));
+    CKC(cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 2) * sizeof(unsigned long long), ctx->stream));
     CKC(cudaMalloc(&ctx->d_row_n, sizeof(unsigned long long)));
     const unsigned long long hint = expected_reads ? expected_reads : (1ull << 20);
     int rc;
-    if (!d.has_umi && d.key_bits <= 27) {
-        ctx->table_capacity = 1ull << d.key_bits;
-        rc = alloc_table(ctx, ctx->table, 0, 0, ctx->table_capacity, ctx->d_counters + BC_N_COUNTERS);
-    } else {
-        ctx->table_capacity = pow2_at_least(2 * hint);
-        rc = alloc_table(ctx, ctx->table, d.has_umi ? 2 : 1, d.wide, ctx->table_capacity, ctx->d_counters + BC_N_COUNTERS);
-    }
+    Tables& T = ctx->tables;
+    T.umi_bits = d.umi_bits;
+    T.has_set = d.has_umi ? 1 : 0;
+    const uint32_t map_bits = d.key_bits - d.umi_bits;
+    if (map_bits <= 27) rc = alloc_table(ctx, T.map, 0, 0, 1ull << map_bits, ctx->d_counters + BC_N_COUNTERS);
+    else rc = alloc_table(ctx, T.map, 1, map_bits > 63, slots_for(hint), ctx->d_counters + BC_N_COUNTERS);
+    if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, d.wide, slots_for(hint), ctx->d_counters + BC_N_COUNTERS + 1);
     if (rc != BC_OK) {
         g_create_error = ctx->err;
         bc_destroy(ctx);
@@ -695,11 +722,11 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, deferred, flags, ctx->stream));
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, deferred, flags, ctx->stream));
     }
     if (!(flags & F_LOCATE_ONLY)) {
         ProfScope p(ctx, BC_K_SCAN);
-        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->table, counters, out, route, deferred, flags, ctx->stream));
+        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, deferred, flags, ctx->stream));
     }
     return release_staging(ctx, staged);
 }
@@ -801,90 +828,62 @@ int bc_decode_only(bc_ctx* ctx, const bc_batch* batch, bc_decode_out* out) {
 
 void bc_table_free(bc_table* t) {
     if (!t) return;
-    free(t->key_lo);
-    free(t->key_hi);
-    free(t->count);
-    free(t->mask);
+    if (!(t->flags & BC_TABLE_BORROWED)) {
+        free(t->key_lo);
+        free(t->key_hi);
+        free(t->count);
+        free(t->mask);
+    }
     memset(t, 0, sizeof *t);
 }
 
+// appends device rows to a malloc-owned host table (small tables: enrichment marginals)
 static int rows_to_host(bc_ctx* ctx, const unsigned long long* lo, const unsigned long long* hi, const unsigned long long* cnt,
-                        unsigned long long n, uint32_t mask, bool with_mask, bc_table* t) {
+                        unsigned long long n, uint32_t mask, bc_table* t) {
     const uint64_t old = t->n_rows;
     const uint64_t tot = old + n;
     if (tot == 0) return BC_OK;
     t->key_lo = (uint64_t*)realloc(t->key_lo, tot * sizeof(uint64_t));
     t->key_hi = (uint64_t*)realloc(t->key_hi, tot * sizeof(uint64_t));
     t->count = (uint64_t*)realloc(t->count, tot * sizeof(uint64_t));
-    if (with_mask) t->mask = (uint32_t*)realloc(t->mask, tot * sizeof(uint32_t));
-    if (!t->key_lo || !t->key_hi || !t->count || (with_mask && !t->mask)) return fail(ctx, BC_ENOMEM, "host rows");
+    t->mask = (uint32_t*)realloc(t->mask, tot * sizeof(uint32_t));
+    if (!t->key_lo || !t->key_hi || !t->count || !t->mask) return fail(ctx, BC_ENOMEM, "host rows");
     if (n) {
         CK(ctx, cudaMemcpy(t->key_lo + old, lo, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        CK(ctx, cudaMemcpy(t->key_hi + old, hi, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (hi) CK(ctx, cudaMemcpy(t->key_hi + old, hi, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        else memset(t->key_hi + old, 0, n * sizeof(uint64_t));
         CK(ctx, cudaMemcpy(t->count + old, cnt, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        ctx->prof.d2h_bytes += 3 * n * sizeof(uint64_t);
+        ctx->prof.d2h_bytes += (hi ? 3 : 2) * n * sizeof(uint64_t);
     }
-    if (with_mask)
-        for (uint64_t i = old; i < tot; i++) t->mask[i] = mask;
+    for (uint64_t i = old; i < tot; i++) t->mask[i] = mask;
     t->n_rows = tot;
     return BC_OK;
 }
 
-// table -> compact device rows
-static int compact_rows(bc_ctx* ctx, const DevTable& t, unsigned long long upper, unsigned long long** lo,
-                        unsigned long long** hi, unsigned long long** cnt, unsigned long long* n) {
-    *lo = *hi = *cnt = nullptr;
-    const unsigned long long cap = upper ? upper : 1;
-    CK(ctx, cudaMalloc(lo, cap * sizeof(unsigned long long)));
-    CK(ctx, cudaMalloc(hi, cap * sizeof(unsigned long long)));
-    CK(ctx, cudaMalloc(cnt, cap * sizeof(unsigned long long)));
-    CK(ctx, cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream));
-    {
-        ProfScope p(ctx, BC_K_FINISH);
-        CK(ctx, launch_compact(t, *lo, *hi, *cnt, ctx->d_row_n, ctx->stream));
-    }
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    CK(ctx, cudaMemcpy(n, ctx->d_row_n, sizeof *n, cudaMemcpyDeviceToHost));
-    return BC_OK;
-}
-
+// the map's occupied entries -> ctx row buffers (device)
 static int build_rows(bc_ctx* ctx) {
     if (ctx->rows_valid) return BC_OK;
     int rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     drop_rows(ctx);
-    unsigned long long h[BC_N_COUNTERS + 1];
-    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    const unsigned long long entries = h[BC_N_COUNTERS];
-    if (ctx->table.kind == 0) {
-        // at most one row per counted read, at most one per counter
-        unsigned long long upper = h[BC_CNT_MATCHED] < ctx->table_capacity ? h[BC_CNT_MATCHED] : ctx->table_capacity;
-        rc = compact_rows(ctx, ctx->table, upper, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
-    } else if (ctx->table.kind == 1) {
-        rc = compact_rows(ctx, ctx->table, entries, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
+    const DevTable& M = ctx->tables.map;
+    unsigned long long upper;
+    if (M.kind == 0) {  // at most one row per counter and per matched read
+        unsigned long long h[BC_N_COUNTERS];
+        CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+        upper = std::min<unsigned long long>(h[BC_CNT_MATCHED], M.cap);
     } else {
-        // UMI set -> number of distinct random barcodes per key (output.rs:265-270)
-        unsigned long long* d_n = nullptr;
-        CK(ctx, cudaMalloc(&d_n, sizeof(unsigned long long)));
-        CK(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
-        DevTable grouped;
-        const int wide = (ctx->cfg.key_bits - ctx->cfg.umi_bits) > 63;
-        rc = alloc_table(ctx, grouped, 1, wide, pow2_at_least(2 * (entries ? entries : 1)), d_n);
-        if (rc == BC_OK) {
-            {
-                ProfScope p(ctx, BC_K_FINISH);
-                cudaError_t e = launch_group(ctx->table, ctx->cfg.umi_bits, grouped, ctx->stream);
-                if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_group: %s", cudaGetErrorString(e));
-            }
-            unsigned long long keys = 0;
-            if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "group sync");
-            if (rc == BC_OK && cudaMemcpy(&keys, d_n, sizeof keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "group count");
-            if (rc == BC_OK) rc = compact_rows(ctx, grouped, keys, &ctx->d_row_lo, &ctx->d_row_hi, &ctx->d_row_cnt, &ctx->n_rows);
-        }
-        free_table(grouped);
-        cudaFree(d_n);
+        CK(ctx, cudaMemcpy(&upper, ctx->d_counters + BC_N_COUNTERS, sizeof upper, cudaMemcpyDeviceToHost));
     }
+    rc = reserve_rows(ctx, upper, M.wide != 0);
     if (rc != BC_OK) return rc;
+    CK(ctx, cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_FINISH);
+        CK(ctx, launch_compact(M, ctx->d_row_lo, M.wide ? ctx->d_row_hi : nullptr, ctx->d_row_cnt, ctx->d_row_n, ctx->stream));
+    }
+    CK(ctx, cudaMemcpyAsync(&ctx->n_rows, ctx->d_row_n, sizeof ctx->n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->rows_valid = true;
     return BC_OK;
 }
@@ -895,7 +894,33 @@ int bc_finish(bc_ctx* ctx, bc_table* rows) {
     memset(rows, 0, sizeof *rows);
     int rc = build_rows(ctx);
     if (rc != BC_OK) return rc;
-    return rows_to_host(ctx, ctx->d_row_lo, ctx->d_row_hi, ctx->d_row_cnt, ctx->n_rows, 0, false, rows);
+    const unsigned long long n = ctx->n_rows;
+    const bool wide = ctx->tables.map.wide != 0;
+    if (n > ctx->h_row_cap || (wide && !ctx->h_row_hi)) {  // pinned mirror, grow-only
+        if (ctx->h_row_lo) cudaFreeHost(ctx->h_row_lo);
+        if (ctx->h_row_hi) cudaFreeHost(ctx->h_row_hi);
+        if (ctx->h_row_cnt) cudaFreeHost(ctx->h_row_cnt);
+        ctx->h_row_lo = ctx->h_row_hi = ctx->h_row_cnt = nullptr;
+        ctx->h_row_cap = 0;
+        const unsigned long long cap = std::max<unsigned long long>(n + n / 8, 1024);
+        CK(ctx, cudaHostAlloc((void**)&ctx->h_row_lo, cap * sizeof(uint64_t), cudaHostAllocDefault));
+        CK(ctx, cudaHostAlloc((void**)&ctx->h_row_cnt, cap * sizeof(uint64_t), cudaHostAllocDefault));
+        if (wide) CK(ctx, cudaHostAlloc((void**)&ctx->h_row_hi, cap * sizeof(uint64_t), cudaHostAllocDefault));
+        ctx->h_row_cap = cap;
+    }
+    if (n) {
+        CK(ctx, cudaMemcpyAsync(ctx->h_row_lo, ctx->d_row_lo, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(ctx->h_row_cnt, ctx->d_row_cnt, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (wide) CK(ctx, cudaMemcpyAsync(ctx->h_row_hi, ctx->d_row_hi, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->prof.d2h_bytes += (wide ? 3 : 2) * n * sizeof(uint64_t);
+    }
+    rows->n_rows = n;
+    rows->key_lo = ctx->h_row_lo;
+    rows->key_hi = wide ? ctx->h_row_hi : nullptr;
+    rows->count = ctx->h_row_cnt;
+    rows->flags = BC_TABLE_BORROWED;
+    return BC_OK;
 }
 
 // key mask keeping the sample field and the counted barcodes listed in `keep` (bit k = k-th counted barcode)
@@ -921,26 +946,39 @@ static int one_marginal(bc_ctx* ctx, uint32_t keep, bc_table* out) {
     Key mask;
     uint32_t kept_bits;
     marginal_mask(ctx, keep, &mask, &kept_bits);
-    unsigned long long cap = pow2_at_least(2 * (ctx->n_rows ? ctx->n_rows : 1));
-    if (kept_bits < 40 && (2ull << kept_bits) < cap) cap = pow2_at_least(2ull << kept_bits);
+    unsigned long long entries = ctx->n_rows ? ctx->n_rows : 1;
+    if (kept_bits < 40 && (1ull << kept_bits) < entries) entries = 1ull << kept_bits;
     unsigned long long* d_n = nullptr;
     CK(ctx, cudaMalloc(&d_n, sizeof(unsigned long long)));
     CK(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
     DevTable t;
-    const int wide = (ctx->cfg.key_bits - ctx->cfg.umi_bits) > 63;
-    int rc = alloc_table(ctx, t, 1, wide, cap, d_n);
+    const int wide = ctx->tables.map.wide;
+    int rc = alloc_table(ctx, t, 1, wide, slots_for(entries), d_n);
     unsigned long long *lo = nullptr, *hi = nullptr, *cnt = nullptr, n = 0;
     if (rc == BC_OK) {
         {
             ProfScope p(ctx, BC_K_FINISH);
-            cudaError_t e = launch_marginal(ctx->d_row_lo, ctx->d_row_hi, ctx->d_row_cnt, ctx->n_rows, mask, t, ctx->stream);
+            cudaError_t e = launch_marginal(ctx->d_row_lo, wide ? ctx->d_row_hi : nullptr, ctx->d_row_cnt, ctx->n_rows, mask, t, ctx->stream);
             if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_marginal: %s", cudaGetErrorString(e));
         }
         unsigned long long keys = 0;
         if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "marginal sync");
         if (rc == BC_OK && cudaMemcpy(&keys, d_n, sizeof keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "marginal count");
-        if (rc == BC_OK) rc = compact_rows(ctx, t, keys, &lo, &hi, &cnt, &n);
-        if (rc == BC_OK) rc = rows_to_host(ctx, lo, hi, cnt, n, keep, true, out);
+        const unsigned long long cap = keys ? keys : 1;
+        if (rc == BC_OK && (cudaMalloc(&lo, cap * 8) != cudaSuccess || cudaMalloc(&cnt, cap * 8) != cudaSuccess ||
+                            (wide && cudaMalloc(&hi, cap * 8) != cudaSuccess)))
+            rc = fail(ctx, BC_ENOMEM, "marginal rows");
+        if (rc == BC_OK) {
+            cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream);
+            {
+                ProfScope p(ctx, BC_K_FINISH);
+                cudaError_t e = launch_compact(t, lo, hi, cnt, ctx->d_row_n, ctx->stream);
+                if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_compact: %s", cudaGetErrorString(e));
+            }
+            if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "compact sync");
+            if (rc == BC_OK && cudaMemcpy(&n, ctx->d_row_n, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "compact count");
+        }
+        if (rc == BC_OK) rc = rows_to_host(ctx, lo, hi, cnt, n, keep, out);
     }
     if (lo) cudaFree(lo);
     if (hi) cudaFree(hi);
@@ -1033,7 +1071,7 @@ int bc_insert_records(bc_ctx* ctx, const bc_record* dev_records, uint64_t n) {
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
     ProfScope p(ctx, BC_K_INSERT);
-    CK(ctx, launch_insert(ctx->table, nullptr, nullptr, reinterpret_cast<const Key*>(dev_records), nullptr, n, ctx->d_counters, ctx->stream));
+    CK(ctx, launch_insert(ctx->tables, nullptr, nullptr, reinterpret_cast<const Key*>(dev_records), nullptr, n, ctx->d_counters, ctx->stream));
     return BC_OK;
 }
 
@@ -1043,7 +1081,7 @@ int bc_export_rows(bc_ctx* ctx, uint64_t** dev_key_lo, uint64_t** dev_key_hi, ui
     int rc = build_rows(ctx);
     if (rc != BC_OK) return rc;
     *dev_key_lo = reinterpret_cast<uint64_t*>(ctx->d_row_lo);
-    *dev_key_hi = reinterpret_cast<uint64_t*>(ctx->d_row_hi);
+    *dev_key_hi = ctx->tables.map.wide ? reinterpret_cast<uint64_t*>(ctx->d_row_hi) : nullptr;
     *dev_count = reinterpret_cast<uint64_t*>(ctx->d_row_cnt);
     *n_rows = ctx->n_rows;
     return BC_OK;
@@ -1060,7 +1098,7 @@ int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
     ProfScope p(ctx, BC_K_INSERT);
-    CK(ctx, launch_insert(ctx->table, reinterpret_cast<const unsigned long long*>(dev_key_lo),
+    CK(ctx, launch_insert(ctx->tables, reinterpret_cast<const unsigned long long*>(dev_key_lo),
                           reinterpret_cast<const unsigned long long*>(dev_key_hi), nullptr,
                           reinterpret_cast<const unsigned long long*>(dev_count), n_rows, nullptr, ctx->stream));
     return BC_OK;
@@ -1082,18 +1120,11 @@ int bc_reset(bc_ctx* ctx) {
     int rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     drop_rows(ctx);
-    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
-    const unsigned long long cap = ctx->table_capacity;
-    if (ctx->table.kind == 0) {
-        CK(ctx, cudaMemsetAsync(ctx->table.counts, 0, cap * sizeof(unsigned long long), ctx->stream));
-    } else {
-        if (ctx->table.wide) CK(ctx, cudaMemsetAsync(ctx->table.keys128, 0xFF, cap * sizeof(ulonglong2), ctx->stream));
-        else CK(ctx, cudaMemsetAsync(ctx->table.keys64, 0xFF, cap * sizeof(unsigned long long), ctx->stream));
-        if (ctx->table.counts) CK(ctx, cudaMemsetAsync(ctx->table.counts, 0, cap * sizeof(unsigned long long), ctx->stream));
-    }
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 2) * sizeof(unsigned long long), ctx->stream));
+    rc = clear_table(ctx, ctx->tables.map);
+    if (rc == BC_OK && ctx->tables.has_set) rc = clear_table(ctx, ctx->tables.set);
     ctx->entries_upper = 0;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return BC_OK;
+    return rc;  // asynchronous: later work on the ctx stream is ordered after the clears
 }
 
 // ---------------------------------------------------------------------------------------------- measurement
@@ -1111,11 +1142,11 @@ int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
     drain_profile(ctx);
     unsigned long long n = 0;
     CK(ctx, cudaMemcpy(&n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
-    ctx->prof.table_capacity = ctx->table_capacity;
+    ctx->prof.table_capacity = ctx->tables.map.cap;
     ctx->prof.table_entries = n;
     ctx->prof.key_bits = ctx->cfg.key_bits;
-    ctx->prof.wide_keys = ctx->table.wide;
-    ctx->prof.dense_table = ctx->table.kind == 0;
+    ctx->prof.wide_keys = ctx->cfg.wide;
+    ctx->prof.dense_table = ctx->tables.map.kind == 0;
     *out = ctx->prof;
     return BC_OK;
 }

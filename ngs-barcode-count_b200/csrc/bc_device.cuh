@@ -70,15 +70,28 @@ struct BatchView {
     uint32_t n_reads, plane_stride, qual_stride, W;
 };
 
-// Main table.  kind: 0 dense counts (index = key), 1 hash with counts, 2 hash set (UMI mode, no counts).
+// Open-addressing tables.  kind 0: dense counts (index = key); kind 1: hash map key -> count; kind 2: hash set.
+// A map slot keeps key and count side by side so that one read touches one 32-byte sector:
+//   map narrow {key, count}   map wide {lo, hi, count, 0}   set narrow {key}   set wide {lo, hi}
 struct DevTable {
-    unsigned long long* keys64;   // narrow keys
-    ulonglong2* keys128;          // wide keys
-    unsigned long long* counts;   // dense / hash-with-counts
-    unsigned long long cap_mask;  // capacity - 1 (hash) ; capacity (dense)
+    unsigned long long* data;
+    unsigned long long cap;  // slots (any size: the home slot is mulhi(hash, cap))
     unsigned long long* n_entries;
     int kind;
     int wide;
+};
+__host__ __device__ __forceinline__ uint32_t table_stride(int kind, int wide) {  // u64 words per slot
+    return kind == 0 ? 1u : kind == 1 ? (wide ? 4u : 2u) : (wide ? 2u : 1u);
+}
+
+// What a matched read is counted into (info.rs:735-808).  Without a random barcode: map[key] += 1.  With one the
+// (key, UMI) pair goes into `set` and only a pair seen for the first time bumps map[key] (info.rs:780-791), so the
+// map always holds the final counts (output.rs:265-270) and nothing has to be regrouped at the end.
+struct Tables {
+    DevTable map;
+    DevTable set;
+    uint32_t umi_bits;
+    int has_set;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -133,47 +146,58 @@ __device__ __forceinline__ ulonglong2 cas128(ulonglong2* addr, ulonglong2 cmp, u
 constexpr unsigned long long kEmpty = ~0ULL;
 
 // Find-or-claim the slot of `key`.  Returns the slot index; *is_new tells whether this call claimed it.
-// Load factor is kept <= 0.5 by the host, so linear probing terminates quickly.
+// The host keeps the load factor <= 0.6, so linear probing stays short.
 __device__ __forceinline__ unsigned long long table_find_or_insert(const DevTable& t, Key key, bool* is_new) {
-    unsigned long long h = hash_key(key) & t.cap_mask;
+    unsigned long long h = __umul64hi(hash_key(key), t.cap);
+    const uint32_t stride = table_stride(t.kind, t.wide);
     if (!t.wide) {
         for (;;) {
-            unsigned long long cur = t.keys64[h];
+            unsigned long long* slot = t.data + h * stride;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
             if (cur == key.lo) { *is_new = false; return h; }
             if (cur == kEmpty) {
-                unsigned long long old = atomicCAS(&t.keys64[h], kEmpty, key.lo);
+                unsigned long long old = atomicCAS(slot, kEmpty, key.lo);
                 if (old == kEmpty) { *is_new = true; return h; }
                 if (old == key.lo) { *is_new = false; return h; }
             }
-            h = (h + 1) & t.cap_mask;
+            if (++h == t.cap) h = 0;
         }
     } else {
         const ulonglong2 empty = make_ulonglong2(kEmpty, kEmpty);
         const ulonglong2 mine = make_ulonglong2(key.lo, key.hi);
         for (;;) {
-            ulonglong2 old = cas128(&t.keys128[h], empty, mine);
+            ulonglong2 old = cas128(reinterpret_cast<ulonglong2*>(t.data + h * stride), empty, mine);
             if (old.x == kEmpty && old.y == kEmpty) { *is_new = true; return h; }
             if (old.x == key.lo && old.y == key.hi) { *is_new = false; return h; }
-            h = (h + 1) & t.cap_mask;
+            if (++h == t.cap) h = 0;
         }
     }
 }
 
-// One read's contribution (info.rs:735-808).  Returns true when the read is "matched", false when it is a
-// duplicate (only possible in UMI/set mode: info.rs:780-791).  *is_new reports a newly claimed hash slot so the
-// caller can aggregate the entry count per CTA instead of hammering one global counter.
-__device__ __forceinline__ bool table_count(const DevTable& t, Key key, unsigned long long add, bool* is_new) {
+// map[key] += add (dense: counts[key] += add)
+__device__ __forceinline__ void map_add(const DevTable& t, Key key, unsigned long long add, bool* is_new) {
     *is_new = false;
     if (t.kind == 0) {
-        atomicAdd(&t.counts[key.lo], add);
+        atomicAdd(&t.data[key.lo], add);
+        return;
+    }
+    const unsigned long long h = table_find_or_insert(t, key, is_new);
+    atomicAdd(t.data + h * (t.wide ? 4u : 2u) + (t.wide ? 2u : 1u), add);
+}
+
+// One matched read (key includes the random barcode when the scheme has one).  Returns true when the read counts as
+// "matched", false when it is a duplicate (parse.rs:65-69).
+__device__ __forceinline__ bool count_read(const Tables& T, Key key, bool* new_key, bool* new_pair) {
+    *new_key = false;
+    *new_pair = false;
+    if (!T.has_set) {
+        map_add(T.map, key, 1ULL, new_key);
         return true;
     }
-    unsigned long long h = table_find_or_insert(t, key, is_new);
-    if (t.kind == 1) {
-        atomicAdd(&t.counts[h], add);
-        return true;
-    }
-    return *is_new;
+    table_find_or_insert(T.set, key, new_pair);
+    if (!*new_pair) return false;
+    map_add(T.map, key_shr(key, T.umi_bits), 1ULL, new_key);
+    return true;
 }
 
 }  // namespace bc

@@ -255,9 +255,9 @@ __device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBi
 }
 
 // K3 for one matched read: count it (info.rs:735-808) or, multi-GPU with a random barcode, hand it to its owner rank
-__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const DevTable& table, const RouteOut& route, int flags,
-                                              Key key, bool* is_new) {
-    if (flags & F_INSERT) return table_count(table, key, 1ULL, is_new) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
+__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& tables, const RouteOut& route, int flags,
+                                              Key key, bool* new_key, bool* new_pair) {
+    if (flags & F_INSERT) return count_read(tables, key, new_key, new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
     if (flags & F_ROUTE) {
         const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
         const uint32_t slot = atomicAdd(&route.counts[owner], 1u);
@@ -273,12 +273,12 @@ constexpr int kDeferred = -3;  // thread-local status: the read went to the defe
 // in global memory and land in shared memory through three TMA bulk copies signalled on one mbarrier.
 template <int TW>
 __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg cfg, const BatchView batch,
-                                                  const DevAux aux, const DevTable table,
+                                                  const DevAux aux, const Tables tables,
                                                   unsigned long long* __restrict__ counters, const DecodeOut out,
                                                   const RouteOut route, const Deferred deferred, const int flags) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ unsigned int s_cnt[BC_N_COUNTERS + 1];
+    __shared__ unsigned int s_cnt[BC_N_COUNTERS + 2];
 
     const uint32_t tid = threadIdx.x;
     const unsigned long long base = (unsigned long long)blockIdx.x * kTile;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     uint8_t* s_q = reinterpret_cast<uint8_t*>(smem + kTile * batch.plane_stride);
     uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (batch.qual ? kTile * batch.qual_stride : 0u));
 
-    if (tid < BC_N_COUNTERS + 1) s_cnt[tid] = 0;
+    if (tid < BC_N_COUNTERS + 2) s_cnt[tid] = 0;
     {
         const uint32_t* g_pl = batch.planes + base * batch.plane_stride;
         const uint8_t* g_q = batch.qual ? batch.qual + base * batch.qual_stride : nullptr;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     }
 
     int status = -1;  // -1: thread has no read
-    bool is_new = false;
+    bool new_key = false, new_pair = false;
     int off = -1;
     bool repaired = false;
     if (tid < n_tile) {
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         key_or(key, idx, S.key_shift);
                     }
                 }
-                if (status == BC_ST_MATCHED) status = count_or_route(cfg, table, route, flags, key, &is_new);
+                if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, flags, key, &new_key, &new_pair);
             }
         }
         if (status != kDeferred && (flags & F_EMIT)) {
@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
             const unsigned b = __ballot_sync(0xFFFFFFFFu, status == st);
             if (lane == 0 && b) atomicAdd(&s_cnt[st], __popc(b));
         }
-        const unsigned bn = __ballot_sync(0xFFFFFFFFu, is_new);
+        const unsigned bn = __ballot_sync(0xFFFFFFFFu, new_key), bp = __ballot_sync(0xFFFFFFFFu, new_pair);
         if (lane == 0 && bn) atomicAdd(&s_cnt[BC_N_COUNTERS], __popc(bn));
+        if (lane == 0 && bp) atomicAdd(&s_cnt[BC_N_COUNTERS + 1], __popc(bp));
         __syncthreads();
         // status order -> counter order
         if (tid < BC_N_COUNTERS) {
@@ -432,8 +433,10 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                                             BC_CNT_SAMPLE,  BC_CNT_COUNTED,    BC_CNT_UNSUPPORTED};
             if (s_cnt[tid]) atomicAdd(&counters[map[tid]], (unsigned long long)s_cnt[tid]);
         }
-        if (tid == BC_N_COUNTERS && s_cnt[BC_N_COUNTERS] && table.n_entries)
-            atomicAdd(table.n_entries, (unsigned long long)s_cnt[BC_N_COUNTERS]);
+        if (tid == BC_N_COUNTERS && s_cnt[BC_N_COUNTERS] && tables.map.n_entries)
+            atomicAdd(tables.map.n_entries, (unsigned long long)s_cnt[BC_N_COUNTERS]);
+        if (tid == BC_N_COUNTERS + 1 && s_cnt[BC_N_COUNTERS + 1] && tables.set.n_entries)
+            atomicAdd(tables.set.n_entries, (unsigned long long)s_cnt[BC_N_COUNTERS + 1]);
     }
 }
 
@@ -512,14 +515,14 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
 }
 
 __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg cfg, const BatchView batch, const DevAux aux,
-                                                 const DevTable table, unsigned long long* __restrict__ counters,
+                                                 const Tables tables, unsigned long long* __restrict__ counters,
                                                  const DecodeOut out, const RouteOut route, const Deferred deferred,
                                                  const int flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = *deferred.count;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t W = batch.W;
-    unsigned long long c_matched = 0, c_dup = 0, c_sample = 0, c_counted = 0, c_new = 0;  // lane 0 only
+    unsigned long long c_matched = 0, c_dup = 0, c_sample = 0, c_counted = 0, c_new = 0, c_pair = 0;  // lane 0 only
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
         const uint2 item = deferred.items[w];
         const unsigned long long ri = item.x;
@@ -559,13 +562,14 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
             key_or(key, idx, S.key_shift);
         }
         if (lane == 0) {
-            bool is_new = false;
-            if (status == BC_ST_MATCHED) status = count_or_route(cfg, table, route, flags, key, &is_new);
+            bool new_key = false, new_pair = false;
+            if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, flags, key, &new_key, &new_pair);
             c_matched += status == BC_ST_MATCHED;
             c_dup += status == BC_ST_DUPLICATE;
             c_sample += status == BC_ST_SAMPLE;
             c_counted += status == BC_ST_COUNTED;
-            c_new += is_new;
+            c_new += new_key;
+            c_pair += new_pair;
             if (flags & F_EMIT) {
                 if (out.status) out.status[ri] = (uint8_t)status;
                 if (out.offset) out.offset[ri] = (int16_t)off;
@@ -580,7 +584,8 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
         if (c_dup) atomicAdd(&counters[BC_CNT_DUPLICATES], c_dup);
         if (c_sample) atomicAdd(&counters[BC_CNT_SAMPLE], c_sample);
         if (c_counted) atomicAdd(&counters[BC_CNT_COUNTED], c_counted);
-        if (c_new && table.n_entries) atomicAdd(table.n_entries, c_new);
+        if (c_new && tables.map.n_entries) atomicAdd(tables.map.n_entries, c_new);
+        if (c_pair && tables.set.n_entries) atomicAdd(tables.set.n_entries, c_pair);
     }
 }
 
@@ -589,7 +594,7 @@ size_t decode_smem_bytes(const BatchView& b) {
 }
 
 template <int TW>
-static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                                     unsigned long long* counters, const DecodeOut& out, const RouteOut& route,
                                     const Deferred& deferred, int flags, cudaStream_t stream) {
     const size_t smem = decode_smem_bytes(batch);
@@ -600,29 +605,29 @@ static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, c
         configured = smem;
     }
     const unsigned grid = (batch.n_reads + kTile - 1) / kTile;
-    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, table, counters, out, route, deferred, flags);
+    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, tables, counters, out, route, deferred, flags);
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
                           int flags, cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     switch (cfg.TW) {
-        case 1: return launch_decode_tw<1>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 2: return launch_decode_tw<2>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 3: return launch_decode_tw<3>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 4: return launch_decode_tw<4>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 5: return launch_decode_tw<5>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 6: return launch_decode_tw<6>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 7: return launch_decode_tw<7>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
-        case 8: return launch_decode_tw<8>(cfg, batch, aux, table, counters, out, route, deferred, flags, stream);
+        case 1: return launch_decode_tw<1>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 2: return launch_decode_tw<2>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 3: return launch_decode_tw<3>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 4: return launch_decode_tw<4>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 5: return launch_decode_tw<5>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 6: return launch_decode_tw<6>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 7: return launch_decode_tw<7>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 8: return launch_decode_tw<8>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // deferred reads of the batch just decoded (their number is read on the device: no host round trip)
-cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                            unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
                            int flags, cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
@@ -630,7 +635,7 @@ cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevA
     unsigned grid = (unsigned)((warps + 3) / 4);
     const unsigned cap = 148u * 16u;  // persistent warps stride over the list
     if (grid > cap) grid = cap;
-    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, table, counters, out, route, deferred, flags);
+    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, tables, counters, out, route, deferred, flags);
     return cudaGetLastError();
 }
 
@@ -652,37 +657,38 @@ cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_insert(const DevTable table, const unsigned long long* __restrict__ key_lo,
+// Records (key incl. UMI) routed from other ranks, or (key, count) rows merged from other ranks' tables.
+__global__ void k_insert(const Tables tables, const unsigned long long* __restrict__ key_lo,
                          const unsigned long long* __restrict__ key_hi, const Key* __restrict__ records,
                          const unsigned long long* __restrict__ counts, const unsigned long long n,
                          unsigned long long* __restrict__ counters) {
-    unsigned long long matched = 0, dup = 0, fresh = 0;
+    unsigned long long matched = 0, dup = 0, fresh = 0, pairs = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        Key k;
-        if (records) {
-            k = records[i];
-        } else {
-            k.lo = key_lo[i];
-            k.hi = key_hi ? key_hi[i] : 0ULL;
+        bool new_key = false, new_pair = false;
+        if (records) {  // one read each, counted like a local one
+            if (count_read(tables, records[i], &new_key, &new_pair)) matched++;
+            else dup++;
+        } else {  // rows: keys without the random barcode, counts[i] reads each
+            Key k{key_lo[i], key_hi ? key_hi[i] : 0ULL};
+            map_add(tables.map, k, counts[i], &new_key);
         }
-        bool is_new;
-        if (table_count(table, k, counts ? counts[i] : 1ULL, &is_new)) matched++;
-        else dup++;
-        if (is_new) fresh++;
+        fresh += new_key;
+        pairs += new_pair;
     }
-    // warp-reduce, then one atomic per warp
     for (int o = 16; o; o >>= 1) {
         matched += __shfl_xor_sync(0xFFFFFFFFu, matched, o);
         dup += __shfl_xor_sync(0xFFFFFFFFu, dup, o);
         fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
+        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (counters) {
             if (matched) atomicAdd(&counters[BC_CNT_MATCHED], matched);
             if (dup) atomicAdd(&counters[BC_CNT_DUPLICATES], dup);
         }
-        if (fresh && table.n_entries) atomicAdd(table.n_entries, fresh);
+        if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
+        if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
     }
 }
 
@@ -692,50 +698,47 @@ static unsigned grid_for(unsigned long long n, unsigned block) {
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-cudaError_t launch_insert(const DevTable& table, const unsigned long long* key_lo, const unsigned long long* key_hi,
+cudaError_t launch_insert(const Tables& tables, const unsigned long long* key_lo, const unsigned long long* key_hi,
                           const Key* records, const unsigned long long* counts, unsigned long long n,
                           unsigned long long* counters, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_insert<<<grid_for(n, 256), 256, 0, stream>>>(table, key_lo, key_hi, records, counts, n, counters);
+    k_insert<<<grid_for(n, 256), 256, 0, stream>>>(tables, key_lo, key_hi, records, counts, n, counters);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool table_entry(const DevTable& t, unsigned long long i, Key* k) {
+__device__ __forceinline__ bool table_entry(const DevTable& t, unsigned long long i, Key* k, unsigned long long* c) {
+    const unsigned long long* slot = t.data + i * table_stride(t.kind, t.wide);
+    if (t.kind == 0) {
+        k->lo = i;
+        k->hi = 0;
+        *c = slot[0];
+        return *c != 0;
+    }
     if (t.wide) {
-        ulonglong2 v = t.keys128[i];
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(slot);
         k->lo = v.x;
         k->hi = v.y;
+        *c = t.kind == 1 ? slot[2] : 1ULL;
         return !(v.x == kEmpty && v.y == kEmpty);
     }
-    k->lo = t.keys64[i];
+    if (t.kind == 1) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(slot);
+        k->lo = v.x;
+        k->hi = 0;
+        *c = v.y;
+        return v.x != kEmpty;
+    }
+    k->lo = slot[0];
     k->hi = 0;
+    *c = 1ULL;
     return k->lo != kEmpty;
 }
 
-__global__ void k_group(const DevTable set, const uint32_t umi_bits, const DevTable dst) {
-    const unsigned long long cap = set.cap_mask + 1;
-    unsigned long long fresh = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        Key k;
-        if (!table_entry(set, i, &k)) continue;
-        bool is_new;
-        table_count(dst, key_shr(k, umi_bits), 1ULL, &is_new);
-        if (is_new) fresh++;
-    }
-    for (int o = 16; o; o >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
-    if ((threadIdx.x & 31) == 0 && fresh && dst.n_entries) atomicAdd(dst.n_entries, fresh);
-}
-
-cudaError_t launch_group(const DevTable& set, uint32_t umi_bits, const DevTable& dst, cudaStream_t stream) {
-    k_group<<<grid_for(set.cap_mask + 1, 256), 256, 0, stream>>>(set, umi_bits, dst);
-    return cudaGetLastError();
-}
-
+// occupied entries -> dense row arrays (key_hi may be nullptr for narrow keys)
 __global__ void k_compact(const DevTable t, unsigned long long* __restrict__ key_lo, unsigned long long* __restrict__ key_hi,
                           unsigned long long* __restrict__ count, unsigned long long* __restrict__ n_rows) {
-    const unsigned long long cap = t.kind == 0 ? t.cap_mask : t.cap_mask + 1;
+    const unsigned long long cap = t.cap;
     const int lane = threadIdx.x & 31;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long start = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -745,17 +748,7 @@ __global__ void k_compact(const DevTable t, unsigned long long* __restrict__ key
         const unsigned long long i = start + it * stride;
         Key k{0, 0};
         unsigned long long c = 0;
-        bool have = false;
-        if (i < cap) {
-            if (t.kind == 0) {
-                c = t.counts[i];
-                k.lo = i;
-                have = c != 0;
-            } else {
-                have = table_entry(t, i, &k);
-                if (have) c = t.counts ? t.counts[i] : 1ULL;
-            }
-        }
+        const bool have = i < cap && table_entry(t, i, &k, &c);
         const unsigned b = __ballot_sync(0xFFFFFFFFu, have);
         if (b) {
             unsigned long long basepos = 0;
@@ -764,7 +757,7 @@ __global__ void k_compact(const DevTable t, unsigned long long* __restrict__ key
             if (have) {
                 const unsigned long long p = basepos + __popc(b & ((1u << lane) - 1u));
                 key_lo[p] = k.lo;
-                key_hi[p] = k.hi;
+                if (key_hi) key_hi[p] = k.hi;
                 count[p] = c;
             }
         }
@@ -773,8 +766,7 @@ __global__ void k_compact(const DevTable t, unsigned long long* __restrict__ key
 
 cudaError_t launch_compact(const DevTable& t, unsigned long long* key_lo, unsigned long long* key_hi,
                            unsigned long long* count, unsigned long long* n_rows, cudaStream_t stream) {
-    const unsigned long long cap = t.kind == 0 ? t.cap_mask : t.cap_mask + 1;
-    k_compact<<<grid_for(cap, 256), 256, 0, stream>>>(t, key_lo, key_hi, count, n_rows);
+    k_compact<<<grid_for(t.cap, 256), 256, 0, stream>>>(t, key_lo, key_hi, count, n_rows);
     return cudaGetLastError();
 }
 
@@ -784,9 +776,9 @@ __global__ void k_marginal(const unsigned long long* __restrict__ key_lo, const 
     unsigned long long fresh = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_rows;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        Key k{key_lo[i] & mask.lo, key_hi[i] & mask.hi};
+        Key k{key_lo[i] & mask.lo, (key_hi ? key_hi[i] : 0ULL) & mask.hi};
         bool is_new;
-        table_count(dst, k, count[i], &is_new);
+        map_add(dst, k, count[i], &is_new);
         if (is_new) fresh++;
     }
     for (int o = 16; o; o >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
@@ -801,19 +793,34 @@ cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned lon
     return cudaGetLastError();
 }
 
+// empty map: every slot {key = kEmpty, count = 0}
+__global__ void k_clear_map(ulonglong2* __restrict__ slots, const unsigned long long n16, const int wide) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        slots[i] = wide ? ((i & 1) ? make_ulonglong2(0ULL, 0ULL) : make_ulonglong2(kEmpty, kEmpty)) : make_ulonglong2(kEmpty, 0ULL);
+}
+
+cudaError_t launch_clear_map(const DevTable& t, cudaStream_t stream) {
+    const unsigned long long n16 = t.cap * (t.wide ? 2ull : 1ull);
+    k_clear_map<<<grid_for(n16, 256), 256, 0, stream>>>(reinterpret_cast<ulonglong2*>(t.data), n16, t.wide);
+    return cudaGetLastError();
+}
+
+// move every entry of `src` (hash kinds) into the larger `dst` of the same kind
 __global__ void k_rehash(const DevTable src, const DevTable dst) {
-    const unsigned long long cap = src.cap_mask + 1;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < src.cap;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         Key k;
-        if (!table_entry(src, i, &k)) continue;
+        unsigned long long c;
+        if (!table_entry(src, i, &k, &c)) continue;
         bool is_new;
-        table_count(dst, k, src.counts ? src.counts[i] : 1ULL, &is_new);
+        if (dst.kind == 1) map_add(dst, k, c, &is_new);
+        else table_find_or_insert(dst, k, &is_new);
     }
 }
 
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream) {
-    k_rehash<<<grid_for(src.cap_mask + 1, 256), 256, 0, stream>>>(src, dst);
+    k_rehash<<<grid_for(src.cap, 256), 256, 0, stream>>>(src, dst);
     return cudaGetLastError();
 }
 

@@ -38,23 +38,21 @@ struct Deferred {  // reads whose barcode step needs a search: {read index, offs
 enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8 };
 
 // counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
-cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
                           int flags, cudaStream_t stream);
-cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const DevTable& table,
+cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                            unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
                            int flags, cudaStream_t stream);
 
 // fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
 cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t* table, cudaStream_t stream);
 
-// inserts n keys (count `add` each, or counts[i]) into `table`; bumps matched/duplicates when counters != nullptr
-cudaError_t launch_insert(const DevTable& table, const unsigned long long* key_lo, const unsigned long long* key_hi,
+// records != nullptr: n reads (key incl. random barcode) counted like local ones, bumping matched/duplicates;
+// otherwise n (key, count) rows added to the map
+cudaError_t launch_insert(const Tables& tables, const unsigned long long* key_lo, const unsigned long long* key_hi,
                           const Key* records, const unsigned long long* counts, unsigned long long n,
                           unsigned long long* counters, cudaStream_t stream);
-
-// UMI set -> per-key counts: for every occupied entry of `set`, dst[key >> umi_bits] += 1
-cudaError_t launch_group(const DevTable& set, uint32_t umi_bits, const DevTable& dst, cudaStream_t stream);
 
 // occupied entries of `t` (dense: non-zero counts) appended to the row arrays; *n_rows is a device counter
 cudaError_t launch_compact(const DevTable& t, unsigned long long* key_lo, unsigned long long* key_hi,
@@ -64,6 +62,8 @@ cudaError_t launch_compact(const DevTable& t, unsigned long long* key_lo, unsign
 cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned long long* key_hi,
                             const unsigned long long* count, unsigned long long n_rows, Key mask, const DevTable& dst,
                             cudaStream_t stream);
+
+cudaError_t launch_clear_map(const DevTable& t, cudaStream_t stream);
 
 // move every entry of `src` (hash kinds) into `dst`
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);

@@ -456,7 +456,7 @@ void decode_rows(const bch_run& run, const bc_ctx* ctx, const bc_table& t, std::
     rows.resize(t.n_rows);
     for (uint64_t r = 0; r < t.n_rows; r++) {
         const uint32_t mask = t.mask ? t.mask[r] : 0;
-        if (bc_key_decode(ctx, t.key_lo[r], t.key_hi[r], mask, 0, idx.data(), str.data(), stride) != BC_OK)
+        if (bc_key_decode(ctx, t.key_lo[r], t.key_hi ? t.key_hi[r] : 0, mask, 0, idx.data(), str.data(), stride) != BC_OK)
             throw Error("bc_key_decode failed");
         DecodedRow& d = rows[r];
         d.count = t.count[r];

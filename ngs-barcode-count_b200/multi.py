@@ -133,7 +133,7 @@ class Job:
             if self.world > 1 and not self.has_umi:
                 return self._merge_rows(to_host)
             if to_host:
-                n = int(ctr.finish()["count"].size)
+                n = ctr.finish_view()[0]
             else:
                 n = ctr.export_rows()[3]
             if self.world > 1:
@@ -150,13 +150,14 @@ class Job:
 
     def _merge_rows(self, to_host):
         lo, hi, cnt, n = self.ctr.export_rows()
-        cols = [dev_tensor(p, n, self.device) for p in (lo, hi, cnt)]
+        wide = hi is not None and hi != 0
+        cols = [dev_tensor(p, n, self.device) for p in ((lo, hi, cnt) if wide else (lo, cnt))]
         parts, sizes = gather_rows_to_root(cols, n, self.rank, self.world, self.device)
         if self.rank == 0:
             for r in range(1, self.world):
                 if sizes[r]:
-                    self.ctr.import_rows(parts[0][r], parts[1][r], parts[2][r], sizes[r])
-            n_rows = int(self.ctr.finish()["count"].size) if to_host else self.ctr.export_rows()[3]
+                    self.ctr.import_rows(parts[0][r], parts[1][r] if wide else None, parts[-1][r], sizes[r])
+            n_rows = self.ctr.finish_view()[0] if to_host else self.ctr.export_rows()[3]
         else:
             n_rows = 0
         t = torch.tensor([n_rows], dtype=torch.int64, device=self.device)
