@@ -102,7 +102,8 @@ enum { BC_LOC_HOST = 0, BC_LOC_DEVICE = 1 };
  *             bc_plane_words(max_read_len) words each — lo, hi, nmask — base i at bit (i & 31) of word (i >> 5):
  *             A=(0,0) C=(1,0) G=(0,1) T=(1,1) as (lo,hi); nmask=1 where the read has 'N' (then lo=hi=0).
  *             Bits at and beyond the read length are 0.  plane_stride = bc_plane_stride(max_read_len) (3W, made odd).
- *   read_len: bases per read; bit 15 (BC_READ_UNSUPPORTED) set when the read held a character outside ACGTN.
+ *   read_len: bases per read; bit 15 (BC_READ_UNSUPPORTED) set when the read held a character outside ACGTN or a
+ *             quality character below '!' (the reference's `q - 33` underflows there, parse.rs:326).
  *   qual    : n_reads records of `qual_stride` bytes of raw FASTQ quality characters (Phred+33), or NULL when
  *             min_quality == 0.  qual_stride = bc_qual_stride(max_read_len).
  * `location` says whether the three pointers are host (pinned or pageable) or device memory. */

@@ -53,12 +53,13 @@ struct bc_ctx {
     bool quality_on = false;
     // reference accelerators
     uint4* d_refs = nullptr;
-    uint16_t* d_tables = nullptr;
+    uint32_t* d_tables = nullptr;
     unsigned long long* d_hash_keys = nullptr;
     uint32_t* d_hash_idx = nullptr;
     unsigned long long* d_half = nullptr;
     DevDeep* d_deep = nullptr;
     uint32_t* d_csr = nullptr;
+    uint4* d_bref = nullptr;
     DevAux aux{};
     // reads of the batch in flight whose barcode step needs a search (filled by k_decode, drained by k_resolve)
     uint2* d_def_items = nullptr;
@@ -362,6 +363,7 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_half) cudaFree(ctx->d_half);
     if (ctx->d_deep) cudaFree(ctx->d_deep);
     if (ctx->d_csr) cudaFree(ctx->d_csr);
+    if (ctx->d_bref) cudaFree(ctx->d_bref);
     if (ctx->d_def_items) cudaFree(ctx->d_def_items);
     if (ctx->d_def_count) cudaFree(ctx->d_def_count);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -480,7 +482,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             while (j < cfg->region_len && cfg->region_codes[j] == cfg->region_codes[i]) j++;
             if (cfg->region_codes[i] != 'C' && j < cfg->region_len) {
                 if (d.n_qruns == kMaxQRuns) FAILC(BC_EUNSUPPORTED, "more than %d quality-tested runs", kMaxQRuns);
-                d.qruns[d.n_qruns++] = DevQRun{(uint16_t)i, (uint16_t)(j - i), quality_threshold(j - i, cfg->min_quality)};
+                // the kernel sums the raw Phred+33 bytes, so the per-byte offset goes into the threshold
+                d.qruns[d.n_qruns++] = DevQRun{(uint16_t)i, (uint16_t)(j - i), quality_threshold(j - i, cfg->min_quality) + 33u * (j - i)};
             }
             i = j;
         }
@@ -523,6 +526,7 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     std::vector<unsigned long long> half;
     std::vector<DevDeep> deep;
     std::vector<uint32_t> csr;
+    std::vector<uint4> bref;
     size_t table_u16 = 0;
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         const bc_slot& S = cfg->slots[s];
@@ -536,7 +540,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         if (S.n_ref == 0) continue;
         if (!S.ref_seqs) FAILC(BC_EINVAL, "slot %u: ref_seqs is NULL", s);
         D.ref_off = (uint32_t)refs.size();
-        bool any_exactable = false, indexable = true;
+        bool any_exactable = false, indexable = true, nfree = true, one_len = true;
+        size_t first_len = 0;
         for (uint32_t i = 0; i < S.n_ref; i++) {
             const char* r = S.ref_seqs[i];
             const size_t rl = r ? strlen(r) : 0;
@@ -555,10 +560,14 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             }
             if (rl == S.len && v.z == 0) any_exactable = true;
             else indexable = false;
+            if (v.z) nfree = false;
+            if (i == 0) first_len = rl;
+            else if (rl != first_len) one_len = false;
             refs.push_back(v);
         }
         if (S.len <= 10 && S.n_ref < 0xFFFFu) {
             D.mode = MODE_TABLE;
+            D.n_inline = nfree && one_len;
             D.aux_off = (uint32_t)table_u16;
             table_u16 += (size_t)1 << (2 * S.len);
         } else if (any_exactable) {
@@ -612,10 +621,10 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
                         const uint32_t nb = 1u << (2 * kl), km = (1u << kl) - 1u;
                         dd.start_off[p] = (uint32_t)csr.size();
                         csr.resize(csr.size() + nb + 1, 0u);
-                        dd.ids_off[p] = (uint32_t)csr.size();
-                        csr.resize(csr.size() + S.n_ref, 0u);
+                        dd.ids_off[p] = (uint32_t)bref.size();
+                        bref.resize(bref.size() + S.n_ref);
                         uint32_t* start = csr.data() + dd.start_off[p];
-                        uint32_t* ids = csr.data() + dd.ids_off[p];
+                        uint4* ids = bref.data() + dd.ids_off[p];
                         auto bucket = [&](uint32_t i) {
                             const uint4 v = refs[D.ref_off + i];
                             return ((v.x >> b0) & km) | (((v.y >> b0) & km) << kl);
@@ -623,7 +632,10 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
                         for (uint32_t i = 0; i < S.n_ref; i++) start[bucket(i) + 1]++;
                         for (uint32_t b = 0; b < nb; b++) start[b + 1] += start[b];
                         std::vector<uint32_t> fill(start, start + nb);
-                        for (uint32_t i = 0; i < S.n_ref; i++) ids[fill[bucket(i)]++] = i;
+                        for (uint32_t i = 0; i < S.n_ref; i++) {
+                            const uint4 v = refs[D.ref_off + i];
+                            ids[fill[bucket(i)]++] = make_uint4(v.x, v.y, i, 0u);
+                        }
                     }
                     deep.push_back(dd);
                 }
@@ -651,10 +663,12 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         CKC(cudaMemcpyAsync(ctx->d_deep, deep.data(), deep.size() * sizeof(DevDeep), cudaMemcpyHostToDevice, ctx->stream));
         CKC(cudaMalloc(&ctx->d_csr, csr.size() * sizeof(uint32_t)));
         CKC(cudaMemcpyAsync(ctx->d_csr, csr.data(), csr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaMalloc(&ctx->d_bref, bref.size() * sizeof(uint4)));
+        CKC(cudaMemcpyAsync(ctx->d_bref, bref.data(), bref.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (table_u16) CKC(cudaMalloc(&ctx->d_tables, table_u16 * sizeof(uint16_t)));
+    if (table_u16) CKC(cudaMalloc(&ctx->d_tables, table_u16 * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_def_count, sizeof(uint32_t)));
-    ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx, ctx->d_half, ctx->d_deep, ctx->d_csr};
+    ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx, ctx->d_half, ctx->d_deep, ctx->d_csr, ctx->d_bref};
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         if (d.slots[s].mode != MODE_TABLE) continue;
         ctx->prof.launches[BC_K_OTHER]++;

@@ -33,6 +33,7 @@ struct DevSlot {
     //                Hamming distance 1 of a query (one of the halves is then error-free)
     //  block index — max_err+1 blocks; a reference within max_err of the query agrees with it on a whole block
     uint8_t has_half, n_blocks;
+    uint8_t n_inline;            // TABLE: N-free references of one length -> queries with 1-2 N resolve from the table
     uint16_t half_len0;          // bases in the first half
     uint32_t half_off, half_mask;  // two tables of half_mask+1 u64 entries {key32, id32} each, at half_off and half_off+cap
     uint32_t deep_off;           // index of this slot's DevDeep descriptor
@@ -41,12 +42,12 @@ struct DevSlot {
 struct DevDeep {  // block index of one slot (global memory, read by k_resolve only)
     uint8_t key_pos[kMaxBlocks], key_len[kMaxBlocks];  // bucket key = bases [key_pos, key_pos+key_len) of the barcode
     uint32_t start_off[kMaxBlocks];                    // first of 4^key_len + 1 u32 bucket starts (CSR) in `csr`
-    uint32_t ids_off[kMaxBlocks];                      // first of n_ref u32 reference ids in `csr`
+    uint32_t ids_off[kMaxBlocks];                      // first of n_ref {lo, hi, id, 0} references, bucket order, in `bref`
 };
 
 struct DevQRun {
     uint16_t off, len;   // position in the region walk (relative to the quality start) and length
-    uint32_t thresh;     // low quality iff sum of (q-33)&0xFF over the run < thresh  (parse.rs:352-355, Q12)
+    uint32_t thresh;     // low quality iff the sum of the run's raw Phred+33 bytes < thresh  (parse.rs:352-355, Q12)
 };
 
 struct DevCfg {

@@ -97,6 +97,42 @@ __device__ __forceinline__ uint32_t hash_exact(const DevAux& aux, const DevSlot&
     }
 }
 
+// Direct table entry (MODE_TABLE): [15:0] reference index, [23:16] smallest distance over the set, [24] several
+// references reach it.  An identical reference is entered as distance 0 without a tie (parse.rs:457,489).
+__device__ __forceinline__ uint32_t table_pick(uint32_t e, uint32_t max_err) {
+    return (!(e & 0x1000000u) && ((e >> 16) & 0xFFu) <= max_err) ? (e & 0xFFFFu) : kFail;
+}
+// A query with one or two N: d(query, c) ignoring the N positions equals the minimum over the completions x' of the
+// N positions of d(x', c), so the unique-minimum rule can be read off the completions' entries: the overall minimum
+// is the smallest entry distance, and it is unique iff every completion reaching it names one and the same reference
+// without a tie.  Valid for N-free reference sets of one length (the host sets DevSlot::n_inline only then).
+__device__ __forceinline__ uint32_t table_lookup_n(const uint32_t* __restrict__ tab, const DevSlot& S, uint32_t lo, uint32_t hi,
+                                                   uint32_t nm) {
+    const uint32_t t = __popc(nm);
+    const uint32_t n1 = (uint32_t)__ffs(nm) - 1u;
+    const uint32_t n2 = 31u - (uint32_t)__clz(nm);
+    uint32_t kmin = 256u, cand = kFail;
+    bool multi = false;
+    for (uint32_t comp = 0; comp < (1u << (2 * t)); comp++) {
+        uint32_t vlo = lo | ((comp & 1u) << n1), vhi = hi | (((comp >> 1) & 1u) << n1);
+        if (t > 1) {
+            vlo |= ((comp >> 2) & 1u) << n2;
+            vhi |= ((comp >> 3) & 1u) << n2;
+        }
+        const uint32_t e = __ldg(&tab[vlo | (vhi << S.len)]);
+        const uint32_t d = (e >> 16) & 0xFFu, id = e & 0xFFFFu;
+        const bool tie = (e & 0x1000000u) != 0;
+        if (d < kmin) {
+            kmin = d;
+            cand = id;
+            multi = tie;
+        } else if (d == kmin && (tie || id != cand)) {
+            multi = true;
+        }
+    }
+    return (!multi && kmin <= S.max_err) ? cand : kFail;
+}
+
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
     x *= 0x7feb352dU;
@@ -106,14 +142,18 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     return x;
 }
 
-// Half index probe for an N-free query that missed the exact lookup.  Every reference within distance 1 agrees
-// with the query on its first or on its second half, so it sits in one of the two probe chains.  Returns
-//   0 resolved: *idx is the unique reference at distance 1, or kFail when several tie at distance 1 (Q5) or the cap is 0
-//   1 nothing within distance 1: the caller needs the block index (distance 2..max_err) -> defer
+// Half index probe for a query that missed the exact lookup (or holds one N).  Every reference within distance 1
+// (N positions of the query never count) agrees with the query on all non-N bases of its first or of its second
+// half, so it sits in the probe chain of one completion of that half.  A reference is counted at the first half
+// it agrees on.  Returns
+//   HALF_RESOLVED: *idx is the unique reference at distance <= 1, or kFail (a tie at the minimum, Q5, or cap too small)
+//   HALF_DEEPER:   nothing within distance 1 — the block index has to look at distance 2..max_err -> defer
 enum { HALF_RESOLVED = 0, HALF_DEEPER = 1 };
-__device__ __forceinline__ int half_probe(const DevAux& aux, const DevSlot& S, uint32_t blo, uint32_t bhi, uint32_t* idx) {
+__device__ __forceinline__ int half_probe(const DevAux& aux, const DevSlot& S, uint32_t blo, uint32_t bhi, uint32_t bnm,
+                                          uint32_t* idx) {
     const uint32_t lm = lenmask(S.len);
     const uint32_t cap = S.half_mask + 1;
+    const uint32_t h0m = lenmask(S.half_len0);
     Best b{2, 0, kFail, kFail};
     bool overflow = false;
 #pragma unroll
@@ -121,28 +161,32 @@ __device__ __forceinline__ int half_probe(const DevAux& aux, const DevSlot& S, u
         const uint32_t pos0 = h ? S.half_len0 : 0u;
         const uint32_t hl = h ? (uint32_t)S.len - S.half_len0 : (uint32_t)S.half_len0;
         const uint32_t hm = lenmask(hl);
-        const uint32_t key = ((blo >> pos0) & hm) | (((bhi >> pos0) & hm) << 16);
+        const uint32_t klo = (blo >> pos0) & hm, khi = (bhi >> pos0) & hm, kn = (bnm >> pos0) & hm;
+        const uint32_t np = kn ? (uint32_t)__ffs(kn) - 1u : 0u;
         const unsigned long long* tab = aux.half + S.half_off + (h ? cap : 0u);
-        uint32_t p = mix32(key) & S.half_mask;
-        uint32_t probes = 0;
-        for (;; probes++) {
-            const unsigned long long e = __ldg(&tab[p]);
-            if (e == kEmpty) break;
-            if (probes == kHalfProbeCap) {
-                overflow = true;
-                break;
+        for (uint32_t comp = 0; comp < (kn ? 4u : 1u); comp++) {
+            const uint32_t key = (klo | ((comp & 1u) << np)) | ((khi | (((comp >> 1) & 1u) << np)) << 16);
+            uint32_t p = mix32(key) & S.half_mask;
+            for (uint32_t probes = 0;; probes++) {
+                const unsigned long long e = __ldg(&tab[p]);
+                if (e == kEmpty) break;
+                if (probes == kHalfProbeCap) {
+                    overflow = true;
+                    break;
+                }
+                if ((uint32_t)e == key) {
+                    const uint32_t id = (uint32_t)(e >> 32);
+                    const uint4 r = __ldg(&aux.refs[S.ref_off + id]);
+                    const uint32_t diff = ((blo ^ r.x) | (bhi ^ r.y)) & ~bnm & lm;
+                    if (h == 0 || (diff & h0m) != 0) best_add(b, __popc(diff), id);
+                }
+                p = (p + 1) & S.half_mask;
             }
-            if ((uint32_t)e == key) {
-                const uint32_t id = (uint32_t)(e >> 32);
-                const uint4 r = __ldg(&aux.refs[S.ref_off + id]);
-                best_add(b, __popc(((blo ^ r.x) | (bhi ^ r.y)) & lm), id);
-            }
-            p = (p + 1) & S.half_mask;
         }
     }
     if (overflow) return HALF_DEEPER;  // a crowded chain was cut short: let the block index decide
-    if (b.d <= 1) {                    // exact was a miss, so this is distance 1
-        *idx = (b.cnt == 1 && S.max_err >= 1) ? b.arg : kFail;
+    if (b.d <= 1) {
+        *idx = (b.cnt == 1 && b.d <= S.max_err) ? b.arg : kFail;
         return HALF_RESOLVED;
     }
     if (S.max_err <= 1) {
@@ -175,15 +219,20 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
         const uint32_t ah = j < W ? hi[j] : 0u, bh = j + 1 < W ? hi[j + 1] : 0u;
         const uint32_t an = j < W ? nm[j] : 0u, bn = j + 1 < W ? nm[j + 1] : 0u;
         uint32_t cand = 0;
-#pragma unroll
-        for (int s = 0; s < 32; s++) {
-            const uint32_t wl = __funnelshift_r(al, bl, s);
-            const uint32_t wh = __funnelshift_r(ah, bh, s);
-            const uint32_t wn = __funnelshift_r(an, bn, s);
-            const uint32_t x = (((wl ^ p_lo) | (wh ^ p_hi)) & p_cm) & ~wn;
-            if ((uint32_t)__popc(x) <= maxc) cand |= 1u << s;
-        }
         const int rem = nwin - (c << 5);
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+            if (g < rem) {
+#pragma unroll
+                for (int s = g; s < g + 8; s++) {
+                    const uint32_t wl = __funnelshift_r(al, bl, s);
+                    const uint32_t wh = __funnelshift_r(ah, bh, s);
+                    const uint32_t wn = __funnelshift_r(an, bn, s);
+                    const uint32_t x = (((wl ^ p_lo) | (wh ^ p_hi)) & p_cm) & ~wn;
+                    if ((uint32_t)__popc(x) <= maxc) cand |= 1u << s;
+                }
+            }
+        }
         if (rem < 32) cand &= (1u << rem) - 1u;
         while (cand) {
             const int s = __ffs(cand) - 1;
@@ -341,12 +390,22 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                 // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
                 // Q6: after a repair the quality string is read from 0, not from the repaired offset.
                 if (cfg.n_qruns) {
-                    const uint8_t* q = s_q + tid * batch.qual_stride + (repaired ? 0 : off);
+                    // byte sums with whole-word loads: dp4a against 0x01010101 adds the four bytes of a word; the
+                    // first and last word of a run are masked.  The packer guarantees every byte >= 33 ('!').
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
+                    const uint32_t q0 = repaired ? 0u : (uint32_t)off;
                     for (uint32_t r = 0; r < cfg.n_qruns; r++) {
                         const DevQRun run = cfg.qruns[r];
+                        const uint32_t a = q0 + run.off, e = a + run.len;  // bytes [a, e)
                         uint32_t sum = 0;
-                        for (uint32_t i = 0; i < run.len; i++) sum += (uint8_t)(q[run.off + i] - 33);
-                        if (sum < run.thresh) {
+                        for (uint32_t w = a >> 2; (w << 2) < e; w++) {
+                            uint32_t v = qw[w];
+                            const uint32_t lo_b = w << 2;
+                            if (lo_b < a) v &= 0xFFFFFFFFu << ((a - lo_b) << 3);
+                            if (lo_b + 4 > e) v &= 0xFFFFFFFFu >> ((lo_b + 4 - e) << 3);
+                            sum = __dp4a(v, 0x01010101u, sum);
+                        }
+                        if (sum < run.thresh) {  // thresh already includes the +33 per byte offset
                             status = BC_ST_LOW_QUALITY;
                             break;
                         }
@@ -365,17 +424,18 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         }
                         uint32_t idx = kFail;
                         bool defer = false;
-                        if (b.nm != 0 || S.mode == MODE_SCAN) {
-                            defer = true;
-                        } else if (S.mode == MODE_TABLE) {
-                            const uint32_t v = __ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]);
-                            idx = v == 0xFFFFu ? kFail : v;
-                        } else {  // MODE_HASH
-                            idx = hash_exact(aux, S, b.lo, b.hi);
+                        if (S.mode == MODE_TABLE) {
+                            if (b.nm == 0) idx = table_pick(__ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]), S.max_err);
+                            else if (S.n_inline && __popc(b.nm) <= 2) idx = table_lookup_n(aux.tables + S.aux_off, S, b.lo, b.hi, b.nm);
+                            else defer = true;
+                        } else if (S.mode == MODE_HASH) {
+                            if (b.nm == 0) idx = hash_exact(aux, S, b.lo, b.hi);
                             if (idx == kFail) {
-                                if (!S.has_half) defer = true;
-                                else defer = half_probe(aux, S, b.lo, b.hi, &idx) == HALF_DEEPER;
+                                if (!S.has_half || __popc(b.nm) > 1) defer = true;
+                                else defer = half_probe(aux, S, b.lo, b.hi, b.nm, &idx) == HALF_DEEPER;
                             }
+                        } else {
+                            defer = true;
                         }
                         if (defer) {
                             status = kDeferred;
@@ -416,16 +476,20 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     make_uint2((uint32_t)(base + tid), (uint32_t)off | (repaired ? 0x10000u : 0u));
         }
     }
-    // ---- outcome counters (info.rs:60-127): warp-aggregated, one global atomic per counter per CTA
+    // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 6-bit field (a warp adds at
+    // most 32 per field), two warp-wide REDUX sums, then per-CTA shared counters and one global atomic per counter
     if (counters) {
+        const uint32_t fa = (status >= 0 && status < 5) ? 1u << (6 * status) : 0u;
+        const uint32_t fb = (status == 5 ? 1u : 0u) | (status == 6 ? 1u << 6 : 0u) | (new_key ? 1u << 12 : 0u) | (new_pair ? 1u << 18 : 0u);
+        const uint32_t sa = __reduce_add_sync(0xFFFFFFFFu, fa), sb = __reduce_add_sync(0xFFFFFFFFu, fb);
+        if (lane == 0) {
 #pragma unroll
-        for (int st = 0; st < BC_N_COUNTERS; st++) {
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, status == st);
-            if (lane == 0 && b) atomicAdd(&s_cnt[st], __popc(b));
+            for (int f = 0; f < 5; f++)
+                if ((sa >> (6 * f)) & 63u) atomicAdd(&s_cnt[f], (sa >> (6 * f)) & 63u);
+#pragma unroll
+            for (int f = 0; f < 4; f++)
+                if ((sb >> (6 * f)) & 63u) atomicAdd(&s_cnt[5 + f], (sb >> (6 * f)) & 63u);
         }
-        const unsigned bn = __ballot_sync(0xFFFFFFFFu, new_key), bp = __ballot_sync(0xFFFFFFFFu, new_pair);
-        if (lane == 0 && bn) atomicAdd(&s_cnt[BC_N_COUNTERS], __popc(bn));
-        if (lane == 0 && bp) atomicAdd(&s_cnt[BC_N_COUNTERS + 1], __popc(bp));
         __syncthreads();
         // status order -> counter order
         if (tid < BC_N_COUNTERS) {
@@ -479,7 +543,6 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
     const DevDeep& D = aux.deep[S.deep_off];
     Best b{S.max_err + 1u, 0, kFail, kFail};
     const uint32_t lm = lenmask(S.len);
-    const uint4* refs = aux.refs + S.ref_off;
     for (uint32_t p = 0; p < S.n_blocks; p++) {
         const uint32_t kpos = D.key_pos[p], kl = D.key_len[p], km = lenmask(kl);
         const uint32_t qlo = (q.lo >> kpos) & km, qhi = (q.hi >> kpos) & km, qn = (q.nm >> kpos) & km;
@@ -487,7 +550,7 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
         const uint32_t n1 = qn ? (uint32_t)__ffs(qn) - 1u : 0u;
         const uint32_t n2 = t > 1 ? 31u - (uint32_t)__clz(qn) : 0u;
         const uint32_t* start = aux.csr + D.start_off[p];
-        const uint32_t* ids = aux.csr + D.ids_off[p];
+        const uint4* bucket_refs = aux.bref + D.ids_off[p];  // {lo, hi, id, 0} in bucket order: no second indirection
         for (uint32_t comp = 0; comp < (1u << (2 * t)); comp++) {
             uint32_t vlo = qlo, vhi = qhi;
             if (t >= 1) {
@@ -501,13 +564,12 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
             const uint32_t bucket = vlo | (vhi << kl);
             const uint32_t a = __ldg(&start[bucket]), e = __ldg(&start[bucket + 1]);
             for (uint32_t j = a + lane; j < e; j += 32) {
-                const uint32_t id = __ldg(&ids[j]);
-                const uint4 r = __ldg(&refs[id]);
+                const uint4 r = __ldg(&bucket_refs[j]);
                 const uint32_t diff = ((q.lo ^ r.x) | (q.hi ^ r.y)) & ~q.nm & lm;
                 bool earlier = false;
                 for (uint32_t pp = 0; pp < p; pp++)
                     earlier |= (diff & (lenmask(D.key_len[pp]) << D.key_pos[pp])) == 0;
-                if (!earlier) best_add(b, __popc(diff), id);
+                if (!earlier) best_add(b, __popc(diff), r.z);
             }
         }
     }
@@ -543,8 +605,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
             uint32_t idx = kFail;
             bool search = true;
             if (b.nm == 0 && S.mode == MODE_TABLE) {
-                const uint32_t v = __ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]);
-                idx = v == 0xFFFFu ? kFail : v;
+                idx = table_pick(__ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]), S.max_err);
                 search = false;  // the table already holds the result of the full search
             } else if (b.nm == 0 && S.mode == MODE_HASH) {
                 idx = hash_exact(aux, S, b.lo, b.hi);
@@ -641,16 +702,26 @@ cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevA
 
 // ---------------------------------------------------------------------------------------------------------
 // MODE_TABLE: result of the correction for every N-free barcode value, so the hot kernel does one lookup.
-__global__ void k_build_table(const DevSlot slot, const uint4* __restrict__ refs, uint16_t* __restrict__ table) {
+__global__ void k_build_table(const DevSlot slot, const uint4* __restrict__ refs, uint32_t* __restrict__ table) {
     const uint32_t n = 1u << (2 * slot.len);
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t m = lenmask(slot.len);
-    const uint32_t idx = scan_refs(refs + slot.ref_off, slot.n_ref, v & m, (v >> slot.len) & m, 0u, slot.len, slot.max_err);
-    table[v] = idx == kFail ? (uint16_t)0xFFFFu : (uint16_t)idx;
+    const uint32_t blo = v & m, bhi = (v >> slot.len) & m;
+    Best b{256u, 0, kFail, kFail};
+    for (uint32_t i = 0; i < slot.n_ref; i++) {
+        const uint4 r = __ldg(&refs[slot.ref_off + i]);
+        if (ref_same(r, blo, bhi, 0u, slot.len)) b.exact = i;
+        best_add(b, ref_dist(r, blo, bhi, 0u, slot.len, m), i);
+    }
+    uint32_t e;
+    if (b.exact != kFail) e = b.exact;                                               // distance 0, no tie
+    else if (b.cnt == 0) e = 0xFFFFu | (0xFFu << 16);                                // empty set
+    else e = (b.arg & 0xFFFFu) | (min(b.d, 255u) << 16) | (b.cnt > 1 ? 0x1000000u : 0u);
+    table[v] = e;
 }
 
-cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t* table, cudaStream_t stream) {
+cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint32_t* table, cudaStream_t stream) {
     const uint32_t n = 1u << (2 * slot.len);
     k_build_table<<<(n + 255) / 256, 256, 0, stream>>>(slot, aux.refs, table);
     return cudaGetLastError();
@@ -735,31 +806,44 @@ __device__ __forceinline__ bool table_entry(const DevTable& t, unsigned long lon
     return k->lo != kEmpty;
 }
 
-// occupied entries -> dense row arrays (key_hi may be nullptr for narrow keys)
+// occupied entries -> dense row arrays (key_hi may be nullptr for narrow keys).  A warp looks at kCompactSub x 32
+// consecutive slots per round and reserves their rows with ONE atomic, so the row counter is not the bottleneck.
+constexpr int kCompactSub = 8;
 __global__ void k_compact(const DevTable t, unsigned long long* __restrict__ key_lo, unsigned long long* __restrict__ key_hi,
                           unsigned long long* __restrict__ count, unsigned long long* __restrict__ n_rows) {
     const unsigned long long cap = t.cap;
     const int lane = threadIdx.x & 31;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long start = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    // every lane of a warp runs the same number of iterations so the ballot below is convergent
-    const unsigned long long iters = (cap + stride - 1) / stride;
-    for (unsigned long long it = 0; it < iters; it++) {
-        const unsigned long long i = start + it * stride;
-        Key k{0, 0};
-        unsigned long long c = 0;
-        const bool have = i < cap && table_entry(t, i, &k, &c);
-        const unsigned b = __ballot_sync(0xFFFFFFFFu, have);
-        if (b) {
-            unsigned long long basepos = 0;
-            if (lane == 0) basepos = atomicAdd(n_rows, (unsigned long long)__popc(b));
-            basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-            if (have) {
-                const unsigned long long p = basepos + __popc(b & ((1u << lane) - 1u));
-                key_lo[p] = k.lo;
-                if (key_hi) key_hi[p] = k.hi;
-                count[p] = c;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long span = 32ull * kCompactSub;
+    for (unsigned long long base = warp * span; base < cap; base += n_warps * span) {  // warp-uniform trip count
+        Key k[kCompactSub];
+        unsigned long long c[kCompactSub];
+        unsigned have = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < kCompactSub; j++) {
+            const unsigned long long i = base + (unsigned long long)j * 32 + lane;
+            k[j] = Key{0, 0};
+            c[j] = 0;
+            const bool h = i < cap && table_entry(t, i, &k[j], &c[j]);
+            if (h) have |= 1u << j;
+            total += __popc(__ballot_sync(0xFFFFFFFFu, h));
+        }
+        if (!total) continue;
+        unsigned long long basepos = 0;
+        if (lane == 0) basepos = atomicAdd(n_rows, (unsigned long long)total);
+        basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+        unsigned run = 0;
+#pragma unroll
+        for (int j = 0; j < kCompactSub; j++) {
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, (have >> j) & 1u);
+            if ((have >> j) & 1u) {
+                const unsigned long long p = basepos + run + __popc(bal & ((1u << lane) - 1u));
+                key_lo[p] = k[j].lo;
+                if (key_hi) key_hi[p] = k[j].hi;
+                count[p] = c[j];
             }
+            run += __popc(bal);
         }
     }
 }

@@ -22,12 +22,13 @@ struct RouteOut {  // multi-GPU: matched (key,UMI) records bucketed by owner ran
 
 struct DevAux {  // reference sets and their accelerators
     const uint4* refs;                    // {lo, hi, nm, len} per reference barcode
-    const uint16_t* tables;               // 4^len direct lookups (MODE_TABLE)
+    const uint32_t* tables;               // 4^len direct lookups (MODE_TABLE): idx | dist << 16 | tie << 24
     const unsigned long long* hash_keys;  // exact-match hash (MODE_HASH): lo | hi << 32
     const uint32_t* hash_idx;
     const unsigned long long* half;       // half index: {key32, id32} entries, kEmpty = free
     const DevDeep* deep;                  // block index descriptors
-    const uint32_t* csr;                  // block index buckets: starts and reference ids
+    const uint32_t* csr;                  // block index: bucket starts
+    const uint4* bref;                    // block index: references in bucket order, {lo, hi, id, 0}
 };
 
 struct Deferred {  // reads whose barcode step needs a search: {read index, offset | repaired << 16}
@@ -46,7 +47,7 @@ cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevA
                            int flags, cudaStream_t stream);
 
 // fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
-cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint16_t* table, cudaStream_t stream);
+cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint32_t* table, cudaStream_t stream);
 
 // records != nullptr: n reads (key incl. random barcode) counted like local ones, bumping matched/duplicates;
 // otherwise n (key, count) rows added to the map

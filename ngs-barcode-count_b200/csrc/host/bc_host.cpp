@@ -297,11 +297,15 @@ inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W
     }
     for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
     if (3 * W != ((3 * W) | 1u)) planes[3 * W] = 0;  // pad word of an even record
-    *read_len = (uint16_t)(len | (other ? BC_READ_UNSUPPORTED : 0u));
     if (qual_out) {
+        // a quality character below '!' underflows the reference's `q - 33` (parse.rs:326, Q13): flag it, never decode it
+        unsigned char lowest = 255;
+        for (uint32_t i = 0; i < len; i++) lowest = std::min<unsigned char>(lowest, (unsigned char)qual[i]);
+        if (len && lowest < 33) other = true;
         memcpy(qual_out, qual, len);
         memset(qual_out + len, '!', qual_stride - len);
     }
+    *read_len = (uint16_t)(len | (other ? BC_READ_UNSUPPORTED : 0u));
 }
 
 struct ReadRef {
