@@ -607,37 +607,42 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
                         tab[pos] = (unsigned long long)key | ((unsigned long long)i << 32);
                     }
                 }
-                // block index: max_err+1 blocks, bucketed by (up to) the first kMaxBlockKey bases of each block
-                const uint32_t P = (uint32_t)S.max_err + 1u;
-                if (P <= (uint32_t)kMaxBlocks && S.len / P >= 3 && S.n_ref >= 256) {
-                    DevDeep dd{};
-                    D.n_blocks = (uint8_t)P;
+                // block index: one level per distance cap k = 2 (or max_err if smaller) .. max_err, k+1 blocks each,
+                // bucketed by (up to) the first kMaxBlockKey bases of each block
+                if ((uint32_t)S.max_err + 1u <= (uint32_t)kMaxBlocks && S.len / ((uint32_t)S.max_err + 1u) >= 3 && S.n_ref >= 256) {
                     D.deep_off = (uint32_t)deep.size();
-                    for (uint32_t p = 0; p < P; p++) {
-                        const uint32_t b0 = p * S.len / P, b1 = (p + 1) * S.len / P;
-                        const uint32_t kl = std::min<uint32_t>(b1 - b0, kMaxBlockKey);
-                        dd.key_pos[p] = (uint8_t)b0;
-                        dd.key_len[p] = (uint8_t)kl;
-                        const uint32_t nb = 1u << (2 * kl), km = (1u << kl) - 1u;
-                        dd.start_off[p] = (uint32_t)csr.size();
-                        csr.resize(csr.size() + nb + 1, 0u);
-                        dd.ids_off[p] = (uint32_t)bref.size();
-                        bref.resize(bref.size() + S.n_ref);
-                        uint32_t* start = csr.data() + dd.start_off[p];
-                        uint4* ids = bref.data() + dd.ids_off[p];
-                        auto bucket = [&](uint32_t i) {
-                            const uint4 v = refs[D.ref_off + i];
-                            return ((v.x >> b0) & km) | (((v.y >> b0) & km) << kl);
-                        };
-                        for (uint32_t i = 0; i < S.n_ref; i++) start[bucket(i) + 1]++;
-                        for (uint32_t b = 0; b < nb; b++) start[b + 1] += start[b];
-                        std::vector<uint32_t> fill(start, start + nb);
-                        for (uint32_t i = 0; i < S.n_ref; i++) {
-                            const uint4 v = refs[D.ref_off + i];
-                            ids[fill[bucket(i)]++] = make_uint4(v.x, v.y, i, 0u);
+                    for (uint32_t k = std::min<uint32_t>(2, S.max_err); k <= S.max_err; k++) {
+                        const uint32_t P = k + 1u;
+                        DevDeep dd{};
+                        dd.n_blocks = P;
+                        dd.cap = k;
+                        for (uint32_t p = 0; p < P; p++) {
+                            const uint32_t b0 = p * S.len / P, b1 = (p + 1) * S.len / P;
+                            const uint32_t kl = std::min<uint32_t>(b1 - b0, kMaxBlockKey);
+                            dd.key_pos[p] = (uint8_t)b0;
+                            dd.key_len[p] = (uint8_t)kl;
+                            const uint32_t nb = 1u << (2 * kl), km = (1u << kl) - 1u;
+                            dd.start_off[p] = (uint32_t)csr.size();
+                            csr.resize(csr.size() + nb + 1, 0u);
+                            dd.ids_off[p] = (uint32_t)bref.size();
+                            bref.resize(bref.size() + S.n_ref);
+                            uint32_t* start = csr.data() + dd.start_off[p];
+                            uint4* ids = bref.data() + dd.ids_off[p];
+                            auto bucket = [&](uint32_t i) {
+                                const uint4 v = refs[D.ref_off + i];
+                                return ((v.x >> b0) & km) | (((v.y >> b0) & km) << kl);
+                            };
+                            for (uint32_t i = 0; i < S.n_ref; i++) start[bucket(i) + 1]++;
+                            for (uint32_t bb = 0; bb < nb; bb++) start[bb + 1] += start[bb];
+                            std::vector<uint32_t> fill(start, start + nb);
+                            for (uint32_t i = 0; i < S.n_ref; i++) {
+                                const uint4 v = refs[D.ref_off + i];
+                                ids[fill[bucket(i)]++] = make_uint4(v.x, v.y, i, 0u);
+                            }
                         }
+                        deep.push_back(dd);
+                        D.n_levels++;
                     }
-                    deep.push_back(dd);
                 }
             }
         } else {
@@ -722,6 +727,7 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
         if (rc != BC_OK) return rc;
         ctx->rows_valid = false;
     }
+    if (getenv("BC_DEBUG_NOINSERT")) flags &= ~F_INSERT;  // measurement aid: decode without the table updates
     BatchView view{};
     const int staged = stage_batch(ctx, batch, &view);
     if (staged < 0) return staged;

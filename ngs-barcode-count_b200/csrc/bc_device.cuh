@@ -31,15 +31,18 @@ struct DevSlot {
     // Exact pruned search for long barcodes (every reference as long as the slot and N-free):
     //  half index  — two hashes keyed by the first / second half of the barcode; holds every reference within
     //                Hamming distance 1 of a query (one of the halves is then error-free)
-    //  block index — max_err+1 blocks; a reference within max_err of the query agrees with it on a whole block
-    uint8_t has_half, n_blocks;
+    //  block index — levels for distance <= 2, 3, .., max_err: level k cuts the barcode into k+1 blocks; a reference
+//                within k of the query agrees with it on a whole block.  Levels are tried in turn: most misses are
+//                settled by the first one, whose buckets are small.
+    uint8_t has_half, n_levels;  // block index levels: level i is complete for distance <= 2 + i
     uint8_t n_inline;            // TABLE: N-free references of one length -> queries with 1-2 N resolve from the table
     uint16_t half_len0;          // bases in the first half
     uint32_t half_off, half_mask;  // two tables of half_mask+1 u64 entries {key32, id32} each, at half_off and half_off+cap
-    uint32_t deep_off;           // index of this slot's DevDeep descriptor
+    uint32_t deep_off;           // index of this slot's first DevDeep descriptor (one per level)
 };
 
-struct DevDeep {  // block index of one slot (global memory, read by k_resolve only)
+struct DevDeep {  // one level of a slot's block index (global memory, read by k_resolve only): n_blocks = cap + 1 blocks
+    uint32_t n_blocks, cap;
     uint8_t key_pos[kMaxBlocks], key_len[kMaxBlocks];  // bucket key = bases [key_pos, key_pos+key_len) of the barcode
     uint32_t start_off[kMaxBlocks];                    // first of 4^key_len + 1 u32 bucket starts (CSR) in `csr`
     uint32_t ids_off[kMaxBlocks];                      // first of n_ref {lo, hi, id, 0} references, bucket order, in `bref`
@@ -167,9 +170,17 @@ __device__ __forceinline__ unsigned long long table_find_or_insert(const DevTabl
         const ulonglong2 empty = make_ulonglong2(kEmpty, kEmpty);
         const ulonglong2 mine = make_ulonglong2(key.lo, key.hi);
         for (;;) {
-            ulonglong2 old = cas128(reinterpret_cast<ulonglong2*>(t.data + h * stride), empty, mine);
-            if (old.x == kEmpty && old.y == kEmpty) { *is_new = true; return h; }
-            if (old.x == key.lo && old.y == key.hi) { *is_new = false; return h; }
+            ulonglong2* slot = reinterpret_cast<ulonglong2*>(t.data + h * stride);
+            // read first: a key that is already there (hot keys!) costs a load, not a contended 128-bit CAS.  A torn
+            // read can only mix "empty" and the final value, so it never equals `mine` unless the slot holds it.
+            ulonglong2 cur;
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(cur.x), "=l"(cur.y) : "l"(slot));
+            if (cur.x == key.lo && cur.y == key.hi) { *is_new = false; return h; }
+            if (cur.x == kEmpty || cur.y == kEmpty) {
+                const ulonglong2 old = cas128(slot, empty, mine);
+                if (old.x == kEmpty && old.y == kEmpty) { *is_new = true; return h; }
+                if (old.x == key.lo && old.y == key.hi) { *is_new = false; return h; }
+            }
             if (++h == t.cap) h = 0;
         }
     }

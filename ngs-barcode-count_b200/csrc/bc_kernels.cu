@@ -524,11 +524,24 @@ __device__ __forceinline__ uint32_t warp_best(Best b, uint32_t max_err) {
     return (cnt == 1 && dmin <= max_err) ? arg : kFail;
 }
 
+constexpr uint32_t kMaxQueryN = 4;  // N per query the block index expands (4^N completions per block at most)
+
 __device__ __forceinline__ uint32_t warp_scan_all(const DevAux& aux, const DevSlot& S, const SlotBits& q, int lane) {
     Best b{S.max_err + 1u, 0, kFail, kFail};
     const uint32_t lm = lenmask(S.len);
     const uint4* refs = aux.refs + S.ref_off;
-    for (uint32_t i = lane; i < S.n_ref; i += 32) {
+    uint32_t i = lane;
+    for (; i + 96 < S.n_ref; i += 128) {  // four independent loads in flight per lane
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) r[u] = __ldg(&refs[i + 32 * u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (ref_same(r[u], q.lo, q.hi, q.nm, S.len)) b.exact = i + 32 * u;
+            best_add(b, ref_dist(r[u], q.lo, q.hi, q.nm, S.len, lm), i + 32 * u);
+        }
+    }
+    for (; i < S.n_ref; i += 32) {
         const uint4 r = __ldg(&refs[i]);
         if (ref_same(r, q.lo, q.hi, q.nm, S.len)) b.exact = i;
         best_add(b, ref_dist(r, q.lo, q.hi, q.nm, S.len, lm), i);
@@ -536,30 +549,24 @@ __device__ __forceinline__ uint32_t warp_scan_all(const DevAux& aux, const DevSl
     return warp_best(b, S.max_err);
 }
 
-// Block index: every reference within max_err of the query (N positions of the query never count) agrees with it
-// on all non-N bases of at least one of the max_err+1 blocks, hence on that block's key bases; it is then found in
-// the bucket of one completion of the key's N positions.  A reference is counted at the FIRST block it agrees on.
-__device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const DevSlot& S, const SlotBits& q, int lane) {
-    const DevDeep& D = aux.deep[S.deep_off];
-    Best b{S.max_err + 1u, 0, kFail, kFail};
-    const uint32_t lm = lenmask(S.len);
-    for (uint32_t p = 0; p < S.n_blocks; p++) {
+// Block index, one level: every reference within D.cap of the query (N positions of the query never count) agrees
+// with it on all non-N bases of at least one of the D.cap+1 blocks, hence on that block's key bases; it is then
+// found in the bucket of one completion of the key's N positions.  A reference is counted at the FIRST block it
+// agrees on.  The result is final when the smallest distance found is <= D.cap (the level is complete up to there).
+__device__ __forceinline__ void warp_scan_level(const DevAux& aux, const DevDeep& D, const SlotBits& q, uint32_t lm, int lane,
+                                                Best& b) {
+    for (uint32_t p = 0; p < D.n_blocks; p++) {
         const uint32_t kpos = D.key_pos[p], kl = D.key_len[p], km = lenmask(kl);
         const uint32_t qlo = (q.lo >> kpos) & km, qhi = (q.hi >> kpos) & km, qn = (q.nm >> kpos) & km;
-        const uint32_t t = __popc(qn);  // <= 2 (checked by the caller)
-        const uint32_t n1 = qn ? (uint32_t)__ffs(qn) - 1u : 0u;
-        const uint32_t n2 = t > 1 ? 31u - (uint32_t)__clz(qn) : 0u;
+        const uint32_t t = __popc(qn);  // <= kMaxQueryN (checked by the caller)
         const uint32_t* start = aux.csr + D.start_off[p];
         const uint4* bucket_refs = aux.bref + D.ids_off[p];  // {lo, hi, id, 0} in bucket order: no second indirection
         for (uint32_t comp = 0; comp < (1u << (2 * t)); comp++) {
             uint32_t vlo = qlo, vhi = qhi;
-            if (t >= 1) {
-                vlo |= (comp & 1u) << n1;
-                vhi |= ((comp >> 1) & 1u) << n1;
-            }
-            if (t >= 2) {
-                vlo |= ((comp >> 2) & 1u) << n2;
-                vhi |= ((comp >> 3) & 1u) << n2;
+            for (uint32_t m = qn, c = comp; m; m &= m - 1, c >>= 2) {  // deposit the completion at the N positions
+                const uint32_t pos = (uint32_t)__ffs(m) - 1u;
+                vlo |= (c & 1u) << pos;
+                vhi |= ((c >> 1) & 1u) << pos;
             }
             const uint32_t bucket = vlo | (vhi << kl);
             const uint32_t a = __ldg(&start[bucket]), e = __ldg(&start[bucket + 1]);
@@ -573,7 +580,22 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
             }
         }
     }
-    return warp_best(b, S.max_err);
+}
+
+__device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const DevSlot& S, const SlotBits& q, int lane) {
+    const uint32_t lm = lenmask(S.len);
+    for (uint32_t lv = 0; lv < S.n_levels; lv++) {
+        const DevDeep& D = aux.deep[S.deep_off + lv];
+        Best b{S.max_err + 1u, 0, kFail, kFail};
+        warp_scan_level(aux, D, q, lm, lane, b);
+        uint32_t dmin = b.d;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) dmin = min(dmin, __shfl_xor_sync(0xFFFFFFFFu, dmin, o));
+        // complete up to D.cap: a minimum within it is the true minimum with its true multiplicity; the last level
+        // (cap == max_err) also settles "nothing within the cap"
+        if (dmin <= D.cap || lv + 1 == S.n_levels) return warp_best(b, S.max_err);
+    }
+    return kFail;
 }
 
 __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg cfg, const BatchView batch, const DevAux aux,
@@ -612,7 +634,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
                 search = idx == kFail;
             }
             if (search) {
-                if (S.n_blocks && __popc(b.nm) <= 2) idx = warp_scan_blocks(aux, S, b, lane);
+                if (S.n_levels && __popc(b.nm) <= kMaxQueryN) idx = warp_scan_blocks(aux, S, b, lane);
                 else idx = warp_scan_all(aux, S, b, lane);
             }
             if (lane == 0 && out.slot_index) out.slot_index[ri * cfg.n_slots + si] = (int32_t)idx;

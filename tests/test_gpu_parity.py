@@ -404,7 +404,7 @@ def test_long_barcode_search_paths(blen, max_err, n_ref, tmp_path):
         b = list(rng.choice(refs))
         for pos in rng.sample(range(blen), rng.choice([0, 1, 1, 1, 2, 2, 3, 4, 5, 6])):
             b[pos] = rng.choice("ACGT")
-        for pos in rng.sample(range(blen), rng.choice([0, 0, 0, 1, 1, 2, 3])):
+        for pos in rng.sample(range(blen), rng.choice([0, 0, 0, 1, 1, 2, 3, 4, 5])):
             b[pos] = "N"
         seq = rand_dna(rng, rng.randint(0, 6)) + "ACGTACGTACGG" + "".join(b) + "TTGACAGTCA" + rand_dna(rng, rng.randint(1, 6))
         reads.append((seq, "I" * len(seq)))
