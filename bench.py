@@ -186,6 +186,8 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     per_gpu = args.reads or synth.WORKLOADS[args.config]["reads"]
     os.makedirs(args.workdir, exist_ok=True)

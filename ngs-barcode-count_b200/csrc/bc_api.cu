@@ -68,6 +68,7 @@ struct bc_ctx {
     // counting state: map (key -> count) and, with a random barcode, the (key, UMI) set
     Tables tables{};
     unsigned long long entries_upper = 0;  // host-side upper bound of entries added to either table
+    unsigned long long imported_rows = 0;  // rows merged in from other ranks (they add keys without bumping "matched")
     unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 2 (then: map entries, set entries)
     // staging for host batches
     Staging staging[2];
@@ -891,7 +892,7 @@ static int build_rows(bc_ctx* ctx) {
     if (M.kind == 0) {  // at most one row per counter and per matched read
         unsigned long long h[BC_N_COUNTERS];
         CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-        upper = std::min<unsigned long long>(h[BC_CNT_MATCHED], M.cap);
+        upper = std::min<unsigned long long>(h[BC_CNT_MATCHED] + ctx->imported_rows, M.cap);
     } else {
         CK(ctx, cudaMemcpy(&upper, ctx->d_counters + BC_N_COUNTERS, sizeof upper, cudaMemcpyDeviceToHost));
     }
@@ -1117,6 +1118,7 @@ int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_
     int rc = ensure_capacity(ctx, n_rows);
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
+    ctx->imported_rows += n_rows;
     ProfScope p(ctx, BC_K_INSERT);
     CK(ctx, launch_insert(ctx->tables, reinterpret_cast<const unsigned long long*>(dev_key_lo),
                           reinterpret_cast<const unsigned long long*>(dev_key_hi), nullptr,
@@ -1144,6 +1146,7 @@ int bc_reset(bc_ctx* ctx) {
     rc = clear_table(ctx, ctx->tables.map);
     if (rc == BC_OK && ctx->tables.has_set) rc = clear_table(ctx, ctx->tables.set);
     ctx->entries_upper = 0;
+    ctx->imported_rows = 0;
     return rc;  // asynchronous: later work on the ctx stream is ordered after the clears
 }
 
