@@ -265,6 +265,16 @@ def main():
                 "avg_launch_ms": dec_ms / max(1, dec_launches), "kernel_share_of_step": dec_ms / (ms_total if ms_total else 1),
                 "peak_source": peak_src, "kernel_ms": prof["ms"], "kernel_launches": prof["launches"]}
     gpu_launches = sum(prof["launches"].values())
+    if rank == 0:
+        try:  # INT-pipe peaks of this GPU (register-only microbenchmarks) and the pivot-test rate the kernel reaches
+            peaks = synth.measure_int_peaks()
+            windows = wl.read_len - wl.template_len + 1
+            roofline["int"] = {"peak_lop3_tops": peaks["lop3"], "peak_popc_tops": peaks["popc"], "peak_shf_tops": peaks["shf"],
+                               "windows_per_read": windows,
+                               "achieved_window_tests_tera_per_s": windows * per_gpu * args.steps / (dec_ms * 1e-3) / 1e12 if dec_ms else 0.0,
+                               "note": "one pivot test = 3 SHF + 3 LOP3 + 1 POPC + compare (alu pipe); peaks are lane-ops/s"}
+        except Exception as e:  # the microbenchmark is informational
+            roofline["int"] = {"error": str(e)}
 
     # ---- end to end from pinned host batches through the C ABI
     e2e = None

@@ -317,6 +317,7 @@ __device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& t
 }
 
 constexpr int kDeferred = -3;  // thread-local status: the read went to the deferred list (k_resolve finishes it)
+constexpr int kRouted = -2;    // thread-local status: matched, handed to its owner rank (which decides matched/duplicate)
 
 // k_decode: one thread per read, kTile reads per CTA.  The tile's packed planes / qualities / lengths are contiguous
 // in global memory and land in shared memory through three TMA bulk copies signalled on one mbarrier.
@@ -371,12 +372,12 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     bool new_key = false, new_pair = false;
     int off = -1;
     bool repaired = false;
+    Key key{0, 0};
     if (tid < n_tile) {
         const uint32_t* lo = s_pl + tid * batch.plane_stride;
         const uint32_t* hi = lo + W;
         const uint32_t* nm = hi + W;
         const uint32_t rl = s_len[tid];
-        Key key{0, 0};
         if (rl & BC_READ_UNSUPPORTED) {
             status = BC_ST_UNSUPPORTED;
         } else {
@@ -449,7 +450,10 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         key_or(key, idx, S.key_shift);
                     }
                 }
-                if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, flags, key, &new_key, &new_pair);
+                if (status == BC_ST_MATCHED) {
+                    if (flags & F_INSERT) status = count_read(tables, key, &new_key, &new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
+                    else if (flags & F_ROUTE) status = kRouted;  // appended to its owner's bucket below, warp-aggregated
+                }
             }
         }
         if (status != kDeferred && (flags & F_EMIT)) {
@@ -462,8 +466,21 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
         }
     }
 
-    // ---- deferred reads: one warp-aggregated append per warp
     const int lane = tid & 31;
+    // ---- multi-GPU: matched (key, UMI) records go to the bucket of their owner rank; one atomic per warp and rank
+    if (flags & F_ROUTE) {
+        const uint32_t owner = status == kRouted ? (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks) : 0xFFFFFFFFu;
+        for (uint32_t r = 0; r < route.n_ranks; r++) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, owner == r);
+            if (!m) continue;
+            const int leader = __ffs(m) - 1;
+            uint32_t at = 0;
+            if (lane == leader) at = atomicAdd(&route.counts[r], (uint32_t)__popc(m));
+            at = __shfl_sync(0xFFFFFFFFu, at, leader) + __popc(m & ((1u << lane) - 1u));
+            if (owner == r && at < route.capacity) route.buckets[(unsigned long long)r * route.capacity + at] = key;
+        }
+    }
+    // ---- deferred reads: one warp-aggregated append per warp
     {
         const unsigned dm = __ballot_sync(0xFFFFFFFFu, status == kDeferred);
         if (dm) {

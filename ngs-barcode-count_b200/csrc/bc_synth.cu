@@ -152,13 +152,51 @@ __global__ void k_generate(const bcs_config cfg, const uint8_t* __restrict__ ref
     }
 }
 
-size_t digits(uint64_t v) {
-    size_t d = 1;
-    while (v >= 10) {
-        v /= 10;
-        d++;
+// ---- INT-pipe peak microbenchmarks (register only): the denominators of the INT roofline --------
+template <int OP>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, const uint32_t seed, const int iters) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 7u, a3 = a0 * 7u + 11u;
+    uint32_t b0 = ~a0, b1 = ~a1, b2 = ~a2, b3 = ~a3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            // inline PTX so that exactly eight instructions of the kind under test are issued per step
+            if (OP == 0) {
+#define L3(d, x, y, z) asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(x), "r"(y), "r"(z))
+                L3(a0, a0, b0, a1); L3(a1, a1, b1, a2); L3(a2, a2, b2, a3); L3(a3, a3, b3, a0);
+                L3(b0, b0, a1, a2); L3(b1, b1, a2, a3); L3(b2, b2, a3, a0); L3(b3, b3, a0, a1);
+#undef L3
+            } else if (OP == 1) {
+#define PC(d, x) asm volatile("popc.b32 %0, %1;" : "=r"(d) : "r"(x))
+                PC(a0, b0); PC(a1, b1); PC(a2, b2); PC(a3, b3);
+                PC(b0, a1); PC(b1, a2); PC(b2, a3); PC(b3, a0);
+#undef PC
+            } else {
+#define SF(d, x, y, n) asm volatile("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(y), "r"(n))
+                SF(a0, a0, b0, 3); SF(a1, a1, b1, 5); SF(a2, a2, b2, 7); SF(a3, a3, b3, 9);
+                SF(b0, b0, a1, 11); SF(b1, b1, a2, 13); SF(b2, b2, a3, 15); SF(b3, b3, a0, 17);
+#undef SF
+            }
+        }
     }
-    return d;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
+}
+
+template <int OP>
+double int_peak_once(uint32_t* d_out, int grid, int iters, double ops_per_iter) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_int_peak<OP><<<grid, 256>>>(d_out, 12345u, iters / 8);
+    cudaEventRecord(e0);
+    k_int_peak<OP><<<grid, 256>>>(d_out, 12345u, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)grid * 256.0 * iters * ops_per_iter / (ms * 1e-3) / 1e12;
 }
 
 size_t name_bytes_upto(uint64_t n) {  // total decimal digits of 0..n-1
@@ -178,6 +216,25 @@ size_t name_bytes_upto(uint64_t n) {  // total decimal digits of 0..n-1
 }  // namespace
 
 extern "C" {
+
+// Measured INT throughput of this GPU in 10^12 lane-operations per second: LOP3 (3-input logic), POPC, SHF (funnel
+// shift).  out[0..2].  Returns a cudaError_t as int.
+int bcs_measure_int_peaks(double* out) {
+    uint32_t* d_out = nullptr;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8;
+    cudaError_t e = cudaMalloc(&d_out, (size_t)grid * 256 * sizeof(uint32_t));
+    if (e != cudaSuccess) return (int)e;
+    const int iters = 4096;
+    out[0] = int_peak_once<0>(d_out, grid, iters, 16.0 * 8.0);        // 8 LOP3 per unrolled step (each line fuses to one)
+    out[1] = int_peak_once<1>(d_out, grid, iters, 16.0 * 8.0);        // 8 POPC per unrolled step
+    out[2] = int_peak_once<2>(d_out, grid, iters, 16.0 * 8.0);        // 8 SHF per unrolled step
+    e = cudaDeviceSynchronize();
+    cudaFree(d_out);
+    return (int)e;
+}
 
 int bcs_generate_device(const bcs_config* cfg, const uint8_t* refs_dev, uint64_t first_read, uint64_t n_reads,
                         uint32_t max_read_len, uint32_t* planes, uint16_t* read_len, uint8_t* qual, void* cuda_stream) {

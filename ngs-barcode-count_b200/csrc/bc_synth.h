@@ -50,6 +50,10 @@ typedef struct {
 int bcs_generate_device(const bcs_config *cfg, const uint8_t *refs_dev, uint64_t first_read, uint64_t n_reads,
                         uint32_t max_read_len, uint32_t *planes, uint16_t *read_len, uint8_t *qual, void *cuda_stream);
 
+/* Register-only microbenchmarks of the INT pipes on the current device, in 10^12 lane-operations per second:
+ * out[0] LOP3 (3-input logic), out[1] POPC, out[2] SHF (funnel shift). */
+int bcs_measure_int_peaks(double *out);
+
 /* The same reads as FASTQ text ("@r<i>\nSEQ\n+\nQUAL\n") into `out`; returns bytes written, 0 when `cap` is too
  * small.  bcs_fastq_bytes gives the exact size. */
 size_t bcs_fastq_bytes(const bcs_config *cfg, uint64_t first_read, uint64_t n_reads);

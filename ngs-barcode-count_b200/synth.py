@@ -46,8 +46,19 @@ def synth_lib():
         l.bcs_fastq_bytes.argtypes = [C.POINTER(bcs_config), C.c_uint64, C.c_uint64]
         l.bcs_generate_fastq.restype = C.c_size_t
         l.bcs_generate_fastq.argtypes = [C.POINTER(bcs_config), C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint]
+        l.bcs_measure_int_peaks.restype = C.c_int
+        l.bcs_measure_int_peaks.argtypes = [C.POINTER(C.c_double)]
         _lib = l
     return _lib
+
+
+def measure_int_peaks():
+    """Measured INT-pipe peaks of the current GPU, in 10^12 lane-ops/s: dict(lop3=, popc=, shf=)."""
+    out = (C.c_double * 3)()
+    rc = synth_lib().bcs_measure_int_peaks(out)
+    if rc != 0:
+        raise BcError(f"bcs_measure_int_peaks: cudaError {rc}")
+    return dict(lop3=out[0], popc=out[1], shf=out[2])
 
 
 # ---- barcode sets with pairwise Hamming distance >= 3: shortened Hamming codes over GF(4) -------------------------
