@@ -5,9 +5,14 @@
 
 #include <cuda_runtime_api.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -73,6 +78,137 @@ struct SlotInfo {
     std::unordered_map<std::string, size_t> pos;  // DNA -> index
 };
 
+struct ReadRef {
+    const char* seq;
+    const char* qual;
+    uint32_t len, qlen;
+};
+
+// ---- FASTQ streaming: big blocks straight from the file (plain) or through zlib's gz layer (gzip; concatenated
+// members are walked like flate2's MultiGzDecoder, input.rs:63), records split in place.  A reader thread fills and
+// splits block i+1 while the caller packs block i.
+struct FastqBlock {
+    std::vector<char> buf;
+    size_t have = 0;
+    std::vector<ReadRef> recs;
+    int state = 0;  // 0 free (reader may fill), 1 filled (consumer may pack)
+};
+
+struct FastqStream {
+    gzFile gz = nullptr;
+    FILE* plain = nullptr;  // not gzip: read straight into the block buffer (no inflate layer, no extra copy)
+    bool eof = false;
+    std::vector<char> carry;  // bytes after the last whole record of the previous block
+    FastqStream(const std::string& path) {
+        auto ends = [&](const char* suf) {
+            const size_t k = strlen(suf);
+            return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
+        };
+        if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
+            throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
+        FILE* probe = fopen(path.c_str(), "rb");
+        if (!probe) throw Error("Failed to open file: " + path);
+        unsigned char magic[2] = {0, 0};
+        const size_t got = fread(magic, 1, 2, probe);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            fclose(probe);
+            gz = gzopen(path.c_str(), "rb");
+            if (!gz) throw Error("Failed to open file: " + path);
+            gzbuffer(gz, 4u << 20);
+        } else {
+            rewind(probe);
+            setvbuf(probe, nullptr, _IONBF, 0);
+            plain = probe;
+        }
+    }
+    ~FastqStream() {
+        if (gz) gzclose(gz);
+        if (plain) fclose(plain);
+    }
+    long fill(char* dst, size_t n) {
+        if (plain) return (long)fread(dst, 1, n, plain);
+        return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+    }
+    // Fills `B` with up to max_records whole records (pointers into B.buf).  Returns false when the input is exhausted.
+    bool next_block(FastqBlock& B, size_t max_records) {
+        B.recs.clear();
+        B.have = 0;
+        if (eof && carry.empty()) return false;
+        if (carry.size() > B.buf.size()) throw Error("FASTQ record longer than the block buffer");
+        memcpy(B.buf.data(), carry.data(), carry.size());
+        B.have = carry.size();
+        carry.clear();
+        while (!eof && B.have < B.buf.size()) {
+            const long got = fill(B.buf.data() + B.have, B.buf.size() - B.have);
+            if (got < 0) throw Error("gzread failed (corrupt input?)");
+            if (got == 0) {
+                eof = true;
+                break;
+            }
+            B.have += (size_t)got;
+        }
+        char* base = B.buf.data();
+        size_t pos = 0;
+        while (B.recs.size() < max_records) {
+            const char* line[4];
+            uint32_t len[4];
+            size_t p = pos;
+            int k = 0;
+            for (; k < 4; k++) {
+                const char* nl = (const char*)memchr(base + p, '\n', B.have - p);
+                size_t end;
+                if (nl) end = (size_t)(nl - base);
+                else if (eof && k == 3 && p < B.have) end = B.have;  // last line without '\n'
+                else break;
+                size_t l = end - p;
+                if (l && base[end - 1] == '\r') l--;
+                line[k] = base + p;
+                len[k] = (uint32_t)l;
+                p = nl ? end + 1 : end;
+            }
+            if (k < 4) break;
+            B.recs.push_back(ReadRef{line[1], line[3], len[1], len[3]});
+            pos = p;
+        }
+        if (B.recs.empty()) {
+            if (eof) return false;  // trailing partial record (fewer than 4 lines) is dropped, as the reference never posts it
+            throw Error("FASTQ record longer than the block buffer");
+        }
+        carry.assign(base + pos, base + B.have);
+        return true;
+    }
+};
+
+struct PinnedBatch {
+    uint32_t* planes = nullptr;
+    uint16_t* read_len = nullptr;
+    uint8_t* qual = nullptr;
+    ~PinnedBatch() { release(); }
+    void release() {
+        if (planes) cudaFreeHost(planes);
+        if (read_len) cudaFreeHost(read_len);
+        if (qual) cudaFreeHost(qual);
+        planes = nullptr;
+        read_len = nullptr;
+        qual = nullptr;
+    }
+    void alloc(uint32_t n, uint32_t max_read_len, bool with_qual) {
+        release();
+        if (cudaHostAlloc((void**)&planes, (size_t)n * bc_plane_stride(max_read_len) * 4, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&read_len, (size_t)n * 2, cudaHostAllocDefault) != cudaSuccess ||
+            (with_qual && cudaHostAlloc((void**)&qual, (size_t)n * bc_qual_stride(max_read_len), cudaHostAllocDefault) != cudaSuccess))
+            throw Error("cudaHostAlloc failed for the pinned batch buffers");
+    }
+};
+
+// ingest buffers, kept by the run so that repeated bch_count_fastq calls do not pay the page-locking again
+struct IngestBuffers {
+    PinnedBatch pinned[2];
+    FastqBlock blocks[2];
+    uint32_t batch_reads = 0;
+    bool with_qual = false;
+};
+
 }  // namespace
 
 struct bch_run {
@@ -87,6 +223,7 @@ struct bch_run {
     float min_quality = 0.f;
     bc_config cfg{};
     std::string description;
+    IngestBuffers ingest;
 };
 
 namespace {
@@ -273,6 +410,39 @@ struct BaseLut {
 };
 const BaseLut kLut;
 
+// 32 bases -> one word of each plane.  Scalar reference version and an AVX2 version (chosen once at start-up).
+inline void pack_word_scalar(const char* seq, uint32_t m, uint32_t* lo, uint32_t* hi, uint32_t* nm, bool* other) {
+    uint32_t l = 0, h = 0, x = 0;
+    for (uint32_t b = 0; b < m; b++) {
+        const uint8_t c = kLut.code[(unsigned char)seq[b]];
+        l |= (uint32_t)(c & 1u) << b;
+        h |= (uint32_t)((c >> 1) & 1u) << b;
+        x |= (uint32_t)(c >> 2) << b;  // N or other
+        *other |= c == 5;
+    }
+    *lo = l & ~x;
+    *hi = h & ~x;
+    *nm = x;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline void pack_word_avx2(const char* seq, uint32_t* lo, uint32_t* hi, uint32_t* nm, bool* other) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(seq));
+    const uint32_t isA = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('A')));
+    const uint32_t isC = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('C')));
+    const uint32_t isG = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('G')));
+    const uint32_t isT = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('T')));
+    *lo = isC | isT;
+    *hi = isG | isT;
+    *nm = ~(isA | isC | isG | isT);  // N or other: the mask convention of the scalar version
+    const uint32_t isN = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('N')));
+    *other |= (*nm & ~isN) != 0;
+}
+const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+#else
+const bool kHaveAvx2 = false;
+#endif
+
 // one read -> three bit planes + length word (+ quality bytes)
 inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W, uint32_t* planes, uint16_t* read_len,
                      uint8_t* qual_out, uint32_t qual_stride) {
@@ -280,21 +450,12 @@ inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W
     uint32_t* hi = planes + W;
     uint32_t* nm = planes + 2 * W;
     bool other = false;
-    uint32_t w = 0;
-    for (uint32_t base = 0; base < len; base += 32, w++) {
-        const uint32_t m = std::min(32u, len - base);
-        uint32_t l = 0, h = 0, x = 0;
-        for (uint32_t b = 0; b < m; b++) {
-            const uint8_t c = kLut.code[(unsigned char)seq[base + b]];
-            l |= (uint32_t)(c & 1u) << b;
-            h |= (uint32_t)((c >> 1) & 1u) << b;
-            x |= (uint32_t)(c >> 2) << b;      // N or other
-            other |= c == 5;
-        }
-        lo[w] = l & ~x;
-        hi[w] = h & ~x;
-        nm[w] = x;
-    }
+    uint32_t w = 0, base = 0;
+#if defined(__x86_64__)
+    if (kHaveAvx2)
+        for (; base + 32 <= len; base += 32, w++) pack_word_avx2(seq + base, &lo[w], &hi[w], &nm[w], &other);
+#endif
+    for (; base < len; base += 32, w++) pack_word_scalar(seq + base, std::min(32u, len - base), &lo[w], &hi[w], &nm[w], &other);
     for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
     if (3 * W != ((3 * W) | 1u)) planes[3 * W] = 0;  // pad word of an even record
     if (qual_out) {
@@ -307,12 +468,6 @@ inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W
     }
     *read_len = (uint16_t)(len | (other ? BC_READ_UNSUPPORTED : 0u));
 }
-
-struct ReadRef {
-    const char* seq;
-    const char* qual;
-    uint32_t len, qlen;
-};
 
 int pack_refs(uint32_t max_read_len, const std::vector<ReadRef>& reads, size_t first, size_t count, uint32_t* planes,
               uint16_t* read_len, uint8_t* qual, unsigned threads) {
@@ -341,101 +496,6 @@ int pack_refs(uint32_t max_read_len, const std::vector<ReadRef>& reads, size_t f
     }
     return bad ? BC_EINVAL : BC_OK;
 }
-
-// ---- FASTQ streaming: big blocks through zlib's gz layer (plain files pass through; concatenated gzip members
-// are walked like flate2's MultiGzDecoder, input.rs:63), records split in place
-struct FastqStream {
-    gzFile gz = nullptr;
-    std::vector<char> buf;
-    size_t have = 0;      // valid bytes in buf
-    bool eof = false;
-    FastqStream(const std::string& path, size_t block_bytes) {
-        auto ends = [&](const char* suf) {
-            const size_t k = strlen(suf);
-            return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
-        };
-        if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
-            throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
-        gz = gzopen(path.c_str(), "rb");
-        if (!gz) throw Error("Failed to open file: " + path);
-        gzbuffer(gz, 4u << 20);
-        buf.resize(std::min<size_t>(std::max<size_t>(block_bytes, 16u << 20), 1u << 30));
-    }
-    ~FastqStream() {
-        if (gz) gzclose(gz);
-    }
-    // Appends whole records to `out` (pointers into buf, valid until the next call).  Returns false at the end.
-    bool next_block(std::vector<ReadRef>& out, size_t max_records) {
-        out.clear();
-        if (eof && have == 0) return false;
-        while (!eof && have < buf.size()) {
-            const int got = gzread(gz, buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, 1u << 30));
-            if (got < 0) throw Error("gzread failed (corrupt input?)");
-            if (got == 0) {
-                eof = true;
-                break;
-            }
-            have += (size_t)got;
-        }
-        size_t pos = 0, consumed = 0;
-        while (out.size() < max_records) {
-            const char* line[4];
-            uint32_t len[4];
-            size_t p = pos;
-            int k = 0;
-            for (; k < 4; k++) {
-                const char* nl = (const char*)memchr(buf.data() + p, '\n', have - p);
-                size_t end;
-                if (nl) end = (size_t)(nl - buf.data());
-                else if (eof && k == 3 && p < have) end = have;  // last line without '\n'
-                else break;
-                size_t l = end - p;
-                if (l && buf[end - 1] == '\r') l--;
-                line[k] = buf.data() + p;
-                len[k] = (uint32_t)l;
-                p = nl ? end + 1 : end;
-            }
-            if (k < 4) break;
-            out.push_back(ReadRef{line[1], line[3], len[1], len[3]});
-            pos = p;
-            consumed = p;
-        }
-        pending_shift = consumed;
-        if (out.empty()) {
-            if (eof) {
-                have = 0;  // trailing partial record (fewer than 4 lines) is dropped, as the reference never posts it
-                return false;
-            }
-            if (have == buf.size()) throw Error("FASTQ record longer than the block buffer");
-        }
-        return true;
-    }
-    size_t pending_shift = 0;
-    void release_block() {  // call once the records of the last block are packed
-        if (pending_shift) {
-            memmove(buf.data(), buf.data() + pending_shift, have - pending_shift);
-            have -= pending_shift;
-            pending_shift = 0;
-        }
-    }
-};
-
-struct PinnedBatch {
-    uint32_t* planes = nullptr;
-    uint16_t* read_len = nullptr;
-    uint8_t* qual = nullptr;
-    ~PinnedBatch() {
-        if (planes) cudaFreeHost(planes);
-        if (read_len) cudaFreeHost(read_len);
-        if (qual) cudaFreeHost(qual);
-    }
-    void alloc(uint32_t n, uint32_t max_read_len, bool with_qual) {
-        if (cudaHostAlloc((void**)&planes, (size_t)n * bc_plane_stride(max_read_len) * 4, cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc((void**)&read_len, (size_t)n * 2, cudaHostAllocDefault) != cudaSuccess ||
-            (with_qual && cudaHostAlloc((void**)&qual, (size_t)n * bc_qual_stride(max_read_len), cudaHostAllocDefault) != cudaSuccess))
-            throw Error("cudaHostAlloc failed for the pinned batch buffers");
-    }
-};
 
 // ---- output ---------------------------------------------------------------------------------------------------
 
@@ -602,32 +662,81 @@ int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned 
     if (!run || !ctx || !fastq_path) return BC_EINVAL;
     if (batch_reads == 0) batch_reads = 1u << 20;
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    std::thread reader;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool abort_reader = false;
+    auto stop_reader = [&]() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            abort_reader = true;
+        }
+        cv.notify_all();
+        if (reader.joinable()) reader.join();
+    };
     try {
         const uint32_t mrl = run->cfg.max_read_len;
         const bool with_qual = run->min_quality > 0.0f;
-        PinnedBatch pinned[2];
-        pinned[0].alloc(batch_reads, mrl, with_qual);
-        pinned[1].alloc(batch_reads, mrl, with_qual);
-        FastqStream in(fastq_path, (size_t)batch_reads * (2 * (size_t)mrl + 64));
-        std::vector<ReadRef> block;
+        IngestBuffers& I = run->ingest;
+        if (I.batch_reads != batch_reads || I.with_qual != with_qual || !I.pinned[0].planes) {
+            I.pinned[0].alloc(batch_reads, mrl, with_qual);
+            I.pinned[1].alloc(batch_reads, mrl, with_qual);
+            const size_t block_bytes = std::min<size_t>(std::max<size_t>((size_t)batch_reads * (2 * (size_t)mrl + 64), 1u << 20), 1u << 30);
+            for (FastqBlock& B : I.blocks) B.buf.resize(block_bytes);
+            I.batch_reads = batch_reads;
+            I.with_qual = with_qual;
+        }
+        for (FastqBlock& B : I.blocks) B.state = 0;
+        FastqStream in(fastq_path);
+        // reader thread: fill + split block i+1 while this thread packs block i
+        std::string reader_error;
+        bool reader_done = false;
+        reader = std::thread([&]() {
+            try {
+                for (int i = 0;; i ^= 1) {
+                    FastqBlock& B = I.blocks[i];
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return B.state == 0 || abort_reader; });
+                        if (abort_reader) return;
+                    }
+                    const bool more = in.next_block(B, batch_reads);
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!more) {
+                        reader_done = true;
+                        cv.notify_all();
+                        return;
+                    }
+                    B.state = 1;
+                    cv.notify_all();
+                }
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lk(mu);
+                reader_error = e.what();
+                reader_done = true;
+                cv.notify_all();
+            }
+        });
         uint64_t total = 0;
         int cur = 0;
         int in_flight = 0;  // submits since the last sync; each pinned buffer is reused every second submit
-        while (in.next_block(block, batch_reads)) {
-            if (block.empty()) {
-                in.release_block();
-                continue;
+        for (int i = 0;; i ^= 1) {
+            FastqBlock& B = I.blocks[i];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return B.state == 1 || reader_done; });
+                if (B.state != 1) break;
             }
             if (in_flight == 2) {  // the buffer we are about to overwrite was handed to the submit before last
                 if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
                 in_flight = 0;
             }
-            PinnedBatch& p = pinned[cur];
-            if (pack_refs(mrl, block, 0, block.size(), p.planes, p.read_len, with_qual ? p.qual : nullptr, threads) != BC_OK)
+            PinnedBatch& p = I.pinned[cur];
+            if (pack_refs(mrl, B.recs, 0, B.recs.size(), p.planes, p.read_len, with_qual ? p.qual : nullptr, threads) != BC_OK)
                 throw Error("FASTQ record " + std::to_string(total) + "+: read longer than max_read_len (" + std::to_string(mrl) +
                             ") or quality/sequence length mismatch");
             bc_batch b{};
-            b.n_reads = (uint32_t)block.size();
+            b.n_reads = (uint32_t)B.recs.size();
             b.plane_stride = bc_plane_stride(mrl);
             b.qual_stride = bc_qual_stride(mrl);
             b.location = BC_LOC_HOST;
@@ -635,15 +744,22 @@ int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned 
             b.read_len = p.read_len;
             b.qual = with_qual ? p.qual : nullptr;
             if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
-            total += block.size();
-            in.release_block();
+            total += B.recs.size();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                B.state = 0;
+            }
+            cv.notify_all();
             cur ^= 1;
             in_flight++;
         }
+        stop_reader();
+        if (!reader_error.empty()) throw Error(reader_error);
         if (bc_sync(ctx) != BC_OK) throw Error(bc_last_error(ctx));
         if (total_reads) *total_reads = total;
         return BC_OK;
     } catch (const std::exception& e) {
+        stop_reader();
         report(e.what());
         return BC_EINVAL;
     }
