@@ -209,6 +209,21 @@ typedef struct {
 int bc_decode_route(bc_ctx *ctx, const bc_batch *batch, uint32_t n_ranks, bc_record *dev_buckets,
                     uint64_t bucket_capacity, uint32_t *dev_bucket_counts);
 int bc_insert_records(bc_ctx *ctx, const bc_record *dev_records, uint64_t n);
+
+/* Fused routing (one process per GPU on one NVLink/NVSwitch box, at most 8 ranks): the decode kernel stores every
+ * matched (key, UMI) record straight into its owner's receive region over NVLink peer memory — no bucket + copy
+ * step.  Each rank opens its receive buffer (2 parities x n_ranks sources x capacity records) and gets a
+ * BC_IPC_HANDLE_BYTES handle; the caller exchanges the handles (any transport) and passes all of them, rank order,
+ * to bc_route_connect.  Per batch: bc_route_submit(parity = batch index & 1) decodes and routes, leaving in
+ * dev_counts[r] the number of records sent to rank r; the caller all-gathers the counts (that collective is also the
+ * barrier that makes the peer stores visible) and hands the owner the counts of what it received:
+ * dev_counts_from[s * count_stride] records from source rank s.  expected_records bounds the table growth check. */
+#define BC_IPC_HANDLE_BYTES 64
+int bc_route_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity, void *ipc_handle_out);
+int bc_route_connect(bc_ctx *ctx, const void *ipc_handles);
+int bc_route_submit(bc_ctx *ctx, const bc_batch *batch, uint32_t parity, uint32_t *dev_counts);
+int bc_route_insert(bc_ctx *ctx, uint32_t parity, const uint32_t *dev_counts_from, uint32_t count_stride,
+                    uint64_t expected_records);
 int bc_export_rows(bc_ctx *ctx, uint64_t **dev_key_lo, uint64_t **dev_key_hi, uint64_t **dev_count, uint64_t *n_rows);
 int bc_import_rows(bc_ctx *ctx, const uint64_t *dev_key_lo, const uint64_t *dev_key_hi, const uint64_t *dev_count,
                    uint64_t n_rows);

@@ -96,6 +96,10 @@ _PROTOS = {
                                 C.c_uint32]),
     "bc_decode_route": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "bc_insert_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bc_route_open": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "bc_route_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bc_route_submit": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.c_uint32, C.c_void_p]),
+    "bc_route_insert": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64]),
     "bc_export_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_uint64)]),
     "bc_import_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -368,6 +372,22 @@ class Counter:
         b = batch.c_struct()
         self._ck(lib().bc_decode_route(self.h, C.byref(b), n_ranks, C.c_void_p(buckets.data_ptr()), capacity,
                                        C.c_void_p(counts.data_ptr())), "bc_decode_route")
+
+    def route_open(self, n_ranks, rank, capacity):
+        """-> this rank's IPC handle (bytes) for its receive buffer"""
+        h = C.create_string_buffer(64)
+        self._ck(lib().bc_route_open(self.h, n_ranks, rank, capacity, h), "bc_route_open")
+        return h.raw
+
+    def route_connect(self, handles):
+        self._ck(lib().bc_route_connect(self.h, b"".join(handles)), "bc_route_connect")
+
+    def route_submit(self, batch, parity, counts):
+        b = batch.c_struct()
+        self._ck(lib().bc_route_submit(self.h, C.byref(b), parity, C.c_void_p(counts.data_ptr())), "bc_route_submit")
+
+    def route_insert(self, parity, counts_from_ptr, stride, expected_records):
+        self._ck(lib().bc_route_insert(self.h, parity, C.c_void_p(counts_from_ptr), stride, int(expected_records)), "bc_route_insert")
 
     def insert_records(self, records, n):
         self._ck(lib().bc_insert_records(self.h, C.c_void_p(records.data_ptr()), n), "bc_insert_records")

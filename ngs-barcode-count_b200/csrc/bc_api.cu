@@ -65,6 +65,11 @@ struct bc_ctx {
     uint2* d_def_items = nullptr;
     uint32_t* d_def_count = nullptr;
     uint64_t def_cap = 0;
+    // fused routing over NVLink (bc_route_*): this rank's receive regions [2 parities][n_ranks][capacity] and the peers'
+    Key* d_recv = nullptr;
+    Key* peer_recv[kMaxRanks] = {nullptr};
+    uint32_t route_ranks = 0, route_rank = 0;
+    uint64_t route_cap = 0;
     // counting state: map (key -> count) and, with a random barcode, the (key, UMI) set
     Tables tables{};
     unsigned long long entries_upper = 0;  // host-side upper bound of entries added to either table
@@ -367,6 +372,9 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_bref) cudaFree(ctx->d_bref);
     if (ctx->d_def_items) cudaFree(ctx->d_def_items);
     if (ctx->d_def_count) cudaFree(ctx->d_def_count);
+    for (uint32_t r = 0; r < ctx->route_ranks; r++)
+        if (r != ctx->route_rank && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
+    if (ctx->d_recv) cudaFree(ctx->d_recv);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1080,8 +1088,76 @@ int bc_decode_route(bc_ctx* ctx, const bc_batch* batch, uint32_t n_ranks, bc_rec
     if (bucket_capacity < batch->n_reads)
         return fail(ctx, BC_EINVAL, "bucket_capacity %llu < n_reads %u: a bucket must be able to hold the whole batch",
                     (unsigned long long)bucket_capacity, batch->n_reads);
-    RouteOut r{reinterpret_cast<Key*>(dev_buckets), bucket_capacity, dev_bucket_counts, n_ranks};
+    if (n_ranks > (uint32_t)kMaxRanks) return fail(ctx, BC_EUNSUPPORTED, "more than %d ranks", kMaxRanks);
+    RouteOut r{};
+    for (uint32_t k = 0; k < n_ranks; k++) r.dst[k] = reinterpret_cast<Key*>(dev_buckets) + (size_t)k * bucket_capacity;
+    r.capacity = bucket_capacity;
+    r.counts = dev_bucket_counts;
+    r.n_ranks = n_ranks;
     return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+}
+
+// ---- fused routing: the decode kernel stores each matched record straight into its owner's receive region over NVLink
+int bc_route_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity, void* ipc_handle_out) {
+    if (!ctx || !ipc_handle_out || n_ranks == 0 || n_ranks > (uint32_t)kMaxRanks || rank >= n_ranks || capacity == 0) return BC_EINVAL;
+    if (ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_open: already open");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BC_IPC_HANDLE_BYTES, "BC_IPC_HANDLE_BYTES");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMalloc(&ctx->d_recv, 2ull * n_ranks * capacity * sizeof(Key)));
+    cudaIpcMemHandle_t h;
+    CK(ctx, cudaIpcGetMemHandle(&h, ctx->d_recv));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    ctx->route_ranks = n_ranks;
+    ctx->route_rank = rank;
+    ctx->route_cap = capacity;
+    ctx->peer_recv[rank] = ctx->d_recv;
+    return BC_OK;
+}
+
+int bc_route_connect(bc_ctx* ctx, const void* ipc_handles) {
+    if (!ctx || !ipc_handles) return BC_EINVAL;
+    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_connect before bc_route_open");
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t r = 0; r < ctx->route_ranks; r++) {
+        if (r == ctx->route_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof h, sizeof h);
+        void* p = nullptr;
+        CK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_recv[r] = static_cast<Key*>(p);
+    }
+    return BC_OK;
+}
+
+int bc_route_submit(bc_ctx* ctx, const bc_batch* batch, uint32_t parity, uint32_t* dev_counts) {
+    if (!ctx || !batch || !dev_counts || parity > 1) return BC_EINVAL;
+    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_submit before bc_route_open");
+    if (batch->n_reads > ctx->route_cap)
+        return fail(ctx, BC_EINVAL, "batch of %u reads exceeds the route capacity %llu", batch->n_reads, (unsigned long long)ctx->route_cap);
+    for (uint32_t r = 0; r < ctx->route_ranks; r++)
+        if (!ctx->peer_recv[r]) return fail(ctx, BC_ESTATE, "bc_route_submit before bc_route_connect");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(dev_counts, 0, ctx->route_ranks * sizeof(uint32_t), ctx->stream));
+    RouteOut r{};
+    for (uint32_t k = 0; k < ctx->route_ranks; k++)  // my region inside rank k's receive buffer
+        r.dst[k] = ctx->peer_recv[k] + ((size_t)parity * ctx->route_ranks + ctx->route_rank) * ctx->route_cap;
+    r.capacity = ctx->route_cap;
+    r.counts = dev_counts;
+    r.n_ranks = ctx->route_ranks;
+    return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+}
+
+int bc_route_insert(bc_ctx* ctx, uint32_t parity, const uint32_t* dev_counts_from, uint32_t count_stride, uint64_t expected_records) {
+    if (!ctx || !dev_counts_from || parity > 1) return BC_EINVAL;
+    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_insert before bc_route_open");
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_capacity(ctx, expected_records);
+    if (rc != BC_OK) return rc;
+    ctx->rows_valid = false;
+    ProfScope p(ctx, BC_K_INSERT);
+    CK(ctx, launch_insert_segments(ctx->tables, ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap,
+                                   dev_counts_from, count_stride, ctx->route_ranks, ctx->d_counters, ctx->stream));
+    return BC_OK;
 }
 
 int bc_insert_records(bc_ctx* ctx, const bc_record* dev_records, uint64_t n) {

@@ -310,7 +310,7 @@ __device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& t
     if (flags & F_ROUTE) {
         const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
         const uint32_t slot = atomicAdd(&route.counts[owner], 1u);
-        if (slot < route.capacity) route.buckets[owner * route.capacity + slot] = key;
+        if (slot < route.capacity) route.dst[owner][slot] = key;
         return -2;  // outcome is decided by the owner rank
     }
     return BC_ST_MATCHED;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
             uint32_t at = 0;
             if (lane == leader) at = atomicAdd(&route.counts[r], (uint32_t)__popc(m));
             at = __shfl_sync(0xFFFFFFFFu, at, leader) + __popc(m & ((1u << lane) - 1u));
-            if (owner == r && at < route.capacity) route.buckets[(unsigned long long)r * route.capacity + at] = key;
+            if (owner == r && at < route.capacity) route.dst[r][at] = key;
         }
     }
     // ---- deferred reads: one warp-aggregated append per warp
@@ -800,6 +800,43 @@ __global__ void k_insert(const Tables tables, const unsigned long long* __restri
         if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
         if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
     }
+}
+
+// routed records of one round: segment s = what rank s sent to this rank, its length read on the device
+__global__ void k_insert_segments(const Tables tables, const Key* __restrict__ records, const unsigned long long capacity,
+                                  const uint32_t* __restrict__ counts, const uint32_t count_stride, const uint32_t n_segments,
+                                  unsigned long long* __restrict__ counters) {
+    unsigned long long matched = 0, dup = 0, fresh = 0, pairs = 0;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        const unsigned long long n = min((unsigned long long)counts[s * count_stride], capacity);
+        const Key* seg = records + (unsigned long long)s * capacity;
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            bool new_key = false, new_pair = false;
+            if (count_read(tables, seg[i], &new_key, &new_pair)) matched++;
+            else dup++;
+            fresh += new_key;
+            pairs += new_pair;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        matched += __shfl_xor_sync(0xFFFFFFFFu, matched, o);
+        dup += __shfl_xor_sync(0xFFFFFFFFu, dup, o);
+        fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
+        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (matched) atomicAdd(&counters[BC_CNT_MATCHED], matched);
+        if (dup) atomicAdd(&counters[BC_CNT_DUPLICATES], dup);
+        if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
+        if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
+    }
+}
+
+cudaError_t launch_insert_segments(const Tables& tables, const Key* records, unsigned long long capacity, const uint32_t* counts,
+                                   uint32_t count_stride, uint32_t n_segments, unsigned long long* counters, cudaStream_t stream) {
+    k_insert_segments<<<148 * 16, 256, 0, stream>>>(tables, records, capacity, counts, count_stride, n_segments, counters);
+    return cudaGetLastError();
 }
 
 static unsigned grid_for(unsigned long long n, unsigned block) {

@@ -13,10 +13,15 @@ struct DecodeOut {  // all optional (test hooks / decode_only)
     unsigned long long* key_hi;
 };
 
-struct RouteOut {  // multi-GPU: matched (key,UMI) records bucketed by owner rank instead of inserted
-    Key* buckets;
-    unsigned long long capacity;  // records per bucket
-    uint32_t* counts;             // [n_ranks]
+constexpr int kMaxRanks = 8;  // one box
+
+// multi-GPU: matched (key, UMI) records are written to their owner rank's bucket instead of being counted.  dst[r] is a
+// local bucket (bc_decode_route) or rank r's receive region mapped over NVLink (bc_route_submit): plain peer stores
+// from inside the decode kernel, cursors stay local — the transfer overlaps the decode, no separate copy step.
+struct RouteOut {
+    Key* dst[kMaxRanks];
+    unsigned long long capacity;  // records per destination
+    uint32_t* counts;             // [n_ranks] local cursors
     uint32_t n_ranks;
 };
 
@@ -65,6 +70,10 @@ cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned lon
                             cudaStream_t stream);
 
 cudaError_t launch_clear_map(const DevTable& t, cudaStream_t stream);
+
+// routed records received from every rank: segment s holds counts[s * count_stride] records at records + s * capacity
+cudaError_t launch_insert_segments(const Tables& tables, const Key* records, unsigned long long capacity, const uint32_t* counts,
+                                   uint32_t count_stride, uint32_t n_segments, unsigned long long* counters, cudaStream_t stream);
 
 // move every entry of `src` (hash kinds) into `dst`
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);

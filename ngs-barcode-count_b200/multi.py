@@ -102,15 +102,22 @@ class Job:
         if world == 1:
             self.parallelism = "1 GPU"
         elif has_umi:
-            self.parallelism = f"reads sharded over {world} GPUs; (key,UMI) records routed to hash(key)%{world} by NCCL all-to-all"
+            self.parallelism = (f"reads sharded over {world} GPUs; (key,UMI) records stored by the decode kernel into the owner "
+                                f"GPU hash(key)%{world} over NVLink peer memory; one tiny NCCL all-gather of counts per batch")
         else:
             self.parallelism = f"reads sharded over {world} GPUs; tables merged once at the end (all-gather of rows)"
         if world > 1 and has_umi:
-            self.cap = batch_reads  # a bucket can hold a whole batch: no overflow whatever the key skew
-            self.send = torch.empty((world, self.cap, 2), dtype=torch.int64, device=device)
-            self.recv = torch.empty((world * self.cap, 2), dtype=torch.int64, device=device)
-            self.counts = torch.zeros(world, dtype=torch.int32, device=device)
-            self.rcounts = torch.zeros(world, dtype=torch.int32, device=device)
+            # fused routing: every rank maps every other rank's receive buffer (CUDA IPC over NVLink); the decode
+            # kernel stores records straight into the owner's memory.  A (source, owner) region can hold a whole
+            # batch, so no key skew can overflow it.
+            self.cap = batch_reads
+            handles = [None] * world
+            dist.all_gather_object(handles, ctr.route_open(world, rank, self.cap))
+            ctr.route_connect(handles)
+            self.counts = torch.zeros((2, world), dtype=torch.int32, device=device)          # what I sent, per parity
+            self.all_counts = torch.zeros((2, world * world), dtype=torch.int32, device=device)  # [source][owner]
+            self.parity = 0
+            dist.barrier()
 
     def to_pinned(self, dev_batch):
         return HostBatch(self.bc, dev_batch)
@@ -143,10 +150,14 @@ class Job:
             return n
 
     def _routed(self, batch):
-        self.counts.zero_()
-        self.ctr.decode_route(batch, self.world, self.send, self.cap, self.counts)
-        n = exchange_records(self.send, self.counts, self.rcounts, self.recv, self.world)
-        self.ctr.insert_records(self.recv, n)
+        """decode + route one batch.  No host synchronisation: the counts stay on the device; the tiny all-gather is
+        the only collective and doubles as the barrier that makes every rank's peer stores visible to the owner."""
+        p = self.parity
+        self.parity ^= 1
+        self.ctr.route_submit(batch, p, self.counts[p])
+        dist.all_gather_into_tensor(self.all_counts[p], self.counts[p])
+        # records sent to me by source s: all_counts[p][s * world + rank]
+        self.ctr.route_insert(p, self.all_counts[p].data_ptr() + 4 * self.rank, self.world, int(batch.n * 1.5))
 
     def _merge_rows(self, to_host):
         lo, hi, cnt, n = self.ctr.export_rows()
