@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -77,6 +77,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
+        note = None
+        if not any(len(l.split(",")) >= 7 for l in self.lines):  # region shorter than nvidia-smi's start-up: one query right after it
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout
+                self.lines = [l.strip() for l in out.splitlines() if l.strip()]
+                note = "timed region shorter than the sampler start-up: one sample taken right after it"
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
@@ -91,8 +100,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        d = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+             "samples": len(sm)}
+        if note:
+            d["note"] = note
+        return d
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
@@ -217,13 +229,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- kernel-resident timing (CUDA events on the ctx stream, max over ranks)
+    sampler = ClockSampler(local)
+    sampler.start()  # sampled from the warm-up on (same load), so that short timed regions still get samples
     for _ in range(args.warmup):
         job.step(batches)
     barrier()
     ctr.reset_profile()
     ctr.set_profiling(True)
-    sampler = ClockSampler(local)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with torch.cuda.stream(stream):

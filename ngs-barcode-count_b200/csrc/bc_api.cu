@@ -492,7 +492,16 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             if (cfg->region_codes[i] != 'C' && j < cfg->region_len) {
                 if (d.n_qruns == kMaxQRuns) FAILC(BC_EUNSUPPORTED, "more than %d quality-tested runs", kMaxQRuns);
                 // the kernel sums the raw Phred+33 bytes, so the per-byte offset goes into the threshold
-                d.qruns[d.n_qruns++] = DevQRun{(uint16_t)i, (uint16_t)(j - i), quality_threshold(j - i, cfg->min_quality) + 33u * (j - i)};
+                {
+                    const uint32_t len = j - i, rem = len & 3u;
+                    DevQRun q{};
+                    q.off = (uint16_t)i;
+                    q.len = (uint16_t)len;
+                    q.n_words = (uint16_t)((len + 3) / 4);
+                    q.tail_mask = rem ? (1u << (8 * rem)) - 1u : 0xFFFFFFFFu;
+                    q.thresh = quality_threshold(len, cfg->min_quality) + 33u * len;
+                    d.qruns[d.n_qruns++] = q;
+                }
             }
             i = j;
         }

@@ -50,6 +50,8 @@ struct DevDeep {  // one level of a slot's block index (global memory, read by k
 
 struct DevQRun {
     uint16_t off, len;   // position in the region walk (relative to the quality start) and length
+    uint16_t n_words;    // ceil(len / 4): re-aligned words that hold the run
+    uint32_t tail_mask;  // bytes of the last word that belong to the run
     uint32_t thresh;     // low quality iff the sum of the run's raw Phred+33 bytes < thresh  (parse.rs:352-355, Q12)
 };
 

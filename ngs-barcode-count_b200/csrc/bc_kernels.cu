@@ -391,22 +391,24 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                 // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
                 // Q6: after a repair the quality string is read from 0, not from the repaired offset.
                 if (cfg.n_qruns) {
-                    // byte sums with whole-word loads: dp4a against 0x01010101 adds the four bytes of a word; the
-                    // first and last word of a run are masked.  The packer guarantees every byte >= 33 ('!').
+                    // byte sums with whole-word loads: the run is re-aligned to a word boundary with funnel shifts, its
+                    // last word masked with a per-run constant, and dp4a against 0x01010101 adds the four bytes of a
+                    // word.  The packer guarantees every byte >= 33 ('!'); the threshold already includes that offset.
                     const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
                     const uint32_t q0 = repaired ? 0u : (uint32_t)off;
                     for (uint32_t r = 0; r < cfg.n_qruns; r++) {
                         const DevQRun run = cfg.qruns[r];
-                        const uint32_t a = q0 + run.off, e = a + run.len;  // bytes [a, e)
-                        uint32_t sum = 0;
-                        for (uint32_t w = a >> 2; (w << 2) < e; w++) {
-                            uint32_t v = qw[w];
-                            const uint32_t lo_b = w << 2;
-                            if (lo_b < a) v &= 0xFFFFFFFFu << ((a - lo_b) << 3);
-                            if (lo_b + 4 > e) v &= 0xFFFFFFFFu >> ((lo_b + 4 - e) << 3);
-                            sum = __dp4a(v, 0x01010101u, sum);
+                        const uint32_t a = q0 + run.off;
+                        const uint32_t* w = qw + (a >> 2);
+                        const uint32_t sh = (a & 3u) << 3;
+                        uint32_t sum = 0, prev = w[0];
+                        for (uint32_t k = 1; k < run.n_words; k++) {
+                            const uint32_t cur = w[k];
+                            sum = __dp4a(__funnelshift_r(prev, cur, sh), 0x01010101u, sum);
+                            prev = cur;
                         }
-                        if (sum < run.thresh) {  // thresh already includes the +33 per byte offset
+                        sum = __dp4a(__funnelshift_r(prev, w[run.n_words], sh) & run.tail_mask, 0x01010101u, sum);
+                        if (sum < run.thresh) {
                             status = BC_ST_LOW_QUALITY;
                             break;
                         }
