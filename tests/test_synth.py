@@ -69,3 +69,40 @@ def test_device_generator_equals_host_and_job_equals_oracle(name, tmp_path):
     orc.write_files()
     ctr.write_counts(str(g_dir), "p", merge=wl.merge, enrich=wl.enrich)
     assert_same_csv_set(read_csv_dir(str(g_dir), "p"), read_csv_dir(str(o_dir), "p"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["del3", "crispr", "lineage"])
+def test_job_is_independent_of_batching_and_order(name, tmp_path):
+    """Size-independent property at a size the oracle would need minutes for: the final table and the counters do not
+    depend on how the reads are cut into batches nor on the order of the batches (every statistic of the path is an
+    order-independent sum or set union); a re-run after bc_reset reproduces them; duplicates +
+    matched == reads that passed the filters."""
+    import torch
+    n = 3_000_000
+    wl = synth.Workload(name, str(tmp_path / name), reads=n)
+    run = wl.run(bc)
+    whole = wl.generate_device(run, 0, n)
+    torch.cuda.synchronize()
+
+    def job(cuts, reverse=False):
+        ctr = bc.Counter(run, expected_reads=0)  # tiny tables: growth by rehash is exercised too
+        edges = list(zip([0] + cuts, cuts + [n]))
+        if reverse:
+            edges = edges[::-1]
+        for a, b in edges:
+            ctr.submit(whole.slice(a, b))
+        c = ctr.counters()
+        k, lo, hi, cnt = ctr.finish_view()
+        hi = hi if hi is not None else np.zeros(k, np.uint64)
+        order = np.lexsort((lo, hi))
+        rows = np.stack([hi[order], lo[order], cnt[order]], axis=1).copy()
+        return c, rows
+
+    c0, r0 = job([])
+    assert sum(c0.values()) == n
+    assert int(r0[:, 2].sum()) == c0["matched"]
+    for cuts, rev in (([1_000_000, 2_000_001], False), ([123, 128, 70_000, 1_500_000, 2_999_999], True)):
+        c1, r1 = job(cuts, rev)
+        assert c1 == c0
+        assert r1.shape == r0.shape and bool((r1 == r0).all())
