@@ -44,6 +44,10 @@ struct ProfEvent {
 struct bc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // routed mode: the owner-side inserts of batch i run on their own stream, concurrently with the decode of batch i+1
+    cudaStream_t insert_stream = nullptr;
+    cudaEvent_t routed_ev = nullptr, insert_done_ev = nullptr;
+    bool insert_pending = false;
     bool own_stream = true;
     DevCfg cfg{};
     std::vector<KeyField> fields;      // per slot, scheme order
@@ -376,6 +380,12 @@ void bc_destroy(bc_ctx* ctx) {
         if (r != ctx->route_rank && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
     if (ctx->d_recv) cudaFree(ctx->d_recv);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->insert_stream) {
+        cudaStreamSynchronize(ctx->insert_stream);
+        cudaStreamDestroy(ctx->insert_stream);
+    }
+    if (ctx->routed_ev) cudaEventDestroy(ctx->routed_ev);
+    if (ctx->insert_done_ev) cudaEventDestroy(ctx->insert_done_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -779,6 +789,8 @@ int bc_sync(bc_ctx* ctx) {
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
+    ctx->insert_pending = false;
     ctx->copies_pending = false;
     return BC_OK;
 }
@@ -1120,6 +1132,11 @@ int bc_route_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacit
     ctx->route_rank = rank;
     ctx->route_cap = capacity;
     ctx->peer_recv[rank] = ctx->d_recv;
+    int lo_prio = 0, hi_prio = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CK(ctx, cudaStreamCreateWithPriority(&ctx->insert_stream, cudaStreamNonBlocking, hi_prio));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->routed_ev, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->insert_done_ev, cudaEventDisableTiming));
     return BC_OK;
 }
 
@@ -1153,19 +1170,37 @@ int bc_route_submit(bc_ctx* ctx, const bc_batch* batch, uint32_t parity, uint32_
     r.capacity = ctx->route_cap;
     r.counts = dev_counts;
     r.n_ranks = ctx->route_ranks;
-    return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+    int rc = run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+    if (rc != BC_OK) return rc;
+    // The caller's collective that follows tells the peers "my receive buffer of the other parity is free again", so it
+    // has to be ordered after my insert of the previous batch — which ran concurrently with the decode just launched.
+    if (ctx->insert_pending) {
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->insert_done_ev, 0));
+        ctx->insert_pending = false;
+    }
+    return BC_OK;
 }
 
 int bc_route_insert(bc_ctx* ctx, uint32_t parity, const uint32_t* dev_counts_from, uint32_t count_stride, uint64_t expected_records) {
     if (!ctx || !dev_counts_from || parity > 1) return BC_EINVAL;
     if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_insert before bc_route_open");
     CK(ctx, cudaSetDevice(ctx->device));
-    int rc = ensure_capacity(ctx, expected_records);
+    if (ctx->insert_pending) {  // only when the caller skipped a submit in between
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->insert_done_ev, 0));
+        ctx->insert_pending = false;
+    }
+    int rc = ensure_capacity(ctx, expected_records);  // may rehash on the main stream: the insert stream is idle here
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
-    ProfScope p(ctx, BC_K_INSERT);
+    // inserts go to their own (high-priority) stream once the exchange of counts, i.e. everything queued on the main
+    // stream so far, is done; the main stream is free to decode the next batch meanwhile
+    CK(ctx, cudaEventRecord(ctx->routed_ev, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->insert_stream, ctx->routed_ev, 0));
+    ctx->prof.launches[BC_K_INSERT]++;
     CK(ctx, launch_insert_segments(ctx->tables, ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap,
-                                   dev_counts_from, count_stride, ctx->route_ranks, ctx->d_counters, ctx->stream));
+                                   dev_counts_from, count_stride, ctx->route_ranks, ctx->d_counters, ctx->insert_stream));
+    CK(ctx, cudaEventRecord(ctx->insert_done_ev, ctx->insert_stream));
+    ctx->insert_pending = true;
     return BC_OK;
 }
 

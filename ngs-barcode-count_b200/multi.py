@@ -8,6 +8,8 @@ Sharding follows SURVEY.md §8(e): reads are independent, so every rank decodes 
     and every owner inserts what it received (bc_insert_records); the owner decides matched vs duplicate.
 torch.distributed is plumbing only (communicator + buffers); all compute is in the CUDA library.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -106,18 +108,26 @@ class Job:
                                 f"GPU hash(key)%{world} over NVLink peer memory; one tiny NCCL all-gather of counts per batch")
         else:
             self.parallelism = f"reads sharded over {world} GPUs; tables merged once at the end (all-gather of rows)"
-        if world > 1 and has_umi:
+        # measurement aid: BC_SPLIT_COUNT=1 uses the routed path on one GPU too (decode and table updates in separate,
+        # overlapping kernels instead of one fused kernel)
+        self.routed = has_umi and (world > 1 or bool(os.environ.get("BC_SPLIT_COUNT")))
+        if self.routed:
             # fused routing: every rank maps every other rank's receive buffer (CUDA IPC over NVLink); the decode
             # kernel stores records straight into the owner's memory.  A (source, owner) region can hold a whole
             # batch, so no key skew can overflow it.
             self.cap = batch_reads
             handles = [None] * world
-            dist.all_gather_object(handles, ctr.route_open(world, rank, self.cap))
+            mine = ctr.route_open(world, rank, self.cap)
+            if world > 1:
+                dist.all_gather_object(handles, mine)
+            else:
+                handles = [mine]
             ctr.route_connect(handles)
             self.counts = torch.zeros((2, world), dtype=torch.int32, device=device)          # what I sent, per parity
             self.all_counts = torch.zeros((2, world * world), dtype=torch.int32, device=device)  # [source][owner]
             self.parity = 0
-            dist.barrier()
+            if world > 1:
+                dist.barrier()
 
     def to_pinned(self, dev_batch):
         return HostBatch(self.bc, dev_batch)
@@ -131,7 +141,7 @@ class Job:
         ctr = self.ctr
         ctr.reset()
         with torch.cuda.stream(self.stream):
-            if self.world > 1 and self.has_umi:
+            if self.routed:
                 for b in batches:
                     self._routed(self._b(b))
             else:
@@ -155,7 +165,10 @@ class Job:
         p = self.parity
         self.parity ^= 1
         self.ctr.route_submit(batch, p, self.counts[p])
-        dist.all_gather_into_tensor(self.all_counts[p], self.counts[p])
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.all_counts[p], self.counts[p])
+        else:
+            self.all_counts[p].copy_(self.counts[p])
         # records sent to me by source s: all_counts[p][s * world + rank]
         self.ctr.route_insert(p, self.all_counts[p].data_ptr() + 4 * self.rank, self.world, int(batch.n * 1.5))
 
