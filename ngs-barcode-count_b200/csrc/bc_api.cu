@@ -719,7 +719,14 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     T.umi_bits = d.umi_bits;
     T.has_set = d.has_umi ? 1 : 0;
     const uint32_t map_bits = d.key_bits - d.umi_bits;
-    if (map_bits <= 27) rc = alloc_table(ctx, T.map, 0, 0, 1ull << map_bits, ctx->d_counters + BC_N_COUNTERS);
+    // Dense counters (index = key: one fire-and-forget RED per update, no key storage, no probe) whenever the key space
+    // is small — or not much larger than the job itself and affordable in HBM (DEL: 3 x 10 bits = 2^30 counters = 8.6 GB)
+    bool dense = map_bits <= 27;
+    if (!dense && map_bits <= 31 && (1ull << map_bits) <= 4 * hint) {
+        size_t free_b = 0, total_b = 0;
+        dense = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (sizeof(unsigned long long) << map_bits) <= free_b / 4;
+    }
+    if (dense) rc = alloc_table(ctx, T.map, 0, 0, 1ull << map_bits, ctx->d_counters + BC_N_COUNTERS);
     else rc = alloc_table(ctx, T.map, 1, map_bits > 63, slots_for(hint), ctx->d_counters + BC_N_COUNTERS);
     if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, d.wide, slots_for(hint), ctx->d_counters + BC_N_COUNTERS + 1);
     if (rc != BC_OK) {

@@ -106,3 +106,41 @@ def test_job_is_independent_of_batching_and_order(name, tmp_path):
         c1, r1 = job(cuts, rev)
         assert c1 == c0
         assert r1.shape == r0.shape and bool((r1 == r0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["del3", "lineage"])
+def test_routed_path_on_one_gpu_equals_fused(name, tmp_path, monkeypatch):
+    """The multi-GPU route API (bc_route_open / connect / submit / insert: records stored into a receive buffer by the
+    decode kernel, inserted by a second kernel on its own stream) driven with a single rank must give exactly the
+    fused single-kernel result.  Covers the N > 1 device code on a one-GPU box."""
+    import torch
+    from ngs_barcode_count_b200.multi import Job
+    n, batch = 1_000_000, 300_000
+    wl = synth.Workload(name, str(tmp_path / name), reads=n)
+    run = wl.run(bc)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        batches = [wl.generate_device(run, a, min(batch, n - a), stream=stream.cuda_stream) for a in range(0, n, batch)]
+    stream.synchronize()
+
+    def result(split):
+        if split:
+            monkeypatch.setenv("BC_SPLIT_COUNT", "1")
+        else:
+            monkeypatch.delenv("BC_SPLIT_COUNT", raising=False)
+        ctr = bc.Counter(run, expected_reads=n)
+        ctr.set_stream(stream.cuda_stream)
+        job = Job(bc, ctr, run, 1, 0, "cuda:0", stream, True, batch)
+        assert job.routed == split
+        for _ in range(2):
+            job.step(batches, to_host=True)
+        k, lo, hi, cnt = ctr.finish_view()
+        hi = hi if hi is not None else np.zeros(k, np.uint64)
+        order = np.lexsort((lo, hi))
+        return ctr.counters(), np.stack([hi[order], lo[order], cnt[order]], axis=1).copy()
+
+    c0, r0 = result(False)
+    c1, r1 = result(True)
+    assert c0 == c1 and sum(c0.values()) == n and (name != "del3" or c0["duplicates"] > 0)
+    assert r0.shape == r1.shape and bool((r0 == r1).all())
