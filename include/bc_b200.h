@@ -227,6 +227,10 @@ int bc_route_insert(bc_ctx *ctx, uint32_t parity, const uint32_t *dev_counts_fro
 int bc_export_rows(bc_ctx *ctx, uint64_t **dev_key_lo, uint64_t **dev_key_hi, uint64_t **dev_count, uint64_t *n_rows);
 int bc_import_rows(bc_ctx *ctx, const uint64_t *dev_key_lo, const uint64_t *dev_key_hi, const uint64_t *dev_count,
                    uint64_t n_rows);
+/* When the count table is a dense array (small key space, no random barcode) ranks can merge with ONE in-place
+ * all-reduce (sum) over it instead of exchanging rows: *dev_counts / *n give the device array (u64 per key), or
+ * NULL / 0 when the table is not dense.  Work queued on the ctx stream so far is ordered before the caller's use. */
+int bc_dense_counts(bc_ctx *ctx, uint64_t **dev_counts, uint64_t *n);
 int bc_add_counters(bc_ctx *ctx, const uint64_t add[BC_N_COUNTERS]);
 int bc_reset(bc_ctx *ctx); /* clear tables and counters, keep configuration */
 

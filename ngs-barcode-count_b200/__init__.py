@@ -103,6 +103,7 @@ _PROTOS = {
     "bc_export_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_uint64)]),
     "bc_import_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bc_dense_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bc_add_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bc_reset": (C.c_int, [C.c_void_p]),
     "bc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -396,6 +397,11 @@ class Counter:
         lo, hi, cnt, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
         self._ck(lib().bc_export_rows(self.h, C.byref(lo), C.byref(hi), C.byref(cnt), C.byref(n)), "bc_export_rows")
         return lo.value, hi.value, cnt.value, int(n.value)
+
+    def dense_counts(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(lib().bc_dense_counts(self.h, C.byref(p), C.byref(n)), "bc_dense_counts")
+        return p.value, int(n.value)
 
     def import_rows(self, lo, hi, cnt, n):
         self._ck(lib().bc_import_rows(self.h, C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()) if hi is not None else None,

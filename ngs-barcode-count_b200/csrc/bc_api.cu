@@ -71,6 +71,8 @@ struct bc_ctx {
     uint64_t def_cap = 0;
     // fused routing over NVLink (bc_route_*): this rank's receive regions [2 parities][n_ranks][capacity] and the peers'
     Key* d_recv = nullptr;
+    Key* d_send = nullptr;  // local buckets [n_ranks][capacity], pushed to the owners after each decode
+    uint32_t* d_cursors = nullptr;  // bucket cursors, one cache line apart
     Key* peer_recv[kMaxRanks] = {nullptr};
     uint32_t route_ranks = 0, route_rank = 0;
     uint64_t route_cap = 0;
@@ -379,6 +381,8 @@ void bc_destroy(bc_ctx* ctx) {
     for (uint32_t r = 0; r < ctx->route_ranks; r++)
         if (r != ctx->route_rank && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
     if (ctx->d_recv) cudaFree(ctx->d_recv);
+    if (ctx->d_send) cudaFree(ctx->d_send);
+    if (ctx->d_cursors) cudaFree(ctx->d_cursors);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->insert_stream) {
         cudaStreamSynchronize(ctx->insert_stream);
@@ -1121,6 +1125,7 @@ int bc_decode_route(bc_ctx* ctx, const bc_batch* batch, uint32_t n_ranks, bc_rec
     for (uint32_t k = 0; k < n_ranks; k++) r.dst[k] = reinterpret_cast<Key*>(dev_buckets) + (size_t)k * bucket_capacity;
     r.capacity = bucket_capacity;
     r.counts = dev_bucket_counts;
+    r.count_stride = 1;
     r.n_ranks = n_ranks;
     return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
 }
@@ -1132,6 +1137,8 @@ int bc_route_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacit
     static_assert(sizeof(cudaIpcMemHandle_t) == BC_IPC_HANDLE_BYTES, "BC_IPC_HANDLE_BYTES");
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaMalloc(&ctx->d_recv, 2ull * n_ranks * capacity * sizeof(Key)));
+    CK(ctx, cudaMalloc(&ctx->d_send, (size_t)n_ranks * capacity * sizeof(Key)));
+    CK(ctx, cudaMalloc(&ctx->d_cursors, (size_t)kMaxRanks * 32 * sizeof(uint32_t)));
     cudaIpcMemHandle_t h;
     CK(ctx, cudaIpcGetMemHandle(&h, ctx->d_recv));
     memcpy(ipc_handle_out, &h, sizeof h);
@@ -1170,15 +1177,23 @@ int bc_route_submit(bc_ctx* ctx, const bc_batch* batch, uint32_t parity, uint32_
     for (uint32_t r = 0; r < ctx->route_ranks; r++)
         if (!ctx->peer_recv[r]) return fail(ctx, BC_ESTATE, "bc_route_submit before bc_route_connect");
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaMemsetAsync(dev_counts, 0, ctx->route_ranks * sizeof(uint32_t), ctx->stream));
-    RouteOut r{};
-    for (uint32_t k = 0; k < ctx->route_ranks; k++)  // my region inside rank k's receive buffer
-        r.dst[k] = ctx->peer_recv[k] + ((size_t)parity * ctx->route_ranks + ctx->route_rank) * ctx->route_cap;
-    r.capacity = ctx->route_cap;
-    r.counts = dev_counts;
-    r.n_ranks = ctx->route_ranks;
-    int rc = run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+    CK(ctx, cudaMemsetAsync(ctx->d_cursors, 0, (size_t)kMaxRanks * 32 * sizeof(uint32_t), ctx->stream));
+    RouteOut local{}, remote{};
+    for (uint32_t k = 0; k < ctx->route_ranks; k++) {
+        local.dst[k] = ctx->d_send + (size_t)k * ctx->route_cap;
+        // my region inside rank k's receive buffer
+        remote.dst[k] = ctx->peer_recv[k] + ((size_t)parity * ctx->route_ranks + ctx->route_rank) * ctx->route_cap;
+    }
+    local.capacity = remote.capacity = ctx->route_cap;
+    local.counts = remote.counts = ctx->d_cursors;
+    local.count_stride = remote.count_stride = 32;
+    local.n_ranks = remote.n_ranks = ctx->route_ranks;
+    int rc = run_decode(ctx, batch, F_ROUTE, DecodeOut{}, local, ctx->d_counters);
     if (rc != BC_OK) return rc;
+    {
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_push(local, remote, dev_counts, ctx->stream));
+    }
     // The caller's collective that follows tells the peers "my receive buffer of the other parity is free again", so it
     // has to be ordered after my insert of the previous batch — which ran concurrently with the decode just launched.
     if (ctx->insert_pending) {
@@ -1250,6 +1265,18 @@ int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_
     CK(ctx, launch_insert(ctx->tables, reinterpret_cast<const unsigned long long*>(dev_key_lo),
                           reinterpret_cast<const unsigned long long*>(dev_key_hi), nullptr,
                           reinterpret_cast<const unsigned long long*>(dev_count), n_rows, nullptr, ctx->stream));
+    return BC_OK;
+}
+
+int bc_dense_counts(bc_ctx* ctx, uint64_t** dev_counts, uint64_t* n) {
+    if (!ctx || !dev_counts || !n) return BC_EINVAL;
+    *dev_counts = nullptr;
+    *n = 0;
+    if (ctx->tables.map.kind != 0 || ctx->tables.has_set) return BC_OK;  // not a dense, UMI-free table: merge rows instead
+    *dev_counts = reinterpret_cast<uint64_t*>(ctx->tables.map.data);
+    *n = ctx->tables.map.cap;
+    ctx->imported_rows = ctx->tables.map.cap;  // the caller is about to add other ranks' counts in place
+    ctx->rows_valid = false;
     return BC_OK;
 }
 

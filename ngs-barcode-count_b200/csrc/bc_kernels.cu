@@ -309,7 +309,7 @@ __device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& t
     if (flags & F_INSERT) return count_read(tables, key, new_key, new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
     if (flags & F_ROUTE) {
         const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
-        const uint32_t slot = atomicAdd(&route.counts[owner], 1u);
+        const uint32_t slot = atomicAdd(&route.counts[owner * route.count_stride], 1u);
         if (slot < route.capacity) route.dst[owner][slot] = key;
         return -2;  // outcome is decided by the owner rank
     }
@@ -469,17 +469,30 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     }
 
     const int lane = tid & 31;
-    // ---- multi-GPU: matched (key, UMI) records go to the bucket of their owner rank; one atomic per warp and rank
+    // ---- multi-GPU: matched (key, UMI) records go to the bucket of their owner rank.  Positions are reserved with ONE
+    // global atomic per CTA and rank (warp counts -> shared-memory prefix -> global cursor): the cursors are hot
+    // addresses and same-address atomics serialise in L2.
     if (flags & F_ROUTE) {
+        __shared__ uint32_t s_rcnt[kMaxRanks], s_rbase[kMaxRanks];
+        if (tid < kMaxRanks) s_rcnt[tid] = 0;
+        __syncthreads();
         const uint32_t owner = status == kRouted ? (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks) : 0xFFFFFFFFu;
+        uint32_t my_pos = 0;
         for (uint32_t r = 0; r < route.n_ranks; r++) {
             const unsigned m = __ballot_sync(0xFFFFFFFFu, owner == r);
             if (!m) continue;
             const int leader = __ffs(m) - 1;
             uint32_t at = 0;
-            if (lane == leader) at = atomicAdd(&route.counts[r], (uint32_t)__popc(m));
+            if (lane == leader) at = atomicAdd(&s_rcnt[r], (uint32_t)__popc(m));
             at = __shfl_sync(0xFFFFFFFFu, at, leader) + __popc(m & ((1u << lane) - 1u));
-            if (owner == r && at < route.capacity) route.dst[r][at] = key;
+            if (owner == r) my_pos = at;
+        }
+        __syncthreads();
+        if (tid < route.n_ranks && s_rcnt[tid]) s_rbase[tid] = atomicAdd(&route.counts[tid * route.count_stride], s_rcnt[tid]);
+        __syncthreads();
+        if (owner != 0xFFFFFFFFu) {
+            const uint32_t at = s_rbase[owner] + my_pos;
+            if (at < route.capacity) route.dst[owner][at] = key;
         }
     }
     // ---- deferred reads: one warp-aggregated append per warp
@@ -802,6 +815,27 @@ __global__ void k_insert(const Tables tables, const unsigned long long* __restri
         if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
         if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
     }
+}
+
+// Local buckets -> the owners' receive regions over NVLink.  Consecutive lanes move consecutive 16-byte records, so
+// the peer stores leave the SM as full 512-byte warp transactions (stores issued record by record from inside the
+// decode kernel were transaction-rate bound on NVLink: 32 GB/s at 8 GPUs).
+__global__ void k_push(const RouteOut local, const RouteOut remote, uint32_t* __restrict__ compact_counts) {
+    if (blockIdx.x == 0 && threadIdx.x < local.n_ranks)  // contiguous counts for the caller's all-gather
+        compact_counts[threadIdx.x] = (uint32_t)min((unsigned long long)local.counts[threadIdx.x * local.count_stride], local.capacity);
+    for (uint32_t r = 0; r < local.n_ranks; r++) {
+        const unsigned long long n = min((unsigned long long)local.counts[r * local.count_stride], local.capacity);
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(local.dst[r]);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(remote.dst[r]);
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
+cudaError_t launch_push(const RouteOut& local, const RouteOut& remote, uint32_t* compact_counts, cudaStream_t stream) {
+    k_push<<<148 * 4, 256, 0, stream>>>(local, remote, compact_counts);
+    return cudaGetLastError();
 }
 
 // routed records of one round: segment s = what rank s sent to this rank, its length read on the device

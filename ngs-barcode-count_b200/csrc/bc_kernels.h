@@ -21,7 +21,8 @@ constexpr int kMaxRanks = 8;  // one box
 struct RouteOut {
     Key* dst[kMaxRanks];
     unsigned long long capacity;  // records per destination
-    uint32_t* counts;             // [n_ranks] local cursors
+    uint32_t* counts;             // local cursors: counts[r * count_stride]
+    uint32_t count_stride;        // cursors of different ranks on different cache lines (same-sector atomics serialise)
     uint32_t n_ranks;
 };
 
@@ -70,6 +71,9 @@ cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned lon
                             cudaStream_t stream);
 
 cudaError_t launch_clear_map(const DevTable& t, cudaStream_t stream);
+
+// copies the local buckets (local.counts[r] records each) to remote.dst[r] with coalesced 16-byte lanes
+cudaError_t launch_push(const RouteOut& local, const RouteOut& remote, uint32_t* compact_counts, cudaStream_t stream);
 
 // routed records received from every rank: segment s holds counts[s * count_stride] records at records + s * capacity
 cudaError_t launch_insert_segments(const Tables& tables, const Key* records, unsigned long long capacity, const uint32_t* counts,

@@ -107,7 +107,8 @@ class Job:
             self.parallelism = (f"reads sharded over {world} GPUs; (key,UMI) records stored by the decode kernel into the owner "
                                 f"GPU hash(key)%{world} over NVLink peer memory; one tiny NCCL all-gather of counts per batch")
         else:
-            self.parallelism = f"reads sharded over {world} GPUs; tables merged once at the end (all-gather of rows)"
+            self.parallelism = (f"reads sharded over {world} GPUs; tables merged once at the end (in-place all-reduce of the "
+                                f"dense count table, or gather of rows for hashed tables)")
         # measurement aid: BC_SPLIT_COUNT=1 uses the routed path on one GPU too (decode and table updates in separate,
         # overlapping kernels instead of one fused kernel)
         self.routed = has_umi and (world > 1 or bool(os.environ.get("BC_SPLIT_COUNT")))
@@ -173,6 +174,16 @@ class Job:
         self.ctr.route_insert(p, self.all_counts[p].data_ptr() + 4 * self.rank, self.world, int(batch.n * 1.5))
 
     def _merge_rows(self, to_host):
+        ptr, n_dense = self.ctr.dense_counts()
+        if n_dense:  # dense table: one in-place all-reduce, then rank 0 extracts the rows
+            dist.all_reduce(dev_tensor(ptr, n_dense, self.device))
+            if self.rank == 0:
+                n_rows = self.ctr.finish_view()[0] if to_host else self.ctr.export_rows()[3]
+            else:
+                n_rows = 0
+            t = torch.tensor([n_rows], dtype=torch.int64, device=self.device)
+            dist.broadcast(t, src=0)
+            return int(t.item())
         lo, hi, cnt, n = self.ctr.export_rows()
         wide = hi is not None and hi != 0
         cols = [dev_tensor(p, n, self.device) for p in ((lo, hi, cnt) if wide else (lo, cnt))]
