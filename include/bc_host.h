@@ -59,7 +59,8 @@ int bch_count_fastq(bch_run *run, bc_ctx *ctx, const char *fastq_path, unsigned 
                     uint64_t *total_reads, char *err, int errlen);
 
 /* WriteFiles::write_counts_files: per-sample count CSVs, merged CSV, Single/Double enrichment CSVs, same names
- * and layout as the reference; rows are written sorted.  names_out receives the '\n'-joined file names. */
+ * and layout as the reference; rows are written sorted.  names_out receives one "file name<TAB>barcode rows" line
+ * per file written (what the reference keeps for its stats file, output.rs:143-165).  Returns the number of files. */
 int bch_write_counts(bch_run *run, bc_ctx *ctx, const char *output_dir, const char *prefix, int merge_output, int enrich,
                      char *names_out, int names_len, char *err, int errlen);
 

@@ -366,7 +366,7 @@ class Counter:
         n = lib().bch_write_counts(self.run.h, self.h, _b(outdir), _b(prefix), int(merge), int(enrich), names, 1 << 20, err, 2048)
         if n < 0:
             raise BcError("bch_write_counts: " + err.value.decode())
-        return [x for x in names.value.decode().split("\n") if x]
+        return [x.split("\t")[0] for x in names.value.decode().split("\n") if x]
 
     # ---- multi-GPU building blocks (device pointers) ----
     def decode_route(self, batch, n_ranks, buckets, capacity, counts):

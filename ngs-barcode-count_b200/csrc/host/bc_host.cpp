@@ -4,6 +4,10 @@
 #include "../../../include/bc_host.h"
 
 #include <cuda_runtime_api.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -497,6 +501,73 @@ int pack_refs(uint32_t max_read_len, const std::vector<ReadRef>& reads, size_t f
     return bad ? BC_EINVAL : BC_OK;
 }
 
+// ---- plain FASTQ through mmap: no read() copy at all; host threads split and pack their own slice of the mapping.
+// A record can only start at a line that begins with '@' and whose line after next begins with '+': a quality line
+// may begin with '@' too, but then the line after next is a sequence line, which never begins with '+'.
+const char* find_record_start(const char* p, const char* end) {
+    while (p < end) {
+        if (*p == '@') {
+            const char* l1 = (const char*)memchr(p, '\n', (size_t)(end - p));
+            if (!l1) return end;
+            const char* l2 = (const char*)memchr(l1 + 1, '\n', (size_t)(end - l1 - 1));
+            if (!l2) return end;
+            if (l2 + 1 < end && l2[1] == '+') return p;
+        }
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!nl) return end;
+        p = nl + 1;
+    }
+    return end;
+}
+
+// whole records of [p, end) -> out; returns the position after the last whole record.  at_eof: the last line may lack '\n'.
+const char* split_records(const char* p, const char* end, bool at_eof, std::vector<ReadRef>& out) {
+    for (;;) {
+        const char* line[4];
+        uint32_t len[4];
+        const char* q = p;
+        int k = 0;
+        for (; k < 4; k++) {
+            const char* nl = q < end ? (const char*)memchr(q, '\n', (size_t)(end - q)) : nullptr;
+            const char* stop;
+            if (nl) stop = nl;
+            else if (at_eof && k == 3 && q < end) stop = end;
+            else break;
+            size_t l = (size_t)(stop - q);
+            if (l && stop[-1] == '\r') l--;
+            line[k] = q;
+            len[k] = (uint32_t)l;
+            q = nl ? nl + 1 : stop;
+        }
+        if (k < 4) return p;
+        out.push_back(ReadRef{line[1], line[3], len[1], len[3]});
+        p = q;
+    }
+}
+
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    ~MappedFile() {
+        if (data && size) munmap(const_cast<char*>(data), size);
+        if (fd >= 0) close(fd);
+    }
+    bool open_plain(const char* path) {  // false: not a plain regular file we can map (gzip, pipe, empty...)
+        fd = open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 2) return false;
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        data = static_cast<const char*>(m);
+        size = (size_t)st.st_size;
+        if ((unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) return false;  // gzip
+        madvise(m, size, MADV_SEQUENTIAL);
+        return true;
+    }
+};
+
 // ---- output ---------------------------------------------------------------------------------------------------
 
 std::string join(const std::vector<std::string>& v) {
@@ -542,6 +613,8 @@ void decode_rows(const bch_run& run, const bc_ctx* ctx, const bc_table& t, std::
     }
 }
 
+// writes one file; `names` collects "name<TAB>number of barcode rows" (the pair the reference keeps in
+// WriteFiles::output_files / output_counts for its stats file, output.rs:143-165)
 void write_text(const std::string& dir, const std::string& name, const std::string& text, std::vector<std::string>& names) {
     std::string path = dir;
     if (!path.empty() && path.back() != '/') path.push_back('/');
@@ -549,7 +622,9 @@ void write_text(const std::string& dir, const std::string& name, const std::stri
     std::ofstream out(path, std::ios::binary);
     if (!out) throw Error("cannot create " + path);
     out << text;
-    names.push_back(name);
+    size_t rows = 0;
+    for (char c : text) rows += c == '\n';
+    names.push_back(name + "\t" + std::to_string(rows ? rows - 1 : 0));
 }
 
 }  // namespace
@@ -685,6 +760,119 @@ int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned 
             for (FastqBlock& B : I.blocks) B.buf.resize(block_bytes);
             I.batch_reads = batch_reads;
             I.with_qual = with_qual;
+        }
+        {
+            const std::string path = fastq_path;
+            auto ends = [&](const char* suf) {
+                const size_t k = strlen(suf);
+                return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
+            };
+            if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
+                throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
+        }
+        MappedFile mf;
+        if (mf.open_plain(fastq_path)) {
+            // plain file: every host thread splits and packs its own slice of each block of the mapping
+            const size_t block_bytes = I.blocks[0].buf.size();
+            const char* pos = mf.data;
+            const char* const eof = mf.data + mf.size;
+            std::vector<std::vector<ReadRef>> parts(threads);
+            uint64_t total = 0;
+            int cur = 0, in_flight = 0;
+            while (pos < eof) {
+                const char* blk_end = std::min(eof, pos + block_bytes);
+                const bool last = blk_end == eof;
+                // slice starts: thread 0 starts at pos (a record start by construction), the others at the first record
+                // start at or after their nominal position
+                std::vector<const char*> start(threads + 1);
+                start[0] = pos;
+                start[threads] = blk_end;
+                const size_t span = (size_t)(blk_end - pos) / threads;
+                {
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 1; t < threads; t++)
+                        pool.emplace_back([&, t]() {
+                            const char* nominal = pos + span * t;
+                            const char* nl = (const char*)memchr(nominal, '\n', (size_t)(blk_end - nominal));
+                            start[t] = nl ? find_record_start(nl + 1, blk_end) : blk_end;
+                        });
+                    for (auto& th : pool) th.join();
+                }
+                for (unsigned t = 1; t < threads; t++) start[t] = std::max(start[t], start[t - 1]);
+                std::vector<const char*> stop(threads);
+                {
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 0; t < threads; t++)
+                        pool.emplace_back([&, t]() {
+                            parts[t].clear();
+                            // a slice ends where the next begins, except the last one, which ends at the last whole record
+                            const bool tail = t + 1 == threads;
+                            stop[t] = split_records(start[t], tail ? blk_end : start[t + 1], tail && last, parts[t]);
+                        });
+                    for (auto& th : pool) th.join();
+                }
+                size_t n_block = 0;
+                for (unsigned t = 0; t < threads; t++) n_block += parts[t].size();
+                const char* consumed = stop[threads - 1];
+                if (n_block == 0) {
+                    if (last) break;  // trailing partial record: dropped, as the reference never posts it
+                    throw Error("FASTQ record longer than the block buffer");
+                }
+                // pack + submit in pinned batches of at most batch_reads records
+                size_t t_idx = 0, r_idx = 0;
+                while (n_block) {
+                    const size_t n = std::min<size_t>(n_block, batch_reads);
+                    if (in_flight == 2) {
+                        if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+                        in_flight = 0;
+                    }
+                    PinnedBatch& p = I.pinned[cur];
+                    // (thread, first record, count, destination offset) work items covering records [done, done + n)
+                    struct Item { size_t t, first, count, dst; };
+                    std::vector<Item> items;
+                    size_t filled = 0;
+                    while (filled < n) {
+                        const size_t avail = parts[t_idx].size() - r_idx;
+                        if (avail == 0) { t_idx++; r_idx = 0; continue; }
+                        const size_t take = std::min(avail, n - filled);
+                        items.push_back(Item{t_idx, r_idx, take, filled});
+                        filled += take;
+                        r_idx += take;
+                    }
+                    std::atomic<int> bad{0};
+                    {
+                        std::vector<std::thread> pool;
+                        for (const Item& it : items)
+                            pool.emplace_back([&, it]() {
+                                const uint32_t ps = bc_plane_stride(mrl), qs = bc_qual_stride(mrl);
+                                if (pack_refs(mrl, parts[it.t], it.first, it.count, p.planes + it.dst * ps, p.read_len + it.dst,
+                                              with_qual ? p.qual + it.dst * qs : nullptr, 1) != BC_OK)
+                                    bad = 1;
+                            });
+                        for (auto& th : pool) th.join();
+                    }
+                    if (bad)
+                        throw Error("FASTQ record " + std::to_string(total) + "+: read longer than max_read_len (" + std::to_string(mrl) +
+                                    ") or quality/sequence length mismatch");
+                    bc_batch b{};
+                    b.n_reads = (uint32_t)n;
+                    b.plane_stride = bc_plane_stride(mrl);
+                    b.qual_stride = bc_qual_stride(mrl);
+                    b.location = BC_LOC_HOST;
+                    b.planes = p.planes;
+                    b.read_len = p.read_len;
+                    b.qual = with_qual ? p.qual : nullptr;
+                    if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
+                    total += n;
+                    n_block -= n;
+                    cur ^= 1;
+                    in_flight++;
+                }
+                pos = consumed;
+            }
+            if (bc_sync(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+            if (total_reads) *total_reads = total;
+            return BC_OK;
         }
         for (FastqBlock& B : I.blocks) B.state = 0;
         FastqStream in(fastq_path);

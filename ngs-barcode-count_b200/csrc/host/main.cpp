@@ -174,7 +174,43 @@ int main(int argc, char** argv) {
         bch_close(run);
         return 1;
     }
-    printf("%s", names);
+    // file names as they were written, then the run record the reference appends to {prefix}_barcode_stats.txt
+    // (output.rs:488-576): same sections; the times are this run's
+    std::string listing, stats_files;
+    for (char* line = strtok(names, "\n"); line; line = strtok(nullptr, "\n")) {
+        char* tab = strchr(line, '\t');
+        const std::string fname = tab ? std::string(line, tab) : std::string(line);
+        const unsigned long long rows = tab ? strtoull(tab + 1, nullptr, 10) : 0;
+        listing += fname + "\n";
+        stats_files += "File & barcodes counted: " + fname + "\t" + thousands(rows) + "\n";
+    }
+    printf("%s", listing.c_str());
+    {
+        std::string dir = outdir;
+        if (!dir.empty() && dir.back() != '/') dir.push_back('/');
+        FILE* sf = fopen((dir + prefix + "_barcode_stats.txt").c_str(), "a");
+        if (sf) {
+            char t_start[32], t_end[32];
+            const time_t now = time(nullptr);
+            const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const time_t started = now - (time_t)elapsed;
+            strftime(t_start, sizeof t_start, "%Y-%m-%d %H:%M:%S", localtime(&started));
+            strftime(t_end, sizeof t_end, "%Y-%m-%d %H:%M:%S", localtime(&now));
+            fprintf(sf, "-TIME INFORMATION-\nStart: %s\nFinish: %s\nTotal time: %s\n\n", t_start, t_end, hms(elapsed).c_str());
+            fprintf(sf, "-INPUT FILES-\nFastq: %s\nFormat: %s\nSamples: %s\nBarcodes: %s\n\n", fastq.c_str(), format.c_str(),
+                    samples.empty() ? "None" : samples.c_str(), counted.empty() ? "None" : counted.c_str());
+            fprintf(sf, "%s\n", bch_describe(run));
+            fprintf(sf, "-RESULTS-\nTotal sequences:             %s\nCorrectly matched sequences: %s\nConstant region mismatches:  %s\n"
+                        "Sample barcode mismatches:   %s\nCounted barcode mismatches:  %s\nDuplicates:                  %s\n"
+                        "Low quality barcodes:        %s\n\n",
+                    thousands(total).c_str(), thousands(c[BC_CNT_MATCHED]).c_str(), thousands(c[BC_CNT_CONSTANT]).c_str(),
+                    thousands(c[BC_CNT_SAMPLE]).c_str(), thousands(c[BC_CNT_COUNTED]).c_str(), thousands(c[BC_CNT_DUPLICATES]).c_str(),
+                    thousands(c[BC_CNT_LOW_QUALITY]).c_str());
+            fprintf(sf, "-OUTPUT FILES-\n%s\n", stats_files.c_str());
+            fprintf(sf, "--------------------------------------------------------------------------------------------------\n\n\n");
+            fclose(sf);
+        }
+    }
     const auto t2 = std::chrono::steady_clock::now();
     printf("\nTotal time: %s\n", hms(std::chrono::duration<double>(t2 - t0).count()).c_str());
     bc_destroy(ctx);

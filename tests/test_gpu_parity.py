@@ -138,6 +138,14 @@ def test_cli_drop_in(case, gz, tmp_path):
     assert f"Correctly matched sequences: {c['matched']:,}" in r.stdout
     assert f"Constant region mismatches:  {c['constant_region']:,}" in r.stdout
     assert f"Duplicates:                  {c['duplicates']:,}" in r.stdout
+    # the run record the reference appends (output.rs:488-576): same sections, one line per file written
+    stats = (out / "golden_barcode_stats.txt").read_text()
+    for section in ("-TIME INFORMATION-", "-INPUT FILES-", "-FORMAT-", "-BARCODE INFO-", "-RESULTS-", "-OUTPUT FILES-"):
+        assert section in stats
+    assert f"Correctly matched sequences: {c['matched']:,}" in stats
+    assert stats.count("File & barcodes counted: ") == len(exp["files"])
+    for fn, lines in exp["files"].items():
+        assert f"File & barcodes counted: {fn}\t{len(lines) - 1:,}" in stats
 
 
 # ---- hand-derived vectors on the reference's example files ------------------------------
