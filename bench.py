@@ -268,13 +268,26 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = (bpr * per_gpu * args.steps / 1e9) / (dec_ms * 1e-3) if dec_ms > 0 else 0.0
+    # the counting step adds "one table slot RMW (random access => count 32 B sector per probe)".  A table
+    # that does not fit the 126 MB L2 costs DRAM sectors: read + write-back of the (key, UMI) set sector for every read
+    # that reaches the count, and of the key->count sector for every pair seen for the first time.
+    reached = (counters["matched"] + counters["duplicates"]) / total_reads
+    fresh = counters["matched"] / total_reads
+    slot_b = 8 if prof["dense_table"] else (32 if prof["wide_keys"] else 16)
+    map_in_dram = prof["table_capacity"] * slot_b > 126e6
+    table_bpr = (64.0 * reached if has_umi else 0.0) + (64.0 * (fresh if has_umi else reached) if map_in_dram else 0.0)
+    if job.routed:  # multi-GPU with a random barcode: the decode kernel only buckets records, the owner's insert kernel counts
+        table_bpr = 16.0 * reached
+    achieved_input = (bpr * per_gpu * args.steps / 1e9) / (dec_ms * 1e-3) if dec_ms > 0 else 0.0
+    achieved = ((bpr + table_bpr) * per_gpu * args.steps / 1e9) / (dec_ms * 1e-3) if dec_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.config)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_decode", "bytes_per_read": bpr, "reads_per_launch": per_gpu * args.steps / max(1, dec_launches),
+                "kernel": "k_decode", "bytes_per_read": bpr + table_bpr, "bytes_per_read_input": bpr,
+                "bytes_per_read_table_sectors": table_bpr, "achieved_input_only": achieved_input,
+                "frac_input_only": achieved_input / peak, "reads_per_launch": per_gpu * args.steps / max(1, dec_launches),
                 "avg_launch_ms": dec_ms / max(1, dec_launches), "kernel_share_of_step": dec_ms / (ms_total if ms_total else 1),
                 "peak_source": peak_src, "kernel_ms": prof["ms"], "kernel_launches": prof["launches"]}
     gpu_launches = sum(prof["launches"].values())
