@@ -52,7 +52,7 @@ def build(force=False, verbose_ptxas=False):
     cli = os.path.join(BIN, "barcode-count")
     cli_src = [os.path.join(CSRC, "host", "main.cpp")]
     if force or _newer(cli, cli_src + [lib] + headers):
-        _run([NVCC] + ARCH + COMMON + ["-o", cli] + cli_src + ["-L", LIB, "-lbc_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"])
+        _run([NVCC] + ARCH + COMMON + ["-o", cli] + cli_src + ["-L", LIB, "-lbc_b200", "-lz", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"])
     return lib
 
 

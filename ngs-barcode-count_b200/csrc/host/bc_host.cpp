@@ -674,7 +674,8 @@ bch_run* bch_open(const bch_args* args, char* err, int errlen) {
         }
         c.max_const_err = run->max_constant;
         c.min_quality = run->min_quality;
-        c.max_read_len = args->max_read_len ? args->max_read_len : std::max<uint32_t>(160, 2 * c.template_len);
+        c.max_read_len = args->max_read_len ? std::max<uint32_t>(args->max_read_len, c.template_len)
+                                            : std::max<uint32_t>(160, 2 * c.template_len);
         describe(*run);
         return run;
     } catch (const std::exception& e) {

@@ -8,6 +8,8 @@
 #include <string>
 #include <thread>
 
+#include <zlib.h>
+
 #include "../../../include/bc_host.h"
 
 static void usage() {
@@ -32,7 +34,7 @@ static void usage() {
             "    -s, --sample-barcodes <sample_file>      Sample barcodes file\n"
             "    -t, --threads <threads>                  Number of host threads (FASTQ parse + pack)\n"
             "        --device <n>                         CUDA device [default: 0]\n"
-            "        --max-read-length <n>                Longest read in the FASTQ [default: max(160, 2 x scheme length)]\n"
+            "        --max-read-length <n>                Longest read in the FASTQ [default: from the first reads of the file]\n"
             "        --batch-reads <n>                    Reads per GPU batch [default: 1048576]\n");
 }
 
@@ -51,6 +53,30 @@ static std::string hms(double secs) {
     char buf[96];
     snprintf(buf, sizeof buf, "%ld hours, %ld minutes, %ld.%03ld seconds", ms / 3600000, (ms / 60000) % 60, (ms / 1000) % 60, ms % 1000);
     return buf;
+}
+
+// Longest sequence line among the first records of the FASTQ (plain or gzip; up to 8 MB of text are looked at), so that
+// --max-read-length rarely has to be given by hand.  0 when the file cannot be read.
+static unsigned probe_read_len(const std::string& path) {
+    gzFile gz = gzopen(path.c_str(), "rb");
+    if (!gz) return 0;
+    std::string buf(8u << 20, '\0');
+    const int got = gzread(gz, &buf[0], (unsigned)buf.size());
+    gzclose(gz);
+    if (got <= 0) return 0;
+    unsigned longest = 0, line_no = 0;
+    size_t start = 0;
+    for (size_t i = 0; i < (size_t)got; i++) {
+        if (buf[i] != '\n') continue;
+        if (line_no % 4 == 1) {
+            size_t len = i - start;
+            if (len && buf[i - 1] == '\r') len--;
+            if (len > longest) longest = (unsigned)len;
+        }
+        line_no++;
+        start = i + 1;
+    }
+    return longest;
 }
 
 int main(int argc, char** argv) {
@@ -130,6 +156,10 @@ int main(int argc, char** argv) {
     args.max_errors_sample = max_s;
     args.max_errors_constant = max_c;
     args.min_quality = min_quality;
+    if (max_read_len == 0) {  // from the data: the longest of the first reads, with head-room for a few untrimmed ones
+        const unsigned seen = probe_read_len(fastq);
+        if (seen) max_read_len = seen + seen / 4 + 8;
+    }
     args.max_read_len = max_read_len;
     bch_run* run = bch_open(&args, err, sizeof err);
     if (!run) {
