@@ -307,7 +307,8 @@ def random_case(rng, tmp_path, idx):
                 counted=str(counted_path) if counted_path else None), reads, len(layout) - layout.count("R") - layout.count("S")
 
 
-@pytest.mark.parametrize("seed", range(24))
+# BC_TEST_SEEDS=N widens the campaign (one-off soak runs); the committed default keeps the suite short
+@pytest.mark.parametrize("seed", range(int(os.environ.get("BC_TEST_SEEDS", "24"))))
 def test_random_schemes_against_oracle(seed, tmp_path):
     rng = random.Random(1000 + seed)
     paths, reads, n_counted = random_case(rng, tmp_path, seed)
@@ -324,7 +325,12 @@ def test_random_schemes_against_oracle(seed, tmp_path):
     # defined by the oracle as constant_region_error, like the GPU path
     outcomes = [orc.process(s, q) for s, q in reads]
     run = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=min_q, **caps)
-    ctr = bc.Counter(run)
+    try:
+        ctr = bc.Counter(run)
+    except bc.BcError as e:  # documented limit: raw barcodes of more than 42 bases in all do not fit a key
+        if "packed key needs" in str(e):
+            pytest.skip(str(e))
+        raise
     batch = check_reads_against(run, ctr, reads, outcomes)
     ctr.submit(batch)
     c = ctr.counters()
