@@ -278,6 +278,10 @@ def main():
     table_bpr = (64.0 * reached if has_umi else 0.0) + (64.0 * (fresh if has_umi else reached) if map_in_dram else 0.0)
     if job.routed:  # multi-GPU with a random barcode: the decode kernel only buckets records, the owner's insert kernel counts
         table_bpr = 16.0 * reached
+    elif prof["deferred_count"]:
+        # deferred counting: k_decode touches no table; every read owns one record slot (8 or 16 bytes, holes included)
+        # that the kernel writes once.  De-duplication / counting run once per job in the flush kernels (kernel_ms.finish).
+        table_bpr = 16.0 if prof["wide_keys"] else 8.0
     achieved_input = (bpr * per_gpu * args.steps / 1e9) / (dec_ms * 1e-3) if dec_ms > 0 else 0.0
     achieved = ((bpr + table_bpr) * per_gpu * args.steps / 1e9) / (dec_ms * 1e-3) if dec_ms > 0 else 0.0
     traffic = None
@@ -289,7 +293,11 @@ def main():
                 "bytes_per_read_table_sectors": table_bpr, "achieved_input_only": achieved_input,
                 "frac_input_only": achieved_input / peak, "reads_per_launch": per_gpu * args.steps / max(1, dec_launches),
                 "avg_launch_ms": dec_ms / max(1, dec_launches), "kernel_share_of_step": dec_ms / (ms_total if ms_total else 1),
-                "peak_source": peak_src, "kernel_ms": prof["ms"], "kernel_launches": prof["launches"]}
+                "peak_source": peak_src, "kernel_ms": prof["ms"], "kernel_launches": prof["launches"],
+                "counting": ("deferred: records appended by k_decode, partitioned shared-memory de-duplication + counting at the "
+                             "flush (kernel_ms.finish)" if prof["deferred_count"] else
+                             "inline: tables updated read by read inside k_decode"),
+                "flushed_global": prof["flushed_global"]}
     gpu_launches = sum(prof["launches"].values())
     if rank == 0:
         try:  # INT-pipe peaks of this GPU (register-only microbenchmarks) and the pivot-test rate the kernel reaches

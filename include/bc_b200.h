@@ -242,6 +242,9 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t table_capacity, table_entries;
     uint32_t key_bits, wide_keys, dense_table;
+    uint32_t deferred_count; /* 1: matched reads are appended to a record buffer and counted at bc_finish /
+                                bc_get_counters (partitioned, in shared memory); 0: tables updated read by read */
+    uint32_t flushed_global; /* 1: the last flush fell back to the global-memory tables */
 } bc_profile;
 int bc_set_profiling(bc_ctx *ctx, int on);
 int bc_get_profile(bc_ctx *ctx, bc_profile *out); /* synchronises */

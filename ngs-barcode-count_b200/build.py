@@ -41,7 +41,8 @@ def build(force=False, verbose_ptxas=False):
     headers = [os.path.join(ROOT, "include", h) for h in ("bc_b200.h", "bc_host.h")] + [
         os.path.join(CSRC, h) for h in ("bc_device.cuh", "bc_kernels.h")]
     lib = os.path.join(LIB, "libbc_b200.so")
-    lib_src = [os.path.join(CSRC, "bc_kernels.cu"), os.path.join(CSRC, "bc_api.cu"), os.path.join(CSRC, "host", "bc_host.cpp")]
+    lib_src = [os.path.join(CSRC, "bc_kernels.cu"), os.path.join(CSRC, "bc_partition.cu"), os.path.join(CSRC, "bc_api.cu"),
+               os.path.join(CSRC, "host", "bc_host.cpp")]
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
     if force or _newer(lib, lib_src + headers):
         _run([NVCC] + ARCH + COMMON + extra + ["-shared", "-o", lib] + lib_src + ["-lz"])

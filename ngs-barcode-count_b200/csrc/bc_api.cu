@@ -39,6 +39,11 @@ struct ProfEvent {
     int kind;
 };
 
+struct ItemBuf {  // structure-of-arrays device buffer of (lo, hi, w) items, grow-only
+    unsigned long long *lo = nullptr, *hi = nullptr, *w = nullptr;
+    unsigned long long cap = 0;
+};
+
 }  // namespace
 
 struct bc_ctx {
@@ -76,8 +81,25 @@ struct bc_ctx {
     Key* peer_recv[kMaxRanks] = {nullptr};
     uint32_t route_ranks = 0, route_rank = 0;
     uint64_t route_cap = 0;
+    // deferred counting (bc_partition.cu): matched reads append their packed key to `rec`; bc_finish / bc_get_counters
+    // de-duplicate and count the whole buffer partition by partition in shared memory
+    bool deferred = false;
+    ItemBuf rec;                          // the record buffer: slot (cursor + read index) per read, kEmpty = hole
+    unsigned long long* d_rec_n = nullptr;   // device cursor: slots used
+    unsigned long long rec_upper = 0;        // host-side upper bound of the cursor
+    ItemBuf part, w1, w2, tmp;            // scratch: partitioned records, (key, weight) items before / after partitioning,
+                                          // and the output of the first radix level when two are needed
+    uint32_t* d_l1 = nullptr;             // histogram / starts / cursors of the first radix level
+    ItemBuf imp;                          // rows imported from other ranks (bc_import_rows), added before stage B
+    unsigned long long imp_n = 0;
+    uint32_t *d_hist = nullptr, *d_starts = nullptr, *d_cursor = nullptr;
+    unsigned long long part_cap = 0;
+    FlushStats* d_flush = nullptr;
+    unsigned long long dup_applied = 0;   // duplicates already moved from "matched" to "duplicates" by earlier flushes
+    bool flushed_global = false;          // the last flush went through the global-memory tables
     // counting state: map (key -> count) and, with a random barcode, the (key, UMI) set
     Tables tables{};
+    unsigned long long expected_reads = 0;
     unsigned long long entries_upper = 0;  // host-side upper bound of entries added to either table
     unsigned long long imported_rows = 0;  // rows merged in from other ranks (they add keys without bumping "matched")
     unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 2 (then: map entries, set entries)
@@ -217,6 +239,83 @@ int reserve_rows(bc_ctx* ctx, unsigned long long n, bool wide) {
     return BC_OK;
 }
 
+void free_items(ItemBuf& b) {
+    if (b.lo) cudaFree(b.lo);
+    if (b.hi) cudaFree(b.hi);
+    if (b.w) cudaFree(b.w);
+    b = ItemBuf{};
+}
+
+// room for n items; with keep, the first `used` items survive a reallocation
+int reserve_items(bc_ctx* ctx, ItemBuf& b, unsigned long long n, bool wide, bool weighted, unsigned long long used = 0) {
+    if (n <= b.cap && (!wide || b.hi) && (!weighted || b.w)) return BC_OK;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
+    const unsigned long long cap = std::max<unsigned long long>(std::max(n, b.cap) + (used ? n / 2 : n / 16), 1024);
+    ItemBuf nb;
+    nb.cap = cap;
+    CK(ctx, cudaMalloc(&nb.lo, cap * sizeof(unsigned long long)));
+    if (wide) CK(ctx, cudaMalloc(&nb.hi, cap * sizeof(unsigned long long)));
+    if (weighted) CK(ctx, cudaMalloc(&nb.w, cap * sizeof(unsigned long long)));
+    if (used) {
+        CK(ctx, cudaMemcpy(nb.lo, b.lo, used * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+        if (wide && b.hi) CK(ctx, cudaMemcpy(nb.hi, b.hi, used * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+        if (weighted && b.w) CK(ctx, cudaMemcpy(nb.w, b.w, used * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+    }
+    free_items(b);
+    b = nb;
+    return BC_OK;
+}
+
+int reserve_parts(bc_ctx* ctx, unsigned long long n_parts) {
+    if (n_parts + 1 <= ctx->part_cap) return BC_OK;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->d_starts) cudaFree(ctx->d_starts);
+    if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    ctx->d_hist = ctx->d_starts = ctx->d_cursor = nullptr;
+    ctx->part_cap = 0;
+    const unsigned long long cap = n_parts + n_parts / 8 + 1024;
+    CK(ctx, cudaMalloc(&ctx->d_hist, cap * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&ctx->d_starts, cap * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&ctx->d_cursor, cap * sizeof(uint32_t)));
+    ctx->part_cap = cap;
+    return BC_OK;
+}
+
+// Room in the record buffer for `extra` more slots beyond the host-side bound of the cursor.  When the bound (which
+// counts the worst case of routed appends) runs into the capacity, the real cursor is read back before growing.
+int reserve_records(bc_ctx* ctx, unsigned long long extra) {
+    const bool wide = ctx->cfg.wide != 0;
+    if (ctx->rec_upper + extra <= ctx->rec.cap && ctx->rec.lo) {
+        ctx->rec_upper += extra;
+        return BC_OK;
+    }
+    unsigned long long used = 0;
+    if (ctx->rec.lo) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
+        CK(ctx, cudaMemcpy(&used, ctx->d_rec_n, sizeof used, cudaMemcpyDeviceToHost));
+    }
+    ctx->rec_upper = used;
+    if (used + extra > ctx->rec.cap || !ctx->rec.lo) {
+        int rc = reserve_items(ctx, ctx->rec, used + extra, wide, false, used);
+        if (rc != BC_OK) return rc;
+    }
+    ctx->rec_upper += extra;
+    return BC_OK;
+}
+
+// first append of a job: size the buffer for the whole job (bc_create's expected_reads) plus `slack`
+int prime_records(bc_ctx* ctx, unsigned long long slack) {
+    if (ctx->rec.lo) return BC_OK;
+    int rc = reserve_records(ctx, ctx->expected_reads + ctx->expected_reads / 8 + slack);
+    ctx->rec_upper = 0;
+    return rc;
+}
+
+RecOut rec_out(const bc_ctx* ctx) { return RecOut{ctx->rec.lo, ctx->cfg.wide ? ctx->rec.hi : nullptr, ctx->d_rec_n}; }
+
 // Smallest integer sum S with fl32(fl32(S) / fl32(len)) >= min_quality: the reference's f32 mean test
 // (parse.rs:352-355) as an exact integer threshold (Q12).  255*len+1 when no sum passes.
 uint32_t quality_threshold(uint32_t len, float min_quality) {
@@ -323,7 +422,7 @@ int grow_table(bc_ctx* ctx, DevTable& t, unsigned long long need_entries) {
 // keep the load factor of the hash tables <= 0.6 (entries are bounded by the reads submitted so far)
 int ensure_capacity(bc_ctx* ctx, unsigned long long incoming) {
     Tables& T = ctx->tables;
-    if (T.map.kind == 0 && !T.has_set) return BC_OK;
+    if (ctx->deferred || (T.map.kind == 0 && !T.has_set)) return BC_OK;
     ctx->entries_upper += incoming;
     const unsigned long long smallest = std::min(T.map.kind ? T.map.cap : ~0ull, T.has_set ? T.set.cap : ~0ull);
     if (slots_for(ctx->entries_upper) <= smallest) return BC_OK;
@@ -361,6 +460,18 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_row_n) cudaFree(ctx->d_row_n);
     free_table(ctx->tables.map);
     free_table(ctx->tables.set);
+    free_items(ctx->rec);
+    free_items(ctx->part);
+    free_items(ctx->w1);
+    free_items(ctx->w2);
+    free_items(ctx->tmp);
+    if (ctx->d_l1) cudaFree(ctx->d_l1);
+    free_items(ctx->imp);
+    if (ctx->d_rec_n) cudaFree(ctx->d_rec_n);
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->d_starts) cudaFree(ctx->d_starts);
+    if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
     for (Staging& s : ctx->staging) {
         if (s.planes) cudaFree(s.planes);
         if (s.read_len) cudaFree(s.read_len);
@@ -726,13 +837,36 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     // Dense counters (index = key: one fire-and-forget RED per update, no key storage, no probe) whenever the key space
     // is small — or not much larger than the job itself and affordable in HBM (DEL: 3 x 10 bits = 2^30 counters = 8.6 GB)
     bool dense = map_bits <= 27;
-    if (!dense && map_bits <= 31 && (1ull << map_bits) <= 4 * hint) {
-        size_t free_b = 0, total_b = 0;
-        dense = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (sizeof(unsigned long long) << map_bits) <= free_b / 4;
+    // Deferred counting whenever read-by-read updates would be random DRAM traffic: a (key, UMI) set, or a hashed map.
+    // A small dense count array without a random barcode lives in L2 and keeps the inline RED (CRISPR screens).
+    // BC_INLINE_COUNT=1 keeps the read-by-read tables (measurement aid, and what the global-path fallback uses).
+    const char* inline_env = getenv("BC_INLINE_COUNT");
+    ctx->deferred = (T.has_set || !dense) && !(inline_env && inline_env[0] == '1');
+    ctx->expected_reads = hint;
+    CKC(cudaMalloc(&ctx->d_rec_n, sizeof(unsigned long long)));
+    CKC(cudaMemsetAsync(ctx->d_rec_n, 0, sizeof(unsigned long long), ctx->stream));
+    CKC(cudaMalloc(&ctx->d_flush, sizeof(FlushStats)));
+    CKC(cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    if (ctx->deferred) {
+        // tables exist only as descriptors (kind / width) until a flush needs the global path
+        T.map = DevTable{};
+        T.map.kind = 1;
+        T.map.wide = map_bits > 63;
+        T.map.n_entries = ctx->d_counters + BC_N_COUNTERS;
+        T.set = DevTable{};
+        T.set.kind = 2;
+        T.set.wide = d.wide;
+        T.set.n_entries = ctx->d_counters + BC_N_COUNTERS + 1;
+        rc = BC_OK;
+    } else {
+        if (!dense && map_bits <= 31 && (1ull << map_bits) <= 4 * hint) {
+            size_t free_b = 0, total_b = 0;
+            dense = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (sizeof(unsigned long long) << map_bits) <= free_b / 4;
+        }
+        if (dense) rc = alloc_table(ctx, T.map, 0, 0, 1ull << map_bits, ctx->d_counters + BC_N_COUNTERS);
+        else rc = alloc_table(ctx, T.map, 1, map_bits > 63, slots_for(hint), ctx->d_counters + BC_N_COUNTERS);
+        if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, d.wide, slots_for(hint), ctx->d_counters + BC_N_COUNTERS + 1);
     }
-    if (dense) rc = alloc_table(ctx, T.map, 0, 0, 1ull << map_bits, ctx->d_counters + BC_N_COUNTERS);
-    else rc = alloc_table(ctx, T.map, 1, map_bits > 63, slots_for(hint), ctx->d_counters + BC_N_COUNTERS);
-    if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, d.wide, slots_for(hint), ctx->d_counters + BC_N_COUNTERS + 1);
     if (rc != BC_OK) {
         g_create_error = ctx->err;
         bc_destroy(ctx);
@@ -766,7 +900,13 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
         if (rc != BC_OK) return rc;
         ctx->rows_valid = false;
     }
-    if (getenv("BC_DEBUG_NOINSERT")) flags &= ~F_INSERT;  // measurement aid: decode without the table updates
+    if (flags & F_APPEND) {
+        rc = prime_records(ctx, batch->n_reads);
+        if (rc == BC_OK) rc = reserve_records(ctx, batch->n_reads);
+        if (rc != BC_OK) return rc;
+        ctx->rows_valid = false;
+    }
+    if (getenv("BC_DEBUG_NOINSERT")) flags &= ~(F_INSERT | F_APPEND);  // measurement aid: decode without the table updates
     BatchView view{};
     const int staged = stage_batch(ctx, batch, &view);
     if (staged < 0) return staged;
@@ -781,18 +921,19 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, deferred, flags, ctx->stream));
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, rec_out(ctx), deferred, flags, ctx->stream));
     }
     if (!(flags & F_LOCATE_ONLY)) {
         ProfScope p(ctx, BC_K_SCAN);
-        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, deferred, flags, ctx->stream));
+        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, rec_out(ctx), deferred, flags, ctx->stream));
     }
+    if (flags & F_APPEND) CK(ctx, launch_bump(ctx->d_rec_n, batch->n_reads, ctx->stream));
     return release_staging(ctx, staged);
 }
 
 int bc_submit(bc_ctx* ctx, const bc_batch* batch) {
     if (!ctx) return BC_EINVAL;
-    return run_decode(ctx, batch, F_INSERT, DecodeOut{}, RouteOut{}, ctx->d_counters);
+    return run_decode(ctx, batch, ctx->deferred ? F_APPEND : F_INSERT, DecodeOut{}, RouteOut{}, ctx->d_counters);
 }
 
 int bc_sync(bc_ctx* ctx) {
@@ -814,10 +955,212 @@ int bc_wait_copies(bc_ctx* ctx) {
     return BC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- deferred counting
+// The whole record buffer -> final rows (ctx row buffers) and the matched / duplicates split.  A pure function of the
+// buffer (plus the imported rows), so it may run any number of times as more batches arrive.
+static int flush_global(bc_ctx* ctx, unsigned long long n_rec);
+
+static int apply_duplicates(bc_ctx* ctx, unsigned long long dup_now) {
+    // k_decode counted every appended record as "matched"; move the repeats to "duplicates" (parse.rs:65-69)
+    if (dup_now == ctx->dup_applied) return BC_OK;
+    unsigned long long h[BC_N_COUNTERS];
+    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    const long long delta = (long long)dup_now - (long long)ctx->dup_applied;
+    h[BC_CNT_MATCHED] -= delta;
+    h[BC_CNT_DUPLICATES] += delta;
+    CK(ctx, cudaMemcpy(ctx->d_counters, h, sizeof h, cudaMemcpyHostToDevice));
+    ctx->dup_applied = dup_now;
+    return BC_OK;
+}
+
+// Hash-partitions n items (about n_valid of them not holes) into *n_parts pieces of ~reduce_fill items each
+// (ctx->d_starts = their offsets in `out`).  One radix level for up to 2048 partitions, otherwise two (through `tmp`).
+// Returns 1 when the input is too large for two levels (the caller then takes the global-table path).
+static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned long long n, unsigned long long n_valid, bool weighted,
+                           const ItemView& out, bool count_valid, unsigned long long* n_parts) {
+    unsigned long long P = (n_valid + reduce_fill(wide) - 1) / reduce_fill(wide);
+    if (P < 1) P = 1;
+    const uint32_t mb = split_max_bits();
+    uint32_t l2 = 0;
+    unsigned long long F1 = P;
+    if (P > (1ull << mb)) {
+        uint32_t lg = 0;
+        while ((1ull << lg) < P) lg++;
+        l2 = (lg + 1) / 2;
+        F1 = (P + (1ull << l2) - 1) >> l2;
+        P = F1 << l2;
+        if (l2 > mb || F1 > (1ull << mb)) return 1;
+    }
+    *n_parts = P;
+    int rc = reserve_parts(ctx, P);
+    if (rc != BC_OK) return rc;
+    ProfScope p(ctx, BC_K_FINISH);
+    CK(ctx, cudaMemsetAsync(ctx->d_hist, 0, (P + 1) * sizeof(uint32_t), ctx->stream));
+    if (l2 == 0) {
+        const SplitLevel lv{P, 0u, 0xFFFFFFFFu, (uint32_t)P};
+        CK(ctx, launch_split(false, wide, in, out, nullptr, 1, n, lv, ctx->d_hist, ctx->d_flush, count_valid, ctx->stream));
+        CK(ctx, launch_seg_scan(ctx->d_hist, 1, (uint32_t)P, nullptr, ctx->d_starts, ctx->d_cursor, ctx->stream));
+        CK(ctx, launch_split(true, wide, in, out, nullptr, 1, n, lv, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
+        return BC_OK;
+    }
+    rc = reserve_items(ctx, ctx->tmp, n, wide, weighted);
+    if (rc != BC_OK) return rc;
+    if (!ctx->d_l1) CK(ctx, cudaMalloc(&ctx->d_l1, 3 * ((1u << mb) + 1) * sizeof(uint32_t)));
+    uint32_t *hist1 = ctx->d_l1, *starts1 = hist1 + (1u << mb) + 1, *cursor1 = starts1 + (1u << mb) + 1;
+    const ItemView tmp{ctx->tmp.lo, wide ? ctx->tmp.hi : nullptr, weighted ? ctx->tmp.w : nullptr};
+    const SplitLevel lv1{P, l2, 0xFFFFFFFFu, (uint32_t)F1}, lv2{P, 0u, (1u << l2) - 1u, 1u << l2};
+    CK(ctx, cudaMemsetAsync(hist1, 0, (F1 + 1) * sizeof(uint32_t), ctx->stream));
+    CK(ctx, launch_split(false, wide, in, tmp, nullptr, 1, n, lv1, hist1, ctx->d_flush, count_valid, ctx->stream));
+    CK(ctx, launch_seg_scan(hist1, 1, (uint32_t)F1, nullptr, starts1, cursor1, ctx->stream));
+    CK(ctx, launch_split(true, wide, in, tmp, nullptr, 1, n, lv1, cursor1, ctx->d_flush, false, ctx->stream));
+    CK(ctx, launch_split(false, wide, tmp, out, starts1, (uint32_t)F1, n, lv2, ctx->d_hist, ctx->d_flush, false, ctx->stream));
+    CK(ctx, launch_seg_scan(ctx->d_hist, (uint32_t)F1, 1u << l2, starts1, ctx->d_starts, ctx->d_cursor, ctx->stream));
+    CK(ctx, launch_split(true, wide, tmp, out, starts1, (uint32_t)F1, n, lv2, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
+    return BC_OK;
+}
+
+static int flush_records(bc_ctx* ctx) {
+    if (ctx->rows_valid) return BC_OK;
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    drop_rows(ctx);
+    unsigned long long n_rec = 0;
+    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
+    ctx->rec_upper = n_rec;
+    ctx->flushed_global = false;
+    const bool has_umi = ctx->cfg.has_umi != 0;
+    const bool wide_in = ctx->cfg.wide != 0, wide_out = ctx->tables.map.wide != 0;
+    FlushStats st{};
+    CK(ctx, cudaMemcpy(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost));
+    if (st.overflow) return fail(ctx, BC_ESTATE, "record buffer overflow while appending routed records (code %llu)", st.overflow);
+    if (n_rec + ctx->imp_n == 0) {
+        ctx->rows_valid = true;
+        return apply_duplicates(ctx, 0);
+    }
+    // records that are not holes = reads counted "matched" so far (the repeats already moved to "duplicates" included)
+    unsigned long long n_valid = n_rec;
+    {
+        unsigned long long h[BC_N_COUNTERS];
+        CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+        n_valid = std::min(n_rec, h[BC_CNT_MATCHED] + h[BC_CNT_DUPLICATES]);
+    }
+    const char* force = getenv("BC_FLUSH_GLOBAL");
+    if ((force && force[0] == '1') || n_rec + ctx->imp_n >= 0xFFFFFFF0ULL) return flush_global(ctx, n_rec);
+
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    // ---- stage A: records -> (key, pairs) items in w1
+    rc = reserve_items(ctx, ctx->w1, n_rec + ctx->imp_n, wide_out, true);
+    if (rc != BC_OK) return rc;
+    if (n_rec) {
+        if (has_umi) {
+            unsigned long long n_parts = 0;
+            rc = reserve_items(ctx, ctx->part, n_rec, wide_in, false);
+            if (rc == BC_OK)
+                rc = partition_items(ctx, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, wide_in, n_rec, n_valid, false,
+                                     ItemView{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr}, true, &n_parts);
+            if (rc == 1) return flush_global(ctx, n_rec);
+            if (rc != BC_OK) return rc;
+            ProfScope p(ctx, BC_K_FINISH);
+            CK(ctx, launch_reduce(RED_DEDUPE, wide_in, ItemView{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr}, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
+                                  ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w}, ctx->w1.cap, ctx->d_flush, ctx->stream));
+        } else {
+            const uint32_t chunk = reduce_chunk(wide_in);
+            ProfScope p(ctx, BC_K_FINISH);
+            CK(ctx, launch_reduce(RED_COUNT, wide_in, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, nullptr, n_rec,
+                                  (n_rec + chunk - 1) / chunk, chunk, 0, ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w},
+                                  ctx->w1.cap, ctx->d_flush, ctx->stream));
+        }
+    }
+    CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (st.overflow) {
+        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+        return flush_global(ctx, n_rec);
+    }
+    unsigned long long n1 = st.n_out;
+    const unsigned long long dup_now = has_umi ? st.valid - st.unique : 0;
+    if (ctx->imp_n) {  // rows of other ranks join as (key, count) items
+        CK(ctx, cudaMemcpyAsync(ctx->w1.lo + n1, ctx->imp.lo, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (wide_out) CK(ctx, cudaMemcpyAsync(ctx->w1.hi + n1, ctx->imp.hi, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(ctx->w1.w + n1, ctx->imp.w, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        n1 += ctx->imp_n;
+    }
+    // ---- stage B: items partitioned by key, summed per key -> rows
+    if (n1) {
+        unsigned long long n_parts = 0;
+        rc = reserve_items(ctx, ctx->w2, n1, wide_out, true);
+        if (rc == BC_OK) rc = reserve_rows(ctx, n1, wide_out);
+        if (rc != BC_OK) return rc;
+        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+        rc = partition_items(ctx, ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w}, wide_out, n1, n1, true,
+                             ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, false, &n_parts);
+        if (rc == 1) return flush_global(ctx, n_rec);
+        if (rc != BC_OK) return rc;
+        {
+            ProfScope p(ctx, BC_K_FINISH);
+            CK(ctx, launch_reduce(RED_COUNT, wide_out, ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, ctx->d_starts, n1,
+                                  n_parts, 0, 0, ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
+                                  ctx->d_flush, ctx->stream));
+        }
+        CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+        if (st.overflow) return flush_global(ctx, n_rec);
+        ctx->n_rows = st.n_out;
+    }
+    ctx->rows_valid = true;
+    return apply_duplicates(ctx, dup_now);
+}
+
+// Fallback: the record buffer through the global-memory set / map of bc_device.cuh (random DRAM accesses).
+static int flush_global(bc_ctx* ctx, unsigned long long n_rec) {
+    Tables& T = ctx->tables;
+    const bool wide_in = ctx->cfg.wide != 0, wide_out = T.map.wide != 0;
+    drop_rows(ctx);
+    ctx->flushed_global = true;
+    free_table(T.map);
+    free_table(T.set);
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + BC_N_COUNTERS, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    int rc = alloc_table(ctx, T.map, 1, wide_out, slots_for(n_rec + ctx->imp_n), ctx->d_counters + BC_N_COUNTERS);
+    if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, wide_in, slots_for(n_rec), ctx->d_counters + BC_N_COUNTERS + 1);
+    if (rc != BC_OK) return rc;
+    {
+        ProfScope p(ctx, BC_K_FINISH);
+        CK(ctx, launch_insert_items(T, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, wide_in, n_rec, ctx->d_flush, ctx->stream));
+        if (ctx->imp_n)
+            CK(ctx, launch_insert(T, ctx->imp.lo, wide_out ? ctx->imp.hi : nullptr, nullptr, ctx->imp.w, ctx->imp_n, nullptr, ctx->stream));
+    }
+    FlushStats st{};
+    unsigned long long keys = 0;
+    CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(&keys, ctx->d_counters + BC_N_COUNTERS, sizeof keys, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = reserve_rows(ctx, keys, wide_out);
+    if (rc != BC_OK) return rc;
+    CK(ctx, cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_FINISH);
+        CK(ctx, launch_compact(T.map, ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt, ctx->d_row_n, ctx->stream));
+    }
+    CK(ctx, cudaMemcpyAsync(&ctx->n_rows, ctx->d_row_n, sizeof ctx->n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    free_table(T.map);
+    free_table(T.set);
+    ctx->rows_valid = true;
+    return apply_duplicates(ctx, T.has_set ? st.valid - st.unique : 0);
+}
+
 int bc_get_counters(bc_ctx* ctx, uint64_t out[BC_N_COUNTERS]) {
     if (!ctx || !out) return BC_EINVAL;
     int rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
+    if (ctx->deferred) {  // the matched / duplicates split is known once the records are de-duplicated
+        CK(ctx, cudaSetDevice(ctx->device));
+        rc = flush_records(ctx);
+        if (rc != BC_OK) return rc;
+    }
     unsigned long long h[BC_N_COUNTERS];
     CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
     ctx->prof.d2h_bytes += sizeof h;
@@ -924,6 +1267,7 @@ static int rows_to_host(bc_ctx* ctx, const unsigned long long* lo, const unsigne
 // the map's occupied entries -> ctx row buffers (device)
 static int build_rows(bc_ctx* ctx) {
     if (ctx->rows_valid) return BC_OK;
+    if (ctx->deferred) return flush_records(ctx);
     int rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     drop_rows(ctx);
@@ -1211,7 +1555,14 @@ int bc_route_insert(bc_ctx* ctx, uint32_t parity, const uint32_t* dev_counts_fro
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->insert_done_ev, 0));
         ctx->insert_pending = false;
     }
-    int rc = ensure_capacity(ctx, expected_records);  // may rehash on the main stream: the insert stream is idle here
+    int rc;
+    if (ctx->deferred) {  // worst case of one round: every source fills its region
+        const unsigned long long worst = (unsigned long long)ctx->route_ranks * ctx->route_cap;
+        rc = prime_records(ctx, 2 * worst);
+        if (rc == BC_OK) rc = reserve_records(ctx, worst);
+    } else {
+        rc = ensure_capacity(ctx, expected_records);  // may rehash on the main stream: the insert stream is idle here
+    }
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
     // inserts go to their own (high-priority) stream once the exchange of counts, i.e. everything queued on the main
@@ -1219,6 +1570,11 @@ int bc_route_insert(bc_ctx* ctx, uint32_t parity, const uint32_t* dev_counts_fro
     CK(ctx, cudaEventRecord(ctx->routed_ev, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(ctx->insert_stream, ctx->routed_ev, 0));
     ctx->prof.launches[BC_K_INSERT]++;
+    if (ctx->deferred)  // the owner only keeps what arrived; de-duplication happens once, at the flush
+        CK(ctx, launch_append_segments(ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap, dev_counts_from,
+                                       count_stride, ctx->route_ranks, rec_out(ctx), ctx->rec.cap, ctx->d_rec_n, ctx->d_counters,
+                                       ctx->d_flush, ctx->insert_stream));
+    else
     CK(ctx, launch_insert_segments(ctx->tables, ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap,
                                    dev_counts_from, count_stride, ctx->route_ranks, ctx->d_counters, ctx->insert_stream));
     CK(ctx, cudaEventRecord(ctx->insert_done_ev, ctx->insert_stream));
@@ -1230,6 +1586,15 @@ int bc_insert_records(bc_ctx* ctx, const bc_record* dev_records, uint64_t n) {
     if (!ctx || (!dev_records && n)) return BC_EINVAL;
     if (n == 0) return BC_OK;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->deferred) {
+        int rc = reserve_records(ctx, n);
+        if (rc != BC_OK) return rc;
+        ctx->rows_valid = false;
+        ProfScope p(ctx, BC_K_INSERT);
+        CK(ctx, launch_append_records(reinterpret_cast<const Key*>(dev_records), n, rec_out(ctx), ctx->d_counters, ctx->stream));
+        CK(ctx, launch_bump(ctx->d_rec_n, n, ctx->stream));
+        return BC_OK;
+    }
     int rc = ensure_capacity(ctx, n);
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
@@ -1257,6 +1622,19 @@ int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_
     if (ctx->cfg.has_umi) return fail(ctx, BC_ESTATE, "bc_import_rows: scheme has a random barcode; route records instead");
     if (n_rows == 0) return BC_OK;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->deferred) {  // kept aside; the next flush sums them with this rank's own (key, count) items
+        const bool wide = ctx->tables.map.wide != 0;
+        if (wide && !dev_key_hi) return fail(ctx, BC_EINVAL, "bc_import_rows: keys wider than 63 bits need dev_key_hi");
+        int rc = reserve_items(ctx, ctx->imp, ctx->imp_n + n_rows, wide, true, ctx->imp_n);
+        if (rc != BC_OK) return rc;
+        CK(ctx, cudaMemcpyAsync(ctx->imp.lo + ctx->imp_n, dev_key_lo, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (wide) CK(ctx, cudaMemcpyAsync(ctx->imp.hi + ctx->imp_n, dev_key_hi, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(ctx->imp.w + ctx->imp_n, dev_count, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->imp_n += n_rows;
+        ctx->imported_rows += n_rows;
+        ctx->rows_valid = false;
+        return BC_OK;
+    }
     int rc = ensure_capacity(ctx, n_rows);
     if (rc != BC_OK) return rc;
     ctx->rows_valid = false;
@@ -1272,7 +1650,7 @@ int bc_dense_counts(bc_ctx* ctx, uint64_t** dev_counts, uint64_t* n) {
     if (!ctx || !dev_counts || !n) return BC_EINVAL;
     *dev_counts = nullptr;
     *n = 0;
-    if (ctx->tables.map.kind != 0 || ctx->tables.has_set) return BC_OK;  // not a dense, UMI-free table: merge rows instead
+    if (ctx->deferred || ctx->tables.map.kind != 0 || ctx->tables.has_set) return BC_OK;  // not a dense, UMI-free table: merge rows instead
     *dev_counts = reinterpret_cast<uint64_t*>(ctx->tables.map.data);
     *n = ctx->tables.map.cap;
     ctx->imported_rows = ctx->tables.map.cap;  // the caller is about to add other ranks' counts in place
@@ -1299,6 +1677,11 @@ int bc_reset(bc_ctx* ctx) {
     CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 2) * sizeof(unsigned long long), ctx->stream));
     rc = clear_table(ctx, ctx->tables.map);
     if (rc == BC_OK && ctx->tables.has_set) rc = clear_table(ctx, ctx->tables.set);
+    CK(ctx, cudaMemsetAsync(ctx->d_rec_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    ctx->rec_upper = 0;
+    ctx->imp_n = 0;
+    ctx->dup_applied = 0;
     ctx->entries_upper = 0;
     ctx->imported_rows = 0;
     return rc;  // asynchronous: later work on the ctx stream is ordered after the clears
@@ -1324,6 +1707,8 @@ int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
     ctx->prof.key_bits = ctx->cfg.key_bits;
     ctx->prof.wide_keys = ctx->cfg.wide;
     ctx->prof.dense_table = ctx->tables.map.kind == 0;
+    ctx->prof.deferred_count = ctx->deferred ? 1u : 0u;
+    ctx->prof.flushed_global = ctx->flushed_global ? 1u : 0u;
     *out = ctx->prof;
     return BC_OK;
 }

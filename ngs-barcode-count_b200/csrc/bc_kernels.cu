@@ -304,9 +304,15 @@ __device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBi
 }
 
 // K3 for one matched read: count it (info.rs:735-808) or, multi-GPU with a random barcode, hand it to its owner rank
-__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& tables, const RouteOut& route, int flags,
-                                              Key key, bool* new_key, bool* new_pair) {
+__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& tables, const RouteOut& route, const RecOut& rec,
+                                              unsigned long long read_index, int flags, Key key, bool* new_key, bool* new_pair) {
     if (flags & F_INSERT) return count_read(tables, key, new_key, new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
+    if (flags & F_APPEND) {  // deferred counting: the record slot of this read (k_decode left it empty)
+        const unsigned long long pos = *rec.cursor + read_index;
+        rec.lo[pos] = key.lo;
+        if (rec.hi) rec.hi[pos] = key.hi;
+        return BC_ST_MATCHED;
+    }
     if (flags & F_ROUTE) {
         const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
         const uint32_t slot = atomicAdd(&route.counts[owner * route.count_stride], 1u);
@@ -325,7 +331,8 @@ template <int TW>
 __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg cfg, const BatchView batch,
                                                   const DevAux aux, const Tables tables,
                                                   unsigned long long* __restrict__ counters, const DecodeOut out,
-                                                  const RouteOut route, const Deferred deferred, const int flags) {
+                                                  const RouteOut route, const RecOut rec, const Deferred deferred,
+                                                  const int flags) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned int s_cnt[BC_N_COUNTERS + 2];
@@ -457,6 +464,14 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     else if (flags & F_ROUTE) status = kRouted;  // appended to its owner's bucket below, warp-aggregated
                 }
             }
+        }
+        if (flags & F_APPEND) {
+            // deferred counting: every read owns one record slot; unmatched reads (and reads handed to k_resolve, which
+            // fills the slot itself when the read matches) leave a hole.  Consecutive lanes, consecutive slots.
+            const unsigned long long pos = *rec.cursor + base + tid;
+            const bool m = status == BC_ST_MATCHED;
+            rec.lo[pos] = m ? key.lo : kEmpty;
+            if (rec.hi) rec.hi[pos] = m ? key.hi : kEmpty;
         }
         if (status != kDeferred && (flags & F_EMIT)) {
             const unsigned long long i = base + tid;
@@ -632,8 +647,8 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
 
 __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg cfg, const BatchView batch, const DevAux aux,
                                                  const Tables tables, unsigned long long* __restrict__ counters,
-                                                 const DecodeOut out, const RouteOut route, const Deferred deferred,
-                                                 const int flags) {
+                                                 const DecodeOut out, const RouteOut route, const RecOut rec,
+                                                 const Deferred deferred, const int flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = *deferred.count;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -678,7 +693,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
         }
         if (lane == 0) {
             bool new_key = false, new_pair = false;
-            if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, flags, key, &new_key, &new_pair);
+            if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, rec, ri, flags, key, &new_key, &new_pair);
             c_matched += status == BC_ST_MATCHED;
             c_dup += status == BC_ST_DUPLICATE;
             c_sample += status == BC_ST_SAMPLE;
@@ -711,7 +726,7 @@ size_t decode_smem_bytes(const BatchView& b) {
 template <int TW>
 static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                                     unsigned long long* counters, const DecodeOut& out, const RouteOut& route,
-                                    const Deferred& deferred, int flags, cudaStream_t stream) {
+                                    const RecOut& rec, const Deferred& deferred, int flags, cudaStream_t stream) {
     const size_t smem = decode_smem_bytes(batch);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -720,37 +735,37 @@ static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, c
         configured = smem;
     }
     const unsigned grid = (batch.n_reads + kTile - 1) / kTile;
-    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, tables, counters, out, route, deferred, flags);
+    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
-                          int flags, cudaStream_t stream) {
+                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
+                          const Deferred& deferred, int flags, cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     switch (cfg.TW) {
-        case 1: return launch_decode_tw<1>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 2: return launch_decode_tw<2>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 3: return launch_decode_tw<3>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 4: return launch_decode_tw<4>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 5: return launch_decode_tw<5>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 6: return launch_decode_tw<6>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 7: return launch_decode_tw<7>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
-        case 8: return launch_decode_tw<8>(cfg, batch, aux, tables, counters, out, route, deferred, flags, stream);
+        case 1: return launch_decode_tw<1>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 2: return launch_decode_tw<2>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 3: return launch_decode_tw<3>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 4: return launch_decode_tw<4>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 5: return launch_decode_tw<5>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 6: return launch_decode_tw<6>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 7: return launch_decode_tw<7>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 8: return launch_decode_tw<8>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // deferred reads of the batch just decoded (their number is read on the device: no host round trip)
 cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
-                           int flags, cudaStream_t stream) {
+                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
+                           const Deferred& deferred, int flags, cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     unsigned long long warps = batch.n_reads;  // at most one warp per read of the batch
     unsigned grid = (unsigned)((warps + 3) / 4);
     const unsigned cap = 148u * 16u;  // persistent warps stride over the list
     if (grid > cap) grid = cap;
-    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, tables, counters, out, route, deferred, flags);
+    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags);
     return cudaGetLastError();
 }
 

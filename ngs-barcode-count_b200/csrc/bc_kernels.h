@@ -42,15 +42,24 @@ struct Deferred {  // reads whose barcode step needs a search: {read index, offs
     uint32_t* count;
 };
 
-enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8 };
+// Deferred counting (bc_partition.cu): instead of updating the tables read by read, a matched read's packed key goes
+// to slot (*cursor + read index) of a flat record buffer — kEmpty marks the reads that did not match — and the whole
+// job is de-duplicated and counted at flush time, partition by partition, in shared memory.
+struct RecOut {
+    unsigned long long* lo;
+    unsigned long long* hi;                // nullptr when the full key (random barcode included) fits 63 bits
+    const unsigned long long* cursor;      // records appended before this batch (bumped by launch_bump after the batch)
+};
+
+enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8, F_APPEND = 16 };
 
 // counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
-                          int flags, cudaStream_t stream);
+                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
+                          const Deferred& deferred, int flags, cudaStream_t stream);
 cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const Deferred& deferred,
-                           int flags, cudaStream_t stream);
+                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
+                           const Deferred& deferred, int flags, cudaStream_t stream);
 
 // fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
 cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint32_t* table, cudaStream_t stream);
@@ -83,5 +92,56 @@ cudaError_t launch_insert_segments(const Tables& tables, const Key* records, uns
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);
 
 size_t decode_smem_bytes(const BatchView& batch);
+
+// ---- deferred partitioned counting (bc_partition.cu) ---------------------------------------------------------------
+// Items are structure-of-arrays (lo, hi, w): hi == nullptr for keys of at most 63 bits, w == nullptr for weight 1.
+// An item whose key is kEmpty (narrow: lo, wide: hi) is a hole and is skipped everywhere.
+struct ItemView {
+    unsigned long long* lo;
+    unsigned long long* hi;
+    unsigned long long* w;
+};
+struct FlushStats {  // device-side results of one flush (u64 each)
+    unsigned long long n_out;     // items written by the reduce kernel in flight (weighted keys, or final rows)
+    unsigned long long overflow;  // != 0: a partition held more distinct keys than the shared-memory table -> global path
+    unsigned long long valid;     // records that were not holes
+    unsigned long long unique;    // distinct (key, random barcode) pairs
+};
+enum ReduceMode { RED_DEDUPE = 0, RED_COUNT = 1 };
+uint32_t reduce_fill(bool wide);   // target items per hashed partition
+uint32_t reduce_chunk(bool wide);  // items per fixed chunk (pre-aggregation of schemes without a random barcode)
+
+cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cudaStream_t stream);
+// per segment s of bins_per_seg bins: starts = seg_base[s] (0 when nullptr) + exclusive prefix of the segment's histogram,
+// cursor = copy of starts; starts[n_seg * bins_per_seg] = grand total
+cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,
+                            uint32_t* cursor, cudaStream_t stream);
+// One radix level of the hash partitioning: partition p of an item = mulhi(hash(key), P); the level's bin is
+// (p >> shift) & mask, F bins.  seg_starts == nullptr: one segment [0, n_total); else n_seg segments, each split on its
+// own (bins of segment s at bins + s * F).  scatter = false adds to the histogram `bins`; scatter = true moves the
+// items to out, `bins` being the cursors (initialised with the exclusive prefix of the histogram).
+struct SplitLevel {
+    unsigned long long P;
+    uint32_t shift, mask, F;
+};
+cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t n_seg,
+                         unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, FlushStats* stats, bool count_valid,
+                         cudaStream_t stream);
+uint32_t split_max_bits();
+// One CTA per partition [starts[p], starts[p+1]) — or, with starts == nullptr, per fixed chunk of `chunk` items.
+//   RED_DEDUPE: distinct records of the partition, then their keys (record >> umi_bits) combined: out = (key, pairs)
+//   RED_COUNT : out = (key, sum of weights)
+cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
+                          unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
+                          unsigned long long out_cap, FlushStats* stats, cudaStream_t stream);
+// routed records received from every rank appended to the record buffer at *cursor (then the cursor is bumped)
+cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,
+                                   uint32_t n_segments, const RecOut& rec, unsigned long long rec_cap, unsigned long long* cursor,
+                                   unsigned long long* counters, FlushStats* stats, cudaStream_t stream);
+cudaError_t launch_append_records(const Key* records, unsigned long long n, const RecOut& rec, unsigned long long* counters,
+                                  cudaStream_t stream);
+// global-table path over the record buffer (oversized partitions, forced by BC_FLUSH_GLOBAL): counts like k_insert
+cudaError_t launch_insert_items(const Tables& tables, const ItemView& in, bool wide, unsigned long long n, FlushStats* stats,
+                                cudaStream_t stream);
 
 }  // namespace bc

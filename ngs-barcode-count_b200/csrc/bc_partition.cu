@@ -1,0 +1,684 @@
+// bc_partition.cu — deferred, partitioned counting: the K3 step (info.rs:735-808) done once per job instead of read
+// by read.
+//
+// Updating a (key, UMI) set and a key -> count map of several GB read by read costs two random DRAM sectors per matched
+// read (with their read-modify-write at the memory controller ~190 B of traffic for an 8-byte record): on the DEL
+// workload that was 40 % of k_decode.  Here k_decode only stores the packed key of every matched read into a flat
+// record buffer (8 or 16 bytes per read, coalesced), and the flush
+//   stage A  hash-partitions the records by (key, UMI) into pieces that fit a shared-memory table, one CTA per piece
+//            drops the repeats (info.rs:780-791: only the first insert of a pair counts) and combines the pairs of
+//            one key into (key, pairs) items;
+//   stage B  hash-partitions those items by key and sums them per key in shared memory: the final (key, count) rows
+//            (output.rs:265-270).
+// Schemes without a random barcode skip the partitioning of stage A: contiguous chunks of records are pre-aggregated
+// into (key, reads) items.  Combining before stage B also bounds the work a hot key (Zipf-distributed lineage
+// barcodes) puts on the one CTA that owns it.  Every pass streams its input once with full-width transactions; the
+// random accesses stay in shared memory.  A partition that holds more distinct keys than the table (cannot happen
+// with uniform hashing: the fill target is 30 standard deviations below the capacity) raises `overflow` and the host
+// falls back to the global-memory tables of bc_device.cuh.
+#include "../../include/bc_b200.h"
+#include "bc_kernels.h"
+
+namespace bc {
+
+namespace {
+
+constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
+constexpr int kRedThreads = 256;
+constexpr uint32_t kTableSlots = 4096;  // u32 slots holding key-store indices
+constexpr uint32_t kKeyCap = 2048;      // distinct keys a CTA can hold (narrow 48 KB, wide 64 KB of shared memory: 4 / 3 CTAs per SM)
+constexpr int kRedLoads = kKeyCap / kRedThreads;  // items per thread of a partition that fits the key store
+
+constexpr int kSplitThreads = 512;      // histogram kernel
+constexpr int kScatterThreads = 256;    // scatter kernel: ~80 registers per thread, three CTAs per SM to overlap its phases
+constexpr uint32_t kSplitMaxBits = 11;    // bins per level <= 2048 (shared-memory histogram)
+
+__device__ __forceinline__ bool item_valid(unsigned long long lo, unsigned long long hi, bool wide) {
+    return wide ? hi != kEmpty : lo != kEmpty;
+}
+
+__global__ void k_bump(unsigned long long* cursor, unsigned long long add) { *cursor += add; }
+
+// One CTA per segment of F bins: starts[s * F + b] = seg_base[s] + exclusive prefix of the segment's histogram
+// (seg_base == nullptr: a single segment starting at 0), cursor = copy, starts[n_seg * F] = grand total.
+__global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ hist, const uint32_t F, const uint32_t* __restrict__ seg_base,
+                                                  uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t s_warp[16];
+    __shared__ uint32_t s_carry;
+    const uint32_t seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long off = (unsigned long long)seg * F;
+    if (tid == 0) s_carry = seg_base ? seg_base[seg] : 0u;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < F; b0 += 512) {
+        const uint32_t b = b0 + tid;
+        const uint32_t v = b < F ? hist[off + b] : 0u;
+        uint32_t x = v;  // inclusive warp scan
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        uint32_t before = s_carry;
+        for (uint32_t w = 0; w < wid; w++) before += s_warp[w];
+        if (b < F) {
+            starts[off + b] = before + x - v;
+            cursor[off + b] = before + x - v;
+        }
+        __syncthreads();
+        if (tid == 511) s_carry = before + x;
+        __syncthreads();
+    }
+    if (seg == gridDim.x - 1 && tid == 0) starts[off + F] = s_carry;
+}
+
+// ---- hash partitioning, one radix level per launch --------------------------------------------------------------
+// The partition of an item is p = mulhi(hash(key), P).  With more than 2048 partitions P = F1 * 2^l2: level 1 splits
+// the whole input into F1 segments (digit p >> l2), level 2 splits every segment into 2^l2 partitions (digit
+// p & (2^l2 - 1)); a level's digit is (p >> shift) & mask.
+// The scatter kernel takes a tile of kSplitThreads * IPT consecutive items of one segment into registers (all loads
+// of a thread in flight at once) and
+//   1  counts the tile per bin in shared memory, turns the counts into offsets of a bin-sorted copy of the tile and
+//      reserves one output run per non-empty bin with a single global atomic;
+//   2  puts every item, with its output position, at its place in the sorted copy (shared memory);
+//   3  writes the copy out: consecutive lanes hold consecutive items of a run, so the stores leave the SM as full
+//      32-byte sectors.
+// Versions measured and dropped: one global atomic per item (55 G atomics/s, ten times below the streaming rate of
+// the same data); per-item stores straight to the output (partial-sector writes: the L2 reads each sector before
+// merging 8 bytes into it — 2x the DRAM reads, 60 G stores/s); re-reading the tile from L2 for every sweep instead of
+// keeping it in registers (latency-bound at 25-50 % occupancy: 280-550 us for 33 M items).
+__device__ __forceinline__ uint32_t split_digit(unsigned long long lo, unsigned long long hi, const SplitLevel& lv) {
+    const uint32_t p = (uint32_t)__umul64hi(hash_key(Key{lo, hi}), lv.P);
+    return (p >> lv.shift) & lv.mask;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kSplitThreads) k_split_hist(const ItemView in, const uint32_t* __restrict__ seg_starts,
+                                                              const uint32_t workers, const unsigned long long n_total,
+                                                              const SplitLevel lv, uint32_t* __restrict__ bins, FlushStats* stats,
+                                                              const bool count_valid) {
+    __shared__ uint32_t s_hist[1u << kSplitMaxBits];
+    __shared__ unsigned long long s_valid;
+    constexpr int U = 4;
+    const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
+    const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
+    const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
+    uint32_t* my_bins = bins + (unsigned long long)seg * lv.F;
+    const uint32_t tid = threadIdx.x;
+    unsigned long long valid = 0;
+    if (tid == 0) s_valid = 0;
+    for (uint32_t b = tid; b < lv.F; b += kSplitThreads) s_hist[b] = 0;
+    __syncthreads();
+    const unsigned long long span = (unsigned long long)U * kSplitThreads;
+    for (unsigned long long t0 = a + worker * span; t0 < e; t0 += workers * span) {
+        unsigned long long lo[U], hi[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const unsigned long long i = t0 + (unsigned long long)k * kSplitThreads + tid;
+            lo[k] = i < e ? in.lo[i] : kEmpty;
+            hi[k] = WIDE ? (i < e ? in.hi[i] : kEmpty) : 0ULL;
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            if (!item_valid(lo[k], hi[k], WIDE)) continue;
+            valid++;
+            atomicAdd(&s_hist[split_digit(lo[k], hi[k], lv)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = tid; b < lv.F; b += kSplitThreads) {
+        const uint32_t c = s_hist[b];
+        if (c) atomicAdd(&my_bins[b], c);
+    }
+    if (count_valid) {
+        for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, o);
+        if ((tid & 31) == 0 && valid) atomicAdd(&s_valid, valid);
+        __syncthreads();
+        if (tid == 0 && s_valid) atomicAdd(&stats->valid, s_valid);
+    }
+}
+
+template <bool WIDE, bool WEIGHTED, int IPT>
+__global__ void __launch_bounds__(kScatterThreads) k_split_scatter(const ItemView in, const ItemView out, const uint32_t* __restrict__ seg_starts,
+                                                                 const uint32_t workers, const unsigned long long n_total,
+                                                                 const SplitLevel lv, uint32_t* __restrict__ bins) {
+    constexpr uint32_t T = kScatterThreads * IPT;
+    extern __shared__ __align__(16) unsigned long long split_stage[];  // [lo | hi | w] x T u64, then T u32 positions
+    __shared__ uint32_t s_hist[1u << kSplitMaxBits], s_delta[1u << kSplitMaxBits];
+    __shared__ uint32_t s_warp[kScatterThreads / 32];
+    const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
+    const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
+    const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
+    const uint32_t F = lv.F;
+    uint32_t* my_bins = bins + (unsigned long long)seg * F;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned long long* st_lo = split_stage;
+    unsigned long long* st_hi = st_lo + (WIDE ? T : 0);
+    unsigned long long* st_w = st_hi + (WEIGHTED ? T : 0);
+    uint32_t* st_pos = reinterpret_cast<uint32_t*>(st_w + T);
+    for (unsigned long long t0 = a + (unsigned long long)worker * T; t0 < e; t0 += (unsigned long long)workers * T) {
+        unsigned long long lo[IPT], hi[IPT], w[IPT];
+        uint32_t bin[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const unsigned long long i = t0 + (unsigned long long)k * kScatterThreads + tid;
+            lo[k] = i < e ? in.lo[i] : kEmpty;
+            hi[k] = WIDE ? (i < e ? in.hi[i] : kEmpty) : 0ULL;
+            w[k] = WEIGHTED ? (i < e ? in.w[i] : 0ULL) : 0ULL;
+        }
+        for (uint32_t b = tid; b < F; b += kScatterThreads) s_hist[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            bin[k] = kEmpty32;
+            if (!item_valid(lo[k], hi[k], WIDE)) continue;
+            bin[k] = split_digit(lo[k], hi[k], lv);
+            atomicAdd(&s_hist[bin[k]], 1u);
+        }
+        __syncthreads();
+        // exclusive prefix of the tile's histogram (thread t owns bins [t * per, t * per + per)); run reservation
+        const uint32_t per = (F + kScatterThreads - 1) / kScatterThreads;  // <= 8
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t b = tid * per + k;
+            c[k] = (k < (int)per && b < F) ? s_hist[b] : 0u;
+            sum += c[k];
+        }
+        uint32_t x = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        uint32_t off = x - sum, n_tile = 0;
+        for (uint32_t ww = 0; ww < kScatterThreads / 32; ww++) {
+            if (ww < wid) off += s_warp[ww];
+            n_tile += s_warp[ww];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t b = tid * per + k;
+            if (k < (int)per && b < F) {
+                const uint32_t g = c[k] ? atomicAdd(&my_bins[b], c[k]) : 0u;
+                s_delta[b] = g - off;  // output position = s_delta[bin] + position in the sorted tile
+                s_hist[b] = off;       // becomes the bin's cursor inside the sorted tile
+                off += c[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            if (bin[k] == kEmpty32) continue;
+            const uint32_t at = atomicAdd(&s_hist[bin[k]], 1u);
+            st_lo[at] = lo[k];
+            if (WIDE) st_hi[at] = hi[k];
+            if (WEIGHTED) st_w[at] = w[k];
+            st_pos[at] = s_delta[bin[k]] + at;
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < n_tile; j += kScatterThreads) {
+            const uint32_t pos = st_pos[j];
+            out.lo[pos] = st_lo[j];
+            if (WIDE) out.hi[pos] = st_hi[j];
+            if (WEIGHTED) out.w[pos] = st_w[j];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- the shared-memory table -----------------------------------------------------------------------------------
+// table[] holds indices into a key store (klo/khi/kcnt); an index is published with a 32-bit CAS on the table slot
+// only after the key behind it is in place, so wide keys need no 128-bit shared-memory CAS.
+//   partition fits the key store (the normal case): the items themselves are the key store — item j of the partition
+//     is staged at index j, no allocation at all;
+//   larger partition (a (key, UMI) pair repeated thousands of times, a hot key's partial counts): items stream
+//     through, a thread reserves a key-store index for each new key from a shared counter, writes the key, fences and
+//     publishes.  A reservation whose CAS lost the race is kept for the thread's next new key; what is left over at
+//     the end has count 0 and is skipped.
+template <bool WIDE>
+struct SmemTable {
+    uint32_t* table;
+    unsigned long long* klo;
+    unsigned long long* khi;
+    uint32_t* kcnt;
+    uint32_t* n_perm;  // streaming path: shared counter of reserved key-store entries (may run past kKeyCap: overflow)
+};
+
+template <bool WIDE>
+__device__ __forceinline__ uint32_t smem_find_or_claim(const SmemTable<WIDE>& t, unsigned long long lo, unsigned long long hi,
+                                                       uint32_t h, uint32_t& reserve) {
+    uint32_t s = h & (kTableSlots - 1);
+    for (;;) {
+        uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
+        if (v == kEmpty32) {
+            if (reserve == kEmpty32) {
+                reserve = atomicAdd(t.n_perm, 1u);
+                if (reserve >= kKeyCap) {  // key store full: the CTA reports overflow after the pass
+                    reserve = kEmpty32;
+                    return kEmpty32;
+                }
+                t.kcnt[reserve] = 0u;
+            }
+            t.klo[reserve] = lo;
+            if (WIDE) t.khi[reserve] = hi;
+            __threadfence_block();
+            const uint32_t old = atomicCAS(&t.table[s], kEmpty32, reserve);
+            if (old == kEmpty32) {
+                const uint32_t mine = reserve;
+                reserve = kEmpty32;
+                return mine;
+            }
+            v = old;
+        }
+        const unsigned long long a = *reinterpret_cast<volatile unsigned long long*>(&t.klo[v]);
+        if (a == lo && (!WIDE || *reinterpret_cast<volatile unsigned long long*>(&t.khi[v]) == hi)) return v;
+        s = (s + 1) & (kTableSlots - 1);
+    }
+}
+
+// staged path: the key of item j is already at klo/khi[j]; returns the index that owns the key (j itself when new)
+template <bool WIDE>
+__device__ __forceinline__ uint32_t smem_find_or_claim_staged(const SmemTable<WIDE>& t, unsigned long long lo, unsigned long long hi,
+                                                              uint32_t h, uint32_t j) {
+    uint32_t s = h & (kTableSlots - 1);
+    for (;;) {
+        uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
+        if (v == kEmpty32) {
+            const uint32_t old = atomicCAS(&t.table[s], kEmpty32, j);
+            if (old == kEmpty32) return j;
+            v = old;
+        }
+        if (t.klo[v] == lo && (!WIDE || t.khi[v] == hi)) return v;
+        s = (s + 1) & (kTableSlots - 1);
+    }
+}
+
+// slot hash inside a CTA: independent of the 64-bit hash that chose the partition, and a handful of instructions
+template <bool WIDE>
+__device__ __forceinline__ uint32_t slot_hash(unsigned long long lo, unsigned long long hi) {
+    uint32_t x = (uint32_t)lo * 0x9E3779B1u ^ (uint32_t)(lo >> 32) * 0x85EBCA77u;
+    if (WIDE) x ^= (uint32_t)hi * 0xC2B2AE3Du ^ (uint32_t)(hi >> 32) * 0x27D4EB2Fu;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    return x;
+}
+template <bool WIDE>
+__device__ __forceinline__ Key drop_umi(unsigned long long lo, unsigned long long hi, uint32_t umi_bits) {
+    if (!WIDE) return Key{lo >> umi_bits, 0ULL};  // umi_bits < 64 whenever the record is narrow
+    return key_shr(Key{lo, hi}, umi_bits);
+}
+
+__device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t value) {  // n multiple of 4, p 16-byte aligned
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const uint4 v = make_uint4(value, value, value, value);
+    for (uint32_t i = threadIdx.x; i < n / 4; i += kRedThreads) q[i] = v;
+}
+
+// MODE RED_DEDUPE: in = records (key incl. random barcode), out = (record >> umi_bits, distinct records with that key)
+// MODE RED_COUNT : in = (key, weight) items,                out = (key, sum of weights)
+template <bool WIDE, int MODE>
+__global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
+    k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
+             const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats) {
+    extern __shared__ __align__(16) unsigned char red_smem[];
+    __shared__ uint32_t s_nperm, s_warp[kRedThreads / 32];
+    __shared__ unsigned long long s_base;
+
+    SmemTable<WIDE> t;
+    t.klo = reinterpret_cast<unsigned long long*>(red_smem);
+    t.khi = WIDE ? t.klo + kKeyCap : nullptr;
+    t.table = reinterpret_cast<uint32_t*>(t.klo + (WIDE ? 2 : 1) * kKeyCap);
+    t.kcnt = t.table + kTableSlots;
+    uint32_t* kw = t.kcnt + kKeyCap;  // RED_DEDUPE only
+    t.n_perm = &s_nperm;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long p = blockIdx.x;
+    const unsigned long long a = starts ? (unsigned long long)starts[p] : p * chunk;
+    const unsigned long long e = starts ? (unsigned long long)starts[p + 1] : min(n_items, a + chunk);
+    if (e <= a) return;  // empty partition: nothing to emit
+
+    clear_u32(t.table, kTableSlots, kEmpty32);
+    if (MODE == RED_DEDUPE) clear_u32(kw, kKeyCap, 0u);
+    if (tid == 0) s_nperm = 0;
+
+    uint32_t n_perm;
+    if (e - a <= kKeyCap) {
+        // ---- pass 1, staged: item j lives at key-store index j
+        const uint32_t n = (uint32_t)(e - a);
+        unsigned long long lo[kRedLoads], hi[kRedLoads];
+        uint32_t w[kRedLoads];
+#pragma unroll
+        for (int k = 0; k < kRedLoads; k++) {
+            const uint32_t j = k * kRedThreads + tid;
+            const bool ok = j < n;
+            lo[k] = ok ? in.lo[a + j] : kEmpty;
+            hi[k] = WIDE ? (ok ? in.hi[a + j] : kEmpty) : 0ULL;
+            w[k] = (MODE == RED_COUNT && in.w && ok) ? (uint32_t)in.w[a + j] : 1u;
+        }
+#pragma unroll
+        for (int k = 0; k < kRedLoads; k++) {
+            const uint32_t j = k * kRedThreads + tid;
+            if (j < n) {
+                t.klo[j] = lo[k];
+                if (WIDE) t.khi[j] = hi[k];
+                t.kcnt[j] = 0u;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kRedLoads; k++) {
+            const uint32_t j = k * kRedThreads + tid;
+            if (j >= n || !item_valid(lo[k], hi[k], WIDE)) continue;
+            const uint32_t at = smem_find_or_claim_staged<WIDE>(t, lo[k], hi[k], slot_hash<WIDE>(lo[k], hi[k]), j);
+            if (MODE == RED_COUNT) atomicAdd(&t.kcnt[at], w[k]);
+            else if (at == j) t.kcnt[j] = 1u;  // first of its kind; repeats keep 0
+        }
+        __syncthreads();
+        n_perm = n;
+    } else {
+        // ---- pass 1, streaming: more items than the key store holds (few distinct keys, or overflow)
+        __syncthreads();
+        uint32_t reserve = kEmpty32;
+        for (unsigned long long b = a; b < e; b += (unsigned long long)kRedLoads * kRedThreads) {
+            unsigned long long lo[kRedLoads], hi[kRedLoads];
+            uint32_t w[kRedLoads];
+#pragma unroll
+            for (int k = 0; k < kRedLoads; k++) {
+                const unsigned long long i = b + (unsigned long long)k * kRedThreads + tid;
+                const bool ok = i < e;
+                lo[k] = ok ? in.lo[i] : kEmpty;
+                hi[k] = WIDE ? (ok ? in.hi[i] : kEmpty) : 0ULL;
+                w[k] = (MODE == RED_COUNT && in.w && ok) ? (uint32_t)in.w[i] : 1u;
+            }
+#pragma unroll
+            for (int k = 0; k < kRedLoads; k++) {
+                if (!item_valid(lo[k], hi[k], WIDE)) continue;
+                const uint32_t at = smem_find_or_claim<WIDE>(t, lo[k], hi[k], slot_hash<WIDE>(lo[k], hi[k]), reserve);
+                if (at != kEmpty32) atomicAdd(&t.kcnt[at], MODE == RED_COUNT ? w[k] : 1u);
+            }
+        }
+        __syncthreads();
+        if (s_nperm > kKeyCap) {  // uniform: more distinct keys than the key store holds
+            if (tid == 0) atomicExch(&stats->overflow, 1ULL);
+            return;
+        }
+        n_perm = s_nperm;
+    }
+    uint32_t* val = t.kcnt;
+
+    if (MODE == RED_DEDUPE) {
+        // ---- pass 2: the distinct records, keyed by the record without its random barcode.  The key store stays as
+        // it is; the table is rebuilt over indices of entries, an entry's key being (record >> umi_bits).
+        clear_u32(t.table, kTableSlots, kEmpty32);
+        __syncthreads();
+        uint32_t uniq = 0;
+        for (uint32_t i = tid; i < n_perm; i += kRedThreads) {
+            if (t.kcnt[i] == 0u) continue;
+            uniq++;
+            const Key k = drop_umi<WIDE>(t.klo[i], WIDE ? t.khi[i] : 0ULL, umi_bits);
+            uint32_t s = slot_hash<WIDE>(k.lo, k.hi) & (kTableSlots - 1);
+            for (;;) {
+                uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
+                if (v == kEmpty32) {
+                    const uint32_t old = atomicCAS(&t.table[s], kEmpty32, i);
+                    if (old == kEmpty32) {
+                        atomicAdd(&kw[i], 1u);
+                        break;
+                    }
+                    v = old;
+                }
+                const Key o = drop_umi<WIDE>(t.klo[v], WIDE ? t.khi[v] : 0ULL, umi_bits);
+                if (o.lo == k.lo && o.hi == k.hi) {
+                    atomicAdd(&kw[v], 1u);
+                    break;
+                }
+                s = (s + 1) & (kTableSlots - 1);
+            }
+        }
+        for (int o = 16; o; o >>= 1) uniq += __shfl_xor_sync(0xFFFFFFFFu, uniq, o);
+        if (lane == 0) s_warp[wid] = uniq;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long u = 0;
+            for (int i = 0; i < kRedThreads / 32; i++) u += s_warp[i];
+            if (u) atomicAdd(&stats->unique, u);
+        }
+        __syncthreads();
+        val = kw;
+    }
+
+    // ---- emit: entries with a non-zero value, one global reservation per CTA, each warp writes a contiguous run
+    uint32_t mine = 0;
+    for (uint32_t i = tid; i < n_perm; i += kRedThreads) mine += val[i] != 0u;
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    if (lane == 0) s_warp[wid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int i = 0; i < kRedThreads / 32; i++) {
+            const uint32_t c = s_warp[i];
+            s_warp[i] = total;
+            total += c;
+        }
+        unsigned long long base = total ? atomicAdd(&stats->n_out, (unsigned long long)total) : 0ULL;
+        if (base + total > out_cap) {  // cannot happen: the host sizes the output for one item per input item
+            atomicExch(&stats->overflow, 2ULL);
+            base = ~0ULL;
+        }
+        s_base = base;
+    }
+    __syncthreads();
+    if (s_base == ~0ULL) return;
+    // a warp's entries are those with (i / 32) % n_warps == wid, in increasing i: the same order the count used
+    unsigned long long at = s_base + s_warp[wid];
+    for (uint32_t i0 = wid * 32; i0 < n_perm; i0 += kRedThreads) {  // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const uint32_t c = i < n_perm ? val[i] : 0u;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, c != 0u);
+        if (c != 0u) {
+            Key k{t.klo[i], WIDE ? t.khi[i] : 0ULL};
+            if (MODE == RED_DEDUPE) k = drop_umi<WIDE>(k.lo, k.hi, umi_bits);
+            const unsigned long long pos = at + __popc(bal & ((1u << lane) - 1u));
+            out.lo[pos] = k.lo;
+            if (out.hi) out.hi[pos] = k.hi;
+            out.w[pos] = c;
+        }
+        at += __popc(bal);
+    }
+}
+
+template <bool WIDE, int MODE>
+cudaError_t launch_reduce_t(const ItemView& in, const uint32_t* starts, unsigned long long n_items, unsigned long long n_ranges,
+                            uint32_t chunk, uint32_t umi_bits, const ItemView& out, unsigned long long out_cap, FlushStats* stats,
+                            cudaStream_t stream) {
+    const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);
+    cudaError_t e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    k_reduce<WIDE, MODE><<<(unsigned)n_ranges, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats);
+    return cudaGetLastError();
+}
+
+unsigned stream_grid(unsigned long long n, unsigned block) {
+    unsigned long long g = (n + block - 1) / block;
+    const unsigned long long cap = 148ULL * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ---- appends that do not come from k_decode --------------------------------------------------------------------
+__global__ void k_append_segments(const Key* __restrict__ records, const unsigned long long capacity,
+                                  const uint32_t* __restrict__ counts, const uint32_t count_stride, const uint32_t n_segments,
+                                  const RecOut rec, const unsigned long long rec_cap, unsigned long long* __restrict__ counters,
+                                  FlushStats* stats) {
+    unsigned long long at = *rec.cursor;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        const unsigned long long n = min((unsigned long long)counts[s * count_stride], capacity);
+        const Key* seg = records + (unsigned long long)s * capacity;
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned long long pos = at + i;
+            if (pos >= rec_cap) {  // the host reserves the worst case before the launch
+                atomicExch(&stats->overflow, 4ULL);
+                continue;
+            }
+            const Key k = seg[i];
+            rec.lo[pos] = k.lo;
+            if (rec.hi) rec.hi[pos] = k.hi;
+        }
+        at += n;
+    }
+    // provisional outcome: every routed record is "matched" until the flush finds the repeats
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[BC_CNT_MATCHED], at - *rec.cursor);
+}
+
+__global__ void k_bump_segments(unsigned long long* cursor, const unsigned long long capacity, const uint32_t* __restrict__ counts,
+                                const uint32_t count_stride, const uint32_t n_segments) {
+    unsigned long long add = 0;
+    for (uint32_t s = 0; s < n_segments; s++) add += min((unsigned long long)counts[s * count_stride], capacity);
+    *cursor += add;
+}
+
+__global__ void k_append_records(const Key* __restrict__ records, const unsigned long long n, const RecOut rec,
+                                 unsigned long long* __restrict__ counters) {
+    const unsigned long long at = *rec.cursor;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const Key k = records[i];
+        rec.lo[at + i] = k.lo;
+        if (rec.hi) rec.hi[at + i] = k.hi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[BC_CNT_MATCHED], n);
+}
+
+// global-table path over the record buffer: what k_insert does for routed records, minus the outcome counters
+template <bool WIDE>
+__global__ void k_insert_items(const Tables tables, const ItemView in, const unsigned long long n, FlushStats* stats) {
+    unsigned long long valid = 0, fresh = 0, pairs = 0, uniq = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long lo = in.lo[i], hi = WIDE ? in.hi[i] : 0ULL;
+        if (!item_valid(lo, hi, WIDE)) continue;
+        valid++;
+        bool new_key = false, new_pair = false;
+        if (count_read(tables, Key{lo, hi}, &new_key, &new_pair)) uniq++;
+        fresh += new_key;
+        pairs += new_pair;
+    }
+    for (int o = 16; o; o >>= 1) {
+        valid += __shfl_xor_sync(0xFFFFFFFFu, valid, o);
+        fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
+        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+        uniq += __shfl_xor_sync(0xFFFFFFFFu, uniq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (valid) atomicAdd(&stats->valid, valid);
+        if (uniq) atomicAdd(&stats->unique, uniq);
+        if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
+        if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
+    }
+}
+
+}  // namespace
+
+uint32_t reduce_fill(bool) { return kKeyCap * 3 / 4; }  // mean 1536, sigma 39: the key store is 13 sigma away
+uint32_t reduce_chunk(bool) { return kKeyCap; }
+uint32_t split_max_bits() { return kSplitMaxBits; }
+
+cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cudaStream_t stream) {
+    k_bump<<<1, 1, 0, stream>>>(cursor, add);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,
+                            uint32_t* cursor, cudaStream_t stream) {
+    k_seg_scan<<<n_seg, 512, 0, stream>>>(hist, bins_per_seg, seg_base, starts, cursor);
+    return cudaGetLastError();
+}
+
+template <bool WIDE, bool WEIGHTED, int IPT>
+static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t workers,
+                                    unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream) {
+    constexpr size_t T = (size_t)kScatterThreads * IPT;
+    const size_t smem = T * 8 * (1 + (WIDE ? 1 : 0) + (WEIGHTED ? 1 : 0)) + T * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    k_split_scatter<WIDE, WEIGHTED, IPT><<<grid, kScatterThreads, smem, stream>>>(in, out, seg_starts, workers, n_total, lv, bins);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t n_seg,
+                         unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, FlushStats* stats, bool count_valid,
+                         cudaStream_t stream) {
+    if (n_total == 0) return cudaSuccess;
+    if (lv.F > (1u << kSplitMaxBits) || lv.F == 0) return cudaErrorInvalidValue;
+    const bool weighted = in.w != nullptr;
+    const unsigned long long tile = scatter ? (unsigned long long)kScatterThreads * ((wide || weighted) ? 8 : 16) : (unsigned long long)kSplitThreads * 16;
+    // single segment: one worker per tile, at most a few waves; many segments: a few workers each
+    unsigned long long workers;
+    if (!seg_starts) {
+        workers = (n_total + tile - 1) / tile;
+        if (workers > 148ULL * 16) workers = 148ULL * 16;
+        n_seg = 1;
+    } else {
+        workers = (148ULL * 16 + n_seg - 1) / n_seg;
+        const unsigned long long per_seg = (n_total / n_seg + tile - 1) / tile;
+        if (workers > per_seg) workers = per_seg;
+    }
+    if (workers < 1) workers = 1;
+    const unsigned grid = (unsigned)(workers * n_seg);
+    const uint32_t w = (uint32_t)workers;
+    if (!scatter) {
+        if (wide) k_split_hist<true><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
+        else k_split_hist<false><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
+        return cudaGetLastError();
+    }
+    if (wide) return weighted ? launch_scatter_t<true, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
+                              : launch_scatter_t<true, false, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
+    return weighted ? launch_scatter_t<false, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
+                    : launch_scatter_t<false, false, 16>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
+}
+
+cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
+                          unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
+                          unsigned long long out_cap, FlushStats* stats, cudaStream_t stream) {
+    if (n_ranges == 0) return cudaSuccess;
+    if (n_ranges > 0x7FFFFFFFULL) return cudaErrorInvalidValue;
+    if (mode == RED_DEDUPE)
+        return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream)
+                    : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream);
+    return wide ? launch_reduce_t<true, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream)
+                : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream);
+}
+
+cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,
+                                   uint32_t n_segments, const RecOut& rec, unsigned long long rec_cap, unsigned long long* cursor,
+                                   unsigned long long* counters, FlushStats* stats, cudaStream_t stream) {
+    k_append_segments<<<148 * 4, 256, 0, stream>>>(records, capacity, counts, count_stride, n_segments, rec, rec_cap, counters, stats);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_bump_segments<<<1, 1, 0, stream>>>(cursor, capacity, counts, count_stride, n_segments);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_append_records(const Key* records, unsigned long long n, const RecOut& rec, unsigned long long* counters,
+                                  cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_append_records<<<stream_grid(n, 256), 256, 0, stream>>>(records, n, rec, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_insert_items(const Tables& tables, const ItemView& in, bool wide, unsigned long long n, FlushStats* stats,
+                                cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (wide) k_insert_items<true><<<stream_grid(n, 256), 256, 0, stream>>>(tables, in, n, stats);
+    else k_insert_items<false><<<stream_grid(n, 256), 256, 0, stream>>>(tables, in, n, stats);
+    return cudaGetLastError();
+}
+
+}  // namespace bc

@@ -388,6 +388,90 @@ def test_table_growth_and_many_keys():
     assert got == want
 
 
+def _count_mode(monkeypatch, mode):
+    """deferred: records appended, partitioned shared-memory flush (default); global: same records flushed through the
+    global-memory tables (the overflow fallback); inline: tables updated read by read inside k_decode."""
+    monkeypatch.delenv("BC_FLUSH_GLOBAL", raising=False)
+    monkeypatch.delenv("BC_INLINE_COUNT", raising=False)
+    if mode == "global":
+        monkeypatch.setenv("BC_FLUSH_GLOBAL", "1")
+    elif mode == "inline":
+        monkeypatch.setenv("BC_INLINE_COUNT", "1")
+
+
+@pytest.mark.parametrize("mode", ["deferred", "global", "inline"])
+def test_counting_modes_skewed_keys(mode, monkeypatch):
+    """What the deferred counting has to survive: one (key, UMI) pair repeated far beyond a partition's table size, one hot
+    key with tens of thousands of distinct UMIs, many singleton keys — in several submits, with counters read (= a flush)
+    in between.  Expected counts are computed in Python from the construction."""
+    _count_mode(monkeypatch, mode)
+    exp, paths = load_golden("lineage_raw")
+    run = make_run(paths, exp["flags"])
+    rng = random.Random(11)
+    reads = read_fastq(paths["fastq"])
+    tmpl = [r for r, o in zip(reads, exp["outcomes"]) if o["status"] == "matched" and not o["repaired"]][0][0]
+    off = [o for o in exp["outcomes"] if o["status"] == "matched" and not o["repaired"]][0]["offset"]
+
+    def read(key, umi):
+        return tmpl[:off + 20] + key + tmpl[off + 50:off + 60] + umi + tmpl[off + 72:]
+
+    seqs, pairs = [], set()
+    hot, rep_key, rep_umi = rand_dna(rng, 30), rand_dna(rng, 30), rand_dna(rng, 12)
+    seqs += [read(rep_key, rep_umi)] * 20000
+    pairs.add((rep_key, rep_umi))
+    for _ in range(30000):
+        u = rand_dna(rng, 12)
+        seqs.append(read(hot, u))
+        pairs.add((hot, u))
+    for _ in range(9000):
+        k, u = rand_dna(rng, 30), rand_dna(rng, 12)
+        seqs.append(read(k, u))
+        pairs.add((k, u))
+    seqs.append("ACGT" * 25)  # no scheme in it
+    rng.shuffle(seqs)
+    want = {}
+    for k, _ in pairs:
+        want[k] = want.get(k, 0) + 1
+    ctr = bc.Counter(run, expected_reads=0)
+    assert ctr.profile()["deferred_count"] == (0 if mode == "inline" else 1)
+    batch = run.pack(seqs)
+    cuts = [0, 7000, 7001, 40000, batch.n]
+    for a, b in zip(cuts, cuts[1:]):
+        ctr.submit(batch.slice(a, b))
+        c = ctr.counters()  # flushes in the deferred modes; later submits must still add up
+        assert sum(c.values()) == b
+    assert c["matched"] == len(pairs) and c["duplicates"] == len(seqs) - 1 - len(pairs) and c["constant_region"] == 1
+    assert ctr.profile()["flushed_global"] == (1 if mode == "global" else 0)
+    rows = ctr.finish()
+    got = {}
+    for lo, hi, cnt in zip(rows["key_lo"], rows["key_hi"], rows["count"]):
+        k = ctr.key_decode(lo, hi)[0]
+        assert k not in got
+        got[k] = int(cnt)
+    assert got == want
+    ctr.reset()
+    ctr.submit(batch.slice(0, 5000))
+    assert sum(ctr.counters().values()) == 5000
+
+
+@pytest.mark.parametrize("mode", ["global", "inline"])
+@pytest.mark.parametrize("case", ["del3_umi", "example", "sample_raw_two"])
+def test_golden_csv_other_counting_modes(case, mode, tmp_path, monkeypatch):
+    """The golden CSV sets through the two non-default counting paths (the default one is test_golden_per_read_and_csv)."""
+    _count_mode(monkeypatch, mode)
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run)
+    reads = read_fastq(paths["fastq"])
+    ctr.submit(run.pack([r[0] for r in reads], [r[1] for r in reads]))
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+
+
 @pytest.mark.parametrize("blen,max_err,n_ref", [(20, None, 700), (20, 1, 300), (20, 7, 400), (16, 2, 5000), (12, None, 900),
                                                 (24, 5, 260), (11, 0, 300), (20, None, 100)])
 def test_long_barcode_search_paths(blen, max_err, n_ref, tmp_path):
