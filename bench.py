@@ -297,7 +297,7 @@ def main():
                 "counting": ("deferred: records appended by k_decode, partitioned shared-memory de-duplication + counting at the "
                              "flush (kernel_ms.finish)" if prof["deferred_count"] else
                              "inline: tables updated read by read inside k_decode"),
-                "flushed_global": prof["flushed_global"]}
+                "flushed_global": prof["flushed_global"], "flush_stages": prof["flush_stages"]}
     gpu_launches = sum(prof["launches"].values())
     if rank == 0:
         try:  # INT-pipe peaks of this GPU (register-only microbenchmarks) and the pivot-test rate the kernel reaches

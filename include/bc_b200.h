@@ -245,6 +245,9 @@ typedef struct {
     uint32_t deferred_count; /* 1: matched reads are appended to a record buffer and counted at bc_finish /
                                 bc_get_counters (partitioned, in shared memory); 0: tables updated read by read */
     uint32_t flushed_global; /* 1: the last flush fell back to the global-memory tables */
+    uint32_t flush_stages;   /* the last shared-memory flush: 1 = no hot key, partitioned by key and counted in one pass;
+                                2 = partitioned by (key, random barcode), then by key; 3 = one pass, with the few hot
+                                keys' partitions set aside and sent through the two stages */
 } bc_profile;
 int bc_set_profiling(bc_ctx *ctx, int on);
 int bc_get_profile(bc_ctx *ctx, bc_profile *out); /* synchronises */

@@ -66,7 +66,7 @@ class bc_profile(C.Structure):
     _fields_ = [("launches", C.c_uint64 * BC_N_KERNELS), ("ms", C.c_double * BC_N_KERNELS), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("table_capacity", C.c_uint64), ("table_entries", C.c_uint64),
                 ("key_bits", C.c_uint32), ("wide_keys", C.c_uint32), ("dense_table", C.c_uint32),
-                ("deferred_count", C.c_uint32), ("flushed_global", C.c_uint32)]
+                ("deferred_count", C.c_uint32), ("flushed_global", C.c_uint32), ("flush_stages", C.c_uint32)]
 
 
 class bch_args(C.Structure):
@@ -422,4 +422,4 @@ class Counter:
                     ms=dict(zip(KERNEL_NAMES, [float(x) for x in p.ms])), h2d_bytes=int(p.h2d_bytes),
                     d2h_bytes=int(p.d2h_bytes), table_capacity=int(p.table_capacity), table_entries=int(p.table_entries),
                     key_bits=int(p.key_bits), wide_keys=int(p.wide_keys), dense_table=int(p.dense_table),
-                    deferred_count=int(p.deferred_count), flushed_global=int(p.flushed_global))
+                    deferred_count=int(p.deferred_count), flushed_global=int(p.flushed_global), flush_stages=int(p.flush_stages))

@@ -87,6 +87,7 @@ struct bc_ctx {
     ItemBuf rec;                          // the record buffer: slot (cursor + read index) per read, kEmpty = hole
     unsigned long long* d_rec_n = nullptr;   // device cursor: slots used
     unsigned long long rec_upper = 0;        // host-side upper bound of the cursor
+    ItemBuf left;                         // records of the hot partitions set aside by the one-stage flush
     ItemBuf part, w1, w2, tmp;            // scratch: partitioned records, (key, weight) items before / after partitioning,
                                           // and the output of the first radix level when two are needed
     uint32_t* d_l1 = nullptr;             // histogram / starts / cursors of the first radix level
@@ -97,6 +98,7 @@ struct bc_ctx {
     FlushStats* d_flush = nullptr;
     unsigned long long dup_applied = 0;   // duplicates already moved from "matched" to "duplicates" by earlier flushes
     bool flushed_global = false;          // the last flush went through the global-memory tables
+    uint32_t flush_stages = 0;            // partition / reduce stages of the last shared-memory flush (1 or 2)
     // counting state: map (key -> count) and, with a random barcode, the (key, UMI) set
     Tables tables{};
     unsigned long long expected_reads = 0;
@@ -465,6 +467,7 @@ void bc_destroy(bc_ctx* ctx) {
     free_items(ctx->w1);
     free_items(ctx->w2);
     free_items(ctx->tmp);
+    free_items(ctx->left);
     if (ctx->d_l1) cudaFree(ctx->d_l1);
     free_items(ctx->imp);
     if (ctx->d_rec_n) cudaFree(ctx->d_rec_n);
@@ -605,6 +608,14 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             }
         }
         d.pivot = (uint32_t)bestw;
+        d.bs_ok = d.max_const_err <= 15 ? 1u : 0u;
+        d.bs_k = 15u - std::min<uint32_t>(d.max_const_err, 15u);
+        for (uint32_t q = 0; q < 32; q++) {
+            if (!((d.t_cm[bestw] >> q) & 1u)) continue;
+            const uint32_t b = ((d.t_lo[bestw] >> q) & 1u) | (((d.t_hi[bestw] >> q) & 1u) << 1);
+            const uint32_t i = d.pv_n[b]++;
+            d.pv_sh4[b][i >> 2] |= q << (8 * (i & 3));
+        }
     }
 
     // ---- quality runs (parse.rs:340-374): maximal runs of one region code; a non-constant run is tested only when
@@ -975,9 +986,14 @@ static int apply_duplicates(bc_ctx* ctx, unsigned long long dup_now) {
 
 // Hash-partitions n items (about n_valid of them not holes) into *n_parts pieces of ~reduce_fill items each
 // (ctx->d_starts = their offsets in `out`).  One radix level for up to 2048 partitions, otherwise two (through `tmp`).
-// Returns 1 when the input is too large for two levels (the caller then takes the global-table path).
+// drop_bits > 0 partitions by the key without its random barcode; max_part > 0 asks for every partition to hold at
+// most that many items.  Returns 1 when the input is too large for two levels (the caller then takes the global-table
+// path); with max_part: 2 when so many items sit in partitions larger than max_part that partitioning by key is
+// pointless (nothing was moved to `out`), 3 when a few partitions are larger (moved like the others; *big_items says
+// how many items they hold).
 static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned long long n, unsigned long long n_valid, bool weighted,
-                           const ItemView& out, bool count_valid, unsigned long long* n_parts) {
+                           const ItemView& out, bool count_valid, uint32_t drop_bits, uint32_t max_part, unsigned long long* n_parts,
+                           unsigned long long* big_items = nullptr, unsigned long long salt = 0) {
     unsigned long long P = (n_valid + reduce_fill(wide) - 1) / reduce_fill(wide);
     if (P < 1) P = 1;
     const uint32_t mb = split_max_bits();
@@ -995,28 +1011,62 @@ static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned 
     int rc = reserve_parts(ctx, P);
     if (rc != BC_OK) return rc;
     ProfScope p(ctx, BC_K_FINISH);
+    int verdict = BC_OK;
+    auto too_big = [&](bool* yes) -> int {  // partitions of the histogram just scanned that exceed max_part
+        FlushStats st{};
+        CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        *yes = st.big_items * 5 > n_valid;  // more than a fifth of the items under hot keys: not worth it
+        if (st.max_bin > max_part) verdict = 3;
+        if (big_items) *big_items = st.big_items;
+        return BC_OK;
+    };
     CK(ctx, cudaMemsetAsync(ctx->d_hist, 0, (P + 1) * sizeof(uint32_t), ctx->stream));
     if (l2 == 0) {
-        const SplitLevel lv{P, 0u, 0xFFFFFFFFu, (uint32_t)P};
+        const SplitLevel lv{P, 0u, 0xFFFFFFFFu, (uint32_t)P, drop_bits, salt};
         CK(ctx, launch_split(false, wide, in, out, nullptr, 1, n, lv, ctx->d_hist, ctx->d_flush, count_valid, ctx->stream));
-        CK(ctx, launch_seg_scan(ctx->d_hist, 1, (uint32_t)P, nullptr, ctx->d_starts, ctx->d_cursor, ctx->stream));
+        CK(ctx, launch_seg_scan(ctx->d_hist, 1, (uint32_t)P, nullptr, ctx->d_starts, ctx->d_cursor, max_part ? ctx->d_flush : nullptr, max_part, ctx->stream));
+        if (max_part) {
+            bool big = false;
+            rc = too_big(&big);
+            if (rc != BC_OK) return rc;
+            if (big) return 2;
+        }
         CK(ctx, launch_split(true, wide, in, out, nullptr, 1, n, lv, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
-        return BC_OK;
+        return verdict;
     }
     rc = reserve_items(ctx, ctx->tmp, n, wide, weighted);
     if (rc != BC_OK) return rc;
     if (!ctx->d_l1) CK(ctx, cudaMalloc(&ctx->d_l1, 3 * ((1u << mb) + 1) * sizeof(uint32_t)));
     uint32_t *hist1 = ctx->d_l1, *starts1 = hist1 + (1u << mb) + 1, *cursor1 = starts1 + (1u << mb) + 1;
     const ItemView tmp{ctx->tmp.lo, wide ? ctx->tmp.hi : nullptr, weighted ? ctx->tmp.w : nullptr};
-    const SplitLevel lv1{P, l2, 0xFFFFFFFFu, (uint32_t)F1}, lv2{P, 0u, (1u << l2) - 1u, 1u << l2};
+    const SplitLevel lv1{P, l2, 0xFFFFFFFFu, (uint32_t)F1, drop_bits, salt}, lv2{P, 0u, (1u << l2) - 1u, 1u << l2, drop_bits, salt};
     CK(ctx, cudaMemsetAsync(hist1, 0, (F1 + 1) * sizeof(uint32_t), ctx->stream));
     CK(ctx, launch_split(false, wide, in, tmp, nullptr, 1, n, lv1, hist1, ctx->d_flush, count_valid, ctx->stream));
-    CK(ctx, launch_seg_scan(hist1, 1, (uint32_t)F1, nullptr, starts1, cursor1, ctx->stream));
+    CK(ctx, launch_seg_scan(hist1, 1, (uint32_t)F1, nullptr, starts1, cursor1, max_part ? ctx->d_flush : nullptr, 0xFFFFFFFFu, ctx->stream));
+    if (max_part) {  // a first-level segment 2^l2 times the limit cannot split into small enough partitions
+        FlushStats st{};
+        CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (st.max_bin > ((unsigned long long)max_part << l2)) return 2;  // a segment whose AVERAGE partition is too large
+        CK(ctx, cudaMemsetAsync(&ctx->d_flush->max_bin, 0, sizeof(unsigned long long), ctx->stream));
+    }
     CK(ctx, launch_split(true, wide, in, tmp, nullptr, 1, n, lv1, cursor1, ctx->d_flush, false, ctx->stream));
     CK(ctx, launch_split(false, wide, tmp, out, starts1, (uint32_t)F1, n, lv2, ctx->d_hist, ctx->d_flush, false, ctx->stream));
-    CK(ctx, launch_seg_scan(ctx->d_hist, (uint32_t)F1, 1u << l2, starts1, ctx->d_starts, ctx->d_cursor, ctx->stream));
+    CK(ctx, launch_seg_scan(ctx->d_hist, (uint32_t)F1, 1u << l2, starts1, ctx->d_starts, ctx->d_cursor, max_part ? ctx->d_flush : nullptr, max_part, ctx->stream));
+    if (max_part) {
+        bool big = false;
+        rc = too_big(&big);
+        if (rc != BC_OK) return rc;
+        if (big) return 2;
+    }
     CK(ctx, launch_split(true, wide, tmp, out, starts1, (uint32_t)F1, n, lv2, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
-    return BC_OK;
+    return verdict;
+}
+
+static int go_global(bc_ctx* ctx, unsigned long long n_rec, int where, unsigned long long code) {
+    if (getenv("BC_DEBUG_FLUSH")) fprintf(stderr, "bc: flush falls back to the global tables (site %d, overflow code %llu, %llu records)\n", where, code, n_rec);
+    return flush_global(ctx, n_rec);
 }
 
 static int flush_records(bc_ctx* ctx) {
@@ -1028,6 +1078,7 @@ static int flush_records(bc_ctx* ctx) {
     CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
     ctx->rec_upper = n_rec;
     ctx->flushed_global = false;
+    ctx->flush_stages = 0;
     const bool has_umi = ctx->cfg.has_umi != 0;
     const bool wide_in = ctx->cfg.wide != 0, wide_out = ctx->tables.map.wide != 0;
     FlushStats st{};
@@ -1045,71 +1096,141 @@ static int flush_records(bc_ctx* ctx) {
         n_valid = std::min(n_rec, h[BC_CNT_MATCHED] + h[BC_CNT_DUPLICATES]);
     }
     const char* force = getenv("BC_FLUSH_GLOBAL");
-    if ((force && force[0] == '1') || n_rec + ctx->imp_n >= 0xFFFFFFF0ULL) return flush_global(ctx, n_rec);
+    if ((force && force[0] == '1') || n_rec + ctx->imp_n >= 0xFFFFFFF0ULL) return go_global(ctx, n_rec, 1, st.overflow);
 
     CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    const ItemView rows_v{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt};
+    ItemView src{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr};
+    unsigned long long n_src = n_rec, src_valid = n_valid, rows_done = 0, valid_total = 0, unique_total = 0;
+    bool count_valid = has_umi;
+    uint32_t stages = 0;
+    unsigned long long salt = 0;
+
+    // ---- one stage when (almost) no key is hot: partition by the key WITHOUT its random barcode, so a partition holds
+    // every pair of its keys and the reduce kernel's (key, pairs) output is final.  A key with more pairs than a CTA's
+    // key store makes its partition too large, which shows in the histogram before anything is moved: a few such
+    // partitions are set aside (k_gather_big) and go through the two stages below on their own; if they hold more
+    // than a fifth of the records, the one-stage attempt is abandoned.
+    const char* two = getenv("BC_FLUSH_TWO_STAGE");
+    if (has_umi && n_rec && ctx->imp_n == 0 && !(two && two[0] == '1')) {
+        unsigned long long n_parts = 0, big = 0;
+        rc = reserve_items(ctx, ctx->part, n_rec, wide_in, false);
+        if (rc == BC_OK) rc = reserve_rows(ctx, n_valid, wide_out);
+        if (rc != BC_OK) return rc;
+        const ItemView part_v{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr};
+        const uint32_t cap = reduce_capacity(wide_in);
+        rc = partition_items(ctx, src, wide_in, n_rec, n_valid, false, part_v, true, ctx->cfg.umi_bits, cap, &n_parts, &big);
+        if (rc == 1) return go_global(ctx, n_rec, 2, st.overflow);
+        if (rc == BC_OK || rc == 3) {
+            {
+                ProfScope p(ctx, BC_K_FINISH);
+                CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
+                                      ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
+                                      ctx->d_flush, rc == 3 ? cap : 0u, ctx->stream));
+            }
+            CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+            if (st.overflow) return go_global(ctx, n_rec, 3, st.overflow);
+            rows_done = st.n_out;
+            valid_total = st.valid;
+            unique_total = st.unique;
+            stages = 1;
+            if (rc == BC_OK) {
+                ctx->n_rows = rows_done;
+                ctx->rows_valid = true;
+                ctx->flush_stages = 1;
+                return apply_duplicates(ctx, valid_total - unique_total);
+            }
+            // the hot partitions, gathered: the input of the two stages
+            int rc2 = reserve_items(ctx, ctx->left, big, wide_in, false);
+            if (rc2 != BC_OK) return rc2;
+            const ItemView left_v{ctx->left.lo, wide_in ? ctx->left.hi : nullptr, nullptr};
+            {
+                ProfScope p(ctx, BC_K_FINISH);
+                CK(ctx, launch_gather_big(part_v, ctx->d_starts, n_parts, cap, left_v, ctx->d_flush, ctx->stream));
+            }
+            CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+            src = left_v;
+            n_src = src_valid = big;
+            count_valid = false;
+            salt = 0x6A09E667F3BCC909ULL;  // these records share the hash bits that chose their partitions: use another hash
+        } else if (rc == 2) {
+            CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));  // hot keys everywhere: two stages
+        } else {
+            return rc;
+        }
+    }
+
     // ---- stage A: records -> (key, pairs) items in w1
-    rc = reserve_items(ctx, ctx->w1, n_rec + ctx->imp_n, wide_out, true);
+    rc = reserve_items(ctx, ctx->w1, src_valid + ctx->imp_n, wide_out, true);
     if (rc != BC_OK) return rc;
-    if (n_rec) {
+    const ItemView w1_v{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w};
+    if (n_src) {
         if (has_umi) {
             unsigned long long n_parts = 0;
-            rc = reserve_items(ctx, ctx->part, n_rec, wide_in, false);
-            if (rc == BC_OK)
-                rc = partition_items(ctx, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, wide_in, n_rec, n_valid, false,
-                                     ItemView{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr}, true, &n_parts);
-            if (rc == 1) return flush_global(ctx, n_rec);
+            rc = reserve_items(ctx, ctx->part, n_src, wide_in, false);
+            if (rc != BC_OK) return rc;
+            const ItemView part_v{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr};
+            rc = partition_items(ctx, src, wide_in, n_src, src_valid, false, part_v, count_valid, 0, 0, &n_parts, nullptr, salt);
+            if (rc == 1) return go_global(ctx, n_rec, 4, st.overflow);
             if (rc != BC_OK) return rc;
             ProfScope p(ctx, BC_K_FINISH);
-            CK(ctx, launch_reduce(RED_DEDUPE, wide_in, ItemView{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr}, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
-                                  ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w}, ctx->w1.cap, ctx->d_flush, ctx->stream));
+            CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_src, n_parts, 0, ctx->cfg.umi_bits, w1_v, ctx->w1.cap,
+                                  ctx->d_flush, 0, ctx->stream));
         } else {
             const uint32_t chunk = reduce_chunk(wide_in);
             ProfScope p(ctx, BC_K_FINISH);
-            CK(ctx, launch_reduce(RED_COUNT, wide_in, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, nullptr, n_rec,
-                                  (n_rec + chunk - 1) / chunk, chunk, 0, ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w},
-                                  ctx->w1.cap, ctx->d_flush, ctx->stream));
+            CK(ctx, launch_reduce(RED_COUNT, wide_in, src, nullptr, n_src, (n_src + chunk - 1) / chunk, chunk, 0, w1_v, ctx->w1.cap,
+                                  ctx->d_flush, 0, ctx->stream));
         }
     }
     CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (st.overflow) {
-        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-        return flush_global(ctx, n_rec);
-    }
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    if (st.overflow) return go_global(ctx, n_rec, 5, st.overflow);
     unsigned long long n1 = st.n_out;
-    const unsigned long long dup_now = has_umi ? st.valid - st.unique : 0;
+    if (count_valid) valid_total = st.valid;
+    unique_total += st.unique;
     if (ctx->imp_n) {  // rows of other ranks join as (key, count) items
+        rc = reserve_items(ctx, ctx->w1, n1 + ctx->imp_n, wide_out, true, n1);
+        if (rc != BC_OK) return rc;
         CK(ctx, cudaMemcpyAsync(ctx->w1.lo + n1, ctx->imp.lo, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (wide_out) CK(ctx, cudaMemcpyAsync(ctx->w1.hi + n1, ctx->imp.hi, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(ctx, cudaMemcpyAsync(ctx->w1.w + n1, ctx->imp.w, ctx->imp_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         n1 += ctx->imp_n;
     }
-    // ---- stage B: items partitioned by key, summed per key -> rows
+    // ---- stage B: items partitioned by key, summed per key -> rows (after the rows of the one-stage part, if any)
+    ctx->n_rows = rows_done;
     if (n1) {
         unsigned long long n_parts = 0;
         rc = reserve_items(ctx, ctx->w2, n1, wide_out, true);
-        if (rc == BC_OK) rc = reserve_rows(ctx, n1, wide_out);
         if (rc != BC_OK) return rc;
-        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-        rc = partition_items(ctx, ItemView{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w}, wide_out, n1, n1, true,
-                             ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, false, &n_parts);
-        if (rc == 1) return flush_global(ctx, n_rec);
+        if (rows_done == 0) rc = reserve_rows(ctx, n1, wide_out);
+        else if (rows_done + n1 > ctx->row_cap) return go_global(ctx, n_rec, 6, st.overflow);  // cannot happen: sized for every valid record
         if (rc != BC_OK) return rc;
+        const ItemView w1_now{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w};
+        rc = partition_items(ctx, w1_now, wide_out, n1, n1, true, ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, false, 0,
+                             0, &n_parts, nullptr, salt);
+        if (rc == 1) return go_global(ctx, n_rec, 7, st.overflow);
+        if (rc != BC_OK) return rc;
+        CK(ctx, cudaMemcpyAsync(&ctx->d_flush->n_out, &rows_done, sizeof rows_done, cudaMemcpyHostToDevice, ctx->stream));
         {
             ProfScope p(ctx, BC_K_FINISH);
             CK(ctx, launch_reduce(RED_COUNT, wide_out, ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, ctx->d_starts, n1,
                                   n_parts, 0, 0, ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
-                                  ctx->d_flush, ctx->stream));
+                                  ctx->d_flush, 0, ctx->stream));
         }
         CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-        if (st.overflow) return flush_global(ctx, n_rec);
+        if (st.overflow) return go_global(ctx, n_rec, 8, st.overflow);
         ctx->n_rows = st.n_out;
     }
+    (void)rows_v;
     ctx->rows_valid = true;
-    return apply_duplicates(ctx, dup_now);
+    ctx->flush_stages = stages ? 3 : 2;  // 3: one stage plus two stages for the hot keys
+    return apply_duplicates(ctx, has_umi ? valid_total - unique_total : 0);
 }
 
 // Fallback: the record buffer through the global-memory set / map of bc_device.cuh (random DRAM accesses).
@@ -1709,6 +1830,7 @@ int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
     ctx->prof.dense_table = ctx->tables.map.kind == 0;
     ctx->prof.deferred_count = ctx->deferred ? 1u : 0u;
     ctx->prof.flushed_global = ctx->flushed_global ? 1u : 0u;
+    ctx->prof.flush_stages = ctx->flush_stages;
     *out = ctx->prof;
     return BC_OK;
 }

@@ -60,6 +60,11 @@ struct DevCfg {
     uint32_t pivot;  // template word with the most constant bases: the locate prefilter looks at it alone
     uint32_t has_umi, umi_bits, key_bits, wide;
     uint32_t t_lo[kMaxTW], t_hi[kMaxTW], t_cm[kMaxTW], t_fn[kMaxTW];
+    // bit-sliced pivot prefilter (max_const_err <= 15): the pivot word's constant positions grouped by their base
+    // (0 A, 1 C, 2 G, 3 T); pv_sh4[b][i] packs the positions 4 i .. 4 i + 3 of base b, one per byte
+    uint32_t bs_ok, bs_k;  // bs_k = 15 - max_const_err: counters start there, overflow into bit 4 <=> too many mismatches
+    uint32_t pv_n[4];
+    uint32_t pv_sh4[4][8];
     DevSlot slots[kMaxSlots];
     uint8_t order[kMaxSlots];  // sample first, then counted barcodes in order, then the random barcode
     DevQRun qruns[kMaxQRuns];

@@ -13,11 +13,16 @@ namespace bc {
 
 __device__ __forceinline__ uint32_t lenmask(uint32_t len) { return len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u); }
 
-// bits [pos, pos+32) of a W-word bit plane
+// bits [pos, pos+32) of a W-word bit plane.  CHECK = false (k_decode, planes staged in shared memory): every caller
+// has pos < 32 W, so word j exists, and word j + 1 is at worst the first word of the next plane / record / array of
+// the tile — readable, and its bits land beyond the read's last base, where every consumer masks (template constant
+// mask, slot length mask).  CHECK = true (k_resolve reads the batch in global memory) never reads past the plane.
+template <bool CHECK>
 __device__ __forceinline__ uint32_t plane_bits(const uint32_t* p, uint32_t W, uint32_t pos) {
-    uint32_t j = pos >> 5, s = pos & 31;
-    uint32_t a = j < W ? p[j] : 0u;
-    uint32_t b = (j + 1) < W ? p[j + 1] : 0u;
+    const uint32_t j = pos >> 5, s = pos & 31;
+    if (!CHECK) return __funnelshift_r(p[j], p[j + 1], s);
+    const uint32_t a = j < W ? p[j] : 0u;
+    const uint32_t b = (j + 1) < W ? p[j + 1] : 0u;
     return __funnelshift_r(a, b, s);
 }
 
@@ -102,35 +107,36 @@ __device__ __forceinline__ uint32_t hash_exact(const DevAux& aux, const DevSlot&
 __device__ __forceinline__ uint32_t table_pick(uint32_t e, uint32_t max_err) {
     return (!(e & 0x1000000u) && ((e >> 16) & 0xFFu) <= max_err) ? (e & 0xFFFFu) : kFail;
 }
-// A query with one or two N: d(query, c) ignoring the N positions equals the minimum over the completions x' of the
-// N positions of d(x', c), so the unique-minimum rule can be read off the completions' entries: the overall minimum
-// is the smallest entry distance, and it is unique iff every completion reaching it names one and the same reference
+// A query with one N: d(query, c) ignoring the N position equals the minimum over the four completions x' of that
+// position of d(x', c), so the unique-minimum rule can be read off the completions' entries: the overall minimum is
+// the smallest entry distance, and it is unique iff every completion reaching it names one and the same reference
 // without a tie.  Valid for N-free reference sets of one length (the host sets DevSlot::n_inline only then).
-__device__ __forceinline__ uint32_t table_lookup_n(const uint32_t* __restrict__ tab, const DevSlot& S, uint32_t lo, uint32_t hi,
-                                                   uint32_t nm) {
-    const uint32_t t = __popc(nm);
-    const uint32_t n1 = (uint32_t)__ffs(nm) - 1u;
-    const uint32_t n2 = 31u - (uint32_t)__clz(nm);
-    uint32_t kmin = 256u, cand = kFail;
+// Queries with more N go to k_resolve.
+// One N (the common case of the rare case): the four completions, unrolled.
+__device__ __forceinline__ uint32_t table_lookup_1n(const uint32_t* __restrict__ tab, const DevSlot& S, uint32_t lo, uint32_t hi,
+                                                    uint32_t nm) {
+    const uint32_t base = lo | (hi << S.len);
+    const uint32_t e0 = __ldg(&tab[base]), e1 = __ldg(&tab[base | nm]), e2 = __ldg(&tab[base | (nm << S.len)]),
+                   e3 = __ldg(&tab[base | nm | (nm << S.len)]);
+    // key = distance << 17 | tie << 16 | id: the smallest key is the smallest distance, ties flagged first
+    const uint32_t k0 = ((e0 >> 16) & 0xFFu) << 17 | ((e0 >> 24) & 1u) << 16 | (e0 & 0xFFFFu);
+    const uint32_t k1 = ((e1 >> 16) & 0xFFu) << 17 | ((e1 >> 24) & 1u) << 16 | (e1 & 0xFFFFu);
+    const uint32_t k2 = ((e2 >> 16) & 0xFFu) << 17 | ((e2 >> 24) & 1u) << 16 | (e2 & 0xFFFFu);
+    const uint32_t k3 = ((e3 >> 16) & 0xFFu) << 17 | ((e3 >> 24) & 1u) << 16 | (e3 & 0xFFFFu);
+    const uint32_t dmin = min(min(k0 >> 17, k1 >> 17), min(k2 >> 17, k3 >> 17));
+    // unique iff every completion at the minimum distance names the same reference and none of them is a tie
+    uint32_t cand = kFail;
     bool multi = false;
-    for (uint32_t comp = 0; comp < (1u << (2 * t)); comp++) {
-        uint32_t vlo = lo | ((comp & 1u) << n1), vhi = hi | (((comp >> 1) & 1u) << n1);
-        if (t > 1) {
-            vlo |= ((comp >> 2) & 1u) << n2;
-            vhi |= ((comp >> 3) & 1u) << n2;
-        }
-        const uint32_t e = __ldg(&tab[vlo | (vhi << S.len)]);
-        const uint32_t d = (e >> 16) & 0xFFu, id = e & 0xFFFFu;
-        const bool tie = (e & 0x1000000u) != 0;
-        if (d < kmin) {
-            kmin = d;
-            cand = id;
-            multi = tie;
-        } else if (d == kmin && (tie || id != cand)) {
-            multi = true;
-        }
+    const uint32_t ks[4] = {k0, k1, k2, k3};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if ((ks[i] >> 17) != dmin) continue;
+        const uint32_t id = ks[i] & 0xFFFFu;
+        if ((ks[i] >> 16) & 1u) multi = true;
+        if (cand == kFail) cand = id;
+        else if (cand != id) multi = true;
     }
-    return (!multi && kmin <= S.max_err) ? cand : kFail;
+    return (!multi && dmin <= S.max_err) ? cand : kFail;
 }
 
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -196,6 +202,42 @@ __device__ __forceinline__ int half_probe(const DevAux& aux, const DevSlot& S, u
     return HALF_DEEPER;
 }
 
+// ---- bit-sliced mismatch counters for the pivot prefilter ---------------------------------------------------------
+// Five bit planes hold, for 32 window offsets at once, a 5-bit counter per offset (plane k = bit k of every counter).
+// bs_add4 adds four 1-bit inputs per offset with carry-save adders: 11 LOP3 for 4 x 32 additions.  The top plane
+// only ever ORs carries in: it says "the counter passed 15".
+struct BsPlanes {
+    uint32_t p1, p2, p4, p8, p16;
+};
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+__device__ __forceinline__ void bs_add4(BsPlanes& P, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
+    const uint32_t a1 = P.p1 ^ x1 ^ x2, c1a = maj3(P.p1, x1, x2);
+    const uint32_t a2 = a1 ^ x3 ^ x4, c1b = maj3(a1, x3, x4);
+    P.p1 = a2;
+    const uint32_t c2 = maj3(P.p2, c1a, c1b);
+    P.p2 = P.p2 ^ c1a ^ c1b;
+    const uint32_t c4 = P.p4 & c2;
+    P.p4 ^= c2;
+    const uint32_t c8 = P.p8 & c4;
+    P.p8 ^= c4;
+    P.p16 |= c8;
+}
+// all pivot positions of one base: M0/M1 = mismatch plane of the read against that base, words j and j + 1
+__device__ __forceinline__ void bs_base(BsPlanes& P, uint32_t M0, uint32_t M1, uint32_t n, const uint32_t* sh4) {
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t sh = sh4[i >> 2];
+        bs_add4(P, __funnelshift_r(M0, M1, sh), __funnelshift_r(M0, M1, sh >> 8), __funnelshift_r(M0, M1, sh >> 16),
+                __funnelshift_r(M0, M1, sh >> 24));
+    }
+    const uint32_t r = n - i;
+    if (r) {
+        const uint32_t sh = sh4[i >> 2];
+        bs_add4(P, __funnelshift_r(M0, M1, sh), r > 1 ? __funnelshift_r(M0, M1, sh >> 8) : 0u,
+                r > 2 ? __funnelshift_r(M0, M1, sh >> 16) : 0u, 0u);
+    }
+}
+
 // ---- K1: locate (parse.rs:89-96, 151-163, 287-313) ----------------------------------------------------------
 // Two predicates per window (Q1): the regex's exact test (a read N in a constant fails, format-N needs ACGT) and
 // the repair's masked Hamming distance (N on either side is a wildcard).  Leftmost exact window wins (P1);
@@ -215,11 +257,23 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
     int arg = -1, first_exact = -1;
     for (int c = 0; (c << 5) < nwin && first_exact < 0; c++) {
         const uint32_t j = c + kp;
-        const uint32_t al = j < W ? lo[j] : 0u, bl = j + 1 < W ? lo[j + 1] : 0u;
-        const uint32_t ah = j < W ? hi[j] : 0u, bh = j + 1 < W ? hi[j + 1] : 0u;
-        const uint32_t an = j < W ? nm[j] : 0u, bn = j + 1 < W ? nm[j + 1] : 0u;
+        // j < W for every chunk that holds a window; word j + 1 may be the next plane's first word: see plane_bits
+        const uint32_t al = lo[j], bl = lo[j + 1];
+        const uint32_t ah = hi[j], bh = hi[j + 1];
+        const uint32_t an = nm[j], bn = nm[j + 1];
         uint32_t cand = 0;
         const int rem = nwin - (c << 5);
+        if (cfg.bs_ok && rem > 8) {
+            // 32 offsets at once: for every constant position q of the pivot word, bit s of (M >> q) says "offset s
+            // mismatches there" (M = the read's mismatch plane against that position's base, N never mismatches);
+            // the planes add them up.  Counters start at 15 - max_const_err, so plane 16 = "more than the cap".
+            BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
+            bs_base(P, (al | ah) & ~an, (bl | bh) & ~bn, cfg.pv_n[0], cfg.pv_sh4[0]);
+            bs_base(P, (~al | ah) & ~an, (~bl | bh) & ~bn, cfg.pv_n[1], cfg.pv_sh4[1]);
+            bs_base(P, (al | ~ah) & ~an, (bl | ~bh) & ~bn, cfg.pv_n[2], cfg.pv_sh4[2]);
+            bs_base(P, ~(al & ah) & ~an, ~(bl & bh) & ~bn, cfg.pv_n[3], cfg.pv_sh4[3]);
+            cand = ~P.p16;
+        } else {
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
             if (g < rem) {
@@ -233,6 +287,7 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
                 }
             }
         }
+        }
         if (rem < 32) cand &= (1u << rem) - 1u;
         while (cand) {
             const int s = __ffs(cand) - 1;
@@ -241,9 +296,9 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
             uint32_t d = 0, e = 0;
 #pragma unroll
             for (int k = 0; k < TW; k++) {
-                const uint32_t wl = plane_bits(lo, W, o + (k << 5));
-                const uint32_t wh = plane_bits(hi, W, o + (k << 5));
-                const uint32_t wn = plane_bits(nm, W, o + (k << 5));
+                const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
+                const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
+                const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
                 const uint32_t x = ((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k];
                 e |= x | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
                 d += __popc(x & ~wn);
@@ -273,7 +328,7 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
         if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
             uint32_t bad = 0;
 #pragma unroll
-            for (int k = 0; k < TW; k++) bad |= plane_bits(nm, W, off + (k << 5)) & cfg.t_fn[k];
+            for (int k = 0; k < TW; k++) bad |= plane_bits<false>(nm, W, off + (k << 5)) & cfg.t_fn[k];
             if (bad) {
                 off = -1;
                 repaired = false;
@@ -287,14 +342,20 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
 struct SlotBits {
     uint32_t lo, hi, nm;
 };
+template <bool CHECK>
 __device__ __forceinline__ SlotBits slot_bits(const uint32_t* lo, const uint32_t* hi, const uint32_t* nm, uint32_t W,
                                               uint32_t pos, uint32_t len) {
     const uint32_t m = lenmask(len);
     SlotBits b;
-    b.nm = plane_bits(nm, W, pos) & m;
-    b.lo = plane_bits(lo, W, pos) & m & ~b.nm;
-    b.hi = plane_bits(hi, W, pos) & m & ~b.nm;
+    b.nm = plane_bits<CHECK>(nm, W, pos) & m;
+    b.lo = plane_bits<CHECK>(lo, W, pos) & m & ~b.nm;
+    b.hi = plane_bits<CHECK>(hi, W, pos) & m & ~b.nm;
     return b;
+}
+// reference index into its key field: schemes whose whole key fits 63 bits never touch the high word
+__device__ __forceinline__ void key_or_index(Key& key, uint32_t idx, uint32_t shift, uint32_t wide) {
+    if (!wide) key.lo |= (unsigned long long)idx << shift;
+    else key_or(key, idx, shift);
 }
 __device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBits& b) {
     // raw key (N kept as its own symbol, Q14): field = [lo:len][hi:len][nm:len]
@@ -398,24 +459,25 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                 // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
                 // Q6: after a repair the quality string is read from 0, not from the repaired offset.
                 if (cfg.n_qruns) {
-                    // byte sums with whole-word loads: the run is re-aligned to a word boundary with funnel shifts, its
-                    // last word masked with a per-run constant, and dp4a against 0x01010101 adds the four bytes of a
-                    // word.  The packer guarantees every byte >= 33 ('!'); the threshold already includes that offset.
+                    // byte sums with whole-word loads: the first and last word of a run are masked down to the bytes
+                    // that belong to it, dp4a against 0x01010101 adds the four bytes of a word.  The packer guarantees
+                    // every byte >= 33 ('!'); the threshold already includes that offset.
                     const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
                     const uint32_t q0 = repaired ? 0u : (uint32_t)off;
                     for (uint32_t r = 0; r < cfg.n_qruns; r++) {
-                        const DevQRun run = cfg.qruns[r];
-                        const uint32_t a = q0 + run.off;
-                        const uint32_t* w = qw + (a >> 2);
-                        const uint32_t sh = (a & 3u) << 3;
-                        uint32_t sum = 0, prev = w[0];
-                        for (uint32_t k = 1; k < run.n_words; k++) {
-                            const uint32_t cur = w[k];
-                            sum = __dp4a(__funnelshift_r(prev, cur, sh), 0x01010101u, sum);
-                            prev = cur;
+                        const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
+                        const uint32_t wa = a >> 2, wb = e1 >> 2;
+                        const uint32_t ma = 0xFFFFFFFFu << ((a & 3u) << 3), mb = 0xFFFFFFFFu >> ((3u - (e1 & 3u)) << 3);
+                        uint32_t sum;
+                        if (wa == wb) {
+                            sum = __dp4a(qw[wa] & ma & mb, 0x01010101u, 0u);
+                        } else {
+                            sum = __dp4a(qw[wa] & ma, 0x01010101u, 0u);
+#pragma unroll 1  // one or two middle words: an unrolled ladder costs more than the loop
+                            for (uint32_t k = wa + 1; k < wb; k++) sum = __dp4a(qw[k], 0x01010101u, sum);
+                            sum = __dp4a(qw[wb] & mb, 0x01010101u, sum);
                         }
-                        sum = __dp4a(__funnelshift_r(prev, w[run.n_words], sh) & run.tail_mask, 0x01010101u, sum);
-                        if (sum < run.thresh) {
+                        if (sum < cfg.qruns[r].thresh) {
                             status = BC_ST_LOW_QUALITY;
                             break;
                         }
@@ -427,7 +489,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
                         const uint32_t si = cfg.order[oi];
                         const DevSlot& S = cfg.slots[si];
-                        const SlotBits b = slot_bits(lo, hi, nm, W, off + S.offset, S.len);
+                        const SlotBits b = slot_bits<false>(lo, hi, nm, W, off + S.offset, S.len);
                         if (S.mode == MODE_RAW) {
                             key_raw(key, S, b);
                             continue;
@@ -436,8 +498,8 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                         bool defer = false;
                         if (S.mode == MODE_TABLE) {
                             if (b.nm == 0) idx = table_pick(__ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]), S.max_err);
-                            else if (S.n_inline && __popc(b.nm) <= 2) idx = table_lookup_n(aux.tables + S.aux_off, S, b.lo, b.hi, b.nm);
-                            else defer = true;
+                            else if (S.n_inline && (b.nm & (b.nm - 1)) == 0) idx = table_lookup_1n(aux.tables + S.aux_off, S, b.lo, b.hi, b.nm);
+                            else defer = true;  // two or more N in one barcode: k_resolve
                         } else if (S.mode == MODE_HASH) {
                             if (b.nm == 0) idx = hash_exact(aux, S, b.lo, b.hi);
                             if (idx == kFail) {
@@ -456,7 +518,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                             status = S.kind == 'S' ? BC_ST_SAMPLE : BC_ST_COUNTED;
                             break;
                         }
-                        key_or(key, idx, S.key_shift);
+                        key_or_index(key, idx, S.key_shift, cfg.wide);
                     }
                 }
                 if (status == BC_ST_MATCHED) {
@@ -523,31 +585,31 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     make_uint2((uint32_t)(base + tid), (uint32_t)off | (repaired ? 0x10000u : 0u));
         }
     }
-    // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 6-bit field (a warp adds at
-    // most 32 per field), two warp-wide REDUX sums, then per-CTA shared counters and one global atomic per counter
+    // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 8-bit field (a CTA adds at
+    // most 128 per field), two warp-wide REDUX sums, two shared-memory adds per warp, one global atomic per counter
     if (counters) {
-        const uint32_t fa = (status >= 0 && status < 5) ? 1u << (6 * status) : 0u;
-        const uint32_t fb = (status == 5 ? 1u : 0u) | (status == 6 ? 1u << 6 : 0u) | (new_key ? 1u << 12 : 0u) | (new_pair ? 1u << 18 : 0u);
+        const uint32_t fa = (status >= 0 && status < 4) ? 1u << (8 * status) : 0u;
+        const uint32_t fb = (status >= 4 && status < 7 ? 1u << (8 * (status - 4)) : 0u) | (new_key ? 1u << 24 : 0u);
         const uint32_t sa = __reduce_add_sync(0xFFFFFFFFu, fa), sb = __reduce_add_sync(0xFFFFFFFFu, fb);
+        const bool inline_set = (flags & F_INSERT) && tables.has_set;
+        const uint32_t sc = inline_set ? __reduce_add_sync(0xFFFFFFFFu, new_pair ? 1u : 0u) : 0u;
         if (lane == 0) {
-#pragma unroll
-            for (int f = 0; f < 5; f++)
-                if ((sa >> (6 * f)) & 63u) atomicAdd(&s_cnt[f], (sa >> (6 * f)) & 63u);
-#pragma unroll
-            for (int f = 0; f < 4; f++)
-                if ((sb >> (6 * f)) & 63u) atomicAdd(&s_cnt[5 + f], (sb >> (6 * f)) & 63u);
+            if (sa) atomicAdd(&s_cnt[0], sa);
+            if (sb) atomicAdd(&s_cnt[1], sb);
+            if (sc) atomicAdd(&s_cnt[2], sc);
         }
         __syncthreads();
         // status order -> counter order
         if (tid < BC_N_COUNTERS) {
             const int map[BC_N_COUNTERS] = {BC_CNT_MATCHED, BC_CNT_DUPLICATES, BC_CNT_CONSTANT, BC_CNT_LOW_QUALITY,
                                             BC_CNT_SAMPLE,  BC_CNT_COUNTED,    BC_CNT_UNSUPPORTED};
-            if (s_cnt[tid]) atomicAdd(&counters[map[tid]], (unsigned long long)s_cnt[tid]);
+            const uint32_t v = (s_cnt[tid >> 2] >> (8 * (tid & 3))) & 0xFFu;
+            if (v) atomicAdd(&counters[map[tid]], (unsigned long long)v);
         }
-        if (tid == BC_N_COUNTERS && s_cnt[BC_N_COUNTERS] && tables.map.n_entries)
-            atomicAdd(tables.map.n_entries, (unsigned long long)s_cnt[BC_N_COUNTERS]);
-        if (tid == BC_N_COUNTERS + 1 && s_cnt[BC_N_COUNTERS + 1] && tables.set.n_entries)
-            atomicAdd(tables.set.n_entries, (unsigned long long)s_cnt[BC_N_COUNTERS + 1]);
+        if (tid == BC_N_COUNTERS && (s_cnt[1] >> 24) && tables.map.n_entries)
+            atomicAdd(tables.map.n_entries, (unsigned long long)(s_cnt[1] >> 24));
+        if (tid == BC_N_COUNTERS + 1 && s_cnt[2] && tables.set.n_entries)
+            atomicAdd(tables.set.n_entries, (unsigned long long)s_cnt[2]);
     }
 }
 
@@ -666,7 +728,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
         for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
             const uint32_t si = cfg.order[oi];
             const DevSlot& S = cfg.slots[si];
-            const SlotBits b = slot_bits(lo, hi, nm, W, off + S.offset, S.len);  // lane-uniform
+            const SlotBits b = slot_bits<true>(lo, hi, nm, W, off + S.offset, S.len);  // lane-uniform
             if (S.mode == MODE_RAW) {
                 key_raw(key, S, b);
                 continue;

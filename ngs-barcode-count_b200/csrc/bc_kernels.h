@@ -106,6 +106,8 @@ struct FlushStats {  // device-side results of one flush (u64 each)
     unsigned long long overflow;  // != 0: a partition held more distinct keys than the shared-memory table -> global path
     unsigned long long valid;     // records that were not holes
     unsigned long long unique;    // distinct (key, random barcode) pairs
+    unsigned long long max_bin;   // largest partition of the last histogram that asked for it
+    unsigned long long big_items; // items in partitions larger than the limit given to that scan
 };
 enum ReduceMode { RED_DEDUPE = 0, RED_COUNT = 1 };
 uint32_t reduce_fill(bool wide);   // target items per hashed partition
@@ -115,7 +117,12 @@ cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cuda
 // per segment s of bins_per_seg bins: starts = seg_base[s] (0 when nullptr) + exclusive prefix of the segment's histogram,
 // cursor = copy of starts; starts[n_seg * bins_per_seg] = grand total
 cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,
-                            uint32_t* cursor, cudaStream_t stream);
+                            uint32_t* cursor, FlushStats* stats /* nullable: records the largest bin and the items in bins > limit */,
+                            uint32_t limit, cudaStream_t stream);
+// partitions larger than `limit` copied to `out` (stats->n_out counts the items moved)
+cudaError_t launch_gather_big(const ItemView& in, const uint32_t* starts, unsigned long long n_parts, uint32_t limit, const ItemView& out,
+                              FlushStats* stats, cudaStream_t stream);
+uint32_t reduce_capacity(bool wide);  // items a partition may hold for the staged (single pass) reduce
 // One radix level of the hash partitioning: partition p of an item = mulhi(hash(key), P); the level's bin is
 // (p >> shift) & mask, F bins.  seg_starts == nullptr: one segment [0, n_total); else n_seg segments, each split on its
 // own (bins of segment s at bins + s * F).  scatter = false adds to the histogram `bins`; scatter = true moves the
@@ -123,6 +130,8 @@ cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_
 struct SplitLevel {
     unsigned long long P;
     uint32_t shift, mask, F;
+    uint32_t drop_bits;  // hash the key shifted right by this many bits (the random barcode) instead of the whole item
+    unsigned long long salt;  // xor-ed into the key before hashing: an independent partitioning of the same keys
 };
 cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t n_seg,
                          unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, FlushStats* stats, bool count_valid,
@@ -133,7 +142,8 @@ uint32_t split_max_bits();
 //   RED_COUNT : out = (key, sum of weights)
 cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
                           unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
-                          unsigned long long out_cap, FlushStats* stats, cudaStream_t stream);
+                          unsigned long long out_cap, FlushStats* stats, uint32_t skip_over /* > 0: leave larger partitions alone */,
+                          cudaStream_t stream);
 // routed records received from every rank appended to the record buffer at *cursor (then the cursor is bumped)
 cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,
                                    uint32_t n_segments, const RecOut& rec, unsigned long long rec_cap, unsigned long long* cursor,

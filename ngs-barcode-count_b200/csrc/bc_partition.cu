@@ -42,9 +42,12 @@ __global__ void k_bump(unsigned long long* cursor, unsigned long long add) { *cu
 // One CTA per segment of F bins: starts[s * F + b] = seg_base[s] + exclusive prefix of the segment's histogram
 // (seg_base == nullptr: a single segment starting at 0), cursor = copy, starts[n_seg * F] = grand total.
 __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ hist, const uint32_t F, const uint32_t* __restrict__ seg_base,
-                                                  uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor) {
+                                                  uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor, FlushStats* stats,
+                                                  const uint32_t limit) {
     __shared__ uint32_t s_warp[16];
     __shared__ uint32_t s_carry;
+    uint32_t biggest = 0;
+    unsigned long long big_items = 0;
     const uint32_t seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned long long off = (unsigned long long)seg * F;
     if (tid == 0) s_carry = seg_base ? seg_base[seg] : 0u;
@@ -52,6 +55,8 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
     for (uint32_t b0 = 0; b0 < F; b0 += 512) {
         const uint32_t b = b0 + tid;
         const uint32_t v = b < F ? hist[off + b] : 0u;
+        biggest = max(biggest, v);
+        if (v > limit) big_items += v;
         uint32_t x = v;  // inclusive warp scan
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
@@ -70,6 +75,14 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
         __syncthreads();
     }
     if (seg == gridDim.x - 1 && tid == 0) starts[off + F] = s_carry;
+    if (stats) {  // largest bin: the host checks that every partition fits a CTA's key store
+        biggest = __reduce_max_sync(0xFFFFFFFFu, biggest);
+        if (lane == 0 && biggest) atomicMax(&stats->max_bin, (unsigned long long)biggest);
+        if (__any_sync(0xFFFFFFFFu, big_items != 0)) {
+            for (int o = 16; o; o >>= 1) big_items += __shfl_xor_sync(0xFFFFFFFFu, big_items, o);
+            if (lane == 0) atomicAdd(&stats->big_items, big_items);
+        }
+    }
 }
 
 // ---- hash partitioning, one radix level per launch --------------------------------------------------------------
@@ -88,7 +101,10 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
 // merging 8 bytes into it — 2x the DRAM reads, 60 G stores/s); re-reading the tile from L2 for every sweep instead of
 // keeping it in registers (latency-bound at 25-50 % occupancy: 280-550 us for 33 M items).
 __device__ __forceinline__ uint32_t split_digit(unsigned long long lo, unsigned long long hi, const SplitLevel& lv) {
-    const uint32_t p = (uint32_t)__umul64hi(hash_key(Key{lo, hi}), lv.P);
+    // drop_bits > 0: partition by the record without its random barcode, so that a partition holds whole keys
+    Key k = lv.drop_bits ? key_shr(Key{lo, hi}, lv.drop_bits) : Key{lo, hi};
+    k.lo ^= lv.salt;  // the hot partitions set aside by a by-key pass share their hash bits: re-partition them with another hash
+    const uint32_t p = (uint32_t)__umul64hi(hash_key(k), lv.P);
     return (p >> lv.shift) & lv.mask;
 }
 
@@ -322,7 +338,8 @@ __device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t valu
 template <bool WIDE, int MODE>
 __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
-             const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats) {
+             const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats,
+             const uint32_t skip_over) {
     extern __shared__ __align__(16) unsigned char red_smem[];
     __shared__ uint32_t s_nperm, s_warp[kRedThreads / 32];
     __shared__ unsigned long long s_base;
@@ -340,6 +357,7 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     const unsigned long long a = starts ? (unsigned long long)starts[p] : p * chunk;
     const unsigned long long e = starts ? (unsigned long long)starts[p + 1] : min(n_items, a + chunk);
     if (e <= a) return;  // empty partition: nothing to emit
+    if (skip_over && e - a > skip_over) return;  // hot keys: k_gather_big hands this partition to the two-stage path
 
     clear_u32(t.table, kTableSlots, kEmpty32);
     if (MODE == RED_DEDUPE) clear_u32(kw, kKeyCap, 0u);
@@ -494,12 +512,12 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
 template <bool WIDE, int MODE>
 cudaError_t launch_reduce_t(const ItemView& in, const uint32_t* starts, unsigned long long n_items, unsigned long long n_ranges,
                             uint32_t chunk, uint32_t umi_bits, const ItemView& out, unsigned long long out_cap, FlushStats* stats,
-                            cudaStream_t stream) {
+                            uint32_t skip_over, cudaStream_t stream) {
     const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);
     cudaError_t e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    k_reduce<WIDE, MODE><<<(unsigned)n_ranges, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats);
+    k_reduce<WIDE, MODE><<<(unsigned)n_ranges, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats, skip_over);
     return cudaGetLastError();
 }
 
@@ -586,6 +604,7 @@ __global__ void k_insert_items(const Tables tables, const ItemView in, const uns
 
 uint32_t reduce_fill(bool) { return kKeyCap * 3 / 4; }  // mean 1536, sigma 39: the key store is 13 sigma away
 uint32_t reduce_chunk(bool) { return kKeyCap; }
+uint32_t reduce_capacity(bool) { return kKeyCap; }
 uint32_t split_max_bits() { return kSplitMaxBits; }
 
 cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cudaStream_t stream) {
@@ -594,8 +613,8 @@ cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cuda
 }
 
 cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,
-                            uint32_t* cursor, cudaStream_t stream) {
-    k_seg_scan<<<n_seg, 512, 0, stream>>>(hist, bins_per_seg, seg_base, starts, cursor);
+                            uint32_t* cursor, FlushStats* stats, uint32_t limit, cudaStream_t stream) {
+    k_seg_scan<<<n_seg, 512, 0, stream>>>(hist, bins_per_seg, seg_base, starts, cursor, stats, limit);
     return cudaGetLastError();
 }
 
@@ -646,14 +665,38 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
 
 cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
                           unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
-                          unsigned long long out_cap, FlushStats* stats, cudaStream_t stream) {
+                          unsigned long long out_cap, FlushStats* stats, uint32_t skip_over, cudaStream_t stream) {
     if (n_ranges == 0) return cudaSuccess;
     if (n_ranges > 0x7FFFFFFFULL) return cudaErrorInvalidValue;
     if (mode == RED_DEDUPE)
-        return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream)
-                    : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream);
-    return wide ? launch_reduce_t<true, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream)
-                : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, stream);
+        return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
+                    : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
+    return wide ? launch_reduce_t<true, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
+                : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
+}
+
+// partitions larger than `limit` copied, one warp each, to a contiguous buffer (their total is known from the scan)
+__global__ void k_gather_big(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_parts, const uint32_t limit,
+                             const ItemView out, FlushStats* stats) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long p = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5; p < n_parts; p += n_warps) {
+        const uint32_t a = starts[p], e = starts[p + 1];
+        if (e - a <= limit) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&stats->n_out, (unsigned long long)(e - a));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t i = a + lane; i < e; i += 32) {
+            out.lo[base + (i - a)] = in.lo[i];
+            if (in.hi) out.hi[base + (i - a)] = in.hi[i];
+        }
+    }
+}
+
+cudaError_t launch_gather_big(const ItemView& in, const uint32_t* starts, unsigned long long n_parts, uint32_t limit, const ItemView& out,
+                              FlushStats* stats, cudaStream_t stream) {
+    k_gather_big<<<148 * 8, 256, 0, stream>>>(in, starts, n_parts, limit, out, stats);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,

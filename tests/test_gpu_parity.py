@@ -393,13 +393,16 @@ def _count_mode(monkeypatch, mode):
     global-memory tables (the overflow fallback); inline: tables updated read by read inside k_decode."""
     monkeypatch.delenv("BC_FLUSH_GLOBAL", raising=False)
     monkeypatch.delenv("BC_INLINE_COUNT", raising=False)
+    monkeypatch.delenv("BC_FLUSH_TWO_STAGE", raising=False)
     if mode == "global":
         monkeypatch.setenv("BC_FLUSH_GLOBAL", "1")
     elif mode == "inline":
         monkeypatch.setenv("BC_INLINE_COUNT", "1")
+    elif mode == "two_stage":
+        monkeypatch.setenv("BC_FLUSH_TWO_STAGE", "1")
 
 
-@pytest.mark.parametrize("mode", ["deferred", "global", "inline"])
+@pytest.mark.parametrize("mode", ["deferred", "two_stage", "global", "inline"])
 def test_counting_modes_skewed_keys(mode, monkeypatch):
     """What the deferred counting has to survive: one (key, UMI) pair repeated far beyond a partition's table size, one hot
     key with tens of thousands of distinct UMIs, many singleton keys — in several submits, with counters read (= a flush)
@@ -441,7 +444,10 @@ def test_counting_modes_skewed_keys(mode, monkeypatch):
         c = ctr.counters()  # flushes in the deferred modes; later submits must still add up
         assert sum(c.values()) == b
     assert c["matched"] == len(pairs) and c["duplicates"] == len(seqs) - 1 - len(pairs) and c["constant_region"] == 1
-    assert ctr.profile()["flushed_global"] == (1 if mode == "global" else 0)
+    prof = ctr.profile()
+    assert prof["flushed_global"] == (1 if mode == "global" else 0)
+    # the hot key (30000 pairs) does not fit one partition: the default flush has to notice and take two stages
+    assert prof["flush_stages"] == (2 if mode in ("deferred", "two_stage") else 0)
     rows = ctr.finish()
     got = {}
     for lo, hi, cnt in zip(rows["key_lo"], rows["key_hi"], rows["count"]):
@@ -454,7 +460,7 @@ def test_counting_modes_skewed_keys(mode, monkeypatch):
     assert sum(ctr.counters().values()) == 5000
 
 
-@pytest.mark.parametrize("mode", ["global", "inline"])
+@pytest.mark.parametrize("mode", ["two_stage", "global", "inline"])
 @pytest.mark.parametrize("case", ["del3_umi", "example", "sample_raw_two"])
 def test_golden_csv_other_counting_modes(case, mode, tmp_path, monkeypatch):
     """The golden CSV sets through the two non-default counting paths (the default one is test_golden_per_read_and_csv)."""

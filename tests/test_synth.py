@@ -166,6 +166,9 @@ def test_counting_modes_agree_on_workloads(name, tmp_path, monkeypatch):
         monkeypatch.delenv("BC_FLUSH_GLOBAL", raising=False)
         monkeypatch.delenv("BC_INLINE_COUNT", raising=False)
         monkeypatch.delenv("BC_SPLIT_COUNT", raising=False)
+        monkeypatch.delenv("BC_FLUSH_TWO_STAGE", raising=False)
+        if mode == "two_stage":
+            monkeypatch.setenv("BC_FLUSH_TWO_STAGE", "1")
         if mode == "global":
             monkeypatch.setenv("BC_FLUSH_GLOBAL", "1")
         elif mode == "inline":
@@ -189,7 +192,11 @@ def test_counting_modes_agree_on_workloads(name, tmp_path, monkeypatch):
     if p0["dense_table"] and not has_umi:
         pytest.skip("dense inline counting: no deferred path for this scheme")
     assert p0["deferred_count"] == 1 and p0["flushed_global"] == 0
-    for mode in ("global", "inline"):
+    # del3: one stage, its 1000 enriched compounds set aside (3) or not even that (1); the 16 keys of the example files
+    # are all hot (two stages); the Zipf lineage barcodes are in between at this size
+    if has_umi:
+        assert p0["flush_stages"] in {"del3": (1, 3), "example": (2,), "lineage": (2, 3)}[name], p0
+    for mode in ("two_stage", "global", "inline"):
         c1, r1, p1 = result(mode)
         assert c1 == c0, mode
         assert r1.shape == r0.shape and bool((r1 == r0).all()), mode
