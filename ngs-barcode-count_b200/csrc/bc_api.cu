@@ -918,6 +918,11 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
         ctx->rows_valid = false;
     }
     if (getenv("BC_DEBUG_NOINSERT")) flags &= ~(F_INSERT | F_APPEND);  // measurement aid: decode without the table updates
+    {   // quality bytes are read from global memory by default (smaller tile, 12 CTAs per SM); BC_QUAL_STAGED=1 stages
+        // the whole 152-byte rows in shared memory with the planes (the measured-slower variant, kept for A/B runs)
+        const char* qs = getenv("BC_QUAL_STAGED");
+        if (!(qs && qs[0] == '1')) flags |= F_QUAL_GLOBAL;
+    }
     BatchView view{};
     const int staged = stage_batch(ctx, batch, &view);
     if (staged < 0) return staged;

@@ -403,13 +403,16 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     const uint32_t n_tile = (uint32_t)min((unsigned long long)kTile, batch.n_reads - base);
     const uint32_t W = batch.W;
     uint32_t* s_pl = smem;
+    // F_QUAL_GLOBAL: the quality bytes stay in global memory — a read needs only the ~34 bytes under its barcodes, and
+    // without the 152-byte rows the tile is 66 bytes per read instead of 218: 12 CTAs per SM instead of 8
+    const bool q_staged = batch.qual && !(flags & F_QUAL_GLOBAL);
     uint8_t* s_q = reinterpret_cast<uint8_t*>(smem + kTile * batch.plane_stride);
-    uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (batch.qual ? kTile * batch.qual_stride : 0u));
+    uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (q_staged ? kTile * batch.qual_stride : 0u));
 
     if (tid < BC_N_COUNTERS + 2) s_cnt[tid] = 0;
     {
         const uint32_t* g_pl = batch.planes + base * batch.plane_stride;
-        const uint8_t* g_q = batch.qual ? batch.qual + base * batch.qual_stride : nullptr;
+        const uint8_t* g_q = q_staged ? batch.qual + base * batch.qual_stride : nullptr;
         const uint16_t* g_len = batch.read_len + base;
         const uint32_t b_pl = n_tile * batch.plane_stride * 4u, b_q = g_q ? n_tile * batch.qual_stride : 0u, b_len = n_tile * 2u;
         const bool bulk = (((b_pl | b_q | b_len) & 15u) == 0) &&
@@ -462,8 +465,30 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     // byte sums with whole-word loads: the first and last word of a run are masked down to the bytes
                     // that belong to it, dp4a against 0x01010101 adds the four bytes of a word.  The packer guarantees
                     // every byte >= 33 ('!'); the threshold already includes that offset.
-                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
                     const uint32_t q0 = repaired ? 0u : (uint32_t)off;
+                    if (!q_staged) {
+                        const uint32_t* qg = reinterpret_cast<const uint32_t*>(batch.qual + (base + tid) * batch.qual_stride);
+                        for (uint32_t r = 0; r < cfg.n_qruns; r++) {
+                            const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
+                            const uint32_t wa = a >> 2, wb = e1 >> 2;
+                            const uint32_t ma = 0xFFFFFFFFu << ((a & 3u) << 3), mb = 0xFFFFFFFFu >> ((3u - (e1 & 3u)) << 3);
+                            uint32_t sum;
+                            if (wa == wb) {
+                                sum = __dp4a(__ldg(qg + wa) & ma & mb, 0x01010101u, 0u);
+                            } else {
+                                const uint32_t first = __ldg(qg + wa), last = __ldg(qg + wb);
+                                sum = __dp4a(first & ma, 0x01010101u, 0u);
+#pragma unroll 1
+                                for (uint32_t k = wa + 1; k < wb; k++) sum = __dp4a(__ldg(qg + k), 0x01010101u, sum);
+                                sum = __dp4a(last & mb, 0x01010101u, sum);
+                            }
+                            if (sum < cfg.qruns[r].thresh) {
+                                status = BC_ST_LOW_QUALITY;
+                                break;
+                            }
+                        }
+                    } else {
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
                     for (uint32_t r = 0; r < cfg.n_qruns; r++) {
                         const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
                         const uint32_t wa = a >> 2, wb = e1 >> 2;
@@ -481,6 +506,7 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                             status = BC_ST_LOW_QUALITY;
                             break;
                         }
+                    }
                     }
                 }
                 // ---- K2b: barcode correction, sample first then counted barcodes in order (parse.rs:448-507).
@@ -781,15 +807,15 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
     }
 }
 
-size_t decode_smem_bytes(const BatchView& b) {
-    return (size_t)kTile * (b.plane_stride * 4u + (b.qual ? b.qual_stride : 0u) + 2u);
+size_t decode_smem_bytes(const BatchView& b, int flags) {
+    return (size_t)kTile * (b.plane_stride * 4u + ((b.qual && !(flags & F_QUAL_GLOBAL)) ? b.qual_stride : 0u) + 2u);
 }
 
 template <int TW>
 static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                                     unsigned long long* counters, const DecodeOut& out, const RouteOut& route,
                                     const RecOut& rec, const Deferred& deferred, int flags, cudaStream_t stream) {
-    const size_t smem = decode_smem_bytes(batch);
+    const size_t smem = decode_smem_bytes(batch, flags);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_decode<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

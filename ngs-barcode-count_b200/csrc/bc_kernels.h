@@ -51,7 +51,7 @@ struct RecOut {
     const unsigned long long* cursor;      // records appended before this batch (bumped by launch_bump after the batch)
 };
 
-enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8, F_APPEND = 16 };
+enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8, F_APPEND = 16, F_QUAL_GLOBAL = 32 };
 
 // counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
@@ -91,7 +91,7 @@ cudaError_t launch_insert_segments(const Tables& tables, const Key* records, uns
 // move every entry of `src` (hash kinds) into `dst`
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);
 
-size_t decode_smem_bytes(const BatchView& batch);
+size_t decode_smem_bytes(const BatchView& batch, int flags);
 
 // ---- deferred partitioned counting (bc_partition.cu) ---------------------------------------------------------------
 // Items are structure-of-arrays (lo, hi, w): hi == nullptr for keys of at most 63 bits, w == nullptr for weight 1.

@@ -460,11 +460,15 @@ def test_counting_modes_skewed_keys(mode, monkeypatch):
     assert sum(ctr.counters().values()) == 5000
 
 
-@pytest.mark.parametrize("mode", ["two_stage", "global", "inline"])
-@pytest.mark.parametrize("case", ["del3_umi", "example", "sample_raw_two"])
+@pytest.mark.parametrize("mode", ["two_stage", "global", "inline", "qual_staged"])
+@pytest.mark.parametrize("case", ["del3_umi", "example", "sample_raw_two", "example_q20"])
 def test_golden_csv_other_counting_modes(case, mode, tmp_path, monkeypatch):
-    """The golden CSV sets through the two non-default counting paths (the default one is test_golden_per_read_and_csv)."""
+    """The golden CSV sets through the non-default paths: the other counting modes, and the quality bytes staged in
+    shared memory instead of read from global memory (the defaults are covered by test_golden_per_read_and_csv)."""
     _count_mode(monkeypatch, mode)
+    monkeypatch.delenv("BC_QUAL_STAGED", raising=False)
+    if mode == "qual_staged":
+        monkeypatch.setenv("BC_QUAL_STAGED", "1")
     exp, paths = load_golden(case)
     fl = exp["flags"]
     run = make_run(paths, fl)
