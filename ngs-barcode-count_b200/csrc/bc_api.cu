@@ -105,6 +105,7 @@ struct bc_ctx {
     unsigned long long entries_upper = 0;  // host-side upper bound of entries added to either table
     unsigned long long imported_rows = 0;  // rows merged in from other ranks (they add keys without bumping "matched")
     unsigned long long* d_counters = nullptr;  // BC_N_COUNTERS + 2 (then: map entries, set entries)
+    unsigned long long* d_stripes = nullptr;   // k_decode's striped copies of them, folded in after every launch
     // staging for host batches
     Staging staging[2];
     int cur = 0;
@@ -498,6 +499,7 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_send) cudaFree(ctx->d_send);
     if (ctx->d_cursors) cudaFree(ctx->d_cursors);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_stripes) cudaFree(ctx->d_stripes);
     if (ctx->insert_stream) {
         cudaStreamSynchronize(ctx->insert_stream);
         cudaStreamDestroy(ctx->insert_stream);
@@ -838,6 +840,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     // ---- counters and the tables
     CKC(cudaMalloc(&ctx->d_counters, (BC_N_COUNTERS + 2) * sizeof(unsigned long long)));
     CKC(cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 2) * sizeof(unsigned long long), ctx->stream));
+    CKC(cudaMalloc(&ctx->d_stripes, (size_t)kCounterStripes * kCounterStride * sizeof(unsigned long long)));
+    CKC(cudaMemsetAsync(ctx->d_stripes, 0, (size_t)kCounterStripes * kCounterStride * sizeof(unsigned long long), ctx->stream));
     CKC(cudaMalloc(&ctx->d_row_n, sizeof(unsigned long long)));
     const unsigned long long hint = expected_reads ? expected_reads : (1ull << 20);
     int rc;
@@ -937,7 +941,9 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, rec_out(ctx), deferred, flags, ctx->stream));
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, route, rec_out(ctx), deferred,
+                              flags, ctx->stream));
+        if (counters) CK(ctx, launch_fold_counters(ctx->d_stripes, counters, ctx->stream));
     }
     if (!(flags & F_LOCATE_ONLY)) {
         ProfScope p(ctx, BC_K_SCAN);

@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                                                   const int flags) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ unsigned int s_cnt[BC_N_COUNTERS + 2];
 
     const uint32_t tid = threadIdx.x;
     const unsigned long long base = (unsigned long long)blockIdx.x * kTile;
@@ -409,7 +408,6 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     uint8_t* s_q = reinterpret_cast<uint8_t*>(smem + kTile * batch.plane_stride);
     uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (q_staged ? kTile * batch.qual_stride : 0u));
 
-    if (tid < BC_N_COUNTERS + 2) s_cnt[tid] = 0;
     {
         const uint32_t* g_pl = batch.planes + base * batch.plane_stride;
         const uint8_t* g_q = q_staged ? batch.qual + base * batch.qual_stride : nullptr;
@@ -611,32 +609,41 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
                     make_uint2((uint32_t)(base + tid), (uint32_t)off | (repaired ? 0x10000u : 0u));
         }
     }
-    // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 8-bit field (a CTA adds at
-    // most 128 per field), two warp-wide REDUX sums, two shared-memory adds per warp, one global atomic per counter
+    // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 8-bit field, two warp-wide
+    // REDUX sums, then lanes 0..8 each add one counter with a single fire-and-forget RED — no shared memory and no CTA
+    // barrier (a barrier at the end made every warp wait for the CTA's slowest).  The adds go to one of kCounterStripes
+    // copies (by CTA) so that no address sees more than a few thousand of them per launch; k_fold_counters sums the
+    // copies into the context's counters right after the launch.
     if (counters) {
         const uint32_t fa = (status >= 0 && status < 4) ? 1u << (8 * status) : 0u;
         const uint32_t fb = (status >= 4 && status < 7 ? 1u << (8 * (status - 4)) : 0u) | (new_key ? 1u << 24 : 0u);
         const uint32_t sa = __reduce_add_sync(0xFFFFFFFFu, fa), sb = __reduce_add_sync(0xFFFFFFFFu, fb);
         const bool inline_set = (flags & F_INSERT) && tables.has_set;
         const uint32_t sc = inline_set ? __reduce_add_sync(0xFFFFFFFFu, new_pair ? 1u : 0u) : 0u;
-        if (lane == 0) {
-            if (sa) atomicAdd(&s_cnt[0], sa);
-            if (sb) atomicAdd(&s_cnt[1], sb);
-            if (sc) atomicAdd(&s_cnt[2], sc);
-        }
-        __syncthreads();
-        // status order -> counter order
-        if (tid < BC_N_COUNTERS) {
-            const int map[BC_N_COUNTERS] = {BC_CNT_MATCHED, BC_CNT_DUPLICATES, BC_CNT_CONSTANT, BC_CNT_LOW_QUALITY,
-                                            BC_CNT_SAMPLE,  BC_CNT_COUNTED,    BC_CNT_UNSUPPORTED};
-            const uint32_t v = (s_cnt[tid >> 2] >> (8 * (tid & 3))) & 0xFFu;
-            if (v) atomicAdd(&counters[map[tid]], (unsigned long long)v);
-        }
-        if (tid == BC_N_COUNTERS && (s_cnt[1] >> 24) && tables.map.n_entries)
-            atomicAdd(tables.map.n_entries, (unsigned long long)(s_cnt[1] >> 24));
-        if (tid == BC_N_COUNTERS + 1 && s_cnt[2] && tables.set.n_entries)
-            atomicAdd(tables.set.n_entries, (unsigned long long)s_cnt[2]);
+        // lane f < 7: outcome f (status order -> counter order, one nibble each); lane 7 / 8: new map / set entries
+        const uint32_t f = lane;
+        const uint32_t v = f < 4 ? (sa >> (8 * f)) & 0xFFu : f < 7 ? (sb >> (8 * (f - 4))) & 0xFFu : f == 7 ? sb >> 24 : f == 8 ? sc : 0u;
+        const uint32_t dst = f < 7 ? (0x6325140u >> (4 * f)) & 0xFu : BC_N_COUNTERS + (f - 7);
+        static_assert(BC_CNT_MATCHED == 0 && BC_CNT_DUPLICATES == 4 && BC_CNT_CONSTANT == 1 && BC_CNT_LOW_QUALITY == 5 &&
+                          BC_CNT_SAMPLE == 2 && BC_CNT_COUNTED == 3 && BC_CNT_UNSUPPORTED == 6, "counter order");
+        if (f < 9 && v) atomicAdd(&counters[(blockIdx.x % kCounterStripes) * kCounterStride + dst], (unsigned long long)v);
     }
+}
+
+__global__ void k_fold_counters(unsigned long long* __restrict__ stripes, unsigned long long* __restrict__ counters) {
+    const uint32_t t = threadIdx.x;
+    if (t >= BC_N_COUNTERS + 2) return;
+    unsigned long long sum = 0;
+    for (uint32_t s = 0; s < kCounterStripes; s++) {
+        sum += stripes[s * kCounterStride + t];
+        stripes[s * kCounterStride + t] = 0;
+    }
+    if (sum) counters[t] += sum;
+}
+
+cudaError_t launch_fold_counters(unsigned long long* stripes, unsigned long long* counters, cudaStream_t stream) {
+    k_fold_counters<<<1, 32, 0, stream>>>(stripes, counters);
+    return cudaGetLastError();
 }
 
 // ---- k_resolve: one WARP per deferred read.  Redoes the barcode step of that read (parse.rs:439-524) with the

@@ -53,7 +53,10 @@ struct RecOut {
 
 enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8, F_APPEND = 16, F_QUAL_GLOBAL = 32 };
 
-// counters: BC_N_COUNTERS u64 on the device; n_new: entries newly claimed in `table`
+// k_decode adds its outcome counters to striped copies (kCounterStripes x kCounterStride u64: the BC_N_COUNTERS
+// outcomes, then new map / set entries); launch_fold_counters sums them into the BC_N_COUNTERS + 2 counters of the ctx.
+constexpr uint32_t kCounterStripes = 64, kCounterStride = 16;
+cudaError_t launch_fold_counters(unsigned long long* stripes, unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
                           const Deferred& deferred, int flags, cudaStream_t stream);
