@@ -618,6 +618,59 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             const uint32_t i = d.pv_n[b]++;
             d.pv_sh4[b][i >> 2] |= q << (8 * (i & 3));
         }
+        // Static-block variant over two template words: pick the pair (w, w + 1) with the most positions left after
+        // rounding every (word, base) group down to blocks of four (two blocks at most).  Used when it keeps at least
+        // as many positions as the single pivot word has (never a weaker filter than the one it replaces).
+        // Measured: with a single 32-offset chunk per read (CRISPR: 16 windows) the static blocks win (0.513 -> 0.480 ms per
+        // batch: no per-base loop set-up, no remainder code); with two or more chunks (DEL: 65 windows) the per-base
+        // loops over one word win (0.531 vs 0.543 ms: one plane word less to load and combine).  BC_BS_ONE_WORD=1 / =0
+        // force one or the other.
+        const char* no2 = getenv("BC_BS_ONE_WORD");
+        const bool one_chunk = cfg->max_read_len - L + 1 <= 32;
+        const bool want_two = no2 ? no2[0] == '0' : one_chunk;
+        if (d.bs_ok && d.TW >= 2 && want_two) {
+            auto kept = [&](uint32_t w, uint32_t b) {
+                uint32_t n = 0;
+                for (uint32_t q = 0; q < 32; q++)
+                    if (((d.t_cm[w] >> q) & 1u) && ((((d.t_lo[w] >> q) & 1u) | (((d.t_hi[w] >> q) & 1u) << 1)) == b)) n++;
+                return std::min<uint32_t>(n / 4, 2) * 4;
+            };
+            int best2 = -1;
+            uint32_t best_n = 0;
+            for (uint32_t w = 0; w + 1 < d.TW; w++) {
+                uint32_t n = 0;
+                for (uint32_t b = 0; b < 4; b++) n += kept(w, b) + kept(w + 1, b);
+                if (n > best_n) {
+                    best_n = n;
+                    best2 = (int)w;
+                }
+            }
+            if (best2 >= 0 && best_n >= (uint32_t)bestc && best_n >= 16) {
+                d.bs_two = 1;
+                d.pivot = (uint32_t)best2;
+                // no more positions than the single pivot word would have used (the kernel is bound by the alu pipe:
+                // every position is a funnel shift and 2.25 LOP3 per 32 offsets): drop whole blocks beyond that
+                uint32_t blocks[2][4], total = 0;
+                for (uint32_t ww = 0; ww < 2; ww++)
+                    for (uint32_t b = 0; b < 4; b++) total += (blocks[ww][b] = kept(best2 + ww, b) / 4);
+                const uint32_t want = ((uint32_t)bestc + 3) / 4;
+                for (int ww = 1; ww >= 0 && total > want; ww--)
+                    for (int b = 3; b >= 0 && total > want; b--)
+                        while (blocks[ww][b] > 0 && total > want) {
+                            blocks[ww][b]--;
+                            total--;
+                        }
+                for (uint32_t ww = 0; ww < 2; ww++)
+                    for (uint32_t b = 0; b < 4; b++) {
+                        const uint32_t w = best2 + ww, keep = blocks[ww][b] * 4;
+                        d.bs2_n[ww][b] = keep / 4;
+                        uint32_t i = 0;
+                        for (uint32_t q = 0; q < 32 && i < keep; q++)
+                            if (((d.t_cm[w] >> q) & 1u) && ((((d.t_lo[w] >> q) & 1u) | (((d.t_hi[w] >> q) & 1u) << 1)) == b))
+                                d.bs2_sh[ww][b][i++] = q;
+                    }
+            }
+        }
     }
 
     // ---- quality runs (parse.rs:340-374): maximal runs of one region code; a non-constant run is tested only when

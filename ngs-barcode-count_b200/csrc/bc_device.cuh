@@ -65,6 +65,12 @@ struct DevCfg {
     uint32_t bs_ok, bs_k;  // bs_k = 15 - max_const_err: counters start there, overflow into bit 4 <=> too many mismatches
     uint32_t pv_n[4];
     uint32_t pv_sh4[4][8];
+    // static-block variant (bs_two = 1): constant positions of the template words pivot and pivot + 1, per base rounded
+    // DOWN to whole blocks of four (a subset of the positions is still a necessary condition), at most two blocks per
+    // (word, base): bs2_n = blocks, bs2_sh = one shift per u32 so that a funnel shift takes it as a constant operand
+    uint32_t bs_two;
+    uint32_t bs2_n[2][4];
+    uint32_t bs2_sh[2][4][8];
     DevSlot slots[kMaxSlots];
     uint8_t order[kMaxSlots];  // sample first, then counted barcodes in order, then the random barcode
     DevQRun qruns[kMaxQRuns];

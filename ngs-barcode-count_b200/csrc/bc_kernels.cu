@@ -238,6 +238,15 @@ __device__ __forceinline__ void bs_base(BsPlanes& P, uint32_t M0, uint32_t M1, u
     }
 }
 
+// static-block variant: up to two whole blocks of four positions of one (template word, base) group; the shifts sit at
+// fixed constant-bank addresses, so a block is four funnel shifts and the carry-save adds, nothing else
+__device__ __forceinline__ void bs_blocks(BsPlanes& P, uint32_t M0, uint32_t M1, uint32_t n_blocks, const uint32_t* sh) {
+    if (n_blocks > 0)
+        bs_add4(P, __funnelshift_r(M0, M1, sh[0]), __funnelshift_r(M0, M1, sh[1]), __funnelshift_r(M0, M1, sh[2]), __funnelshift_r(M0, M1, sh[3]));
+    if (n_blocks > 1)
+        bs_add4(P, __funnelshift_r(M0, M1, sh[4]), __funnelshift_r(M0, M1, sh[5]), __funnelshift_r(M0, M1, sh[6]), __funnelshift_r(M0, M1, sh[7]));
+}
+
 // ---- K1: locate (parse.rs:89-96, 151-163, 287-313) ----------------------------------------------------------
 // Two predicates per window (Q1): the regex's exact test (a read N in a constant fails, format-N needs ACGT) and
 // the repair's masked Hamming distance (N on either side is a wildcard).  Leftmost exact window wins (P1);
@@ -263,7 +272,33 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
         const uint32_t an = nm[j], bn = nm[j + 1];
         uint32_t cand = 0;
         const int rem = nwin - (c << 5);
-        if (cfg.bs_ok && rem > 8) {
+        if (cfg.bs_two && rem > 8) {
+            // as below, over the constant positions of TWO template words (pivot, pivot + 1), whole blocks only: the
+            // third plane word is at worst the next plane's first word (see plane_bits), its bits beyond every window
+            const uint32_t cl = lo[j + 2], ch = hi[j + 2], cn = nm[j + 2];
+            BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
+            {
+                const uint32_t A0 = (al | ah) & ~an, A1 = (bl | bh) & ~bn, A2 = (cl | ch) & ~cn;
+                bs_blocks(P, A0, A1, cfg.bs2_n[0][0], cfg.bs2_sh[0][0]);
+                bs_blocks(P, A1, A2, cfg.bs2_n[1][0], cfg.bs2_sh[1][0]);
+            }
+            {
+                const uint32_t C0 = (~al | ah) & ~an, C1 = (~bl | bh) & ~bn, C2 = (~cl | ch) & ~cn;
+                bs_blocks(P, C0, C1, cfg.bs2_n[0][1], cfg.bs2_sh[0][1]);
+                bs_blocks(P, C1, C2, cfg.bs2_n[1][1], cfg.bs2_sh[1][1]);
+            }
+            {
+                const uint32_t G0 = (al | ~ah) & ~an, G1 = (bl | ~bh) & ~bn, G2 = (cl | ~ch) & ~cn;
+                bs_blocks(P, G0, G1, cfg.bs2_n[0][2], cfg.bs2_sh[0][2]);
+                bs_blocks(P, G1, G2, cfg.bs2_n[1][2], cfg.bs2_sh[1][2]);
+            }
+            {
+                const uint32_t T0 = ~(al & ah) & ~an, T1 = ~(bl & bh) & ~bn, T2 = ~(cl & ch) & ~cn;
+                bs_blocks(P, T0, T1, cfg.bs2_n[0][3], cfg.bs2_sh[0][3]);
+                bs_blocks(P, T1, T2, cfg.bs2_n[1][3], cfg.bs2_sh[1][3]);
+            }
+            cand = ~P.p16;
+        } else if (cfg.bs_ok && rem > 8) {
             // 32 offsets at once: for every constant position q of the pivot word, bit s of (M >> q) says "offset s
             // mismatches there" (M = the read's mismatch plane against that position's base, N never mismatches);
             // the planes add them up.  Counters start at 15 - max_const_err, so plane 16 = "more than the cap".
