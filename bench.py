@@ -306,7 +306,8 @@ def main():
             roofline["int"] = {"peak_lop3_tops": peaks["lop3"], "peak_popc_tops": peaks["popc"], "peak_shf_tops": peaks["shf"],
                                "windows_per_read": windows,
                                "achieved_window_tests_tera_per_s": windows * per_gpu * args.steps / (dec_ms * 1e-3) / 1e12 if dec_ms else 0.0,
-                               "note": "one pivot test = 3 SHF + 3 LOP3 + 1 POPC + compare (alu pipe); peaks are lane-ops/s"}
+                               "note": "peaks are lane-ops/s of the alu pipe (LOP3, SHF) and of POPC; the pivot prefilter is bit-sliced: per "
+                                       "32 window offsets and constant position one funnel shift + 2.25 LOP3 (carry-save adds), no POPC"}
         except Exception as e:  # the microbenchmark is informational
             roofline["int"] = {"error": str(e)}
 
