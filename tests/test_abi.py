@@ -28,6 +28,21 @@ def test_library_exports_every_declared_symbol():
     assert sorted(bc._PROTOS) == sorted(names)
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the ABI structs have the size the C compiler gives the header's structs (a field added on
+    one side only would shift everything behind it)."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "bc_b200.h"\n#include "bc_host.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bc_slot), sizeof(bc_config), sizeof(bc_batch), '
+                   'sizeof(bc_table), sizeof(bc_profile), sizeof(bc_decode_out), sizeof(bch_args)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(t) for t in (bc.bc_slot, bc.bc_config, bc.bc_batch, bc.bc_table, bc.bc_profile, bc.bc_decode_out, bc.bch_args)]
+    assert got == want
+
+
 def test_cli_binary_exists_and_prints_version():
     import subprocess
     out = subprocess.run([bc.CLI_PATH, "--version"], capture_output=True, text=True)
