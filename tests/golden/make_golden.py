@@ -446,6 +446,13 @@ CASES = {
                            enrich=True),
     "format_n": dict(fmt="ACGTACNNGTAC{6}TTGNCA(5)GG", read_len=48, n=400, min_quality=22.0, merge=False,
                      enrich=False, gen_counted=(1, 5, 6)),
+    # sample barcode + three counted barcodes + random barcode + quality filter, merged and enriched output
+    "del3_sample_umi": dict(fmt="[6]ACGTTGCAGTCCAGTA{8}GATTACAG{8}CCTGAAGT{8}TGCATGCATGCA(10)AGGCTTAC\n",
+                            gen_samples=(4, 6), gen_counted=(3, 10, 8), read_len=120, n=500, min_quality=18.0,
+                            merge=True, enrich=True),
+    # reads far longer than the scheme: more than 64 window offsets (three 32-offset chunks in the GPU locate step)
+    "long_reads": dict(fmt="GTCAGTTACGCATGCA{7}TTGACCAGTGCA{7}CAGGTTCAATGC(8)ACGT\n", gen_counted=(2, 9, 7), read_len=160, n=500,
+                       min_quality=0.0, merge=False, enrich=True),
 }
 
 
