@@ -526,3 +526,35 @@ def test_long_barcode_search_paths(blen, max_err, n_ref, tmp_path):
     c = ctr.counters()
     assert c.pop("unsupported") == 0 and c == orc.counters()
     assert ctr.profile()["launches"]["scan"] >= 1
+
+
+def test_import_rows_merge_without_random_barcode():
+    """The final-merge path of schemes without a random barcode whose key space is too large for a dense table (raw
+    keys): two contexts count half of the reads each, the rows of one are imported into the other (bc_export_rows ->
+    bc_import_rows, what ranks do at the end of a multi-GPU job) and the merged rows must equal one context over all reads."""
+    from ngs_barcode_count_b200.multi import dev_tensor
+    exp, paths = load_golden("sample_raw_two")
+    run = make_run(paths, exp["flags"])
+    reads = read_fastq(paths["fastq"]) * 3  # repeats: counts above one
+    batch = run.pack([r[0] for r in reads], [r[1] for r in reads])
+
+    def rows_of(ctr):
+        rows = ctr.finish()
+        return sorted(zip([int(x) for x in rows["key_hi"]], [int(x) for x in rows["key_lo"]], [int(x) for x in rows["count"]]))
+
+    whole = bc.Counter(run)
+    assert whole.profile()["deferred_count"] == 1 and whole.profile()["dense_table"] == 0
+    whole.submit(batch)
+    want = rows_of(whole)
+    half = batch.n // 2
+    a, b = bc.Counter(run), bc.Counter(run)
+    a.submit(batch.slice(0, half))
+    b.submit(batch.slice(half, batch.n))
+    assert rows_of(a) != want  # flushed once already: the import below has to re-flush with the extra rows
+    lo, hi, cnt, n = b.export_rows()
+    t_lo, t_cnt = dev_tensor(lo, n, "cuda:0"), dev_tensor(cnt, n, "cuda:0")
+    t_hi = dev_tensor(hi, n, "cuda:0") if hi else None
+    a.import_rows(t_lo, t_hi, t_cnt, n)
+    assert rows_of(a) == want
+    ca, cb, cw = a.counters(), b.counters(), whole.counters()
+    assert ca["matched"] + cb["matched"] == cw["matched"] and sum(r[2] for r in want) == cw["matched"]
