@@ -21,6 +21,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -98,12 +99,115 @@ struct FastqBlock {
     int state = 0;  // 0 free (reader may fill), 1 filled (consumer may pack)
 };
 
+// BGZF (bgzip): a gzip file made of independent members of at most 64 KB, each carrying its compressed size in a
+// 'BC' extra subfield (SAM specification, section 4.1).  The member boundaries are known without inflating
+// anything, so the members that fit the caller's buffer are inflated on all host threads at once, each straight to
+// its place in the buffer — the reference's MultiGzDecoder (input.rs:63) inflates them one after the other.
+struct BgzfReader {
+    const unsigned char* data = nullptr;
+    size_t size = 0, pos = 0;
+    int fd = -1;
+    unsigned threads = 1;
+    ~BgzfReader() {
+        if (data) munmap(const_cast<unsigned char*>(data), size);
+        if (fd >= 0) close(fd);
+    }
+    static uint32_t le16(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+    static uint32_t le32(const unsigned char* p) { return le16(p) | (le16(p + 2) << 16); }
+    // total size of the member at p (0: not a BGZF member), and where its deflate stream starts
+    static size_t member(const unsigned char* p, size_t avail, size_t* cdata_off) {
+        if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+        const uint32_t xlen = le16(p + 10);
+        if (12 + (size_t)xlen > avail) return 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const unsigned char* sf = p + 12 + x;
+            const uint32_t slen = le16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) {
+                *cdata_off = 12 + (size_t)xlen;
+                return (size_t)le16(sf + 4) + 1;
+            }
+            x += 4 + slen;
+        }
+        return 0;
+    }
+    bool open(const std::string& path, unsigned n_threads) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 28) return false;
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        data = static_cast<const unsigned char*>(m);
+        size = (size_t)st.st_size;
+        threads = std::max(1u, n_threads);
+        size_t off = 0;
+        return member(data, size, &off) != 0;
+    }
+    // whole members, as many as fit n bytes; 0 at the end of the file, -2 when the next member does not fit
+    long fill(char* dst, size_t n) {
+        struct Blk {
+            size_t in, in_len, out;
+            uint32_t isize, crc;
+        };
+        std::vector<Blk> blks;
+        size_t out = 0, p = pos;
+        while (p < size) {
+            size_t coff = 0;
+            const size_t total = member(data + p, size - p, &coff);
+            if (total == 0 || p + total > size || total < coff + 8) throw Error("corrupt or truncated BGZF member in the input");
+            const uint32_t isize = le32(data + p + total - 4);
+            if (out + isize > n) {
+                if (blks.empty() && out == 0) return -2;  // not even one member fits what is left of the buffer
+                break;
+            }
+            if (isize) blks.push_back(Blk{p + coff, total - coff - 8, out, isize, le32(data + p + total - 8)});
+            out += isize;
+            p += total;
+        }
+        std::atomic<size_t> next{0};
+        std::atomic<int> bad{0};
+        auto work = [&]() {
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) {
+                bad = 1;
+                return;
+            }
+            for (size_t i = next++; i < blks.size(); i = next++) {
+                const Blk& b = blks[i];
+                inflateReset(&z);
+                z.next_in = const_cast<unsigned char*>(data + b.in);
+                z.avail_in = (uInt)b.in_len;
+                z.next_out = reinterpret_cast<unsigned char*>(dst + b.out);
+                z.avail_out = b.isize;
+                const int rc = inflate(&z, Z_FINISH);
+                if (rc != Z_STREAM_END || z.avail_out != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char*>(dst + b.out), b.isize) != b.crc)
+                    bad = 1;
+            }
+            inflateEnd(&z);
+        };
+        const unsigned nt = (unsigned)std::min<size_t>(threads, std::max<size_t>(1, blks.size() / 8));
+        if (nt <= 1) {
+            work();
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+            for (auto& th : pool) th.join();
+        }
+        if (bad) throw Error("inflate failed on a BGZF member (corrupt input?)");
+        pos = p;
+        return (long)out;
+    }
+};
+
 struct FastqStream {
     gzFile gz = nullptr;
     FILE* plain = nullptr;  // not gzip: read straight into the block buffer (no inflate layer, no extra copy)
+    std::unique_ptr<BgzfReader> bgzf;  // bgzip input: members inflated in parallel
     bool eof = false;
     std::vector<char> carry;  // bytes after the last whole record of the previous block
-    FastqStream(const std::string& path) {
+    FastqStream(const std::string& path, unsigned threads = 1) {
         auto ends = [&](const char* suf) {
             const size_t k = strlen(suf);
             return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
@@ -116,6 +220,9 @@ struct FastqStream {
         const size_t got = fread(magic, 1, 2, probe);
         if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
             fclose(probe);
+            bgzf.reset(new BgzfReader());
+            if (bgzf->open(path, threads)) return;
+            bgzf.reset();
             gz = gzopen(path.c_str(), "rb");
             if (!gz) throw Error("Failed to open file: " + path);
             gzbuffer(gz, 4u << 20);
@@ -130,6 +237,7 @@ struct FastqStream {
         if (plain) fclose(plain);
     }
     long fill(char* dst, size_t n) {
+        if (bgzf) return bgzf->fill(dst, n);
         if (plain) return (long)fread(dst, 1, n, plain);
         return gzread(gz, dst, (unsigned)std::min<size_t>(n, 1u << 30));
     }
@@ -144,6 +252,10 @@ struct FastqStream {
         carry.clear();
         while (!eof && B.have < B.buf.size()) {
             const long got = fill(B.buf.data() + B.have, B.buf.size() - B.have);
+            if (got == -2) {  // BGZF: the next member needs more room than is left in this block
+                if (B.have == 0) throw Error("BGZF member larger than the block buffer");
+                break;
+            }
             if (got < 0) throw Error("gzread failed (corrupt input?)");
             if (got == 0) {
                 eof = true;
@@ -876,7 +988,7 @@ int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned 
             return BC_OK;
         }
         for (FastqBlock& B : I.blocks) B.state = 0;
-        FastqStream in(fastq_path);
+        FastqStream in(fastq_path, threads);
         // reader thread: fill + split block i+1 while this thread packs block i
         std::string reader_error;
         bool reader_done = false;

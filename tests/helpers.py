@@ -180,3 +180,22 @@ def assert_same_csv_set(got, want):
             assert canonical_merged(got[fn]) == canonical_merged(want[fn]), fn
         else:
             assert got[fn] == want[fn], fn
+
+
+def bgzf_compress(data, chunk=20000, level=6):
+    """bgzip-style gzip: independent members of at most 64 KB with their compressed size in a 'BC' extra subfield, ended
+    by the empty end-of-file member (SAM specification, section 4.1)."""
+    import struct
+    import zlib
+    out = bytearray()
+    i = 0
+    while True:
+        block = data[i:i + chunk]
+        i += chunk
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        cd = c.compress(block) + c.flush()
+        out += b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(cd) + 25)
+        out += cd + struct.pack("<II", zlib.crc32(block) & 0xFFFFFFFF, len(block))
+        if not block:
+            break
+    return bytes(out)

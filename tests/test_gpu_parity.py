@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import ngs_barcode_count_b200 as bc
-from helpers import (GOLDEN, Oracle, assert_same_csv_set, golden_cases, load_golden, read_csv_dir, read_fastq)
+from helpers import (GOLDEN, Oracle, assert_same_csv_set, bgzf_compress, golden_cases, load_golden, read_csv_dir, read_fastq)
 
 pytestmark = pytest.mark.gpu
 
@@ -101,13 +101,18 @@ def test_golden_fastq_ingest_small_batches(case, tmp_path):
 
 
 @pytest.mark.parametrize("case", ["example", "crispr", "del3_umi", "lineage_raw"])
-@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("gz", [False, True, "bgzf"])
 def test_cli_drop_in(case, gz, tmp_path):
-    """The `barcode-count` binary with the reference's flags writes the reference's CSV set."""
+    """The `barcode-count` binary with the reference's flags writes the reference's CSV set (plain FASTQ, two concatenated
+    gzip members, and bgzip members inflated in parallel)."""
     exp, paths = load_golden(case)
     fl = exp["flags"]
     fastq = paths["fastq"]
-    if gz:
+    if gz == "bgzf":
+        fastq = str(tmp_path / "reads.fastq.gz")
+        with open(fastq, "wb") as f:
+            f.write(bgzf_compress(open(paths["fastq"], "rb").read(), chunk=3000))
+    elif gz:
         import gzip
         fastq = str(tmp_path / "reads.fastq.gz")
         data = open(paths["fastq"], "rb").read()
