@@ -563,3 +563,35 @@ def test_import_rows_merge_without_random_barcode():
     assert rows_of(a) == want
     ca, cb, cw = a.counters(), b.counters(), whole.counters()
     assert ca["matched"] + cb["matched"] == cw["matched"] and sum(r[2] for r in want) == cw["matched"]
+
+
+@pytest.mark.parametrize("case", ["del3_umi", "lineage_raw"])
+def test_decode_route_then_insert_records(case):
+    """The bucket API of hash-routed de-duplication (bc_decode_route -> exchange -> bc_insert_records), with one context
+    playing every owner: decoding into three owner buckets and inserting the buckets must give what bc_submit gives."""
+    import torch
+    exp, paths = load_golden(case)
+    run = make_run(paths, exp["flags"])
+    reads = read_fastq(paths["fastq"])
+    batch = run.pack([r[0] for r in reads], [r[1] for r in reads])
+
+    def rows_of(ctr):
+        rows = ctr.finish()
+        return sorted(zip([int(x) for x in rows["key_hi"]], [int(x) for x in rows["key_lo"]], [int(x) for x in rows["count"]]))
+
+    direct = bc.Counter(run)
+    direct.submit(batch)
+    routed = bc.Counter(run)
+    n_ranks, cap = 3, batch.n
+    buckets = torch.zeros((n_ranks, cap, 2), dtype=torch.int64, device="cuda:0")
+    counts = torch.zeros(n_ranks, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()  # the context works on its own stream
+    routed.decode_route(batch, n_ranks, buckets, cap, counts)
+    routed.sync()
+    got_counts = counts.cpu().tolist()
+    assert sum(got_counts) == exp["counters"]["matched"] + exp["counters"]["duplicates"]
+    for r in range(n_ranks):
+        routed.insert_records(buckets[r], got_counts[r])
+    c0, c1 = direct.counters(), routed.counters()
+    assert c0 == c1 and {k: v for k, v in c0.items() if k != "unsupported"} == exp["counters"]
+    assert rows_of(routed) == rows_of(direct)
