@@ -52,6 +52,13 @@ int bch_pack(uint32_t max_read_len, uint32_t n, const char *const *seqs, const c
 int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, const char *qual_lines, uint32_t *planes_out,
                    uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
 
+/* Host-only test hook of the record framing (input.rs:115-148): streams a .fastq / .fastq.gz file (plain, gzip with any
+ * number of members, or bgzip — whose members are inflated on `threads` host threads) through the same block reader
+ * bch_count_fastq uses and reports the number of records, of bases, and the CRC-32 of every record's sequence and
+ * quality bytes in file order.  No GPU work. */
+int bch_scan_fastq(const char *fastq_path, unsigned threads, uint64_t *n_records, uint64_t *n_bases, uint32_t *crc, char *err,
+                   int errlen);
+
 /* input::read_fastq replacement: streams a .fastq / .fastq.gz file through pinned double-buffered batches of
  * `batch_reads` reads into ctx (bc_submit).  threads = host threads used for packing.  Returns BC_OK and the
  * number of records. */

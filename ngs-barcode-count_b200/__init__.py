@@ -69,6 +69,16 @@ class bc_profile(C.Structure):
                 ("deferred_count", C.c_uint32), ("flushed_global", C.c_uint32), ("flush_stages", C.c_uint32)]
 
 
+def scan_fastq(path, threads=0):
+    """(records, bases, crc32 of all sequence + quality bytes) of a FASTQ file read by the library's block reader (host only)."""
+    n, b, c = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    err = C.create_string_buffer(512)
+    rc = lib().bch_scan_fastq(os.fsencode(path), threads, C.byref(n), C.byref(b), C.byref(c), err, 512)
+    if rc != 0:
+        raise BcError("bch_scan_fastq: " + err.value.decode())
+    return int(n.value), int(b.value), int(c.value)
+
+
 class bch_args(C.Structure):
     _fields_ = [("format_path", C.c_char_p), ("sample_barcodes_path", C.c_char_p), ("counted_barcodes_path", C.c_char_p),
                 ("max_errors_counted_barcode", C.c_int), ("max_errors_sample", C.c_int), ("max_errors_constant", C.c_int),
@@ -120,6 +130,8 @@ _PROTOS = {
     "bch_pack": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_uint]),
     "bch_pack_lines": (C.c_int, [C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "bch_scan_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p,
+                                 C.c_int]),
     "bch_count_fastq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint, C.c_uint32, C.POINTER(C.c_uint64), C.c_char_p,
                                   C.c_int]),
     "bch_write_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,

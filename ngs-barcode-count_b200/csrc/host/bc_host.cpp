@@ -842,6 +842,34 @@ int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char* seq_lines, con
     return pack_refs(max_read_len, refs, 0, n, planes_out, read_len_out, qual_lines ? qual_out : nullptr, threads);
 }
 
+int bch_scan_fastq(const char* fastq_path, unsigned threads, uint64_t* n_records, uint64_t* n_bases, uint32_t* crc, char* err,
+                   int errlen) {
+    if (!fastq_path) return BC_EINVAL;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    try {
+        FastqStream in(fastq_path, threads);
+        FastqBlock B;
+        B.buf.resize(8u << 20);
+        uint64_t recs = 0, bases = 0;
+        uLong c = crc32(0L, Z_NULL, 0);
+        while (in.next_block(B, 1u << 20)) {
+            for (const ReadRef& r : B.recs) {
+                c = crc32(c, reinterpret_cast<const unsigned char*>(r.seq), r.len);
+                c = crc32(c, reinterpret_cast<const unsigned char*>(r.qual), r.qlen);
+                bases += r.len;
+            }
+            recs += B.recs.size();
+        }
+        if (n_records) *n_records = recs;
+        if (n_bases) *n_bases = bases;
+        if (crc) *crc = (uint32_t)c;
+        return BC_OK;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return BC_EINVAL;
+    }
+}
+
 int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads,
                     uint64_t* total_reads, char* err, int errlen) {
     auto report = [&](const std::string& m) {

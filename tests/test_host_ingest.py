@@ -1,0 +1,78 @@
+"""CPU tests of the FASTQ block reader (host side of bch_count_fastq, reached through the bch_scan_fastq test hook):
+plain text, gzip with one and with several members, and bgzip (BGZF) input whose members are inflated in parallel must
+all yield the same records, in file order (input.rs:24-89, 115-148)."""
+import gzip
+import random
+import zlib
+
+import pytest
+
+import ngs_barcode_count_b200 as bc
+from helpers import bgzf_compress
+
+
+def make_fastq(n, seed, crlf=False, last_newline=True):
+    rng = random.Random(seed)
+    recs, crc, bases = [], zlib.crc32(b""), 0
+    eol = "\r\n" if crlf else "\n"
+    for i in range(n):
+        length = rng.randint(1, 151)
+        seq = "".join(rng.choice("ACGTN") for _ in range(length))
+        qual = "".join(chr(33 + rng.randint(0, 41)) for _ in range(length))
+        recs.append(f"@read{i} extra{eol}{seq}{eol}+{eol}{qual}{eol}")
+        crc = zlib.crc32(qual.encode(), zlib.crc32(seq.encode(), crc))
+        bases += length
+    text = "".join(recs)
+    if not last_newline:
+        text = text[:-len(eol)]
+    return text.encode(), (n, bases, crc)
+
+
+@pytest.mark.parametrize("crlf,last_newline", [(False, True), (True, True), (False, False)])
+def test_block_reader_plain_gzip_bgzip_agree(tmp_path, crlf, last_newline):
+    data, want = make_fastq(30000, 5, crlf=crlf, last_newline=last_newline)
+    plain = tmp_path / "r.fastq"
+    plain.write_bytes(data)
+    assert bc.scan_fastq(str(plain)) == want
+    one = tmp_path / "one.fastq.gz"
+    one.write_bytes(gzip.compress(data))
+    assert bc.scan_fastq(str(one)) == want
+    cut = data.find(b"\n@read", len(data) // 3) + 1
+    two = tmp_path / "two.fastq.gz"
+    two.write_bytes(gzip.compress(data[:cut]) + gzip.compress(data[cut:]))  # MultiGzDecoder semantics (input.rs:63)
+    assert bc.scan_fastq(str(two)) == want
+    for chunk, threads in ((700, 1), (3000, 3), (65280, 8), (20000, 0)):
+        bg = tmp_path / f"bg{chunk}.fastq.gz"
+        bg.write_bytes(bgzf_compress(data, chunk=chunk))
+        assert bc.scan_fastq(str(bg), threads=threads) == want, (chunk, threads)
+
+
+def test_block_reader_large_bgzip_spans_blocks(tmp_path):
+    """More than the reader's 8 MB block: members are consumed block by block, records straddle block boundaries."""
+    data, want = make_fastq(120000, 9)
+    assert len(data) > (8 << 20)
+    bg = tmp_path / "big.fastq.gz"
+    bg.write_bytes(bgzf_compress(data, chunk=60000, level=1))
+    assert bc.scan_fastq(str(bg), threads=4) == want
+
+
+def test_block_reader_rejects_corrupt_bgzip(tmp_path):
+    data, _ = make_fastq(5000, 3)
+    blob = bytearray(bgzf_compress(data, chunk=10000))
+    bad = tmp_path / "bad.fastq.gz"
+    flipped = bytearray(blob)
+    flipped[len(flipped) // 2] ^= 0x55  # inside a deflate stream: inflate or the CRC has to notice
+    bad.write_bytes(bytes(flipped))
+    with pytest.raises(bc.BcError):
+        bc.scan_fastq(str(bad), threads=2)
+    trunc = tmp_path / "trunc.fastq.gz"
+    trunc.write_bytes(bytes(blob[:len(blob) // 2]))
+    with pytest.raises(bc.BcError):
+        bc.scan_fastq(str(trunc), threads=2)
+
+
+def test_block_reader_rejects_other_extensions(tmp_path):
+    p = tmp_path / "reads.txt"
+    p.write_bytes(b"@r\nACGT\n+\nIIII\n")
+    with pytest.raises(bc.BcError, match="only works with"):
+        bc.scan_fastq(str(p))
