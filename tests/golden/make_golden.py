@@ -450,6 +450,13 @@ CASES = {
     "del3_sample_umi": dict(fmt="[6]ACGTTGCAGTCCAGTA{8}GATTACAG{8}CCTGAAGT{8}TGCATGCATGCA(10)AGGCTTAC\n",
                             gen_samples=(4, 6), gen_counted=(3, 10, 8), read_len=120, n=500, min_quality=18.0,
                             merge=True, enrich=True),
+    # reference barcodes of mixed lengths (shorter and longer than their slot, Q10) and with N in them: the whole-set
+    # search with fix_error's "N never counts" rule on both sides (parse.rs:568-577)
+    "refs_mixed_n": dict(fmt="[6]ACGTACGGTCAGT{9}TTGACCAT(6)GGCA\n",
+                         sample_text="Barcode,Sample_ID\nACGTAC,s1\nTTGCAN,s2\nGGATCCA,s3\n",
+                         counted_text="Barcode,Barcode_ID,Barcode_Number\nACGTTGCAA,b1,1\nTTGACNGTA,b2,1\nGGCATCAG,b3,1\n"
+                                      "CATGGTACCA,b4,1\nAGTCAGTCA,b5,1\nNNGTCATGA,b6,1\nTCAGGTCAGTT,b7,1\n",
+                         read_len=60, n=500, min_quality=0.0, merge=True, enrich=False),
     # reads far longer than the scheme: more than 64 window offsets (three 32-offset chunks in the GPU locate step)
     "long_reads": dict(fmt="GTCAGTTACGCATGCA{7}TTGACCAGTGCA{7}CAGGTTCAATGC(8)ACGT\n", gen_counted=(2, 9, 7), read_len=160, n=500,
                        min_quality=0.0, merge=False, enrich=True),
@@ -485,7 +492,7 @@ def main():
             counted_text = open(os.path.join(HERE, "example", "barcodes.csv")).read()
         else:
             fmt_text = c["fmt"]
-            sample_text = counted_text = None
+            sample_text, counted_text = c.get("sample_text"), c.get("counted_text")
             if "gen_samples" in c:
                 n, ln = c["gen_samples"]
                 sample_text = "Barcode,Sample_ID\n" + "".join(
