@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BC_ABI_VERSION 1
+#define BC_ABI_VERSION 2
 #define BC_MAX_SLOTS 16        /* sample + counted + random barcodes in one scheme */
 #define BC_MAX_TEMPLATE 256    /* template (format_string) length limit, bases */
 #define BC_MAX_READ_LEN 1024   /* read length limit, bases */
@@ -93,13 +93,20 @@ typedef struct {
     uint16_t max_const_err;      /* MaxSeqErrors::max_constant_errors (info.rs:527-531) */
     float min_quality;           /* --min-quality; 0 disables the filter (parse.rs:98) */
     uint32_t max_read_len;       /* longest read any batch will carry */
+    uint32_t flags;              /* BC_CFG_* (0 for production use) */
 } bc_config;
+
+/* bc_config.flags.  BC_CFG_INLINE_COUNT: update global hash tables read by read inside the decode kernel instead of
+ * appending records and counting them at the flush (measurement aid: the design the deferred flush replaced). */
+#define BC_CFG_INLINE_COUNT 1u
 
 enum { BC_LOC_HOST = 0, BC_LOC_DEVICE = 1 };
 
 /* Fixed-stride packed batch of reads.
- *   planes  : n_reads records of `plane_stride` u32 words.  A record holds three bit planes of W =
- *             bc_plane_words(max_read_len) words each — lo, hi, nmask — base i at bit (i & 31) of word (i >> 5):
+ *   planes  : n_reads records of `plane_stride` u32 words.  A record holds three bit planes of W words each — lo, hi,
+ *             nmask — base i at bit (i & 31) of word (i >> 5); W = plane_stride / 3 is the batch's own geometry
+ *             (reads of up to 32 W bases): normally bc_plane_words(cfg.max_read_len), wider for a batch that holds a
+ *             longer read (up to BC_MAX_READ_LEN) —
  *             A=(0,0) C=(1,0) G=(0,1) T=(1,1) as (lo,hi); nmask=1 where the read has 'N' (then lo=hi=0).
  *             Bits at and beyond the read length are 0.  plane_stride = bc_plane_stride(max_read_len) (3W, made odd).
  *   read_len: bases per read; bit 15 (BC_READ_UNSUPPORTED) set when the read held a character outside ACGTN or a
@@ -128,6 +135,7 @@ typedef struct bc_ctx bc_ctx;
  * (info.rs:678-732, 40-49).  expected_reads sizes the device tables (they grow on demand; 0 = small default). */
 int bc_create(const bc_config *cfg, int device, uint64_t expected_reads, bc_ctx **out);
 void bc_destroy(bc_ctx *ctx);
+int bc_device_of(const bc_ctx *ctx); /* the CUDA device the context was created on */
 /* Message of the last failure on `ctx`; ctx == NULL gives the last bc_create failure of this thread. */
 const char *bc_last_error(const bc_ctx *ctx);
 
@@ -143,6 +151,11 @@ int bc_sync(bc_ctx *ctx);
 /* Blocks until the host->device copies of every submitted host batch are done (their memory may then be
  * rewritten) without waiting for the kernels. */
 int bc_wait_copies(bc_ctx *ctx);
+
+/* Test / measurement switches of the counting step (results never change): "flush_global" = 1 sends the flush through
+ * the global-memory hash tables (the fallback of oversized partitions), "flush_two_stage" = 1 always partitions by
+ * (key, random barcode) first (the path of hot keys). */
+int bc_set_option(bc_ctx *ctx, const char *name, int value);
 
 /* SequenceErrors (info.rs:16-23) so far, BC_CNT_* order.  Synchronises. */
 int bc_get_counters(bc_ctx *ctx, uint64_t out[BC_N_COUNTERS]);
@@ -186,8 +199,13 @@ void bc_table_free(bc_table *t);
 int bc_finish(bc_ctx *ctx, bc_table *rows);
 
 /* Replaces ResultsEnrichment::add_single / add_double (info.rs:840-904) over the final table: marginal sums
- * over one and over two counted barcodes, per sample.  `doubles` may be NULL. */
+ * over one and over two counted barcodes, per sample.  `doubles` may be NULL.  With index-coded barcodes all
+ * marginals are dense counter arrays filled in one pass over the rows. */
 int bc_enrich(bc_ctx *ctx, bc_table *singles, bc_table *doubles);
+/* The dense marginal counters of this context's rows (computed on first use): *dev_counters / *n give the device
+ * array (u64 each), or NULL / 0 when the scheme has raw barcodes (no dense index space).  Ranks of a multi-GPU job
+ * whose rows are partitioned by key sum these arrays (all-reduce, or bc_peer_add) before one of them calls bc_enrich. */
+int bc_marginals(bc_ctx *ctx, uint64_t **dev_counters, uint64_t *n);
 
 /* Decode a key: per slot (scheme order) either the reference index or, for raw slots, the DNA string.
  * with_umi = 0 for table rows (bc_finish / bc_enrich: the random barcode is not part of the key), 1 for the
@@ -197,33 +215,45 @@ int bc_enrich(bc_ctx *ctx, bc_table *singles, bc_table *doubles);
 int bc_key_decode(const bc_ctx *ctx, uint64_t key_lo, uint64_t key_hi, uint32_t mask, int with_umi, int32_t *idx_out,
                   char *str_out, uint32_t str_stride);
 
-/* ---- multi-GPU (one process per GPU; the caller owns the communicator, e.g. torch.distributed/NCCL) ----------
- * Without a random barcode each rank counts its own reads and the tables are merged at the end:
- * bc_export_rows gives device-resident (key_lo,key_hi,count) arrays to all-gather, bc_import_rows adds them.
- * With a random barcode, de-duplication must be global: bc_decode_route decodes a batch and writes the
- * (key,UMI) records of matched reads into n_ranks device buckets by owner = hash(key) % n_ranks instead of
- * inserting them; after the all-to-all the owner calls bc_insert_records. */
-typedef struct {
-    uint64_t lo, hi;
-} bc_record;
-int bc_decode_route(bc_ctx *ctx, const bc_batch *batch, uint32_t n_ranks, bc_record *dev_buckets,
-                    uint64_t bucket_capacity, uint32_t *dev_bucket_counts);
-int bc_insert_records(bc_ctx *ctx, const bc_record *dev_records, uint64_t n);
-
-/* Fused routing (one process per GPU on one NVLink/NVSwitch box, at most 8 ranks): the decode kernel stores every
- * matched (key, UMI) record straight into its owner's receive region over NVLink peer memory — no bucket + copy
- * step.  Each rank opens its receive buffer (2 parities x n_ranks sources x capacity records) and gets a
- * BC_IPC_HANDLE_BYTES handle; the caller exchanges the handles (any transport) and passes all of them, rank order,
- * to bc_route_connect.  Per batch: bc_route_submit(parity = batch index & 1) decodes and routes, leaving in
- * dev_counts[r] the number of records sent to rank r; the caller all-gathers the counts (that collective is also the
- * barrier that makes the peer stores visible) and hands the owner the counts of what it received:
- * dev_counts_from[s * count_stride] records from source rank s.  expected_records bounds the table growth check. */
+/* ---- multi-GPU: reads shard over the GPUs of one box; every rank (one bc_ctx per GPU, in one process or one process
+ * per GPU) decodes its own shard with bc_submit.  What follows the last batch depends on the counting state:
+ *
+ *  dense count table (small index-coded key space without a random barcode, e.g. a CRISPR screen): ranks sum their
+ *    tables once — bc_dense_counts + an all-reduce, or bc_peer_add inside one process.
+ *
+ *  hashed keys (any scheme with a random barcode, raw or large key spaces): ONE exchange of the (key[, UMI]) records.
+ *    record -> owner = hash(key without the random barcode) % n_ranks; the partitioning kernel writes each record
+ *    straight into its owner's receive buffer over NVLink peer memory, and every owner then de-duplicates and counts
+ *    the keys it owns, so de-duplication is globally exact.  Afterwards a rank's rows are
+ *    its owned keys (disjoint across ranks), its matched / duplicates counters are those of the records it owns and
+ *    its other counters those of the reads it decoded: every statistic sums over ranks to the single-GPU value.
+ *
+ *    set-up   bc_exchange_open(capacity)  this rank's receive buffer, in records; the same capacity on every rank
+ *             one process per GPU: bc_exchange_handle -> caller exchanges the BC_IPC_HANDLE_BYTES handles ->
+ *                                  bc_exchange_connect(all handles, rank order)
+ *             one process:         bc_exchange_connect_local(all contexts, rank order)
+ *    per job  bc_exchange_count   -> sent[r] = records of this rank owned by rank r (synchronises)
+ *             caller: all-gather the n_ranks x n_ranks matrix; first[r] = sum of sent[r] of the ranks before this one;
+ *                     received = sum over ranks of what they send to this one; if any rank's total exceeds the
+ *                     capacity, every rank re-opens larger and reconnects
+ *             bc_exchange_scatter(first)  asynchronous on the ctx stream
+ *             caller: a barrier ordered after every rank's scatter (a collective on the same stream, or stream syncs)
+ *             bc_exchange_finish(received)
+ *    Until bc_exchange_finish, bc_get_counters / bc_finish on a rank of a multi-GPU job fail with BC_ESTATE. */
 #define BC_IPC_HANDLE_BYTES 64
-int bc_route_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity, void *ipc_handle_out);
-int bc_route_connect(bc_ctx *ctx, const void *ipc_handles);
-int bc_route_submit(bc_ctx *ctx, const bc_batch *batch, uint32_t parity, uint32_t *dev_counts);
-int bc_route_insert(bc_ctx *ctx, uint32_t parity, const uint32_t *dev_counts_from, uint32_t count_stride,
-                    uint64_t expected_records);
+int bc_exchange_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity);
+int bc_exchange_handle(bc_ctx *ctx, void *ipc_handle_out);
+int bc_exchange_connect(bc_ctx *ctx, const void *ipc_handles);
+int bc_exchange_connect_local(bc_ctx *ctx, bc_ctx *const *ranks);
+int bc_exchange_count(bc_ctx *ctx, uint64_t *sent);
+int bc_exchange_scatter(bc_ctx *ctx, const uint64_t *first);
+int bc_exchange_finish(bc_ctx *ctx, uint64_t n_received);
+/* One process, several contexts: dst += src for the dense count table (BC_ADD_DENSE_COUNTS) or the dense marginals
+ * (BC_ADD_MARGINALS); src may be on another GPU.  Both contexts must be idle.  Synchronises dst. */
+enum { BC_ADD_DENSE_COUNTS = 0, BC_ADD_MARGINALS = 1 };
+int bc_peer_add(bc_ctx *dst, bc_ctx *src, int what);
+/* Without a random barcode and without a dense table, rows can also be merged explicitly: bc_export_rows gives
+ * device-resident (key_lo, key_hi, count) arrays, bc_import_rows adds such rows to this rank's. */
 int bc_export_rows(bc_ctx *ctx, uint64_t **dev_key_lo, uint64_t **dev_key_hi, uint64_t **dev_count, uint64_t *n_rows);
 int bc_import_rows(bc_ctx *ctx, const uint64_t *dev_key_lo, const uint64_t *dev_key_hi, const uint64_t *dev_count,
                    uint64_t n_rows);
@@ -235,7 +265,8 @@ int bc_add_counters(bc_ctx *ctx, const uint64_t add[BC_N_COUNTERS]);
 int bc_reset(bc_ctx *ctx); /* clear tables and counters, keep configuration */
 
 /* ---- measurement ------------------------------------------------------------------------------------------ */
-enum { BC_K_DECODE = 0, BC_K_SCAN = 1, BC_K_INSERT = 2, BC_K_FINISH = 3, BC_K_OTHER = 4, BC_N_KERNELS = 5 };
+enum { BC_K_DECODE = 0, BC_K_SCAN = 1, BC_K_INSERT = 2, BC_K_FINISH = 3, BC_K_OTHER = 4, BC_K_ENRICH = 5, BC_K_EXCHANGE = 6,
+       BC_N_KERNELS = 7 };
 typedef struct {
     uint64_t launches[BC_N_KERNELS];
     double ms[BC_N_KERNELS]; /* CUDA-event time on the ctx stream, only while profiling is on */

@@ -44,8 +44,10 @@ const char *bch_ref_dna(const bch_run *run, uint32_t slot, uint32_t i);
 const char *bch_ref_name(const bch_run *run, uint32_t slot, uint32_t i);
 
 /* Packs n reads (text) into caller-provided batch arrays sized with bc_plane_stride / bc_qual_stride.
- * quals may be NULL (then qual_out is not touched).  Reads longer than max_read_len give BC_EINVAL; a quality
- * string whose length differs from its sequence gives BC_EINVAL.  threads <= 1 packs on the calling thread. */
+ * quals may be NULL (then qual_out is not touched).  Reads longer than max_read_len give BC_EINVAL (the caller chose
+ * the geometry).  A quality string shorter than its sequence is packed so that the filter behaves as the reference's
+ * zip of scores and region codes does (parse.rs:338-343: a barcode run the string does not outlast is never tested);
+ * a longer one is cut at the sequence length.  threads <= 1 packs on the calling thread. */
 int bch_pack(uint32_t max_read_len, uint32_t n, const char *const *seqs, const char *const *quals, uint32_t *planes_out,
              uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
 /* Same, for reads given as one '\n'-separated text block each (convenient from ctypes). */
@@ -59,17 +61,38 @@ int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, con
 int bch_scan_fastq(const char *fastq_path, unsigned threads, uint64_t *n_records, uint64_t *n_bases, uint32_t *crc, char *err,
                    int errlen);
 
+/* Host-only test hook of the plain-file path of bch_count_fastq: the file is mapped and cut into blocks of block_bytes
+ * (0: 64 MB) that `threads` host threads split into records slice by slice (a slice is at least min_slice_bytes, 0:
+ * 64 KB as in bch_count_fastq); reports like bch_scan_fastq.  No GPU work. */
+int bch_split_fastq(const char *fastq_path, unsigned threads, size_t block_bytes, size_t min_slice_bytes, uint64_t *n_records,
+                    uint64_t *n_bases, uint32_t *crc, char *err, int errlen);
+
 /* input::read_fastq replacement: streams a .fastq / .fastq.gz file through pinned double-buffered batches of
- * `batch_reads` reads into ctx (bc_submit).  threads = host threads used for packing.  Returns BC_OK and the
- * number of records. */
+ * `batch_reads` reads into ctx (bc_submit).  threads = host threads (a pool kept by the run) that split and pack.
+ * Reads of any length up to BC_MAX_READ_LEN are decoded: a batch that holds a read longer than the run's
+ * max_read_len is packed with a wider stride (the reference has no length limit, input.rs:115-148); longer reads
+ * still are counted, as unsupported.  Returns BC_OK and the number of records. */
 int bch_count_fastq(bch_run *run, bc_ctx *ctx, const char *fastq_path, unsigned threads, uint32_t batch_reads,
                     uint64_t *total_reads, char *err, int errlen);
+
+/* The same over several GPUs in one process — one context per GPU, all created from bch_config(run): batches go to
+ * the contexts in turn (pinned staging buffers on each GPU's own NUMA node); after the last batch the contexts merge as
+ * SURVEY.md section 8(e) prescribes: hashed keys through one exchange of the records over NVLink peer memory
+ * (bc_exchange_*: every context then owns a disjoint set of keys), a dense count table by adding the tables into
+ * ctxs[0].  bch_counters_multi / bch_write_counts_multi then read the merged result. */
+int bch_count_fastq_multi(bch_run *run, bc_ctx *const *ctxs, int n_ctx, const char *fastq_path, unsigned threads,
+                          uint32_t batch_reads, uint64_t *total_reads, char *err, int errlen);
+int bch_counters_multi(bc_ctx *const *ctxs, int n_ctx, uint64_t out[BC_N_COUNTERS]);
 
 /* WriteFiles::write_counts_files: per-sample count CSVs, merged CSV, Single/Double enrichment CSVs, same names
  * and layout as the reference; rows are written sorted.  names_out receives one "file name<TAB>barcode rows" line
  * per file written (what the reference keeps for its stats file, output.rs:143-165).  Returns the number of files. */
 int bch_write_counts(bch_run *run, bc_ctx *ctx, const char *output_dir, const char *prefix, int merge_output, int enrich,
                      char *names_out, int names_len, char *err, int errlen);
+/* After bch_count_fastq_multi: the rows of every owner form one table (output.rs:74-181); enrichment marginals of the
+ * owners are summed (on the device when they are dense counter arrays). */
+int bch_write_counts_multi(bch_run *run, bc_ctx *const *ctxs, int n_ctx, const char *output_dir, const char *prefix,
+                           int merge_output, int enrich, char *names_out, int names_len, char *err, int errlen);
 
 #ifdef __cplusplus
 }

@@ -16,15 +16,17 @@ ROOT = os.path.dirname(PKG)
 LIB_PATH = os.path.join(PKG, "lib", "libbc_b200.so")
 CLI_PATH = os.path.join(PKG, "bin", "barcode-count")
 
-BC_ABI_VERSION = 1
+BC_ABI_VERSION = 2
 BC_MAX_SLOTS = 16
 BC_N_COUNTERS = 7
-BC_N_KERNELS = 5
+BC_N_KERNELS = 7
 BC_LOC_HOST, BC_LOC_DEVICE = 0, 1
 BC_READ_UNSUPPORTED = 0x8000
 STATUS_NAMES = ["matched", "duplicate", "constant_region", "low_quality", "sample_barcode", "barcode", "unsupported"]
 COUNTER_NAMES = ["matched", "constant_region", "sample_barcode", "barcode", "duplicates", "low_quality", "unsupported"]
-KERNEL_NAMES = ["decode", "scan", "insert", "finish", "other"]
+KERNEL_NAMES = ["decode", "scan", "insert", "finish", "other", "enrich", "exchange"]
+BC_CFG_INLINE_COUNT = 1
+BC_ADD_DENSE_COUNTS, BC_ADD_MARGINALS = 0, 1
 
 
 class BcError(RuntimeError):
@@ -40,7 +42,7 @@ class bc_config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("template_chars", C.c_char_p), ("template_len", C.c_uint32),
                 ("region_codes", C.c_char_p), ("region_len", C.c_uint32), ("n_slots", C.c_uint32),
                 ("slots", bc_slot * BC_MAX_SLOTS), ("max_const_err", C.c_uint16), ("min_quality", C.c_float),
-                ("max_read_len", C.c_uint32)]
+                ("max_read_len", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class bc_batch(C.Structure):
@@ -79,6 +81,45 @@ def scan_fastq(path, threads=0):
     return int(n.value), int(b.value), int(c.value)
 
 
+def split_fastq(path, threads=0, block_bytes=0, min_slice=0):
+    """Like scan_fastq, through the mapped-file splitter of bch_count_fastq's plain-file path (host only)."""
+    n, b, c = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    err = C.create_string_buffer(512)
+    rc = lib().bch_split_fastq(os.fsencode(path), threads, block_bytes, min_slice, C.byref(n), C.byref(b), C.byref(c), err, 512)
+    if rc != 0:
+        raise BcError("bch_split_fastq: " + err.value.decode())
+    return int(n.value), int(b.value), int(c.value)
+
+
+def count_fastq_multi(run, counters, path, threads=0, batch_reads=1 << 20):
+    """bch_count_fastq_multi over several Counters (one per GPU, or several on one GPU in tests) -> reads"""
+    arr = (C.c_void_p * len(counters))(*[c.h for c in counters])
+    total = C.c_uint64(0)
+    err = C.create_string_buffer(2048)
+    rc = lib().bch_count_fastq_multi(run.h, arr, len(counters), _b(path), threads, batch_reads, C.byref(total), err, 2048)
+    if rc != 0:
+        raise BcError("bch_count_fastq_multi: " + err.value.decode())
+    return total.value
+
+
+def counters_multi(counters):
+    arr = (C.c_void_p * len(counters))(*[c.h for c in counters])
+    out = (C.c_uint64 * BC_N_COUNTERS)()
+    if lib().bch_counters_multi(arr, len(counters), out) != 0:
+        raise BcError("bch_counters_multi: " + lib().bc_last_error(counters[0].h).decode())
+    return dict(zip(COUNTER_NAMES, [int(x) for x in out]))
+
+
+def write_counts_multi(run, counters, outdir, prefix, merge=False, enrich=False):
+    arr = (C.c_void_p * len(counters))(*[c.h for c in counters])
+    names = C.create_string_buffer(1 << 20)
+    err = C.create_string_buffer(2048)
+    n = lib().bch_write_counts_multi(run.h, arr, len(counters), _b(outdir), _b(prefix), int(merge), int(enrich), names, 1 << 20, err, 2048)
+    if n < 0:
+        raise BcError("bch_write_counts_multi: " + err.value.decode())
+    return [x.split("\t")[0] for x in names.value.decode().split("\n") if x]
+
+
 class bch_args(C.Structure):
     _fields_ = [("format_path", C.c_char_p), ("sample_barcodes_path", C.c_char_p), ("counted_barcodes_path", C.c_char_p),
                 ("max_errors_counted_barcode", C.c_int), ("max_errors_sample", C.c_int), ("max_errors_constant", C.c_int),
@@ -92,6 +133,7 @@ _PROTOS = {
     "bc_qual_stride": (C.c_uint32, [C.c_uint32]),
     "bc_create": (C.c_int, [C.POINTER(bc_config), C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bc_destroy": (None, [C.c_void_p]),
+    "bc_device_of": (C.c_int, [C.c_void_p]),
     "bc_last_error": (C.c_char_p, [C.c_void_p]),
     "bc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_submit": (C.c_int, [C.c_void_p, C.POINTER(bc_batch)]),
@@ -105,12 +147,16 @@ _PROTOS = {
     "bc_enrich": (C.c_int, [C.c_void_p, C.POINTER(bc_table), C.POINTER(bc_table)]),
     "bc_key_decode": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int32), C.c_char_p,
                                 C.c_uint32]),
-    "bc_decode_route": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
-    "bc_insert_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
-    "bc_route_open": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
-    "bc_route_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "bc_route_submit": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.c_uint32, C.c_void_p]),
-    "bc_route_insert": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64]),
+    "bc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bc_marginals": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "bc_exchange_open": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]),
+    "bc_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bc_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bc_exchange_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bc_exchange_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "bc_exchange_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "bc_exchange_finish": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "bc_peer_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "bc_export_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_uint64)]),
     "bc_import_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -132,6 +178,13 @@ _PROTOS = {
     "bch_pack_lines": (C.c_int, [C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
     "bch_scan_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p,
                                  C.c_int]),
+    "bch_split_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                  C.c_char_p, C.c_int]),
+    "bch_count_fastq_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_uint, C.c_uint32,
+                                        C.POINTER(C.c_uint64), C.c_char_p, C.c_int]),
+    "bch_counters_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_uint64)]),
+    "bch_write_counts_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                         C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "bch_count_fastq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint, C.c_uint32, C.POINTER(C.c_uint64), C.c_char_p,
                                   C.c_int]),
     "bch_write_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
@@ -224,7 +277,7 @@ class Run:
                                       "\n".join(quals).encode() if want_q else None, _ptr(planes), _ptr(read_len),
                                       _ptr(qual), threads)
             if rc != 0:
-                raise BcError("bch_pack_lines: a read is longer than max_read_len or its quality string has another length")
+                raise BcError("bch_pack_lines: a read is longer than max_read_len")
         return Batch(n, self.plane_stride, self.qual_stride, planes, read_len, qual)
 
 
@@ -257,10 +310,12 @@ class Counter:
     """One GPU's decode-and-count context (bc_ctx): stands where the reference has its SequenceParser worker pool,
     the shared Results and the SequenceErrors counters (parse.rs:28-76, info.rs:16-139, 661-808)."""
 
-    def __init__(self, run, device=0, expected_reads=0):
+    def __init__(self, run, device=0, expected_reads=0, flags=0):
         self.run = run
         h = C.c_void_p()
-        rc = lib().bc_create(C.byref(run.cfg), device, expected_reads, C.byref(h))
+        cfg = bc_config.from_buffer_copy(run.cfg)  # the run owns the strings the copy points to
+        cfg.flags = flags
+        rc = lib().bc_create(C.byref(cfg), device, expected_reads, C.byref(h))
         if rc != 0:
             raise BcError(f"bc_create failed ({rc}): " + lib().bc_last_error(None).decode())
         self.h = h
@@ -280,6 +335,9 @@ class Counter:
 
     def set_stream(self, cuda_stream):
         self._ck(lib().bc_set_stream(self.h, C.c_void_p(cuda_stream)), "bc_set_stream")
+
+    def set_option(self, name, value):
+        self._ck(lib().bc_set_option(self.h, name.encode(), int(value)), "bc_set_option")
 
     def submit(self, batch):
         b = batch.c_struct()
@@ -381,30 +439,43 @@ class Counter:
             raise BcError("bch_write_counts: " + err.value.decode())
         return [x.split("\t")[0] for x in names.value.decode().split("\n") if x]
 
-    # ---- multi-GPU building blocks (device pointers) ----
-    def decode_route(self, batch, n_ranks, buckets, capacity, counts):
-        b = batch.c_struct()
-        self._ck(lib().bc_decode_route(self.h, C.byref(b), n_ranks, C.c_void_p(buckets.data_ptr()), capacity,
-                                       C.c_void_p(counts.data_ptr())), "bc_decode_route")
+    # ---- multi-GPU building blocks ----
+    def exchange_open(self, n_ranks, rank, capacity):
+        self._ck(lib().bc_exchange_open(self.h, n_ranks, rank, int(capacity)), "bc_exchange_open")
 
-    def route_open(self, n_ranks, rank, capacity):
-        """-> this rank's IPC handle (bytes) for its receive buffer"""
+    def exchange_handle(self):
+        """-> the CUDA IPC handle (bytes) of this rank's receive buffer"""
         h = C.create_string_buffer(64)
-        self._ck(lib().bc_route_open(self.h, n_ranks, rank, capacity, h), "bc_route_open")
+        self._ck(lib().bc_exchange_handle(self.h, h), "bc_exchange_handle")
         return h.raw
 
-    def route_connect(self, handles):
-        self._ck(lib().bc_route_connect(self.h, b"".join(handles)), "bc_route_connect")
+    def exchange_connect(self, handles):
+        self._ck(lib().bc_exchange_connect(self.h, b"".join(handles)), "bc_exchange_connect")
 
-    def route_submit(self, batch, parity, counts):
-        b = batch.c_struct()
-        self._ck(lib().bc_route_submit(self.h, C.byref(b), parity, C.c_void_p(counts.data_ptr())), "bc_route_submit")
+    def exchange_connect_local(self, counters):
+        arr = (C.c_void_p * len(counters))(*[c.h for c in counters])
+        self._ck(lib().bc_exchange_connect_local(self.h, arr), "bc_exchange_connect_local")
 
-    def route_insert(self, parity, counts_from_ptr, stride, expected_records):
-        self._ck(lib().bc_route_insert(self.h, parity, C.c_void_p(counts_from_ptr), stride, int(expected_records)), "bc_route_insert")
+    def exchange_count(self, n_ranks):
+        out = (C.c_uint64 * n_ranks)()
+        self._ck(lib().bc_exchange_count(self.h, out), "bc_exchange_count")
+        return [int(x) for x in out]
 
-    def insert_records(self, records, n):
-        self._ck(lib().bc_insert_records(self.h, C.c_void_p(records.data_ptr()), n), "bc_insert_records")
+    def exchange_scatter(self, first):
+        arr = (C.c_uint64 * len(first))(*[int(x) for x in first])
+        self._ck(lib().bc_exchange_scatter(self.h, arr), "bc_exchange_scatter")
+
+    def exchange_finish(self, n_received):
+        self._ck(lib().bc_exchange_finish(self.h, int(n_received)), "bc_exchange_finish")
+
+    def peer_add(self, src, what):
+        self._ck(lib().bc_peer_add(self.h, src.h, int(what)), "bc_peer_add")
+
+    def marginals(self):
+        """-> (device pointer, n) of the dense enrichment counters, or (None, 0) for schemes with raw barcodes"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(lib().bc_marginals(self.h, C.byref(p), C.byref(n)), "bc_marginals")
+        return p.value, int(n.value)
 
     def export_rows(self):
         lo, hi, cnt, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()

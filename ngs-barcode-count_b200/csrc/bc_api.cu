@@ -22,7 +22,7 @@ struct Staging {
     uint32_t* planes = nullptr;
     uint16_t* read_len = nullptr;
     uint8_t* qual = nullptr;
-    uint64_t cap_reads = 0;
+    size_t cap_planes = 0, cap_len = 0, cap_qual = 0;  // bytes
     cudaEvent_t free_ev = nullptr;    // recorded on the main stream after the last kernel that read the buffer
     cudaEvent_t copied_ev = nullptr;  // recorded on the copy stream after the H2D copies
 };
@@ -49,10 +49,6 @@ struct ItemBuf {  // structure-of-arrays device buffer of (lo, hi, w) items, gro
 struct bc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    // routed mode: the owner-side inserts of batch i run on their own stream, concurrently with the decode of batch i+1
-    cudaStream_t insert_stream = nullptr;
-    cudaEvent_t routed_ev = nullptr, insert_done_ev = nullptr;
-    bool insert_pending = false;
     bool own_stream = true;
     DevCfg cfg{};
     std::vector<KeyField> fields;      // per slot, scheme order
@@ -74,13 +70,26 @@ struct bc_ctx {
     uint2* d_def_items = nullptr;
     uint32_t* d_def_count = nullptr;
     uint64_t def_cap = 0;
-    // fused routing over NVLink (bc_route_*): this rank's receive regions [2 parities][n_ranks][capacity] and the peers'
-    Key* d_recv = nullptr;
-    Key* d_send = nullptr;  // local buckets [n_ranks][capacity], pushed to the owners after each decode
-    uint32_t* d_cursors = nullptr;  // bucket cursors, one cache line apart
-    Key* peer_recv[kMaxRanks] = {nullptr};
-    uint32_t route_ranks = 0, route_rank = 0;
-    uint64_t route_cap = 0;
+    // multi-GPU exchange at the flush (bc_exchange_*): this rank's receive buffer [lo: cap][hi: cap], the peers' buffers
+    // (CUDA IPC mappings, or plain pointers of contexts in this process), and what the last exchange delivered
+    unsigned long long* d_xrecv = nullptr;
+    unsigned long long xcap = 0;
+    uint32_t x_ranks = 0, x_rank = 0;
+    unsigned long long* x_peer[kMaxRanks] = {nullptr};
+    bool x_peer_ipc[kMaxRanks] = {false};
+    uint32_t* d_xcursor = nullptr;         // kMaxRanks cursors / owner counts
+    uint32_t h_xcur[kMaxRanks] = {0};
+    unsigned long long x_sent[kMaxRanks] = {0};
+    unsigned long long x_local_valid = 0;  // records of this rank that were not holes at the last bc_exchange_count
+    int x_state = 0;                       // 0: records not exchanged; 1: counted; 2: scattered; 3: finished (rows valid)
+    unsigned long long x_received = 0;
+    // options (bc_set_option): measurement / test switches of the flush
+    bool opt_flush_global = false, opt_flush_two_stage = false;
+    uint32_t cfg_flags = 0;
+    // K4: dense enrichment marginals (valid for the current rows while marg_valid)
+    MargPlan marg{};
+    bool marg_dense = false, marg_valid = false;
+    unsigned long long* d_marg = nullptr;
     // deferred counting (bc_partition.cu): matched reads append their packed key to `rec`; bc_finish / bc_get_counters
     // de-duplicate and count the whole buffer partition by partition in shared memory
     bool deferred = false;
@@ -96,6 +105,7 @@ struct bc_ctx {
     uint32_t *d_hist = nullptr, *d_starts = nullptr, *d_cursor = nullptr;
     unsigned long long part_cap = 0;
     FlushStats* d_flush = nullptr;
+    unsigned long long last_valid = 0, last_unique = 0;  // of the last flush
     unsigned long long dup_applied = 0;   // duplicates already moved from "matched" to "duplicates" by earlier flushes
     bool flushed_global = false;          // the last flush went through the global-memory tables
     uint32_t flush_stages = 0;            // partition / reduce stages of the last shared-memory flush (1 or 2)
@@ -224,6 +234,7 @@ unsigned long long slots_for(unsigned long long entries) {
 void drop_rows(bc_ctx* ctx) {
     ctx->n_rows = 0;
     ctx->rows_valid = false;
+    ctx->marg_valid = false;
 }
 
 int reserve_rows(bc_ctx* ctx, unsigned long long n, bool wide) {
@@ -253,7 +264,6 @@ void free_items(ItemBuf& b) {
 int reserve_items(bc_ctx* ctx, ItemBuf& b, unsigned long long n, bool wide, bool weighted, unsigned long long used = 0) {
     if (n <= b.cap && (!wide || b.hi) && (!weighted || b.w)) return BC_OK;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
     const unsigned long long cap = std::max<unsigned long long>(std::max(n, b.cap) + (used ? n / 2 : n / 16), 1024);
     ItemBuf nb;
     nb.cap = cap;
@@ -297,7 +307,6 @@ int reserve_records(bc_ctx* ctx, unsigned long long extra) {
     unsigned long long used = 0;
     if (ctx->rec.lo) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
         CK(ctx, cudaMemcpy(&used, ctx->d_rec_n, sizeof used, cudaMemcpyDeviceToHost));
     }
     ctx->rec_upper = used;
@@ -330,16 +339,21 @@ uint32_t quality_threshold(uint32_t len, float min_quality) {
     return top + 1;
 }
 
+// A batch carries its own geometry: W = plane_stride / 3 words per plane, i.e. reads of up to 32 W bases.  The context's
+// max_read_len is only the default; a host that meets a longer read packs that batch wider (up to BC_MAX_READ_LEN).
 int validate_batch(bc_ctx* ctx, const bc_batch* b) {
     if (!b) return fail(ctx, BC_EINVAL, "batch is NULL");
     if (b->n_reads == 0) return BC_OK;
     if (!b->planes || !b->read_len) return fail(ctx, BC_EINVAL, "batch.planes / batch.read_len is NULL");
-    if (b->plane_stride != ctx->plane_stride)
-        return fail(ctx, BC_EINVAL, "batch.plane_stride %u != %u (bc_plane_stride(max_read_len))", b->plane_stride, ctx->plane_stride);
+    const uint32_t W = b->plane_stride / 3;
+    if (W == 0 || b->plane_stride != ((3 * W) | 1u) || 32 * W > BC_MAX_READ_LEN)
+        return fail(ctx, BC_EINVAL, "batch.plane_stride %u is not bc_plane_stride(n) of a read length up to %d", b->plane_stride, BC_MAX_READ_LEN);
+    if (32 * W < ctx->cfg.L)
+        return fail(ctx, BC_EINVAL, "batch.plane_stride %u: reads of at most %u bases cannot hold the %u-base scheme", b->plane_stride, 32 * W, ctx->cfg.L);
     if (ctx->quality_on) {
         if (!b->qual) return fail(ctx, BC_EINVAL, "min_quality > 0 but batch.qual is NULL");
-        if (b->qual_stride != ctx->qual_stride)
-            return fail(ctx, BC_EINVAL, "batch.qual_stride %u != %u (bc_qual_stride(max_read_len))", b->qual_stride, ctx->qual_stride);
+        if ((b->qual_stride & 3u) || b->qual_stride < 32 * (W - 1) + 1)
+            return fail(ctx, BC_EINVAL, "batch.qual_stride %u does not go with plane_stride %u (use bc_qual_stride(n))", b->qual_stride, b->plane_stride);
     }
     if (b->location != BC_LOC_HOST && b->location != BC_LOC_DEVICE) return fail(ctx, BC_EINVAL, "batch.location");
     return BC_OK;
@@ -349,9 +363,10 @@ int validate_batch(bc_ctx* ctx, const bc_batch* b) {
 // double-buffered staging on the copy stream (H2D of batch i+1 overlaps the kernels of batch i).
 int stage_batch(bc_ctx* ctx, const bc_batch* b, BatchView* view) {
     view->n_reads = b->n_reads;
-    view->plane_stride = ctx->plane_stride;
-    view->qual_stride = ctx->qual_stride;
-    view->W = ctx->W;
+    view->plane_stride = b->plane_stride;
+    view->qual_stride = b->qual_stride;
+    view->W = b->plane_stride / 3;
+    view->rep_chunks = (32 * view->W - ctx->cfg.L + 31) / 32;
     const bool want_qual = ctx->quality_on;
     if (b->location == BC_LOC_DEVICE) {
         view->planes = b->planes;
@@ -365,23 +380,23 @@ int stage_batch(bc_ctx* ctx, const bc_batch* b, BatchView* view) {
         CK(ctx, cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
         CK(ctx, cudaEventCreateWithFlags(&s.copied_ev, cudaEventDisableTiming));
     }
-    if (s.cap_reads < b->n_reads) {
+    const size_t pb = (size_t)b->n_reads * b->plane_stride * sizeof(uint32_t);
+    const size_t lb = (size_t)b->n_reads * sizeof(uint16_t);
+    const size_t qb = want_qual ? (size_t)b->n_reads * b->qual_stride : 0;
+    if (s.cap_planes < pb || s.cap_len < lb || s.cap_qual < qb) {
         CK(ctx, cudaEventSynchronize(s.free_ev));
         if (s.planes) cudaFree(s.planes);
         if (s.read_len) cudaFree(s.read_len);
         if (s.qual) cudaFree(s.qual);
         s.planes = nullptr; s.read_len = nullptr; s.qual = nullptr;
-        // round the tile count up so tile-granular staging never reads past the allocation
-        const uint64_t cap = ((uint64_t)b->n_reads + kTile - 1) / kTile * kTile;
-        CK(ctx, cudaMalloc(&s.planes, cap * ctx->plane_stride * sizeof(uint32_t)));
-        CK(ctx, cudaMalloc(&s.read_len, cap * sizeof(uint16_t)));
-        if (want_qual) CK(ctx, cudaMalloc(&s.qual, cap * ctx->qual_stride));
-        s.cap_reads = cap;
+        s.cap_planes = std::max(s.cap_planes, pb + pb / 8);
+        s.cap_len = std::max(s.cap_len, lb + lb / 8);
+        s.cap_qual = std::max(s.cap_qual, qb + qb / 8);
+        CK(ctx, cudaMalloc(&s.planes, s.cap_planes));
+        CK(ctx, cudaMalloc(&s.read_len, s.cap_len));
+        if (want_qual) CK(ctx, cudaMalloc(&s.qual, s.cap_qual));
     }
     CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, s.free_ev, 0));
-    const size_t pb = (size_t)b->n_reads * ctx->plane_stride * sizeof(uint32_t);
-    const size_t lb = (size_t)b->n_reads * sizeof(uint16_t);
-    const size_t qb = want_qual ? (size_t)b->n_reads * ctx->qual_stride : 0;
     CK(ctx, cudaMemcpyAsync(s.planes, b->planes, pb, cudaMemcpyHostToDevice, ctx->copy_stream));
     CK(ctx, cudaMemcpyAsync(s.read_len, b->read_len, lb, cudaMemcpyHostToDevice, ctx->copy_stream));
     if (want_qual) CK(ctx, cudaMemcpyAsync(s.qual, b->qual, qb, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -448,6 +463,8 @@ uint32_t bc_qual_stride(uint32_t max_read_len) { return (((max_read_len + 3) / 4
 
 const char* bc_last_error(const bc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int bc_device_of(const bc_ctx* ctx) { return ctx ? ctx->device : -1; }
+
 void bc_destroy(bc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -493,23 +510,19 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_bref) cudaFree(ctx->d_bref);
     if (ctx->d_def_items) cudaFree(ctx->d_def_items);
     if (ctx->d_def_count) cudaFree(ctx->d_def_count);
-    for (uint32_t r = 0; r < ctx->route_ranks; r++)
-        if (r != ctx->route_rank && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
-    if (ctx->d_recv) cudaFree(ctx->d_recv);
-    if (ctx->d_send) cudaFree(ctx->d_send);
-    if (ctx->d_cursors) cudaFree(ctx->d_cursors);
+    for (uint32_t r = 0; r < ctx->x_ranks; r++)
+        if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
+    if (ctx->d_xrecv) cudaFree(ctx->d_xrecv);
+    if (ctx->d_xcursor) cudaFree(ctx->d_xcursor);
+    if (ctx->d_marg) cudaFree(ctx->d_marg);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_stripes) cudaFree(ctx->d_stripes);
-    if (ctx->insert_stream) {
-        cudaStreamSynchronize(ctx->insert_stream);
-        cudaStreamDestroy(ctx->insert_stream);
-    }
-    if (ctx->routed_ev) cudaEventDestroy(ctx->routed_ev);
-    if (ctx->insert_done_ev) cudaEventDestroy(ctx->insert_done_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
+
+static void plan_marginals(bc_ctx* ctx);
 
 int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx** out) {
     if (!cfg || !out) return fail(nullptr, BC_EINVAL, "cfg / out is NULL");
@@ -555,7 +568,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     d.L = L;
     d.TW = (L + 31) / 32;
     d.n_slots = cfg->n_slots;
-    d.max_const_err = cfg->max_const_err;
+    d.max_const_err = std::min<uint32_t>(cfg->max_const_err, L);  // a cap above the scheme length admits nothing more
+    ctx->cfg_flags = cfg->flags;
     ctx->max_read_len = cfg->max_read_len;
     ctx->W = bc_plane_words(cfg->max_read_len);
     ctx->plane_stride = bc_plane_stride(cfg->max_read_len);
@@ -610,6 +624,17 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             }
         }
         d.pivot = (uint32_t)bestw;
+        // exact-match prefilter (phase A): four constant positions of that word per base, spread over the word; a base with
+        // fewer than four repeats its last one
+        d.xpivot = (uint32_t)bestw;
+        for (uint32_t b = 0; b < 4; b++) {
+            std::vector<uint32_t> pos;
+            for (uint32_t q = 0; q < 32; q++)
+                if (((d.t_cm[bestw] >> q) & 1u) && ((((d.t_lo[bestw] >> q) & 1u) | (((d.t_hi[bestw] >> q) & 1u) << 1)) == b)) pos.push_back(q);
+            if (pos.empty()) continue;
+            d.xs_has |= 1u << b;
+            for (uint32_t i = 0; i < 4; i++) d.xs_sh[b][i] = pos[std::min<size_t>(pos.size() - 1, i * pos.size() / 4)];
+        }
         d.bs_ok = d.max_const_err <= 15 ? 1u : 0u;
         d.bs_k = 15u - std::min<uint32_t>(d.max_const_err, 15u);
         for (uint32_t q = 0; q < 32; q++) {
@@ -623,11 +648,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         // as many positions as the single pivot word has (never a weaker filter than the one it replaces).
         // Measured: with a single 32-offset chunk per read (CRISPR: 16 windows) the static blocks win (0.513 -> 0.480 ms per
         // batch: no per-base loop set-up, no remainder code); with two or more chunks (DEL: 65 windows) the per-base
-        // loops over one word win (0.531 vs 0.543 ms: one plane word less to load and combine).  BC_BS_ONE_WORD=1 / =0
-        // force one or the other.
-        const char* no2 = getenv("BC_BS_ONE_WORD");
-        const bool one_chunk = cfg->max_read_len - L + 1 <= 32;
-        const bool want_two = no2 ? no2[0] == '0' : one_chunk;
+        // loops over one word win (0.531 vs 0.543 ms: one plane word less to load and combine).
+        const bool want_two = cfg->max_read_len - L + 1 <= 32;
         if (d.bs_ok && d.TW >= 2 && want_two) {
             auto kept = [&](uint32_t w, uint32_t b) {
                 uint32_t n = 0;
@@ -907,9 +929,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     bool dense = map_bits <= 27;
     // Deferred counting whenever read-by-read updates would be random DRAM traffic: a (key, UMI) set, or a hashed map.
     // A small dense count array without a random barcode lives in L2 and keeps the inline RED (CRISPR screens).
-    // BC_INLINE_COUNT=1 keeps the read-by-read tables (measurement aid, and what the global-path fallback uses).
-    const char* inline_env = getenv("BC_INLINE_COUNT");
-    ctx->deferred = (T.has_set || !dense) && !(inline_env && inline_env[0] == '1');
+    // BC_CFG_INLINE_COUNT keeps the read-by-read tables (measurement aid; the same tables are the flush's fallback).
+    ctx->deferred = (T.has_set || !dense) && !(cfg->flags & BC_CFG_INLINE_COUNT);
     ctx->expected_reads = hint;
     CKC(cudaMalloc(&ctx->d_rec_n, sizeof(unsigned long long)));
     CKC(cudaMemsetAsync(ctx->d_rec_n, 0, sizeof(unsigned long long), ctx->stream));
@@ -940,6 +961,7 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         bc_destroy(ctx);
         return rc;
     }
+    plan_marginals(ctx);
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return BC_OK;
@@ -957,8 +979,7 @@ int bc_set_stream(bc_ctx* ctx, void* cuda_stream) {
     return BC_OK;
 }
 
-static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const DecodeOut& out, const RouteOut& route,
-                      unsigned long long* counters) {
+static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const DecodeOut& out, unsigned long long* counters) {
     int rc = validate_batch(ctx, batch);
     if (rc != BC_OK) return rc;
     if (batch->n_reads == 0) return BC_OK;
@@ -966,19 +987,16 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     if (flags & F_INSERT) {
         rc = ensure_capacity(ctx, batch->n_reads);
         if (rc != BC_OK) return rc;
-        ctx->rows_valid = false;
     }
     if (flags & F_APPEND) {
         rc = prime_records(ctx, batch->n_reads);
         if (rc == BC_OK) rc = reserve_records(ctx, batch->n_reads);
         if (rc != BC_OK) return rc;
-        ctx->rows_valid = false;
     }
-    if (getenv("BC_DEBUG_NOINSERT")) flags &= ~(F_INSERT | F_APPEND);  // measurement aid: decode without the table updates
-    {   // quality bytes are read from global memory by default (smaller tile, 12 CTAs per SM); BC_QUAL_STAGED=1 stages
-        // the whole 152-byte rows in shared memory with the planes (the measured-slower variant, kept for A/B runs)
-        const char* qs = getenv("BC_QUAL_STAGED");
-        if (!(qs && qs[0] == '1')) flags |= F_QUAL_GLOBAL;
+    if (flags & (F_INSERT | F_APPEND)) {
+        ctx->rows_valid = false;
+        ctx->marg_valid = false;
+        ctx->x_state = 0;
     }
     BatchView view{};
     const int staged = stage_batch(ctx, batch, &view);
@@ -994,21 +1012,36 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, route, rec_out(ctx), deferred,
-                              flags, ctx->stream));
-        if (counters) CK(ctx, launch_fold_counters(ctx->d_stripes, counters, ctx->stream));
+        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, rec_out(ctx), deferred, flags,
+                              ctx->stream));
+    }
+    if (counters) {
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_fold_counters(ctx->d_stripes, counters, ctx->stream));
     }
     if (!(flags & F_LOCATE_ONLY)) {
         ProfScope p(ctx, BC_K_SCAN);
-        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, route, rec_out(ctx), deferred, flags, ctx->stream));
+        CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, rec_out(ctx), deferred, flags, ctx->stream));
     }
-    if (flags & F_APPEND) CK(ctx, launch_bump(ctx->d_rec_n, batch->n_reads, ctx->stream));
+    if (flags & F_APPEND) {
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_bump(ctx->d_rec_n, batch->n_reads, ctx->stream));
+    }
     return release_staging(ctx, staged);
 }
 
 int bc_submit(bc_ctx* ctx, const bc_batch* batch) {
     if (!ctx) return BC_EINVAL;
-    return run_decode(ctx, batch, ctx->deferred ? F_APPEND : F_INSERT, DecodeOut{}, RouteOut{}, ctx->d_counters);
+    return run_decode(ctx, batch, ctx->deferred ? F_APPEND : F_INSERT, DecodeOut{}, ctx->d_counters);
+}
+
+int bc_set_option(bc_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return BC_EINVAL;
+    if (!strcmp(name, "flush_global")) ctx->opt_flush_global = value != 0;
+    else if (!strcmp(name, "flush_two_stage")) ctx->opt_flush_two_stage = value != 0;
+    else return fail(ctx, BC_EINVAL, "bc_set_option: unknown option '%s'", name);
+    ctx->rows_valid = false;
+    return BC_OK;
 }
 
 int bc_sync(bc_ctx* ctx) {
@@ -1016,8 +1049,6 @@ int bc_sync(bc_ctx* ctx) {
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->insert_stream) CK(ctx, cudaStreamSynchronize(ctx->insert_stream));
-    ctx->insert_pending = false;
     ctx->copies_pending = false;
     return BC_OK;
 }
@@ -1033,7 +1064,11 @@ int bc_wait_copies(bc_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------- deferred counting
 // The whole record buffer -> final rows (ctx row buffers) and the matched / duplicates split.  A pure function of the
 // buffer (plus the imported rows), so it may run any number of times as more batches arrive.
-static int flush_global(bc_ctx* ctx, unsigned long long n_rec);
+struct FlushSrc {  // what a flush reads: the record buffer, or (multi-GPU) what the exchange delivered
+    ItemView v;
+    unsigned long long n, n_valid;
+};
+static int flush_global(bc_ctx* ctx, const FlushSrc& in);
 
 static int apply_duplicates(bc_ctx* ctx, unsigned long long dup_now) {
     // k_decode counted every appended record as "matched"; move the repeats to "duplicates" (parse.rs:65-69)
@@ -1128,43 +1163,32 @@ static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned 
     return verdict;
 }
 
-static int go_global(bc_ctx* ctx, unsigned long long n_rec, int where, unsigned long long code) {
-    if (getenv("BC_DEBUG_FLUSH")) fprintf(stderr, "bc: flush falls back to the global tables (site %d, overflow code %llu, %llu records)\n", where, code, n_rec);
-    return flush_global(ctx, n_rec);
+static int go_global(bc_ctx* ctx, const FlushSrc& in, int where, unsigned long long code) {
+    (void)where;
+    (void)code;
+    return flush_global(ctx, in);
 }
 
-static int flush_records(bc_ctx* ctx) {
-    if (ctx->rows_valid) return BC_OK;
-    int rc = bc_sync(ctx);
-    if (rc != BC_OK) return rc;
+// Items of `in` -> final rows (ctx row buffers); ctx->last_valid / last_unique = records that were not holes / distinct
+// (key, random barcode) pairs among them.
+static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
     drop_rows(ctx);
-    unsigned long long n_rec = 0;
-    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
-    ctx->rec_upper = n_rec;
     ctx->flushed_global = false;
     ctx->flush_stages = 0;
+    ctx->last_valid = ctx->last_unique = 0;
+    const unsigned long long n_rec = in.n, n_valid = in.n_valid;
     const bool has_umi = ctx->cfg.has_umi != 0;
     const bool wide_in = ctx->cfg.wide != 0, wide_out = ctx->tables.map.wide != 0;
     FlushStats st{};
-    CK(ctx, cudaMemcpy(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost));
-    if (st.overflow) return fail(ctx, BC_ESTATE, "record buffer overflow while appending routed records (code %llu)", st.overflow);
     if (n_rec + ctx->imp_n == 0) {
         ctx->rows_valid = true;
-        return apply_duplicates(ctx, 0);
+        return BC_OK;
     }
-    // records that are not holes = reads counted "matched" so far (the repeats already moved to "duplicates" included)
-    unsigned long long n_valid = n_rec;
-    {
-        unsigned long long h[BC_N_COUNTERS];
-        CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-        n_valid = std::min(n_rec, h[BC_CNT_MATCHED] + h[BC_CNT_DUPLICATES]);
-    }
-    const char* force = getenv("BC_FLUSH_GLOBAL");
-    if ((force && force[0] == '1') || n_rec + ctx->imp_n >= 0xFFFFFFF0ULL) return go_global(ctx, n_rec, 1, st.overflow);
+    if (ctx->opt_flush_global || n_rec + ctx->imp_n >= 0xFFFFFFF0ULL) return go_global(ctx, in, 1, 0);
 
+    int rc;
     CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-    const ItemView rows_v{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt};
-    ItemView src{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr};
+    ItemView src = in.v;
     unsigned long long n_src = n_rec, src_valid = n_valid, rows_done = 0, valid_total = 0, unique_total = 0;
     bool count_valid = has_umi;
     uint32_t stages = 0;
@@ -1175,8 +1199,7 @@ static int flush_records(bc_ctx* ctx) {
     // key store makes its partition too large, which shows in the histogram before anything is moved: a few such
     // partitions are set aside (k_gather_big) and go through the two stages below on their own; if they hold more
     // than a fifth of the records, the one-stage attempt is abandoned.
-    const char* two = getenv("BC_FLUSH_TWO_STAGE");
-    if (has_umi && n_rec && ctx->imp_n == 0 && !(two && two[0] == '1')) {
+    if (has_umi && n_rec && ctx->imp_n == 0 && !ctx->opt_flush_two_stage) {
         unsigned long long n_parts = 0, big = 0;
         rc = reserve_items(ctx, ctx->part, n_rec, wide_in, false);
         if (rc == BC_OK) rc = reserve_rows(ctx, n_valid, wide_out);
@@ -1184,18 +1207,18 @@ static int flush_records(bc_ctx* ctx) {
         const ItemView part_v{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr};
         const uint32_t cap = reduce_capacity(wide_in);
         rc = partition_items(ctx, src, wide_in, n_rec, n_valid, false, part_v, true, ctx->cfg.umi_bits, cap, &n_parts, &big);
-        if (rc == 1) return go_global(ctx, n_rec, 2, st.overflow);
+        if (rc == 1) return go_global(ctx, in, 2, 0);
         if (rc == BC_OK || rc == 3) {
             {
                 ProfScope p(ctx, BC_K_FINISH);
-                CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
+                CK(ctx, launch_reduce(RED_DEDUPE_KEYED, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
                                       ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
                                       ctx->d_flush, rc == 3 ? cap : 0u, ctx->stream));
             }
             CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
             CK(ctx, cudaStreamSynchronize(ctx->stream));
             CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-            if (st.overflow) return go_global(ctx, n_rec, 3, st.overflow);
+            if (st.overflow) return go_global(ctx, in, 3, st.overflow);
             rows_done = st.n_out;
             valid_total = st.valid;
             unique_total = st.unique;
@@ -1204,7 +1227,9 @@ static int flush_records(bc_ctx* ctx) {
                 ctx->n_rows = rows_done;
                 ctx->rows_valid = true;
                 ctx->flush_stages = 1;
-                return apply_duplicates(ctx, valid_total - unique_total);
+                ctx->last_valid = valid_total;
+                ctx->last_unique = unique_total;
+                return BC_OK;
             }
             // the hot partitions, gathered: the input of the two stages
             int rc2 = reserve_items(ctx, ctx->left, big, wide_in, false);
@@ -1237,7 +1262,7 @@ static int flush_records(bc_ctx* ctx) {
             if (rc != BC_OK) return rc;
             const ItemView part_v{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr};
             rc = partition_items(ctx, src, wide_in, n_src, src_valid, false, part_v, count_valid, 0, 0, &n_parts, nullptr, salt);
-            if (rc == 1) return go_global(ctx, n_rec, 4, st.overflow);
+            if (rc == 1) return go_global(ctx, in, 4, 0);
             if (rc != BC_OK) return rc;
             ProfScope p(ctx, BC_K_FINISH);
             CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_src, n_parts, 0, ctx->cfg.umi_bits, w1_v, ctx->w1.cap,
@@ -1252,7 +1277,7 @@ static int flush_records(bc_ctx* ctx) {
     CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-    if (st.overflow) return go_global(ctx, n_rec, 5, st.overflow);
+    if (st.overflow) return go_global(ctx, in, 5, st.overflow);
     unsigned long long n1 = st.n_out;
     if (count_valid) valid_total = st.valid;
     unique_total += st.unique;
@@ -1271,12 +1296,12 @@ static int flush_records(bc_ctx* ctx) {
         rc = reserve_items(ctx, ctx->w2, n1, wide_out, true);
         if (rc != BC_OK) return rc;
         if (rows_done == 0) rc = reserve_rows(ctx, n1, wide_out);
-        else if (rows_done + n1 > ctx->row_cap) return go_global(ctx, n_rec, 6, st.overflow);  // cannot happen: sized for every valid record
+        else if (rows_done + n1 > ctx->row_cap) return go_global(ctx, in, 6, 0);  // cannot happen: sized for every valid record
         if (rc != BC_OK) return rc;
         const ItemView w1_now{ctx->w1.lo, wide_out ? ctx->w1.hi : nullptr, ctx->w1.w};
         rc = partition_items(ctx, w1_now, wide_out, n1, n1, true, ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, false, 0,
                              0, &n_parts, nullptr, salt);
-        if (rc == 1) return go_global(ctx, n_rec, 7, st.overflow);
+        if (rc == 1) return go_global(ctx, in, 7, 0);
         if (rc != BC_OK) return rc;
         CK(ctx, cudaMemcpyAsync(&ctx->d_flush->n_out, &rows_done, sizeof rows_done, cudaMemcpyHostToDevice, ctx->stream));
         {
@@ -1288,17 +1313,18 @@ static int flush_records(bc_ctx* ctx) {
         CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-        if (st.overflow) return go_global(ctx, n_rec, 8, st.overflow);
+        if (st.overflow) return go_global(ctx, in, 8, st.overflow);
         ctx->n_rows = st.n_out;
     }
-    (void)rows_v;
     ctx->rows_valid = true;
     ctx->flush_stages = stages ? 3 : 2;  // 3: one stage plus two stages for the hot keys
-    return apply_duplicates(ctx, has_umi ? valid_total - unique_total : 0);
+    ctx->last_valid = has_umi ? valid_total : n_valid;
+    ctx->last_unique = has_umi ? unique_total : n_valid;
+    return BC_OK;
 }
 
-// Fallback: the record buffer through the global-memory set / map of bc_device.cuh (random DRAM accesses).
-static int flush_global(bc_ctx* ctx, unsigned long long n_rec) {
+// Fallback: the items through the global-memory set / map of bc_device.cuh (random DRAM accesses; counts add in 64 bits).
+static int flush_global(bc_ctx* ctx, const FlushSrc& in) {
     Tables& T = ctx->tables;
     const bool wide_in = ctx->cfg.wide != 0, wide_out = T.map.wide != 0;
     drop_rows(ctx);
@@ -1307,14 +1333,13 @@ static int flush_global(bc_ctx* ctx, unsigned long long n_rec) {
     free_table(T.set);
     CK(ctx, cudaMemsetAsync(ctx->d_counters + BC_N_COUNTERS, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-    int rc = alloc_table(ctx, T.map, 1, wide_out, slots_for(n_rec + ctx->imp_n), ctx->d_counters + BC_N_COUNTERS);
-    if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, wide_in, slots_for(n_rec), ctx->d_counters + BC_N_COUNTERS + 1);
+    int rc = alloc_table(ctx, T.map, 1, wide_out, slots_for(in.n + ctx->imp_n), ctx->d_counters + BC_N_COUNTERS);
+    if (rc == BC_OK && T.has_set) rc = alloc_table(ctx, T.set, 2, wide_in, slots_for(in.n), ctx->d_counters + BC_N_COUNTERS + 1);
     if (rc != BC_OK) return rc;
     {
         ProfScope p(ctx, BC_K_FINISH);
-        CK(ctx, launch_insert_items(T, ItemView{ctx->rec.lo, wide_in ? ctx->rec.hi : nullptr, nullptr}, wide_in, n_rec, ctx->d_flush, ctx->stream));
-        if (ctx->imp_n)
-            CK(ctx, launch_insert(T, ctx->imp.lo, wide_out ? ctx->imp.hi : nullptr, nullptr, ctx->imp.w, ctx->imp_n, nullptr, ctx->stream));
+        CK(ctx, launch_insert_items(T, in.v, wide_in, in.n, ctx->d_flush, ctx->stream));
+        if (ctx->imp_n) CK(ctx, launch_insert(T, ctx->imp.lo, wide_out ? ctx->imp.hi : nullptr, ctx->imp.w, ctx->imp_n, ctx->stream));
     }
     FlushStats st{};
     unsigned long long keys = 0;
@@ -1334,7 +1359,31 @@ static int flush_global(bc_ctx* ctx, unsigned long long n_rec) {
     free_table(T.map);
     free_table(T.set);
     ctx->rows_valid = true;
-    return apply_duplicates(ctx, T.has_set ? st.valid - st.unique : 0);
+    ctx->last_valid = st.valid;
+    ctx->last_unique = T.has_set ? st.unique : st.valid;
+    return BC_OK;
+}
+
+// The whole record buffer -> final rows and the matched / duplicates split.  A pure function of the buffer (plus the
+// imported rows), so it may run any number of times as more batches arrive.
+static int flush_records(bc_ctx* ctx) {
+    if (ctx->rows_valid) return BC_OK;
+    if (ctx->x_ranks > 1)
+        return fail(ctx, BC_ESTATE, "this context is one rank of a multi-GPU job: run bc_exchange_count / _scatter / _finish after the "
+                                    "last bc_submit before asking for counters or rows");
+    int rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
+    unsigned long long n_rec = 0;
+    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
+    ctx->rec_upper = n_rec;
+    // records that are not holes = reads counted "matched" so far (the repeats already moved to "duplicates" included)
+    unsigned long long h[BC_N_COUNTERS];
+    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    const unsigned long long n_valid = std::min(n_rec, h[BC_CNT_MATCHED] + h[BC_CNT_DUPLICATES]);
+    const FlushSrc in{ItemView{ctx->rec.lo, ctx->cfg.wide ? ctx->rec.hi : nullptr, nullptr}, n_rec, n_valid};
+    rc = flush_core(ctx, in);
+    if (rc != BC_OK) return rc;
+    return apply_duplicates(ctx, ctx->cfg.has_umi ? ctx->last_valid - ctx->last_unique : 0);
 }
 
 int bc_get_counters(bc_ctx* ctx, uint64_t out[BC_N_COUNTERS]) {
@@ -1386,7 +1435,7 @@ static int decode_hook(bc_ctx* ctx, const bc_batch* batch, int flags, uint8_t* s
     }
     if (key_lo) CKH(cudaMalloc(&d.key_lo, n * sizeof(unsigned long long)));
     if (key_hi) CKH(cudaMalloc(&d.key_hi, n * sizeof(unsigned long long)));
-    int rc = run_decode(ctx, batch, flags | F_EMIT, d, RouteOut{}, nullptr);
+    int rc = run_decode(ctx, batch, flags | F_EMIT, d, nullptr);
     if (rc != BC_OK) {
         cleanup();
         return rc;
@@ -1547,7 +1596,7 @@ static int one_marginal(bc_ctx* ctx, uint32_t keep, bc_table* out) {
     unsigned long long *lo = nullptr, *hi = nullptr, *cnt = nullptr, n = 0;
     if (rc == BC_OK) {
         {
-            ProfScope p(ctx, BC_K_FINISH);
+            ProfScope p(ctx, BC_K_ENRICH);
             cudaError_t e = launch_marginal(ctx->d_row_lo, wide ? ctx->d_row_hi : nullptr, ctx->d_row_cnt, ctx->n_rows, mask, t, ctx->stream);
             if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_marginal: %s", cudaGetErrorString(e));
         }
@@ -1561,7 +1610,7 @@ static int one_marginal(bc_ctx* ctx, uint32_t keep, bc_table* out) {
         if (rc == BC_OK) {
             cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream);
             {
-                ProfScope p(ctx, BC_K_FINISH);
+                ProfScope p(ctx, BC_K_ENRICH);
                 cudaError_t e = launch_compact(t, lo, hi, cnt, ctx->d_row_n, ctx->stream);
                 if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_compact: %s", cudaGetErrorString(e));
             }
@@ -1578,6 +1627,127 @@ static int one_marginal(bc_ctx* ctx, uint32_t keep, bc_table* out) {
     return rc;
 }
 
+// Dense plan for the marginals: possible when every counted barcode (and the sample barcode, if any) is index-coded and
+// the counters of all singles and doubles together stay within a budget.
+static void plan_marginals(bc_ctx* ctx) {
+    MargPlan& P = ctx->marg;
+    P = MargPlan{};
+    ctx->marg_dense = false;
+    const uint32_t k = (uint32_t)ctx->counted_slots.size();
+    if (k == 0 || k > (uint32_t)kMaxSlots) return;
+    const uint32_t drop = ctx->cfg.umi_bits;
+    for (uint32_t a = 0; a < k; a++) {
+        const KeyField& f = ctx->fields[ctx->counted_slots[a]];
+        if (f.raw || f.bits > 24) return;
+        P.f_shift[a] = f.shift - drop;
+        P.f_bits[a] = f.bits;
+    }
+    if (ctx->sample_slot >= 0) {
+        const KeyField& f = ctx->fields[ctx->sample_slot];
+        if (f.raw || f.bits > 24) return;
+        P.s_shift = f.shift - drop;
+        P.s_bits = f.bits;
+    }
+    const unsigned long long budget = 1ULL << 26;  // counters (512 MB)
+    unsigned long long off = 0;
+    P.k = k;
+    for (uint32_t a = 0; a < k; a++) {
+        P.s_off[a] = off;
+        off += 1ULL << (P.s_bits + P.f_bits[a]);
+        if (off > budget) return;
+    }
+    P.n_single = off;
+    for (uint32_t a = 0; a + 1 < k; a++)
+        for (uint32_t b = a + 1; b < k; b++) {
+            const uint32_t bits = P.s_bits + P.f_bits[a] + P.f_bits[b];
+            if (bits > 40) return;
+            P.pa[P.n_pairs] = (uint8_t)a;
+            P.pb[P.n_pairs] = (uint8_t)b;
+            P.d_off[P.n_pairs++] = off;
+            off += 1ULL << bits;
+            if (off > budget) return;
+        }
+    P.n_total = off;
+    ctx->marg_dense = true;
+}
+
+static int compute_marginals(bc_ctx* ctx) {
+    if (ctx->marg_valid) return BC_OK;
+    if (!ctx->d_marg) CK(ctx, cudaMalloc(&ctx->d_marg, ctx->marg.n_total * sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(ctx->d_marg, 0, ctx->marg.n_total * sizeof(unsigned long long), ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_ENRICH);
+        CK(ctx, launch_marginals_dense(ctx->d_row_lo, ctx->tables.map.wide ? ctx->d_row_hi : nullptr, ctx->d_row_cnt, ctx->n_rows, ctx->marg,
+                                       ctx->d_marg, ctx->stream));
+    }
+    ctx->marg_valid = true;
+    return BC_OK;
+}
+
+// marginals [m_first, m_first + m_count) of the dense arrays -> host rows
+static int marginals_to_host(bc_ctx* ctx, uint32_t m_first, uint32_t m_count, bc_table* out) {
+    if (m_count == 0) return BC_OK;
+    unsigned long long n = 0;
+    CK(ctx, cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_ENRICH);
+        CK(ctx, launch_marginals_rows(ctx->marg, m_first, m_count, ctx->d_marg, nullptr, nullptr, nullptr, nullptr, ctx->d_row_n, ctx->stream));
+    }
+    CK(ctx, cudaMemcpyAsync(&n, ctx->d_row_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n == 0) return BC_OK;
+    unsigned long long *lo = nullptr, *hi = nullptr, *cnt = nullptr;
+    uint32_t* mask = nullptr;
+    int rc = BC_OK;
+    if (cudaMalloc(&lo, n * 8) != cudaSuccess || cudaMalloc(&hi, n * 8) != cudaSuccess || cudaMalloc(&cnt, n * 8) != cudaSuccess ||
+        cudaMalloc(&mask, n * 4) != cudaSuccess)
+        rc = fail(ctx, BC_ENOMEM, "marginal rows");
+    if (rc == BC_OK) {
+        cudaMemsetAsync(ctx->d_row_n, 0, sizeof(unsigned long long), ctx->stream);
+        ProfScope p(ctx, BC_K_ENRICH);
+        cudaError_t e = launch_marginals_rows(ctx->marg, m_first, m_count, ctx->d_marg, lo, hi, cnt, mask, ctx->d_row_n, ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, BC_ECUDA, "launch_marginals_rows: %s", cudaGetErrorString(e));
+    }
+    if (rc == BC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, BC_ECUDA, "marginal rows sync");
+    if (rc == BC_OK) {
+        const uint64_t old = out->n_rows, tot = old + n;
+        out->key_lo = (uint64_t*)realloc(out->key_lo, tot * sizeof(uint64_t));
+        out->key_hi = (uint64_t*)realloc(out->key_hi, tot * sizeof(uint64_t));
+        out->count = (uint64_t*)realloc(out->count, tot * sizeof(uint64_t));
+        out->mask = (uint32_t*)realloc(out->mask, tot * sizeof(uint32_t));
+        if (!out->key_lo || !out->key_hi || !out->count || !out->mask) rc = fail(ctx, BC_ENOMEM, "host rows");
+        if (rc == BC_OK &&
+            (cudaMemcpy(out->key_lo + old, lo, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+             cudaMemcpy(out->key_hi + old, hi, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+             cudaMemcpy(out->count + old, cnt, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+             cudaMemcpy(out->mask + old, mask, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess))
+            rc = fail(ctx, BC_ECUDA, "marginal rows D2H");
+        if (rc == BC_OK) {
+            out->n_rows = tot;
+            ctx->prof.d2h_bytes += n * 28;
+        }
+    }
+    if (lo) cudaFree(lo);
+    if (hi) cudaFree(hi);
+    if (cnt) cudaFree(cnt);
+    if (mask) cudaFree(mask);
+    return rc;
+}
+
+int bc_marginals(bc_ctx* ctx, uint64_t** dev_counters, uint64_t* n) {
+    if (!ctx || !dev_counters || !n) return BC_EINVAL;
+    *dev_counters = nullptr;
+    *n = 0;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->marg_dense) return BC_OK;
+    int rc = build_rows(ctx);
+    if (rc == BC_OK) rc = compute_marginals(ctx);
+    if (rc != BC_OK) return rc;
+    *dev_counters = reinterpret_cast<uint64_t*>(ctx->d_marg);
+    *n = ctx->marg.n_total;
+    return BC_OK;
+}
+
 int bc_enrich(bc_ctx* ctx, bc_table* singles, bc_table* doubles) {
     if (!ctx || !singles) return BC_EINVAL;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -1586,6 +1756,13 @@ int bc_enrich(bc_ctx* ctx, bc_table* singles, bc_table* doubles) {
     int rc = build_rows(ctx);
     if (rc != BC_OK) return rc;
     const uint32_t k = (uint32_t)ctx->counted_slots.size();
+    if (ctx->marg_dense) {  // one pass over the rows fills every marginal; the arrays may have been merged across ranks since
+        rc = compute_marginals(ctx);
+        if (rc == BC_OK) rc = marginals_to_host(ctx, 0, k, singles);
+        if (rc == BC_OK && doubles) rc = marginals_to_host(ctx, k, ctx->marg.n_pairs, doubles);
+        return rc;
+    }
+    // raw (file-less) barcodes have no dense index space: one hash map per marginal
     for (uint32_t a = 0; a < k; a++) {  // info.rs:840-866
         rc = one_marginal(ctx, 1u << a, singles);
         if (rc != BC_OK) return rc;
@@ -1642,149 +1819,203 @@ int bc_key_decode(const bc_ctx* ctx, uint64_t key_lo, uint64_t key_hi, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------- multi-GPU
+// One exchange at the flush: record -> owner = hash(key without its random barcode) % n_ranks, written by the partitioning
+// kernel straight into the owner's receive buffer (NVLink peer memory); every owner then runs the usual flush over what
+// it received.  The owner hash uses its own salt so that it is independent of the hash that partitions an owner's records.
+static const unsigned long long kOwnerSalt = 0xBB67AE8584CAA73BULL;
 
-int bc_decode_route(bc_ctx* ctx, const bc_batch* batch, uint32_t n_ranks, bc_record* dev_buckets, uint64_t bucket_capacity,
-                    uint32_t* dev_bucket_counts) {
-    if (!ctx || !batch || !dev_buckets || !dev_bucket_counts || n_ranks == 0) return BC_EINVAL;
-    if (bucket_capacity < batch->n_reads)
-        return fail(ctx, BC_EINVAL, "bucket_capacity %llu < n_reads %u: a bucket must be able to hold the whole batch",
-                    (unsigned long long)bucket_capacity, batch->n_reads);
-    if (n_ranks > (uint32_t)kMaxRanks) return fail(ctx, BC_EUNSUPPORTED, "more than %d ranks", kMaxRanks);
-    RouteOut r{};
-    for (uint32_t k = 0; k < n_ranks; k++) r.dst[k] = reinterpret_cast<Key*>(dev_buckets) + (size_t)k * bucket_capacity;
-    r.capacity = bucket_capacity;
-    r.counts = dev_bucket_counts;
-    r.count_stride = 1;
-    r.n_ranks = n_ranks;
-    return run_decode(ctx, batch, F_ROUTE, DecodeOut{}, r, ctx->d_counters);
+static SplitLevel owner_level(const bc_ctx* ctx) {
+    return SplitLevel{ctx->x_ranks, 0u, 0xFFFFFFFFu, ctx->x_ranks, ctx->cfg.umi_bits, kOwnerSalt};
 }
 
-// ---- fused routing: the decode kernel stores each matched record straight into its owner's receive region over NVLink
-int bc_route_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity, void* ipc_handle_out) {
-    if (!ctx || !ipc_handle_out || n_ranks == 0 || n_ranks > (uint32_t)kMaxRanks || rank >= n_ranks || capacity == 0) return BC_EINVAL;
-    if (ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_open: already open");
-    static_assert(sizeof(cudaIpcMemHandle_t) == BC_IPC_HANDLE_BYTES, "BC_IPC_HANDLE_BYTES");
+static void close_peers(bc_ctx* ctx) {
+    for (uint32_t r = 0; r < (uint32_t)kMaxRanks; r++) {
+        if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
+        ctx->x_peer[r] = nullptr;
+        ctx->x_peer_ipc[r] = false;
+    }
+}
+
+int bc_exchange_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity) {
+    if (!ctx || n_ranks == 0 || n_ranks > (uint32_t)kMaxRanks || rank >= n_ranks || capacity == 0) return BC_EINVAL;
+    if (!ctx->deferred)
+        return fail(ctx, BC_ESTATE, "bc_exchange_open: this scheme counts into a dense table; merge ranks with bc_dense_counts / bc_peer_add");
+    if (capacity >= 0xFFFFFFF0ULL) return fail(ctx, BC_EUNSUPPORTED, "bc_exchange_open: more than 2^32 records per owner");
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaMalloc(&ctx->d_recv, 2ull * n_ranks * capacity * sizeof(Key)));
-    CK(ctx, cudaMalloc(&ctx->d_send, (size_t)n_ranks * capacity * sizeof(Key)));
-    CK(ctx, cudaMalloc(&ctx->d_cursors, (size_t)kMaxRanks * 32 * sizeof(uint32_t)));
-    cudaIpcMemHandle_t h;
-    CK(ctx, cudaIpcGetMemHandle(&h, ctx->d_recv));
-    memcpy(ipc_handle_out, &h, sizeof h);
-    ctx->route_ranks = n_ranks;
-    ctx->route_rank = rank;
-    ctx->route_cap = capacity;
-    ctx->peer_recv[rank] = ctx->d_recv;
-    int lo_prio = 0, hi_prio = 0;
-    CK(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
-    CK(ctx, cudaStreamCreateWithPriority(&ctx->insert_stream, cudaStreamNonBlocking, hi_prio));
-    CK(ctx, cudaEventCreateWithFlags(&ctx->routed_ev, cudaEventDisableTiming));
-    CK(ctx, cudaEventCreateWithFlags(&ctx->insert_done_ev, cudaEventDisableTiming));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    close_peers(ctx);
+    if (ctx->d_xrecv) cudaFree(ctx->d_xrecv);
+    ctx->d_xrecv = nullptr;
+    CK(ctx, cudaMalloc(&ctx->d_xrecv, capacity * sizeof(unsigned long long) * (ctx->cfg.wide ? 2 : 1)));
+    if (!ctx->d_xcursor) CK(ctx, cudaMalloc(&ctx->d_xcursor, kMaxRanks * sizeof(uint32_t)));
+    ctx->xcap = capacity;
+    ctx->x_ranks = n_ranks;
+    ctx->x_rank = rank;
+    ctx->x_peer[rank] = ctx->d_xrecv;
+    ctx->x_state = 0;
+    ctx->rows_valid = false;
     return BC_OK;
 }
 
-int bc_route_connect(bc_ctx* ctx, const void* ipc_handles) {
-    if (!ctx || !ipc_handles) return BC_EINVAL;
-    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_connect before bc_route_open");
+int bc_exchange_handle(bc_ctx* ctx, void* ipc_handle_out) {
+    if (!ctx || !ipc_handle_out) return BC_EINVAL;
+    if (!ctx->d_xrecv) return fail(ctx, BC_ESTATE, "bc_exchange_handle before bc_exchange_open");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BC_IPC_HANDLE_BYTES, "BC_IPC_HANDLE_BYTES");
     CK(ctx, cudaSetDevice(ctx->device));
-    for (uint32_t r = 0; r < ctx->route_ranks; r++) {
-        if (r == ctx->route_rank) continue;
+    cudaIpcMemHandle_t h;
+    CK(ctx, cudaIpcGetMemHandle(&h, ctx->d_xrecv));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return BC_OK;
+}
+
+int bc_exchange_connect(bc_ctx* ctx, const void* ipc_handles) {
+    if (!ctx || !ipc_handles) return BC_EINVAL;
+    if (!ctx->d_xrecv) return fail(ctx, BC_ESTATE, "bc_exchange_connect before bc_exchange_open");
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t r = 0; r < ctx->x_ranks; r++) {
+        if (r == ctx->x_rank) continue;
+        if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
         cudaIpcMemHandle_t h;
         memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof h, sizeof h);
         void* p = nullptr;
         CK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        ctx->peer_recv[r] = static_cast<Key*>(p);
+        ctx->x_peer[r] = static_cast<unsigned long long*>(p);
+        ctx->x_peer_ipc[r] = true;
     }
     return BC_OK;
 }
 
-int bc_route_submit(bc_ctx* ctx, const bc_batch* batch, uint32_t parity, uint32_t* dev_counts) {
-    if (!ctx || !batch || !dev_counts || parity > 1) return BC_EINVAL;
-    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_submit before bc_route_open");
-    if (batch->n_reads > ctx->route_cap)
-        return fail(ctx, BC_EINVAL, "batch of %u reads exceeds the route capacity %llu", batch->n_reads, (unsigned long long)ctx->route_cap);
-    for (uint32_t r = 0; r < ctx->route_ranks; r++)
-        if (!ctx->peer_recv[r]) return fail(ctx, BC_ESTATE, "bc_route_submit before bc_route_connect");
-    CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaMemsetAsync(ctx->d_cursors, 0, (size_t)kMaxRanks * 32 * sizeof(uint32_t), ctx->stream));
-    RouteOut local{}, remote{};
-    for (uint32_t k = 0; k < ctx->route_ranks; k++) {
-        local.dst[k] = ctx->d_send + (size_t)k * ctx->route_cap;
-        // my region inside rank k's receive buffer
-        remote.dst[k] = ctx->peer_recv[k] + ((size_t)parity * ctx->route_ranks + ctx->route_rank) * ctx->route_cap;
-    }
-    local.capacity = remote.capacity = ctx->route_cap;
-    local.counts = remote.counts = ctx->d_cursors;
-    local.count_stride = remote.count_stride = 32;
-    local.n_ranks = remote.n_ranks = ctx->route_ranks;
-    int rc = run_decode(ctx, batch, F_ROUTE, DecodeOut{}, local, ctx->d_counters);
-    if (rc != BC_OK) return rc;
-    {
-        ProfScope p(ctx, BC_K_OTHER);
-        CK(ctx, launch_push(local, remote, dev_counts, ctx->stream));
-    }
-    // The caller's collective that follows tells the peers "my receive buffer of the other parity is free again", so it
-    // has to be ordered after my insert of the previous batch — which ran concurrently with the decode just launched.
-    if (ctx->insert_pending) {
-        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->insert_done_ev, 0));
-        ctx->insert_pending = false;
-    }
+static int enable_peer(bc_ctx* ctx, int other_device) {
+    if (other_device == ctx->device) return BC_OK;
+    int can = 0;
+    CK(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, other_device));
+    if (!can) return fail(ctx, BC_EUNSUPPORTED, "device %d cannot access device %d (no NVLink / PCIe peer path)", ctx->device, other_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(other_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) return fail(ctx, BC_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", other_device, cudaGetErrorString(e));
     return BC_OK;
 }
 
-int bc_route_insert(bc_ctx* ctx, uint32_t parity, const uint32_t* dev_counts_from, uint32_t count_stride, uint64_t expected_records) {
-    if (!ctx || !dev_counts_from || parity > 1) return BC_EINVAL;
-    if (!ctx->d_recv) return fail(ctx, BC_ESTATE, "bc_route_insert before bc_route_open");
+int bc_exchange_connect_local(bc_ctx* ctx, bc_ctx* const* ranks) {
+    if (!ctx || !ranks) return BC_EINVAL;
+    if (!ctx->d_xrecv) return fail(ctx, BC_ESTATE, "bc_exchange_connect_local before bc_exchange_open");
     CK(ctx, cudaSetDevice(ctx->device));
-    if (ctx->insert_pending) {  // only when the caller skipped a submit in between
-        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->insert_done_ev, 0));
-        ctx->insert_pending = false;
-    }
-    int rc;
-    if (ctx->deferred) {  // worst case of one round: every source fills its region
-        const unsigned long long worst = (unsigned long long)ctx->route_ranks * ctx->route_cap;
-        rc = prime_records(ctx, 2 * worst);
-        if (rc == BC_OK) rc = reserve_records(ctx, worst);
-    } else {
-        rc = ensure_capacity(ctx, expected_records);  // may rehash on the main stream: the insert stream is idle here
-    }
-    if (rc != BC_OK) return rc;
-    ctx->rows_valid = false;
-    // inserts go to their own (high-priority) stream once the exchange of counts, i.e. everything queued on the main
-    // stream so far, is done; the main stream is free to decode the next batch meanwhile
-    CK(ctx, cudaEventRecord(ctx->routed_ev, ctx->stream));
-    CK(ctx, cudaStreamWaitEvent(ctx->insert_stream, ctx->routed_ev, 0));
-    ctx->prof.launches[BC_K_INSERT]++;
-    if (ctx->deferred)  // the owner only keeps what arrived; de-duplication happens once, at the flush
-        CK(ctx, launch_append_segments(ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap, dev_counts_from,
-                                       count_stride, ctx->route_ranks, rec_out(ctx), ctx->rec.cap, ctx->d_rec_n, ctx->d_counters,
-                                       ctx->d_flush, ctx->insert_stream));
-    else
-    CK(ctx, launch_insert_segments(ctx->tables, ctx->d_recv + (size_t)parity * ctx->route_ranks * ctx->route_cap, ctx->route_cap,
-                                   dev_counts_from, count_stride, ctx->route_ranks, ctx->d_counters, ctx->insert_stream));
-    CK(ctx, cudaEventRecord(ctx->insert_done_ev, ctx->insert_stream));
-    ctx->insert_pending = true;
-    return BC_OK;
-}
-
-int bc_insert_records(bc_ctx* ctx, const bc_record* dev_records, uint64_t n) {
-    if (!ctx || (!dev_records && n)) return BC_EINVAL;
-    if (n == 0) return BC_OK;
-    CK(ctx, cudaSetDevice(ctx->device));
-    if (ctx->deferred) {
-        int rc = reserve_records(ctx, n);
+    for (uint32_t r = 0; r < ctx->x_ranks; r++) {
+        if (r == ctx->x_rank) continue;
+        bc_ctx* o = ranks[r];
+        if (!o || !o->d_xrecv || o->xcap != ctx->xcap || o->x_ranks != ctx->x_ranks || o->x_rank != r || o->cfg.wide != ctx->cfg.wide)
+            return fail(ctx, BC_EINVAL, "bc_exchange_connect_local: rank %u is not open with the same geometry", r);
+        int rc = enable_peer(ctx, o->device);
         if (rc != BC_OK) return rc;
-        ctx->rows_valid = false;
-        ProfScope p(ctx, BC_K_INSERT);
-        CK(ctx, launch_append_records(reinterpret_cast<const Key*>(dev_records), n, rec_out(ctx), ctx->d_counters, ctx->stream));
-        CK(ctx, launch_bump(ctx->d_rec_n, n, ctx->stream));
-        return BC_OK;
+        if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
+        ctx->x_peer[r] = o->d_xrecv;
+        ctx->x_peer_ipc[r] = false;
     }
-    int rc = ensure_capacity(ctx, n);
+    return BC_OK;
+}
+
+int bc_exchange_count(bc_ctx* ctx, uint64_t* sent) {
+    if (!ctx || !sent) return BC_EINVAL;
+    if (ctx->x_ranks == 0) return fail(ctx, BC_ESTATE, "bc_exchange_count before bc_exchange_open");
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
-    ctx->rows_valid = false;
-    ProfScope p(ctx, BC_K_INSERT);
-    CK(ctx, launch_insert(ctx->tables, nullptr, nullptr, reinterpret_cast<const Key*>(dev_records), nullptr, n, ctx->d_counters, ctx->stream));
+    unsigned long long n_rec = 0;
+    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
+    ctx->rec_upper = n_rec;
+    if (n_rec >= 0xFFFFFFF0ULL) return fail(ctx, BC_EUNSUPPORTED, "bc_exchange_count: more than 2^32 records on one rank");
+    uint32_t h[kMaxRanks] = {0};
+    FlushStats st{};
+    if (n_rec) {
+        const bool wide = ctx->cfg.wide != 0;
+        CK(ctx, cudaMemsetAsync(ctx->d_xcursor, 0, kMaxRanks * sizeof(uint32_t), ctx->stream));
+        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+        {
+            ProfScope p(ctx, BC_K_EXCHANGE);
+            CK(ctx, launch_split(false, wide, ItemView{ctx->rec.lo, wide ? ctx->rec.hi : nullptr, nullptr}, ItemView{}, nullptr, 1, n_rec,
+                                 owner_level(ctx), ctx->d_xcursor, ctx->d_flush, true, ctx->stream));
+        }
+        CK(ctx, cudaMemcpyAsync(h, ctx->d_xcursor, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
+    }
+    ctx->x_local_valid = st.valid;
+    for (uint32_t r = 0; r < ctx->x_ranks; r++) sent[r] = ctx->x_sent[r] = h[r];
+    ctx->x_state = 1;
+    return BC_OK;
+}
+
+int bc_exchange_scatter(bc_ctx* ctx, const uint64_t* first) {
+    if (!ctx || !first) return BC_EINVAL;
+    if (ctx->x_state != 1) return fail(ctx, BC_ESTATE, "bc_exchange_scatter: call bc_exchange_count first (and nothing may be submitted in between)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint32_t cur[kMaxRanks] = {0};
+    PeerOut peers{};
+    for (uint32_t r = 0; r < ctx->x_ranks; r++) {
+        if (!ctx->x_peer[r]) return fail(ctx, BC_ESTATE, "bc_exchange_scatter: rank %u is not connected", r);
+        if (first[r] + ctx->x_sent[r] > ctx->xcap)
+            return fail(ctx, BC_EINVAL, "bc_exchange_scatter: rank %u would receive past its capacity (%llu + %llu > %llu): reopen larger", r,
+                        (unsigned long long)first[r], ctx->x_sent[r], ctx->xcap);
+        cur[r] = (uint32_t)first[r];
+        peers.lo[r] = ctx->x_peer[r];
+        peers.hi[r] = ctx->cfg.wide ? ctx->x_peer[r] + ctx->xcap : nullptr;
+    }
+    const bool wide = ctx->cfg.wide != 0;
+    memcpy(ctx->h_xcur, cur, sizeof cur);  // outlives this call: the copy below is asynchronous
+    CK(ctx, cudaMemcpyAsync(ctx->d_xcursor, ctx->h_xcur, sizeof cur, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope p(ctx, BC_K_EXCHANGE);
+        CK(ctx, launch_owner_scatter(wide, ItemView{ctx->rec.lo, wide ? ctx->rec.hi : nullptr, nullptr}, peers, ctx->rec_upper, owner_level(ctx),
+                                     ctx->d_xcursor, ctx->stream));
+    }
+    ctx->x_state = 2;
+    return BC_OK;
+}
+
+int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
+    if (!ctx) return BC_EINVAL;
+    if (ctx->x_state != 2) return fail(ctx, BC_ESTATE, "bc_exchange_finish: call bc_exchange_scatter first");
+    if (n_received > ctx->xcap) return fail(ctx, BC_EINVAL, "bc_exchange_finish: %llu records exceed the receive capacity", (unsigned long long)n_received);
+    CK(ctx, cudaSetDevice(ctx->device));
+    const bool wide = ctx->cfg.wide != 0;
+    const FlushSrc in{ItemView{ctx->d_xrecv, wide ? ctx->d_xrecv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
+    int rc = flush_core(ctx, in);
+    if (rc != BC_OK) return rc;
+    // this rank's share of the job's outcome: the records it owns (matched = distinct pairs, duplicates = their repeats)
+    unsigned long long h[BC_N_COUNTERS];
+    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    h[BC_CNT_MATCHED] = ctx->last_unique;
+    h[BC_CNT_DUPLICATES] = ctx->last_valid - ctx->last_unique;
+    CK(ctx, cudaMemcpy(ctx->d_counters, h, sizeof h, cudaMemcpyHostToDevice));
+    ctx->dup_applied = 0;
+    ctx->x_received = n_received;
+    ctx->x_state = 3;
+    return BC_OK;
+}
+
+// dst += src for the dense count table (what = 0) or the dense enrichment marginals (what = 1) of two contexts of this
+// process; src may live on another GPU (peer access is enabled as needed).  Both must be idle (synchronised).
+int bc_peer_add(bc_ctx* dst, bc_ctx* src, int what) {
+    if (!dst || !src || dst == src) return BC_EINVAL;
+    CK(dst, cudaSetDevice(dst->device));
+    int rc = enable_peer(dst, src->device);
+    if (rc != BC_OK) return rc;
+    if (what == BC_ADD_DENSE_COUNTS) {
+        if (dst->deferred || src->deferred || dst->tables.map.kind != 0 || src->tables.map.kind != 0 || dst->tables.map.cap != src->tables.map.cap)
+            return fail(dst, BC_ESTATE, "bc_peer_add: both contexts need the same dense count table");
+        CK(dst, launch_add_u64(dst->tables.map.data, src->tables.map.data, dst->tables.map.cap, dst->stream));
+        dst->imported_rows = dst->tables.map.cap;
+        dst->rows_valid = false;
+        dst->marg_valid = false;
+    } else if (what == BC_ADD_MARGINALS) {
+        if (!dst->marg_dense || !src->marg_dense || !dst->marg_valid || !src->marg_valid || dst->marg.n_total != src->marg.n_total)
+            return fail(dst, BC_ESTATE, "bc_peer_add: both contexts need computed dense marginals (bc_marginals)");
+        CK(dst, launch_add_u64(dst->d_marg, src->d_marg, dst->marg.n_total, dst->stream));
+    } else {
+        return BC_EINVAL;
+    }
+    CK(dst, cudaStreamSynchronize(dst->stream));
     return BC_OK;
 }
 
@@ -1804,7 +2035,7 @@ int bc_export_rows(bc_ctx* ctx, uint64_t** dev_key_lo, uint64_t** dev_key_hi, ui
 // schemes without a random barcode (with one, de-duplication is routed per record, see bc_decode_route).
 int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_key_hi, const uint64_t* dev_count, uint64_t n_rows) {
     if (!ctx) return BC_EINVAL;
-    if (ctx->cfg.has_umi) return fail(ctx, BC_ESTATE, "bc_import_rows: scheme has a random barcode; route records instead");
+    if (ctx->cfg.has_umi) return fail(ctx, BC_ESTATE, "bc_import_rows: scheme has a random barcode; exchange records instead (bc_exchange_*)");
     if (n_rows == 0) return BC_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     if (ctx->deferred) {  // kept aside; the next flush sums them with this rank's own (key, count) items
@@ -1826,8 +2057,8 @@ int bc_import_rows(bc_ctx* ctx, const uint64_t* dev_key_lo, const uint64_t* dev_
     ctx->imported_rows += n_rows;
     ProfScope p(ctx, BC_K_INSERT);
     CK(ctx, launch_insert(ctx->tables, reinterpret_cast<const unsigned long long*>(dev_key_lo),
-                          reinterpret_cast<const unsigned long long*>(dev_key_hi), nullptr,
-                          reinterpret_cast<const unsigned long long*>(dev_count), n_rows, nullptr, ctx->stream));
+                          reinterpret_cast<const unsigned long long*>(dev_key_hi),
+                          reinterpret_cast<const unsigned long long*>(dev_count), n_rows, ctx->stream));
     return BC_OK;
 }
 
@@ -1840,6 +2071,7 @@ int bc_dense_counts(bc_ctx* ctx, uint64_t** dev_counts, uint64_t* n) {
     *n = ctx->tables.map.cap;
     ctx->imported_rows = ctx->tables.map.cap;  // the caller is about to add other ranks' counts in place
     ctx->rows_valid = false;
+    ctx->marg_valid = false;
     return BC_OK;
 }
 
@@ -1867,6 +2099,8 @@ int bc_reset(bc_ctx* ctx) {
     ctx->rec_upper = 0;
     ctx->imp_n = 0;
     ctx->dup_applied = 0;
+    ctx->marg_valid = false;
+    ctx->x_state = 0;
     ctx->entries_upper = 0;
     ctx->imported_rows = 0;
     return rc;  // asynchronous: later work on the ctx stream is ordered after the clears

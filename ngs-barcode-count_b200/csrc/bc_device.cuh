@@ -71,6 +71,11 @@ struct DevCfg {
     uint32_t bs_two;
     uint32_t bs2_n[2][4];
     uint32_t bs2_sh[2][4][8];
+    // exact-match prefilter (phase A of the locate step): template word `xpivot`, four of its constant positions per base
+    // (a base with fewer than four repeats one: testing a position twice is harmless; xs_has bit b = base b has any).
+    // A window survives iff the read equals the template at all of them — necessary for an exact match.
+    uint32_t xpivot, xs_has;
+    uint32_t xs_sh[4][4];
     DevSlot slots[kMaxSlots];
     uint8_t order[kMaxSlots];  // sample first, then counted barcodes in order, then the random barcode
     DevQRun qruns[kMaxQRuns];
@@ -85,6 +90,7 @@ struct BatchView {
     const uint16_t* read_len;
     const uint8_t* qual;  // nullptr when the quality filter is off
     uint32_t n_reads, plane_stride, qual_stride, W;
+    uint32_t rep_chunks;  // 32-offset chunks the repair range of a read of this batch can have: ceil((32 W - L) / 32)
 };
 
 // Open-addressing tables.  kind 0: dense counts (index = key); kind 1: hash map key -> count; kind 2: hash set.

@@ -251,64 +251,127 @@ __device__ __forceinline__ void bs_blocks(BsPlanes& P, uint32_t M0, uint32_t M1,
 // Two predicates per window (Q1): the regex's exact test (a read N in a constant fails, format-N needs ACGT) and
 // the repair's masked Hamming distance (N on either side is a wildcard).  Leftmost exact window wins (P1);
 // otherwise the unique minimum over offsets [0, R-L) within the cap (P2, Q3, Q5).
-// Every window is first looked at through ONE template word (the pivot: the word with the most constant bases):
-// a window whose pivot word alone already has more than max_const_err mismatches can be neither exact nor within
-// the cap, so only the survivors (typically just the true offset) get the full-width test.
+//
+// The two run as separate phases of k_decode.  Phase A (every read): the exact test only.  Bit-sliced over 32 offsets:
+// for constant position q of the pivot word, funnelshift(M, q) — M the read's "differs from that position's base, or
+// is N" plane — says which of the 32 offsets fail there; OR-ing sixteen of them (four per base) leaves the offsets
+// that agree with the template on all sixteen, and only those (typically the one true offset) get the full-width
+// test.  16 funnel shifts + 8 LOP3 per 32 windows.  Phase B (only the reads phase A could not place, about a quarter
+// of a typical run): the masked Hamming scan, cut into (read, 32-offset chunk) work items that the CTA's threads take
+// in turn, so that the expensive counting prefilter below runs in full warps instead of in the few lanes of every
+// warp whose read needs it.
 template <int TW>
-__device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, const uint32_t* hi, const uint32_t* nm,
-                                       const uint32_t W, const int len, int* off_out, bool* repaired_out) {
-    const int L = cfg.L;
-    const int nwin = len - L + 1;  // <= 0: read shorter than the scheme (Q4) -> constant-region error
+__device__ __forceinline__ int locate_exact(const DevCfg& cfg, const uint32_t* lo, const uint32_t* hi, const uint32_t* nm,
+                                            const uint32_t W, const int nwin) {
+    const uint32_t kp = cfg.xpivot;
+    // word kp + c exists for every chunk c that holds a window; word kp + c + 1 may be the next plane's first word: see
+    // plane_bits
+    uint32_t al = lo[kp], ah = hi[kp], an = nm[kp];
+    for (int c = 0; (c << 5) < nwin; c++) {
+        const uint32_t j = kp + c + 1;
+        const uint32_t bl = lo[j], bh = hi[j], bn = nm[j];
+        uint32_t bad = 0;
+        if (cfg.xs_has & 1u) {  // template A = (0, 0)
+            const uint32_t M0 = al | ah | an, M1 = bl | bh | bn;
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[0][0]) | __funnelshift_r(M0, M1, cfg.xs_sh[0][1]);
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[0][2]) | __funnelshift_r(M0, M1, cfg.xs_sh[0][3]);
+        }
+        if (cfg.xs_has & 2u) {  // C = (1, 0)
+            const uint32_t M0 = ~al | ah | an, M1 = ~bl | bh | bn;
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[1][0]) | __funnelshift_r(M0, M1, cfg.xs_sh[1][1]);
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[1][2]) | __funnelshift_r(M0, M1, cfg.xs_sh[1][3]);
+        }
+        if (cfg.xs_has & 4u) {  // G = (0, 1)
+            const uint32_t M0 = al | ~ah | an, M1 = bl | ~bh | bn;
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[2][0]) | __funnelshift_r(M0, M1, cfg.xs_sh[2][1]);
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[2][2]) | __funnelshift_r(M0, M1, cfg.xs_sh[2][3]);
+        }
+        if (cfg.xs_has & 8u) {  // T = (1, 1)
+            const uint32_t M0 = ~(al & ah) | an, M1 = ~(bl & bh) | bn;
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[3][0]) | __funnelshift_r(M0, M1, cfg.xs_sh[3][1]);
+            bad |= __funnelshift_r(M0, M1, cfg.xs_sh[3][2]) | __funnelshift_r(M0, M1, cfg.xs_sh[3][3]);
+        }
+        uint32_t cand = ~bad;
+        const int rem = nwin - (c << 5);
+        if (rem < 32) cand &= (1u << rem) - 1u;
+        while (cand) {
+            const int s = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int o = (c << 5) + s;
+            uint32_t e = 0;
+#pragma unroll
+            for (int k = 0; k < TW; k++) {
+                const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
+                const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
+                const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
+                e |= (((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k]) | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
+            }
+            if (e == 0) return o;  // offsets are visited in increasing order: the leftmost exact window
+        }
+        al = bl;
+        ah = bh;
+        an = bn;
+    }
+    return -1;
+}
+
+// Result of one repair chunk, packed: [29:20] smallest distance, [17:16] how many offsets reach it (saturating at 2),
+// [15:0] one of them.
+__device__ __forceinline__ uint32_t rep_pack(uint32_t d, uint32_t cnt, uint32_t arg) { return d << 20 | min(cnt, 2u) << 16 | arg; }
+
+// Phase B, one work item: offsets [32 c, 32 c + 32) of the repair range [0, nwin - 1) of one read (Q3: the last offset
+// is never scanned).  Every window is first looked at through ONE template word (the pivot: the word with the most
+// constant bases): a window whose pivot word alone already has more than max_const_err mismatches cannot be within the
+// cap, so only the survivors get the full-width count.  The pivot test is bit-sliced over the 32 offsets: for each
+// constant position q of the pivot word, funnelshift(M, q) says which offsets mismatch there (N never mismatches), and
+// carry-save adders accumulate five counter planes that start at 15 - max_const_err, so the top plane is "over the cap".
+template <int TW>
+__device__ __forceinline__ uint32_t repair_chunk(const DevCfg& cfg, const uint32_t* lo, const uint32_t* hi, const uint32_t* nm,
+                                                 const uint32_t W, const int nwin, const int c) {
+    const uint32_t maxc = cfg.max_const_err;
+    const int rem = nwin - 1 - (c << 5);
+    if (rem <= 0) return rep_pack(maxc + 1, 0, 0);
     const uint32_t kp = cfg.pivot;
     const uint32_t p_lo = cfg.t_lo[kp], p_hi = cfg.t_hi[kp], p_cm = cfg.t_cm[kp];
-    const uint32_t maxc = cfg.max_const_err;
-    uint32_t best = maxc + 1, cnt = 0;
-    int arg = -1, first_exact = -1;
-    for (int c = 0; (c << 5) < nwin && first_exact < 0; c++) {
-        const uint32_t j = c + kp;
-        // j < W for every chunk that holds a window; word j + 1 may be the next plane's first word: see plane_bits
-        const uint32_t al = lo[j], bl = lo[j + 1];
-        const uint32_t ah = hi[j], bh = hi[j + 1];
-        const uint32_t an = nm[j], bn = nm[j + 1];
-        uint32_t cand = 0;
-        const int rem = nwin - (c << 5);
-        if (cfg.bs_two && rem > 8) {
-            // as below, over the constant positions of TWO template words (pivot, pivot + 1), whole blocks only: the
-            // third plane word is at worst the next plane's first word (see plane_bits), its bits beyond every window
-            const uint32_t cl = lo[j + 2], ch = hi[j + 2], cn = nm[j + 2];
-            BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
-            {
-                const uint32_t A0 = (al | ah) & ~an, A1 = (bl | bh) & ~bn, A2 = (cl | ch) & ~cn;
-                bs_blocks(P, A0, A1, cfg.bs2_n[0][0], cfg.bs2_sh[0][0]);
-                bs_blocks(P, A1, A2, cfg.bs2_n[1][0], cfg.bs2_sh[1][0]);
-            }
-            {
-                const uint32_t C0 = (~al | ah) & ~an, C1 = (~bl | bh) & ~bn, C2 = (~cl | ch) & ~cn;
-                bs_blocks(P, C0, C1, cfg.bs2_n[0][1], cfg.bs2_sh[0][1]);
-                bs_blocks(P, C1, C2, cfg.bs2_n[1][1], cfg.bs2_sh[1][1]);
-            }
-            {
-                const uint32_t G0 = (al | ~ah) & ~an, G1 = (bl | ~bh) & ~bn, G2 = (cl | ~ch) & ~cn;
-                bs_blocks(P, G0, G1, cfg.bs2_n[0][2], cfg.bs2_sh[0][2]);
-                bs_blocks(P, G1, G2, cfg.bs2_n[1][2], cfg.bs2_sh[1][2]);
-            }
-            {
-                const uint32_t T0 = ~(al & ah) & ~an, T1 = ~(bl & bh) & ~bn, T2 = ~(cl & ch) & ~cn;
-                bs_blocks(P, T0, T1, cfg.bs2_n[0][3], cfg.bs2_sh[0][3]);
-                bs_blocks(P, T1, T2, cfg.bs2_n[1][3], cfg.bs2_sh[1][3]);
-            }
-            cand = ~P.p16;
-        } else if (cfg.bs_ok && rem > 8) {
-            // 32 offsets at once: for every constant position q of the pivot word, bit s of (M >> q) says "offset s
-            // mismatches there" (M = the read's mismatch plane against that position's base, N never mismatches);
-            // the planes add them up.  Counters start at 15 - max_const_err, so plane 16 = "more than the cap".
-            BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
-            bs_base(P, (al | ah) & ~an, (bl | bh) & ~bn, cfg.pv_n[0], cfg.pv_sh4[0]);
-            bs_base(P, (~al | ah) & ~an, (~bl | bh) & ~bn, cfg.pv_n[1], cfg.pv_sh4[1]);
-            bs_base(P, (al | ~ah) & ~an, (bl | ~bh) & ~bn, cfg.pv_n[2], cfg.pv_sh4[2]);
-            bs_base(P, ~(al & ah) & ~an, ~(bl & bh) & ~bn, cfg.pv_n[3], cfg.pv_sh4[3]);
-            cand = ~P.p16;
-        } else {
+    const uint32_t j = c + kp;
+    const uint32_t al = lo[j], bl = lo[j + 1];
+    const uint32_t ah = hi[j], bh = hi[j + 1];
+    const uint32_t an = nm[j], bn = nm[j + 1];
+    uint32_t cand = 0;
+    if (cfg.bs_two && rem > 8) {
+        // over the constant positions of TWO template words (pivot, pivot + 1), whole blocks of four only: the third plane
+        // word is at worst the next plane's first word (see plane_bits), its bits beyond every window
+        const uint32_t cl = lo[j + 2], ch = hi[j + 2], cn = nm[j + 2];
+        BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
+        {
+            const uint32_t A0 = (al | ah) & ~an, A1 = (bl | bh) & ~bn, A2 = (cl | ch) & ~cn;
+            bs_blocks(P, A0, A1, cfg.bs2_n[0][0], cfg.bs2_sh[0][0]);
+            bs_blocks(P, A1, A2, cfg.bs2_n[1][0], cfg.bs2_sh[1][0]);
+        }
+        {
+            const uint32_t C0 = (~al | ah) & ~an, C1 = (~bl | bh) & ~bn, C2 = (~cl | ch) & ~cn;
+            bs_blocks(P, C0, C1, cfg.bs2_n[0][1], cfg.bs2_sh[0][1]);
+            bs_blocks(P, C1, C2, cfg.bs2_n[1][1], cfg.bs2_sh[1][1]);
+        }
+        {
+            const uint32_t G0 = (al | ~ah) & ~an, G1 = (bl | ~bh) & ~bn, G2 = (cl | ~ch) & ~cn;
+            bs_blocks(P, G0, G1, cfg.bs2_n[0][2], cfg.bs2_sh[0][2]);
+            bs_blocks(P, G1, G2, cfg.bs2_n[1][2], cfg.bs2_sh[1][2]);
+        }
+        {
+            const uint32_t T0 = ~(al & ah) & ~an, T1 = ~(bl & bh) & ~bn, T2 = ~(cl & ch) & ~cn;
+            bs_blocks(P, T0, T1, cfg.bs2_n[0][3], cfg.bs2_sh[0][3]);
+            bs_blocks(P, T1, T2, cfg.bs2_n[1][3], cfg.bs2_sh[1][3]);
+        }
+        cand = ~P.p16;
+    } else if (cfg.bs_ok && rem > 8) {
+        BsPlanes P{(cfg.bs_k & 1u) ? ~0u : 0u, (cfg.bs_k & 2u) ? ~0u : 0u, (cfg.bs_k & 4u) ? ~0u : 0u, (cfg.bs_k & 8u) ? ~0u : 0u, 0u};
+        bs_base(P, (al | ah) & ~an, (bl | bh) & ~bn, cfg.pv_n[0], cfg.pv_sh4[0]);
+        bs_base(P, (~al | ah) & ~an, (~bl | bh) & ~bn, cfg.pv_n[1], cfg.pv_sh4[1]);
+        bs_base(P, (al | ~ah) & ~an, (bl | ~bh) & ~bn, cfg.pv_n[2], cfg.pv_sh4[2]);
+        bs_base(P, ~(al & ah) & ~an, ~(bl & bh) & ~bn, cfg.pv_n[3], cfg.pv_sh4[3]);
+        cand = ~P.p16;
+    } else {  // a tail of at most 8 windows, or a cap above 15: window by window
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
             if (g < rem) {
@@ -322,56 +385,30 @@ __device__ __forceinline__ void locate(const DevCfg& cfg, const uint32_t* lo, co
                 }
             }
         }
-        }
-        if (rem < 32) cand &= (1u << rem) - 1u;
-        while (cand) {
-            const int s = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const int o = (c << 5) + s;
-            uint32_t d = 0, e = 0;
+    }
+    if (rem < 32) cand &= (1u << rem) - 1u;
+    uint32_t best = maxc + 1, cnt = 0, arg = 0;
+    while (cand) {
+        const int s = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int o = (c << 5) + s;
+        uint32_t d = 0;
 #pragma unroll
-            for (int k = 0; k < TW; k++) {
-                const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
-                const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
-                const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
-                const uint32_t x = ((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k];
-                e |= x | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
-                d += __popc(x & ~wn);
-            }
-            if (e == 0) {
-                first_exact = o;
-                break;
-            }
-            if (o < nwin - 1) {
-                if (d < best) {
-                    best = d;
-                    cnt = 1;
-                    arg = o;
-                } else if (d == best) {
-                    cnt++;
-                }
-            }
+        for (int k = 0; k < TW; k++) {
+            const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
+            const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
+            const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
+            d += __popc(((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k] & ~wn);
+        }
+        if (d < best) {
+            best = d;
+            cnt = 1;
+            arg = (uint32_t)o;
+        } else if (d == best) {
+            cnt++;
         }
     }
-    int off = -1;
-    bool repaired = false;
-    if (first_exact >= 0) {
-        off = first_exact;
-    } else if (cnt == 1 && best <= maxc) {
-        off = arg;
-        repaired = true;
-        if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
-            uint32_t bad = 0;
-#pragma unroll
-            for (int k = 0; k < TW; k++) bad |= plane_bits<false>(nm, W, off + (k << 5)) & cfg.t_fn[k];
-            if (bad) {
-                off = -1;
-                repaired = false;
-            }
-        }
-    }
-    *off_out = off;
-    *repaired_out = repaired;
+    return rep_pack(best, cnt, arg);
 }
 
 struct SlotBits {
@@ -392,81 +429,83 @@ __device__ __forceinline__ void key_or_index(Key& key, uint32_t idx, uint32_t sh
     if (!wide) key.lo |= (unsigned long long)idx << shift;
     else key_or(key, idx, shift);
 }
-__device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBits& b) {
+__device__ __forceinline__ void key_raw(Key& key, const DevSlot& S, const SlotBits& b, uint32_t wide) {
     // raw key (N kept as its own symbol, Q14): field = [lo:len][hi:len][nm:len]
+    if (!wide && 3u * S.len <= 64u) {  // the whole field in one 64-bit word, one shift
+        const unsigned long long f = (unsigned long long)b.lo | (unsigned long long)b.hi << S.len | (unsigned long long)b.nm << (2u * S.len);
+        key.lo |= f << S.key_shift;
+        return;
+    }
     key_or(key, b.lo, S.key_shift);
     key_or(key, b.hi, S.key_shift + S.len);
     key_or(key, b.nm, S.key_shift + 2 * S.len);
 }
 
-// K3 for one matched read: count it (info.rs:735-808) or, multi-GPU with a random barcode, hand it to its owner rank
-__device__ __forceinline__ int count_or_route(const DevCfg& cfg, const Tables& tables, const RouteOut& route, const RecOut& rec,
-                                              unsigned long long read_index, int flags, Key key, bool* new_key, bool* new_pair) {
+// K3 for one matched read that k_resolve finished: count it (info.rs:735-808) or fill its record slot
+__device__ __forceinline__ int count_or_append(const Tables& tables, const RecOut& rec, unsigned long long read_index, int flags,
+                                               Key key, bool* new_key, bool* new_pair) {
     if (flags & F_INSERT) return count_read(tables, key, new_key, new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
     if (flags & F_APPEND) {  // deferred counting: the record slot of this read (k_decode left it empty)
         const unsigned long long pos = *rec.cursor + read_index;
         rec.lo[pos] = key.lo;
         if (rec.hi) rec.hi[pos] = key.hi;
-        return BC_ST_MATCHED;
-    }
-    if (flags & F_ROUTE) {
-        const uint32_t owner = (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks);
-        const uint32_t slot = atomicAdd(&route.counts[owner * route.count_stride], 1u);
-        if (slot < route.capacity) route.dst[owner][slot] = key;
-        return -2;  // outcome is decided by the owner rank
     }
     return BC_ST_MATCHED;
 }
 
 constexpr int kDeferred = -3;  // thread-local status: the read went to the deferred list (k_resolve finishes it)
-constexpr int kRouted = -2;    // thread-local status: matched, handed to its owner rank (which decides matched/duplicate)
 
-// k_decode: one thread per read, kTile reads per CTA.  The tile's packed planes / qualities / lengths are contiguous
-// in global memory and land in shared memory through three TMA bulk copies signalled on one mbarrier.
+// k_decode: one thread per read, kTile reads per CTA.  The tile's packed planes and lengths are contiguous in global
+// memory and land in shared memory through two TMA bulk copies signalled on one mbarrier.  The quality bytes stay in
+// global memory: a read needs only the ~34 bytes under its barcodes, and without the 152-byte rows the tile is 66 bytes
+// per read instead of 218 (12 CTAs per SM instead of 8); every thread prefetches its row into L2 before the locate step.
+// Shared memory: [planes kTile x plane_stride u32][read_len kTile u16][repair results batch.rep_chunks x kTile u32]
 template <int TW>
 __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg cfg, const BatchView batch,
                                                   const DevAux aux, const Tables tables,
                                                   unsigned long long* __restrict__ counters, const DecodeOut out,
-                                                  const RouteOut route, const RecOut rec, const Deferred deferred,
-                                                  const int flags) {
+                                                  const RecOut rec, const Deferred deferred, const int flags) {
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_nlist, s_maxwin;
+    __shared__ uint16_t s_list[kTile];
 
     const uint32_t tid = threadIdx.x;
+    const int lane = tid & 31;
     const unsigned long long base = (unsigned long long)blockIdx.x * kTile;
     const uint32_t n_tile = (uint32_t)min((unsigned long long)kTile, batch.n_reads - base);
     const uint32_t W = batch.W;
     uint32_t* s_pl = smem;
-    // F_QUAL_GLOBAL: the quality bytes stay in global memory — a read needs only the ~34 bytes under its barcodes, and
-    // without the 152-byte rows the tile is 66 bytes per read instead of 218: 12 CTAs per SM instead of 8
-    const bool q_staged = batch.qual && !(flags & F_QUAL_GLOBAL);
-    uint8_t* s_q = reinterpret_cast<uint8_t*>(smem + kTile * batch.plane_stride);
-    uint16_t* s_len = reinterpret_cast<uint16_t*>(s_q + (q_staged ? kTile * batch.qual_stride : 0u));
+    uint16_t* s_len = reinterpret_cast<uint16_t*>(smem + kTile * batch.plane_stride);
+    uint32_t* s_res = reinterpret_cast<uint32_t*>(s_len + kTile);  // kTile * 2 bytes keeps it 4-byte aligned
 
+    const uint32_t* qrow = nullptr;
+    if (batch.qual && tid < n_tile) {  // this read's quality row: on its way into L2 while the planes are staged and searched
+        qrow = reinterpret_cast<const uint32_t*>(batch.qual + (base + tid) * batch.qual_stride);
+        const char* p = reinterpret_cast<const char*>(qrow);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        if (batch.qual_stride > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+    }
     {
         const uint32_t* g_pl = batch.planes + base * batch.plane_stride;
-        const uint8_t* g_q = q_staged ? batch.qual + base * batch.qual_stride : nullptr;
         const uint16_t* g_len = batch.read_len + base;
-        const uint32_t b_pl = n_tile * batch.plane_stride * 4u, b_q = g_q ? n_tile * batch.qual_stride : 0u, b_len = n_tile * 2u;
-        const bool bulk = (((b_pl | b_q | b_len) & 15u) == 0) &&
-                          ((((unsigned long long)g_pl | (unsigned long long)g_q | (unsigned long long)g_len) & 15ull) == 0);
+        const uint32_t b_pl = n_tile * batch.plane_stride * 4u, b_len = n_tile * 2u;
+        const bool bulk = (((b_pl | b_len) & 15u) == 0) && ((((unsigned long long)g_pl | (unsigned long long)g_len) & 15ull) == 0);
+        if (tid == 0) {
+            s_nlist = 0;
+            s_maxwin = 0;
+        }
         if (bulk) {  // uniform per CTA
             if (tid == 0) mbar_init(&s_bar, 1);
             __syncthreads();
             if (tid == 0) {
-                mbar_expect_tx(&s_bar, b_pl + b_q + b_len);
+                mbar_expect_tx(&s_bar, b_pl + b_len);
                 bulk_g2s(s_pl, g_pl, b_pl, &s_bar);
-                if (b_q) bulk_g2s(s_q, g_q, b_q, &s_bar);
                 bulk_g2s(s_len, g_len, b_len, &s_bar);
             }
             mbar_wait(&s_bar, 0);
         } else {  // ragged last tile / unaligned caller buffers: plain cooperative copy
             for (uint32_t i = tid; i < n_tile * batch.plane_stride; i += kTile) s_pl[i] = __ldg(g_pl + i);
-            if (g_q) {
-                const uint32_t* gq = reinterpret_cast<const uint32_t*>(g_q);
-                uint32_t* sq = reinterpret_cast<uint32_t*>(s_q);
-                for (uint32_t i = tid; i < n_tile * (batch.qual_stride >> 2); i += kTile) sq[i] = __ldg(gq + i);
-            }
             if (tid < n_tile) s_len[tid] = g_len[tid];
             __syncthreads();
         }
@@ -477,115 +516,155 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     int off = -1;
     bool repaired = false;
     Key key{0, 0};
+    const uint32_t* lo = s_pl + tid * batch.plane_stride;
+    const uint32_t* hi = lo + W;
+    const uint32_t* nm = hi + W;
+
+    // ---- K1, phase A: leftmost exact window of this thread's read
+    bool need_repair = false;
     if (tid < n_tile) {
-        const uint32_t* lo = s_pl + tid * batch.plane_stride;
-        const uint32_t* hi = lo + W;
-        const uint32_t* nm = hi + W;
         const uint32_t rl = s_len[tid];
         if (rl & BC_READ_UNSUPPORTED) {
             status = BC_ST_UNSUPPORTED;
         } else {
-            locate<TW>(cfg, lo, hi, nm, W, (int)(rl & 0x7FFF), &off, &repaired);
-            if (off < 0) {
-                status = BC_ST_CONSTANT;
-            } else if (flags & F_LOCATE_ONLY) {
-                status = BC_ST_MATCHED;
-            } else {
-                status = BC_ST_MATCHED;
-                // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
-                // Q6: after a repair the quality string is read from 0, not from the repaired offset.
-                if (cfg.n_qruns) {
-                    // byte sums with whole-word loads: the first and last word of a run are masked down to the bytes
-                    // that belong to it, dp4a against 0x01010101 adds the four bytes of a word.  The packer guarantees
-                    // every byte >= 33 ('!'); the threshold already includes that offset.
-                    const uint32_t q0 = repaired ? 0u : (uint32_t)off;
-                    if (!q_staged) {
-                        const uint32_t* qg = reinterpret_cast<const uint32_t*>(batch.qual + (base + tid) * batch.qual_stride);
-                        for (uint32_t r = 0; r < cfg.n_qruns; r++) {
-                            const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
-                            const uint32_t wa = a >> 2, wb = e1 >> 2;
-                            const uint32_t ma = 0xFFFFFFFFu << ((a & 3u) << 3), mb = 0xFFFFFFFFu >> ((3u - (e1 & 3u)) << 3);
-                            uint32_t sum;
-                            if (wa == wb) {
-                                sum = __dp4a(__ldg(qg + wa) & ma & mb, 0x01010101u, 0u);
-                            } else {
-                                const uint32_t first = __ldg(qg + wa), last = __ldg(qg + wb);
-                                sum = __dp4a(first & ma, 0x01010101u, 0u);
-#pragma unroll 1
-                                for (uint32_t k = wa + 1; k < wb; k++) sum = __dp4a(__ldg(qg + k), 0x01010101u, sum);
-                                sum = __dp4a(last & mb, 0x01010101u, sum);
-                            }
-                            if (sum < cfg.qruns[r].thresh) {
-                                status = BC_ST_LOW_QUALITY;
-                                break;
-                            }
-                        }
-                    } else {
-                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(s_q + tid * batch.qual_stride);
-                    for (uint32_t r = 0; r < cfg.n_qruns; r++) {
-                        const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
-                        const uint32_t wa = a >> 2, wb = e1 >> 2;
-                        const uint32_t ma = 0xFFFFFFFFu << ((a & 3u) << 3), mb = 0xFFFFFFFFu >> ((3u - (e1 & 3u)) << 3);
-                        uint32_t sum;
-                        if (wa == wb) {
-                            sum = __dp4a(qw[wa] & ma & mb, 0x01010101u, 0u);
-                        } else {
-                            sum = __dp4a(qw[wa] & ma, 0x01010101u, 0u);
-#pragma unroll 1  // one or two middle words: an unrolled ladder costs more than the loop
-                            for (uint32_t k = wa + 1; k < wb; k++) sum = __dp4a(qw[k], 0x01010101u, sum);
-                            sum = __dp4a(qw[wb] & mb, 0x01010101u, sum);
-                        }
-                        if (sum < cfg.qruns[r].thresh) {
-                            status = BC_ST_LOW_QUALITY;
-                            break;
-                        }
-                    }
-                    }
+            const int nwin = (int)(rl & 0x7FFF) - (int)cfg.L + 1;  // <= 0: read shorter than the scheme (Q4) -> constant-region error
+            status = BC_ST_CONSTANT;
+            if (nwin > 0) {
+                off = locate_exact<TW>(cfg, lo, hi, nm, W, nwin);
+                if (off >= 0) status = BC_ST_MATCHED;
+                else need_repair = nwin > 1;  // the repair range [0, nwin - 1) is not empty
+            }
+        }
+    }
+    // ---- K1, phase B: the reads without an exact window, as (read, chunk) items over all threads of the CTA
+    uint32_t my_li = 0;
+    {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, need_repair);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t at = 0;
+            if (lane == leader) at = atomicAdd(&s_nlist, (uint32_t)__popc(m));
+            at = __shfl_sync(0xFFFFFFFFu, at, leader);
+            if (need_repair) {
+                my_li = at + __popc(m & ((1u << lane) - 1u));
+                s_list[my_li] = (uint16_t)tid;
+                atomicMax(&s_maxwin, (uint32_t)((int)(s_len[tid] & 0x7FFF) - (int)cfg.L));  // size of this read's repair range
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_list = s_nlist;
+    if (n_list) {  // uniform per CTA
+        const uint32_t n_ch = min((s_maxwin + 31u) >> 5, batch.rep_chunks);  // equal for well-formed batches (read_len <= 32 W)
+        for (uint32_t it = tid; it < n_list * n_ch; it += kTile) {
+            const uint32_t ch = it / n_list, li = it - ch * n_list;
+            const uint32_t r = s_list[li];
+            const uint32_t* rlo = s_pl + r * batch.plane_stride;
+            const int nwin = (int)(s_len[r] & 0x7FFF) - (int)cfg.L + 1;
+            s_res[ch * kTile + li] = repair_chunk<TW>(cfg, rlo, rlo + W, rlo + 2 * W, W, nwin, (int)ch);
+        }
+        __syncthreads();
+        if (need_repair) {  // unique minimum over the chunks, within the cap (Q5)
+            uint32_t best = cfg.max_const_err + 1, cnt = 0, arg = 0;
+            for (uint32_t ch = 0; ch < n_ch; ch++) {
+                const uint32_t p = s_res[ch * kTile + my_li];
+                const uint32_t d = p >> 20, c = (p >> 16) & 3u;
+                if (d < best) {
+                    best = d;
+                    cnt = c;
+                    arg = p & 0xFFFFu;
+                } else if (d == best) {
+                    cnt += c;
                 }
-                // ---- K2b: barcode correction, sample first then counted barcodes in order (parse.rs:448-507).
-                // Fast paths only: anything that needs a search over the reference set goes to k_resolve.
-                if (status == BC_ST_MATCHED) {
-                    for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
-                        const uint32_t si = cfg.order[oi];
-                        const DevSlot& S = cfg.slots[si];
-                        const SlotBits b = slot_bits<false>(lo, hi, nm, W, off + S.offset, S.len);
-                        if (S.mode == MODE_RAW) {
-                            key_raw(key, S, b);
-                            continue;
-                        }
-                        uint32_t idx = kFail;
-                        bool defer = false;
-                        if (S.mode == MODE_TABLE) {
-                            if (b.nm == 0) idx = table_pick(__ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]), S.max_err);
-                            else if (S.n_inline && (b.nm & (b.nm - 1)) == 0) idx = table_lookup_1n(aux.tables + S.aux_off, S, b.lo, b.hi, b.nm);
-                            else defer = true;  // two or more N in one barcode: k_resolve
-                        } else if (S.mode == MODE_HASH) {
-                            if (b.nm == 0) idx = hash_exact(aux, S, b.lo, b.hi);
-                            if (idx == kFail) {
-                                if (!S.has_half || __popc(b.nm) > 1) defer = true;
-                                else defer = half_probe(aux, S, b.lo, b.hi, b.nm, &idx) == HALF_DEEPER;
-                            }
-                        } else {
-                            defer = true;
-                        }
-                        if (defer) {
-                            status = kDeferred;
-                            break;
-                        }
-                        if (out.slot_index) out.slot_index[(base + tid) * cfg.n_slots + si] = (int32_t)idx;
-                        if (idx == kFail) {
-                            status = S.kind == 'S' ? BC_ST_SAMPLE : BC_ST_COUNTED;
-                            break;
-                        }
-                        key_or_index(key, idx, S.key_shift, cfg.wide);
+            }
+            if (cnt == 1 && best <= cfg.max_const_err) {
+                off = (int)arg;
+                repaired = true;
+                status = BC_ST_MATCHED;
+                if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
+                    uint32_t bad = 0;
+#pragma unroll
+                    for (int k = 0; k < TW; k++) bad |= plane_bits<false>(nm, W, off + (k << 5)) & cfg.t_fn[k];
+                    if (bad) {
+                        off = -1;
+                        repaired = false;
+                        status = BC_ST_CONSTANT;
                     }
-                }
-                if (status == BC_ST_MATCHED) {
-                    if (flags & F_INSERT) status = count_read(tables, key, &new_key, &new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
-                    else if (flags & F_ROUTE) status = kRouted;  // appended to its owner's bucket below, warp-aggregated
                 }
             }
         }
+    }
+
+    if (status == BC_ST_MATCHED && !(flags & F_LOCATE_ONLY)) {
+        // ---- K2a: per-barcode average quality (parse.rs:331-375); runs and thresholds precomputed (Q8, Q12).
+        // Q6: after a repair the quality string is read from 0, not from the repaired offset.
+        // Byte sums with whole-word loads: the first and last word of a run are masked down to the bytes that belong to
+        // it, dp4a against 0x01010101 adds the four bytes of a word.  The packer guarantees every byte >= 33 ('!'); the
+        // threshold already includes that offset.  No early exit between runs: their loads overlap.
+        bool lowq = false;
+        if (cfg.n_qruns) {
+            const uint32_t q0 = repaired ? 0u : (uint32_t)off;
+            for (uint32_t r = 0; r < cfg.n_qruns; r++) {
+                const uint32_t a = q0 + cfg.qruns[r].off, e1 = a + cfg.qruns[r].len - 1u;
+                const uint32_t wa = a >> 2, wb = e1 >> 2;
+                const uint32_t ma = 0xFFFFFFFFu << ((a & 3u) << 3), mb = 0xFFFFFFFFu >> ((3u - (e1 & 3u)) << 3);
+                uint32_t sum;
+                if (wa == wb) {
+                    sum = __dp4a(__ldg(qrow + wa) & ma & mb, 0x01010101u, 0u);
+                } else {
+                    const uint32_t first = __ldg(qrow + wa), last = __ldg(qrow + wb);
+                    sum = __dp4a(first & ma, 0x01010101u, 0u);
+#pragma unroll 1
+                    for (uint32_t k = wa + 1; k < wb; k++) sum = __dp4a(__ldg(qrow + k), 0x01010101u, sum);
+                    sum = __dp4a(last & mb, 0x01010101u, sum);
+                }
+                lowq |= sum < cfg.qruns[r].thresh;
+            }
+        }
+        // ---- K2b: barcode correction, sample first then counted barcodes in order (parse.rs:448-507).
+        // Fast paths only: anything that needs a search over the reference set goes to k_resolve.
+        if (lowq) {
+            status = BC_ST_LOW_QUALITY;
+        } else {
+            for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
+                const uint32_t si = cfg.order[oi];
+                const DevSlot& S = cfg.slots[si];
+                const SlotBits b = slot_bits<false>(lo, hi, nm, W, off + S.offset, S.len);
+                if (S.mode == MODE_RAW) {
+                    key_raw(key, S, b, cfg.wide);
+                    continue;
+                }
+                uint32_t idx = kFail;
+                bool defer = false;
+                if (S.mode == MODE_TABLE) {
+                    if (b.nm == 0) idx = table_pick(__ldg(&aux.tables[S.aux_off + (b.lo | (b.hi << S.len))]), S.max_err);
+                    else if (S.n_inline && (b.nm & (b.nm - 1)) == 0) idx = table_lookup_1n(aux.tables + S.aux_off, S, b.lo, b.hi, b.nm);
+                    else defer = true;  // two or more N in one barcode: k_resolve
+                } else if (S.mode == MODE_HASH) {
+                    if (b.nm == 0) idx = hash_exact(aux, S, b.lo, b.hi);
+                    if (idx == kFail) {
+                        if (!S.has_half || __popc(b.nm) > 1) defer = true;
+                        else defer = half_probe(aux, S, b.lo, b.hi, b.nm, &idx) == HALF_DEEPER;
+                    }
+                } else {
+                    defer = true;
+                }
+                if (defer) {
+                    status = kDeferred;
+                    break;
+                }
+                if (out.slot_index) out.slot_index[(base + tid) * cfg.n_slots + si] = (int32_t)idx;
+                if (idx == kFail) {
+                    status = S.kind == 'S' ? BC_ST_SAMPLE : BC_ST_COUNTED;
+                    break;
+                }
+                key_or_index(key, idx, S.key_shift, cfg.wide);
+            }
+        }
+        if (status == BC_ST_MATCHED && (flags & F_INSERT))
+            status = count_read(tables, key, &new_key, &new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
+    }
+    if (tid < n_tile) {
         if (flags & F_APPEND) {
             // deferred counting: every read owns one record slot; unmatched reads (and reads handed to k_resolve, which
             // fills the slot itself when the read matches) leave a hole.  Consecutive lanes, consecutive slots.
@@ -604,33 +683,6 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
         }
     }
 
-    const int lane = tid & 31;
-    // ---- multi-GPU: matched (key, UMI) records go to the bucket of their owner rank.  Positions are reserved with ONE
-    // global atomic per CTA and rank (warp counts -> shared-memory prefix -> global cursor): the cursors are hot
-    // addresses and same-address atomics serialise in L2.
-    if (flags & F_ROUTE) {
-        __shared__ uint32_t s_rcnt[kMaxRanks], s_rbase[kMaxRanks];
-        if (tid < kMaxRanks) s_rcnt[tid] = 0;
-        __syncthreads();
-        const uint32_t owner = status == kRouted ? (uint32_t)(hash_key(key_shr(key, cfg.umi_bits)) % route.n_ranks) : 0xFFFFFFFFu;
-        uint32_t my_pos = 0;
-        for (uint32_t r = 0; r < route.n_ranks; r++) {
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, owner == r);
-            if (!m) continue;
-            const int leader = __ffs(m) - 1;
-            uint32_t at = 0;
-            if (lane == leader) at = atomicAdd(&s_rcnt[r], (uint32_t)__popc(m));
-            at = __shfl_sync(0xFFFFFFFFu, at, leader) + __popc(m & ((1u << lane) - 1u));
-            if (owner == r) my_pos = at;
-        }
-        __syncthreads();
-        if (tid < route.n_ranks && s_rcnt[tid]) s_rbase[tid] = atomicAdd(&route.counts[tid * route.count_stride], s_rcnt[tid]);
-        __syncthreads();
-        if (owner != 0xFFFFFFFFu) {
-            const uint32_t at = s_rbase[owner] + my_pos;
-            if (at < route.capacity) route.dst[owner][at] = key;
-        }
-    }
     // ---- deferred reads: one warp-aggregated append per warp
     {
         const unsigned dm = __ballot_sync(0xFFFFFFFFu, status == kDeferred);
@@ -646,9 +698,8 @@ __global__ void __launch_bounds__(kTile) k_decode(const __grid_constant__ DevCfg
     }
     // ---- outcome counters (info.rs:60-127): every lane contributes a 1 in its outcome's 8-bit field, two warp-wide
     // REDUX sums, then lanes 0..8 each add one counter with a single fire-and-forget RED — no shared memory and no CTA
-    // barrier (a barrier at the end made every warp wait for the CTA's slowest).  The adds go to one of kCounterStripes
-    // copies (by CTA) so that no address sees more than a few thousand of them per launch; k_fold_counters sums the
-    // copies into the context's counters right after the launch.
+    // barrier at the end.  The adds go to one of kCounterStripes copies (by CTA) so that no address sees more than a
+    // few thousand of them per launch; k_fold_counters sums the copies into the context's counters right after.
     if (counters) {
         const uint32_t fa = (status >= 0 && status < 4) ? 1u << (8 * status) : 0u;
         const uint32_t fb = (status >= 4 && status < 7 ? 1u << (8 * (status - 4)) : 0u) | (new_key ? 1u << 24 : 0u);
@@ -777,8 +828,7 @@ __device__ __forceinline__ uint32_t warp_scan_blocks(const DevAux& aux, const De
 
 __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg cfg, const BatchView batch, const DevAux aux,
                                                  const Tables tables, unsigned long long* __restrict__ counters,
-                                                 const DecodeOut out, const RouteOut route, const RecOut rec,
-                                                 const Deferred deferred, const int flags) {
+                                                 const DecodeOut out, const RecOut rec, const Deferred deferred, const int flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = *deferred.count;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -798,7 +848,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
             const DevSlot& S = cfg.slots[si];
             const SlotBits b = slot_bits<true>(lo, hi, nm, W, off + S.offset, S.len);  // lane-uniform
             if (S.mode == MODE_RAW) {
-                key_raw(key, S, b);
+                key_raw(key, S, b, cfg.wide);
                 continue;
             }
             uint32_t idx = kFail;
@@ -823,7 +873,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
         }
         if (lane == 0) {
             bool new_key = false, new_pair = false;
-            if (status == BC_ST_MATCHED) status = count_or_route(cfg, tables, route, rec, ri, flags, key, &new_key, &new_pair);
+            if (status == BC_ST_MATCHED) status = count_or_append(tables, rec, ri, flags, key, &new_key, &new_pair);
             c_matched += status == BC_ST_MATCHED;
             c_dup += status == BC_ST_DUPLICATE;
             c_sample += status == BC_ST_SAMPLE;
@@ -849,53 +899,49 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
     }
 }
 
-size_t decode_smem_bytes(const BatchView& b, int flags) {
-    return (size_t)kTile * (b.plane_stride * 4u + ((b.qual && !(flags & F_QUAL_GLOBAL)) ? b.qual_stride : 0u) + 2u);
-}
+size_t decode_smem_bytes(const BatchView& b) { return (size_t)kTile * (b.plane_stride * 4u + 2u + 4u * b.rep_chunks); }
 
 template <int TW>
 static cudaError_t launch_decode_tw(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                                    unsigned long long* counters, const DecodeOut& out, const RouteOut& route,
-                                    const RecOut& rec, const Deferred& deferred, int flags, cudaStream_t stream) {
-    const size_t smem = decode_smem_bytes(batch, flags);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+                                    unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred,
+                                    int flags, cudaStream_t stream) {
+    const size_t smem = decode_smem_bytes(batch);
+    if (smem > 48 * 1024) {  // per device and per instantiation: set on every such launch (a cheap driver call, reads above ~380 nt only)
         cudaError_t e = cudaFuncSetAttribute(k_decode<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const unsigned grid = (batch.n_reads + kTile - 1) / kTile;
-    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags);
+    k_decode<TW><<<grid, kTile, smem, stream>>>(cfg, batch, aux, tables, counters, out, rec, deferred, flags);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
-                          const Deferred& deferred, int flags, cudaStream_t stream) {
+                          unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
+                          cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     switch (cfg.TW) {
-        case 1: return launch_decode_tw<1>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 2: return launch_decode_tw<2>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 3: return launch_decode_tw<3>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 4: return launch_decode_tw<4>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 5: return launch_decode_tw<5>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 6: return launch_decode_tw<6>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 7: return launch_decode_tw<7>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
-        case 8: return launch_decode_tw<8>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags, stream);
+        case 1: return launch_decode_tw<1>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 2: return launch_decode_tw<2>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 3: return launch_decode_tw<3>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 4: return launch_decode_tw<4>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 5: return launch_decode_tw<5>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 6: return launch_decode_tw<6>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 7: return launch_decode_tw<7>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
+        case 8: return launch_decode_tw<8>(cfg, batch, aux, tables, counters, out, rec, deferred, flags, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // deferred reads of the batch just decoded (their number is read on the device: no host round trip)
 cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
-                           const Deferred& deferred, int flags, cudaStream_t stream) {
+                           unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
+                           cudaStream_t stream) {
     if (batch.n_reads == 0) return cudaSuccess;
     unsigned long long warps = batch.n_reads;  // at most one warp per read of the batch
     unsigned grid = (unsigned)((warps + 3) / 4);
     const unsigned cap = 148u * 16u;  // persistent warps stride over the list
     if (grid > cap) grid = cap;
-    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, tables, counters, out, route, rec, deferred, flags);
+    k_resolve<<<grid, 128, 0, stream>>>(cfg, batch, aux, tables, counters, out, rec, deferred, flags);
     return cudaGetLastError();
 }
 
@@ -927,97 +973,20 @@ cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint32_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Records (key incl. UMI) routed from other ranks, or (key, count) rows merged from other ranks' tables.
+// (key, count) rows merged from other ranks' tables (keys without the random barcode)
 __global__ void k_insert(const Tables tables, const unsigned long long* __restrict__ key_lo,
-                         const unsigned long long* __restrict__ key_hi, const Key* __restrict__ records,
-                         const unsigned long long* __restrict__ counts, const unsigned long long n,
-                         unsigned long long* __restrict__ counters) {
-    unsigned long long matched = 0, dup = 0, fresh = 0, pairs = 0;
+                         const unsigned long long* __restrict__ key_hi, const unsigned long long* __restrict__ counts,
+                         const unsigned long long n) {
+    unsigned long long fresh = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        bool new_key = false, new_pair = false;
-        if (records) {  // one read each, counted like a local one
-            if (count_read(tables, records[i], &new_key, &new_pair)) matched++;
-            else dup++;
-        } else {  // rows: keys without the random barcode, counts[i] reads each
-            Key k{key_lo[i], key_hi ? key_hi[i] : 0ULL};
-            map_add(tables.map, k, counts[i], &new_key);
-        }
+        bool new_key = false;
+        Key k{key_lo[i], key_hi ? key_hi[i] : 0ULL};
+        map_add(tables.map, k, counts[i], &new_key);
         fresh += new_key;
-        pairs += new_pair;
     }
-    for (int o = 16; o; o >>= 1) {
-        matched += __shfl_xor_sync(0xFFFFFFFFu, matched, o);
-        dup += __shfl_xor_sync(0xFFFFFFFFu, dup, o);
-        fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
-        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (counters) {
-            if (matched) atomicAdd(&counters[BC_CNT_MATCHED], matched);
-            if (dup) atomicAdd(&counters[BC_CNT_DUPLICATES], dup);
-        }
-        if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
-        if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
-    }
-}
-
-// Local buckets -> the owners' receive regions over NVLink.  Consecutive lanes move consecutive 16-byte records, so
-// the peer stores leave the SM as full 512-byte warp transactions (stores issued record by record from inside the
-// decode kernel were transaction-rate bound on NVLink: 32 GB/s at 8 GPUs).
-__global__ void k_push(const RouteOut local, const RouteOut remote, uint32_t* __restrict__ compact_counts) {
-    if (blockIdx.x == 0 && threadIdx.x < local.n_ranks)  // contiguous counts for the caller's all-gather
-        compact_counts[threadIdx.x] = (uint32_t)min((unsigned long long)local.counts[threadIdx.x * local.count_stride], local.capacity);
-    for (uint32_t r = 0; r < local.n_ranks; r++) {
-        const unsigned long long n = min((unsigned long long)local.counts[r * local.count_stride], local.capacity);
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(local.dst[r]);
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(remote.dst[r]);
-        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-             i += (unsigned long long)gridDim.x * blockDim.x)
-            dst[i] = src[i];
-    }
-}
-
-cudaError_t launch_push(const RouteOut& local, const RouteOut& remote, uint32_t* compact_counts, cudaStream_t stream) {
-    k_push<<<148 * 4, 256, 0, stream>>>(local, remote, compact_counts);
-    return cudaGetLastError();
-}
-
-// routed records of one round: segment s = what rank s sent to this rank, its length read on the device
-__global__ void k_insert_segments(const Tables tables, const Key* __restrict__ records, const unsigned long long capacity,
-                                  const uint32_t* __restrict__ counts, const uint32_t count_stride, const uint32_t n_segments,
-                                  unsigned long long* __restrict__ counters) {
-    unsigned long long matched = 0, dup = 0, fresh = 0, pairs = 0;
-    for (uint32_t s = 0; s < n_segments; s++) {
-        const unsigned long long n = min((unsigned long long)counts[s * count_stride], capacity);
-        const Key* seg = records + (unsigned long long)s * capacity;
-        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-             i += (unsigned long long)gridDim.x * blockDim.x) {
-            bool new_key = false, new_pair = false;
-            if (count_read(tables, seg[i], &new_key, &new_pair)) matched++;
-            else dup++;
-            fresh += new_key;
-            pairs += new_pair;
-        }
-    }
-    for (int o = 16; o; o >>= 1) {
-        matched += __shfl_xor_sync(0xFFFFFFFFu, matched, o);
-        dup += __shfl_xor_sync(0xFFFFFFFFu, dup, o);
-        fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
-        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (matched) atomicAdd(&counters[BC_CNT_MATCHED], matched);
-        if (dup) atomicAdd(&counters[BC_CNT_DUPLICATES], dup);
-        if (fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
-        if (pairs && tables.set.n_entries) atomicAdd(tables.set.n_entries, pairs);
-    }
-}
-
-cudaError_t launch_insert_segments(const Tables& tables, const Key* records, unsigned long long capacity, const uint32_t* counts,
-                                   uint32_t count_stride, uint32_t n_segments, unsigned long long* counters, cudaStream_t stream) {
-    k_insert_segments<<<148 * 16, 256, 0, stream>>>(tables, records, capacity, counts, count_stride, n_segments, counters);
-    return cudaGetLastError();
+    for (int o = 16; o; o >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, o);
+    if ((threadIdx.x & 31) == 0 && fresh && tables.map.n_entries) atomicAdd(tables.map.n_entries, fresh);
 }
 
 static unsigned grid_for(unsigned long long n, unsigned block) {
@@ -1027,10 +996,9 @@ static unsigned grid_for(unsigned long long n, unsigned block) {
 }
 
 cudaError_t launch_insert(const Tables& tables, const unsigned long long* key_lo, const unsigned long long* key_hi,
-                          const Key* records, const unsigned long long* counts, unsigned long long n,
-                          unsigned long long* counters, cudaStream_t stream) {
+                          const unsigned long long* counts, unsigned long long n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_insert<<<grid_for(n, 256), 256, 0, stream>>>(tables, key_lo, key_hi, records, counts, n, counters);
+    k_insert<<<grid_for(n, 256), 256, 0, stream>>>(tables, key_lo, key_hi, counts, n);
     return cudaGetLastError();
 }
 
@@ -1131,6 +1099,126 @@ cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned lon
                             cudaStream_t stream) {
     if (n_rows == 0) return cudaSuccess;
     k_marginal<<<grid_for(n_rows, 256), 256, 0, stream>>>(key_lo, key_hi, count, n_rows, mask, dst);
+    return cudaGetLastError();
+}
+
+// ---- K4: enrichment marginals, dense (info.rs:840-904).  One pass over the final rows fills every single- and
+// double-barcode marginal at once.  Singles (a few thousand counters that every row hits) are privatised in shared memory and
+// flushed once per CTA; doubles (2^20 counters each for three 1,024-barcode slots: L2-resident) take one fire-and-forget
+// RED per row and pair.
+__device__ __forceinline__ uint32_t key_field(unsigned long long lo, unsigned long long hi, uint32_t shift, uint32_t bits) {
+    if (bits == 0) return 0u;
+    unsigned long long v;
+    if (shift >= 64) v = hi >> (shift - 64);
+    else v = (lo >> shift) | (shift ? hi << (64 - shift) : 0ULL);
+    return (uint32_t)v & (0xFFFFFFFFu >> (32 - bits));  // index fields are at most 24 bits wide (plan_marginals)
+}
+
+__global__ void __launch_bounds__(256) k_marginals(const unsigned long long* __restrict__ key_lo, const unsigned long long* __restrict__ key_hi,
+                                                   const unsigned long long* __restrict__ count, const unsigned long long n_rows,
+                                                   const __grid_constant__ MargPlan plan, unsigned long long* __restrict__ dense,
+                                                   const int priv) {
+    extern __shared__ unsigned long long s_single[];  // plan.n_single counters when priv
+    if (priv) {
+        for (uint32_t i = threadIdx.x; i < plan.n_single; i += blockDim.x) s_single[i] = 0ULL;
+        __syncthreads();
+    }
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_rows;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long lo = key_lo[i], hi = key_hi ? key_hi[i] : 0ULL, c = count[i];
+        const unsigned long long smp = key_field(lo, hi, plan.s_shift, plan.s_bits);
+        for (uint32_t a = 0; a < plan.k; a++) {
+            const unsigned long long idx = plan.s_off[a] + ((smp << plan.f_bits[a]) | key_field(lo, hi, plan.f_shift[a], plan.f_bits[a]));
+            if (priv) atomicAdd(&s_single[idx], c);
+            else atomicAdd(&dense[idx], c);
+        }
+        for (uint32_t p = 0; p < plan.n_pairs; p++) {
+            const uint32_t a = plan.pa[p], b = plan.pb[p];
+            const unsigned long long fa = key_field(lo, hi, plan.f_shift[a], plan.f_bits[a]);
+            const unsigned long long fb = key_field(lo, hi, plan.f_shift[b], plan.f_bits[b]);
+            atomicAdd(&dense[plan.d_off[p] + ((((smp << plan.f_bits[b]) | fb) << plan.f_bits[a]) | fa)], c);
+        }
+    }
+    if (priv) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < plan.n_single; i += blockDim.x) {
+            const unsigned long long v = s_single[i];
+            if (v) atomicAdd(&dense[i], v);  // the singles come first in `dense`
+        }
+    }
+}
+
+size_t marginal_smem_limit() { return 48 * 1024; }
+
+cudaError_t launch_marginals_dense(const unsigned long long* key_lo, const unsigned long long* key_hi, const unsigned long long* count,
+                                   unsigned long long n_rows, const MargPlan& plan, unsigned long long* dense, cudaStream_t stream) {
+    if (n_rows == 0) return cudaSuccess;
+    const bool priv = plan.n_single * 8 <= marginal_smem_limit();
+    unsigned long long g = (n_rows + 255) / 256;
+    if (g > 148ULL * 8) g = 148ULL * 8;  // persistent CTAs: the private singles are flushed once per CTA
+    k_marginals<<<(unsigned)g, 256, priv ? plan.n_single * 8 : 0, stream>>>(key_lo, key_hi, count, n_rows, plan, dense, priv ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// blockIdx.y = marginal (singles first, then pairs); non-zero counters of it -> rows, or just their number
+__global__ void k_marginal_rows(const __grid_constant__ MargPlan plan, const uint32_t m_first, const unsigned long long* __restrict__ dense,
+                                unsigned long long* __restrict__ key_lo, unsigned long long* __restrict__ key_hi,
+                                unsigned long long* __restrict__ count, uint32_t* __restrict__ mask, unsigned long long* __restrict__ n_out) {
+    const uint32_t m = m_first + blockIdx.y;
+    const bool single = m < plan.k;
+    const uint32_t a = single ? m : plan.pa[m - plan.k], b = single ? 0u : plan.pb[m - plan.k];
+    const unsigned long long off = single ? plan.s_off[a] : plan.d_off[m - plan.k];
+    const uint32_t bits = plan.s_bits + plan.f_bits[a] + (single ? 0u : plan.f_bits[b]);
+    const unsigned long long n = 1ULL << bits;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long span = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long first = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    for (unsigned long long i0 = first - lane; i0 < n; i0 += span) {  // warp-uniform trip count
+        const unsigned long long i = i0 + lane;
+        const unsigned long long c = i < n ? dense[off + i] : 0ULL;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, c != 0ULL);
+        if (!bal) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (c != 0ULL && key_lo) {
+            const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+            const unsigned long long fa = i & ((1ULL << plan.f_bits[a]) - 1ULL);
+            unsigned long long rest = i >> plan.f_bits[a], fb = 0;
+            if (!single) {
+                fb = rest & ((1ULL << plan.f_bits[b]) - 1ULL);
+                rest >>= plan.f_bits[b];
+            }
+            Key k{0, 0};
+            key_or(k, fa, plan.f_shift[a]);
+            if (!single) key_or(k, fb, plan.f_shift[b]);
+            if (plan.s_bits) key_or(k, rest, plan.s_shift);
+            key_lo[pos] = k.lo;
+            key_hi[pos] = k.hi;
+            count[pos] = c;
+            mask[pos] = single ? 1u << a : (1u << a) | (1u << b);
+        }
+    }
+}
+
+cudaError_t launch_marginals_rows(const MargPlan& plan, uint32_t m_first, uint32_t m_count, const unsigned long long* dense,
+                                  unsigned long long* key_lo, unsigned long long* key_hi, unsigned long long* count, uint32_t* mask,
+                                  unsigned long long* n_out, cudaStream_t stream) {
+    if (m_count == 0) return cudaSuccess;
+    if (m_first + m_count > plan.k + plan.n_pairs) return cudaErrorInvalidValue;
+    k_marginal_rows<<<dim3(148 * 2, m_count), 256, 0, stream>>>(plan, m_first, dense, key_lo, key_hi, count, mask, n_out);
+    return cudaGetLastError();
+}
+
+__global__ void k_add_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, const unsigned long long n) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] += src[i];
+}
+
+cudaError_t launch_add_u64(unsigned long long* dst, const unsigned long long* src, unsigned long long n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_add_u64<<<grid_for(n, 256), 256, 0, stream>>>(dst, src, n);
     return cudaGetLastError();
 }
 

@@ -13,17 +13,12 @@ struct DecodeOut {  // all optional (test hooks / decode_only)
     unsigned long long* key_hi;
 };
 
-constexpr int kMaxRanks = 8;  // one box
+constexpr int kMaxRanks = 8;  // GPUs of one box (NVLink / NVSwitch peers)
 
-// multi-GPU: matched (key, UMI) records are written to their owner rank's bucket instead of being counted.  dst[r] is a
-// local bucket (bc_decode_route) or rank r's receive region mapped over NVLink (bc_route_submit): plain peer stores
-// from inside the decode kernel, cursors stay local — the transfer overlaps the decode, no separate copy step.
-struct RouteOut {
-    Key* dst[kMaxRanks];
-    unsigned long long capacity;  // records per destination
-    uint32_t* counts;             // local cursors: counts[r * count_stride]
-    uint32_t count_stride;        // cursors of different ranks on different cache lines (same-sector atomics serialise)
-    uint32_t n_ranks;
+// multi-GPU exchange (launch_owner_scatter): the record buffers of the owner ranks, local or mapped over NVLink
+struct PeerOut {
+    unsigned long long* lo[kMaxRanks];
+    unsigned long long* hi[kMaxRanks];  // nullptr for keys of at most 63 bits
 };
 
 struct DevAux {  // reference sets and their accelerators
@@ -51,27 +46,25 @@ struct RecOut {
     const unsigned long long* cursor;      // records appended before this batch (bumped by launch_bump after the batch)
 };
 
-enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_ROUTE = 4, F_LOCATE_ONLY = 8, F_APPEND = 16, F_QUAL_GLOBAL = 32 };
+enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_LOCATE_ONLY = 8, F_APPEND = 16 };
 
 // k_decode adds its outcome counters to striped copies (kCounterStripes x kCounterStride u64: the BC_N_COUNTERS
 // outcomes, then new map / set entries); launch_fold_counters sums them into the BC_N_COUNTERS + 2 counters of the ctx.
 constexpr uint32_t kCounterStripes = 64, kCounterStride = 16;
 cudaError_t launch_fold_counters(unsigned long long* stripes, unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                          unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
-                          const Deferred& deferred, int flags, cudaStream_t stream);
+                          unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
+                          cudaStream_t stream);
 cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
-                           unsigned long long* counters, const DecodeOut& out, const RouteOut& route, const RecOut& rec,
-                           const Deferred& deferred, int flags, cudaStream_t stream);
+                           unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
+                           cudaStream_t stream);
 
 // fills MODE_TABLE lookups with the exact correction result for every N-free barcode value
 cudaError_t launch_build_table(const DevSlot& slot, const DevAux& aux, uint32_t* table, cudaStream_t stream);
 
-// records != nullptr: n reads (key incl. random barcode) counted like local ones, bumping matched/duplicates;
-// otherwise n (key, count) rows added to the map
+// n (key, count) rows added to the map
 cudaError_t launch_insert(const Tables& tables, const unsigned long long* key_lo, const unsigned long long* key_hi,
-                          const Key* records, const unsigned long long* counts, unsigned long long n,
-                          unsigned long long* counters, cudaStream_t stream);
+                          const unsigned long long* counts, unsigned long long n, cudaStream_t stream);
 
 // occupied entries of `t` (dense: non-zero counts) appended to the row arrays; *n_rows is a device counter
 cudaError_t launch_compact(const DevTable& t, unsigned long long* key_lo, unsigned long long* key_hi,
@@ -84,17 +77,34 @@ cudaError_t launch_marginal(const unsigned long long* key_lo, const unsigned lon
 
 cudaError_t launch_clear_map(const DevTable& t, cudaStream_t stream);
 
-// copies the local buckets (local.counts[r] records each) to remote.dst[r] with coalesced 16-byte lanes
-cudaError_t launch_push(const RouteOut& local, const RouteOut& remote, uint32_t* compact_counts, cudaStream_t stream);
-
-// routed records received from every rank: segment s holds counts[s * count_stride] records at records + s * capacity
-cudaError_t launch_insert_segments(const Tables& tables, const Key* records, unsigned long long capacity, const uint32_t* counts,
-                                   uint32_t count_stride, uint32_t n_segments, unsigned long long* counters, cudaStream_t stream);
+// ---- K4, enrichment marginals (info.rs:840-904) over index-coded keys: dense counter arrays, one pass over the rows ----
+// single a   : counter [(sample << bits_a) | f_a]                       at s_off[a]
+// double a<b : counter [(((sample << bits_b) | f_b) << bits_a) | f_a]   at d_off[pair]
+constexpr int kMaxPairs = kMaxSlots * (kMaxSlots - 1) / 2;
+struct MargPlan {
+    uint32_t k;  // counted barcodes
+    uint32_t f_shift[kMaxSlots], f_bits[kMaxSlots];  // their fields in a row key (random barcode already dropped)
+    uint32_t s_shift, s_bits;                        // the sample field (0 bits: none)
+    uint32_t n_pairs;                                // 0: singles only
+    uint8_t pa[kMaxPairs], pb[kMaxPairs];
+    unsigned long long s_off[kMaxSlots], d_off[kMaxPairs];
+    unsigned long long n_single, n_total;  // counters in the singles / in all arrays
+};
+size_t marginal_smem_limit();
+cudaError_t launch_marginals_dense(const unsigned long long* key_lo, const unsigned long long* key_hi, const unsigned long long* count,
+                                   unsigned long long n_rows, const MargPlan& plan, unsigned long long* dense, cudaStream_t stream);
+// non-zero counters of marginals [m_first, m_first + m_count) (singles first, then pairs) -> (key, count, mask) rows;
+// key_lo == nullptr only counts them into *n_out
+cudaError_t launch_marginals_rows(const MargPlan& plan, uint32_t m_first, uint32_t m_count, const unsigned long long* dense,
+                                  unsigned long long* key_lo, unsigned long long* key_hi, unsigned long long* count, uint32_t* mask,
+                                  unsigned long long* n_out, cudaStream_t stream);
+// dst[i] += src[i] (src may be another GPU's memory)
+cudaError_t launch_add_u64(unsigned long long* dst, const unsigned long long* src, unsigned long long n, cudaStream_t stream);
 
 // move every entry of `src` (hash kinds) into `dst`
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);
 
-size_t decode_smem_bytes(const BatchView& batch, int flags);
+size_t decode_smem_bytes(const BatchView& batch);
 
 // ---- deferred partitioned counting (bc_partition.cu) ---------------------------------------------------------------
 // Items are structure-of-arrays (lo, hi, w): hi == nullptr for keys of at most 63 bits, w == nullptr for weight 1.
@@ -112,7 +122,7 @@ struct FlushStats {  // device-side results of one flush (u64 each)
     unsigned long long max_bin;   // largest partition of the last histogram that asked for it
     unsigned long long big_items; // items in partitions larger than the limit given to that scan
 };
-enum ReduceMode { RED_DEDUPE = 0, RED_COUNT = 1 };
+enum ReduceMode { RED_DEDUPE = 0, RED_COUNT = 1, RED_DEDUPE_KEYED = 2 };
 uint32_t reduce_fill(bool wide);   // target items per hashed partition
 uint32_t reduce_chunk(bool wide);  // items per fixed chunk (pre-aggregation of schemes without a random barcode)
 
@@ -147,12 +157,9 @@ cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_
                           unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
                           unsigned long long out_cap, FlushStats* stats, uint32_t skip_over /* > 0: leave larger partitions alone */,
                           cudaStream_t stream);
-// routed records received from every rank appended to the record buffer at *cursor (then the cursor is bumped)
-cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,
-                                   uint32_t n_segments, const RecOut& rec, unsigned long long rec_cap, unsigned long long* cursor,
-                                   unsigned long long* counters, FlushStats* stats, cudaStream_t stream);
-cudaError_t launch_append_records(const Key* records, unsigned long long n, const RecOut& rec, unsigned long long* counters,
-                                  cudaStream_t stream);
+// multi-GPU exchange: valid items of `in` -> peers.lo/hi[owner] at cursors[owner]++ (see bc_partition.cu)
+cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& peers, unsigned long long n_total, const SplitLevel& lv,
+                                 uint32_t* cursors, cudaStream_t stream);
 // global-table path over the record buffer (oversized partitions, forced by BC_FLUSH_GLOBAL): counts like k_insert
 cudaError_t launch_insert_items(const Tables& tables, const ItemView& in, bool wide, unsigned long long n, FlushStats* stats,
                                 cudaStream_t stream);

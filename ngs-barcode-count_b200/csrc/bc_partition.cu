@@ -154,10 +154,14 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const ItemView in,
     }
 }
 
-template <bool WIDE, bool WEIGHTED, int IPT>
-__global__ void __launch_bounds__(kScatterThreads) k_split_scatter(const ItemView in, const ItemView out, const uint32_t* __restrict__ seg_starts,
-                                                                 const uint32_t workers, const unsigned long long n_total,
-                                                                 const SplitLevel lv, uint32_t* __restrict__ bins) {
+// PEER: the bins are owner ranks (F <= kMaxRanks) and bin b's items go to peers.lo/hi[b] — another GPU's receive buffer
+// mapped over NVLink — at the positions the cursors give; a tile's run for one owner is hundreds of consecutive records,
+// so the peer stores leave the SM as full-width transactions.
+template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
+__global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const ItemView in, const ItemView out, const PeerOut peers,
+                                                                    const uint32_t* __restrict__ seg_starts, const uint32_t workers,
+                                                                    const unsigned long long n_total, const SplitLevel lv,
+                                                                    uint32_t* __restrict__ bins) {
     constexpr uint32_t T = kScatterThreads * IPT;
     extern __shared__ __align__(16) unsigned long long split_stage[];  // [lo | hi | w] x T u64, then T u32 positions
     __shared__ uint32_t s_hist[1u << kSplitMaxBits], s_delta[1u << kSplitMaxBits];
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_split_scatter(const ItemVie
     uint32_t* st_pos = reinterpret_cast<uint32_t*>(st_w + T);
     for (unsigned long long t0 = a + (unsigned long long)worker * T; t0 < e; t0 += (unsigned long long)workers * T) {
         unsigned long long lo[IPT], hi[IPT], w[IPT];
-        uint32_t bin[IPT];
+        uint32_t bin2[IPT / 2];  // two 16-bit bins per register (F <= 2048; 0xFFFF = hole)
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             const unsigned long long i = t0 + (unsigned long long)k * kScatterThreads + tid;
@@ -186,10 +190,13 @@ __global__ void __launch_bounds__(kScatterThreads) k_split_scatter(const ItemVie
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            bin[k] = kEmpty32;
-            if (!item_valid(lo[k], hi[k], WIDE)) continue;
-            bin[k] = split_digit(lo[k], hi[k], lv);
-            atomicAdd(&s_hist[bin[k]], 1u);
+            uint32_t bn = 0xFFFFu;
+            if (item_valid(lo[k], hi[k], WIDE)) {
+                bn = split_digit(lo[k], hi[k], lv);
+                atomicAdd(&s_hist[bn], 1u);
+            }
+            if (k & 1) bin2[k >> 1] |= bn << 16;
+            else bin2[k >> 1] = bn;
         }
         __syncthreads();
         // exclusive prefix of the tile's histogram (thread t owns bins [t * per, t * per + per)); run reservation
@@ -226,19 +233,27 @@ __global__ void __launch_bounds__(kScatterThreads) k_split_scatter(const ItemVie
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            if (bin[k] == kEmpty32) continue;
-            const uint32_t at = atomicAdd(&s_hist[bin[k]], 1u);
+            const uint32_t bn = (k & 1) ? bin2[k >> 1] >> 16 : bin2[k >> 1] & 0xFFFFu;
+            if (bn == 0xFFFFu) continue;
+            const uint32_t at = atomicAdd(&s_hist[bn], 1u);
             st_lo[at] = lo[k];
             if (WIDE) st_hi[at] = hi[k];
             if (WEIGHTED) st_w[at] = w[k];
-            st_pos[at] = s_delta[bin[k]] + at;
+            st_pos[at] = s_delta[bn] + at;
         }
         __syncthreads();
         for (uint32_t j = tid; j < n_tile; j += kScatterThreads) {
             const uint32_t pos = st_pos[j];
-            out.lo[pos] = st_lo[j];
-            if (WIDE) out.hi[pos] = st_hi[j];
-            if (WEIGHTED) out.w[pos] = st_w[j];
+            if (PEER) {  // the sorted tile is in bin order and s_hist[b] is now the end of bin b's run: count the runs that end at or before j
+                uint32_t b = 0;
+                for (uint32_t q = 0; q + 1 < F; q++) b += j >= s_hist[q];
+                peers.lo[b][pos] = st_lo[j];
+                if (WIDE) peers.hi[b][pos] = st_hi[j];
+            } else {
+                out.lo[pos] = st_lo[j];
+                if (WIDE) out.hi[pos] = st_hi[j];
+                if (WEIGHTED) out.w[pos] = st_w[j];
+            }
         }
         __syncthreads();
     }
@@ -327,14 +342,30 @@ __device__ __forceinline__ Key drop_umi(unsigned long long lo, unsigned long lon
     return key_shr(Key{lo, hi}, umi_bits);
 }
 
+// Weights travel as u64 but are summed in 32-bit shared-memory counters: a weight or a per-key sum of 2^32 or more raises
+// `overflow`, and the host redoes the flush through the global tables, which add in 64 bits (the reference counts in usize).
+__device__ __forceinline__ uint32_t narrow_weight(unsigned long long w, FlushStats* stats) {
+    if (w >> 32) atomicExch(&stats->overflow, 16ULL);
+    return (uint32_t)w;
+}
+__device__ __forceinline__ void add_weight(uint32_t* c, uint32_t w, FlushStats* stats) {
+    const uint32_t old = atomicAdd(c, w);
+    if (old + w < old) atomicExch(&stats->overflow, 16ULL);
+}
+
 __device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t value) {  // n multiple of 4, p 16-byte aligned
     uint4* q = reinterpret_cast<uint4*>(p);
     const uint4 v = make_uint4(value, value, value, value);
     for (uint32_t i = threadIdx.x; i < n / 4; i += kRedThreads) q[i] = v;
 }
 
-// MODE RED_DEDUPE: in = records (key incl. random barcode), out = (record >> umi_bits, distinct records with that key)
-// MODE RED_COUNT : in = (key, weight) items,                out = (key, sum of weights)
+// MODE RED_DEDUPE      : in = records (key incl. random barcode), out = (record >> umi_bits, distinct records with that key)
+// MODE RED_COUNT       : in = (key, weight) items,                out = (key, sum of weights)
+// MODE RED_DEDUPE_KEYED: RED_DEDUPE for partitions that hold whole keys (partitioned by the record WITHOUT its random
+//   barcode) and fit the key store — one pass instead of two.  A record's home slot is the hash of its KEY, so all records
+//   of a key walk the same probe sequence; slots of a sequence fill in order and never empty, hence the first entry
+//   of that key a record meets on its way (or the record itself when it meets none) is the same for all of them: that
+//   entry carries the key's count of distinct records.
 template <bool WIDE, int MODE>
 __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     t.khi = WIDE ? t.klo + kKeyCap : nullptr;
     t.table = reinterpret_cast<uint32_t*>(t.klo + (WIDE ? 2 : 1) * kKeyCap);
     t.kcnt = t.table + kTableSlots;
-    uint32_t* kw = t.kcnt + kKeyCap;  // RED_DEDUPE only
+    uint32_t* kw = MODE == RED_DEDUPE_KEYED ? t.kcnt : t.kcnt + kKeyCap;  // RED_DEDUPE*: distinct records per key
     t.n_perm = &s_nperm;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -360,10 +391,98 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     if (skip_over && e - a > skip_over) return;  // hot keys: k_gather_big hands this partition to the two-stage path
 
     clear_u32(t.table, kTableSlots, kEmpty32);
-    if (MODE == RED_DEDUPE) clear_u32(kw, kKeyCap, 0u);
+    if (MODE != RED_COUNT) clear_u32(kw, kKeyCap, 0u);
     if (tid == 0) s_nperm = 0;
 
     uint32_t n_perm;
+    uint32_t* val = t.kcnt;
+    if (MODE == RED_DEDUPE_KEYED) {
+        if (e - a > kKeyCap) {  // the host only uses this mode when every partition fits (or is skipped above)
+            if (tid == 0) atomicExch(&stats->overflow, 32ULL);
+            return;
+        }
+        const uint32_t n = (uint32_t)(e - a);
+        unsigned long long lo[kRedLoads], hi[kRedLoads];
+#pragma unroll
+        for (int k = 0; k < kRedLoads; k++) {
+            const uint32_t j = k * kRedThreads + tid;
+            const bool ok = j < n;
+            lo[k] = ok ? in.lo[a + j] : kEmpty;
+            hi[k] = WIDE ? (ok ? in.hi[a + j] : kEmpty) : 0ULL;
+        }
+#pragma unroll
+        for (int k = 0; k < kRedLoads; k++) {
+            const uint32_t j = k * kRedThreads + tid;
+            if (j < n) {
+                t.klo[j] = lo[k];
+                if (WIDE) t.khi[j] = hi[k];
+            }
+        }
+        __syncthreads();
+        // One loop over probe STEPS, not over items: a lane that settles an item moves on to its next one at once, so a
+        // warp runs for the longest lane total (about items x 1.5 steps) instead of the sum of per-item maxima.
+        uint32_t uniq = 0;
+        {
+            uint32_t j = tid, s = 0, rep = kEmpty32;
+            unsigned long long clo = 0, chi = 0;
+            Key K{0, 0};
+            bool fresh = true;
+            while (j < n) {
+                if (fresh) {
+                    clo = t.klo[j];
+                    chi = WIDE ? t.khi[j] : 0ULL;
+                    if (!item_valid(clo, chi, WIDE)) {
+                        j += kRedThreads;
+                        continue;
+                    }
+                    K = drop_umi<WIDE>(clo, chi, umi_bits);
+                    s = slot_hash<WIDE>(K.lo, K.hi) & (kTableSlots - 1);
+                    rep = kEmpty32;  // first entry of this key met so far
+                    fresh = false;
+                }
+                uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
+                if (v == kEmpty32) {
+                    const uint32_t old = atomicCAS(&t.table[s], kEmpty32, j);
+                    if (old == kEmpty32) {  // a record not seen before
+                        atomicAdd(&kw[rep == kEmpty32 ? j : rep], 1u);
+                        uniq++;
+                        j += kRedThreads;
+                        fresh = true;
+                        continue;
+                    }
+                    v = old;
+                }
+                const unsigned long long vlo = t.klo[v], vhi = WIDE ? t.khi[v] : 0ULL;
+                if (vlo == clo && (!WIDE || vhi == chi)) {  // a repeat (info.rs:780-791: only the first insert counts)
+                    j += kRedThreads;
+                    fresh = true;
+                    continue;
+                }
+                if (rep == kEmpty32) {
+                    bool same;
+                    if (!WIDE) {
+                        same = ((vlo ^ clo) >> umi_bits) == 0ULL;
+                    } else {
+                        const Key o = drop_umi<true>(vlo, vhi, umi_bits);
+                        same = o.lo == K.lo && o.hi == K.hi;
+                    }
+                    if (same) rep = v;
+                }
+                s = (s + 1) & (kTableSlots - 1);
+            }
+        }
+        for (int o = 16; o; o >>= 1) uniq += __shfl_xor_sync(0xFFFFFFFFu, uniq, o);
+        if (lane == 0) s_warp[wid] = uniq;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long u = 0;
+            for (int i = 0; i < kRedThreads / 32; i++) u += s_warp[i];
+            if (u) atomicAdd(&stats->unique, u);
+        }
+        __syncthreads();
+        n_perm = n;
+        val = kw;
+    } else {
     if (e - a <= kKeyCap) {
         // ---- pass 1, staged: item j lives at key-store index j
         const uint32_t n = (uint32_t)(e - a);
@@ -375,7 +494,7 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
             const bool ok = j < n;
             lo[k] = ok ? in.lo[a + j] : kEmpty;
             hi[k] = WIDE ? (ok ? in.hi[a + j] : kEmpty) : 0ULL;
-            w[k] = (MODE == RED_COUNT && in.w && ok) ? (uint32_t)in.w[a + j] : 1u;
+            w[k] = (MODE == RED_COUNT && in.w && ok) ? narrow_weight(in.w[a + j], stats) : 1u;
         }
 #pragma unroll
         for (int k = 0; k < kRedLoads; k++) {
@@ -392,7 +511,7 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
             const uint32_t j = k * kRedThreads + tid;
             if (j >= n || !item_valid(lo[k], hi[k], WIDE)) continue;
             const uint32_t at = smem_find_or_claim_staged<WIDE>(t, lo[k], hi[k], slot_hash<WIDE>(lo[k], hi[k]), j);
-            if (MODE == RED_COUNT) atomicAdd(&t.kcnt[at], w[k]);
+            if (MODE == RED_COUNT) add_weight(&t.kcnt[at], w[k], stats);
             else if (at == j) t.kcnt[j] = 1u;  // first of its kind; repeats keep 0
         }
         __syncthreads();
@@ -410,13 +529,16 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
                 const bool ok = i < e;
                 lo[k] = ok ? in.lo[i] : kEmpty;
                 hi[k] = WIDE ? (ok ? in.hi[i] : kEmpty) : 0ULL;
-                w[k] = (MODE == RED_COUNT && in.w && ok) ? (uint32_t)in.w[i] : 1u;
+                w[k] = (MODE == RED_COUNT && in.w && ok) ? narrow_weight(in.w[i], stats) : 1u;
             }
 #pragma unroll
             for (int k = 0; k < kRedLoads; k++) {
                 if (!item_valid(lo[k], hi[k], WIDE)) continue;
                 const uint32_t at = smem_find_or_claim<WIDE>(t, lo[k], hi[k], slot_hash<WIDE>(lo[k], hi[k]), reserve);
-                if (at != kEmpty32) atomicAdd(&t.kcnt[at], MODE == RED_COUNT ? w[k] : 1u);
+                if (at != kEmpty32) {
+                    if (MODE == RED_COUNT) add_weight(&t.kcnt[at], w[k], stats);
+                    else atomicAdd(&t.kcnt[at], 1u);
+                }
             }
         }
         __syncthreads();
@@ -426,7 +548,6 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
         }
         n_perm = s_nperm;
     }
-    uint32_t* val = t.kcnt;
 
     if (MODE == RED_DEDUPE) {
         // ---- pass 2: the distinct records, keyed by the record without its random barcode.  The key store stays as
@@ -469,6 +590,8 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
         val = kw;
     }
 
+    }  // two-pass modes
+
     // ---- emit: entries with a non-zero value, one global reservation per CTA, each warp writes a contiguous run
     uint32_t mine = 0;
     for (uint32_t i = tid; i < n_perm; i += kRedThreads) mine += val[i] != 0u;
@@ -499,7 +622,7 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, c != 0u);
         if (c != 0u) {
             Key k{t.klo[i], WIDE ? t.khi[i] : 0ULL};
-            if (MODE == RED_DEDUPE) k = drop_umi<WIDE>(k.lo, k.hi, umi_bits);
+            if (MODE != RED_COUNT) k = drop_umi<WIDE>(k.lo, k.hi, umi_bits);
             const unsigned long long pos = at + __popc(bal & ((1u << lane) - 1u));
             out.lo[pos] = k.lo;
             if (out.hi) out.hi[pos] = k.hi;
@@ -513,7 +636,7 @@ template <bool WIDE, int MODE>
 cudaError_t launch_reduce_t(const ItemView& in, const uint32_t* starts, unsigned long long n_items, unsigned long long n_ranges,
                             uint32_t chunk, uint32_t umi_bits, const ItemView& out, unsigned long long out_cap, FlushStats* stats,
                             uint32_t skip_over, cudaStream_t stream) {
-    const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);
+    const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);  // keyed: no kcnt
     cudaError_t e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
@@ -525,51 +648,6 @@ unsigned stream_grid(unsigned long long n, unsigned block) {
     unsigned long long g = (n + block - 1) / block;
     const unsigned long long cap = 148ULL * 16;
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
-}
-
-// ---- appends that do not come from k_decode --------------------------------------------------------------------
-__global__ void k_append_segments(const Key* __restrict__ records, const unsigned long long capacity,
-                                  const uint32_t* __restrict__ counts, const uint32_t count_stride, const uint32_t n_segments,
-                                  const RecOut rec, const unsigned long long rec_cap, unsigned long long* __restrict__ counters,
-                                  FlushStats* stats) {
-    unsigned long long at = *rec.cursor;
-    for (uint32_t s = 0; s < n_segments; s++) {
-        const unsigned long long n = min((unsigned long long)counts[s * count_stride], capacity);
-        const Key* seg = records + (unsigned long long)s * capacity;
-        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-             i += (unsigned long long)gridDim.x * blockDim.x) {
-            const unsigned long long pos = at + i;
-            if (pos >= rec_cap) {  // the host reserves the worst case before the launch
-                atomicExch(&stats->overflow, 4ULL);
-                continue;
-            }
-            const Key k = seg[i];
-            rec.lo[pos] = k.lo;
-            if (rec.hi) rec.hi[pos] = k.hi;
-        }
-        at += n;
-    }
-    // provisional outcome: every routed record is "matched" until the flush finds the repeats
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[BC_CNT_MATCHED], at - *rec.cursor);
-}
-
-__global__ void k_bump_segments(unsigned long long* cursor, const unsigned long long capacity, const uint32_t* __restrict__ counts,
-                                const uint32_t count_stride, const uint32_t n_segments) {
-    unsigned long long add = 0;
-    for (uint32_t s = 0; s < n_segments; s++) add += min((unsigned long long)counts[s * count_stride], capacity);
-    *cursor += add;
-}
-
-__global__ void k_append_records(const Key* __restrict__ records, const unsigned long long n, const RecOut rec,
-                                 unsigned long long* __restrict__ counters) {
-    const unsigned long long at = *rec.cursor;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const Key k = records[i];
-        rec.lo[at + i] = k.lo;
-        if (rec.hi) rec.hi[at + i] = k.hi;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[BC_CNT_MATCHED], n);
 }
 
 // global-table path over the record buffer: what k_insert does for routed records, minus the outcome counters
@@ -618,16 +696,17 @@ cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_
     return cudaGetLastError();
 }
 
-template <bool WIDE, bool WEIGHTED, int IPT>
-static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t workers,
-                                    unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream) {
+template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
+static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const PeerOut& peers, const uint32_t* seg_starts,
+                                    uint32_t workers, unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream) {
     constexpr size_t T = (size_t)kScatterThreads * IPT;
     const size_t smem = T * 8 * (1 + (WIDE ? 1 : 0) + (WEIGHTED ? 1 : 0)) + T * 4;
-    cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    k_split_scatter<WIDE, WEIGHTED, IPT><<<grid, kScatterThreads, smem, stream>>>(in, out, seg_starts, workers, n_total, lv, bins);
+    k_split_scatter<WIDE, WEIGHTED, IPT, PEER><<<grid, kScatterThreads, smem, stream>>>(in, out, peers, seg_starts, workers, n_total, lv, bins);
     return cudaGetLastError();
 }
 
@@ -657,10 +736,26 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
         else k_split_hist<false><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
         return cudaGetLastError();
     }
-    if (wide) return weighted ? launch_scatter_t<true, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
-                              : launch_scatter_t<true, false, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
-    return weighted ? launch_scatter_t<false, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
-                    : launch_scatter_t<false, false, 16>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
+    const PeerOut none{};
+    if (wide) return weighted ? launch_scatter_t<true, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
+                              : launch_scatter_t<true, false, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
+    return weighted ? launch_scatter_t<false, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
+                    : launch_scatter_t<false, false, 16, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
+}
+
+// Exchange step of a multi-GPU job: this rank's records -> their owners' receive buffers.  owner = digit of `lv`
+// (F = number of ranks, the key without its random barcode hashed with the level's salt); cursors[b] holds, on entry, the
+// position in owner b's buffer where this rank's run starts.
+cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& peers, unsigned long long n_total, const SplitLevel& lv,
+                                 uint32_t* cursors, cudaStream_t stream) {
+    if (n_total == 0) return cudaSuccess;
+    if (lv.F == 0 || lv.F > (uint32_t)kMaxRanks) return cudaErrorInvalidValue;
+    const unsigned long long tile = (unsigned long long)kScatterThreads * (wide ? 8 : 16);
+    unsigned long long workers = (n_total + tile - 1) / tile;
+    if (workers > 148ULL * 16) workers = 148ULL * 16;
+    const ItemView none{};
+    if (wide) return launch_scatter_t<true, false, 8, true>((unsigned)workers, in, none, peers, nullptr, (uint32_t)workers, n_total, lv, cursors, stream);
+    return launch_scatter_t<false, false, 16, true>((unsigned)workers, in, none, peers, nullptr, (uint32_t)workers, n_total, lv, cursors, stream);
 }
 
 cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
@@ -668,6 +763,9 @@ cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_
                           unsigned long long out_cap, FlushStats* stats, uint32_t skip_over, cudaStream_t stream) {
     if (n_ranges == 0) return cudaSuccess;
     if (n_ranges > 0x7FFFFFFFULL) return cudaErrorInvalidValue;
+    if (mode == RED_DEDUPE_KEYED)
+        return wide ? launch_reduce_t<true, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
+                    : launch_reduce_t<false, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
     if (mode == RED_DEDUPE)
         return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
                     : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
@@ -696,23 +794,6 @@ __global__ void k_gather_big(const ItemView in, const uint32_t* __restrict__ sta
 cudaError_t launch_gather_big(const ItemView& in, const uint32_t* starts, unsigned long long n_parts, uint32_t limit, const ItemView& out,
                               FlushStats* stats, cudaStream_t stream) {
     k_gather_big<<<148 * 8, 256, 0, stream>>>(in, starts, n_parts, limit, out, stats);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_append_segments(const Key* records, unsigned long long capacity, const uint32_t* counts, uint32_t count_stride,
-                                   uint32_t n_segments, const RecOut& rec, unsigned long long rec_cap, unsigned long long* cursor,
-                                   unsigned long long* counters, FlushStats* stats, cudaStream_t stream) {
-    k_append_segments<<<148 * 4, 256, 0, stream>>>(records, capacity, counts, count_stride, n_segments, rec, rec_cap, counters, stats);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_bump_segments<<<1, 1, 0, stream>>>(cursor, capacity, counts, count_stride, n_segments);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_append_records(const Key* records, unsigned long long n, const RecOut& rec, unsigned long long* counters,
-                                  cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    k_append_records<<<stream_grid(n, 256), 256, 0, stream>>>(records, n, rec, counters);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <sched.h>
 #include <zlib.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -20,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <memory>
 #include <set>
@@ -299,6 +301,7 @@ struct PinnedBatch {
     uint32_t* planes = nullptr;
     uint16_t* read_len = nullptr;
     uint8_t* qual = nullptr;
+    size_t cap_planes = 0, cap_qual = 0;  // bytes
     ~PinnedBatch() { release(); }
     void release() {
         if (planes) cudaFreeHost(planes);
@@ -310,18 +313,31 @@ struct PinnedBatch {
     }
     void alloc(uint32_t n, uint32_t max_read_len, bool with_qual) {
         release();
-        if (cudaHostAlloc((void**)&planes, (size_t)n * bc_plane_stride(max_read_len) * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cap_planes = (size_t)n * bc_plane_stride(max_read_len) * 4;
+        cap_qual = with_qual ? (size_t)n * bc_qual_stride(max_read_len) : 0;
+        if (cudaHostAlloc((void**)&planes, cap_planes, cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc((void**)&read_len, (size_t)n * 2, cudaHostAllocDefault) != cudaSuccess ||
-            (with_qual && cudaHostAlloc((void**)&qual, (size_t)n * bc_qual_stride(max_read_len), cudaHostAllocDefault) != cudaSuccess))
+            (with_qual && cudaHostAlloc((void**)&qual, cap_qual, cudaHostAllocDefault) != cudaSuccess))
             throw Error("cudaHostAlloc failed for the pinned batch buffers");
     }
 };
 
-// ingest buffers, kept by the run so that repeated bch_count_fastq calls do not pay the page-locking again
-struct IngestBuffers {
+// one GPU of an ingest: two pinned batches that alternate (the copy of one overlaps the packing of the other)
+struct Lane {
     PinnedBatch pinned[2];
+    int cur = 0, in_flight = 0;
+    int device = -1;
+};
+
+class Pool;
+
+// ingest state, kept by the run so that repeated bch_count_fastq calls pay neither the page-locking nor the thread
+// creation again
+struct IngestBuffers {
+    std::vector<std::unique_ptr<Lane>> lanes;
     FastqBlock blocks[2];
-    uint32_t batch_reads = 0;
+    std::shared_ptr<Pool> pool;
+    uint32_t batch_reads = 0, mrl = 0;
     bool with_qual = false;
 };
 
@@ -340,6 +356,7 @@ struct bch_run {
     bc_config cfg{};
     std::string description;
     IngestBuffers ingest;
+    int multi_mode = 0;  // after bch_count_fastq_multi: 1 = rows partitioned over the contexts, 2 = all rows on the first
 };
 
 namespace {
@@ -560,7 +577,7 @@ const bool kHaveAvx2 = false;
 #endif
 
 // one read -> three bit planes + length word (+ quality bytes)
-inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W, uint32_t* planes, uint16_t* read_len,
+inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t qlen, uint32_t W, uint32_t* planes, uint16_t* read_len,
                      uint8_t* qual_out, uint32_t qual_stride) {
     uint32_t* lo = planes;
     uint32_t* hi = planes + W;
@@ -576,28 +593,121 @@ inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t W
     if (3 * W != ((3 * W) | 1u)) planes[3 * W] = 0;  // pad word of an even record
     if (qual_out) {
         // a quality character below '!' underflows the reference's `q - 33` (parse.rs:326, Q13): flag it, never decode it
+        const uint32_t n = std::min(qlen, len);
         unsigned char lowest = 255;
-        for (uint32_t i = 0; i < len; i++) lowest = std::min<unsigned char>(lowest, (unsigned char)qual[i]);
-        if (len && lowest < 33) other = true;
-        memcpy(qual_out, qual, len);
-        memset(qual_out + len, '!', qual_stride - len);
+        for (uint32_t i = 0; i < n; i++) lowest = std::min<unsigned char>(lowest, (unsigned char)qual[i]);
+        if (n && lowest < 33) other = true;
+        memcpy(qual_out, qual, n);
+        if (qlen < len) {
+            // A quality line shorter than its sequence: the reference zips scores with region codes (parse.rs:338-343), so the
+            // walk ends with the line and a barcode run is tested only if the line goes at least one score beyond it.  A score
+            // of 255 from the line's last position on makes the sum of any run that reaches it pass every threshold.
+            if (n) qual_out[n - 1] = 0xFF;
+            memset(qual_out + n, 0xFF, qual_stride - n);
+        } else {
+            memset(qual_out + len, '!', qual_stride - len);
+        }
     }
     *read_len = (uint16_t)(len | (other ? BC_READ_UNSUPPORTED : 0u));
 }
 
+// a read this build cannot represent (longer than BC_MAX_READ_LEN): an empty record flagged unsupported, counted separately
+inline void pack_unsupported(uint32_t W, uint32_t* planes, uint16_t* read_len, uint8_t* qual_out, uint32_t qual_stride) {
+    memset(planes, 0, (size_t)((3 * W) | 1u) * 4);
+    if (qual_out) memset(qual_out, '!', qual_stride);
+    *read_len = (uint16_t)BC_READ_UNSUPPORTED;
+}
+
+// reads [0, count) of `reads` -> batch arrays of geometry max_read_len.  strict: a read longer than max_read_len is an error
+// (the caller chose the geometry); otherwise only reads beyond BC_MAX_READ_LEN can be too long and are flagged unsupported.
+bool pack_range(uint32_t max_read_len, const ReadRef* reads, size_t count, uint32_t* planes, uint16_t* read_len, uint8_t* qual,
+                bool strict) {
+    const uint32_t W = bc_plane_words(max_read_len), ps = bc_plane_stride(max_read_len), qs = bc_qual_stride(max_read_len);
+    bool ok = true;
+    for (size_t i = 0; i < count; i++) {
+        const ReadRef& r = reads[i];
+        if (r.len > max_read_len || r.len > 0x7FFF) {
+            if (strict) ok = false;
+            pack_unsupported(W, planes + i * ps, read_len + i, qual ? qual + i * qs : nullptr, qs);
+            continue;
+        }
+        pack_one(r.seq, r.len, r.qual, r.qlen, W, planes + i * ps, read_len + i, qual ? qual + i * qs : nullptr, qs);
+    }
+    return ok;
+}
+
+// A persistent pool of host threads: run(n, f) calls f(0) .. f(n-1) on the workers and on the calling thread and returns
+// when all are done.  One pool per run, created at the first ingest and kept (no thread is spawned per block or batch).
+class Pool {
+  public:
+    explicit Pool(unsigned threads) {
+        for (unsigned t = 1; t < std::max(1u, threads); t++) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_start_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    unsigned size() const { return (unsigned)workers_.size() + 1; }
+    void run(size_t n, const std::function<void(size_t)>& f) {
+        if (n == 0) return;
+        if (n == 1 || workers_.empty()) {
+            for (size_t i = 0; i < n; i++) f(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f;
+            n_ = n;
+            next_.store(0);
+            busy_ = workers_.size();
+            gen_++;
+        }
+        cv_start_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return busy_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (size_t i = next_++; i < n_; i = next_++) (*fn_)(i);
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--busy_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_start_, cv_done_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t n_ = 0, busy_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 int pack_refs(uint32_t max_read_len, const std::vector<ReadRef>& reads, size_t first, size_t count, uint32_t* planes,
               uint16_t* read_len, uint8_t* qual, unsigned threads) {
-    const uint32_t W = bc_plane_words(max_read_len), ps = bc_plane_stride(max_read_len), qs = bc_qual_stride(max_read_len);
+    const uint32_t ps = bc_plane_stride(max_read_len), qs = bc_qual_stride(max_read_len);
     std::atomic<int> bad{0};
     auto work = [&](size_t a, size_t b) {
-        for (size_t i = a; i < b; i++) {
-            const ReadRef& r = reads[first + i];
-            if (r.len > max_read_len || r.len > 0x7FFF || (qual && r.qlen != r.len)) {
-                bad = 1;
-                continue;
-            }
-            pack_one(r.seq, r.len, r.qual, W, planes + i * ps, read_len + i, qual ? qual + i * qs : nullptr, qs);
-        }
+        if (!pack_range(max_read_len, reads.data() + first + a, b - a, planes + a * ps, read_len + a, qual ? qual + a * qs : nullptr, true))
+            bad = 1;
     };
     if (threads <= 1 || count < 4096) {
         work(0, count);
@@ -700,12 +810,13 @@ void decode_rows(const bch_run& run, const bc_ctx* ctx, const bc_table& t, std::
     const uint32_t stride = BC_MAX_REF_LEN + 1;
     std::vector<int32_t> idx(ns);
     std::vector<char> str((size_t)ns * stride);
-    rows.resize(t.n_rows);
+    const size_t old = rows.size();
+    rows.resize(old + t.n_rows);  // appends: the rows of several contexts (multi-GPU owners) form one table
     for (uint64_t r = 0; r < t.n_rows; r++) {
         const uint32_t mask = t.mask ? t.mask[r] : 0;
         if (bc_key_decode(ctx, t.key_lo[r], t.key_hi ? t.key_hi[r] : 0, mask, 0, idx.data(), str.data(), stride) != BC_OK)
             throw Error("bc_key_decode failed");
-        DecodedRow& d = rows[r];
+        DecodedRow& d = rows[old + r];
         d.count = t.count[r];
         if (run.sample_slot < 0) d.sample = "barcode";
         else if (run.have_sample_file) d.sample = run.slots[run.sample_slot].dna.at((size_t)idx[run.sample_slot]);
@@ -737,6 +848,336 @@ void write_text(const std::string& dir, const std::string& name, const std::stri
     size_t rows = 0;
     for (char c : text) rows += c == '\n';
     names.push_back(name + "\t" + std::to_string(rows ? rows - 1 : 0));
+}
+
+
+// ---- NUMA placement: the pinned staging buffers of a GPU belong on the memory of the socket the GPU hangs off ----------
+int numa_node_of_device(int device) {
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    std::ifstream in(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+    int node = -1;
+    if (!(in >> node)) return -1;
+    return node;
+}
+
+bool cpus_of_node(int node, cpu_set_t* set) {
+    std::ifstream in("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    std::string list;
+    if (!std::getline(in, list)) return false;
+    CPU_ZERO(set);
+    size_t i = 0;
+    bool any = false;
+    while (i < list.size()) {
+        size_t j = i;
+        while (j < list.size() && list[j] != ',') j++;
+        const std::string part = list.substr(i, j - i);
+        const size_t dash = part.find('-');
+        const int lo = atoi(part.c_str()), hi = dash == std::string::npos ? lo : atoi(part.c_str() + dash + 1);
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; c++) {
+            CPU_SET(c, set);
+            any = true;
+        }
+        i = j + 1;
+    }
+    return any;
+}
+
+// runs f on a thread confined to the CPUs of `device`'s NUMA node (pages it allocates land on that node); on boxes that
+// do not expose the topology f simply runs
+void on_device_node(int device, const std::function<void()>& f) {
+    const int node = numa_node_of_device(device);
+    cpu_set_t set;
+    if (node < 0 || !cpus_of_node(node, &set)) {
+        f();
+        return;
+    }
+    std::exception_ptr err;
+    std::thread t([&] {
+        sched_setaffinity(0, sizeof set, &set);
+        try {
+            f();
+        } catch (...) {
+            err = std::current_exception();
+        }
+    });
+    t.join();
+    if (err) std::rethrow_exception(err);
+}
+
+// ---- the records of one block: one vector per splitter slice, seen as one sequence --------------------------------
+struct RecSeq {
+    const std::vector<std::vector<ReadRef>>* parts = nullptr;
+    std::vector<size_t> first;  // first[t] = index of parts[t][0] in the sequence; first[n] = size
+    std::vector<uint32_t> longest;  // longest read of each part
+    void index(const std::vector<std::vector<ReadRef>>& p, size_t used) {
+        parts = &p;
+        first.assign(used + 1, 0);
+        longest.assign(used, 0);
+        for (size_t t = 0; t < used; t++) first[t + 1] = first[t] + p[t].size();
+    }
+    size_t size() const { return first.back(); }
+    size_t part_of(size_t i) const { return (size_t)(std::upper_bound(first.begin(), first.end(), i) - first.begin()) - 1; }
+};
+
+// Splits [pos, blk_end) of a mapped plain FASTQ into records on all pool threads: slice t starts at the first record
+// start at or after its nominal position and ends where slice t + 1 starts.  The slice that ends at blk_end — whichever
+// it is: later slices are empty when the block holds fewer records than threads — may end with an unterminated line
+// when the block is the file's last.  Returns the position after the last whole record.
+const char* split_block(Pool& pool, const char* pos, const char* blk_end, bool last, std::vector<std::vector<ReadRef>>& parts,
+                        RecSeq& seq, size_t min_slice = 65536) {
+    const size_t bytes = (size_t)(blk_end - pos);
+    const size_t slices = std::max<size_t>(1, std::min<size_t>(pool.size(), bytes / std::max<size_t>(1, min_slice)));
+    if (parts.size() < slices) parts.resize(slices);
+    std::vector<const char*> start(slices + 1), stop(slices);
+    start[0] = pos;
+    start[slices] = blk_end;
+    const size_t span = bytes / slices;
+    pool.run(slices, [&](size_t t) {
+        if (t == 0) return;
+        const char* nominal = pos + span * t;
+        const char* nl = (const char*)memchr(nominal, '\n', (size_t)(blk_end - nominal));
+        start[t] = nl ? find_record_start(nl + 1, blk_end) : blk_end;
+    });
+    for (size_t t = 1; t < slices; t++) start[t] = std::max(start[t], start[t - 1]);
+    std::vector<uint32_t> longest(slices, 0);
+    pool.run(slices, [&](size_t t) {
+        parts[t].clear();
+        const char* end = start[t + 1];
+        stop[t] = start[t] < end ? split_records(start[t], end, last && end == blk_end, parts[t]) : start[t];
+        uint32_t m = 0;
+        for (const ReadRef& r : parts[t]) m = std::max(m, r.len);
+        longest[t] = m;
+    });
+    const char* consumed = pos;
+    for (size_t t = 0; t < slices; t++) {
+        if (start[t] == start[t + 1]) continue;  // empty slice
+        if (start[t + 1] != blk_end && stop[t] != start[t + 1])
+            throw Error("malformed FASTQ: a record near byte offset " + std::to_string((size_t)(stop[t] - pos)) +
+                        " of the current block does not have four lines");
+        consumed = stop[t];
+    }
+    seq.index(parts, slices);
+    seq.longest = longest;
+    return consumed;
+}
+
+// ---- one ingest: blocks of records -> pinned batches -> bc_submit, round-robin over the contexts ----------------------
+struct Ingest {
+    bch_run* run;
+    bc_ctx* const* ctxs;
+    int n_ctx;
+    Pool* pool;
+    uint32_t mrl0, batch_reads;
+    bool with_qual;
+    uint64_t total = 0, n_batches = 0;
+
+    Ingest(bch_run* r, bc_ctx* const* c, int n, unsigned threads, uint32_t batch) : run(r), ctxs(c), n_ctx(n), batch_reads(batch) {
+        mrl0 = run->cfg.max_read_len;
+        with_qual = run->min_quality > 0.0f;
+        IngestBuffers& I = run->ingest;
+        if (!I.pool || I.pool->size() != std::max(1u, threads)) I.pool = std::make_shared<Pool>(threads);
+        pool = I.pool.get();
+        if (I.batch_reads != batch_reads || I.with_qual != with_qual || I.mrl != mrl0 || (int)I.lanes.size() != n_ctx) {
+            I.lanes.clear();
+            for (int d = 0; d < n_ctx; d++) I.lanes.emplace_back(new Lane());
+            const size_t block_bytes = std::min<size_t>(std::max<size_t>((size_t)batch_reads * (2 * (size_t)mrl0 + 64), 1u << 20), 1u << 30);
+            for (FastqBlock& B : I.blocks) B.buf.resize(block_bytes);
+            I.batch_reads = batch_reads;
+            I.with_qual = with_qual;
+            I.mrl = mrl0;
+        }
+        for (int d = 0; d < n_ctx; d++) {
+            Lane& L = *I.lanes[d];
+            const int dev = bc_device_of(ctxs[d]);
+            if (L.pinned[0].planes && L.device == dev) continue;
+            L.device = dev;
+            on_device_node(dev, [&] {  // first touch on the GPU's own socket
+                cudaSetDevice(dev);
+                L.pinned[0].alloc(batch_reads, mrl0, with_qual);
+                L.pinned[1].alloc(batch_reads, mrl0, with_qual);
+            });
+            L.cur = L.in_flight = 0;
+        }
+        for (auto& L : I.lanes) L->in_flight = 0;
+    }
+
+    // records [from, seq.size()) of the block, in batches
+    void submit(const RecSeq& seq) {
+        size_t done = 0;
+        const size_t n_rec = seq.size();
+        while (done < n_rec) {
+            const int d = (int)(n_batches % (uint64_t)n_ctx);
+            Lane& L = *run->ingest.lanes[d];
+            bc_ctx* ctx = ctxs[d];
+            if (L.in_flight == 2) {  // the buffer we are about to overwrite was handed to the submit before last
+                if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+                L.in_flight = 0;
+            }
+            PinnedBatch& p = L.pinned[L.cur];
+            // geometry of this batch: the run's default, or wider when a read of the parts it touches is longer (reads of
+            // any length up to BC_MAX_READ_LEN are decoded; the reference has no length limit, input.rs:115-148)
+            size_t n = std::min<size_t>(n_rec - done, batch_reads);
+            uint32_t longest = 0;
+            for (size_t t = seq.part_of(done), e = seq.part_of(done + n - 1); t <= e; t++) longest = std::max(longest, seq.longest[t]);
+            uint32_t mrl = mrl0;
+            if (longest > mrl0) {
+                mrl = std::min<uint32_t>((longest + 31) / 32 * 32, BC_MAX_READ_LEN);
+                n = std::min<size_t>(n, p.cap_planes / ((size_t)bc_plane_stride(mrl) * 4));
+                if (with_qual) n = std::min<size_t>(n, p.cap_qual / bc_qual_stride(mrl));
+                if (n == 0) throw Error("batch buffers too small for a read of " + std::to_string(longest) + " bases: raise --batch-reads");
+            }
+            const uint32_t ps = bc_plane_stride(mrl), qs = bc_qual_stride(mrl);
+            const size_t chunk = 2048, tasks = (n + chunk - 1) / chunk;
+            pool->run(tasks, [&](size_t k) {
+                size_t a = done + k * chunk;
+                const size_t b = std::min(done + n, a + chunk);
+                while (a < b) {
+                    const size_t t = seq.part_of(a);
+                    const size_t take = std::min(b, seq.first[t + 1]) - a, dst = a - done;
+                    pack_range(mrl, (*seq.parts)[t].data() + (a - seq.first[t]), take, p.planes + dst * ps, p.read_len + dst,
+                               with_qual ? p.qual + dst * qs : nullptr, false);
+                    a += take;
+                }
+            });
+            bc_batch b{};
+            b.n_reads = (uint32_t)n;
+            b.plane_stride = ps;
+            b.qual_stride = qs;
+            b.location = BC_LOC_HOST;
+            b.planes = p.planes;
+            b.read_len = p.read_len;
+            b.qual = with_qual ? p.qual : nullptr;
+            if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
+            total += n;
+            done += n;
+            n_batches++;
+            L.cur ^= 1;
+            L.in_flight++;
+        }
+    }
+
+    void finish() {
+        for (int d = 0; d < n_ctx; d++)
+            if (bc_sync(ctxs[d]) != BC_OK) throw Error(bc_last_error(ctxs[d]));
+    }
+};
+
+void check_fastq_name(const std::string& path) {
+    auto ends = [&](const char* suf) {
+        const size_t k = strlen(suf);
+        return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
+    };
+    if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
+        throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
+}
+
+// input::read_fastq for one or several contexts (throws)
+uint64_t ingest_fastq(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads) {
+    if (batch_reads == 0) batch_reads = 1u << 20;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    check_fastq_name(fastq_path);
+    Ingest ing(run, ctxs, n_ctx, threads, batch_reads);
+    IngestBuffers& I = run->ingest;
+    MappedFile mf;
+    if (mf.open_plain(fastq_path)) {
+        // plain file: no read() copy at all; every host thread splits and packs its own slice of each block of the mapping
+        const size_t block_bytes = I.blocks[0].buf.size();
+        const char* pos = mf.data;
+        const char* const eof = mf.data + mf.size;
+        std::vector<std::vector<ReadRef>> parts;
+        RecSeq seq;
+        while (pos < eof) {
+            const char* blk_end = std::min(eof, pos + block_bytes);
+            const bool last = blk_end == eof;
+            const char* consumed = split_block(*ing.pool, pos, blk_end, last, parts, seq);
+            if (seq.size() == 0) {
+                if (last) break;  // trailing partial record: dropped, as the reference never posts it
+                throw Error("FASTQ record longer than the block buffer");
+            }
+            ing.submit(seq);
+            pos = consumed;
+        }
+        ing.finish();
+        return ing.total;
+    }
+    // gzip / bgzip / anything that cannot be mapped: a reader thread fills and splits block i + 1 while this thread packs block i
+    for (FastqBlock& B : I.blocks) B.state = 0;
+    FastqStream in(fastq_path, threads);
+    std::mutex mu;
+    std::condition_variable cv;
+    bool abort_reader = false, reader_done = false;
+    std::string reader_error;
+    std::thread reader([&]() {
+        try {
+            for (int i = 0;; i ^= 1) {
+                FastqBlock& B = I.blocks[i];
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return B.state == 0 || abort_reader; });
+                    if (abort_reader) return;
+                }
+                const bool more = in.next_block(B, batch_reads);
+                std::lock_guard<std::mutex> lk(mu);
+                if (!more) {
+                    reader_done = true;
+                    cv.notify_all();
+                    return;
+                }
+                B.state = 1;
+                cv.notify_all();
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            reader_error = e.what();
+            reader_done = true;
+            cv.notify_all();
+        }
+    });
+    auto stop_reader = [&]() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            abort_reader = true;
+        }
+        cv.notify_all();
+        if (reader.joinable()) reader.join();
+    };
+    try {
+        std::vector<std::vector<ReadRef>> parts(1);
+        RecSeq seq;
+        for (int i = 0;; i ^= 1) {
+            FastqBlock& B = I.blocks[i];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return B.state == 1 || reader_done; });
+                if (B.state != 1) break;
+            }
+            parts[0].swap(B.recs);
+            seq.index(parts, 1);
+            uint32_t m = 0;
+            for (const ReadRef& r : parts[0]) m = std::max(m, r.len);
+            seq.longest[0] = m;
+            ing.submit(seq);
+            // the pinned copy of the block's bytes is complete when submit returns (packing is synchronous)
+            parts[0].swap(B.recs);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                B.state = 0;
+            }
+            cv.notify_all();
+        }
+    } catch (...) {
+        stop_reader();
+        throw;
+    }
+    stop_reader();
+    if (!reader_error.empty()) throw Error(reader_error);
+    ing.finish();
+    return ing.total;
 }
 
 }  // namespace
@@ -870,236 +1311,146 @@ int bch_scan_fastq(const char* fastq_path, unsigned threads, uint64_t* n_records
     }
 }
 
-int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads,
-                    uint64_t* total_reads, char* err, int errlen) {
-    auto report = [&](const std::string& m) {
-        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
-    };
-    if (!run || !ctx || !fastq_path) return BC_EINVAL;
-    if (batch_reads == 0) batch_reads = 1u << 20;
+int bch_split_fastq(const char* fastq_path, unsigned threads, size_t block_bytes, size_t min_slice_bytes, uint64_t* n_records,
+                    uint64_t* n_bases, uint32_t* crc, char* err, int errlen) {
+    if (!fastq_path) return BC_EINVAL;
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
-    std::thread reader;
-    std::mutex mu;
-    std::condition_variable cv;
-    bool abort_reader = false;
-    auto stop_reader = [&]() {
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            abort_reader = true;
-        }
-        cv.notify_all();
-        if (reader.joinable()) reader.join();
-    };
+    if (block_bytes == 0) block_bytes = 64u << 20;
     try {
-        const uint32_t mrl = run->cfg.max_read_len;
-        const bool with_qual = run->min_quality > 0.0f;
-        IngestBuffers& I = run->ingest;
-        if (I.batch_reads != batch_reads || I.with_qual != with_qual || !I.pinned[0].planes) {
-            I.pinned[0].alloc(batch_reads, mrl, with_qual);
-            I.pinned[1].alloc(batch_reads, mrl, with_qual);
-            const size_t block_bytes = std::min<size_t>(std::max<size_t>((size_t)batch_reads * (2 * (size_t)mrl + 64), 1u << 20), 1u << 30);
-            for (FastqBlock& B : I.blocks) B.buf.resize(block_bytes);
-            I.batch_reads = batch_reads;
-            I.with_qual = with_qual;
-        }
-        {
-            const std::string path = fastq_path;
-            auto ends = [&](const char* suf) {
-                const size_t k = strlen(suf);
-                return path.size() >= k && path.compare(path.size() - k, k, suf) == 0;
-            };
-            if (!ends("fastq") && !ends("fastq.gz"))  // input.rs:33-39
-                throw Error("This program only works with *.fastq files and *.fastq.gz files.  The latter is still experimental");
-        }
         MappedFile mf;
-        if (mf.open_plain(fastq_path)) {
-            // plain file: every host thread splits and packs its own slice of each block of the mapping
-            const size_t block_bytes = I.blocks[0].buf.size();
-            const char* pos = mf.data;
-            const char* const eof = mf.data + mf.size;
-            std::vector<std::vector<ReadRef>> parts(threads);
-            uint64_t total = 0;
-            int cur = 0, in_flight = 0;
-            while (pos < eof) {
-                const char* blk_end = std::min(eof, pos + block_bytes);
-                const bool last = blk_end == eof;
-                // slice starts: thread 0 starts at pos (a record start by construction), the others at the first record
-                // start at or after their nominal position
-                std::vector<const char*> start(threads + 1);
-                start[0] = pos;
-                start[threads] = blk_end;
-                const size_t span = (size_t)(blk_end - pos) / threads;
-                {
-                    std::vector<std::thread> pool;
-                    for (unsigned t = 1; t < threads; t++)
-                        pool.emplace_back([&, t]() {
-                            const char* nominal = pos + span * t;
-                            const char* nl = (const char*)memchr(nominal, '\n', (size_t)(blk_end - nominal));
-                            start[t] = nl ? find_record_start(nl + 1, blk_end) : blk_end;
-                        });
-                    for (auto& th : pool) th.join();
-                }
-                for (unsigned t = 1; t < threads; t++) start[t] = std::max(start[t], start[t - 1]);
-                std::vector<const char*> stop(threads);
-                {
-                    std::vector<std::thread> pool;
-                    for (unsigned t = 0; t < threads; t++)
-                        pool.emplace_back([&, t]() {
-                            parts[t].clear();
-                            // a slice ends where the next begins, except the last one, which ends at the last whole record
-                            const bool tail = t + 1 == threads;
-                            stop[t] = split_records(start[t], tail ? blk_end : start[t + 1], tail && last, parts[t]);
-                        });
-                    for (auto& th : pool) th.join();
-                }
-                size_t n_block = 0;
-                for (unsigned t = 0; t < threads; t++) n_block += parts[t].size();
-                const char* consumed = stop[threads - 1];
-                if (n_block == 0) {
-                    if (last) break;  // trailing partial record: dropped, as the reference never posts it
-                    throw Error("FASTQ record longer than the block buffer");
-                }
-                // pack + submit in pinned batches of at most batch_reads records
-                size_t t_idx = 0, r_idx = 0;
-                while (n_block) {
-                    const size_t n = std::min<size_t>(n_block, batch_reads);
-                    if (in_flight == 2) {
-                        if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
-                        in_flight = 0;
-                    }
-                    PinnedBatch& p = I.pinned[cur];
-                    // (thread, first record, count, destination offset) work items covering records [done, done + n)
-                    struct Item { size_t t, first, count, dst; };
-                    std::vector<Item> items;
-                    size_t filled = 0;
-                    while (filled < n) {
-                        const size_t avail = parts[t_idx].size() - r_idx;
-                        if (avail == 0) { t_idx++; r_idx = 0; continue; }
-                        const size_t take = std::min(avail, n - filled);
-                        items.push_back(Item{t_idx, r_idx, take, filled});
-                        filled += take;
-                        r_idx += take;
-                    }
-                    std::atomic<int> bad{0};
-                    {
-                        std::vector<std::thread> pool;
-                        for (const Item& it : items)
-                            pool.emplace_back([&, it]() {
-                                const uint32_t ps = bc_plane_stride(mrl), qs = bc_qual_stride(mrl);
-                                if (pack_refs(mrl, parts[it.t], it.first, it.count, p.planes + it.dst * ps, p.read_len + it.dst,
-                                              with_qual ? p.qual + it.dst * qs : nullptr, 1) != BC_OK)
-                                    bad = 1;
-                            });
-                        for (auto& th : pool) th.join();
-                    }
-                    if (bad)
-                        throw Error("FASTQ record " + std::to_string(total) + "+: read longer than max_read_len (" + std::to_string(mrl) +
-                                    ") or quality/sequence length mismatch");
-                    bc_batch b{};
-                    b.n_reads = (uint32_t)n;
-                    b.plane_stride = bc_plane_stride(mrl);
-                    b.qual_stride = bc_qual_stride(mrl);
-                    b.location = BC_LOC_HOST;
-                    b.planes = p.planes;
-                    b.read_len = p.read_len;
-                    b.qual = with_qual ? p.qual : nullptr;
-                    if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
-                    total += n;
-                    n_block -= n;
-                    cur ^= 1;
-                    in_flight++;
-                }
-                pos = consumed;
+        if (!mf.open_plain(fastq_path)) throw Error("not a plain, mappable FASTQ file");
+        Pool pool(threads);
+        std::vector<std::vector<ReadRef>> parts;
+        RecSeq seq;
+        uint64_t recs = 0, bases = 0;
+        uLong c = crc32(0L, Z_NULL, 0);
+        const char* pos = mf.data;
+        const char* const eof = mf.data + mf.size;
+        while (pos < eof) {
+            const char* blk_end = std::min(eof, pos + block_bytes);
+            const bool last = blk_end == eof;
+            const char* consumed = split_block(pool, pos, blk_end, last, parts, seq, min_slice_bytes ? min_slice_bytes : 65536);
+            if (seq.size() == 0) {
+                if (last) break;
+                throw Error("FASTQ record longer than the block buffer");
             }
-            if (bc_sync(ctx) != BC_OK) throw Error(bc_last_error(ctx));
-            if (total_reads) *total_reads = total;
-            return BC_OK;
+            for (size_t t = 0; t + 1 < seq.first.size(); t++)
+                for (const ReadRef& r : parts[t]) {
+                    c = crc32(c, reinterpret_cast<const unsigned char*>(r.seq), r.len);
+                    c = crc32(c, reinterpret_cast<const unsigned char*>(r.qual), r.qlen);
+                    bases += r.len;
+                }
+            recs += seq.size();
+            pos = consumed;
         }
-        for (FastqBlock& B : I.blocks) B.state = 0;
-        FastqStream in(fastq_path, threads);
-        // reader thread: fill + split block i+1 while this thread packs block i
-        std::string reader_error;
-        bool reader_done = false;
-        reader = std::thread([&]() {
-            try {
-                for (int i = 0;; i ^= 1) {
-                    FastqBlock& B = I.blocks[i];
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [&] { return B.state == 0 || abort_reader; });
-                        if (abort_reader) return;
-                    }
-                    const bool more = in.next_block(B, batch_reads);
-                    std::lock_guard<std::mutex> lk(mu);
-                    if (!more) {
-                        reader_done = true;
-                        cv.notify_all();
-                        return;
-                    }
-                    B.state = 1;
-                    cv.notify_all();
-                }
-            } catch (const std::exception& e) {
-                std::lock_guard<std::mutex> lk(mu);
-                reader_error = e.what();
-                reader_done = true;
-                cv.notify_all();
-            }
-        });
-        uint64_t total = 0;
-        int cur = 0;
-        int in_flight = 0;  // submits since the last sync; each pinned buffer is reused every second submit
-        for (int i = 0;; i ^= 1) {
-            FastqBlock& B = I.blocks[i];
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return B.state == 1 || reader_done; });
-                if (B.state != 1) break;
-            }
-            if (in_flight == 2) {  // the buffer we are about to overwrite was handed to the submit before last
-                if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
-                in_flight = 0;
-            }
-            PinnedBatch& p = I.pinned[cur];
-            if (pack_refs(mrl, B.recs, 0, B.recs.size(), p.planes, p.read_len, with_qual ? p.qual : nullptr, threads) != BC_OK)
-                throw Error("FASTQ record " + std::to_string(total) + "+: read longer than max_read_len (" + std::to_string(mrl) +
-                            ") or quality/sequence length mismatch");
-            bc_batch b{};
-            b.n_reads = (uint32_t)B.recs.size();
-            b.plane_stride = bc_plane_stride(mrl);
-            b.qual_stride = bc_qual_stride(mrl);
-            b.location = BC_LOC_HOST;
-            b.planes = p.planes;
-            b.read_len = p.read_len;
-            b.qual = with_qual ? p.qual : nullptr;
-            if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
-            total += B.recs.size();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                B.state = 0;
-            }
-            cv.notify_all();
-            cur ^= 1;
-            in_flight++;
-        }
-        stop_reader();
-        if (!reader_error.empty()) throw Error(reader_error);
-        if (bc_sync(ctx) != BC_OK) throw Error(bc_last_error(ctx));
-        if (total_reads) *total_reads = total;
+        if (n_records) *n_records = recs;
+        if (n_bases) *n_bases = bases;
+        if (crc) *crc = (uint32_t)c;
         return BC_OK;
     } catch (const std::exception& e) {
-        stop_reader();
-        report(e.what());
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
         return BC_EINVAL;
     }
 }
 
+int bch_count_fastq(bch_run* run, bc_ctx* ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads,
+                    uint64_t* total_reads, char* err, int errlen) {
+    if (!run || !ctx || !fastq_path) return BC_EINVAL;
+    try {
+        run->multi_mode = 0;
+        const uint64_t total = ingest_fastq(run, &ctx, 1, fastq_path, threads, batch_reads);
+        if (total_reads) *total_reads = total;
+        return BC_OK;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return BC_EINVAL;
+    }
+}
+
+// Several GPUs in one process (main.rs:69-121 has one worker pool; here one context per GPU): batches go to the contexts in
+// turn; after the last one the ranks merge as SURVEY.md section 8(e) prescribes — hashed keys through ONE exchange of the
+// records over NVLink peer memory (every context ends up owning a disjoint set of keys), a dense count table by adding
+// the tables into the first context.
+int bch_count_fastq_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const char* fastq_path, unsigned threads, uint32_t batch_reads,
+                          uint64_t* total_reads, char* err, int errlen) {
+    if (!run || !ctxs || n_ctx < 1 || n_ctx > 8 || !fastq_path) return BC_EINVAL;
+    try {
+        run->multi_mode = 0;
+        const uint64_t total = ingest_fastq(run, ctxs, n_ctx, fastq_path, threads, batch_reads);
+        if (total_reads) *total_reads = total;
+        if (n_ctx == 1) return BC_OK;
+        auto ck = [&](int rc, bc_ctx* c) {
+            if (rc != BC_OK) throw Error(bc_last_error(c));
+        };
+        bc_profile prof;
+        ck(bc_get_profile(ctxs[0], &prof), ctxs[0]);
+        if (prof.deferred_count) {
+            // 1 x 1 x n matrix of what every context holds for every owner; then each writes its runs into the owners' buffers
+            std::vector<std::vector<uint64_t>> sent(n_ctx, std::vector<uint64_t>(n_ctx, 0));
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_open(ctxs[r], (uint32_t)n_ctx, (uint32_t)r, 1), ctxs[r]);  // geometry only
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_count(ctxs[r], sent[r].data()), ctxs[r]);
+            uint64_t need = 1;
+            std::vector<uint64_t> received(n_ctx, 0);
+            for (int o = 0; o < n_ctx; o++) {
+                for (int r = 0; r < n_ctx; r++) received[o] += sent[r][o];
+                need = std::max(need, received[o]);
+            }
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_open(ctxs[r], (uint32_t)n_ctx, (uint32_t)r, need), ctxs[r]);
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_connect_local(ctxs[r], ctxs), ctxs[r]);
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_count(ctxs[r], sent[r].data()), ctxs[r]);
+            for (int r = 0; r < n_ctx; r++) {
+                std::vector<uint64_t> first(n_ctx, 0);
+                for (int o = 0; o < n_ctx; o++)
+                    for (int q = 0; q < r; q++) first[o] += sent[q][o];
+                ck(bc_exchange_scatter(ctxs[r], first.data()), ctxs[r]);
+            }
+            for (int r = 0; r < n_ctx; r++) ck(bc_sync(ctxs[r]), ctxs[r]);  // every scatter has landed
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_finish(ctxs[r], received[r]), ctxs[r]);
+            run->multi_mode = 1;
+        } else {
+            for (int r = 1; r < n_ctx; r++) {
+                ck(bc_sync(ctxs[r]), ctxs[r]);
+                ck(bc_peer_add(ctxs[0], ctxs[r], BC_ADD_DENSE_COUNTS), ctxs[0]);
+            }
+            run->multi_mode = 2;
+        }
+        return BC_OK;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return BC_EINVAL;
+    }
+}
+
+int bch_counters_multi(bc_ctx* const* ctxs, int n_ctx, uint64_t out[BC_N_COUNTERS]) {
+    if (!ctxs || n_ctx < 1 || !out) return BC_EINVAL;
+    for (int i = 0; i < BC_N_COUNTERS; i++) out[i] = 0;
+    for (int r = 0; r < n_ctx; r++) {
+        uint64_t c[BC_N_COUNTERS];
+        const int rc = bc_get_counters(ctxs[r], c);
+        if (rc != BC_OK) return rc;
+        for (int i = 0; i < BC_N_COUNTERS; i++) out[i] += c[i];
+    }
+    return BC_OK;
+}
+
 int bch_write_counts(bch_run* run, bc_ctx* ctx, const char* output_dir, const char* prefix, int merge_output, int enrich,
                      char* names_out, int names_len, char* err, int errlen) {
+    if (!run || !ctx) return BC_EINVAL;
+    const int mode = run->multi_mode;
+    run->multi_mode = 0;  // a single context holds everything
+    const int rc = bch_write_counts_multi(run, &ctx, 1, output_dir, prefix, merge_output, enrich, names_out, names_len, err, errlen);
+    run->multi_mode = mode;
+    return rc;
+}
+
+int bch_write_counts_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const char* output_dir, const char* prefix, int merge_output,
+                           int enrich, char* names_out, int names_len, char* err, int errlen) {
     auto report = [&](const std::string& m) {
         if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.c_str());
     };
-    if (!run || !ctx) return BC_EINVAL;
+    if (!run || !ctxs || n_ctx < 1) return BC_EINVAL;
+    bc_ctx* ctx = ctxs[0];
+    const int n_src = (n_ctx > 1 && run->multi_mode == 1) ? n_ctx : 1;  // contexts that hold rows of the result
     bc_table full{}, singles{}, doubles{};
     try {
         const std::string dir = output_dir ? output_dir : "./";
@@ -1107,9 +1458,12 @@ int bch_write_counts(bch_run* run, bc_ctx* ctx, const char* output_dir, const ch
         const size_t nb = run->counted.size();
         bool merge = merge_output != 0;
         bool do_enrich = enrich != 0 && nb >= 2;  // main.rs:22-25
-        if (bc_finish(ctx, &full) != BC_OK) throw Error(bc_last_error(ctx));
         std::vector<DecodedRow> rows;
-        decode_rows(*run, ctx, full, rows);
+        for (int r = 0; r < n_src; r++) {
+            if (bc_finish(ctxs[r], &full) != BC_OK) throw Error(bc_last_error(ctxs[r]));
+            decode_rows(*run, ctx, full, rows);
+            bc_table_free(&full);
+        }
 
         // sample list and its order (output.rs:77-97): with a sample file every listed sample gets files (Q16) and the
         // order is by sample ID; otherwise the samples seen, ordered by DNA for reproducibility
@@ -1216,14 +1570,31 @@ int bch_write_counts(bch_run* run, bc_ctx* ctx, const char* output_dir, const ch
 
         emit(rows, true, "");
         if (do_enrich) {
-            if (bc_enrich(ctx, &singles, nb > 2 ? &doubles : nullptr) != BC_OK) throw Error(bc_last_error(ctx));
             std::vector<DecodedRow> srows, drows;
-            decode_rows(*run, ctx, singles, srows);
-            emit(srows, false, "Single");
-            if (nb > 2) {  // output.rs:176-178
-                decode_rows(*run, ctx, doubles, drows);
-                emit(drows, false, "Double");
+            // the owners' marginals add up: on the device when they are dense counter arrays, else row by row in emit()
+            uint64_t* dense = nullptr;
+            uint64_t n_dense = 0;
+            int n_enrich = n_src;
+            if (n_src > 1) {
+                if (bc_marginals(ctx, &dense, &n_dense) != BC_OK) throw Error(bc_last_error(ctx));
+                if (n_dense) {
+                    for (int r = 1; r < n_src; r++) {
+                        if (bc_marginals(ctxs[r], &dense, &n_dense) != BC_OK) throw Error(bc_last_error(ctxs[r]));
+                        if (bc_sync(ctxs[r]) != BC_OK) throw Error(bc_last_error(ctxs[r]));
+                        if (bc_peer_add(ctx, ctxs[r], BC_ADD_MARGINALS) != BC_OK) throw Error(bc_last_error(ctx));
+                    }
+                    n_enrich = 1;
+                }
             }
+            for (int r = 0; r < n_enrich; r++) {
+                if (bc_enrich(ctxs[r], &singles, nb > 2 ? &doubles : nullptr) != BC_OK) throw Error(bc_last_error(ctxs[r]));
+                decode_rows(*run, ctx, singles, srows);
+                if (nb > 2) decode_rows(*run, ctx, doubles, drows);  // output.rs:176-178
+                bc_table_free(&singles);
+                bc_table_free(&doubles);
+            }
+            emit(srows, false, "Single");
+            if (nb > 2) emit(drows, false, "Double");
         }
         if (names_out && names_len > 0) {
             std::string joined;

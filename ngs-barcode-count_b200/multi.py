@@ -1,15 +1,16 @@
 """One whole decode-and-count job over a rank's shard of the reads, for 1..N GPUs (one process per GPU).
 
-Sharding follows SURVEY.md §8(e): reads are independent, so every rank decodes its own contiguous range.
-  * scheme without a random barcode: ranks count locally; the (key, count) rows are merged once at the end
-    (all-gather of the rows, summed into rank 0's table with bc_import_rows);
-  * scheme with a random barcode (UMI): de-duplication has to be global, so bc_decode_route buckets the matched
-    (key, UMI) records by owner = hash(key) % N on the device, the buckets are exchanged with an NCCL all-to-all
-    and every owner inserts what it received (bc_insert_records); the owner decides matched vs duplicate.
-torch.distributed is plumbing only (communicator + buffers); all compute is in the CUDA library.
+Sharding follows SURVEY.md §8(e): reads are independent, so every rank decodes its own contiguous range with the
+single-GPU kernels.  What follows the last batch depends on the counting state of the scheme:
+  * dense count table (small index-coded key space, no random barcode — CRISPR): ONE in-place all-reduce of the table;
+  * hashed keys (any scheme with a random barcode, raw or large key spaces): ONE exchange of the (key[, UMI]) records —
+    record -> owner = hash(key without UMI) % N, written by the library's partitioning kernel straight into the owner's
+    receive buffer over NVLink peer memory (bc_exchange_*); every owner then de-duplicates and counts the keys it owns,
+    so de-duplication is globally exact.  The only collectives are an all-gather of the N x N count matrix and the
+    tiny all-reduce that orders the owners' flush after every rank's scatter.
+torch.distributed is plumbing only (communicator + a few integers); all compute is in the CUDA library.  The same steps
+inside one process (one context per GPU, no communicator) are `bch_count_fastq_multi` in csrc/host/bc_host.cpp.
 """
-import os
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -28,61 +29,42 @@ def dev_tensor(ptr, n, device):
     return torch.as_tensor(_DevArray(ptr, n), device=device)
 
 
-def exchange_records(send, counts, rcounts, recv, world):
-    """All-to-all of variable-length record buckets.  send: [world, cap, 2] int64 (bucket r holds counts[r] records for
-    rank r); recv: [>= total, 2] int64.  Returns the number of records received (packed at the front of recv).
-    Device-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
-    dist.all_to_all_single(rcounts, counts)
-    sc = counts.cpu().tolist()
-    rc = rcounts.cpu().tolist()
-    if max(sc) > send.shape[1]:
-        raise RuntimeError("route bucket overflow: a bucket received more records than its capacity")
-    if sum(rc) > recv.shape[0]:
-        raise RuntimeError("route receive buffer too small")
-    rank = dist.get_rank()
-    ops, off = [], 0
-    for r in range(world):
-        out = recv[off:off + rc[r]]
-        off += rc[r]
-        if r == rank:
-            out.copy_(send[r, :sc[r]])
-            continue
-        if rc[r]:
-            ops.append(dist.P2POp(dist.irecv, out, r))
-        if sc[r]:
-            ops.append(dist.P2POp(dist.isend, send[r, :sc[r]], r))
-    if ops:  # one grouped NCCL call (ncclGroupStart/End) == an all-to-all-v; plain isend/irecv pairs under gloo
-        for q in dist.batch_isend_irecv(ops):
-            q.wait()
-    return off
+def exchange_plan(matrix, rank):
+    """matrix[s][o] = records rank s holds that rank o owns.  Owner o's receive buffer takes the ranks' runs in rank
+    order, so this rank's run starts at first[o] = sum of matrix[s][o] over s < rank.
+    -> (first, received by this rank, largest total any owner receives)"""
+    world = len(matrix)
+    first = [sum(int(matrix[s][o]) for s in range(rank)) for o in range(world)]
+    totals = [sum(int(matrix[s][o]) for s in range(world)) for o in range(world)]
+    return first, totals[rank], max(totals)
 
 
-def gather_rows_to_root(cols, n, rank, world, device):
-    """Gathers every rank's row columns (same length n per rank, differing across ranks) to rank 0.
-    Returns (parts, sizes): parts[c][r] is column c of rank r (rank 0 only), sizes[r] the row count of rank r."""
-    sizes = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=device))
-    sizes = sizes.cpu().tolist()
-    parts = []
-    for src in cols:
-        if rank == 0:
-            p = [torch.empty(s, dtype=torch.int64, device=device) for s in sizes]
-            _gather_var(src, p, sizes, rank, world)
-            parts.append(p)
-        else:
-            _gather_var(src, None, sizes, rank, world)
-    return parts, sizes
+_MASK64 = (1 << 64) - 1
 
 
-def _gather_var(src, parts, sizes, rank, world):
-    # variable-length gather as point-to-point sends (dist.gather needs equal sizes)
-    if rank == 0:
-        parts[0].copy_(src)
-        reqs = [dist.irecv(parts[r], src=r) for r in range(1, world) if sizes[r]]
-        for q in reqs:
-            q.wait()
-    elif sizes[rank]:
-        dist.send(src.contiguous(), dst=0)
+def _lsr(x, s):
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def _mix64(x):
+    """bc::mix64 on int64 tensors (two's complement wrap-around = arithmetic mod 2^64)."""
+    c1 = torch.tensor(0xff51afd7ed558ccd - (1 << 64), dtype=torch.int64, device=x.device)
+    c2 = torch.tensor(0xc4ceb9fe1a85ec53 - (1 << 64), dtype=torch.int64, device=x.device)
+    x = x ^ _lsr(x, 33)
+    x = x * c1
+    x = x ^ _lsr(x, 33)
+    x = x * c2
+    return x ^ _lsr(x, 33)
+
+
+def rows_checksum(lo, hi, cnt):
+    """Order-independent digest of a set of (key, count) rows: (rows, sum of counts, sum of mix64(key) * count), the
+    sums mod 2^64.  Digests of disjoint row sets add up to the digest of their union."""
+    n = lo.numel()
+    if n == 0:
+        return [0, 0, 0]
+    h = _mix64(lo ^ _mix64(hi + 0x1234567)) if hi is not None else _mix64(lo ^ _mix64(torch.full_like(lo, 0x1234567)))
+    return [n, int(cnt.sum().item()) & _MASK64, int((h * cnt).sum().item()) & _MASK64]
 
 
 class HostBatch:
@@ -98,37 +80,34 @@ class HostBatch:
 
 
 class Job:
-    def __init__(self, bc, ctr, run, world, rank, device, stream, has_umi, batch_reads):
+    """ctr: this rank's Counter (or any object with the same methods: the CPU test drives the host logic with a fake).
+    expected_reads: reads per rank, sizes the exchange's receive buffer (it grows when a job needs more)."""
+
+    def __init__(self, bc, ctr, run, world, rank, device, stream, has_umi, expected_reads, deferred=None):
         self.bc, self.ctr, self.run = bc, ctr, run
         self.world, self.rank, self.device, self.stream, self.has_umi = world, rank, device, stream, has_umi
+        self.deferred = bool(ctr.profile()["deferred_count"]) if deferred is None else deferred
+        self.exchange = world > 1 and self.deferred
         if world == 1:
             self.parallelism = "1 GPU"
-        elif has_umi:
-            self.parallelism = (f"reads sharded over {world} GPUs; (key,UMI) records stored by the decode kernel into the owner "
-                                f"GPU hash(key)%{world} over NVLink peer memory; one tiny NCCL all-gather of counts per batch")
+        elif self.exchange:
+            self.parallelism = (f"reads sharded over {world} GPUs; after the last batch the (key,UMI) records are exchanged once: "
+                                f"owner = hash(key) % {world}, written by the partitioning kernel into the owner GPU's memory over "
+                                f"NVLink; each owner de-duplicates and counts its keys")
         else:
-            self.parallelism = (f"reads sharded over {world} GPUs; tables merged once at the end (in-place all-reduce of the "
-                                f"dense count table, or gather of rows for hashed tables)")
-        # measurement aid: BC_SPLIT_COUNT=1 uses the routed path on one GPU too (decode and table updates in separate,
-        # overlapping kernels instead of one fused kernel)
-        self.routed = has_umi and (world > 1 or bool(os.environ.get("BC_SPLIT_COUNT")))
-        if self.routed:
-            # fused routing: every rank maps every other rank's receive buffer (CUDA IPC over NVLink); the decode
-            # kernel stores records straight into the owner's memory.  A (source, owner) region can hold a whole
-            # batch, so no key skew can overflow it.
-            self.cap = batch_reads
-            handles = [None] * world
-            mine = ctr.route_open(world, rank, self.cap)
-            if world > 1:
-                dist.all_gather_object(handles, mine)
-            else:
-                handles = [mine]
-            ctr.route_connect(handles)
-            self.counts = torch.zeros((2, world), dtype=torch.int32, device=device)          # what I sent, per parity
-            self.all_counts = torch.zeros((2, world * world), dtype=torch.int32, device=device)  # [source][owner]
-            self.parity = 0
-            if world > 1:
-                dist.barrier()
+            self.parallelism = (f"reads sharded over {world} GPUs; one in-place all-reduce of the dense count table at the end")
+        if self.exchange:
+            self.cap = 0
+            self._open(int(expected_reads * 1.25) + 4096)
+
+    def _open(self, capacity):
+        """(re)allocate the receive buffers and connect every rank to every other (collective)."""
+        self.ctr.exchange_open(self.world, self.rank, capacity)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.ctr.exchange_handle())
+        self.ctr.exchange_connect(handles)
+        self.cap = capacity
+        dist.barrier()
 
     def to_pinned(self, dev_batch):
         return HostBatch(self.bc, dev_batch)
@@ -137,67 +116,82 @@ class Job:
         return b.batch if isinstance(b, HostBatch) else b
 
     def step(self, batches, to_host=False):
-        """reset -> decode+count every batch -> rows.  Returns the number of (key, count) rows of the whole job
-        (to_host: the rows themselves are also copied to the host, as a drop-in caller would need them)."""
+        """reset -> decode every batch -> merge across ranks -> rows.  Returns the number of (key, count) rows of the
+        whole job (to_host: this rank's rows are also copied to the host, as a drop-in caller would need them)."""
         ctr = self.ctr
         ctr.reset()
         with torch.cuda.stream(self.stream):
-            if self.routed:
-                for b in batches:
-                    self._routed(self._b(b))
-            else:
-                for b in batches:
-                    ctr.submit(self._b(b))
-            if self.world > 1 and not self.has_umi:
-                return self._merge_rows(to_host)
-            if to_host:
-                n = ctr.finish_view()[0]
-            else:
-                n = ctr.export_rows()[3]
+            for b in batches:
+                ctr.submit(self._b(b))
+            if self.exchange:
+                self._exchange()
+            elif self.world > 1:
+                return self._merge_dense(to_host)
+            n = ctr.finish_view()[0] if to_host else ctr.export_rows()[3]
             if self.world > 1:
                 t = torch.tensor([n], dtype=torch.int64, device=self.device)
                 dist.all_reduce(t)
                 n = int(t.item())
             return n
 
-    def _routed(self, batch):
-        """decode + route one batch.  No host synchronisation: the counts stay on the device; the tiny all-gather is
-        the only collective and doubles as the barrier that makes every rank's peer stores visible to the owner."""
-        p = self.parity
-        self.parity ^= 1
-        self.ctr.route_submit(batch, p, self.counts[p])
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.all_counts[p], self.counts[p])
-        else:
-            self.all_counts[p].copy_(self.counts[p])
-        # records sent to me by source s: all_counts[p][s * world + rank]
-        self.ctr.route_insert(p, self.all_counts[p].data_ptr() + 4 * self.rank, self.world, int(batch.n * 1.5))
+    def _exchange(self):
+        """The one exchange step of a job with hashed keys.  Every rank computes the same plan from the same matrix."""
+        sent = self.ctr.exchange_count(self.world)
+        mine = torch.tensor(sent, dtype=torch.int64, device=self.device)
+        matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(matrix, mine)
+        matrix = matrix.view(self.world, self.world).cpu().tolist()
+        first, received, need = exchange_plan(matrix, self.rank)
+        if need > self.cap:  # a skewed job (hot keys): every rank sees the same matrix and grows together
+            self._open(int(need * 1.1) + 4096)
+        self.ctr.exchange_scatter(first)
+        # orders the owners' flush after every rank's scatter: a rank leaves the all-reduce only once all have entered it,
+        # and each enters it on the stream its scatter kernel runs on
+        dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=self.device))
+        self.ctr.exchange_finish(received)
+        self.last_matrix = matrix
 
-    def _merge_rows(self, to_host):
+    def _merge_dense(self, to_host):
         ptr, n_dense = self.ctr.dense_counts()
-        if n_dense:  # dense table: one in-place all-reduce, then rank 0 extracts the rows
-            dist.all_reduce(dev_tensor(ptr, n_dense, self.device))
-            if self.rank == 0:
-                n_rows = self.ctr.finish_view()[0] if to_host else self.ctr.export_rows()[3]
-            else:
-                n_rows = 0
-            t = torch.tensor([n_rows], dtype=torch.int64, device=self.device)
-            dist.broadcast(t, src=0)
-            return int(t.item())
-        lo, hi, cnt, n = self.ctr.export_rows()
-        wide = hi is not None and hi != 0
-        cols = [dev_tensor(p, n, self.device) for p in ((lo, hi, cnt) if wide else (lo, cnt))]
-        parts, sizes = gather_rows_to_root(cols, n, self.rank, self.world, self.device)
-        if self.rank == 0:
-            for r in range(1, self.world):
-                if sizes[r]:
-                    self.ctr.import_rows(parts[0][r], parts[1][r] if wide else None, parts[-1][r], sizes[r])
+        if not n_dense:
+            raise RuntimeError("multi-GPU jobs need deferred counting (exchange) or a dense count table (all-reduce); "
+                               "BC_CFG_INLINE_COUNT hash tables are a single-GPU measurement aid")
+        dist.all_reduce(dev_tensor(ptr, n_dense, self.device))
+        if self.rank == 0:  # the merged table is on every rank; rank 0 extracts the rows
             n_rows = self.ctr.finish_view()[0] if to_host else self.ctr.export_rows()[3]
         else:
             n_rows = 0
         t = torch.tensor([n_rows], dtype=torch.int64, device=self.device)
         dist.broadcast(t, src=0)
         return int(t.item())
+
+    def owns_rows(self):
+        """whether this rank's rows are part of the job's result (exchange: every owner; dense merge: rank 0 only)"""
+        return self.world == 1 or self.exchange or self.rank == 0
+
+    def checksum(self):
+        """Digest of the job's final rows, summed over the ranks (see rows_checksum)."""
+        d = [0, 0, 0]
+        if self.owns_rows():
+            lo, hi, cnt, n = self.ctr.export_rows()
+            with torch.cuda.stream(self.stream):
+                d = rows_checksum(dev_tensor(lo, n, self.device), dev_tensor(hi, n, self.device) if hi else None,
+                                  dev_tensor(cnt, n, self.device))
+        if self.world > 1:
+            t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in d], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t)
+            d = [int(x) & _MASK64 for x in t.tolist()]
+        return d
+
+    def merged_marginals(self):
+        """Enrichment marginals of the whole job (dense counters summed over the owners); rank 0 then calls enrich()."""
+        ptr, n = self.ctr.marginals()
+        if self.world > 1 and self.exchange and n:
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(dev_tensor(ptr, n, self.device))
+            torch.cuda.current_stream().synchronize()
+            self.stream.synchronize()
+        return n
 
     def global_counters(self):
         c = self.ctr.counters()

@@ -1,6 +1,7 @@
 """Run under torchrun with N >= 2 GPUs (tests/test_multi_gpu.py launches it): every rank decodes its shard of one
-global read range through ngs-barcode-count_b200/multi.py (hash-routed UMI de-duplication or final table merge over
-NCCL); the merged result must be identical to a single-GPU job over the whole range."""
+global read range through ngs-barcode-count_b200/multi.py (one exchange of the records over NVLink, or one all-reduce of
+the dense table); the merged result must be identical to a single-GPU job over the whole range: counters, every
+(key, count) row, the order-independent row digest bench.py prints, and the enrichment marginals."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ngs_barcode_count_b200 as bc  # noqa: E402
 from ngs_barcode_count_b200 import synth  # noqa: E402
-from ngs_barcode_count_b200.multi import Job, dev_tensor  # noqa: E402
+from ngs_barcode_count_b200.multi import Job  # noqa: E402
 
 
 def rows_of(ctr):
@@ -20,6 +21,14 @@ def rows_of(ctr):
     hi = hi if hi is not None else np.zeros(n, np.uint64)
     order = np.lexsort((lo, hi))
     return np.stack([hi[order], lo[order], cnt[order]], axis=1).copy()
+
+
+def marg_of(ctr):
+    s, d = ctr.enrich(doubles=True)
+    out = []
+    for t in (s, d):
+        out += sorted(zip(t["mask"].tolist(), t["key_hi"].tolist(), t["key_lo"].tolist(), t["count"].tolist()))
+    return out
 
 
 def main():
@@ -34,15 +43,18 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctr = bc.Counter(run, device=local, expected_reads=per_gpu * 2)
     ctr.set_stream(stream.cuda_stream)
-    job = Job(bc, ctr, run, world, rank, dev, stream, has_umi, batch)
+    # a receive buffer sized for a tenth of the shard: the first job has to grow it (collectively)
+    job = Job(bc, ctr, run, world, rank, dev, stream, has_umi, max(1, per_gpu // 10))
     with torch.cuda.stream(stream):
         batches = [wl.generate_device(run, rank * per_gpu + a, min(batch, per_gpu - a), device=dev, stream=stream.cuda_stream)
                    for a in range(0, per_gpu, batch)]
     for _ in range(2):  # twice: reset between jobs must work
         n_rows = job.step(batches, to_host=True)
     counters = job.global_counters()
-    # gather every rank's rows on rank 0 (routed mode: disjoint key partitions; merge mode: rank 0 holds everything)
-    mine = rows_of(ctr) if (has_umi or rank == 0) else np.zeros((0, 3), np.uint64)
+    digest = job.checksum()
+    n_marg = job.merged_marginals() if wl.enrich else 0
+    # gather every rank's rows on rank 0 (exchange: disjoint key partitions; dense merge: rank 0 holds everything)
+    mine = rows_of(ctr) if job.owns_rows() else np.zeros((0, 3), np.uint64)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     ok = True
@@ -56,9 +68,12 @@ def main():
             single.submit(b)
         want_counters = single.counters()
         want_rows = rows_of(single)
+        sjob = Job(bc, single, run, 1, 0, dev, torch.cuda.current_stream(), has_umi, per_gpu * world)
         ok = counters == want_counters and multi_rows.shape == want_rows.shape and bool((multi_rows == want_rows).all()) \
-            and n_rows == want_rows.shape[0]
-        print(f"MULTI_GPU_CHECK {name} world={world} reads={per_gpu * world} rows={n_rows} counters={counters} "
+            and n_rows == want_rows.shape[0] and digest == sjob.checksum()
+        if ok and wl.enrich and n_marg:
+            ok = marg_of(ctr) == marg_of(single)
+        print(f"MULTI_GPU_CHECK {name} world={world} reads={per_gpu * world} rows={n_rows} counters={counters} digest={digest} "
               f"{'OK' if ok else 'MISMATCH ' + str(want_counters) + ' rows ' + str(want_rows.shape)}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)

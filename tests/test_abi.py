@@ -122,8 +122,13 @@ def test_pack_bit_layout():
         assert set(bytes(b.qual[i, len(s):])) <= {ord("!")}
     with pytest.raises(bc.BcError):
         run.pack(["A" * (run.max_read_len + 1)], ["I" * (run.max_read_len + 1)])
-    with pytest.raises(bc.BcError):
-        run.pack(["ACGT"], ["II"])
+    # a quality line shorter than its sequence is not an error (the reference zips scores with region codes and simply
+    # stops with the line, parse.rs:338-343): from the line's last score on the row holds 255, which no threshold rejects
+    b = run.pack(["ACGTACGTAC", "ACGT", "ACGT"], ["IIII", "", "IIIIIIII"])
+    assert bytes(b.qual[0, :3]) == b"III" and set(bytes(b.qual[0, 3:])) == {255}
+    assert set(bytes(b.qual[1])) == {255}
+    assert bytes(b.qual[2, :4]) == b"IIII" and set(bytes(b.qual[2, 4:])) == {ord("!")}  # a longer line is cut
+    assert list(b.read_len[:3]) == [10, 4, 4]
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -393,26 +393,23 @@ def test_table_growth_and_many_keys():
     assert got == want
 
 
-def _count_mode(monkeypatch, mode):
-    """deferred: records appended, partitioned shared-memory flush (default); global: same records flushed through the
-    global-memory tables (the overflow fallback); inline: tables updated read by read inside k_decode."""
-    monkeypatch.delenv("BC_FLUSH_GLOBAL", raising=False)
-    monkeypatch.delenv("BC_INLINE_COUNT", raising=False)
-    monkeypatch.delenv("BC_FLUSH_TWO_STAGE", raising=False)
+def _counter(run, mode, **kw):
+    """deferred: records appended, partitioned shared-memory flush (default); two_stage: the flush's hot-key path for every
+    key; global: same records flushed through the global-memory tables (the overflow fallback); inline: tables updated
+    read by read inside k_decode (bc_config.flags = BC_CFG_INLINE_COUNT)."""
+    ctr = bc.Counter(run, flags=bc.BC_CFG_INLINE_COUNT if mode == "inline" else 0, **kw)
     if mode == "global":
-        monkeypatch.setenv("BC_FLUSH_GLOBAL", "1")
-    elif mode == "inline":
-        monkeypatch.setenv("BC_INLINE_COUNT", "1")
+        ctr.set_option("flush_global", 1)
     elif mode == "two_stage":
-        monkeypatch.setenv("BC_FLUSH_TWO_STAGE", "1")
+        ctr.set_option("flush_two_stage", 1)
+    return ctr
 
 
 @pytest.mark.parametrize("mode", ["deferred", "two_stage", "global", "inline"])
-def test_counting_modes_skewed_keys(mode, monkeypatch):
+def test_counting_modes_skewed_keys(mode):
     """What the deferred counting has to survive: one (key, UMI) pair repeated far beyond a partition's table size, one hot
     key with tens of thousands of distinct UMIs, many singleton keys — in several submits, with counters read (= a flush)
     in between.  Expected counts are computed in Python from the construction."""
-    _count_mode(monkeypatch, mode)
     exp, paths = load_golden("lineage_raw")
     run = make_run(paths, exp["flags"])
     rng = random.Random(11)
@@ -440,7 +437,7 @@ def test_counting_modes_skewed_keys(mode, monkeypatch):
     want = {}
     for k, _ in pairs:
         want[k] = want.get(k, 0) + 1
-    ctr = bc.Counter(run, expected_reads=0)
+    ctr = _counter(run, mode, expected_reads=0)
     assert ctr.profile()["deferred_count"] == (0 if mode == "inline" else 1)
     batch = run.pack(seqs)
     cuts = [0, 7000, 7001, 40000, batch.n]
@@ -465,19 +462,14 @@ def test_counting_modes_skewed_keys(mode, monkeypatch):
     assert sum(ctr.counters().values()) == 5000
 
 
-@pytest.mark.parametrize("mode", ["two_stage", "global", "inline", "qual_staged"])
+@pytest.mark.parametrize("mode", ["two_stage", "global", "inline"])
 @pytest.mark.parametrize("case", ["del3_umi", "example", "sample_raw_two", "example_q20"])
-def test_golden_csv_other_counting_modes(case, mode, tmp_path, monkeypatch):
-    """The golden CSV sets through the non-default paths: the other counting modes, and the quality bytes staged in
-    shared memory instead of read from global memory (the defaults are covered by test_golden_per_read_and_csv)."""
-    _count_mode(monkeypatch, mode)
-    monkeypatch.delenv("BC_QUAL_STAGED", raising=False)
-    if mode == "qual_staged":
-        monkeypatch.setenv("BC_QUAL_STAGED", "1")
+def test_golden_csv_other_counting_modes(case, mode, tmp_path):
+    """The golden CSV sets through the non-default counting paths (the default is covered by test_golden_per_read_and_csv)."""
     exp, paths = load_golden(case)
     fl = exp["flags"]
     run = make_run(paths, fl)
-    ctr = bc.Counter(run)
+    ctr = _counter(run, mode)
     reads = read_fastq(paths["fastq"])
     ctr.submit(run.pack([r[0] for r in reads], [r[1] for r in reads]))
     c = ctr.counters()
@@ -565,11 +557,14 @@ def test_import_rows_merge_without_random_barcode():
     assert ca["matched"] + cb["matched"] == cw["matched"] and sum(r[2] for r in want) == cw["matched"]
 
 
-@pytest.mark.parametrize("case", ["del3_umi", "lineage_raw"])
-def test_decode_route_then_insert_records(case):
-    """The bucket API of hash-routed de-duplication (bc_decode_route -> exchange -> bc_insert_records), with one context
-    playing every owner: decoding into three owner buckets and inserting the buckets must give what bc_submit gives."""
-    import torch
+@pytest.mark.parametrize("n_ranks", [2, 3])
+@pytest.mark.parametrize("case", ["del3_umi", "lineage_raw", "example", "sample_raw_two"])
+def test_exchange_between_contexts_on_one_gpu(case, n_ranks):
+    """The multi-GPU exchange (bc_exchange_*: records scattered into their owner's receive buffer by the partitioning
+    kernel, every owner de-duplicating what it received) with the ranks being contexts on ONE GPU: the union of the
+    owners' rows, and the sum of their counters, must be exactly what a single context gives on all the reads.  Covers
+    the N > 1 device code on a one-GPU box (tests/test_multi_gpu.py runs it over NVLink when the box has more)."""
+    from ngs_barcode_count_b200.multi import exchange_plan
     exp, paths = load_golden(case)
     run = make_run(paths, exp["flags"])
     reads = read_fastq(paths["fastq"])
@@ -581,17 +576,35 @@ def test_decode_route_then_insert_records(case):
 
     direct = bc.Counter(run)
     direct.submit(batch)
-    routed = bc.Counter(run)
-    n_ranks, cap = 3, batch.n
-    buckets = torch.zeros((n_ranks, cap, 2), dtype=torch.int64, device="cuda:0")
-    counts = torch.zeros(n_ranks, dtype=torch.int32, device="cuda:0")
-    torch.cuda.synchronize()  # the context works on its own stream
-    routed.decode_route(batch, n_ranks, buckets, cap, counts)
-    routed.sync()
-    got_counts = counts.cpu().tolist()
-    assert sum(got_counts) == exp["counters"]["matched"] + exp["counters"]["duplicates"]
-    for r in range(n_ranks):
-        routed.insert_records(buckets[r], got_counts[r])
-    c0, c1 = direct.counters(), routed.counters()
-    assert c0 == c1 and {k: v for k, v in c0.items() if k != "unsupported"} == exp["counters"]
-    assert rows_of(routed) == rows_of(direct)
+    want_rows, want_c = rows_of(direct), direct.counters()
+    if not direct.profile()["deferred_count"]:
+        pytest.skip("dense count table: ranks merge with an all-reduce, not an exchange")
+    ranks = [bc.Counter(run) for _ in range(n_ranks)]
+    for r, c in enumerate(ranks):
+        c.exchange_open(n_ranks, r, batch.n + 16)
+    for c in ranks:
+        c.exchange_connect_local(ranks)
+    cuts = [batch.n * r // n_ranks for r in range(n_ranks + 1)]
+    for rep in range(2):  # twice: a reset in between must leave the exchange usable
+        for r, c in enumerate(ranks):
+            c.reset()
+            c.submit(batch.slice(cuts[r], cuts[r + 1]))
+        with pytest.raises(bc.BcError):
+            ranks[0].counters()  # a rank of a multi-GPU job has no counters before the exchange
+        matrix = [c.exchange_count(n_ranks) for c in ranks]
+        assert sum(map(sum, matrix)) == want_c["matched"] + want_c["duplicates"]
+        for r, c in enumerate(ranks):
+            c.exchange_scatter(exchange_plan(matrix, r)[0])
+        for c in ranks:
+            c.sync()  # the barrier of the in-process form
+        for r, c in enumerate(ranks):
+            c.exchange_finish(exchange_plan(matrix, r)[1])
+        got_rows, got_c = [], {k: 0 for k in want_c}
+        for c in ranks:
+            got_rows += rows_of(c)
+            for k, v in c.counters().items():
+                got_c[k] += v
+        assert got_c == want_c
+        assert sorted(got_rows) == want_rows
+        keys = [(h, l) for h, l, _ in got_rows]
+        assert len(set(keys)) == len(keys)  # owners hold disjoint key sets

@@ -1,6 +1,7 @@
-"""CPU tests of the FASTQ block reader (host side of bch_count_fastq, reached through the bch_scan_fastq test hook):
-plain text, gzip with one and with several members, and bgzip (BGZF) input whose members are inflated in parallel must
-all yield the same records, in file order (input.rs:24-89, 115-148)."""
+"""CPU tests of the FASTQ readers (host side of bch_count_fastq, reached through the bch_scan_fastq / bch_split_fastq test
+hooks): plain text through the block reader and through the mapped-file splitter, gzip with one and with several members,
+and bgzip (BGZF) input whose members are inflated in parallel must all yield the same records, in file order
+(input.rs:24-89, 115-148)."""
 import gzip
 import random
 import zlib
@@ -76,3 +77,57 @@ def test_block_reader_rejects_other_extensions(tmp_path):
     p.write_bytes(b"@r\nACGT\n+\nIIII\n")
     with pytest.raises(bc.BcError, match="only works with"):
         bc.scan_fastq(str(p))
+
+
+@pytest.mark.parametrize("n_records", [1, 2, 3, 5, 20, 700])
+@pytest.mark.parametrize("last_newline", [True, False])
+def test_mapped_splitter_small_files_many_threads(tmp_path, n_records, last_newline):
+    """The plain-file path cuts every block into one slice per host thread.  A file with fewer records than threads
+    leaves slices empty; the slice that really ends at the end of the file is the one that may lack the final newline
+    (the reference's BufRead::lines() yields that last line, input.rs:44)."""
+    data, want = make_fastq(n_records, 100 + n_records, last_newline=last_newline)
+    p = tmp_path / "r.fastq"
+    p.write_bytes(data)
+    for threads in (1, 2, 16, 64):
+        assert bc.split_fastq(str(p), threads=threads) == want, threads
+        assert bc.split_fastq(str(p), threads=threads, min_slice=1) == want, threads  # one slice per thread: most are empty
+        assert bc.split_fastq(str(p), threads=threads, block_bytes=2000, min_slice=16) == want, threads
+
+
+@pytest.mark.parametrize("crlf,last_newline", [(False, True), (True, True), (False, False), (True, False)])
+def test_mapped_splitter_equals_block_reader(tmp_path, crlf, last_newline):
+    data, want = make_fastq(40000, 21, crlf=crlf, last_newline=last_newline)
+    p = tmp_path / "r.fastq"
+    p.write_bytes(data)
+    assert bc.scan_fastq(str(p)) == want
+    for threads, block in ((1, 0), (7, 0), (16, 1 << 20), (64, 300_000), (3, 70_000)):
+        assert bc.split_fastq(str(p), threads=threads, block_bytes=block) == want, (threads, block)
+        assert bc.split_fastq(str(p), threads=threads, block_bytes=block, min_slice=500) == want, (threads, block)
+
+
+def test_mapped_splitter_quality_lines_starting_with_at(tmp_path):
+    """'@' is a legal quality character (Phred 31): a quality line that starts with it must not be taken for a header."""
+    rng = random.Random(4)
+    recs, crc, bases = [], zlib.crc32(b""), 0
+    for i in range(5000):
+        n = rng.randint(20, 60)
+        seq = "".join(rng.choice("ACGT") for _ in range(n))
+        qual = "@" + "".join(rng.choice("@+IF") for _ in range(n - 1))
+        recs.append(f"@r{i}\n{seq}\n+\n{qual}\n")
+        crc = zlib.crc32(qual.encode(), zlib.crc32(seq.encode(), crc))
+        bases += n
+    p = tmp_path / "at.fastq"
+    p.write_bytes("".join(recs).encode())
+    for threads in (1, 5, 32):
+        assert bc.split_fastq(str(p), threads=threads, block_bytes=100_000, min_slice=1000) == (5000, bases, crc)
+
+
+def test_mapped_splitter_reports_malformed_records(tmp_path):
+    good, _ = make_fastq(3000, 8)
+    lines = good.decode().split("\n")
+    del lines[4001]  # a record in the middle loses its sequence line
+    p = tmp_path / "bad.fastq"
+    p.write_bytes("\n".join(lines).encode())
+    with pytest.raises(bc.BcError):
+        for threads in (4, 16):
+            bc.split_fastq(str(p), threads=threads, block_bytes=50_000, min_slice=1000)

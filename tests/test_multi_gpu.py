@@ -1,5 +1,5 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): N ranks over NCCL give exactly the single-GPU
-result — counters, number of rows and every (key, count) row — both for hash-routed UMI de-duplication (DEL, lineage)
+result — counters, number of rows, every (key, count) row and the enrichment marginals — both for the one-exchange UMI de-duplication (DEL, lineage)
 and for the final table merge (CRISPR)."""
 import os
 import subprocess

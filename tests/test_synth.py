@@ -110,45 +110,62 @@ def test_job_is_independent_of_batching_and_order(name, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["del3", "lineage"])
-def test_routed_path_on_one_gpu_equals_fused(name, tmp_path, monkeypatch):
-    """The multi-GPU route API (bc_route_open / connect / submit / insert: records stored into a receive buffer by the
-    decode kernel, inserted by a second kernel on its own stream) driven with a single rank must give exactly the
-    fused single-kernel result.  Covers the N > 1 device code on a one-GPU box."""
+def test_exchange_on_one_gpu_equals_single_context(name, tmp_path):
+    """Four contexts on one GPU play the ranks of a multi-GPU job on a BASELINE workload (hundreds of partitions per
+    owner, hot keys for lineage): decode a quarter of the reads each, exchange once (bc_exchange_*), and the union of the
+    owners' rows / the sum of their counters must equal the single-context job."""
     import torch
-    from ngs_barcode_count_b200.multi import Job
-    n, batch = 1_000_000, 300_000
+    from ngs_barcode_count_b200.multi import exchange_plan
+    n, batch, world = 2_000_000, 250_000, 4
     wl = synth.Workload(name, str(tmp_path / name), reads=n)
     run = wl.run(bc)
-    stream = torch.cuda.Stream()
-    with torch.cuda.stream(stream):
-        batches = [wl.generate_device(run, a, min(batch, n - a), stream=stream.cuda_stream) for a in range(0, n, batch)]
-    stream.synchronize()
+    batches = [wl.generate_device(run, a, min(batch, n - a)) for a in range(0, n, batch)]
+    torch.cuda.synchronize()
 
-    def result(split):
-        if split:
-            monkeypatch.setenv("BC_SPLIT_COUNT", "1")
-        else:
-            monkeypatch.delenv("BC_SPLIT_COUNT", raising=False)
-        ctr = bc.Counter(run, expected_reads=n)
-        ctr.set_stream(stream.cuda_stream)
-        job = Job(bc, ctr, run, 1, 0, "cuda:0", stream, True, batch)
-        assert job.routed == split
-        for _ in range(2):
-            job.step(batches, to_host=True)
+    def rows(ctr):
         k, lo, hi, cnt = ctr.finish_view()
         hi = hi if hi is not None else np.zeros(k, np.uint64)
-        order = np.lexsort((lo, hi))
-        return ctr.counters(), np.stack([hi[order], lo[order], cnt[order]], axis=1).copy()
+        return np.stack([hi, lo, cnt], axis=1).copy()
 
-    c0, r0 = result(False)
-    c1, r1 = result(True)
-    assert c0 == c1 and sum(c0.values()) == n and (name != "del3" or c0["duplicates"] > 0)
+    def canon(r):
+        return r[np.lexsort((r[:, 1], r[:, 0]))]
+
+    single = bc.Counter(run, expected_reads=n)
+    for b in batches:
+        single.submit(b)
+    c0, r0 = single.counters(), canon(rows(single))
+    ranks = [bc.Counter(run, expected_reads=n // world) for _ in range(world)]
+    for r, c in enumerate(ranks):
+        c.exchange_open(world, r, 64)  # far too small: the plan below has to ask for more
+    for i, b in enumerate(batches):
+        ranks[i * world // len(batches)].submit(b)
+    matrix = [c.exchange_count(world) for c in ranks]
+    need = max(exchange_plan(matrix, r)[2] for r in range(world))
+    assert need > 64
+    with pytest.raises(bc.BcError):
+        ranks[0].exchange_connect_local(ranks)
+        ranks[0].exchange_scatter(exchange_plan(matrix, 0)[0])  # past the capacity: refused, nothing written
+    for r, c in enumerate(ranks):
+        c.exchange_open(world, r, need)  # re-open larger: the records are still there
+    for c in ranks:
+        c.exchange_connect_local(ranks)
+    matrix2 = [c.exchange_count(world) for c in ranks]
+    assert matrix2 == matrix
+    for r, c in enumerate(ranks):
+        c.exchange_scatter(exchange_plan(matrix, r)[0])
+    for c in ranks:
+        c.sync()
+    for r, c in enumerate(ranks):
+        c.exchange_finish(exchange_plan(matrix, r)[1])
+    c1 = {k: sum(c.counters()[k] for c in ranks) for k in c0}
+    r1 = canon(np.concatenate([rows(c) for c in ranks]))
+    assert c1 == c0 and sum(c0.values()) == n and (name != "del3" or c0["duplicates"] > 0)
     assert r0.shape == r1.shape and bool((r0 == r1).all())
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["del3", "lineage", "example"])
-def test_counting_modes_agree_on_workloads(name, tmp_path, monkeypatch):
+def test_counting_modes_agree_on_workloads(name, tmp_path):
     """Deferred partitioned counting (default), its global-table fallback and the read-by-read inline tables must give the
     same counters and the same (key, count) rows on the BASELINE workloads (hundreds of partitions per stage)."""
     import torch
@@ -163,19 +180,13 @@ def test_counting_modes_agree_on_workloads(name, tmp_path, monkeypatch):
     stream.synchronize()
 
     def result(mode):
-        monkeypatch.delenv("BC_FLUSH_GLOBAL", raising=False)
-        monkeypatch.delenv("BC_INLINE_COUNT", raising=False)
-        monkeypatch.delenv("BC_SPLIT_COUNT", raising=False)
-        monkeypatch.delenv("BC_FLUSH_TWO_STAGE", raising=False)
+        ctr = bc.Counter(run, expected_reads=n, flags=bc.BC_CFG_INLINE_COUNT if mode == "inline" else 0)
         if mode == "two_stage":
-            monkeypatch.setenv("BC_FLUSH_TWO_STAGE", "1")
+            ctr.set_option("flush_two_stage", 1)
         if mode == "global":
-            monkeypatch.setenv("BC_FLUSH_GLOBAL", "1")
-        elif mode == "inline":
-            monkeypatch.setenv("BC_INLINE_COUNT", "1")
-        ctr = bc.Counter(run, expected_reads=n)
+            ctr.set_option("flush_global", 1)
         ctr.set_stream(stream.cuda_stream)
-        job = Job(bc, ctr, run, 1, 0, "cuda:0", stream, has_umi, batch)
+        job = Job(bc, ctr, run, 1, 0, "cuda:0", stream, has_umi, n)
         for _ in range(2):
             job.step(batches, to_host=True)
         k, lo, hi, cnt = ctr.finish_view()
