@@ -285,7 +285,8 @@ def decode_roofline(leg, prof, counters, steps, ms_total, peak, config):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(config)
     return {"bound": "hbm", "achieved": achieved, "peak": peak[0], "unit": "GB/s", "frac": achieved / peak[0], "traffic": traffic,
-            "kernel": "k_decode", "bytes_per_read": bpr + table_bpr, "bytes_per_read_input": bpr,
+            "kernel": "k_decode_jit (the decode kernel specialised for the run by NVRTC)" if prof["specialized_launches"] else "k_decode",
+            "specialization": prof["specialization"], "bytes_per_read": bpr + table_bpr, "bytes_per_read_input": bpr,
             "bytes_per_read_written_or_touched": table_bpr, "achieved_input_only": achieved_input,
             "frac_input_only": achieved_input / peak[0], "reads_per_launch": per_gpu * steps / max(1, dec_launches),
             "avg_launch_ms": dec_ms / max(1, dec_launches), "kernel_share_of_step": dec_ms / (ms_total if ms_total else 1),

@@ -99,6 +99,12 @@ typedef struct {
 /* bc_config.flags.  BC_CFG_INLINE_COUNT: update global hash tables read by read inside the decode kernel instead of
  * appending records and counting them at the flush (measurement aid: the design the deferred flush replaced). */
 #define BC_CFG_INLINE_COUNT 1u
+/* The decode kernel exists twice: generic (any scheme, run constants read from a kernel parameter) and specialised for
+ * the run by NVRTC (same device code, constants folded in; about two seconds of compilation, cached per process and
+ * configuration).  bc_create specialises when expected_reads >= 2^22; these flags force it (bc_create fails when the
+ * specialisation cannot be built) or forbid it.  Results are identical either way. */
+#define BC_CFG_SPECIALIZE 2u
+#define BC_CFG_NO_SPECIALIZE 4u
 
 enum { BC_LOC_HOST = 0, BC_LOC_DEVICE = 1 };
 
@@ -136,6 +142,11 @@ typedef struct bc_ctx bc_ctx;
 int bc_create(const bc_config *cfg, int device, uint64_t expected_reads, bc_ctx **out);
 void bc_destroy(bc_ctx *ctx);
 int bc_device_of(const bc_ctx *ctx); /* the CUDA device the context was created on */
+/* "specialised", or why the context runs the generic decode kernel (small job, no libnvrtc, compile log). */
+const char *bc_specialization_note(const bc_ctx *ctx);
+/* Host-only check that the specialised decode kernel of `cfg` compiles for sm_100a (NVRTC, no GPU needed): BC_OK and
+ * "cubin bytes: N" in log, or an error code and the reason. */
+int bc_jit_check(const bc_config *cfg, char *log, int loglen);
 /* Message of the last failure on `ctx`; ctx == NULL gives the last bc_create failure of this thread. */
 const char *bc_last_error(const bc_ctx *ctx);
 
@@ -276,6 +287,7 @@ typedef struct {
     uint32_t deferred_count; /* 1: matched reads are appended to a record buffer and counted at bc_finish /
                                 bc_get_counters (partitioned, in shared memory); 0: tables updated read by read */
     uint32_t flushed_global; /* 1: the last flush fell back to the global-memory tables */
+    uint64_t specialized_launches, generic_launches; /* decode launches through the NVRTC-specialised / the generic kernel */
     uint32_t flush_stages;   /* the last shared-memory flush: 1 = no hot key, partitioned by key and counted in one pass;
                                 2 = partitioned by (key, random barcode), then by key; 3 = one pass, with the few hot
                                 keys' partitions set aside and sent through the two stages */

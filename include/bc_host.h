@@ -34,6 +34,10 @@ typedef struct {
 /* Parses the three input files and derives the caps; on failure returns NULL and writes the message. */
 bch_run *bch_open(const bch_args *args, char *err, int errlen);
 void bch_close(bch_run *run);
+/* The reference rewrites "Total sequences: N" in place while it reads (input.rs:54-57, 151-158): fn is called with the
+ * number of records handed to the GPU so far, after every batch of bch_count_fastq[_multi]. */
+typedef void (*bch_progress_fn)(uint64_t reads_so_far, void *user);
+void bch_set_progress(bch_run *run, bch_progress_fn fn, void *user);
 /* The configuration to hand to bc_create (owned by `run`). */
 const bc_config *bch_config(const bch_run *run);
 /* "-FORMAT-" and "-BARCODE INFO-" blocks as the reference prints them (info.rs:313-335, 618-659). */

@@ -25,7 +25,7 @@ BC_READ_UNSUPPORTED = 0x8000
 STATUS_NAMES = ["matched", "duplicate", "constant_region", "low_quality", "sample_barcode", "barcode", "unsupported"]
 COUNTER_NAMES = ["matched", "constant_region", "sample_barcode", "barcode", "duplicates", "low_quality", "unsupported"]
 KERNEL_NAMES = ["decode", "scan", "insert", "finish", "other", "enrich", "exchange"]
-BC_CFG_INLINE_COUNT = 1
+BC_CFG_INLINE_COUNT, BC_CFG_SPECIALIZE, BC_CFG_NO_SPECIALIZE = 1, 2, 4
 BC_ADD_DENSE_COUNTS, BC_ADD_MARGINALS = 0, 1
 
 
@@ -68,7 +68,8 @@ class bc_profile(C.Structure):
     _fields_ = [("launches", C.c_uint64 * BC_N_KERNELS), ("ms", C.c_double * BC_N_KERNELS), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("table_capacity", C.c_uint64), ("table_entries", C.c_uint64),
                 ("key_bits", C.c_uint32), ("wide_keys", C.c_uint32), ("dense_table", C.c_uint32),
-                ("deferred_count", C.c_uint32), ("flushed_global", C.c_uint32), ("flush_stages", C.c_uint32)]
+                ("deferred_count", C.c_uint32), ("flushed_global", C.c_uint32), ("specialized_launches", C.c_uint64),
+                ("generic_launches", C.c_uint64), ("flush_stages", C.c_uint32)]
 
 
 def scan_fastq(path, threads=0):
@@ -134,6 +135,8 @@ _PROTOS = {
     "bc_create": (C.c_int, [C.POINTER(bc_config), C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bc_destroy": (None, [C.c_void_p]),
     "bc_device_of": (C.c_int, [C.c_void_p]),
+    "bc_specialization_note": (C.c_char_p, [C.c_void_p]),
+    "bc_jit_check": (C.c_int, [C.POINTER(bc_config), C.c_char_p, C.c_int]),
     "bc_last_error": (C.c_char_p, [C.c_void_p]),
     "bc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_submit": (C.c_int, [C.c_void_p, C.POINTER(bc_batch)]),
@@ -168,6 +171,7 @@ _PROTOS = {
     "bc_reset_profile": (C.c_int, [C.c_void_p]),
     "bch_open": (C.c_void_p, [C.POINTER(bch_args), C.c_char_p, C.c_int]),
     "bch_close": (None, [C.c_void_p]),
+    "bch_set_progress": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bch_config": (C.POINTER(bc_config), [C.c_void_p]),
     "bch_describe": (C.c_char_p, [C.c_void_p]),
     "bch_barcode_num": (C.c_uint32, [C.c_void_p]),
@@ -254,6 +258,12 @@ class Run:
 
     def describe(self):
         return lib().bch_describe(self.h).decode()
+
+    def jit_check(self):
+        """Compiles the run's specialised decode kernel with NVRTC (no GPU needed) -> (ok, log)"""
+        log = C.create_string_buffer(8192)
+        rc = lib().bc_jit_check(C.byref(self.cfg), log, 8192)
+        return rc == 0, log.value.decode()
 
     def ref_dna(self, slot, i):
         v = lib().bch_ref_dna(self.h, slot, i)
@@ -505,4 +515,6 @@ class Counter:
                     ms=dict(zip(KERNEL_NAMES, [float(x) for x in p.ms])), h2d_bytes=int(p.h2d_bytes),
                     d2h_bytes=int(p.d2h_bytes), table_capacity=int(p.table_capacity), table_entries=int(p.table_entries),
                     key_bits=int(p.key_bits), wide_keys=int(p.wide_keys), dense_table=int(p.dense_table),
-                    deferred_count=int(p.deferred_count), flushed_global=int(p.flushed_global), flush_stages=int(p.flush_stages))
+                    deferred_count=int(p.deferred_count), flushed_global=int(p.flushed_global), flush_stages=int(p.flush_stages),
+                    specialized_launches=int(p.specialized_launches), generic_launches=int(p.generic_launches),
+                    specialization=lib().bc_specialization_note(self.h).decode())

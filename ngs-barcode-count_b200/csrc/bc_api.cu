@@ -11,6 +11,7 @@
 
 #include "../../include/bc_b200.h"
 #include "bc_kernels.h"
+#include "bc_jit.h"
 
 using namespace bc;
 
@@ -86,6 +87,10 @@ struct bc_ctx {
     // options (bc_set_option): measurement / test switches of the flush
     bool opt_flush_global = false, opt_flush_two_stage = false;
     uint32_t cfg_flags = 0;
+    // the decode kernel specialised for this run by NVRTC (bc_jit.cu); kernel == nullptr: the generic kernel is used
+    JitDecode jit{};
+    std::string jit_note;
+    uint64_t jit_launches = 0, generic_launches = 0;
     // K4: dense enrichment marginals (valid for the current rows while marg_valid)
     MargPlan marg{};
     bool marg_dense = false, marg_valid = false;
@@ -522,48 +527,23 @@ void bc_destroy(bc_ctx* ctx) {
     delete ctx;
 }
 
-static void plan_marginals(bc_ctx* ctx);
+// Host copies of the reference-set accelerators, built with the run constants and uploaded by bc_create
+struct HostRefs {
+    std::vector<uint4> refs;
+    std::vector<unsigned long long> hkeys;
+    std::vector<uint32_t> hidx;
+    std::vector<unsigned long long> half;
+    std::vector<DevDeep> deep;
+    std::vector<uint32_t> csr;
+    std::vector<uint4> bref;
+    size_t table_u16 = 0;
+};
 
-int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx** out) {
-    if (!cfg || !out) return fail(nullptr, BC_EINVAL, "cfg / out is NULL");
-    *out = nullptr;
-    if (cfg->abi_version != BC_ABI_VERSION) return fail(nullptr, BC_EINVAL, "abi_version %u != %u", cfg->abi_version, BC_ABI_VERSION);
+// bc_config -> the run constants (ctx->cfg: what the kernels read; also what bc_jit.cu specialises the decode kernel on),
+// the key layout and the host side of the look-up structures.  No CUDA call in here.
+static int build_run_constants(const bc_config* cfg, bc_ctx* ctx, HostRefs& H) {
+#define FAILC(code, ...) return fail(nullptr, code, __VA_ARGS__)
     const uint32_t L = cfg->template_len;
-    if (L == 0 || L > BC_MAX_TEMPLATE) return fail(nullptr, BC_EUNSUPPORTED, "template length %u outside 1..%d", L, BC_MAX_TEMPLATE);
-    if (cfg->max_read_len < L || cfg->max_read_len > BC_MAX_READ_LEN)
-        return fail(nullptr, BC_EUNSUPPORTED, "max_read_len %u outside %u..%d", cfg->max_read_len, L, BC_MAX_READ_LEN);
-    if (cfg->n_slots > BC_MAX_SLOTS) return fail(nullptr, BC_EUNSUPPORTED, "more than %d barcodes", BC_MAX_SLOTS);
-    if (cfg->region_len > L) return fail(nullptr, BC_EINVAL, "region_codes longer than the template");
-    if (!cfg->template_chars || (cfg->region_len && !cfg->region_codes)) return fail(nullptr, BC_EINVAL, "template / region pointers");
-
-    int n_dev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&n_dev);
-    if (ce != cudaSuccess || n_dev == 0)
-        return fail(nullptr, BC_ECUDA, "no usable CUDA device (%s); this library has no CPU path", cudaGetErrorString(ce));
-    if (device < 0 || device >= n_dev) return fail(nullptr, BC_EINVAL, "device %d of %d", device, n_dev);
-
-    bc_ctx* ctx = new bc_ctx();
-    ctx->device = device;
-#define CKC(call)                                                                                              \
-    do {                                                                                                       \
-        cudaError_t e_ = (call);                                                                               \
-        if (e_ != cudaSuccess) {                                                                               \
-            int rc_ = fail(nullptr, BC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            bc_destroy(ctx);                                                                                   \
-            return rc_;                                                                                        \
-        }                                                                                                      \
-    } while (0)
-#define FAILC(code, ...)                              \
-    do {                                              \
-        int rc_ = fail(nullptr, code, __VA_ARGS__);   \
-        bc_destroy(ctx);                              \
-        return rc_;                                   \
-    } while (0)
-
-    CKC(cudaSetDevice(device));
-    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-
     DevCfg& d = ctx->cfg;
     d.L = L;
     d.TW = (L + 31) / 32;
@@ -751,14 +731,14 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     d.wide = shift > 63;
 
     // ---- reference sets -> {lo,hi,nm,len} words, direct tables, exact-match hashes
-    std::vector<uint4> refs;
-    std::vector<unsigned long long> hkeys;
-    std::vector<uint32_t> hidx;
-    std::vector<unsigned long long> half;
-    std::vector<DevDeep> deep;
-    std::vector<uint32_t> csr;
-    std::vector<uint4> bref;
-    size_t table_u16 = 0;
+    std::vector<uint4>& refs = H.refs;
+    std::vector<unsigned long long>& hkeys = H.hkeys;
+    std::vector<uint32_t>& hidx = H.hidx;
+    std::vector<unsigned long long>& half = H.half;
+    std::vector<DevDeep>& deep = H.deep;
+    std::vector<uint32_t>& csr = H.csr;
+    std::vector<uint4>& bref = H.bref;
+    size_t& table_u16 = H.table_u16;
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         const bc_slot& S = cfg->slots[s];
         DevSlot& D = d.slots[s];
@@ -880,6 +860,69 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
             D.mode = MODE_SCAN;
         }
     }
+    return BC_OK;
+#undef FAILC
+}
+
+static void plan_marginals(bc_ctx* ctx);
+
+int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, BC_EINVAL, "cfg / out is NULL");
+    *out = nullptr;
+    if (cfg->abi_version != BC_ABI_VERSION) return fail(nullptr, BC_EINVAL, "abi_version %u != %u", cfg->abi_version, BC_ABI_VERSION);
+    const uint32_t L = cfg->template_len;
+    if (L == 0 || L > BC_MAX_TEMPLATE) return fail(nullptr, BC_EUNSUPPORTED, "template length %u outside 1..%d", L, BC_MAX_TEMPLATE);
+    if (cfg->max_read_len < L || cfg->max_read_len > BC_MAX_READ_LEN)
+        return fail(nullptr, BC_EUNSUPPORTED, "max_read_len %u outside %u..%d", cfg->max_read_len, L, BC_MAX_READ_LEN);
+    if (cfg->n_slots > BC_MAX_SLOTS) return fail(nullptr, BC_EUNSUPPORTED, "more than %d barcodes", BC_MAX_SLOTS);
+    if (cfg->region_len > L) return fail(nullptr, BC_EINVAL, "region_codes longer than the template");
+    if (!cfg->template_chars || (cfg->region_len && !cfg->region_codes)) return fail(nullptr, BC_EINVAL, "template / region pointers");
+
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0)
+        return fail(nullptr, BC_ECUDA, "no usable CUDA device (%s); this library has no CPU path", cudaGetErrorString(ce));
+    if (device < 0 || device >= n_dev) return fail(nullptr, BC_EINVAL, "device %d of %d", device, n_dev);
+
+    bc_ctx* ctx = new bc_ctx();
+    ctx->device = device;
+#define CKC(call)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess) {                                                                               \
+            int rc_ = fail(nullptr, BC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            bc_destroy(ctx);                                                                                   \
+            return rc_;                                                                                        \
+        }                                                                                                      \
+    } while (0)
+#define FAILC(code, ...)                              \
+    do {                                              \
+        int rc_ = fail(nullptr, code, __VA_ARGS__);   \
+        bc_destroy(ctx);                              \
+        return rc_;                                   \
+    } while (0)
+
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+
+    HostRefs H;
+    {
+        const int rc_ = build_run_constants(cfg, ctx, H);
+        if (rc_ != BC_OK) {
+            bc_destroy(ctx);
+            return rc_;
+        }
+    }
+    DevCfg& d = ctx->cfg;
+    std::vector<uint4>& refs = H.refs;
+    std::vector<unsigned long long>& hkeys = H.hkeys;
+    std::vector<uint32_t>& hidx = H.hidx;
+    std::vector<unsigned long long>& half = H.half;
+    std::vector<DevDeep>& deep = H.deep;
+    std::vector<uint32_t>& csr = H.csr;
+    std::vector<uint4>& bref = H.bref;
+    const size_t table_u16 = H.table_u16;
     if (!refs.empty()) {
         CKC(cudaMalloc(&ctx->d_refs, refs.size() * sizeof(uint4)));
         CKC(cudaMemcpyAsync(ctx->d_refs, refs.data(), refs.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
@@ -962,11 +1005,43 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         return rc;
     }
     plan_marginals(ctx);
+    // Specialise the decode kernel for this run when the job is large enough to repay a second or two of compilation
+    // (or when asked to): same device code, run constants folded in.
+    if (!(cfg->flags & BC_CFG_NO_SPECIALIZE) && ((cfg->flags & BC_CFG_SPECIALIZE) || expected_reads >= (1ull << 22))) {
+        ctx->jit = jit_decode(d, ctx->W, ctx->plane_stride, ctx->qual_stride, &ctx->jit_note);
+        if (!ctx->jit.kernel && (cfg->flags & BC_CFG_SPECIALIZE)) FAILC(BC_ECUDA, "BC_CFG_SPECIALIZE: %s", ctx->jit_note.c_str());
+    } else {
+        ctx->jit_note = "not requested (small job)";
+    }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return BC_OK;
 #undef CKC
 #undef FAILC
+}
+
+const char* bc_specialization_note(const bc_ctx* ctx) { return ctx ? (ctx->jit.kernel ? "specialised" : ctx->jit_note.c_str()) : ""; }
+
+int bc_jit_check(const bc_config* cfg, char* log, int loglen) {
+    if (!cfg || !log || loglen <= 0) return BC_EINVAL;
+    log[0] = 0;
+    if (cfg->abi_version != BC_ABI_VERSION || cfg->template_len == 0 || cfg->template_len > BC_MAX_TEMPLATE || cfg->n_slots > BC_MAX_SLOTS ||
+        cfg->max_read_len < cfg->template_len || cfg->max_read_len > BC_MAX_READ_LEN || !cfg->template_chars)
+        return BC_EINVAL;
+    bc_ctx* ctx = new bc_ctx();
+    HostRefs H;
+    int rc = build_run_constants(cfg, ctx, H);
+    std::string msg;
+    size_t bytes = 0;
+    if (rc == BC_OK) {
+        bytes = jit_compile_check(ctx->cfg, bc_plane_words(cfg->max_read_len), bc_plane_stride(cfg->max_read_len), bc_qual_stride(cfg->max_read_len), &msg);
+        if (bytes == 0) rc = BC_ECUDA;
+    } else {
+        msg = g_create_error;
+    }
+    snprintf(log, (size_t)loglen, "%s", rc == BC_OK ? ("cubin bytes: " + std::to_string(bytes)).c_str() : msg.c_str());
+    delete ctx;
+    return rc;
 }
 
 int bc_set_stream(bc_ctx* ctx, void* cuda_stream) {
@@ -1012,8 +1087,17 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
     {
         ProfScope p(ctx, BC_K_DECODE);
-        CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, rec_out(ctx), deferred, flags,
-                              ctx->stream));
+        const bool fits = ctx->jit.kernel && view.W == ctx->jit.W && view.plane_stride == ctx->jit.plane_stride &&
+                          (!ctx->quality_on || view.qual_stride == ctx->jit.qual_stride) && decode_smem_bytes(view) <= 48 * 1024;
+        if (fits) {
+            ctx->jit_launches++;
+            CK(ctx, launch_decode_jit(ctx->jit.kernel, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, rec_out(ctx),
+                                      deferred, flags, ctx->stream));
+        } else {
+            ctx->generic_launches++;
+            CK(ctx, launch_decode(ctx->cfg, view, ctx->aux, ctx->tables, counters ? ctx->d_stripes : nullptr, out, rec_out(ctx), deferred,
+                                  flags, ctx->stream));
+        }
     }
     if (counters) {
         ProfScope p(ctx, BC_K_OTHER);
@@ -2129,6 +2213,8 @@ int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
     ctx->prof.deferred_count = ctx->deferred ? 1u : 0u;
     ctx->prof.flushed_global = ctx->flushed_global ? 1u : 0u;
     ctx->prof.flush_stages = ctx->flush_stages;
+    ctx->prof.specialized_launches = ctx->jit_launches;
+    ctx->prof.generic_launches = ctx->generic_launches;
     *out = ctx->prof;
     return BC_OK;
 }
@@ -2139,6 +2225,7 @@ int bc_reset_profile(bc_ctx* ctx) {
     if (rc != BC_OK) return rc;
     drain_profile(ctx);
     ctx->prof = bc_profile{};
+    ctx->jit_launches = ctx->generic_launches = 0;
     return BC_OK;
 }
 

@@ -4,15 +4,6 @@
 
 namespace bc {
 
-struct DecodeOut {  // all optional (test hooks / decode_only)
-    uint8_t* status;
-    int16_t* offset;
-    uint8_t* repaired;
-    int32_t* slot_index;
-    unsigned long long* key_lo;
-    unsigned long long* key_hi;
-};
-
 constexpr int kMaxRanks = 8;  // GPUs of one box (NVLink / NVSwitch peers)
 
 // multi-GPU exchange (launch_owner_scatter): the record buffers of the owner ranks, local or mapped over NVLink
@@ -21,40 +12,12 @@ struct PeerOut {
     unsigned long long* hi[kMaxRanks];  // nullptr for keys of at most 63 bits
 };
 
-struct DevAux {  // reference sets and their accelerators
-    const uint4* refs;                    // {lo, hi, nm, len} per reference barcode
-    const uint32_t* tables;               // 4^len direct lookups (MODE_TABLE): idx | dist << 16 | tie << 24
-    const unsigned long long* hash_keys;  // exact-match hash (MODE_HASH): lo | hi << 32
-    const uint32_t* hash_idx;
-    const unsigned long long* half;       // half index: {key32, id32} entries, kEmpty = free
-    const DevDeep* deep;                  // block index descriptors
-    const uint32_t* csr;                  // block index: bucket starts
-    const uint4* bref;                    // block index: references in bucket order, {lo, hi, id, 0}
-};
-
-struct Deferred {  // reads whose barcode step needs a search: {read index, offset | repaired << 16}
-    uint2* items;
-    uint32_t* count;
-};
-
-// Deferred counting (bc_partition.cu): instead of updating the tables read by read, a matched read's packed key goes
-// to slot (*cursor + read index) of a flat record buffer — kEmpty marks the reads that did not match — and the whole
-// job is de-duplicated and counted at flush time, partition by partition, in shared memory.
-struct RecOut {
-    unsigned long long* lo;
-    unsigned long long* hi;                // nullptr when the full key (random barcode included) fits 63 bits
-    const unsigned long long* cursor;      // records appended before this batch (bumped by launch_bump after the batch)
-};
-
-enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_LOCATE_ONLY = 8, F_APPEND = 16 };
-
-// k_decode adds its outcome counters to striped copies (kCounterStripes x kCounterStride u64: the BC_N_COUNTERS
-// outcomes, then new map / set entries); launch_fold_counters sums them into the BC_N_COUNTERS + 2 counters of the ctx.
-constexpr uint32_t kCounterStripes = 64, kCounterStride = 16;
 cudaError_t launch_fold_counters(unsigned long long* stripes, unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_decode(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                           unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
                           cudaStream_t stream);
+cudaError_t launch_decode_jit(const void* kernel, const BatchView& batch, const DevAux& aux, const Tables& tables, unsigned long long* counters,
+                              const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags, cudaStream_t stream);
 cudaError_t launch_resolve(const DevCfg& cfg, const BatchView& batch, const DevAux& aux, const Tables& tables,
                            unsigned long long* counters, const DecodeOut& out, const RecOut& rec, const Deferred& deferred, int flags,
                            cudaStream_t stream);

@@ -362,10 +362,11 @@ __device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t valu
 // MODE RED_DEDUPE      : in = records (key incl. random barcode), out = (record >> umi_bits, distinct records with that key)
 // MODE RED_COUNT       : in = (key, weight) items,                out = (key, sum of weights)
 // MODE RED_DEDUPE_KEYED: RED_DEDUPE for partitions that hold whole keys (partitioned by the record WITHOUT its random
-//   barcode) and fit the key store — one pass instead of two.  A record's home slot is the hash of its KEY, so all records
-//   of a key walk the same probe sequence; slots of a sequence fill in order and never empty, hence the first entry
-//   of that key a record meets on its way (or the record itself when it meets none) is the same for all of them: that
-//   entry carries the key's count of distinct records.
+//   barcode) and fit the key store — one pass instead of two.  Two small tables of 16-bit key-store indices: a record is
+//   looked up by its full value in the first (a repeat stops there: info.rs:780-791, only the first insert of a pair
+//   counts); a record seen for the first time then finds or claims its KEY's entry in the second, and that entry's
+//   counter takes the +1.  Both are ordinary open-addressing sets with independent hashes, so a key with hundreds of
+//   random barcodes costs what any other records cost (chaining a key's records behind one home slot was quadratic).
 template <bool WIDE, int MODE>
 __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
@@ -380,7 +381,10 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     t.khi = WIDE ? t.klo + kKeyCap : nullptr;
     t.table = reinterpret_cast<uint32_t*>(t.klo + (WIDE ? 2 : 1) * kKeyCap);
     t.kcnt = t.table + kTableSlots;
-    uint32_t* kw = MODE == RED_DEDUPE_KEYED ? t.kcnt : t.kcnt + kKeyCap;  // RED_DEDUPE*: distinct records per key
+    // RED_DEDUPE_KEYED lays the space after the key store out as [records u16 x slots][keys u16 x slots][kw u32 x cap]
+    unsigned short* t_rec = reinterpret_cast<unsigned short*>(t.table);
+    unsigned short* t_key = t_rec + kTableSlots;
+    uint32_t* kw = MODE == RED_DEDUPE_KEYED ? reinterpret_cast<uint32_t*>(t_key + kTableSlots) : t.kcnt + kKeyCap;  // distinct records per key
     t.n_perm = &s_nperm;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -420,53 +424,58 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
         }
         __syncthreads();
         // One loop over probe STEPS, not over items: a lane that settles an item moves on to its next one at once, so a
-        // warp runs for the longest lane total (about items x 1.5 steps) instead of the sum of per-item maxima.
+        // warp runs for the longest lane total (about items x 2.5 steps) instead of the sum of per-item maxima.
         uint32_t uniq = 0;
         {
-            uint32_t j = tid, s = 0, rep = kEmpty32;
+            constexpr uint32_t kNone = 0xFFFFu;
+            uint32_t j = tid, s = 0;
             unsigned long long clo = 0, chi = 0;
             Key K{0, 0};
-            bool fresh = true;
+            int phase = -1;  // -1: fetch item j; 0: looking the record up; 1: looking its key up
             while (j < n) {
-                if (fresh) {
+                if (phase < 0) {
                     clo = t.klo[j];
                     chi = WIDE ? t.khi[j] : 0ULL;
                     if (!item_valid(clo, chi, WIDE)) {
                         j += kRedThreads;
                         continue;
                     }
-                    K = drop_umi<WIDE>(clo, chi, umi_bits);
-                    s = slot_hash<WIDE>(K.lo, K.hi) & (kTableSlots - 1);
-                    rep = kEmpty32;  // first entry of this key met so far
-                    fresh = false;
+                    s = slot_hash<WIDE>(clo, chi) & (kTableSlots - 1);
+                    phase = 0;
                 }
-                uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
-                if (v == kEmpty32) {
-                    const uint32_t old = atomicCAS(&t.table[s], kEmpty32, j);
-                    if (old == kEmpty32) {  // a record not seen before
-                        atomicAdd(&kw[rep == kEmpty32 ? j : rep], 1u);
-                        uniq++;
-                        j += kRedThreads;
-                        fresh = true;
-                        continue;
-                    }
+                unsigned short* tab = phase == 0 ? t_rec : t_key;
+                uint32_t v = *reinterpret_cast<volatile unsigned short*>(&tab[s]);
+                bool claimed = false;
+                if (v == kNone) {
+                    const unsigned short old = atomicCAS(&tab[s], (unsigned short)kNone, (unsigned short)j);
+                    claimed = old == kNone;
                     v = old;
                 }
-                const unsigned long long vlo = t.klo[v], vhi = WIDE ? t.khi[v] : 0ULL;
-                if (vlo == clo && (!WIDE || vhi == chi)) {  // a repeat (info.rs:780-791: only the first insert counts)
-                    j += kRedThreads;
-                    fresh = true;
-                    continue;
-                }
-                if (rep == kEmpty32) {
-                    bool same;
-                    if (!WIDE) {
-                        same = ((vlo ^ clo) >> umi_bits) == 0ULL;
-                    } else {
-                        const Key o = drop_umi<true>(vlo, vhi, umi_bits);
+                if (phase == 0) {
+                    if (claimed) {  // a record not seen before: on to its key
+                        uniq++;
+                        K = drop_umi<WIDE>(clo, chi, umi_bits);
+                        s = (slot_hash<WIDE>(K.lo, K.hi) * 0x9E3779B1u >> 7) & (kTableSlots - 1);
+                        phase = 1;
+                        continue;
+                    }
+                    if (t.klo[v] == clo && (!WIDE || t.khi[v] == chi)) {  // a repeat
+                        j += kRedThreads;
+                        phase = -1;
+                        continue;
+                    }
+                } else {
+                    bool same = claimed;
+                    if (!claimed) {
+                        const Key o = drop_umi<WIDE>(t.klo[v], WIDE ? t.khi[v] : 0ULL, umi_bits);
                         same = o.lo == K.lo && o.hi == K.hi;
                     }
-                    if (same) rep = v;
+                    if (same) {  // entry v (this record itself when it claimed the slot) stands for the key
+                        atomicAdd(&kw[claimed ? j : v], 1u);
+                        j += kRedThreads;
+                        phase = -1;
+                        continue;
+                    }
                 }
                 s = (s + 1) & (kTableSlots - 1);
             }
@@ -636,7 +645,8 @@ template <bool WIDE, int MODE>
 cudaError_t launch_reduce_t(const ItemView& in, const uint32_t* starts, unsigned long long n_items, unsigned long long n_ranges,
                             uint32_t chunk, uint32_t umi_bits, const ItemView& out, unsigned long long out_cap, FlushStats* stats,
                             uint32_t skip_over, cudaStream_t stream) {
-    const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);  // keyed: no kcnt
+    const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);
+    // (RED_DEDUPE_KEYED: two tables of u16 in the space of the one u32 table, then the per-key counters)
     cudaError_t e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;

@@ -356,6 +356,8 @@ struct bch_run {
     bc_config cfg{};
     std::string description;
     IngestBuffers ingest;
+    bch_progress_fn progress = nullptr;  // called with the running number of records after every batch
+    void* progress_user = nullptr;
     int multi_mode = 0;  // after bch_count_fastq_multi: 1 = rows partitioned over the contexts, 2 = all rows on the first
 };
 
@@ -1058,6 +1060,7 @@ struct Ingest {
             n_batches++;
             L.cur ^= 1;
             L.in_flight++;
+            if (run->progress) run->progress(total, run->progress_user);
         }
     }
 
@@ -1239,6 +1242,11 @@ bch_run* bch_open(const bch_args* args, char* err, int errlen) {
 }
 
 void bch_close(bch_run* run) { delete run; }
+void bch_set_progress(bch_run* run, bch_progress_fn fn, void* user) {
+    if (!run) return;
+    run->progress = fn;
+    run->progress_user = user;
+}
 const bc_config* bch_config(const bch_run* run) { return run ? &run->cfg : nullptr; }
 const char* bch_describe(const bch_run* run) { return run ? run->description.c_str() : ""; }
 uint32_t bch_barcode_num(const bch_run* run) { return run ? (uint32_t)run->counted.size() : 0; }

@@ -7,6 +7,9 @@
 #include <ctime>
 #include <string>
 #include <thread>
+#include <vector>
+
+#include <cuda_runtime_api.h>
 
 #include <zlib.h>
 
@@ -33,7 +36,7 @@ static void usage() {
             "    -p, --prefix <prefix>                    File prefix name [default: today's date]\n"
             "    -s, --sample-barcodes <sample_file>      Sample barcodes file\n"
             "    -t, --threads <threads>                  Number of host threads (FASTQ parse + pack)\n"
-            "        --device <n>                         CUDA device [default: 0]\n"
+            "        --devices <list>                     GPUs to use: 0 | 0,1 | 0-7 | all (reads are sharded over them) [default: 0]\n"
             "        --max-read-length <n>                Longest read in the FASTQ [default: from the first reads of the file]\n"
             "        --batch-reads <n>                    Reads per GPU batch [default: 1048576]\n");
 }
@@ -79,10 +82,70 @@ static unsigned probe_read_len(const std::string& path) {
     return longest;
 }
 
+// The reference's command line is clap's (arguments.rs:27-124): long options take "--name value" or "--name=value", short
+// ones "-t 8", "-t8" or "-t=8", and short flags bundle ("-me", "-met8").  argv -> one token per option / value.
+static std::vector<std::string> clap_tokens(int argc, char** argv) {
+    static const std::string short_with_value = "fqsctop";
+    std::vector<std::string> out;
+    bool only_values = false;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        if (only_values || a.size() < 2 || a[0] != '-') {
+            out.push_back(a);
+        } else if (a == "--") {
+            only_values = true;
+        } else if (a[1] == '-') {
+            const size_t eq = a.find('=');
+            if (eq == std::string::npos) {
+                out.push_back(a);
+            } else {
+                out.push_back(a.substr(0, eq));
+                out.push_back(a.substr(eq + 1));
+            }
+        } else {
+            for (size_t k = 1; k < a.size(); k++) {
+                out.push_back(std::string("-") + a[k]);
+                if (short_with_value.find(a[k]) != std::string::npos) {
+                    if (k + 1 < a.size()) out.push_back(a.substr(k + 1 + (a[k + 1] == '=' ? 1 : 0)));
+                    break;
+                }
+            }
+        }
+    }
+    return out;
+}
+
+// "0", "0,2,3", "0-3", "all"
+static bool parse_devices(const std::string& spec, std::vector<int>& out) {
+    out.clear();
+    if (spec == "all") {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) return false;
+        for (int d = 0; d < n; d++) out.push_back(d);
+        return true;
+    }
+    size_t i = 0;
+    while (i < spec.size()) {
+        size_t j = spec.find(',', i);
+        if (j == std::string::npos) j = spec.size();
+        const std::string part = spec.substr(i, j - i);
+        const size_t dash = part.find('-');
+        char* end = nullptr;
+        const long lo = strtol(part.c_str(), &end, 10);
+        long hi = lo;
+        if (dash != std::string::npos) hi = strtol(part.c_str() + dash + 1, &end, 10);
+        if (part.empty() || lo < 0 || hi < lo || hi > 63) return false;
+        for (long d = lo; d <= hi; d++) out.push_back((int)d);
+        i = j + 1;
+    }
+    return !out.empty() && out.size() <= 8;
+}
+
 int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     std::string fastq, format, samples, counted, outdir = "./", prefix;
-    int max_b = -1, max_s = -1, max_c = -1, device = 0;
+    int max_b = -1, max_s = -1, max_c = -1;
+    std::vector<int> devices{0};
     float min_quality = 0.f;
     bool merge = false, enrich = false;
     unsigned threads = std::thread::hardware_concurrency();
@@ -93,14 +156,15 @@ int main(int argc, char** argv) {
         strftime(buf, sizeof buf, "%Y-%m-%d", localtime(&now));
         prefix = buf;
     }
-    for (int i = 1; i < argc; i++) {
-        const std::string a = argv[i];
+    const std::vector<std::string> tok = clap_tokens(argc, argv);
+    for (size_t i = 0; i < tok.size(); i++) {
+        const std::string& a = tok[i];
         auto val = [&]() -> const char* {
-            if (i + 1 >= argc) {
+            if (i + 1 >= tok.size()) {
                 fprintf(stderr, "error: The argument '%s' requires a value but none was supplied\n", a.c_str());
                 exit(2);
             }
-            return argv[++i];
+            return tok[++i].c_str();
         };
         auto num = [&](const char* what) -> int {
             const char* v = val();
@@ -132,8 +196,13 @@ int main(int argc, char** argv) {
                 fprintf(stderr, "Error: Unable to convert min score to a float\n");
                 return 1;
             }
-        } else if (a == "--device") device = num("device");
-        else if (a == "--max-read-length") max_read_len = (unsigned)num("max read length");
+        } else if (a == "--device" || a == "--devices") {
+            const char* v = val();
+            if (!parse_devices(v, devices)) {
+                fprintf(stderr, "Error: --devices wants a list like 0,1 or 0-7 (at most 8 GPUs of one box), or 'all'\n");
+                return 1;
+            }
+        } else if (a == "--max-read-length") max_read_len = (unsigned)num("max read length");
         else if (a == "--batch-reads") batch_reads = (unsigned)strtoul(val(), nullptr, 10);
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "-V" || a == "--version") { printf("NGS-Barcode-Count 0.11.1-b200\n"); return 0; }
@@ -156,9 +225,9 @@ int main(int argc, char** argv) {
     args.max_errors_sample = max_s;
     args.max_errors_constant = max_c;
     args.min_quality = min_quality;
-    if (max_read_len == 0) {  // from the data: the longest of the first reads, with head-room for a few untrimmed ones
-        const unsigned seen = probe_read_len(fastq);
-        if (seen) max_read_len = seen + seen / 4 + 8;
+    if (max_read_len == 0) {  // the default batch geometry: the longest of the first reads, with some head-room; a batch that
+        const unsigned seen = probe_read_len(fastq);  // meets a longer read is packed wider, nothing aborts
+        if (seen) max_read_len = std::min(1024u, seen + seen / 8 + 8);
     }
     args.max_read_len = max_read_len;
     bch_run* run = bch_open(&args, err, sizeof err);
@@ -171,50 +240,82 @@ int main(int argc, char** argv) {
         fprintf(stderr, "Fewer than 2 counted barcodes.  Too few for barcode enrichment.  Argument flag is ignored\n");
         enrich = false;
     }
-    bc_ctx* ctx = nullptr;
-    if (bc_create(bch_config(run), device, 0, &ctx) != BC_OK) {
-        fprintf(stderr, "Error: %s\n", bc_last_error(nullptr));
+    std::vector<bc_ctx*> ctxs;
+    auto cleanup = [&]() {
+        for (bc_ctx* c : ctxs) bc_destroy(c);
         bch_close(run);
-        return 1;
+    };
+    for (int d : devices) {
+        bc_ctx* c = nullptr;
+        if (bc_create(bch_config(run), d, 0, &c) != BC_OK) {
+            fprintf(stderr, "Error: %s\n", bc_last_error(nullptr));
+            cleanup();
+            return 1;
+        }
+        ctxs.push_back(c);
     }
+    const bool gz = fastq.size() >= 8 && fastq.compare(fastq.size() - 8, 8, "fastq.gz") == 0;
+    if (gz)  // input.rs:60-61
+        printf("If this program stops reading before the expected number of sequencing reads, unzip the gzipped fastq and rerun.\n\n");
+    // input.rs:54-57, 151-158: the running total, rewritten in place
+    bch_set_progress(run, [](uint64_t n, void*) {
+        printf("Total sequences:             %s\r", thousands(n).c_str());
+        fflush(stdout);
+    }, nullptr);
     uint64_t total = 0;
-    if (bch_count_fastq(run, ctx, fastq.c_str(), threads, batch_reads, &total, err, sizeof err) != BC_OK) {
+    if (bch_count_fastq_multi(run, ctxs.data(), (int)ctxs.size(), fastq.c_str(), threads, batch_reads, &total, err, sizeof err) != BC_OK) {
         fprintf(stderr, "Error: %s\n", err);
-        bc_destroy(ctx);
-        bch_close(run);
+        cleanup();
         return 1;
     }
+    // Q21: on the gzip path the reference's read loop feeds one more (empty) line to its line counter at the end of the
+    // stream (input.rs:69-73, 129-133), so its total is one above the number of records
+    const uint64_t shown_total = total + (gz && total ? 1 : 0);
     uint64_t c[BC_N_COUNTERS] = {0};
-    bc_get_counters(ctx, c);
-    printf("Total sequences:             %s\n", thousands(total).c_str());
+    if (bch_counters_multi(ctxs.data(), (int)ctxs.size(), c) != BC_OK) {
+        fprintf(stderr, "Error: %s\n", bc_last_error(ctxs[0]));
+        cleanup();
+        return 1;
+    }
+    printf("Total sequences:             %s\r\n", thousands(shown_total).c_str());
     printf("Correctly matched sequences: %s\nConstant region mismatches:  %s\nSample barcode mismatches:   %s\n"
-           "Counted barcode mismatches:  %s\nDuplicates:                  %s\nLow quality barcodes:        %s\n",
+           "Counted barcode mismatches:  %s\nDuplicates:                  %s\nLow quality barcodes:        %s\n\n",
            thousands(c[BC_CNT_MATCHED]).c_str(), thousands(c[BC_CNT_CONSTANT]).c_str(), thousands(c[BC_CNT_SAMPLE]).c_str(),
            thousands(c[BC_CNT_COUNTED]).c_str(), thousands(c[BC_CNT_DUPLICATES]).c_str(), thousands(c[BC_CNT_LOW_QUALITY]).c_str());
     if (c[BC_CNT_UNSUPPORTED])
-        fprintf(stderr, "WARNING: %s reads hold characters outside A/C/G/T/N and were not decoded (the reference treats such "
-                        "characters as plain mismatching symbols)\n", thousands(c[BC_CNT_UNSUPPORTED]).c_str());
+        fprintf(stderr, "WARNING: %s reads hold characters outside A/C/G/T/N (or are longer than %d bases) and were not decoded (the "
+                        "reference treats such characters as plain mismatching symbols)\n", thousands(c[BC_CNT_UNSUPPORTED]).c_str(),
+                BC_MAX_READ_LEN);
     const auto t1 = std::chrono::steady_clock::now();
-    printf("\nCompute time: %s\n\n-WRITING COUNTS-\n", hms(std::chrono::duration<double>(t1 - t0).count()).c_str());
+    printf("Compute time: %s\n\n-WRITING COUNTS-\n", hms(std::chrono::duration<double>(t1 - t0).count()).c_str());
     static char names[1 << 20];
-    const int nfiles = bch_write_counts(run, ctx, outdir.c_str(), prefix.c_str(), merge, enrich, names, sizeof names, err, sizeof err);
+    const int nfiles = bch_write_counts_multi(run, ctxs.data(), (int)ctxs.size(), outdir.c_str(), prefix.c_str(), merge, enrich, names,
+                                              sizeof names, err, sizeof err);
     if (nfiles < 0) {
         fprintf(stderr, "Error: %s\n", err);
-        bc_destroy(ctx);
-        bch_close(run);
+        cleanup();
         return 1;
     }
-    // file names as they were written, then the run record the reference appends to {prefix}_barcode_stats.txt
-    // (output.rs:488-576): same sections; the times are this run's
-    std::string listing, stats_files;
+    // File names and "Barcodes counted" as the reference prints them while writing (output.rs:143-165, 355-359, 450-475),
+    // then the run record it appends to {prefix}_barcode_stats.txt (output.rs:488-576): same sections; the times are this
+    // run's.  (The reference pairs its file list with a count list in which each family's merged count comes first,
+    // output.rs:169, 476-479, so with --merge-output its record attributes counts to the wrong files; here every file is
+    // listed with its own count.)
+    std::vector<std::string> fnames;
+    std::vector<unsigned long long> frows;
     for (char* line = strtok(names, "\n"); line; line = strtok(nullptr, "\n")) {
         char* tab = strchr(line, '\t');
-        const std::string fname = tab ? std::string(line, tab) : std::string(line);
-        const unsigned long long rows = tab ? strtoull(tab + 1, nullptr, 10) : 0;
-        listing += fname + "\n";
-        stats_files += "File & barcodes counted: " + fname + "\t" + thousands(rows) + "\n";
+        fnames.push_back(tab ? std::string(line, tab) : std::string(line));
+        frows.push_back(tab ? strtoull(tab + 1, nullptr, 10) : 0);
     }
-    printf("%s", listing.c_str());
+    std::string stats_files;
+    for (size_t i = 0; i < fnames.size(); i++) {
+        const bool merged_file = fnames[i].find("_counts.all") != std::string::npos;
+        printf("%s\n", fnames[i].c_str());
+        if (merged_file) printf("Barcodes counted: %s\n", thousands(frows[i]).c_str());
+        else printf("Barcodes counted: %s\r\n", thousands(frows[i]).c_str());
+        stats_files += "File & barcodes counted: " + fnames[i] + "\t" + thousands(frows[i]) + "\n";
+    }
     {
         std::string dir = outdir;
         if (!dir.empty() && dir.back() != '/') dir.push_back('/');
@@ -233,17 +334,22 @@ int main(int argc, char** argv) {
             fprintf(sf, "-RESULTS-\nTotal sequences:             %s\nCorrectly matched sequences: %s\nConstant region mismatches:  %s\n"
                         "Sample barcode mismatches:   %s\nCounted barcode mismatches:  %s\nDuplicates:                  %s\n"
                         "Low quality barcodes:        %s\n\n",
-                    thousands(total).c_str(), thousands(c[BC_CNT_MATCHED]).c_str(), thousands(c[BC_CNT_CONSTANT]).c_str(),
+                    thousands(shown_total).c_str(), thousands(c[BC_CNT_MATCHED]).c_str(), thousands(c[BC_CNT_CONSTANT]).c_str(),
                     thousands(c[BC_CNT_SAMPLE]).c_str(), thousands(c[BC_CNT_COUNTED]).c_str(), thousands(c[BC_CNT_DUPLICATES]).c_str(),
                     thousands(c[BC_CNT_LOW_QUALITY]).c_str());
             fprintf(sf, "-OUTPUT FILES-\n%s\n", stats_files.c_str());
+            if (gz && shown_total < 1000000) {  // output.rs:566-571
+                const char* warning = "WARNING: The program may have stopped early with the gzipped file.  Unzip the fastq.gz and rerun the "
+                                      "algorithm on the unzipped fastq file if the number of reads is expected to be above 1,000,000 ";
+                printf("\n%s\n\n", warning);
+                fprintf(sf, "\n%s\n", warning);
+            }
             fprintf(sf, "--------------------------------------------------------------------------------------------------\n\n\n");
             fclose(sf);
         }
     }
     const auto t2 = std::chrono::steady_clock::now();
     printf("\nTotal time: %s\n", hms(std::chrono::duration<double>(t2 - t0).count()).c_str());
-    bc_destroy(ctx);
-    bch_close(run);
+    cleanup();
     return 0;
 }

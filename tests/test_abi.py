@@ -143,3 +143,14 @@ def test_no_cpu_fallback_without_gpu():
     out = subprocess.run([bc.CLI_PATH, "-f", os.path.join(ex, "reads.fastq"), "-q", os.path.join(ex, "scheme.txt")],
                          capture_output=True, text=True)
     assert out.returncode != 0 and "CUDA" in out.stderr
+
+
+@pytest.mark.parametrize("case", ["del3_umi", "crispr", "lineage_raw", "format_n", "refs_mixed_n", "long_reads"])
+def test_specialized_decode_kernel_compiles_for_sm_100a(case):
+    """bc_jit.cu hands NVRTC the library's own device code (csrc/bc_decode.cuh, embedded at build time) with the run
+    constants as a constant object.  No GPU is needed to compile it: the cubin must come out for every kind of scheme."""
+    from helpers import load_golden
+    exp, p = load_golden(case)
+    run = bc.Run(p["fmt"], p["samples"], p["counted"], min_quality=exp["flags"]["min_quality"])
+    ok, log = run.jit_check()
+    assert ok and log.startswith("cubin bytes: ") and int(log.split(": ")[1]) > 10_000, log

@@ -84,6 +84,39 @@ def test_golden_per_read_and_csv(case, tmp_path):
 
 
 @pytest.mark.parametrize("case", golden_cases())
+def test_golden_specialized_kernel(case, tmp_path):
+    """The decode kernel compiled for the run by NVRTC (bc_jit.cu: the same device code with the run constants folded in,
+    what bc_create does on its own for jobs of 2^22 reads and more) against the golden per-read outcomes, counters and CSV
+    set — and the launches really went through it."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run, flags=bc.BC_CFG_SPECIALIZE)
+    assert ctr.profile()["specialization"] == "specialised"
+    reads = read_fastq(paths["fastq"])
+    batch = check_reads_against(run, ctr, reads, exp["outcomes"])
+    n = batch.n
+    for a, b in ((0, n // 2), (n // 2, n - 3), (n - 3, n)):
+        ctr.submit(batch.slice(a, b))
+    c = ctr.counters()
+    assert c.pop("unsupported") == 0
+    assert c == exp["counters"]
+    prof = ctr.profile()
+    assert prof["specialized_launches"] >= 5 and prof["generic_launches"] == 0, prof
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+    # a batch of another geometry (longer reads) falls back to the generic kernel of the same context
+    wide = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], max_barcode=fl["max_barcode"],
+                  max_sample=fl["max_sample"], max_constant=fl["max_constant"], max_read_len=run.max_read_len + 64)
+    ctr.reset()
+    ctr.reset_profile()
+    ctr.submit(wide.pack([r[0] for r in reads], [r[1] for r in reads]))
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"] and ctr.profile()["generic_launches"] == 1
+
+
+@pytest.mark.parametrize("case", golden_cases())
 def test_golden_fastq_ingest_small_batches(case, tmp_path):
     """bch_count_fastq (the read_fastq replacement) with batches far smaller than the file: pinned double
     buffering, staging reuse and table growth are all exercised."""
@@ -151,6 +184,119 @@ def test_cli_drop_in(case, gz, tmp_path):
     assert stats.count("File & barcodes counted: ") == len(exp["files"])
     for fn, lines in exp["files"].items():
         assert f"File & barcodes counted: {fn}\t{len(lines) - 1:,}" in stats
+
+
+@pytest.mark.parametrize("case", ["del3_umi", "crispr", "example", "sample_raw_two"])
+def test_cli_several_contexts_and_clap_syntax(case, tmp_path):
+    """`--devices` shards the reads over several contexts inside one process (here twice the same GPU, so that a
+    one-GPU box covers it): batches alternate between them and the result is merged by one record exchange (hashed keys)
+    or by adding the dense tables (crispr) — the CSV set must still be the reference's.  The command line is clap's:
+    `--name=value`, bundled short flags, attached short values (arguments.rs:27-124)."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    out = tmp_path / "out"
+    out.mkdir()
+    cmd = [bc.CLI_PATH, f"--fastq={paths['fastq']}", "-q", paths["fmt"], f"-o={out}", "-pgolden", "-t3", "--devices=0,0,0",
+           "--batch-reads=64", f"--min-quality={fl['min_quality']}"]
+    if paths["samples"]:
+        cmd += ["-s", paths["samples"]]
+    if paths["counted"]:
+        cmd += [f"--counted-barcodes={paths['counted']}"]
+    short = ("m" if fl["merge"] else "") + ("e" if fl["enrich"] else "")
+    if short:
+        cmd.append("-" + short)
+    for flag, key in (("--max-errors-counted-barcode", "max_barcode"), ("--max-errors-sample", "max_sample"),
+                      ("--max-errors-constant", "max_constant")):
+        if fl[key] is not None:
+            cmd += [f"{flag}={fl[key]}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert_same_csv_set(read_csv_dir(str(out), "golden"), exp["files"])
+    c = exp["counters"]
+    n_reads = len(exp["outcomes"])
+    assert f"Total sequences:             {n_reads:,}\r\n" in r.stdout  # input.rs:151-158: rewritten in place, then a newline
+    assert f"Correctly matched sequences: {c['matched']:,}" in r.stdout
+    assert f"Duplicates:                  {c['duplicates']:,}" in r.stdout
+    assert f"Low quality barcodes:        {c['low_quality']:,}" in r.stdout
+    for fn, lines in exp["files"].items():  # output.rs:143-165, 355-359: file name, then its number of barcode rows
+        end = "\n" if "_counts.all" in fn else "\r\n"
+        assert f"{fn}\nBarcodes counted: {len(lines) - 1:,}{end}" in r.stdout, fn
+
+
+def test_cli_gzip_total_has_the_reference_phantom_read(tmp_path):
+    """Q21: on the gzip path the reference's reader counts one more 'read' at the end of the stream (input.rs:69-73, 129-133)
+    and warns about short gzip files (output.rs:566-571); the counters and CSVs are those of the real reads."""
+    import gzip
+    exp, paths = load_golden("example")
+    fastq = str(tmp_path / "reads.fastq.gz")
+    with open(fastq, "wb") as f:
+        f.write(gzip.compress(open(paths["fastq"], "rb").read()))
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([bc.CLI_PATH, "-f", fastq, "-q", paths["fmt"], "-s", paths["samples"], "-c", paths["counted"], "-o", str(out),
+                        "-p", "golden", "-me"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("-FORMAT-")
+    assert "If this program stops reading before the expected number of sequencing reads" in r.stdout
+    assert f"Total sequences:             {len(exp['outcomes']) + 1:,}\r\n" in r.stdout
+    assert "WARNING: The program may have stopped early with the gzipped file." in r.stdout
+    assert_same_csv_set(read_csv_dir(str(out), "golden"), exp["files"])
+
+
+def test_reads_of_any_length_and_ragged_quality_lines(tmp_path):
+    """The reference has no read-length limit and zips a quality line of any length with the scheme (input.rs:115-148,
+    parse.rs:287-313, 338-343).  A FASTQ whose later reads are far longer than the first ones (the CLI sizes its batches
+    from the first reads), up to the build's 1024-base limit, with quality lines shorter and longer than their sequences:
+    same counters and CSV set as the oracle; nothing aborts; reads beyond 1024 bases are counted as unsupported."""
+    import mirror
+    exp, paths = load_golden("del3_umi")
+    rng = random.Random(77)
+    base = read_fastq(paths["fastq"])
+    reads = list(base[:150])
+    for k, (s, q) in enumerate(base[150:400]):
+        extra = rng.choice([0, 30, 200, 500, 1024 - len(s)])
+        pre = mirror.rand_seq(rng, rng.randint(0, extra))
+        s2 = pre + s + mirror.rand_seq(rng, extra - len(pre))
+        q2 = "".join(chr(33 + rng.randint(15, 40)) for _ in range(len(s2)))
+        r = rng.random()
+        if r < 0.25:
+            q2 = q2[:rng.randint(0, len(q2))]
+        elif r < 0.35:
+            q2 += "IIII"
+        reads.append((s2, q2))
+    too_long = [("ACGT" * 300, "I" * 1200), (base[0][0] + "A" * 1100, "I" * (len(base[0][0]) + 1100))]
+    fq = tmp_path / "ragged.fastq"
+    with open(fq, "w") as f:
+        for i, (s, q) in enumerate(reads + too_long):
+            f.write(f"@r{i}\n{s}\n+\n{q}\n")
+    o_dir, g_dir = tmp_path / "o", tmp_path / "g"
+    o_dir.mkdir()
+    g_dir.mkdir()
+    fl = exp["flags"]
+    orc = Oracle(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], merge=fl["merge"], enrich=fl["enrich"],
+                 outdir=str(o_dir), prefix="p")
+    for s, q in reads:
+        orc.process(s, q)
+    orc.write_files()
+    want = orc.counters()
+    assert want["low_quality"] > 0 and want["matched"] > 100
+    # the library's ingest with a run sized for the short reads only
+    run = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], max_read_len=len(base[0][0]))
+    ctr = bc.Counter(run)
+    assert ctr.count_fastq(str(fq), threads=3, batch_reads=64) == len(reads) + 2
+    got = ctr.counters()
+    assert got.pop("unsupported") == 2 and got == want
+    ctr.write_counts(str(g_dir), "p", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(g_dir), "p"), read_csv_dir(str(o_dir), "p"))
+    # and the command line, which probes the first reads for its default geometry
+    c_dir = tmp_path / "c"
+    c_dir.mkdir()
+    r = subprocess.run([bc.CLI_PATH, "-f", str(fq), "-q", paths["fmt"], "-c", paths["counted"], "-o", str(c_dir), "-p", "p",
+                        f"--min-quality={fl['min_quality']}", "--batch-reads=100"] + (["-e"] if fl["enrich"] else []),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert_same_csv_set(read_csv_dir(str(c_dir), "p"), read_csv_dir(str(o_dir), "p"))
+    assert f"Correctly matched sequences: {want['matched']:,}" in r.stdout and "2 reads hold characters outside" in r.stderr
 
 
 # ---- hand-derived vectors on the reference's example files (SURVEY.md §8(c) G1-G8) ------------------------------

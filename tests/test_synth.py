@@ -164,6 +164,38 @@ def test_exchange_on_one_gpu_equals_single_context(name, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["del3", "crispr", "lineage", "example"])
+def test_specialized_kernel_equals_generic_on_workloads(name, tmp_path):
+    """Millions of reads of every BASELINE workload through the NVRTC-specialised decode kernel and through the generic
+    one: identical counters and identical (key, count) rows."""
+    import torch
+    n, batch = 3_000_000, 1_000_000
+    wl = synth.Workload(name, str(tmp_path / name), reads=n)
+    run = wl.run(bc)
+    batches = [wl.generate_device(run, a, min(batch, n - a)) for a in range(0, n, batch)]
+    torch.cuda.synchronize()
+
+    def result(flags):
+        ctr = bc.Counter(run, expected_reads=n, flags=flags)
+        for b in batches:
+            ctr.submit(b)
+        c = ctr.counters()
+        k, lo, hi, cnt = ctr.finish_view()
+        hi = hi if hi is not None else np.zeros(k, np.uint64)
+        order = np.lexsort((lo, hi))
+        rows = np.stack([hi[order], lo[order], cnt[order]], axis=1).copy()
+        prof = ctr.profile()
+        ctr.close()
+        return c, rows, prof
+
+    c0, r0, p0 = result(bc.BC_CFG_NO_SPECIALIZE)
+    c1, r1, p1 = result(bc.BC_CFG_SPECIALIZE)
+    assert p0["specialized_launches"] == 0 and p1["generic_launches"] == 0 and p1["specialized_launches"] == len(batches)
+    assert c0 == c1 and sum(c0.values()) == n
+    assert r0.shape == r1.shape and bool((r0 == r1).all())
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["del3", "lineage", "example"])
 def test_counting_modes_agree_on_workloads(name, tmp_path):
     """Deferred partitioned counting (default), its global-table fallback and the read-by-read inline tables must give the
