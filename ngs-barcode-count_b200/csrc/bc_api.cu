@@ -108,6 +108,7 @@ struct bc_ctx {
     ItemBuf imp;                          // rows imported from other ranks (bc_import_rows), added before stage B
     unsigned long long imp_n = 0;
     uint32_t *d_hist = nullptr, *d_starts = nullptr, *d_cursor = nullptr;
+    uint32_t *d_hot = nullptr, *d_hot_n = nullptr;  // partitions the keyed reduce handed to the two-pass kernel
     unsigned long long part_cap = 0;
     FlushStats* d_flush = nullptr;
     unsigned long long last_valid = 0, last_unique = 0;  // of the last flush
@@ -291,9 +292,12 @@ int reserve_parts(bc_ctx* ctx, unsigned long long n_parts) {
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_starts) cudaFree(ctx->d_starts);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
-    ctx->d_hist = ctx->d_starts = ctx->d_cursor = nullptr;
+    if (ctx->d_hot) cudaFree(ctx->d_hot);
+    ctx->d_hist = ctx->d_starts = ctx->d_cursor = ctx->d_hot = nullptr;
     ctx->part_cap = 0;
     const unsigned long long cap = n_parts + n_parts / 8 + 1024;
+    CK(ctx, cudaMalloc(&ctx->d_hot, cap * sizeof(uint32_t)));
+    if (!ctx->d_hot_n) CK(ctx, cudaMalloc(&ctx->d_hot_n, sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&ctx->d_hist, cap * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&ctx->d_starts, cap * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&ctx->d_cursor, cap * sizeof(uint32_t)));
@@ -497,6 +501,8 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_starts) cudaFree(ctx->d_starts);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    if (ctx->d_hot) cudaFree(ctx->d_hot);
+    if (ctx->d_hot_n) cudaFree(ctx->d_hot_n);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     for (Staging& s : ctx->staging) {
         if (s.planes) cudaFree(s.planes);
@@ -1294,10 +1300,15 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
         if (rc == 1) return go_global(ctx, in, 2, 0);
         if (rc == BC_OK || rc == 3) {
             {
+                // one pass for partitions whose keys have few random barcodes each; the ones it gives up on (listed on the
+                // device) go through the two-pass kernel right after — their output is final as well, the partition being by key
+                const ItemView rows_out{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt};
                 ProfScope p(ctx, BC_K_FINISH);
-                CK(ctx, launch_reduce(RED_DEDUPE_KEYED, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits,
-                                      ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
-                                      ctx->d_flush, rc == 3 ? cap : 0u, ctx->stream));
+                CK(ctx, cudaMemsetAsync(ctx->d_hot_n, 0, sizeof(uint32_t), ctx->stream));
+                CK(ctx, launch_reduce(RED_DEDUPE_KEYED, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits, rows_out,
+                                      ctx->row_cap, ctx->d_flush, rc == 3 ? cap : 0u, HotList{ctx->d_hot, ctx->d_hot_n, false}, ctx->stream));
+                CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_rec, n_parts, 0, ctx->cfg.umi_bits, rows_out,
+                                      ctx->row_cap, ctx->d_flush, rc == 3 ? cap : 0u, HotList{ctx->d_hot, ctx->d_hot_n, true}, ctx->stream));
             }
             CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
             CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1350,12 +1361,12 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
             if (rc != BC_OK) return rc;
             ProfScope p(ctx, BC_K_FINISH);
             CK(ctx, launch_reduce(RED_DEDUPE, wide_in, part_v, ctx->d_starts, n_src, n_parts, 0, ctx->cfg.umi_bits, w1_v, ctx->w1.cap,
-                                  ctx->d_flush, 0, ctx->stream));
+                                  ctx->d_flush, 0, HotList{}, ctx->stream));
         } else {
             const uint32_t chunk = reduce_chunk(wide_in);
             ProfScope p(ctx, BC_K_FINISH);
             CK(ctx, launch_reduce(RED_COUNT, wide_in, src, nullptr, n_src, (n_src + chunk - 1) / chunk, chunk, 0, w1_v, ctx->w1.cap,
-                                  ctx->d_flush, 0, ctx->stream));
+                                  ctx->d_flush, 0, HotList{}, ctx->stream));
         }
     }
     CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1392,7 +1403,7 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
             ProfScope p(ctx, BC_K_FINISH);
             CK(ctx, launch_reduce(RED_COUNT, wide_out, ItemView{ctx->w2.lo, wide_out ? ctx->w2.hi : nullptr, ctx->w2.w}, ctx->d_starts, n1,
                                   n_parts, 0, 0, ItemView{ctx->d_row_lo, wide_out ? ctx->d_row_hi : nullptr, ctx->d_row_cnt}, ctx->row_cap,
-                                  ctx->d_flush, 0, ctx->stream));
+                                  ctx->d_flush, 0, HotList{}, ctx->stream));
         }
         CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));

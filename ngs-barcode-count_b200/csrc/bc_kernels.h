@@ -116,10 +116,17 @@ uint32_t split_max_bits();
 // One CTA per partition [starts[p], starts[p+1]) — or, with starts == nullptr, per fixed chunk of `chunk` items.
 //   RED_DEDUPE: distinct records of the partition, then their keys (record >> umi_bits) combined: out = (key, pairs)
 //   RED_COUNT : out = (key, sum of weights)
+// hot: RED_DEDUPE_KEYED appends the partitions it gives up on (a key with very many random barcodes) to hot.list / *hot.n
+// (device memory); with hot.consume the launch instead processes exactly the listed partitions.
+struct HotList {
+    uint32_t* list = nullptr;
+    uint32_t* n = nullptr;
+    bool consume = false;
+};
 cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
                           unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
                           unsigned long long out_cap, FlushStats* stats, uint32_t skip_over /* > 0: leave larger partitions alone */,
-                          cudaStream_t stream);
+                          const HotList& hot, cudaStream_t stream);
 // multi-GPU exchange: valid items of `in` -> peers.lo/hi[owner] at cursors[owner]++ (see bc_partition.cu)
 cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& peers, unsigned long long n_total, const SplitLevel& lv,
                                  uint32_t* cursors, cudaStream_t stream);

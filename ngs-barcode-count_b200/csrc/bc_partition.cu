@@ -17,6 +17,8 @@
 // with uniform hashing: the fill target is 30 standard deviations below the capacity) raises `overflow` and the host
 // falls back to the global-memory tables of bc_device.cuh.
 #include "../../include/bc_b200.h"
+#include <algorithm>
+
 #include "bc_kernels.h"
 
 namespace bc {
@@ -362,18 +364,22 @@ __device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t valu
 // MODE RED_DEDUPE      : in = records (key incl. random barcode), out = (record >> umi_bits, distinct records with that key)
 // MODE RED_COUNT       : in = (key, weight) items,                out = (key, sum of weights)
 // MODE RED_DEDUPE_KEYED: RED_DEDUPE for partitions that hold whole keys (partitioned by the record WITHOUT its random
-//   barcode) and fit the key store — one pass instead of two.  Two small tables of 16-bit key-store indices: a record is
-//   looked up by its full value in the first (a repeat stops there: info.rs:780-791, only the first insert of a pair
-//   counts); a record seen for the first time then finds or claims its KEY's entry in the second, and that entry's
-//   counter takes the +1.  Both are ordinary open-addressing sets with independent hashes, so a key with hundreds of
-//   random barcodes costs what any other records cost (chaining a key's records behind one home slot was quadratic).
+//   barcode) and fit the key store — one pass instead of two.  A record's home slot is the hash of its KEY, so all records
+//   of a key walk the same probe sequence; slots of a sequence fill in order and never empty, hence the first entry
+//   of that key a record meets on its way (or the record itself when it meets none) is the same for all of them: that
+//   entry carries the key's count of distinct records.  The price is that a key's records chain behind one home slot:
+//   fine for the usual one to a few random barcodes per key, quadratic for a key with hundreds.  A lane that has walked
+//   kChainLimit slots for one record gives the partition up: nothing is emitted, its number goes on `hot_list`, and a
+//   second launch puts the listed partitions through the two-pass RED_DEDUPE, whose cost does not depend on the keys.
+constexpr uint32_t kChainLimit = 40;
+
 template <bool WIDE, int MODE>
-__global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
-    k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
-             const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats,
-             const uint32_t skip_over) {
+__device__ __forceinline__ void reduce_one(const unsigned long long p, const ItemView& in, const uint32_t* __restrict__ starts,
+                                           const unsigned long long n_items, const uint32_t chunk, const uint32_t umi_bits,
+                                           const ItemView& out, const unsigned long long out_cap, FlushStats* stats,
+                                           const uint32_t skip_over, uint32_t* hot_list, uint32_t* hot_n) {
     extern __shared__ __align__(16) unsigned char red_smem[];
-    __shared__ uint32_t s_nperm, s_warp[kRedThreads / 32];
+    __shared__ uint32_t s_nperm, s_warp[kRedThreads / 32], s_abort;
     __shared__ unsigned long long s_base;
 
     SmemTable<WIDE> t;
@@ -381,14 +387,10 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     t.khi = WIDE ? t.klo + kKeyCap : nullptr;
     t.table = reinterpret_cast<uint32_t*>(t.klo + (WIDE ? 2 : 1) * kKeyCap);
     t.kcnt = t.table + kTableSlots;
-    // RED_DEDUPE_KEYED lays the space after the key store out as [records u16 x slots][keys u16 x slots][kw u32 x cap]
-    unsigned short* t_rec = reinterpret_cast<unsigned short*>(t.table);
-    unsigned short* t_key = t_rec + kTableSlots;
-    uint32_t* kw = MODE == RED_DEDUPE_KEYED ? reinterpret_cast<uint32_t*>(t_key + kTableSlots) : t.kcnt + kKeyCap;  // distinct records per key
+    uint32_t* kw = MODE == RED_DEDUPE_KEYED ? t.kcnt : t.kcnt + kKeyCap;  // RED_DEDUPE*: distinct records per key
     t.n_perm = &s_nperm;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned long long p = blockIdx.x;
     const unsigned long long a = starts ? (unsigned long long)starts[p] : p * chunk;
     const unsigned long long e = starts ? (unsigned long long)starts[p + 1] : min(n_items, a + chunk);
     if (e <= a) return;  // empty partition: nothing to emit
@@ -396,7 +398,10 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
 
     clear_u32(t.table, kTableSlots, kEmpty32);
     if (MODE != RED_COUNT) clear_u32(kw, kKeyCap, 0u);
-    if (tid == 0) s_nperm = 0;
+    if (tid == 0) {
+        s_nperm = 0;
+        s_abort = 0;
+    }
 
     uint32_t n_perm;
     uint32_t* val = t.kcnt;
@@ -424,61 +429,70 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
         }
         __syncthreads();
         // One loop over probe STEPS, not over items: a lane that settles an item moves on to its next one at once, so a
-        // warp runs for the longest lane total (about items x 2.5 steps) instead of the sum of per-item maxima.
+        // warp runs for the longest lane total (about items x 1.5 steps) instead of the sum of per-item maxima.
         uint32_t uniq = 0;
         {
-            constexpr uint32_t kNone = 0xFFFFu;
-            uint32_t j = tid, s = 0;
+            uint32_t j = tid, s = 0, rep = kEmpty32, walked = 0;
             unsigned long long clo = 0, chi = 0;
             Key K{0, 0};
-            int phase = -1;  // -1: fetch item j; 0: looking the record up; 1: looking its key up
+            bool fresh = true;
             while (j < n) {
-                if (phase < 0) {
+                if (fresh) {
                     clo = t.klo[j];
                     chi = WIDE ? t.khi[j] : 0ULL;
                     if (!item_valid(clo, chi, WIDE)) {
                         j += kRedThreads;
                         continue;
                     }
-                    s = slot_hash<WIDE>(clo, chi) & (kTableSlots - 1);
-                    phase = 0;
+                    K = drop_umi<WIDE>(clo, chi, umi_bits);
+                    s = slot_hash<WIDE>(K.lo, K.hi) & (kTableSlots - 1);
+                    rep = kEmpty32;  // first entry of this key met so far
+                    walked = 0;
+                    fresh = false;
                 }
-                unsigned short* tab = phase == 0 ? t_rec : t_key;
-                uint32_t v = *reinterpret_cast<volatile unsigned short*>(&tab[s]);
-                bool claimed = false;
-                if (v == kNone) {
-                    const unsigned short old = atomicCAS(&tab[s], (unsigned short)kNone, (unsigned short)j);
-                    claimed = old == kNone;
+                uint32_t v = *reinterpret_cast<volatile uint32_t*>(&t.table[s]);
+                if (v == kEmpty32) {
+                    const uint32_t old = atomicCAS(&t.table[s], kEmpty32, j);
+                    if (old == kEmpty32) {  // a record not seen before
+                        atomicAdd(&kw[rep == kEmpty32 ? j : rep], 1u);
+                        uniq++;
+                        j += kRedThreads;
+                        fresh = true;
+                        continue;
+                    }
                     v = old;
                 }
-                if (phase == 0) {
-                    if (claimed) {  // a record not seen before: on to its key
-                        uniq++;
-                        K = drop_umi<WIDE>(clo, chi, umi_bits);
-                        s = (slot_hash<WIDE>(K.lo, K.hi) * 0x9E3779B1u >> 7) & (kTableSlots - 1);
-                        phase = 1;
-                        continue;
-                    }
-                    if (t.klo[v] == clo && (!WIDE || t.khi[v] == chi)) {  // a repeat
-                        j += kRedThreads;
-                        phase = -1;
-                        continue;
-                    }
-                } else {
-                    bool same = claimed;
-                    if (!claimed) {
-                        const Key o = drop_umi<WIDE>(t.klo[v], WIDE ? t.khi[v] : 0ULL, umi_bits);
+                const unsigned long long vlo = t.klo[v], vhi = WIDE ? t.khi[v] : 0ULL;
+                if (vlo == clo && (!WIDE || vhi == chi)) {  // a repeat (info.rs:780-791: only the first insert counts)
+                    j += kRedThreads;
+                    fresh = true;
+                    continue;
+                }
+                if (rep == kEmpty32) {
+                    bool same;
+                    if (!WIDE) {
+                        same = ((vlo ^ clo) >> umi_bits) == 0ULL;
+                    } else {
+                        const Key o = drop_umi<true>(vlo, vhi, umi_bits);
                         same = o.lo == K.lo && o.hi == K.hi;
                     }
-                    if (same) {  // entry v (this record itself when it claimed the slot) stands for the key
-                        atomicAdd(&kw[claimed ? j : v], 1u);
-                        j += kRedThreads;
-                        phase = -1;
-                        continue;
-                    }
+                    if (same) rep = v;
                 }
                 s = (s + 1) & (kTableSlots - 1);
+                if (++walked >= kChainLimit) {  // a hot key (or an unlucky cluster): hand the partition to the two-pass kernel
+                    if (hot_list) {
+                        s_abort = 1;
+                        break;
+                    }
+                    walked = 0;
+                }
+                if ((walked & 7u) == 7u && *reinterpret_cast<volatile uint32_t*>(&s_abort)) break;  // another lane gave up
             }
+        }
+        __syncthreads();
+        if (s_abort) {  // uniform: nothing was emitted, no statistic was touched
+            if (tid == 0) hot_list[atomicAdd(hot_n, 1u)] = (uint32_t)p;
+            return;
         }
         for (int o = 16; o; o >>= 1) uniq += __shfl_xor_sync(0xFFFFFFFFu, uniq, o);
         if (lane == 0) s_warp[wid] = uniq;
@@ -641,16 +655,41 @@ __global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
     }
 }
 
+// One CTA per partition; or, with `list`, persistent CTAs over the partitions listed on the device (the hot partitions the
+// keyed pass gave up on: their number is only known there).
+template <bool WIDE, int MODE>
+__global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
+    k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
+             const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats,
+             const uint32_t skip_over, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_n, uint32_t* hot_list,
+             uint32_t* hot_n) {
+    if (!list) {
+        reduce_one<WIDE, MODE>(blockIdx.x, in, starts, n_items, chunk, umi_bits, out, out_cap, stats, skip_over, hot_list, hot_n);
+        return;
+    }
+    const uint32_t n = *list_n;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        reduce_one<WIDE, MODE>(list[i], in, starts, n_items, chunk, umi_bits, out, out_cap, stats, skip_over, nullptr, nullptr);
+        __syncthreads();  // the next partition reuses the shared memory
+    }
+}
+
 template <bool WIDE, int MODE>
 cudaError_t launch_reduce_t(const ItemView& in, const uint32_t* starts, unsigned long long n_items, unsigned long long n_ranges,
                             uint32_t chunk, uint32_t umi_bits, const ItemView& out, unsigned long long out_cap, FlushStats* stats,
-                            uint32_t skip_over, cudaStream_t stream) {
+                            uint32_t skip_over, const HotList& hot, cudaStream_t stream) {
     const size_t smem = (size_t)kKeyCap * 8 * (WIDE ? 2 : 1) + (size_t)kTableSlots * 4 + (size_t)kKeyCap * 4 * (MODE == RED_DEDUPE ? 2 : 1);
-    // (RED_DEDUPE_KEYED: two tables of u16 in the space of the one u32 table, then the per-key counters)
     cudaError_t e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce<WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    k_reduce<WIDE, MODE><<<(unsigned)n_ranges, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats, skip_over);
+    if (hot.consume) {  // persistent CTAs over the listed partitions
+        const unsigned grid = (unsigned)std::min<unsigned long long>(n_ranges, 148ULL * (WIDE ? 3 : 4));
+        k_reduce<WIDE, MODE><<<grid, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats, skip_over, hot.list,
+                                                                  hot.n, nullptr, nullptr);
+    } else {
+        k_reduce<WIDE, MODE><<<(unsigned)n_ranges, kRedThreads, smem, stream>>>(in, starts, n_items, chunk, umi_bits, out, out_cap, stats,
+                                                                                skip_over, nullptr, nullptr, hot.list, hot.n);
+    }
     return cudaGetLastError();
 }
 
@@ -770,17 +809,17 @@ cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& p
 
 cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_t* starts, unsigned long long n_items,
                           unsigned long long n_ranges, uint32_t chunk, uint32_t umi_bits, const ItemView& out,
-                          unsigned long long out_cap, FlushStats* stats, uint32_t skip_over, cudaStream_t stream) {
+                          unsigned long long out_cap, FlushStats* stats, uint32_t skip_over, const HotList& hot, cudaStream_t stream) {
     if (n_ranges == 0) return cudaSuccess;
     if (n_ranges > 0x7FFFFFFFULL) return cudaErrorInvalidValue;
     if (mode == RED_DEDUPE_KEYED)
-        return wide ? launch_reduce_t<true, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
-                    : launch_reduce_t<false, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
+        return wide ? launch_reduce_t<true, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream)
+                    : launch_reduce_t<false, RED_DEDUPE_KEYED>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream);
     if (mode == RED_DEDUPE)
-        return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
-                    : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
-    return wide ? launch_reduce_t<true, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream)
-                : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, stream);
+        return wide ? launch_reduce_t<true, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream)
+                    : launch_reduce_t<false, RED_DEDUPE>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream);
+    return wide ? launch_reduce_t<true, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream)
+                : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream);
 }
 
 // partitions larger than `limit` copied, one warp each, to a contiguous buffer (their total is known from the scan)

@@ -280,6 +280,9 @@ struct FastqStream {
                 else break;
                 size_t l = end - p;
                 if (l && base[end - 1] == '\r') l--;
+                // input.rs:133-137: the reference drops the last character of a record as "the newline"; on its gzip path a
+                // last line without one loses its last quality character instead (its plain path adds the newline first)
+                if (!nl && !plain && l) l--;
                 line[k] = base + p;
                 len[k] = (uint32_t)l;
                 p = nl ? end + 1 : end;

@@ -209,18 +209,19 @@ def test_cli_several_contexts_and_clap_syntax(case, tmp_path):
                       ("--max-errors-constant", "max_constant")):
         if fl[key] is not None:
             cmd += [f"{flag}={fl[key]}"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True)  # bytes: text mode would translate the carriage returns
     assert r.returncode == 0, r.stderr
+    stdout = r.stdout.decode()
     assert_same_csv_set(read_csv_dir(str(out), "golden"), exp["files"])
     c = exp["counters"]
     n_reads = len(exp["outcomes"])
-    assert f"Total sequences:             {n_reads:,}\r\n" in r.stdout  # input.rs:151-158: rewritten in place, then a newline
-    assert f"Correctly matched sequences: {c['matched']:,}" in r.stdout
-    assert f"Duplicates:                  {c['duplicates']:,}" in r.stdout
-    assert f"Low quality barcodes:        {c['low_quality']:,}" in r.stdout
+    assert f"Total sequences:             {n_reads:,}\r\n" in stdout  # input.rs:151-158: rewritten in place, then a newline
+    assert f"Correctly matched sequences: {c['matched']:,}" in stdout
+    assert f"Duplicates:                  {c['duplicates']:,}" in stdout
+    assert f"Low quality barcodes:        {c['low_quality']:,}" in stdout
     for fn, lines in exp["files"].items():  # output.rs:143-165, 355-359: file name, then its number of barcode rows
         end = "\n" if "_counts.all" in fn else "\r\n"
-        assert f"{fn}\nBarcodes counted: {len(lines) - 1:,}{end}" in r.stdout, fn
+        assert f"{fn}\nBarcodes counted: {len(lines) - 1:,}{end}" in stdout, fn
 
 
 def test_cli_gzip_total_has_the_reference_phantom_read(tmp_path):
@@ -234,12 +235,13 @@ def test_cli_gzip_total_has_the_reference_phantom_read(tmp_path):
     out = tmp_path / "out"
     out.mkdir()
     r = subprocess.run([bc.CLI_PATH, "-f", fastq, "-q", paths["fmt"], "-s", paths["samples"], "-c", paths["counted"], "-o", str(out),
-                        "-p", "golden", "-me"], capture_output=True, text=True)
+                        "-p", "golden", "-me"], capture_output=True)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.startswith("-FORMAT-")
-    assert "If this program stops reading before the expected number of sequencing reads" in r.stdout
-    assert f"Total sequences:             {len(exp['outcomes']) + 1:,}\r\n" in r.stdout
-    assert "WARNING: The program may have stopped early with the gzipped file." in r.stdout
+    stdout = r.stdout.decode()
+    assert stdout.startswith("-FORMAT-")
+    assert "If this program stops reading before the expected number of sequencing reads" in stdout
+    assert f"Total sequences:             {len(exp['outcomes']) + 1:,}\r\n" in stdout
+    assert "WARNING: The program may have stopped early with the gzipped file." in stdout
     assert_same_csv_set(read_csv_dir(str(out), "golden"), exp["files"])
 
 

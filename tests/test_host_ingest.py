@@ -35,6 +35,17 @@ def test_block_reader_plain_gzip_bgzip_agree(tmp_path, crlf, last_newline):
     plain = tmp_path / "r.fastq"
     plain.write_bytes(data)
     assert bc.scan_fastq(str(plain)) == want
+    if not last_newline:
+        # the reference's gzip path pops the last character of the last record as "the newline" (input.rs:133-137):
+        # without a final newline that is the last quality character
+        text = data.decode()
+        last_q = text[text.rfind("\n") + 1:]
+        recs = text.split("\n")
+        crc = zlib.crc32(b"")
+        for i in range(0, len(recs), 4):
+            q = recs[i + 3] if i + 4 < len(recs) else last_q[:-1]
+            crc = zlib.crc32(q.encode(), zlib.crc32(recs[i + 1].encode(), crc))
+        want = (want[0], want[1], crc)
     one = tmp_path / "one.fastq.gz"
     one.write_bytes(gzip.compress(data))
     assert bc.scan_fastq(str(one)) == want
