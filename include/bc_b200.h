@@ -254,6 +254,9 @@ int bc_key_decode(const bc_ctx *ctx, uint64_t key_lo, uint64_t key_hi, uint32_t 
 #define BC_IPC_HANDLE_BYTES 64
 int bc_exchange_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity);
 int bc_exchange_handle(bc_ctx *ctx, void *ipc_handle_out);
+/* Unmaps the other ranks' buffers.  Before re-opening larger, every rank disconnects and the caller synchronises the ranks:
+ * a buffer must not be freed while another process still maps it. */
+int bc_exchange_disconnect(bc_ctx *ctx);
 int bc_exchange_connect(bc_ctx *ctx, const void *ipc_handles);
 int bc_exchange_connect_local(bc_ctx *ctx, bc_ctx *const *ranks);
 int bc_exchange_count(bc_ctx *ctx, uint64_t *sent);

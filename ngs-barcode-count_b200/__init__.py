@@ -154,6 +154,7 @@ _PROTOS = {
     "bc_marginals": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bc_exchange_open": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]),
     "bc_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bc_exchange_disconnect": (C.c_int, [C.c_void_p]),
     "bc_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_exchange_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bc_exchange_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -452,6 +453,9 @@ class Counter:
     # ---- multi-GPU building blocks ----
     def exchange_open(self, n_ranks, rank, capacity):
         self._ck(lib().bc_exchange_open(self.h, n_ranks, rank, int(capacity)), "bc_exchange_open")
+
+    def exchange_disconnect(self):
+        self._ck(lib().bc_exchange_disconnect(self.h), "bc_exchange_disconnect")
 
     def exchange_handle(self):
         """-> the CUDA IPC handle (bytes) of this rank's receive buffer"""

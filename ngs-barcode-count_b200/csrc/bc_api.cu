@@ -69,7 +69,8 @@ struct bc_ctx {
     DevAux aux{};
     // reads of the batch in flight whose barcode step needs a search (filled by k_decode, drained by k_resolve)
     uint2* d_def_items = nullptr;
-    uint32_t* d_def_count = nullptr;
+    uint32_t* d_def_count = nullptr;  // two counters, used by alternate batches
+    uint32_t def_parity = 0;
     uint64_t def_cap = 0;
     // multi-GPU exchange at the flush (bc_exchange_*): this rank's receive buffer [lo: cap][hi: cap], the peers' buffers
     // (CUDA IPC mappings, or plain pointers of contexts in this process), and what the last exchange delivered
@@ -99,8 +100,8 @@ struct bc_ctx {
     // de-duplicate and count the whole buffer partition by partition in shared memory
     bool deferred = false;
     ItemBuf rec;                          // the record buffer: slot (cursor + read index) per read, kEmpty = hole
-    unsigned long long* d_rec_n = nullptr;   // device cursor: slots used
-    unsigned long long rec_upper = 0;        // host-side upper bound of the cursor
+    unsigned long long rec_n = 0;            // slots used: every appended batch takes exactly n_reads of them
+    bool stripes_dirty = false;              // k_decode's striped counters hold counts not yet folded into d_counters
     ItemBuf left;                         // records of the hot partitions set aside by the one-stage flush
     ItemBuf part, w1, w2, tmp;            // scratch: partitioned records, (key, weight) items before / after partitioning,
                                           // and the output of the first radix level when two are needed
@@ -305,37 +306,29 @@ int reserve_parts(bc_ctx* ctx, unsigned long long n_parts) {
     return BC_OK;
 }
 
-// Room in the record buffer for `extra` more slots beyond the host-side bound of the cursor.  When the bound (which
-// counts the worst case of routed appends) runs into the capacity, the real cursor is read back before growing.
+// Room in the record buffer for `extra` more slots (the buffer grows, keeping what it holds)
 int reserve_records(bc_ctx* ctx, unsigned long long extra) {
     const bool wide = ctx->cfg.wide != 0;
-    if (ctx->rec_upper + extra <= ctx->rec.cap && ctx->rec.lo) {
-        ctx->rec_upper += extra;
-        return BC_OK;
-    }
-    unsigned long long used = 0;
-    if (ctx->rec.lo) {
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        CK(ctx, cudaMemcpy(&used, ctx->d_rec_n, sizeof used, cudaMemcpyDeviceToHost));
-    }
-    ctx->rec_upper = used;
-    if (used + extra > ctx->rec.cap || !ctx->rec.lo) {
-        int rc = reserve_items(ctx, ctx->rec, used + extra, wide, false, used);
-        if (rc != BC_OK) return rc;
-    }
-    ctx->rec_upper += extra;
-    return BC_OK;
+    if (ctx->rec_n + extra <= ctx->rec.cap && ctx->rec.lo) return BC_OK;
+    return reserve_items(ctx, ctx->rec, ctx->rec_n + extra, wide, false, ctx->rec_n);
 }
 
 // first append of a job: size the buffer for the whole job (bc_create's expected_reads) plus `slack`
 int prime_records(bc_ctx* ctx, unsigned long long slack) {
     if (ctx->rec.lo) return BC_OK;
-    int rc = reserve_records(ctx, ctx->expected_reads + ctx->expected_reads / 8 + slack);
-    ctx->rec_upper = 0;
-    return rc;
+    return reserve_records(ctx, ctx->expected_reads + ctx->expected_reads / 8 + slack);
 }
 
-RecOut rec_out(const bc_ctx* ctx) { return RecOut{ctx->rec.lo, ctx->cfg.wide ? ctx->rec.hi : nullptr, ctx->d_rec_n}; }
+RecOut rec_out(const bc_ctx* ctx) { return RecOut{ctx->rec.lo, ctx->cfg.wide ? ctx->rec.hi : nullptr, ctx->rec_n}; }
+
+// k_decode adds its outcome counters to striped copies; they are folded into d_counters when somebody reads them
+int fold_counters(bc_ctx* ctx) {
+    if (!ctx->stripes_dirty) return BC_OK;
+    ProfScope p(ctx, BC_K_OTHER);
+    CK(ctx, launch_fold_counters(ctx->d_stripes, ctx->d_counters, ctx->stream));
+    ctx->stripes_dirty = false;
+    return BC_OK;
+}
 
 // Smallest integer sum S with fl32(fl32(S) / fl32(len)) >= min_quality: the reference's f32 mean test
 // (parse.rs:352-355) as an exact integer threshold (Q12).  255*len+1 when no sum passes.
@@ -453,6 +446,10 @@ int ensure_capacity(bc_ctx* ctx, unsigned long long incoming) {
     ctx->entries_upper += incoming;
     const unsigned long long smallest = std::min(T.map.kind ? T.map.cap : ~0ull, T.has_set ? T.set.cap : ~0ull);
     if (slots_for(ctx->entries_upper) <= smallest) return BC_OK;
+    {
+        const int rc_ = fold_counters(ctx);
+        if (rc_ != BC_OK) return rc_;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned long long n[2] = {0, 0};
     CK(ctx, cudaMemcpy(n, ctx->d_counters + BC_N_COUNTERS, sizeof n, cudaMemcpyDeviceToHost));
@@ -497,7 +494,6 @@ void bc_destroy(bc_ctx* ctx) {
     free_items(ctx->left);
     if (ctx->d_l1) cudaFree(ctx->d_l1);
     free_items(ctx->imp);
-    if (ctx->d_rec_n) cudaFree(ctx->d_rec_n);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_starts) cudaFree(ctx->d_starts);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
@@ -952,7 +948,8 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
         CKC(cudaMemcpyAsync(ctx->d_bref, bref.data(), bref.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (table_u16) CKC(cudaMalloc(&ctx->d_tables, table_u16 * sizeof(uint32_t)));
-    CKC(cudaMalloc(&ctx->d_def_count, sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_def_count, 2 * sizeof(uint32_t)));
+    CKC(cudaMemsetAsync(ctx->d_def_count, 0, 2 * sizeof(uint32_t), ctx->stream));
     ctx->aux = DevAux{ctx->d_refs, ctx->d_tables, ctx->d_hash_keys, ctx->d_hash_idx, ctx->d_half, ctx->d_deep, ctx->d_csr, ctx->d_bref};
     for (uint32_t s = 0; s < cfg->n_slots; s++) {
         if (d.slots[s].mode != MODE_TABLE) continue;
@@ -981,8 +978,6 @@ int bc_create(const bc_config* cfg, int device, uint64_t expected_reads, bc_ctx*
     // BC_CFG_INLINE_COUNT keeps the read-by-read tables (measurement aid; the same tables are the flush's fallback).
     ctx->deferred = (T.has_set || !dense) && !(cfg->flags & BC_CFG_INLINE_COUNT);
     ctx->expected_reads = hint;
-    CKC(cudaMalloc(&ctx->d_rec_n, sizeof(unsigned long long)));
-    CKC(cudaMemsetAsync(ctx->d_rec_n, 0, sizeof(unsigned long long), ctx->stream));
     CKC(cudaMalloc(&ctx->d_flush, sizeof(FlushStats)));
     CKC(cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
     if (ctx->deferred) {
@@ -1089,8 +1084,9 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
         CK(ctx, cudaMalloc(&ctx->d_def_items, (size_t)batch->n_reads * sizeof(uint2)));
         ctx->def_cap = batch->n_reads;
     }
-    const Deferred deferred{ctx->d_def_items, ctx->d_def_count};
-    CK(ctx, cudaMemsetAsync(ctx->d_def_count, 0, sizeof(uint32_t), ctx->stream));
+    // the two counters of the deferred list alternate: this batch's k_resolve zeroes the one the next batch will fill
+    const Deferred deferred{ctx->d_def_items, ctx->d_def_count + ctx->def_parity, ctx->d_def_count + (ctx->def_parity ^ 1u)};
+    ctx->def_parity ^= 1u;
     {
         ProfScope p(ctx, BC_K_DECODE);
         const bool fits = ctx->jit.kernel && view.W == ctx->jit.W && view.plane_stride == ctx->jit.plane_stride &&
@@ -1105,18 +1101,12 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
                                   flags, ctx->stream));
         }
     }
-    if (counters) {
-        ProfScope p(ctx, BC_K_OTHER);
-        CK(ctx, launch_fold_counters(ctx->d_stripes, counters, ctx->stream));
-    }
-    if (!(flags & F_LOCATE_ONLY)) {
+    if (counters) ctx->stripes_dirty = true;
+    {   // also after a locate-only launch (nothing deferred): it is k_resolve that zeroes the next batch's list counter
         ProfScope p(ctx, BC_K_SCAN);
         CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, rec_out(ctx), deferred, flags, ctx->stream));
     }
-    if (flags & F_APPEND) {
-        ProfScope p(ctx, BC_K_OTHER);
-        CK(ctx, launch_bump(ctx->d_rec_n, batch->n_reads, ctx->stream));
-    }
+    if (flags & F_APPEND) ctx->rec_n += batch->n_reads;
     return release_staging(ctx, staged);
 }
 
@@ -1466,11 +1456,10 @@ static int flush_records(bc_ctx* ctx) {
     if (ctx->x_ranks > 1)
         return fail(ctx, BC_ESTATE, "this context is one rank of a multi-GPU job: run bc_exchange_count / _scatter / _finish after the "
                                     "last bc_submit before asking for counters or rows");
-    int rc = bc_sync(ctx);
+    int rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
-    unsigned long long n_rec = 0;
-    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
-    ctx->rec_upper = n_rec;
+    const unsigned long long n_rec = ctx->rec_n;
     // records that are not holes = reads counted "matched" so far (the repeats already moved to "duplicates" included)
     unsigned long long h[BC_N_COUNTERS];
     CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
@@ -1483,7 +1472,9 @@ static int flush_records(bc_ctx* ctx) {
 
 int bc_get_counters(bc_ctx* ctx, uint64_t out[BC_N_COUNTERS]) {
     if (!ctx || !out) return BC_EINVAL;
-    int rc = bc_sync(ctx);
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     if (ctx->deferred) {  // the matched / duplicates split is known once the records are de-duplicated
         CK(ctx, cudaSetDevice(ctx->device));
@@ -1597,7 +1588,8 @@ static int rows_to_host(bc_ctx* ctx, const unsigned long long* lo, const unsigne
 static int build_rows(bc_ctx* ctx) {
     if (ctx->rows_valid) return BC_OK;
     if (ctx->deferred) return flush_records(ctx);
-    int rc = bc_sync(ctx);
+    int rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     drop_rows(ctx);
     const DevTable& M = ctx->tables.map;
@@ -1952,6 +1944,15 @@ int bc_exchange_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capa
     return BC_OK;
 }
 
+int bc_exchange_disconnect(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    close_peers(ctx);
+    if (ctx->d_xrecv) ctx->x_peer[ctx->x_rank] = ctx->d_xrecv;
+    return BC_OK;
+}
+
 int bc_exchange_handle(bc_ctx* ctx, void* ipc_handle_out) {
     if (!ctx || !ipc_handle_out) return BC_EINVAL;
     if (!ctx->d_xrecv) return fail(ctx, BC_ESTATE, "bc_exchange_handle before bc_exchange_open");
@@ -2013,11 +2014,10 @@ int bc_exchange_count(bc_ctx* ctx, uint64_t* sent) {
     if (!ctx || !sent) return BC_EINVAL;
     if (ctx->x_ranks == 0) return fail(ctx, BC_ESTATE, "bc_exchange_count before bc_exchange_open");
     CK(ctx, cudaSetDevice(ctx->device));
-    int rc = bc_sync(ctx);
+    int rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
-    unsigned long long n_rec = 0;
-    CK(ctx, cudaMemcpy(&n_rec, ctx->d_rec_n, sizeof n_rec, cudaMemcpyDeviceToHost));
-    ctx->rec_upper = n_rec;
+    const unsigned long long n_rec = ctx->rec_n;
     if (n_rec >= 0xFFFFFFF0ULL) return fail(ctx, BC_EUNSUPPORTED, "bc_exchange_count: more than 2^32 records on one rank");
     uint32_t h[kMaxRanks] = {0};
     FlushStats st{};
@@ -2061,7 +2061,7 @@ int bc_exchange_scatter(bc_ctx* ctx, const uint64_t* first) {
     CK(ctx, cudaMemcpyAsync(ctx->d_xcursor, ctx->h_xcur, sizeof cur, cudaMemcpyHostToDevice, ctx->stream));
     {
         ProfScope p(ctx, BC_K_EXCHANGE);
-        CK(ctx, launch_owner_scatter(wide, ItemView{ctx->rec.lo, wide ? ctx->rec.hi : nullptr, nullptr}, peers, ctx->rec_upper, owner_level(ctx),
+        CK(ctx, launch_owner_scatter(wide, ItemView{ctx->rec.lo, wide ? ctx->rec.hi : nullptr, nullptr}, peers, ctx->rec_n, owner_level(ctx),
                                      ctx->d_xcursor, ctx->stream));
     }
     ctx->x_state = 2;
@@ -2078,6 +2078,9 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
     int rc = flush_core(ctx, in);
     if (rc != BC_OK) return rc;
     // this rank's share of the job's outcome: the records it owns (matched = distinct pairs, duplicates = their repeats)
+    rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
+    if (rc != BC_OK) return rc;
     unsigned long long h[BC_N_COUNTERS];
     CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
     h[BC_CNT_MATCHED] = ctx->last_unique;
@@ -2189,9 +2192,10 @@ int bc_reset(bc_ctx* ctx) {
     CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, (BC_N_COUNTERS + 2) * sizeof(unsigned long long), ctx->stream));
     rc = clear_table(ctx, ctx->tables.map);
     if (rc == BC_OK && ctx->tables.has_set) rc = clear_table(ctx, ctx->tables.set);
-    CK(ctx, cudaMemsetAsync(ctx->d_rec_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_stripes, 0, (size_t)kCounterStripes * kCounterStride * sizeof(unsigned long long), ctx->stream));
     CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-    ctx->rec_upper = 0;
+    ctx->stripes_dirty = false;
+    ctx->rec_n = 0;
     ctx->imp_n = 0;
     ctx->dup_applied = 0;
     ctx->marg_valid = false;
@@ -2211,7 +2215,8 @@ int bc_set_profiling(bc_ctx* ctx, int on) {
 
 int bc_get_profile(bc_ctx* ctx, bc_profile* out) {
     if (!ctx || !out) return BC_EINVAL;
-    int rc = bc_sync(ctx);
+    int rc = fold_counters(ctx);
+    if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;
     drain_profile(ctx);
     unsigned long long n = 0;

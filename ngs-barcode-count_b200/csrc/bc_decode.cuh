@@ -451,7 +451,7 @@ __device__ __forceinline__ int count_or_append(const Tables& tables, const RecOu
                                                Key key, bool* new_key, bool* new_pair) {
     if (flags & F_INSERT) return count_read(tables, key, new_key, new_pair) ? BC_ST_MATCHED : BC_ST_DUPLICATE;
     if (flags & F_APPEND) {  // deferred counting: the record slot of this read (k_decode left it empty)
-        const unsigned long long pos = *rec.cursor + read_index;
+        const unsigned long long pos = rec.base + read_index;
         rec.lo[pos] = key.lo;
         if (rec.hi) rec.hi[pos] = key.hi;
     }
@@ -674,7 +674,7 @@ __device__ __forceinline__ void decode_body(const DevCfg& cfg, const BatchView& 
         if (flags & F_APPEND) {
             // deferred counting: every read owns one record slot; unmatched reads (and reads handed to k_resolve, which
             // fills the slot itself when the read matches) leave a hole.  Consecutive lanes, consecutive slots.
-            const unsigned long long pos = *rec.cursor + base + tid;
+            const unsigned long long pos = rec.base + base + tid;
             const bool m = status == BC_ST_MATCHED;
             rec.lo[pos] = m ? key.lo : kEmpty;
             if (rec.hi) rec.hi[pos] = m ? key.hi : kEmpty;

@@ -140,16 +140,17 @@ struct DevAux {  // reference sets and their accelerators
 
 struct Deferred {  // reads whose barcode step needs a search: {read index, offset | repaired << 16}
     uint2* items;
-    uint32_t* count;
+    uint32_t* count;       // filled by k_decode, drained by k_resolve
+    uint32_t* next_count;  // the counter of the NEXT batch (two alternate): k_resolve zeroes it, so no memset per batch
 };
 
 // Deferred counting (bc_partition.cu): instead of updating the tables read by read, a matched read's packed key goes
-// to slot (*cursor + read index) of a flat record buffer — kEmpty marks the reads that did not match — and the whole
+// to slot (base + read index) of a flat record buffer — kEmpty marks the reads that did not match — and the whole
 // job is de-duplicated and counted at flush time, partition by partition, in shared memory.
 struct RecOut {
     unsigned long long* lo;
     unsigned long long* hi;                // nullptr when the full key (random barcode included) fits 63 bits
-    const unsigned long long* cursor;      // records appended before this batch (bumped by launch_bump after the batch)
+    unsigned long long base;               // records appended before this batch (every batch appends exactly n_reads slots)
 };
 
 enum DecodeFlags { F_INSERT = 1, F_EMIT = 2, F_LOCATE_ONLY = 8, F_APPEND = 16 };

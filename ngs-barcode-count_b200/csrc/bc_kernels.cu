@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ DevCfg 
                                                  const DecodeOut out, const RecOut rec, const Deferred deferred, const int flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = *deferred.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *deferred.next_count = 0;  // nobody touches it before the next batch's k_decode
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t W = batch.W;
     unsigned long long c_matched = 0, c_dup = 0, c_sample = 0, c_counted = 0, c_new = 0, c_pair = 0;  // lane 0 only

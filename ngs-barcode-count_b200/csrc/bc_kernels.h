@@ -89,7 +89,6 @@ enum ReduceMode { RED_DEDUPE = 0, RED_COUNT = 1, RED_DEDUPE_KEYED = 2 };
 uint32_t reduce_fill(bool wide);   // target items per hashed partition
 uint32_t reduce_chunk(bool wide);  // items per fixed chunk (pre-aggregation of schemes without a random barcode)
 
-cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cudaStream_t stream);
 // per segment s of bins_per_seg bins: starts = seg_base[s] (0 when nullptr) + exclusive prefix of the segment's histogram,
 // cursor = copy of starts; starts[n_seg * bins_per_seg] = grand total
 cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,

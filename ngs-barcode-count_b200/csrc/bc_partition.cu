@@ -39,8 +39,6 @@ __device__ __forceinline__ bool item_valid(unsigned long long lo, unsigned long 
     return wide ? hi != kEmpty : lo != kEmpty;
 }
 
-__global__ void k_bump(unsigned long long* cursor, unsigned long long add) { *cursor += add; }
-
 // One CTA per segment of F bins: starts[s * F + b] = seg_base[s] + exclusive prefix of the segment's histogram
 // (seg_base == nullptr: a single segment starting at 0), cursor = copy, starts[n_seg * F] = grand total.
 __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ hist, const uint32_t F, const uint32_t* __restrict__ seg_base,
@@ -733,11 +731,6 @@ uint32_t reduce_fill(bool) { return kKeyCap * 3 / 4; }  // mean 1536, sigma 39: 
 uint32_t reduce_chunk(bool) { return kKeyCap; }
 uint32_t reduce_capacity(bool) { return kKeyCap; }
 uint32_t split_max_bits() { return kSplitMaxBits; }
-
-cudaError_t launch_bump(unsigned long long* cursor, unsigned long long add, cudaStream_t stream) {
-    k_bump<<<1, 1, 0, stream>>>(cursor, add);
-    return cudaGetLastError();
-}
 
 cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_per_seg, const uint32_t* seg_base, uint32_t* starts,
                             uint32_t* cursor, FlushStats* stats, uint32_t limit, cudaStream_t stream) {

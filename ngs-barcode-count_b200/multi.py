@@ -102,6 +102,9 @@ class Job:
 
     def _open(self, capacity):
         """(re)allocate the receive buffers and connect every rank to every other (collective)."""
+        if self.cap:  # growing: nobody frees a buffer that another rank still maps
+            self.ctr.exchange_disconnect()
+            dist.barrier()
         self.ctr.exchange_open(self.world, self.rank, capacity)
         handles = [None] * self.world
         dist.all_gather_object(handles, self.ctr.exchange_handle())
@@ -144,6 +147,7 @@ class Job:
         first, received, need = exchange_plan(matrix, self.rank)
         if need > self.cap:  # a skewed job (hot keys): every rank sees the same matrix and grows together
             self._open(int(need * 1.1) + 4096)
+            assert self.ctr.exchange_count(self.world) == sent  # a re-opened exchange starts over; the records have not changed
         self.ctr.exchange_scatter(first)
         # orders the owners' flush after every rank's scatter: a rank leaves the all-reduce only once all have entered it,
         # and each enters it on the stream its scatter kernel runs on

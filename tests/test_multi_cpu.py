@@ -30,6 +30,9 @@ class FakeCounter:
         self.calls.append(("open", capacity))
         self.cap = capacity
 
+    def exchange_disconnect(self):
+        self.calls.append("disconnect")
+
     def exchange_handle(self):
         return b"h" * 64
 
@@ -77,7 +80,7 @@ def _worker(rank, world, port, q):
             totals = [sum(sent_by_rank[s][o] for s in range(world)) for o in range(world)]
             grew = max(totals) > int(expected * 1.25) + 4096
             want = ["reset", "submit", "submit", "submit", "count"] + \
-                ([("open", int(max(totals) * 1.1) + 4096), "connect"] if grew else []) + ["scatter", "finish"]
+                (["disconnect", ("open", int(max(totals) * 1.1) + 4096), "connect", "count"] if grew else []) + ["scatter", "finish"]
             assert ctr.calls[2:] == want, ctr.calls
             assert ctr.received == totals[rank]
             # every owner's buffer is tiled by the ranks' runs, in rank order
