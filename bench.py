@@ -162,7 +162,7 @@ def run_reference(args):
     t = sum(times) / len(times)
     value = n / t
     sample = f"first {n} reads of the {wl.name} workload as a FASTQ file, {threads} threads (1 reader + {threads - 1} workers)"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
@@ -172,7 +172,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU oracle (oracle/): C++ restatement of the reference algorithm in the reference's threading shape; the Rust "
                 "reference itself cannot be built in this image (no cargo/rustc)",
-    }))
+    })
 
 
 def workload_config(wl, per_gpu, args, extra=None):
@@ -326,8 +326,25 @@ def oracle_parity(bc, leg, n, workdir, threads):
     return ok
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Libraries print to stdout (NCCL its version, torchrun its banner): keep stdout for the ONE JSON line."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -456,7 +473,7 @@ def main():
         pleg.close()
         if not int(flag.item()):
             if rank == 0:
-                print(json.dumps({"error": "N-rank result differs from the single-GPU result", "parity_n_ranks": parity_n}))
+                emit_json({"error": "N-rank result differs from the single-GPU result", "parity_n_ranks": parity_n})
             dist.destroy_process_group()
             sys.exit(1)
 
@@ -579,7 +596,7 @@ def main():
             "other_configs": others,
         }
         line.update(extras)
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

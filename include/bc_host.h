@@ -34,6 +34,9 @@ typedef struct {
 /* Parses the three input files and derives the caps; on failure returns NULL and writes the message. */
 bch_run *bch_open(const bch_args *args, char *err, int errlen);
 void bch_close(bch_run *run);
+/* Tuning / test switches of the host side (results never change).  "lean_writer_min_rows": count tables of at least this
+ * many rows are written by the streaming CSV writer (text straight from the packed keys on all host threads; default 4 M). */
+int bch_set_option(bch_run *run, const char *name, long long value);
 /* The reference rewrites "Total sequences: N" in place while it reads (input.rs:54-57, 151-158): fn is called with the
  * number of records handed to the GPU so far, after every batch of bch_count_fastq[_multi]. */
 typedef void (*bch_progress_fn)(uint64_t reads_so_far, void *user);

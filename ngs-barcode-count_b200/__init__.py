@@ -173,6 +173,7 @@ _PROTOS = {
     "bch_open": (C.c_void_p, [C.POINTER(bch_args), C.c_char_p, C.c_int]),
     "bch_close": (None, [C.c_void_p]),
     "bch_set_progress": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bch_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
     "bch_config": (C.POINTER(bc_config), [C.c_void_p]),
     "bch_describe": (C.c_char_p, [C.c_void_p]),
     "bch_barcode_num": (C.c_uint32, [C.c_void_p]),
@@ -259,6 +260,10 @@ class Run:
 
     def describe(self):
         return lib().bch_describe(self.h).decode()
+
+    def set_option(self, name, value):
+        if lib().bch_set_option(self.h, name.encode(), int(value)) != 0:
+            raise BcError(f"bch_set_option: unknown option {name!r}")
 
     def jit_check(self):
         """Compiles the run's specialised decode kernel with NVRTC (no GPU needed) -> (ok, log)"""

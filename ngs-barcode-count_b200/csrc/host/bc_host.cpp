@@ -361,6 +361,7 @@ struct bch_run {
     IngestBuffers ingest;
     bch_progress_fn progress = nullptr;  // called with the running number of records after every batch
     void* progress_user = nullptr;
+    uint64_t lean_rows = 4u << 20;  // tables of at least this many rows go through the lean CSV writer (bch_set_option)
     int multi_mode = 0;  // after bch_count_fastq_multi: 1 = rows partitioned over the contexts, 2 = all rows on the first
 };
 
@@ -1245,6 +1246,12 @@ bch_run* bch_open(const bch_args* args, char* err, int errlen) {
 }
 
 void bch_close(bch_run* run) { delete run; }
+int bch_set_option(bch_run* run, const char* name, long long value) {
+    if (!run || !name) return BC_EINVAL;
+    if (!strcmp(name, "lean_writer_min_rows") && value >= 0) run->lean_rows = (uint64_t)value;
+    else return BC_EINVAL;
+    return BC_OK;
+}
 void bch_set_progress(bch_run* run, bch_progress_fn fn, void* user) {
     if (!run) return;
     run->progress = fn;
@@ -1469,12 +1476,20 @@ int bch_write_counts_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const c
         const size_t nb = run->counted.size();
         bool merge = merge_output != 0;
         bool do_enrich = enrich != 0 && nb >= 2;  // main.rs:22-25
-        std::vector<DecodedRow> rows;
+        // the rows of every context that holds some (pinned memory owned by the contexts, valid until their next bc_finish)
+        std::vector<bc_table> tabs((size_t)n_src);
+        uint64_t n_total = 0;
         for (int r = 0; r < n_src; r++) {
-            if (bc_finish(ctxs[r], &full) != BC_OK) throw Error(bc_last_error(ctxs[r]));
-            decode_rows(*run, ctx, full, rows);
-            bc_table_free(&full);
+            if (bc_finish(ctxs[r], &tabs[(size_t)r]) != BC_OK) throw Error(bc_last_error(ctxs[r]));
+            n_total += tabs[(size_t)r].n_rows;
         }
+        // Large tables are written by write_full_lean (below): text straight from the packed keys on all host threads, no
+        // per-row strings or maps.  The merged file needs every sample's count of a compound side by side, i.e. a map
+        // over all rows (as in the reference, output.rs:286-300), so --merge-output keeps the map-based path.
+        const bool lean = n_total >= run->lean_rows && !(merge && (run->have_sample_file ? run->slots[run->sample_slot].dna.size() > 1 : run->sample_slot >= 0));
+        std::vector<DecodedRow> rows;
+        if (!lean)
+            for (const bc_table& t : tabs) decode_rows(*run, ctx, t, rows);
 
         // sample list and its order (output.rs:77-97): with a sample file every listed sample gets files (Q16) and the
         // order is by sample ID; otherwise the samples seen, ordered by DNA for reproducibility
@@ -1490,6 +1505,17 @@ int bch_write_counts_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const c
             }
         } else if (run->sample_slot >= 0) {
             std::set<std::string> seen;
+            if (lean) {
+                const uint32_t ns = (uint32_t)run->slots.size(), stride = BC_MAX_REF_LEN + 1;
+                std::vector<int32_t> idx(ns);
+                std::vector<char> str((size_t)ns * stride);
+                for (const bc_table& t : tabs)
+                    for (uint64_t r = 0; r < t.n_rows; r++) {
+                        if (bc_key_decode(ctx, t.key_lo[r], t.key_hi ? t.key_hi[r] : 0, 0, 0, idx.data(), str.data(), stride) != BC_OK)
+                            throw Error("bc_key_decode failed");
+                        seen.insert(str.data() + (size_t)run->sample_slot * stride);
+                    }
+            }
             for (const DecodedRow& r : rows) seen.insert(r.sample);
             for (const std::string& s : seen) {
                 samples.push_back(s);
@@ -1579,7 +1605,100 @@ int bch_write_counts_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const c
             }
         };
 
-        emit(rows, true, "");
+        // The Full family of a large table: every host thread turns a chunk of packed rows into text lines, one buffer per
+        // sample; a sample's file is then its chunks one after the other.  Files of up to kSortRows rows are still written
+        // byte-sorted; larger ones in the order the GPU produced the rows (the reference writes its hash map's order, Q17).
+        auto write_full_lean = [&]() {
+            const uint32_t ns = (uint32_t)run->slots.size(), stride = BC_MAX_REF_LEN + 1;
+            const size_t kChunk = 1u << 18, kSortRows = 4u << 20, n_samples = samples.size();
+            std::vector<size_t> pos_of_idx;  // sample reference index -> position in `samples`
+            if (run->have_sample_file) {
+                const SlotInfo& S = run->slots[run->sample_slot];
+                pos_of_idx.resize(S.dna.size());
+                for (size_t i = 0; i < S.dna.size(); i++) pos_of_idx[i] = sample_pos.at(S.dna[i]);
+            }
+            struct Chunk { const bc_table* t; uint64_t a, b; };
+            std::vector<Chunk> chunks;
+            for (const bc_table& t : tabs)
+                for (uint64_t a = 0; a < t.n_rows; a += kChunk) chunks.push_back(Chunk{&t, a, std::min<uint64_t>(t.n_rows, a + kChunk)});
+            std::vector<std::vector<std::string>> text(chunks.size(), std::vector<std::string>(n_samples));
+            std::vector<std::vector<uint64_t>> lines(chunks.size(), std::vector<uint64_t>(n_samples, 0));
+            std::atomic<int> failed{0};
+            Pool pool(std::max(1u, std::thread::hardware_concurrency()));
+            pool.run(chunks.size(), [&](size_t c) {
+                std::vector<int32_t> idx(ns);
+                std::vector<char> str((size_t)ns * stride);
+                char num[24];
+                const bc_table& t = *chunks[c].t;
+                for (uint64_t r = chunks[c].a; r < chunks[c].b; r++) {
+                    if (bc_key_decode(ctx, t.key_lo[r], t.key_hi ? t.key_hi[r] : 0, 0, 0, idx.data(), str.data(), stride) != BC_OK) {
+                        failed = 1;
+                        return;
+                    }
+                    size_t si = 0;
+                    if (run->have_sample_file) si = pos_of_idx[(size_t)idx[run->sample_slot]];
+                    else if (run->sample_slot >= 0) si = sample_pos.at(str.data() + (size_t)run->sample_slot * stride);
+                    std::string& out = text[c][si];
+                    for (size_t k = 0; k < nb; k++) {
+                        const int s = run->counted[k];
+                        if (k) out.push_back(',');
+                        if (run->have_counted_file) out += run->slots[s].name[(size_t)idx[s]];
+                        else out += str.data() + (size_t)s * stride;
+                    }
+                    const int len = snprintf(num, sizeof num, ",%llu\n", (unsigned long long)t.count[r]);
+                    out.append(num, (size_t)len);
+                    lines[c][si]++;
+                }
+            });
+            if (failed) throw Error("bc_key_decode failed");
+            for (size_t si = 0; si < n_samples; si++) {
+                uint64_t n_lines = 0;
+                size_t bytes = 0;
+                for (size_t c = 0; c < chunks.size(); c++) {
+                    n_lines += lines[c][si];
+                    bytes += text[c][si].size();
+                }
+                const std::string name = pre + "_" + sample_names[si] + "_counts.csv";
+                std::string path = dir;
+                if (!path.empty() && path.back() != '/') path.push_back('/');
+                std::ofstream out(path + name, std::ios::binary);
+                if (!out) throw Error("cannot create " + path + name);
+                out << header << ",Count\n";
+                if (n_lines <= kSortRows) {
+                    std::string all;
+                    all.reserve(bytes);
+                    for (size_t c = 0; c < chunks.size(); c++) {
+                        all += text[c][si];
+                        std::string().swap(text[c][si]);
+                    }
+                    std::vector<std::pair<const char*, size_t>> ls;
+                    ls.reserve(n_lines);
+                    for (size_t p = 0; p < all.size();) {
+                        const size_t e = all.find('\n', p);
+                        ls.emplace_back(all.data() + p, e - p);
+                        p = e + 1;
+                    }
+                    std::sort(ls.begin(), ls.end(), [](const std::pair<const char*, size_t>& x, const std::pair<const char*, size_t>& y) {
+                        const int c = memcmp(x.first, y.first, std::min(x.second, y.second));
+                        return c ? c < 0 : x.second < y.second;
+                    });
+                    for (const auto& l : ls) {
+                        out.write(l.first, (std::streamsize)l.second);
+                        out.put('\n');
+                    }
+                } else {
+                    for (size_t c = 0; c < chunks.size(); c++) {
+                        out.write(text[c][si].data(), (std::streamsize)text[c][si].size());
+                        std::string().swap(text[c][si]);
+                    }
+                }
+                if (!out) throw Error("write failed: " + path + name);
+                names.push_back(name + "\t" + std::to_string(n_lines));
+            }
+        };
+
+        if (lean) write_full_lean();
+        else emit(rows, true, "");
         if (do_enrich) {
             std::vector<DecodedRow> srows, drows;
             // the owners' marginals add up: on the device when they are dense counter arrays, else row by row in emit()

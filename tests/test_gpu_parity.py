@@ -117,6 +117,27 @@ def test_golden_specialized_kernel(case, tmp_path):
 
 
 @pytest.mark.parametrize("case", golden_cases())
+def test_golden_lean_csv_writer(case, tmp_path):
+    """Large count tables are written by the streaming writer (text straight from the packed keys on all host threads);
+    forced here for every golden case: same CSV set (it steps aside by itself when a merged file is due)."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    run.set_option("lean_writer_min_rows", 0)
+    ctr = bc.Counter(run)
+    reads = read_fastq(paths["fastq"])
+    ctr.submit(run.pack([r[0] for r in reads], [r[1] for r in reads]))
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+    # without --merge-output every case goes through it, whatever its sample barcodes are
+    out2 = tmp_path / "nomerge"
+    out2.mkdir()
+    ctr.write_counts(str(out2), "golden", merge=False, enrich=fl["enrich"])
+    want = {fn: lines for fn, lines in exp["files"].items() if "_counts.all" not in fn}
+    assert_same_csv_set(read_csv_dir(str(out2), "golden"), want)
+
+
+@pytest.mark.parametrize("case", golden_cases())
 def test_golden_fastq_ingest_small_batches(case, tmp_path):
     """bch_count_fastq (the read_fastq replacement) with batches far smaller than the file: pinned double
     buffering, staging reuse and table growth are all exercised."""
