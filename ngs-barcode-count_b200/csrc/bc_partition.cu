@@ -27,7 +27,20 @@ namespace {
 
 constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
 constexpr int kRedThreads = 256;
-constexpr uint32_t kTableSlots = 4096;  // u32 slots holding key-store indices
+// (the BC_* macros exist so that tools/build_variants.py can compile alternatives for A/B timing; the defaults ship)
+#ifndef BC_TABLE_SLOTS
+#define BC_TABLE_SLOTS 4096
+#endif
+#ifndef BC_CHAIN_LIMIT
+#define BC_CHAIN_LIMIT 40
+#endif
+#ifndef BC_SCATTER_IPT
+#define BC_SCATTER_IPT 16
+#endif
+#ifndef BC_REDUCE_BLOCKS
+#define BC_REDUCE_BLOCKS 4
+#endif
+constexpr uint32_t kTableSlots = BC_TABLE_SLOTS;  // u32 slots holding key-store indices
 constexpr uint32_t kKeyCap = 2048;      // distinct keys a CTA can hold (narrow 48 KB, wide 64 KB of shared memory: 4 / 3 CTAs per SM)
 constexpr int kRedLoads = kKeyCap / kRedThreads;  // items per thread of a partition that fits the key store
 
@@ -369,7 +382,7 @@ __device__ __forceinline__ void clear_u32(uint32_t* p, uint32_t n, uint32_t valu
 //   fine for the usual one to a few random barcodes per key, quadratic for a key with hundreds.  A lane that has walked
 //   kChainLimit slots for one record gives the partition up: nothing is emitted, its number goes on `hot_list`, and a
 //   second launch puts the listed partitions through the two-pass RED_DEDUPE, whose cost does not depend on the keys.
-constexpr uint32_t kChainLimit = 40;
+constexpr uint32_t kChainLimit = BC_CHAIN_LIMIT;
 
 template <bool WIDE, int MODE>
 __device__ __forceinline__ void reduce_one(const unsigned long long p, const ItemView& in, const uint32_t* __restrict__ starts,
@@ -656,7 +669,7 @@ __device__ __forceinline__ void reduce_one(const unsigned long long p, const Ite
 // One CTA per partition; or, with `list`, persistent CTAs over the partitions listed on the device (the hot partitions the
 // keyed pass gave up on: their number is only known there).
 template <bool WIDE, int MODE>
-__global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : 4)
+__global__ void __launch_bounds__(kRedThreads, WIDE ? 3 : BC_REDUCE_BLOCKS)
     k_reduce(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_items, const uint32_t chunk,
              const uint32_t umi_bits, const ItemView out, const unsigned long long out_cap, FlushStats* stats,
              const uint32_t skip_over, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_n, uint32_t* hot_list,
@@ -758,7 +771,7 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
     if (n_total == 0) return cudaSuccess;
     if (lv.F > (1u << kSplitMaxBits) || lv.F == 0) return cudaErrorInvalidValue;
     const bool weighted = in.w != nullptr;
-    const unsigned long long tile = scatter ? (unsigned long long)kScatterThreads * ((wide || weighted) ? 8 : 16) : (unsigned long long)kSplitThreads * 16;
+    const unsigned long long tile = scatter ? (unsigned long long)kScatterThreads * ((wide || weighted) ? 8 : BC_SCATTER_IPT) : (unsigned long long)kSplitThreads * 16;
     // single segment: one worker per tile, at most a few waves; many segments: a few workers each
     unsigned long long workers;
     if (!seg_starts) {
@@ -782,7 +795,7 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
     if (wide) return weighted ? launch_scatter_t<true, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
                               : launch_scatter_t<true, false, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
     return weighted ? launch_scatter_t<false, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
-                    : launch_scatter_t<false, false, 16, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
+                    : launch_scatter_t<false, false, BC_SCATTER_IPT, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
 }
 
 // Exchange step of a multi-GPU job: this rank's records -> their owners' receive buffers.  owner = digit of `lv`
