@@ -135,6 +135,38 @@ uint32_t bc_plane_words(uint32_t max_read_len);
 uint32_t bc_plane_stride(uint32_t max_read_len);
 uint32_t bc_qual_stride(uint32_t max_read_len);
 
+/* Transfer form of a HOST batch ("wire batch"): the same reads as a bc_batch in fewer bytes, for the PCIe crossing that
+ * bounds the end-to-end rate (DEL, 150-nt reads with quality: 218 -> 159 bytes per read).  bc_submit_wire copies the arrays
+ * as they are and expands them on the device into the bc_batch layout before the decode kernel runs; results are those
+ * of bc_submit on the equivalent bc_batch.  Geometry: W = bc_plane_words(max_read_len).
+ *   lohi    : n_reads records of 2W words — the lo plane, then the hi plane (both 0 where the read has 'N').
+ *   read_len: as in bc_batch (bit 15 = BC_READ_UNSUPPORTED).
+ *   N calls : either `nmask`, n_reads records of W words (the N plane), or — nmask == NULL — a list of n_calls
+ *             (n_read[i] = read index in the batch, n_pos[i] = base position) pairs; the list pays when N calls are
+ *             rarer than one per ~3W/2 reads' worth of plane words, which is every real run.
+ *   qual    : the first bc_wire_qual_codes(max_read_len) quality characters of every read as `qual_bits`-bit codes,
+ *             code i at bits [i * qual_bits, (i + 1) * qual_bits) of the record's little-endian bit stream, records of
+ *             qual_stride = bc_wire_qual_stride(max_read_len, qual_bits) bytes.  qual_bits 8: the characters themselves;
+ *             6: character - 33 (characters '!' .. '_'; code 63 stands for the byte 0xFF that the packer writes where a
+ *             quality line ends before its sequence, see bc_batch / parse.rs:338-343); 4 and 2: index into qual_dict
+ *             (instruments that bin their qualities emit 4 to 8 distinct characters).  Ignored when min_quality == 0. */
+typedef struct {
+    uint32_t n_reads;
+    uint32_t max_read_len;
+    uint32_t qual_bits;
+    uint32_t qual_stride;
+    uint32_t n_calls;
+    uint8_t qual_dict[16];
+    const uint32_t *lohi;
+    const uint16_t *read_len;
+    const uint32_t *nmask;
+    const uint32_t *n_read;
+    const uint16_t *n_pos;
+    const uint8_t *qual;
+} bc_wire_batch;
+uint32_t bc_wire_qual_codes(uint32_t max_read_len);                 /* max_read_len rounded up to a multiple of 4 */
+uint32_t bc_wire_qual_stride(uint32_t max_read_len, uint32_t bits); /* bytes per read, a multiple of 4 */
+
 typedef struct bc_ctx bc_ctx;
 
 /* Replaces the construction of the worker pool (main.rs:93-113, parse.rs:28-52) and of Results/SequenceErrors
@@ -158,6 +190,9 @@ int bc_set_stream(bc_ctx *ctx, void *cuda_stream);
  * (info.rs:735-808) and the outcome counters.  Asynchronous; host batches are copied through internal pinned
  * staging.  Batch memory may be rewritten after bc_wait_copies (host batches) / bc_sync (device batches). */
 int bc_submit(bc_ctx *ctx, const bc_batch *batch);
+/* bc_submit for a host batch in its transfer form (see bc_wire_batch).  Asynchronous; the arrays may be rewritten after
+ * bc_wait_copies. */
+int bc_submit_wire(bc_ctx *ctx, const bc_wire_batch *batch);
 int bc_sync(bc_ctx *ctx);
 /* Blocks until the host->device copies of every submitted host batch are done (their memory may then be
  * rewritten) without waiting for the kernels. */

@@ -35,7 +35,8 @@ typedef struct {
 bch_run *bch_open(const bch_args *args, char *err, int errlen);
 void bch_close(bch_run *run);
 /* Tuning / test switches of the host side (results never change).  "lean_writer_min_rows": count tables of at least this
- * many rows are written by the streaming CSV writer (text straight from the packed keys on all host threads; default 4 M). */
+ * many rows are written by the streaming CSV writer (text straight from the packed keys on all host threads; default 4 M);
+ * "wire_batches": 0 makes bch_count_fastq hand the GPU plain bc_batch arrays instead of the transfer form (default 1). */
 int bch_set_option(bch_run *run, const char *name, long long value);
 /* The reference rewrites "Total sequences: N" in place while it reads (input.rs:54-57, 151-158): fn is called with the
  * number of records handed to the GPU so far, after every batch of bch_count_fastq[_multi]. */
@@ -60,6 +61,19 @@ int bch_pack(uint32_t max_read_len, uint32_t n, const char *const *seqs, const c
 /* Same, for reads given as one '\n'-separated text block each (convenient from ctypes). */
 int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, const char *qual_lines, uint32_t *planes_out,
                    uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
+
+/* The transfer form of a host batch (bc_wire_batch, bc_submit_wire): bch_wire_from_batch converts a host bc_batch of
+ * geometry max_read_len into arrays laid out in `buf` (at least bch_wire_bound bytes; pinned memory for full-rate copies)
+ * and fills *out with pointers into it.  qual_bits = 0 picks the narrowest quality form that holds every character of the
+ * batch (2 or 4 bits with a dictionary, 6 bits, or plain bytes); 2 / 4 / 6 / 8 ask for that form (BC_EINVAL when the
+ * batch does not fit it).  bch_count_fastq packs reads straight into this form (6-bit quality, N calls as a list). */
+size_t bch_wire_bound(uint32_t n_reads, uint32_t max_read_len, int with_qual);
+int bch_wire_from_batch(const bc_batch *batch, uint32_t max_read_len, uint32_t qual_bits, void *buf, size_t buf_bytes,
+                        bc_wire_batch *out);
+/* Wall time of the phases of the last bch_count_fastq[_multi] on the ingest thread: seconds[5] = split (record framing),
+ * pack, submit calls, waiting for copies / the GPU, total; counts[3] = batches, batches whose quality went as plain bytes,
+ * batches whose N calls went as a dense plane. */
+int bch_ingest_stats(const bch_run *run, double *seconds, uint64_t *counts);
 
 /* Host-only test hook of the record framing (input.rs:115-148): streams a .fastq / .fastq.gz file (plain, gzip with any
  * number of members, or bgzip — whose members are inflated on `threads` host threads) through the same block reader

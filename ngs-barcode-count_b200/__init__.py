@@ -50,6 +50,12 @@ class bc_batch(C.Structure):
                 ("location", C.c_int32), ("planes", C.c_void_p), ("read_len", C.c_void_p), ("qual", C.c_void_p)]
 
 
+class bc_wire_batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("max_read_len", C.c_uint32), ("qual_bits", C.c_uint32), ("qual_stride", C.c_uint32),
+                ("n_calls", C.c_uint32), ("qual_dict", C.c_uint8 * 16), ("lohi", C.c_void_p), ("read_len", C.c_void_p),
+                ("nmask", C.c_void_p), ("n_read", C.c_void_p), ("n_pos", C.c_void_p), ("qual", C.c_void_p)]
+
+
 class bc_locate_out(C.Structure):
     _fields_ = [("status", C.c_void_p), ("offset", C.c_void_p), ("repaired", C.c_void_p)]
 
@@ -140,6 +146,9 @@ _PROTOS = {
     "bc_last_error": (C.c_char_p, [C.c_void_p]),
     "bc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_submit": (C.c_int, [C.c_void_p, C.POINTER(bc_batch)]),
+    "bc_wire_qual_codes": (C.c_uint32, [C.c_uint32]),
+    "bc_wire_qual_stride": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "bc_submit_wire": (C.c_int, [C.c_void_p, C.POINTER(bc_wire_batch)]),
     "bc_sync": (C.c_int, [C.c_void_p]),
     "bc_wait_copies": (C.c_int, [C.c_void_p]),
     "bc_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -182,6 +191,9 @@ _PROTOS = {
     "bch_pack": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_uint]),
     "bch_pack_lines": (C.c_int, [C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "bch_wire_bound": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_int]),
+    "bch_wire_from_batch": (C.c_int, [C.POINTER(bc_batch), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(bc_wire_batch)]),
+    "bch_ingest_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "bch_scan_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p,
                                  C.c_int]),
     "bch_split_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
@@ -322,6 +334,34 @@ class Batch:
         return Batch(self.n, self.plane_stride, self.qual_stride, t(self.planes), t(self.read_len), t(self.qual), True)
 
 
+class WireBatch:
+    """A host Batch in its transfer form (bc_wire_batch): lo / hi planes, N calls as a list (or a dense plane), quality
+    characters as 8-, 6-, 4- or 2-bit codes, all inside one buffer — `buf` if given (a uint8 numpy array, e.g. the view
+    of a pinned torch tensor, of at least WireBatch.bound(...) bytes), else a fresh numpy array."""
+
+    @staticmethod
+    def bound(n, max_read_len, with_qual):
+        return int(lib().bch_wire_bound(n, max_read_len, int(with_qual)))
+
+    def __init__(self, batch, max_read_len, qual_bits=0, buf=None):
+        if batch.device:
+            raise BcError("WireBatch: the transfer form is made from a host batch")
+        need = self.bound(batch.n, max_read_len, batch.qual is not None)
+        self.buf = np.zeros(max(need, 1), np.uint8) if buf is None else buf
+        self.n, self.max_read_len = batch.n, max_read_len
+        self.c = bc_wire_batch()
+        b = batch.c_struct()
+        rc = lib().bch_wire_from_batch(C.byref(b), max_read_len, qual_bits, _ptr(self.buf), self.buf.nbytes, C.byref(self.c))
+        if rc != 0:
+            raise BcError(f"bch_wire_from_batch failed ({rc}): the batch does not fit the requested form")
+        w = lib().bc_plane_words(max_read_len)
+        dense = bool(self.c.nmask)
+        self.nbytes = (batch.n * (2 * w * 4 + 2) + (batch.n * w * 4 if dense else self.c.n_calls * 6) + batch.n * self.c.qual_stride)
+
+    def c_struct(self):
+        return self.c
+
+
 class Counter:
     """One GPU's decode-and-count context (bc_ctx): stands where the reference has its SequenceParser worker pool,
     the shared Results and the SequenceErrors counters (parse.rs:28-76, info.rs:16-139, 661-808)."""
@@ -357,7 +397,10 @@ class Counter:
 
     def submit(self, batch):
         b = batch.c_struct()
-        self._ck(lib().bc_submit(self.h, C.byref(b)), "bc_submit")
+        if isinstance(batch, WireBatch):
+            self._ck(lib().bc_submit_wire(self.h, C.byref(b)), "bc_submit_wire")
+        else:
+            self._ck(lib().bc_submit(self.h, C.byref(b)), "bc_submit")
 
     def sync(self):
         self._ck(lib().bc_sync(self.h), "bc_sync")
@@ -446,6 +489,13 @@ class Counter:
         if rc != 0:
             raise BcError("bch_count_fastq: " + err.value.decode())
         return total.value
+
+    def ingest_stats(self):
+        """phases of the last count_fastq on the ingest thread (seconds) and its batch counts"""
+        sec, cnt = (C.c_double * 5)(), (C.c_uint64 * 3)()
+        lib().bch_ingest_stats(self.run.h, sec, cnt)
+        return dict(split_s=sec[0], pack_s=sec[1], submit_s=sec[2], wait_s=sec[3], total_s=sec[4], batches=int(cnt[0]),
+                    batches_qual8=int(cnt[1]), batches_dense_n=int(cnt[2]))
 
     def write_counts(self, outdir, prefix, merge=False, enrich=False):
         names = C.create_string_buffer(1 << 20)

@@ -125,6 +125,18 @@ struct bc_ctx {
     unsigned long long* d_stripes = nullptr;   // k_decode's striped copies of them, folded in after every launch
     // staging for host batches
     Staging staging[2];
+    // host batches in their transfer form (bc_submit_wire): two arenas that alternate like `staging`, and the one set of
+    // expanded arrays the decode kernel reads (written and read on the main stream, so one set is enough)
+    struct WireStage {
+        unsigned char* buf = nullptr;
+        size_t cap = 0;
+        cudaEvent_t free_ev = nullptr, copied_ev = nullptr;
+    } wire[2];
+    int wire_cur = 0;
+    uint32_t* x_planes = nullptr;
+    uint16_t* x_len = nullptr;
+    uint8_t* x_qual = nullptr;
+    size_t x_cap_planes = 0, x_cap_len = 0, x_cap_qual = 0;
     int cur = 0;
     bool copies_pending = false;
     // scratch for the test hooks
@@ -507,6 +519,14 @@ void bc_destroy(bc_ctx* ctx) {
         if (s.free_ev) cudaEventDestroy(s.free_ev);
         if (s.copied_ev) cudaEventDestroy(s.copied_ev);
     }
+    for (bc_ctx::WireStage& s : ctx->wire) {
+        if (s.buf) cudaFree(s.buf);
+        if (s.free_ev) cudaEventDestroy(s.free_ev);
+        if (s.copied_ev) cudaEventDestroy(s.copied_ev);
+    }
+    if (ctx->x_planes) cudaFree(ctx->x_planes);
+    if (ctx->x_len) cudaFree(ctx->x_len);
+    if (ctx->x_qual) cudaFree(ctx->x_qual);
     if (ctx->d_refs) cudaFree(ctx->d_refs);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_hash_keys) cudaFree(ctx->d_hash_keys);
@@ -1113,6 +1133,110 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
 int bc_submit(bc_ctx* ctx, const bc_batch* batch) {
     if (!ctx) return BC_EINVAL;
     return run_decode(ctx, batch, ctx->deferred ? F_APPEND : F_INSERT, DecodeOut{}, ctx->d_counters);
+}
+
+uint32_t bc_wire_qual_codes(uint32_t max_read_len) { return (max_read_len + 3u) & ~3u; }
+uint32_t bc_wire_qual_stride(uint32_t max_read_len, uint32_t bits) {
+    return (uint32_t)(((unsigned long long)bc_wire_qual_codes(max_read_len) * bits + 31) / 32 * 4);
+}
+
+// A host batch in its transfer form: copied to the device as it is (fewer bytes across PCIe), expanded there into the
+// bc_batch layout, then decoded like any device batch.
+int bc_submit_wire(bc_ctx* ctx, const bc_wire_batch* wb) {
+    if (!ctx) return BC_EINVAL;
+    if (!wb) return fail(ctx, BC_EINVAL, "wire batch is NULL");
+    if (wb->n_reads == 0) return BC_OK;
+    const uint32_t mrl = wb->max_read_len, W = bc_plane_words(mrl);
+    if (mrl == 0 || mrl > BC_MAX_READ_LEN) return fail(ctx, BC_EINVAL, "wire batch: max_read_len %u", mrl);
+    if (!wb->lohi || !wb->read_len) return fail(ctx, BC_EINVAL, "wire batch: lohi / read_len is NULL");
+    if (!wb->nmask && wb->n_calls && (!wb->n_read || !wb->n_pos)) return fail(ctx, BC_EINVAL, "wire batch: n_calls > 0 but no list");
+    const bool want_qual = ctx->quality_on;
+    const uint32_t bits = wb->qual_bits;
+    if (want_qual) {
+        if (!wb->qual) return fail(ctx, BC_EINVAL, "min_quality > 0 but the wire batch has no quality codes");
+        if (bits != 8 && bits != 6 && bits != 4 && bits != 2) return fail(ctx, BC_EINVAL, "wire batch: qual_bits %u (8, 6, 4 or 2)", bits);
+        if (wb->qual_stride != bc_wire_qual_stride(mrl, bits))
+            return fail(ctx, BC_EINVAL, "wire batch: qual_stride %u is not bc_wire_qual_stride(%u, %u)", wb->qual_stride, mrl, bits);
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = wb->n_reads;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const bool dense_n = wb->nmask != nullptr;
+    const size_t b_lohi = n * 2 * W * 4, b_len = n * 2, b_nm = dense_n ? n * W * 4 : 0, b_nr = dense_n ? 0 : (size_t)wb->n_calls * 4,
+                 b_np = dense_n ? 0 : (size_t)wb->n_calls * 2, b_q = want_qual ? n * wb->qual_stride : 0;
+    const size_t o_lohi = 0, o_len = o_lohi + up(b_lohi), o_nm = o_len + up(b_len), o_nr = o_nm + up(b_nm), o_np = o_nr + up(b_nr),
+                 o_q = o_np + up(b_np), need = o_q + up(b_q);
+    bc_ctx::WireStage& s = ctx->wire[ctx->wire_cur];
+    ctx->wire_cur ^= 1;
+    if (!s.free_ev) {
+        CK(ctx, cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&s.copied_ev, cudaEventDisableTiming));
+    }
+    if (s.cap < need) {
+        CK(ctx, cudaEventSynchronize(s.free_ev));
+        if (s.buf) cudaFree(s.buf);
+        s.buf = nullptr;
+        s.cap = need + need / 8;
+        CK(ctx, cudaMalloc(&s.buf, s.cap));
+    }
+    // the expanded arrays: the batch's own geometry (like a device bc_batch)
+    const uint32_t ps = bc_plane_stride(mrl), qs = bc_qual_stride(mrl);
+    const size_t xb_p = n * ps * 4, xb_l = n * 2, xb_q = want_qual ? n * qs : 0;
+    if (ctx->x_cap_planes < xb_p || ctx->x_cap_len < xb_l || ctx->x_cap_qual < xb_q) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));  // an earlier batch's kernels may still read them
+        if (ctx->x_planes) cudaFree(ctx->x_planes);
+        if (ctx->x_len) cudaFree(ctx->x_len);
+        if (ctx->x_qual) cudaFree(ctx->x_qual);
+        ctx->x_planes = nullptr; ctx->x_len = nullptr; ctx->x_qual = nullptr;
+        ctx->x_cap_planes = std::max(ctx->x_cap_planes, xb_p + xb_p / 8);
+        ctx->x_cap_len = std::max(ctx->x_cap_len, xb_l + xb_l / 8);
+        ctx->x_cap_qual = std::max(ctx->x_cap_qual, xb_q + xb_q / 8);
+        CK(ctx, cudaMalloc(&ctx->x_planes, ctx->x_cap_planes));
+        CK(ctx, cudaMalloc(&ctx->x_len, ctx->x_cap_len));
+        if (want_qual) CK(ctx, cudaMalloc(&ctx->x_qual, ctx->x_cap_qual));
+    }
+    CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, s.free_ev, 0));
+    auto h2d = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(s.buf + off, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream) : cudaSuccess;
+    };
+    CK(ctx, h2d(o_lohi, wb->lohi, b_lohi));
+    CK(ctx, h2d(o_len, wb->read_len, b_len));
+    CK(ctx, h2d(o_nm, wb->nmask, b_nm));
+    CK(ctx, h2d(o_nr, wb->n_read, b_nr));
+    CK(ctx, h2d(o_np, wb->n_pos, b_np));
+    CK(ctx, h2d(o_q, wb->qual, b_q));
+    CK(ctx, cudaEventRecord(s.copied_ev, ctx->copy_stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, s.copied_ev, 0));
+    ctx->prof.h2d_bytes += b_lohi + b_len + b_nm + b_nr + b_np + b_q;
+    ctx->copies_pending = true;
+    WireView v{};
+    v.lohi = reinterpret_cast<const uint32_t*>(s.buf + o_lohi);
+    v.read_len = reinterpret_cast<const uint16_t*>(s.buf + o_len);
+    v.nmask = dense_n ? reinterpret_cast<const uint32_t*>(s.buf + o_nm) : nullptr;
+    v.n_read = reinterpret_cast<const uint32_t*>(s.buf + o_nr);
+    v.n_pos = reinterpret_cast<const uint16_t*>(s.buf + o_np);
+    v.qual = s.buf + o_q;
+    v.n_reads = wb->n_reads;
+    v.W = W;
+    v.n_calls = dense_n ? 0u : wb->n_calls;
+    v.qual_bits = bits;
+    v.qual_stride = wb->qual_stride;
+    v.n_codes = bc_wire_qual_codes(mrl);
+    memcpy(v.dict.c, wb->qual_dict, sizeof v.dict.c);
+    {
+        ProfScope p(ctx, BC_K_OTHER);
+        CK(ctx, launch_wire_expand(v, ctx->x_planes, ctx->x_len, want_qual ? ctx->x_qual : nullptr, ps, qs, ctx->stream));
+    }
+    CK(ctx, cudaEventRecord(s.free_ev, ctx->stream));  // the arena is free once it is expanded
+    bc_batch b{};
+    b.n_reads = wb->n_reads;
+    b.plane_stride = ps;
+    b.qual_stride = qs;
+    b.location = BC_LOC_DEVICE;
+    b.planes = ctx->x_planes;
+    b.read_len = ctx->x_len;
+    b.qual = want_qual ? ctx->x_qual : nullptr;
+    return run_decode(ctx, &b, ctx->deferred ? F_APPEND : F_INSERT, DecodeOut{}, ctx->d_counters);
 }
 
 int bc_set_option(bc_ctx* ctx, const char* name, int value) {

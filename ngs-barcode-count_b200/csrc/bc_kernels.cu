@@ -536,6 +536,96 @@ cudaError_t launch_add_u64(unsigned long long* dst, const unsigned long long* sr
     return cudaGetLastError();
 }
 
+// ---- transfer form of a host batch -> the bc_batch layout the decode kernel reads (include/bc_b200.h: bc_wire_batch) ----
+// What crosses PCIe is the lo / hi planes, the lengths, the N calls (a dense plane, or a list when they are rare) and the
+// quality characters as 8-, 6-, 4- or 2-bit codes.  Three small streaming kernels rebuild the fixed-stride records in HBM;
+// at 8.4 M reads per batch they take well under a millisecond against tens of milliseconds for the copy they shorten.
+__global__ void k_wire_planes(const WireView w, uint32_t* __restrict__ planes, uint16_t* __restrict__ read_len, const uint32_t plane_stride) {
+    const unsigned long long total = (unsigned long long)w.n_reads * w.W;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = i / w.W;
+        const uint32_t k = (uint32_t)(i - r * w.W);
+        uint32_t* rec = planes + r * plane_stride;
+        const uint32_t nm = w.nmask ? w.nmask[i] : 0u;
+        rec[k] = w.lohi[r * 2 * w.W + k] & ~nm;  // lo = hi = 0 where the read has N: the convention of bc_batch
+        rec[w.W + k] = w.lohi[r * 2 * w.W + w.W + k] & ~nm;
+        rec[2 * w.W + k] = nm;
+        if (k == 0) {
+            if (plane_stride > 3 * w.W) rec[3 * w.W] = 0u;  // pad word of an even record
+            read_len[r] = w.read_len[r];
+        }
+    }
+}
+
+// the N calls of the list: one bit set in the N plane, the same bit cleared in lo and hi (entries out of range are ignored)
+__global__ void k_wire_ncalls(const WireView w, uint32_t* __restrict__ planes, const uint32_t plane_stride) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < w.n_calls;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t r = w.n_read[i], pos = w.n_pos[i];
+        if (r >= w.n_reads || pos >= 32 * w.W) continue;
+        uint32_t* rec = planes + (unsigned long long)r * plane_stride;
+        const uint32_t bit = 1u << (pos & 31);
+        atomicOr(&rec[2 * w.W + (pos >> 5)], bit);
+        atomicAnd(&rec[pos >> 5], ~bit);
+        atomicAnd(&rec[w.W + (pos >> 5)], ~bit);
+    }
+}
+
+// one thread per four quality characters of a read: code i of a record sits at bits [i * BITS, (i + 1) * BITS) of its
+// little-endian bit stream
+template <int BITS>
+__global__ void k_wire_qual(const WireView w, uint8_t* __restrict__ qual, const uint32_t qual_stride) {
+    const uint32_t words = qual_stride / 4;  // output words per read
+    const unsigned long long total = (unsigned long long)w.n_reads * words;
+    const uint32_t* dict = reinterpret_cast<const uint32_t*>(w.dict.c);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = i / words;
+        const uint32_t j = (uint32_t)(i - r * words);
+        uint32_t out = 0x21212121u;  // '!' beyond the packed codes
+        if (4 * j < w.n_codes) {
+            const uint8_t* rec = w.qual + r * w.qual_stride;
+            if (BITS == 8) {
+                out = reinterpret_cast<const uint32_t*>(rec)[j];
+            } else {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(rec);
+                const uint32_t bit = 4 * BITS * j, wi = bit >> 5, sh = bit & 31;
+                const uint32_t a = rw[wi], b = (sh + 4 * BITS > 32) ? rw[wi + 1] : 0u;
+                const uint32_t v = __funnelshift_r(a, b, sh);
+                out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t c = (v >> (BITS * k)) & ((1u << BITS) - 1u);
+                    uint32_t ch;
+                    if (BITS == 6) ch = c == 63u ? 0xFFu : c + 33u;
+                    else ch = (dict[c >> 2] >> (8 * (c & 3u))) & 0xFFu;
+                    out |= ch << (8 * k);
+                }
+            }
+        }
+        reinterpret_cast<uint32_t*>(qual + r * qual_stride)[j] = out;
+    }
+}
+
+cudaError_t launch_wire_expand(const WireView& w, uint32_t* planes, uint16_t* read_len, uint8_t* qual, uint32_t plane_stride,
+                               uint32_t qual_stride, cudaStream_t stream) {
+    if (w.n_reads == 0) return cudaSuccess;
+    k_wire_planes<<<grid_for((unsigned long long)w.n_reads * w.W, 256), 256, 0, stream>>>(w, planes, read_len, plane_stride);
+    if (!w.nmask && w.n_calls) k_wire_ncalls<<<grid_for(w.n_calls, 256), 256, 0, stream>>>(w, planes, plane_stride);
+    if (qual) {
+        const unsigned g = grid_for((unsigned long long)w.n_reads * (qual_stride / 4), 256);
+        switch (w.qual_bits) {
+            case 8: k_wire_qual<8><<<g, 256, 0, stream>>>(w, qual, qual_stride); break;
+            case 6: k_wire_qual<6><<<g, 256, 0, stream>>>(w, qual, qual_stride); break;
+            case 4: k_wire_qual<4><<<g, 256, 0, stream>>>(w, qual, qual_stride); break;
+            case 2: k_wire_qual<2><<<g, 256, 0, stream>>>(w, qual, qual_stride); break;
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    return cudaGetLastError();
+}
+
 // empty map: every slot {key = kEmpty, count = 0}
 __global__ void k_clear_map(ulonglong2* __restrict__ slots, const unsigned long long n16, const int wide) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16;

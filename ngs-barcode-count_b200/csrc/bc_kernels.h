@@ -64,6 +64,23 @@ cudaError_t launch_marginals_rows(const MargPlan& plan, uint32_t m_first, uint32
 // dst[i] += src[i] (src may be another GPU's memory)
 cudaError_t launch_add_u64(unsigned long long* dst, const unsigned long long* src, unsigned long long n, cudaStream_t stream);
 
+// A host batch in its transfer form, staged on the device (bc_wire_batch of include/bc_b200.h) -> bc_batch layout
+struct WireDict {
+    uint8_t c[16];
+};
+struct WireView {
+    const uint32_t* lohi;     // n_reads x 2W words
+    const uint16_t* read_len;
+    const uint32_t* nmask;    // n_reads x W words, or nullptr: the N calls come as a list
+    const uint32_t* n_read;
+    const uint16_t* n_pos;
+    const uint8_t* qual;      // packed codes, qual_stride bytes per read (a multiple of 4)
+    uint32_t n_reads, W, n_calls, qual_bits, qual_stride, n_codes;
+    WireDict dict;
+};
+cudaError_t launch_wire_expand(const WireView& w, uint32_t* planes, uint16_t* read_len, uint8_t* qual, uint32_t plane_stride,
+                               uint32_t qual_stride, cudaStream_t stream);
+
 // move every entry of `src` (hash kinds) into `dst`
 cudaError_t launch_rehash(const DevTable& src, const DevTable& dst, cudaStream_t stream);
 

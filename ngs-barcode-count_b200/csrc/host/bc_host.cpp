@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <cstdio>
@@ -305,14 +306,24 @@ struct PinnedBatch {
     uint16_t* read_len = nullptr;
     uint8_t* qual = nullptr;
     size_t cap_planes = 0, cap_qual = 0;  // bytes
+    unsigned char* arena = nullptr;       // transfer form (bc_wire_batch): one allocation, laid out by WireLayout
+    size_t cap_arena = 0;
     ~PinnedBatch() { release(); }
     void release() {
         if (planes) cudaFreeHost(planes);
         if (read_len) cudaFreeHost(read_len);
         if (qual) cudaFreeHost(qual);
+        if (arena) cudaFreeHost(arena);
         planes = nullptr;
         read_len = nullptr;
         qual = nullptr;
+        arena = nullptr;
+        cap_arena = 0;
+    }
+    void alloc_wire(size_t bytes) {
+        release();
+        if (cudaHostAlloc((void**)&arena, bytes, cudaHostAllocDefault) != cudaSuccess) throw Error("cudaHostAlloc failed for the pinned batch buffers");
+        cap_arena = bytes;
     }
     void alloc(uint32_t n, uint32_t max_read_len, bool with_qual) {
         release();
@@ -341,7 +352,12 @@ struct IngestBuffers {
     FastqBlock blocks[2];
     std::shared_ptr<Pool> pool;
     uint32_t batch_reads = 0, mrl = 0;
-    bool with_qual = false;
+    bool with_qual = false, wire = false;
+};
+
+struct IngestStats {  // wall time of the phases of the last ingest, on the ingest thread (bch_ingest_stats)
+    double split_s = 0, pack_s = 0, submit_s = 0, wait_s = 0, total_s = 0;
+    uint64_t batches = 0, batches_qual8 = 0, batches_dense_n = 0, h2d_bytes = 0;
 };
 
 }  // namespace
@@ -362,6 +378,8 @@ struct bch_run {
     bch_progress_fn progress = nullptr;  // called with the running number of records after every batch
     void* progress_user = nullptr;
     uint64_t lean_rows = 4u << 20;  // tables of at least this many rows go through the lean CSV writer (bch_set_option)
+    bool wire_batches = true;       // host batches cross PCIe in their transfer form (bc_submit_wire); 0: as bc_batch
+    IngestStats stats;
     int multi_mode = 0;  // after bch_count_fastq_multi: 1 = rows partitioned over the contexts, 2 = all rows on the first
 };
 
@@ -583,11 +601,8 @@ const bool kHaveAvx2 = false;
 #endif
 
 // one read -> three bit planes + length word (+ quality bytes)
-inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t qlen, uint32_t W, uint32_t* planes, uint16_t* read_len,
-                     uint8_t* qual_out, uint32_t qual_stride) {
-    uint32_t* lo = planes;
-    uint32_t* hi = planes + W;
-    uint32_t* nm = planes + 2 * W;
+// the bases of one read -> W words of each plane; true when the read holds a character outside ACGTN
+inline bool pack_planes(const char* seq, uint32_t len, uint32_t W, uint32_t* lo, uint32_t* hi, uint32_t* nm) {
     bool other = false;
     uint32_t w = 0, base = 0;
 #if defined(__x86_64__)
@@ -596,6 +611,12 @@ inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t q
 #endif
     for (; base < len; base += 32, w++) pack_word_scalar(seq + base, std::min(32u, len - base), &lo[w], &hi[w], &nm[w], &other);
     for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
+    return other;
+}
+
+inline void pack_one(const char* seq, uint32_t len, const char* qual, uint32_t qlen, uint32_t W, uint32_t* planes, uint16_t* read_len,
+                     uint8_t* qual_out, uint32_t qual_stride) {
+    bool other = pack_planes(seq, len, W, planes, planes + W, planes + 2 * W);
     if (3 * W != ((3 * W) | 1u)) planes[3 * W] = 0;  // pad word of an even record
     if (qual_out) {
         // a quality character below '!' underflows the reference's `q - 33` (parse.rs:326, Q13): flag it, never decode it
@@ -640,6 +661,169 @@ bool pack_range(uint32_t max_read_len, const ReadRef* reads, size_t count, uint3
         pack_one(r.seq, r.len, r.qual, r.qlen, W, planes + i * ps, read_len + i, qual ? qual + i * qs : nullptr, qs);
     }
     return ok;
+}
+
+// ---- transfer form (bc_wire_batch, include/bc_b200.h): lo / hi planes, N calls as a list, quality as 6-bit codes ----------
+// One arena per batch; the dense N plane is always written (the list is derived from it and used when it is the smaller).
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct WireLayout {
+    uint32_t W = 0, n_codes = 0, list_cap = 0;
+    size_t o_lohi = 0, o_len = 0, o_nm = 0, o_nr = 0, o_np = 0, o_q = 0, total = 0;
+    WireLayout() = default;
+    WireLayout(size_t n, uint32_t mrl, bool with_qual) {
+        W = bc_plane_words(mrl);
+        n_codes = bc_wire_qual_codes(mrl);
+        list_cap = (uint32_t)std::min<size_t>(n * W * 4 / 6 + 1, 0xFFFFFFF0u);  // beyond this many calls the dense plane is smaller
+        o_lohi = 0;
+        o_len = o_lohi + up256(n * 2 * W * 4);
+        o_nm = o_len + up256(n * 2);
+        o_nr = o_nm + up256(n * W * 4);
+        o_np = o_nr + up256((size_t)list_cap * 4);
+        o_q = o_np + up256((size_t)list_cap * 2);
+        total = o_q + (with_qual ? up256(n * bc_wire_qual_stride(mrl, 8)) : 0);
+    }
+};
+
+// the quality line of one read as the decode kernel wants it (see pack_one), n_codes characters
+inline void qual_chars(const char* qual, uint32_t qlen, uint32_t len, uint32_t n_codes, uint8_t* out) {
+    const uint32_t n = std::min(qlen, len);
+    memcpy(out, qual, n);
+    if (qlen < len) {
+        if (n) out[n - 1] = 0xFF;
+        memset(out + n, 0xFF, n_codes - n);
+    } else {
+        memset(out + len, '!', n_codes - len);
+    }
+}
+
+// n_codes characters (a multiple of 4) -> 6-bit codes: character - 33, 63 for the 0xFF mark.  false: a character does not
+// fit (below '!' is flagged by the caller; '`' and above need the 8-bit form).
+inline bool pack_qual6_scalar(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
+    bool ok = true;
+    for (uint32_t i = 0; i < n_codes; i += 4) {
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint8_t ch = c[i + k];
+            uint32_t code = ch == 0xFF ? 63u : (uint32_t)(uint8_t)(ch - 33);
+            if (ch != 0xFF && code > 62u) {
+                ok = false;
+                code = 0;
+            }
+            v |= code << (6 * k);
+        }
+        out[0] = (uint8_t)v;
+        out[1] = (uint8_t)(v >> 8);
+        out[2] = (uint8_t)(v >> 16);
+        out += 3;
+    }
+    return ok;
+}
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline bool pack_qual6_avx2(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
+    const __m256i k33 = _mm256_set1_epi8(33), k63 = _mm256_set1_epi8(63), k62 = _mm256_set1_epi8(62), kff = _mm256_set1_epi8((char)0xFF);
+    const __m256i mul1 = _mm256_set1_epi16(0x4001), mul2 = _mm256_set1_epi32(0x10000001);
+    const __m256i shuf = _mm256_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1, 0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
+    __m256i bad = _mm256_setzero_si256();
+    uint32_t i = 0;
+    for (; i + 32 <= n_codes; i += 32, out += 24) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(c + i));
+        const __m256i mark = _mm256_cmpeq_epi8(v, kff);
+        __m256i code = _mm256_sub_epi8(v, k33);
+        bad = _mm256_or_si256(bad, _mm256_andnot_si256(mark, _mm256_xor_si256(_mm256_cmpeq_epi8(_mm256_max_epu8(code, k62), k62), kff)));
+        code = _mm256_and_si256(_mm256_blendv_epi8(code, k63, mark), k63);
+        const __m256i m = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code, mul1), mul2), shuf);
+        const __m128i a = _mm256_castsi256_si128(m), b = _mm256_extracti128_si256(m, 1);
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(out), a);
+        const uint32_t a2 = (uint32_t)_mm_extract_epi32(a, 2), b2 = (uint32_t)_mm_extract_epi32(b, 2);
+        memcpy(out + 8, &a2, 4);
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 12), b);
+        memcpy(out + 20, &b2, 4);
+    }
+    bool ok = _mm256_testz_si256(bad, bad) != 0;
+    if (i < n_codes) ok = pack_qual6_scalar(c + i, n_codes - i, out) && ok;
+    return ok;
+}
+#endif
+inline bool pack_qual6(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
+#if defined(__x86_64__)
+    if (kHaveAvx2) return pack_qual6_avx2(c, n_codes, out);
+#endif
+    return pack_qual6_scalar(c, n_codes, out);
+}
+
+// n_codes characters -> `bits`-bit dictionary codes (bits 4 or 2); false: a character is not in the dictionary
+inline bool pack_qual_dict(const uint8_t* c, uint32_t n_codes, const uint8_t* code_of /* 256 entries, 0xFF = absent */, uint32_t bits,
+                           uint8_t* out, uint32_t stride) {
+    memset(out, 0, stride);
+    bool ok = true;
+    for (uint32_t i = 0; i < n_codes; i++) {
+        uint8_t code = code_of[c[i]];
+        if (code == 0xFF) {
+            ok = false;
+            code = 0;
+        }
+        out[(i * bits) >> 3] |= (uint8_t)(code << ((i * bits) & 7));
+    }
+    return ok;
+}
+
+// N plane of reads [first, first + count) -> (read, position) pairs
+inline void list_ncalls(const uint32_t* nmask, uint32_t W, size_t first, size_t count, std::vector<uint32_t>& reads, std::vector<uint16_t>& pos) {
+    for (size_t r = first; r < first + count; r++)
+        for (uint32_t w = 0; w < W; w++) {
+            uint32_t m = nmask[r * W + w];
+            while (m) {
+                reads.push_back((uint32_t)r);
+                pos.push_back((uint16_t)(32 * w + (uint32_t)__builtin_ctz(m)));
+                m &= m - 1;
+            }
+        }
+}
+
+// reads [0, count) of `reads` -> rows [at, at + count) of a wire arena; returns false when a quality character needs
+// the 8-bit form (bits == 6 only).  Too long reads as in pack_range (never strict: the ingest chose the geometry).
+bool pack_range_wire(uint32_t mrl, const WireLayout& L, unsigned char* arena, const ReadRef* reads, size_t at, size_t count, uint32_t bits) {
+    const uint32_t W = L.W, qs = bits ? bc_wire_qual_stride(mrl, bits) : 0;
+    uint32_t* lohi = reinterpret_cast<uint32_t*>(arena + L.o_lohi);
+    uint16_t* rl = reinterpret_cast<uint16_t*>(arena + L.o_len);
+    uint32_t* nm = reinterpret_cast<uint32_t*>(arena + L.o_nm);
+    uint8_t* q = arena + L.o_q;
+    uint8_t chars[BC_MAX_READ_LEN + 32];
+    bool fits = true;
+    for (size_t i = 0; i < count; i++) {
+        const ReadRef& r = reads[i];
+        const size_t row = at + i;
+        uint32_t* lo = lohi + row * 2 * W;
+        if (r.len > mrl || r.len > 0x7FFF) {
+            memset(lo, 0, (size_t)2 * W * 4);
+            memset(nm + row * W, 0, (size_t)W * 4);
+            rl[row] = (uint16_t)BC_READ_UNSUPPORTED;
+            if (bits) {
+                memset(chars, '!', L.n_codes);
+                if (bits == 6) pack_qual6(chars, L.n_codes, q + row * qs);
+                else memcpy(q + row * qs, chars, L.n_codes);
+            }
+            continue;
+        }
+        bool other = pack_planes(r.seq, r.len, W, lo, lo + W, nm + row * W);
+        if (bits) {
+            const uint32_t n = std::min(r.qlen, r.len);
+            unsigned char lowest = 255;
+            for (uint32_t k = 0; k < n; k++) lowest = std::min<unsigned char>(lowest, (unsigned char)r.qual[k]);
+            if (n && lowest < 33) other = true;  // Q13, as pack_one
+            qual_chars(r.qual, r.qlen, r.len, L.n_codes, chars);
+            if (bits == 6) {
+                if (other && lowest < 33) {  // never decoded: any representable characters do
+                    memset(chars, '!', L.n_codes);
+                }
+                fits = pack_qual6(chars, L.n_codes, q + row * qs) && fits;
+            } else {
+                memcpy(q + row * qs, chars, L.n_codes);
+            }
+        }
+        rl[row] = (uint16_t)(r.len | (other ? BC_READ_UNSUPPORTED : 0u));
+    }
+    return fits;
 }
 
 // A persistent pool of host threads: run(n, f) calls f(0) .. f(n-1) on the workers and on the calling thread and returns
@@ -982,13 +1166,25 @@ struct Ingest {
     bool with_qual;
     uint64_t total = 0, n_batches = 0;
 
+    bool wire;
+    std::vector<std::vector<uint32_t>> call_reads;  // N calls per packing task
+    std::vector<std::vector<uint16_t>> call_pos;
+    std::vector<size_t> call_first;
+    IngestStats st;
+    using Clock = std::chrono::steady_clock;
+    static double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+    Clock::time_point t_begin;
+
     Ingest(bch_run* r, bc_ctx* const* c, int n, unsigned threads, uint32_t batch) : run(r), ctxs(c), n_ctx(n), batch_reads(batch) {
         mrl0 = run->cfg.max_read_len;
         with_qual = run->min_quality > 0.0f;
+        wire = run->wire_batches;
+        t_begin = Clock::now();
         IngestBuffers& I = run->ingest;
         if (!I.pool || I.pool->size() != std::max(1u, threads)) I.pool = std::make_shared<Pool>(threads);
         pool = I.pool.get();
-        if (I.batch_reads != batch_reads || I.with_qual != with_qual || I.mrl != mrl0 || (int)I.lanes.size() != n_ctx) {
+        if (I.batch_reads != batch_reads || I.with_qual != with_qual || I.mrl != mrl0 || (int)I.lanes.size() != n_ctx || I.wire != wire) {
+            I.wire = wire;
             I.lanes.clear();
             for (int d = 0; d < n_ctx; d++) I.lanes.emplace_back(new Lane());
             const size_t block_bytes = std::min<size_t>(std::max<size_t>((size_t)batch_reads * (2 * (size_t)mrl0 + 64), 1u << 20), 1u << 30);
@@ -1000,12 +1196,14 @@ struct Ingest {
         for (int d = 0; d < n_ctx; d++) {
             Lane& L = *I.lanes[d];
             const int dev = bc_device_of(ctxs[d]);
-            if (L.pinned[0].planes && L.device == dev) continue;
+            if ((wire ? (void*)L.pinned[0].arena : (void*)L.pinned[0].planes) && L.device == dev) continue;
             L.device = dev;
             on_device_node(dev, [&] {  // first touch on the GPU's own socket
                 cudaSetDevice(dev);
-                L.pinned[0].alloc(batch_reads, mrl0, with_qual);
-                L.pinned[1].alloc(batch_reads, mrl0, with_qual);
+                for (PinnedBatch& p : L.pinned) {
+                    if (wire) p.alloc_wire(WireLayout(batch_reads, mrl0, with_qual).total);
+                    else p.alloc(batch_reads, mrl0, with_qual);
+                }
             });
             L.cur = L.in_flight = 0;
         }
@@ -1021,10 +1219,22 @@ struct Ingest {
             Lane& L = *run->ingest.lanes[d];
             bc_ctx* ctx = ctxs[d];
             if (L.in_flight == 2) {  // the buffer we are about to overwrite was handed to the submit before last
+                const auto t0 = Clock::now();
                 if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+                st.wait_s += since(t0);
                 L.in_flight = 0;
             }
             PinnedBatch& p = L.pinned[L.cur];
+            if (wire) {
+                const size_t n = submit_wire(seq, done, n_rec, p, ctx);
+                total += n;
+                done += n;
+                n_batches++;
+                L.cur ^= 1;
+                L.in_flight++;
+                if (run->progress) run->progress(total, run->progress_user);
+                continue;
+            }
             // geometry of this batch: the run's default, or wider when a read of the parts it touches is longer (reads of
             // any length up to BC_MAX_READ_LEN are decoded; the reference has no length limit, input.rs:115-148)
             size_t n = std::min<size_t>(n_rec - done, batch_reads);
@@ -1039,6 +1249,7 @@ struct Ingest {
             }
             const uint32_t ps = bc_plane_stride(mrl), qs = bc_qual_stride(mrl);
             const size_t chunk = 2048, tasks = (n + chunk - 1) / chunk;
+            auto t0 = Clock::now();
             pool->run(tasks, [&](size_t k) {
                 size_t a = done + k * chunk;
                 const size_t b = std::min(done + n, a + chunk);
@@ -1058,7 +1269,11 @@ struct Ingest {
             b.planes = p.planes;
             b.read_len = p.read_len;
             b.qual = with_qual ? p.qual : nullptr;
+            st.pack_s += since(t0);
+            t0 = Clock::now();
             if (bc_submit(ctx, &b) != BC_OK) throw Error(bc_last_error(ctx));
+            st.submit_s += since(t0);
+            st.batches++;
             total += n;
             done += n;
             n_batches++;
@@ -1068,9 +1283,91 @@ struct Ingest {
         }
     }
 
+    // records [done, ...) of the block -> one batch in its transfer form -> bc_submit_wire; returns the reads taken
+    size_t submit_wire(const RecSeq& seq, size_t done, size_t n_rec, PinnedBatch& p, bc_ctx* ctx) {
+        size_t n = std::min<size_t>(n_rec - done, batch_reads);
+        uint32_t longest = 0;
+        for (size_t t = seq.part_of(done), e = seq.part_of(done + n - 1); t <= e; t++) longest = std::max(longest, seq.longest[t]);
+        uint32_t mrl = mrl0;
+        if (longest > mrl0) {  // a wider batch of fewer reads, as on the bc_batch path
+            mrl = std::min<uint32_t>((longest + 31) / 32 * 32, BC_MAX_READ_LEN);
+            while (n && WireLayout(n, mrl, with_qual).total > p.cap_arena) n = n * 3 / 4;
+            if (n == 0) throw Error("batch buffers too small for a read of " + std::to_string(longest) + " bases: raise --batch-reads");
+        }
+        const WireLayout L(n, mrl, with_qual);
+        const size_t chunk = 2048, tasks = (n + chunk - 1) / chunk;
+        if (call_reads.size() < tasks) {
+            call_reads.resize(tasks);
+            call_pos.resize(tasks);
+        }
+        call_first.assign(tasks + 1, 0);
+        const uint32_t* nm = reinterpret_cast<const uint32_t*>(p.arena + L.o_nm);
+        std::atomic<int> need8{0};
+        auto pack_all = [&](uint32_t bits, bool planes_too) {
+            pool->run(tasks, [&](size_t k) {
+                size_t a = done + k * chunk;
+                const size_t b = std::min(done + n, a + chunk);
+                if (planes_too) {
+                    call_reads[k].clear();
+                    call_pos[k].clear();
+                }
+                while (a < b) {
+                    const size_t t = seq.part_of(a);
+                    const size_t take = std::min(b, seq.first[t + 1]) - a, dst = a - done;
+                    if (!pack_range_wire(mrl, L, p.arena, (*seq.parts)[t].data() + (a - seq.first[t]), dst, take, bits)) need8 = 1;
+                    if (planes_too) list_ncalls(nm, L.W, dst, take, call_reads[k], call_pos[k]);
+                    a += take;
+                }
+            });
+        };
+        auto t0 = Clock::now();
+        uint32_t bits = with_qual ? 6u : 0u;
+        pack_all(bits, true);
+        if (need8) {  // a quality character beyond '_': this batch goes as plain bytes
+            bits = 8;
+            pack_all(bits, false);
+            st.batches_qual8++;
+        }
+        for (size_t k = 0; k < tasks; k++) call_first[k + 1] = call_first[k] + call_reads[k].size();
+        const size_t n_calls = call_first[tasks];
+        const bool list = n_calls <= L.list_cap;
+        if (list && n_calls) {
+            uint32_t* nr = reinterpret_cast<uint32_t*>(p.arena + L.o_nr);
+            uint16_t* np = reinterpret_cast<uint16_t*>(p.arena + L.o_np);
+            pool->run(tasks, [&](size_t k) {
+                if (call_reads[k].empty()) return;
+                memcpy(nr + call_first[k], call_reads[k].data(), call_reads[k].size() * 4);
+                memcpy(np + call_first[k], call_pos[k].data(), call_pos[k].size() * 2);
+            });
+        }
+        if (!list) st.batches_dense_n++;
+        st.pack_s += since(t0);
+        bc_wire_batch wb{};
+        wb.n_reads = (uint32_t)n;
+        wb.max_read_len = mrl;
+        wb.qual_bits = bits;
+        wb.qual_stride = bits ? bc_wire_qual_stride(mrl, bits) : 0;
+        wb.n_calls = list ? (uint32_t)n_calls : 0;
+        wb.lohi = reinterpret_cast<const uint32_t*>(p.arena + L.o_lohi);
+        wb.read_len = reinterpret_cast<const uint16_t*>(p.arena + L.o_len);
+        wb.nmask = list ? nullptr : nm;
+        wb.n_read = reinterpret_cast<const uint32_t*>(p.arena + L.o_nr);
+        wb.n_pos = reinterpret_cast<const uint16_t*>(p.arena + L.o_np);
+        wb.qual = bits ? p.arena + L.o_q : nullptr;
+        t0 = Clock::now();
+        if (bc_submit_wire(ctx, &wb) != BC_OK) throw Error(bc_last_error(ctx));
+        st.submit_s += since(t0);
+        st.batches++;
+        return n;
+    }
+
     void finish() {
+        const auto t0 = Clock::now();
         for (int d = 0; d < n_ctx; d++)
             if (bc_sync(ctxs[d]) != BC_OK) throw Error(bc_last_error(ctxs[d]));
+        st.wait_s += since(t0);
+        st.total_s = since(t_begin);
+        run->stats = st;
     }
 };
 
@@ -1101,7 +1398,9 @@ uint64_t ingest_fastq(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const char* 
         while (pos < eof) {
             const char* blk_end = std::min(eof, pos + block_bytes);
             const bool last = blk_end == eof;
+            const auto t0 = Ingest::Clock::now();
             const char* consumed = split_block(*ing.pool, pos, blk_end, last, parts, seq);
+            ing.st.split_s += Ingest::since(t0);
             if (seq.size() == 0) {
                 if (last) break;  // trailing partial record: dropped, as the reference never posts it
                 throw Error("FASTQ record longer than the block buffer");
@@ -1248,6 +1547,10 @@ bch_run* bch_open(const bch_args* args, char* err, int errlen) {
 void bch_close(bch_run* run) { delete run; }
 int bch_set_option(bch_run* run, const char* name, long long value) {
     if (!run || !name) return BC_EINVAL;
+    if (!strcmp(name, "wire_batches")) {
+        run->wire_batches = value != 0;
+        return BC_OK;
+    }
     if (!strcmp(name, "lean_writer_min_rows") && value >= 0) run->lean_rows = (uint64_t)value;
     else return BC_EINVAL;
     return BC_OK;
@@ -1299,6 +1602,106 @@ int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char* seq_lines, con
         s = se ? se + 1 : s + sl;
     }
     return pack_refs(max_read_len, refs, 0, n, planes_out, read_len_out, qual_lines ? qual_out : nullptr, threads);
+}
+
+size_t bch_wire_bound(uint32_t n_reads, uint32_t max_read_len, int with_qual) {
+    return WireLayout(n_reads, max_read_len, with_qual != 0).total;
+}
+
+// a host bc_batch -> its transfer form in `buf`.  qual_bits 0: the narrowest form that holds every quality character.
+int bch_wire_from_batch(const bc_batch* in, uint32_t max_read_len, uint32_t qual_bits, void* buf, size_t buf_bytes, bc_wire_batch* out) {
+    if (!in || !out || !buf || in->location != BC_LOC_HOST || !in->planes || !in->read_len) return BC_EINVAL;
+    const uint32_t W = bc_plane_words(max_read_len);
+    if (max_read_len == 0 || max_read_len > BC_MAX_READ_LEN || in->plane_stride != bc_plane_stride(max_read_len)) return BC_EINVAL;
+    const bool with_qual = in->qual != nullptr;
+    if (with_qual && in->qual_stride != bc_qual_stride(max_read_len)) return BC_EINVAL;
+    const size_t n = in->n_reads;
+    const WireLayout L(n, max_read_len, with_qual);
+    if (buf_bytes < L.total) return BC_ENOMEM;
+    unsigned char* arena = static_cast<unsigned char*>(buf);
+    uint32_t* lohi = reinterpret_cast<uint32_t*>(arena + L.o_lohi);
+    uint16_t* rl = reinterpret_cast<uint16_t*>(arena + L.o_len);
+    uint32_t* nm = reinterpret_cast<uint32_t*>(arena + L.o_nm);
+    for (size_t r = 0; r < n; r++) {
+        const uint32_t* rec = in->planes + r * in->plane_stride;
+        memcpy(lohi + r * 2 * W, rec, (size_t)2 * W * 4);
+        memcpy(nm + r * W, rec + 2 * W, (size_t)W * 4);
+        rl[r] = in->read_len[r];
+    }
+    std::vector<uint32_t> cr;
+    std::vector<uint16_t> cp;
+    list_ncalls(nm, W, 0, n, cr, cp);
+    const bool list = cr.size() <= L.list_cap;
+    if (list && !cr.empty()) {
+        memcpy(arena + L.o_nr, cr.data(), cr.size() * 4);
+        memcpy(arena + L.o_np, cp.data(), cp.size() * 2);
+    }
+    memset(out, 0, sizeof *out);
+    out->n_reads = in->n_reads;
+    out->max_read_len = max_read_len;
+    out->n_calls = list ? (uint32_t)cr.size() : 0;
+    out->lohi = lohi;
+    out->read_len = rl;
+    out->nmask = list ? nullptr : nm;
+    out->n_read = reinterpret_cast<const uint32_t*>(arena + L.o_nr);
+    out->n_pos = reinterpret_cast<const uint16_t*>(arena + L.o_np);
+    if (!with_qual) return BC_OK;
+    // which characters occur among the first n_codes of every read
+    bool seen[256] = {false};
+    const uint32_t n_codes = L.n_codes, have = std::min(n_codes, in->qual_stride);
+    // (characters at and beyond a read's length are never looked at by the filter: they do not count, and travel as code 0)
+    for (size_t r = 0; r < n; r++) {
+        const uint8_t* q = in->qual + r * in->qual_stride;
+        const uint32_t len = std::min<uint32_t>(in->read_len[r] & 0x7FFFu, have);
+        for (uint32_t i = 0; i < len; i++) seen[q[i]] = true;
+    }
+    uint32_t distinct = 0;
+    bool six = true;
+    for (int c = 0; c < 256; c++)
+        if (seen[c]) {
+            distinct++;
+            if (c != 0xFF && (c < 33 || c > 95)) six = false;
+        }
+    uint32_t bits = qual_bits;
+    if (bits == 0) bits = distinct <= 4 ? 2 : distinct <= 16 ? 4 : six ? 6 : 8;
+    if ((bits == 2 && distinct > 4) || (bits == 4 && distinct > 16) || (bits == 6 && !six) || (bits != 2 && bits != 4 && bits != 6 && bits != 8))
+        return BC_EINVAL;
+    uint8_t code_of[256];
+    memset(code_of, 0xFF, sizeof code_of);
+    if (distinct == 0) out->qual_dict[0] = '!';
+    if (bits <= 4) {
+        uint32_t k = 0;
+        for (int c = 0; c < 256; c++)
+            if (seen[c]) {
+                out->qual_dict[k] = (uint8_t)c;
+                code_of[c] = (uint8_t)k++;
+            }
+    }
+    const uint32_t qs = bc_wire_qual_stride(max_read_len, bits);
+    uint8_t* qo = arena + L.o_q;
+    std::vector<uint8_t> chars(n_codes + 32);
+    for (size_t r = 0; r < n; r++) {
+        const uint32_t len = std::min<uint32_t>(in->read_len[r] & 0x7FFFu, have);
+        memcpy(chars.data(), in->qual + r * in->qual_stride, len);
+        memset(chars.data() + len, bits <= 4 ? out->qual_dict[0] : '!', n_codes - len);
+        bool ok = true;
+        if (bits == 8) memcpy(qo + r * qs, chars.data(), n_codes);
+        else if (bits == 6) ok = pack_qual6(chars.data(), n_codes, qo + r * qs);
+        else ok = pack_qual_dict(chars.data(), n_codes, code_of, bits, qo + r * qs, qs);
+        if (!ok) return BC_EINVAL;
+    }
+    out->qual_bits = bits;
+    out->qual_stride = qs;
+    out->qual = qo;
+    return BC_OK;
+}
+
+int bch_ingest_stats(const bch_run* run, double* seconds, uint64_t* counts) {
+    if (!run || !seconds || !counts) return BC_EINVAL;
+    const IngestStats& s = run->stats;
+    seconds[0] = s.split_s; seconds[1] = s.pack_s; seconds[2] = s.submit_s; seconds[3] = s.wait_s; seconds[4] = s.total_s;
+    counts[0] = s.batches; counts[1] = s.batches_qual8; counts[2] = s.batches_dense_n;
+    return BC_OK;
 }
 
 int bch_scan_fastq(const char* fastq_path, unsigned threads, uint64_t* n_records, uint64_t* n_bases, uint32_t* crc, char* err,

@@ -79,6 +79,22 @@ class HostBatch:
         self.nbytes = sum(t.numel() * t.element_size() for t in self._t if t is not None)
 
 
+class HostWireBatch:
+    """The same batch in its transfer form (bc_wire_batch) inside one pinned buffer: what a host that packs for the PCIe
+    crossing hands to bc_submit_wire."""
+
+    def __init__(self, bc, dev_batch, max_read_len):
+        host = bc.Batch(dev_batch.n, dev_batch.plane_stride, dev_batch.qual_stride, dev_batch.planes.cpu().numpy(),
+                        dev_batch.read_len.cpu().numpy(), None if dev_batch.qual is None else dev_batch.qual.cpu().numpy(), device=False)
+        need = bc.WireBatch.bound(dev_batch.n, max_read_len, dev_batch.qual is not None)
+        self._t = torch.empty(max(need, 1), dtype=torch.uint8, pin_memory=True)
+        self.batch = bc.WireBatch(host, max_read_len, buf=self._t.numpy())
+        self.n = dev_batch.n
+        self.nbytes = self.batch.nbytes
+        self.qual_bits = self.batch.c.qual_bits
+        self.n_calls_listed = self.batch.c.n_calls if not self.batch.c.nmask else None
+
+
 class Job:
     """ctr: this rank's Counter (or any object with the same methods: the CPU test drives the host logic with a fake).
     expected_reads: reads per rank, sizes the exchange's receive buffer (it grows when a job needs more)."""
@@ -112,11 +128,11 @@ class Job:
         self.cap = capacity
         dist.barrier()
 
-    def to_pinned(self, dev_batch):
-        return HostBatch(self.bc, dev_batch)
+    def to_pinned(self, dev_batch, wire=False):
+        return HostWireBatch(self.bc, dev_batch, self.run.max_read_len) if wire else HostBatch(self.bc, dev_batch)
 
     def _b(self, b):
-        return b.batch if isinstance(b, HostBatch) else b
+        return b.batch if isinstance(b, (HostBatch, HostWireBatch)) else b
 
     def step(self, batches, to_host=False):
         """reset -> decode every batch -> merge across ranks -> rows.  Returns the number of (key, count) rows of the

@@ -34,12 +34,13 @@ def test_struct_layouts_match_the_header(tmp_path):
     import subprocess
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "bc_b200.h"\n#include "bc_host.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bc_slot), sizeof(bc_config), sizeof(bc_batch), '
-                   'sizeof(bc_table), sizeof(bc_profile), sizeof(bc_decode_out), sizeof(bch_args)); return 0; }\n')
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bc_slot), sizeof(bc_config), sizeof(bc_batch), '
+                   'sizeof(bc_table), sizeof(bc_profile), sizeof(bc_decode_out), sizeof(bch_args), sizeof(bc_wire_batch)); return 0; }\n')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [C.sizeof(t) for t in (bc.bc_slot, bc.bc_config, bc.bc_batch, bc.bc_table, bc.bc_profile, bc.bc_decode_out, bc.bch_args)]
+    want = [C.sizeof(t) for t in (bc.bc_slot, bc.bc_config, bc.bc_batch, bc.bc_table, bc.bc_profile, bc.bc_decode_out, bc.bch_args,
+                               bc.bc_wire_batch)]
     assert got == want
 
 

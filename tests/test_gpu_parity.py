@@ -154,6 +154,105 @@ def test_golden_fastq_ingest_small_batches(case, tmp_path):
     assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
 
 
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_wire_batches(case, tmp_path):
+    """Host batches in their transfer form (bc_submit_wire: lo / hi planes, N calls as a list, quality as 2- to 8-bit codes,
+    expanded on the device) give the golden counters and CSV set, in every quality form that holds the batch."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run)
+    reads = read_fastq(paths["fastq"])
+    batch = run.pack([r[0] for r in reads], [r[1] for r in reads])
+    n = batch.n
+    auto = bc.WireBatch(batch, run.max_read_len)
+    forms = [0] + ([b for b in (4, 6, 8) if b > auto.c.qual_bits] if run.quality_on else [])
+    for bits in forms:
+        ctr.reset()
+        for a, b in ((0, n // 3), (n // 3, n - 1), (n - 1, n)):
+            ctr.submit(bc.WireBatch(batch.slice(a, b), run.max_read_len, qual_bits=bits))
+        c = ctr.counters()
+        assert c.pop("unsupported") == 0
+        assert c == exp["counters"], bits
+    assert ctr.profile()["h2d_bytes"] > 0
+    ctr.write_counts(str(tmp_path), "golden", merge=fl["merge"], enrich=fl["enrich"])
+    assert_same_csv_set(read_csv_dir(str(tmp_path), "golden"), exp["files"])
+    # a wider geometry than the run's (a batch that met a longer read) and the specialised kernel's context
+    ctr2 = bc.Counter(run, flags=bc.BC_CFG_SPECIALIZE)
+    wide = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], max_barcode=fl["max_barcode"],
+                  max_sample=fl["max_sample"], max_constant=fl["max_constant"], max_read_len=run.max_read_len + 70)
+    ctr2.submit(bc.WireBatch(batch.slice(0, n // 2), run.max_read_len))
+    ctr2.submit(bc.WireBatch(wide.pack([r[0] for r in reads[n // 2:]], [r[1] for r in reads[n // 2:]]), wide.max_read_len))
+    c = ctr2.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    prof = ctr2.profile()
+    assert prof["specialized_launches"] == 1 and prof["generic_launches"] == 1, prof
+
+
+@pytest.mark.parametrize("case", ["del3_umi", "example_q20", "crispr"])
+def test_golden_fastq_ingest_plain_batches(case, tmp_path):
+    """bch_count_fastq with the transfer form switched off (plain bc_batch arrays across PCIe): same result."""
+    exp, paths = load_golden(case)
+    fl = exp["flags"]
+    run = make_run(paths, fl)
+    run.set_option("wire_batches", 0)
+    ctr = bc.Counter(run)
+    assert ctr.count_fastq(paths["fastq"], threads=2, batch_reads=41) == len(exp["outcomes"])
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    plain_bytes = ctr.profile()["h2d_bytes"]
+    run.set_option("wire_batches", 1)
+    ctr.reset()
+    ctr.reset_profile()
+    assert ctr.count_fastq(paths["fastq"], threads=2, batch_reads=41) == len(exp["outcomes"])
+    c = ctr.counters()
+    c.pop("unsupported")
+    assert c == exp["counters"]
+    assert ctr.profile()["h2d_bytes"] < plain_bytes
+
+
+def test_ingest_wire_fallbacks(tmp_path):
+    """A batch with a quality character beyond '_' crosses as plain bytes, a batch full of N calls sends its N plane whole:
+    the ingest notices both by itself and the result equals the plain-batch path's."""
+    exp, paths = load_golden("example_q20")
+    fl = exp["flags"]
+    rng = random.Random(9)
+    reads = read_fastq(paths["fastq"])
+    out = []
+    for i, (s, q) in enumerate(reads):
+        if i % 50 == 7:
+            q = q[:5] + "~" + q[6:]  # Phred 93: long-read instruments
+        if 100 <= i < 160:
+            s = "".join("N" if rng.random() < 0.4 else ch for ch in s)
+        out.append((s, q))
+    fq = tmp_path / "fallbacks.fastq"
+    with open(fq, "w") as f:
+        for i, (s, q) in enumerate(out):
+            f.write(f"@r{i}\n{s}\n+\n{q}\n")
+    run = make_run(paths, fl)
+    ctr = bc.Counter(run)
+    got = {}
+    for wire in (0, 1):
+        run.set_option("wire_batches", wire)
+        ctr.reset()
+        assert ctr.count_fastq(str(fq), threads=2, batch_reads=20) == len(out)
+        got[wire] = ctr.counters()
+        st = ctr.ingest_stats()
+        if wire:
+            assert st["batches"] == (len(out) + 19) // 20 and 0 < st["batches_qual8"] < st["batches"] and 0 < st["batches_dense_n"] <= 4, st
+    assert got[0] == got[1] and got[1]["matched"] > 0
+    # and against the oracle
+    orc = Oracle(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], outdir=str(tmp_path), prefix="o")
+    for s, q in out:
+        orc.process(s, q)
+    want = orc.counters()
+    g = dict(got[1])
+    g.pop("unsupported")
+    assert g == want
+
+
 @pytest.mark.parametrize("case", ["example", "crispr", "del3_umi", "lineage_raw"])
 @pytest.mark.parametrize("gz", [False, True, "bgzf"])
 def test_cli_drop_in(case, gz, tmp_path):
@@ -306,9 +405,12 @@ def test_reads_of_any_length_and_ragged_quality_lines(tmp_path):
     # the library's ingest with a run sized for the short reads only
     run = bc.Run(paths["fmt"], paths["samples"], paths["counted"], min_quality=fl["min_quality"], max_read_len=len(base[0][0]))
     ctr = bc.Counter(run)
-    assert ctr.count_fastq(str(fq), threads=3, batch_reads=64) == len(reads) + 2
-    got = ctr.counters()
-    assert got.pop("unsupported") == 2 and got == want
+    for wire in (0, 1):  # plain bc_batch arrays, then (the default) the transfer form
+        run.set_option("wire_batches", wire)
+        ctr.reset()
+        assert ctr.count_fastq(str(fq), threads=3, batch_reads=64) == len(reads) + 2
+        got = ctr.counters()
+        assert got.pop("unsupported") == 2 and got == want, wire
     ctr.write_counts(str(g_dir), "p", merge=fl["merge"], enrich=fl["enrich"])
     assert_same_csv_set(read_csv_dir(str(g_dir), "p"), read_csv_dir(str(o_dir), "p"))
     # and the command line, which probes the first reads for its default geometry
