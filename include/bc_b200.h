@@ -274,21 +274,30 @@ int bc_key_decode(const bc_ctx *ctx, uint64_t key_lo, uint64_t key_hi, uint32_t 
  *    its owned keys (disjoint across ranks), its matched / duplicates counters are those of the records it owns and
  *    its other counters those of the reads it decoded: every statistic sums over ranks to the single-GPU value.
  *
- *    set-up   bc_exchange_open(capacity)  this rank's receive buffer, in records; the same capacity on every rank
+ *    set-up   bc_exchange_open(capacity)  this rank's receive buffers, in records; the same capacity on every rank
  *             one process per GPU: bc_exchange_handle -> caller exchanges the BC_IPC_HANDLE_BYTES handles ->
  *                                  bc_exchange_connect(all handles, rank order)
  *             one process:         bc_exchange_connect_local(all contexts, rank order)
- *    per job  bc_exchange_count   -> sent[r] = records of this rank owned by rank r (synchronises)
+ *    per job  bc_submit ...       when the exchange is connected before a job's first batch the exchange is STREAMED: every
+ *                                 batch's records leave for their owners right after its decode, on a side stream, under
+ *                                 the decode of the next batch (a tile reserves its run in the owner's buffer with one
+ *                                 atomic on the owner's receive cursor over NVLink); otherwise they leave in bulk below
+ *             bc_exchange_count   -> sent[r] = records of this rank owned by rank r (synchronises)
  *             caller: all-gather the n_ranks x n_ranks matrix; first[r] = sum of sent[r] of the ranks before this one;
  *                     received = sum over ranks of what they send to this one; if any rank's total exceeds the
- *                     capacity, every rank re-opens larger and reconnects
- *             bc_exchange_scatter(first)  asynchronous on the ctx stream
- *             caller: a barrier ordered after every rank's scatter (a collective on the same stream, or stream syncs)
+ *                     capacity, every rank disconnects, re-opens larger, reconnects and calls bc_exchange_count again
+ *                     (the job's exchange then starts over, in bulk from the record buffers)
+ *             bc_exchange_scatter(first)  bulk: asynchronous on the ctx stream; streamed: nothing left to move
+ *             caller: a barrier ordered after every rank's bc_exchange_count / _scatter (a collective, or stream syncs)
  *             bc_exchange_finish(received)
- *    Until bc_exchange_finish, bc_get_counters / bc_finish on a rank of a multi-GPU job fail with BC_ESTATE. */
+ *    Until bc_exchange_finish, bc_get_counters / bc_finish on a rank of a multi-GPU job fail with BC_ESTATE.  A rank holds
+ *    two receive buffers that alternate job by job, so a fast rank may start streaming the next job while a slow one still
+ *    counts this one; the ranks must run the same sequence of jobs.  bc_set_option("exchange_bulk", 1) forbids streaming. */
 #define BC_IPC_HANDLE_BYTES 64
 int bc_exchange_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity);
 int bc_exchange_handle(bc_ctx *ctx, void *ipc_handle_out);
+/* Receive capacity (records) of an exchange that is open and connected to every peer, else 0. */
+uint64_t bc_exchange_capacity(const bc_ctx *ctx);
 /* Unmaps the other ranks' buffers.  Before re-opening larger, every rank disconnects and the caller synchronises the ranks:
  * a buffer must not be freed while another process still maps it. */
 int bc_exchange_disconnect(bc_ctx *ctx);

@@ -163,6 +163,7 @@ _PROTOS = {
     "bc_marginals": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "bc_exchange_open": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]),
     "bc_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bc_exchange_capacity": (C.c_uint64, [C.c_void_p]),
     "bc_exchange_disconnect": (C.c_int, [C.c_void_p]),
     "bc_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_exchange_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

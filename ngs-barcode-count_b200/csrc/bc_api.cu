@@ -85,6 +85,16 @@ struct bc_ctx {
     unsigned long long x_local_valid = 0;  // records of this rank that were not holes at the last bc_exchange_count
     int x_state = 0;                       // 0: records not exchanged; 1: counted; 2: scattered; 3: finished (rows valid)
     unsigned long long x_received = 0;
+    // streamed exchange: the receive allocation holds TWO buffers that alternate job by job (a fast rank may stream the next
+    // job's records while this one still counts the last job's) and, behind them, one 64-bit receive cursor per buffer that
+    // the senders advance over NVLink.  A batch's records leave on x_stream right after its decode.
+    cudaStream_t x_stream = nullptr;
+    cudaEvent_t x_ev = nullptr;
+    uint32_t x_epoch = 0;                  // jobs finished since the buffers were opened: parity picks the buffer
+    int x_mode = 0;                        // of the job in progress: 0 undecided (nothing submitted), 1 streamed, 2 bulk
+    bool x_overflowed = false, x_dirty = false, opt_exchange_bulk = false;
+    unsigned long long* d_xsent = nullptr; // kMaxRanks counters: records sent to each owner by the streamed scatters
+    unsigned int* d_xoverflow = nullptr;
     // options (bc_set_option): measurement / test switches of the flush
     bool opt_flush_global = false, opt_flush_two_stage = false;
     uint32_t cfg_flags = 0;
@@ -189,17 +199,18 @@ struct ProfScope {  // CUDA events around one launch, only while profiling is on
     bc_ctx* ctx;
     int kind;
     cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(bc_ctx* c, int k) : ctx(c), kind(k) {
+    cudaStream_t on;
+    ProfScope(bc_ctx* c, int k, cudaStream_t stream = nullptr) : ctx(c), kind(k), on(stream ? stream : c->stream) {
         ctx->prof.launches[kind]++;
         if (ctx->profiling) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, on);
         }
     }
     ~ProfScope() {
         if (a) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, on);
             ctx->prof_events.push_back({a, b, kind});
         }
     }
@@ -541,6 +552,13 @@ void bc_destroy(bc_ctx* ctx) {
         if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
     if (ctx->d_xrecv) cudaFree(ctx->d_xrecv);
     if (ctx->d_xcursor) cudaFree(ctx->d_xcursor);
+    if (ctx->d_xsent) cudaFree(ctx->d_xsent);
+    if (ctx->d_xoverflow) cudaFree(ctx->d_xoverflow);
+    if (ctx->x_stream) {
+        cudaStreamSynchronize(ctx->x_stream);
+        cudaStreamDestroy(ctx->x_stream);
+    }
+    if (ctx->x_ev) cudaEventDestroy(ctx->x_ev);
     if (ctx->d_marg) cudaFree(ctx->d_marg);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_stripes) cudaFree(ctx->d_stripes);
@@ -1075,6 +1093,55 @@ int bc_set_stream(bc_ctx* ctx, void* cuda_stream) {
     return BC_OK;
 }
 
+static SplitLevel owner_level(const bc_ctx* ctx);
+
+// receive allocation of a rank (local, or a peer's mapping): [buffer 0][buffer 1][cursor 0, cursor 1], a buffer being
+// xcap keys (lo) followed, for wide keys, by xcap high words
+static unsigned long long* xbuf_lo(const bc_ctx* ctx, unsigned long long* base, uint32_t parity) {
+    return base + (unsigned long long)parity * ctx->xcap * (ctx->cfg.wide ? 2 : 1);
+}
+static unsigned long long* xbuf_cursor(const bc_ctx* ctx, unsigned long long* base, uint32_t parity) {
+    return base + 2 * ctx->xcap * (ctx->cfg.wide ? 2 : 1) + parity;
+}
+
+
+// Streamed exchange: records [first, first + n) of the record buffer — the batch the main stream has just decoded — go to their
+// owners' receive buffers on x_stream, under the decode of the next batch.  The mode of a job is fixed by its first batch:
+// streamed when every peer is connected by then, else the bulk exchange after the last batch (bc_exchange_count / _scatter).
+static int stream_records(bc_ctx* ctx, unsigned long long first, unsigned long long n) {
+    if (ctx->x_dirty)
+        return fail(ctx, BC_ESTATE, "a multi-GPU job was reset after some of its records had been streamed to their owners: re-open the "
+                                    "exchange (bc_exchange_open + connect) on every rank before the next job");
+    if (ctx->x_mode == 0) {
+        bool connected = !ctx->opt_exchange_bulk;
+        for (uint32_t r = 0; r < ctx->x_ranks; r++) connected = connected && ctx->x_peer[r] != nullptr;
+        ctx->x_mode = connected ? 1 : 2;
+        if (connected) {
+            CK(ctx, cudaMemsetAsync(ctx->d_xsent, 0, kMaxRanks * sizeof(unsigned long long), ctx->stream));
+            CK(ctx, cudaMemsetAsync(ctx->d_xoverflow, 0, sizeof(unsigned int), ctx->stream));
+            ctx->x_overflowed = false;
+        }
+    }
+    if (ctx->x_mode != 1 || n == 0) return BC_OK;
+    const bool wide = ctx->cfg.wide != 0;
+    const uint32_t parity = ctx->x_epoch & 1u;
+    PeerOut peers{};
+    for (uint32_t r = 0; r < ctx->x_ranks; r++) {
+        peers.lo[r] = xbuf_lo(ctx, ctx->x_peer[r], parity);
+        peers.hi[r] = wide ? peers.lo[r] + ctx->xcap : nullptr;
+        peers.cursor[r] = xbuf_cursor(ctx, ctx->x_peer[r], parity);
+    }
+    peers.cap = ctx->xcap;
+    peers.sent = ctx->d_xsent;
+    peers.overflow = ctx->d_xoverflow;
+    CK(ctx, cudaEventRecord(ctx->x_ev, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->x_stream, ctx->x_ev, 0));
+    ProfScope p(ctx, BC_K_EXCHANGE, ctx->x_stream);
+    CK(ctx, launch_owner_scatter(wide, ItemView{ctx->rec.lo + first, wide ? ctx->rec.hi + first : nullptr, nullptr}, peers, n, owner_level(ctx),
+                                 ctx->d_xcursor, ctx->x_stream));
+    return BC_OK;
+}
+
 static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const DecodeOut& out, unsigned long long* counters) {
     int rc = validate_batch(ctx, batch);
     if (rc != BC_OK) return rc;
@@ -1125,6 +1192,10 @@ static int run_decode(bc_ctx* ctx, const bc_batch* batch, int flags, const Decod
     {   // also after a locate-only launch (nothing deferred): it is k_resolve that zeroes the next batch's list counter
         ProfScope p(ctx, BC_K_SCAN);
         CK(ctx, launch_resolve(ctx->cfg, view, ctx->aux, ctx->tables, counters, out, rec_out(ctx), deferred, flags, ctx->stream));
+    }
+    if ((flags & F_APPEND) && ctx->x_ranks > 1) {
+        rc = stream_records(ctx, ctx->rec_n, batch->n_reads);
+        if (rc != BC_OK) return rc;
     }
     if (flags & F_APPEND) ctx->rec_n += batch->n_reads;
     return release_staging(ctx, staged);
@@ -1243,6 +1314,7 @@ int bc_set_option(bc_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return BC_EINVAL;
     if (!strcmp(name, "flush_global")) ctx->opt_flush_global = value != 0;
     else if (!strcmp(name, "flush_two_stage")) ctx->opt_flush_two_stage = value != 0;
+    else if (!strcmp(name, "exchange_bulk")) ctx->opt_exchange_bulk = value != 0;
     else return fail(ctx, BC_EINVAL, "bc_set_option: unknown option '%s'", name);
     ctx->rows_valid = false;
     return BC_OK;
@@ -1253,6 +1325,7 @@ int bc_sync(bc_ctx* ctx) {
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->x_stream) CK(ctx, cudaStreamSynchronize(ctx->x_stream));
     ctx->copies_pending = false;
     return BC_OK;
 }
@@ -2057,15 +2130,33 @@ int bc_exchange_open(bc_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint64_t capa
     close_peers(ctx);
     if (ctx->d_xrecv) cudaFree(ctx->d_xrecv);
     ctx->d_xrecv = nullptr;
-    CK(ctx, cudaMalloc(&ctx->d_xrecv, capacity * sizeof(unsigned long long) * (ctx->cfg.wide ? 2 : 1)));
+    const size_t buf_words = (size_t)capacity * (ctx->cfg.wide ? 2 : 1);
+    CK(ctx, cudaMalloc(&ctx->d_xrecv, (2 * buf_words + 32) * sizeof(unsigned long long)));
+    CK(ctx, cudaMemset(ctx->d_xrecv + 2 * buf_words, 0, 32 * sizeof(unsigned long long)));  // the two receive cursors
     if (!ctx->d_xcursor) CK(ctx, cudaMalloc(&ctx->d_xcursor, kMaxRanks * sizeof(uint32_t)));
+    if (!ctx->d_xsent) {
+        CK(ctx, cudaMalloc(&ctx->d_xsent, kMaxRanks * sizeof(unsigned long long)));
+        CK(ctx, cudaMalloc(&ctx->d_xoverflow, sizeof(unsigned int)));
+        CK(ctx, cudaStreamCreateWithFlags(&ctx->x_stream, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->x_ev, cudaEventDisableTiming));
+    }
     ctx->xcap = capacity;
     ctx->x_ranks = n_ranks;
     ctx->x_rank = rank;
     ctx->x_peer[rank] = ctx->d_xrecv;
     ctx->x_state = 0;
+    ctx->x_epoch = 0;
+    ctx->x_mode = ctx->rec_n ? 2 : 0;  // records decoded before the buffers existed (a skewed job growing them) go in bulk
+    ctx->x_overflowed = ctx->x_dirty = false;
     ctx->rows_valid = false;
     return BC_OK;
+}
+
+uint64_t bc_exchange_capacity(const bc_ctx* ctx) {
+    if (!ctx || !ctx->d_xrecv || ctx->x_ranks == 0 || ctx->x_dirty) return 0;
+    for (uint32_t r = 0; r < ctx->x_ranks; r++)
+        if (!ctx->x_peer[r]) return 0;
+    return ctx->xcap;
 }
 
 int bc_exchange_disconnect(bc_ctx* ctx) {
@@ -2143,6 +2234,21 @@ int bc_exchange_count(bc_ctx* ctx, uint64_t* sent) {
     if (rc != BC_OK) return rc;
     const unsigned long long n_rec = ctx->rec_n;
     if (n_rec >= 0xFFFFFFF0ULL) return fail(ctx, BC_EUNSUPPORTED, "bc_exchange_count: more than 2^32 records on one rank");
+    if (ctx->x_mode == 1) {  // streamed: the records have left already, batch by batch; what went where was counted on the way
+        CK(ctx, cudaStreamSynchronize(ctx->x_stream));
+        unsigned long long hs[kMaxRanks];
+        unsigned int over = 0;
+        CK(ctx, cudaMemcpy(hs, ctx->d_xsent, sizeof hs, cudaMemcpyDeviceToHost));
+        CK(ctx, cudaMemcpy(&over, ctx->d_xoverflow, sizeof over, cudaMemcpyDeviceToHost));
+        ctx->x_overflowed = over != 0;  // an owner's buffer was too small: the caller sees it in the matrix and re-opens larger
+        ctx->x_local_valid = 0;
+        for (uint32_t r = 0; r < ctx->x_ranks; r++) {
+            sent[r] = ctx->x_sent[r] = hs[r];
+            ctx->x_local_valid += hs[r];
+        }
+        ctx->x_state = 1;
+        return BC_OK;
+    }
     uint32_t h[kMaxRanks] = {0};
     FlushStats st{};
     if (n_rec) {
@@ -2169,16 +2275,24 @@ int bc_exchange_scatter(bc_ctx* ctx, const uint64_t* first) {
     if (!ctx || !first) return BC_EINVAL;
     if (ctx->x_state != 1) return fail(ctx, BC_ESTATE, "bc_exchange_scatter: call bc_exchange_count first (and nothing may be submitted in between)");
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->x_mode == 1) {
+        if (ctx->x_overflowed)
+            return fail(ctx, BC_EINVAL, "bc_exchange_scatter: an owner's receive buffer was too small for the streamed records: every rank "
+                                        "re-opens larger (bc_exchange_open) and the exchange starts over");
+        ctx->x_state = 2;  // nothing left to move
+        return BC_OK;
+    }
     uint32_t cur[kMaxRanks] = {0};
     PeerOut peers{};
+    const uint32_t parity = ctx->x_epoch & 1u;
     for (uint32_t r = 0; r < ctx->x_ranks; r++) {
         if (!ctx->x_peer[r]) return fail(ctx, BC_ESTATE, "bc_exchange_scatter: rank %u is not connected", r);
         if (first[r] + ctx->x_sent[r] > ctx->xcap)
             return fail(ctx, BC_EINVAL, "bc_exchange_scatter: rank %u would receive past its capacity (%llu + %llu > %llu): reopen larger", r,
                         (unsigned long long)first[r], ctx->x_sent[r], ctx->xcap);
         cur[r] = (uint32_t)first[r];
-        peers.lo[r] = ctx->x_peer[r];
-        peers.hi[r] = ctx->cfg.wide ? ctx->x_peer[r] + ctx->xcap : nullptr;
+        peers.lo[r] = xbuf_lo(ctx, ctx->x_peer[r], parity);
+        peers.hi[r] = ctx->cfg.wide ? peers.lo[r] + ctx->xcap : nullptr;
     }
     const bool wide = ctx->cfg.wide != 0;
     memcpy(ctx->h_xcur, cur, sizeof cur);  // outlives this call: the copy below is asynchronous
@@ -2198,7 +2312,18 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
     if (n_received > ctx->xcap) return fail(ctx, BC_EINVAL, "bc_exchange_finish: %llu records exceed the receive capacity", (unsigned long long)n_received);
     CK(ctx, cudaSetDevice(ctx->device));
     const bool wide = ctx->cfg.wide != 0;
-    const FlushSrc in{ItemView{ctx->d_xrecv, wide ? ctx->d_xrecv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
+    const uint32_t parity = ctx->x_epoch & 1u;
+    if (ctx->x_mode == 1) {  // the senders advanced this buffer's cursor: it must agree with the caller's plan
+        unsigned long long got = 0;
+        CK(ctx, cudaMemcpy(&got, xbuf_cursor(ctx, ctx->d_xrecv, parity), sizeof got, cudaMemcpyDeviceToHost));
+        if (got != n_received)
+            return fail(ctx, BC_ESTATE, "bc_exchange_finish: %llu records arrived, the caller's plan says %llu (was the barrier after the "
+                                        "last rank's bc_exchange_count skipped?)", got, (unsigned long long)n_received);
+        CK(ctx, cudaMemset(xbuf_cursor(ctx, ctx->d_xrecv, parity), 0, sizeof got));  // for the job after next
+    }
+    unsigned long long* recv = xbuf_lo(ctx, ctx->d_xrecv, parity);
+    const FlushSrc in{ItemView{recv, wide ? recv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
+    ctx->x_epoch++;
     int rc = flush_core(ctx, in);
     if (rc != BC_OK) return rc;
     // this rank's share of the job's outcome: the records it owns (matched = distinct pairs, duplicates = their repeats)
@@ -2323,6 +2448,9 @@ int bc_reset(bc_ctx* ctx) {
     ctx->imp_n = 0;
     ctx->dup_applied = 0;
     ctx->marg_valid = false;
+    // a streamed job dropped half way has left records in its owners' buffers: the exchange must be re-opened
+    if (ctx->x_mode == 1 && ctx->x_state != 3) ctx->x_dirty = true;
+    ctx->x_mode = 0;
     ctx->x_state = 0;
     ctx->entries_upper = 0;
     ctx->imported_rows = 0;

@@ -10,6 +10,13 @@ constexpr int kMaxRanks = 8;  // GPUs of one box (NVLink / NVSwitch peers)
 struct PeerOut {
     unsigned long long* lo[kMaxRanks];
     unsigned long long* hi[kMaxRanks];  // nullptr for keys of at most 63 bits
+    // streamed exchange (a batch's records leave right after its decode): a tile reserves its run in owner b's buffer with
+    // one system-scope atomic on the OWNER's receive cursor (in the owner's memory, reached over NVLink like the buffer);
+    // nullptr: the positions come from the local cursors handed to the launch (the bulk exchange after the last batch)
+    unsigned long long* cursor[kMaxRanks];
+    unsigned long long cap;        // records an owner's buffer holds: a run that would pass it is not written...
+    unsigned long long* sent;      // ...but still counted here (local, one counter per owner)
+    unsigned int* overflow;        // and this local flag is raised: the host then redoes the exchange in bulk, buffers re-opened larger
 };
 
 cudaError_t launch_fold_counters(unsigned long long* stripes, unsigned long long* counters, cudaStream_t stream);

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
     extern __shared__ __align__(16) unsigned long long split_stage[];  // [lo | hi | w] x T u64, then T u32 positions
     __shared__ uint32_t s_hist[1u << kSplitMaxBits], s_delta[1u << kSplitMaxBits];
     __shared__ uint32_t s_warp[kScatterThreads / 32];
+    __shared__ uint32_t s_fits;  // PEER, streamed: bit b = this tile's run fits owner b's buffer
     const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
     const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
     const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
             w[k] = WEIGHTED ? (i < e ? in.w[i] : 0ULL) : 0ULL;
         }
         for (uint32_t b = tid; b < F; b += kScatterThreads) s_hist[b] = 0;
+        if (PEER && tid == 0) s_fits = 0xFFFFFFFFu;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
@@ -237,7 +239,20 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
         for (int k = 0; k < 8; k++) {
             const uint32_t b = tid * per + k;
             if (k < (int)per && b < F) {
-                const uint32_t g = c[k] ? atomicAdd(&my_bins[b], c[k]) : 0u;
+                uint32_t g = 0u;
+                if (PEER && peers.cursor[b]) {
+                    if (c[k]) {
+                        const unsigned long long at = atomicAdd_system(peers.cursor[b], (unsigned long long)c[k]);
+                        atomicAdd(&peers.sent[b], (unsigned long long)c[k]);
+                        if (at + c[k] > peers.cap) {
+                            atomicAnd(&s_fits, ~(1u << b));
+                            atomicExch(peers.overflow, 1u);
+                        }
+                        g = (uint32_t)at;
+                    }
+                } else if (c[k]) {
+                    g = atomicAdd(&my_bins[b], c[k]);
+                }
                 s_delta[b] = g - off;  // output position = s_delta[bin] + position in the sorted tile
                 s_hist[b] = off;       // becomes the bin's cursor inside the sorted tile
                 off += c[k];
@@ -260,6 +275,7 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
             if (PEER) {  // the sorted tile is in bin order and s_hist[b] is now the end of bin b's run: count the runs that end at or before j
                 uint32_t b = 0;
                 for (uint32_t q = 0; q + 1 < F; q++) b += j >= s_hist[q];
+                if (!((s_fits >> b) & 1u)) continue;
                 peers.lo[b][pos] = st_lo[j];
                 if (WIDE) peers.hi[b][pos] = st_hi[j];
             } else {

@@ -1797,18 +1797,44 @@ int bch_count_fastq_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const ch
     if (!run || !ctxs || n_ctx < 1 || n_ctx > 8 || !fastq_path) return BC_EINVAL;
     try {
         run->multi_mode = 0;
-        const uint64_t total = ingest_fastq(run, ctxs, n_ctx, fastq_path, threads, batch_reads);
-        if (total_reads) *total_reads = total;
-        if (n_ctx == 1) return BC_OK;
         auto ck = [&](int rc, bc_ctx* c) {
             if (rc != BC_OK) throw Error(bc_last_error(c));
         };
         bc_profile prof;
         ck(bc_get_profile(ctxs[0], &prof), ctxs[0]);
-        if (prof.deferred_count) {
-            // 1 x 1 x n matrix of what every context holds for every owner; then each writes its runs into the owners' buffers
+        const bool exchange = n_ctx > 1 && prof.deferred_count;
+        auto open_all = [&](uint64_t cap) {
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_disconnect(ctxs[r]), ctxs[r]);
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_open(ctxs[r], (uint32_t)n_ctx, (uint32_t)r, cap), ctxs[r]);
+            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_connect_local(ctxs[r], ctxs), ctxs[r]);
+        };
+        uint64_t cap = 0;
+        if (exchange) {
+            // Receive buffers before the first batch, so that every batch's records leave for their owners right after its
+            // decode (streamed exchange).  Sized from the file: an owner gets about 1/n of the reads; a guess that turns out
+            // too small only costs the bulk exchange below.
+            struct stat st;
+            uint64_t bytes = stat(fastq_path, &st) == 0 ? (uint64_t)st.st_size : 0;
+            const std::string path = fastq_path;
+            if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0) bytes *= 4;
+            const uint64_t est_reads = bytes / (2 * (uint64_t)std::max<uint32_t>(run->cfg.template_len, 20) + 16) + 1024;
+            cap = est_reads / (uint64_t)n_ctx * 5 / 4 + 4096;
+            bool reuse = true;
+            for (int r = 0; r < n_ctx; r++) reuse = reuse && bc_exchange_capacity(ctxs[r]) >= cap;
+            if (reuse) cap = bc_exchange_capacity(ctxs[0]);
+            else open_all(cap);
+            for (int r = 1; r < n_ctx; r++)
+                if (bc_exchange_capacity(ctxs[r]) != cap) {
+                    open_all(cap);
+                    break;
+                }
+        }
+        const uint64_t total = ingest_fastq(run, ctxs, n_ctx, fastq_path, threads, batch_reads);
+        if (total_reads) *total_reads = total;
+        if (n_ctx == 1) return BC_OK;
+        if (exchange) {
+            // n x n matrix of what every context holds (or has streamed) for every owner
             std::vector<std::vector<uint64_t>> sent(n_ctx, std::vector<uint64_t>(n_ctx, 0));
-            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_open(ctxs[r], (uint32_t)n_ctx, (uint32_t)r, 1), ctxs[r]);  // geometry only
             for (int r = 0; r < n_ctx; r++) ck(bc_exchange_count(ctxs[r], sent[r].data()), ctxs[r]);
             uint64_t need = 1;
             std::vector<uint64_t> received(n_ctx, 0);
@@ -1816,9 +1842,10 @@ int bch_count_fastq_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const ch
                 for (int r = 0; r < n_ctx; r++) received[o] += sent[r][o];
                 need = std::max(need, received[o]);
             }
-            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_open(ctxs[r], (uint32_t)n_ctx, (uint32_t)r, need), ctxs[r]);
-            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_connect_local(ctxs[r], ctxs), ctxs[r]);
-            for (int r = 0; r < n_ctx; r++) ck(bc_exchange_count(ctxs[r], sent[r].data()), ctxs[r]);
+            if (need > cap) {  // an owner's share did not fit: larger buffers, and the whole exchange in bulk from the record buffers
+                open_all(need + need / 16);
+                for (int r = 0; r < n_ctx; r++) ck(bc_exchange_count(ctxs[r], sent[r].data()), ctxs[r]);
+            }
             for (int r = 0; r < n_ctx; r++) {
                 std::vector<uint64_t> first(n_ctx, 0);
                 for (int o = 0; o < n_ctx; o++)

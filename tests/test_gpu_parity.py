@@ -828,9 +828,10 @@ def test_import_rows_merge_without_random_barcode():
     assert ca["matched"] + cb["matched"] == cw["matched"] and sum(r[2] for r in want) == cw["matched"]
 
 
+@pytest.mark.parametrize("bulk", [False, True])
 @pytest.mark.parametrize("n_ranks", [2, 3])
 @pytest.mark.parametrize("case", ["del3_umi", "lineage_raw", "example", "sample_raw_two"])
-def test_exchange_between_contexts_on_one_gpu(case, n_ranks):
+def test_exchange_between_contexts_on_one_gpu(case, n_ranks, bulk):
     """The multi-GPU exchange (bc_exchange_*: records scattered into their owner's receive buffer by the partitioning
     kernel, every owner de-duplicating what it received) with the ranks being contexts on ONE GPU: the union of the
     owners' rows, and the sum of their counters, must be exactly what a single context gives on all the reads.  Covers
@@ -855,15 +856,39 @@ def test_exchange_between_contexts_on_one_gpu(case, n_ranks):
         c.exchange_open(n_ranks, r, batch.n + 16)
     for c in ranks:
         c.exchange_connect_local(ranks)
+        if bulk:  # the records leave after the last batch instead of batch by batch
+            c.set_option("exchange_bulk", 1)
     cuts = [batch.n * r // n_ranks for r in range(n_ranks + 1)]
-    for rep in range(2):  # twice: a reset in between must leave the exchange usable
+    for rep in range(3):  # several jobs: a reset in between must leave the exchange usable (the receive buffers alternate)
+        if rep == 2:  # buffers far too small: the streamed records do not fit, the job's exchange starts over in bulk
+            for c in ranks:
+                c.exchange_disconnect()
+            for r, c in enumerate(ranks):
+                c.exchange_open(n_ranks, r, max(1, batch.n // (4 * n_ranks)))
+            for c in ranks:
+                c.exchange_connect_local(ranks)
         for r, c in enumerate(ranks):
             c.reset()
-            c.submit(batch.slice(cuts[r], cuts[r + 1]))
+            mid = (cuts[r] + cuts[r + 1]) // 2
+            c.submit(batch.slice(cuts[r], mid))  # two batches per rank: the streamed exchange moves them one by one
+            c.submit(batch.slice(mid, cuts[r + 1]))
         with pytest.raises(bc.BcError):
             ranks[0].counters()  # a rank of a multi-GPU job has no counters before the exchange
         matrix = [c.exchange_count(n_ranks) for c in ranks]
         assert sum(map(sum, matrix)) == want_c["matched"] + want_c["duplicates"]
+        if rep == 2:
+            need = exchange_plan(matrix, 0)[2]
+            assert need > batch.n // (4 * n_ranks)
+            if not bulk:
+                with pytest.raises(bc.BcError):
+                    ranks[0].exchange_scatter(exchange_plan(matrix, 0)[0])
+            for c in ranks:
+                c.exchange_disconnect()
+            for r, c in enumerate(ranks):
+                c.exchange_open(n_ranks, r, need)
+            for c in ranks:
+                c.exchange_connect_local(ranks)
+            assert [c.exchange_count(n_ranks) for c in ranks] == matrix
         for r, c in enumerate(ranks):
             c.exchange_scatter(exchange_plan(matrix, r)[0])
         for c in ranks:
