@@ -36,7 +36,8 @@ bch_run *bch_open(const bch_args *args, char *err, int errlen);
 void bch_close(bch_run *run);
 /* Tuning / test switches of the host side (results never change).  "lean_writer_min_rows": count tables of at least this
  * many rows are written by the streaming CSV writer (text straight from the packed keys on all host threads; default 4 M);
- * "wire_batches": 0 makes bch_count_fastq hand the GPU plain bc_batch arrays instead of the transfer form (default 1). */
+ * "wire_batches": 0 makes bch_count_fastq hand the GPU plain bc_batch arrays instead of the transfer form (default 1);
+ * "fused_ingest": 0 makes it frame a whole block of a plain file before packing it instead of doing both in one pass (default 1). */
 int bch_set_option(bch_run *run, const char *name, long long value);
 /* The reference rewrites "Total sequences: N" in place while it reads (input.rs:54-57, 151-158): fn is called with the
  * number of records handed to the GPU so far, after every batch of bch_count_fastq[_multi]. */
@@ -70,8 +71,8 @@ int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, con
 size_t bch_wire_bound(uint32_t n_reads, uint32_t max_read_len, int with_qual);
 int bch_wire_from_batch(const bc_batch *batch, uint32_t max_read_len, uint32_t qual_bits, void *buf, size_t buf_bytes,
                         bc_wire_batch *out);
-/* Wall time of the phases of the last bch_count_fastq[_multi] on the ingest thread: seconds[5] = split (record framing),
- * pack, submit calls, waiting for copies / the GPU, total; counts[3] = batches, batches whose quality went as plain bytes,
+/* Wall time of the phases of the last bch_count_fastq[_multi] on the ingest thread: seconds[6] = split (record framing),
+ * pack, submit calls, waiting for copies / the GPU, total, mapping the file; counts[3] = batches, batches whose quality went as plain bytes,
  * batches whose N calls went as a dense plane. */
 int bch_ingest_stats(const bch_run *run, double *seconds, uint64_t *counts);
 
@@ -87,6 +88,13 @@ int bch_scan_fastq(const char *fastq_path, unsigned threads, uint64_t *n_records
  * 64 KB as in bch_count_fastq); reports like bch_scan_fastq.  No GPU work. */
 int bch_split_fastq(const char *fastq_path, unsigned threads, size_t block_bytes, size_t min_slice_bytes, uint64_t *n_records,
                     uint64_t *n_bases, uint32_t *crc, char *err, int errlen);
+
+/* Host-only test hook of the one-pass walker behind bch_count_fastq on plain files (a host thread frames a cache-sized chunk
+ * of the mapping and packs its records at once into rows it reserves in the batch): batches of batch_rows rows, chunks of
+ * chunk_bytes (0: 256 KB).  Checks that every row of every batch is filled exactly once; digest = sum over the records of
+ * the CRC-32 of their sequence and quality bytes (rows of a batch are in no particular order).  No GPU work. */
+int bch_walk_fastq(const char *fastq_path, unsigned threads, size_t chunk_bytes, uint32_t batch_rows, uint64_t *n_records,
+                   uint64_t *n_bases, uint64_t *digest, uint64_t *n_batches, char *err, int errlen);
 
 /* input::read_fastq replacement: streams a .fastq / .fastq.gz file through pinned double-buffered batches of
  * `batch_reads` reads into ctx (bc_submit).  threads = host threads (a pool kept by the run) that split and pack.

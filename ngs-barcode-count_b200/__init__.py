@@ -98,6 +98,16 @@ def split_fastq(path, threads=0, block_bytes=0, min_slice=0):
     return int(n.value), int(b.value), int(c.value)
 
 
+def walk_fastq(path, threads=0, chunk_bytes=0, batch_rows=1 << 16):
+    """(records, bases, sum of per-record crc32, batches) through the one-pass walker of bch_count_fastq's plain-file path (host only)."""
+    n, b, d, k = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    err = C.create_string_buffer(512)
+    rc = lib().bch_walk_fastq(os.fsencode(path), threads, chunk_bytes, batch_rows, C.byref(n), C.byref(b), C.byref(d), C.byref(k), err, 512)
+    if rc != 0:
+        raise BcError("bch_walk_fastq: " + err.value.decode())
+    return int(n.value), int(b.value), int(d.value), int(k.value)
+
+
 def count_fastq_multi(run, counters, path, threads=0, batch_reads=1 << 20):
     """bch_count_fastq_multi over several Counters (one per GPU, or several on one GPU in tests) -> reads"""
     arr = (C.c_void_p * len(counters))(*[c.h for c in counters])
@@ -199,6 +209,8 @@ _PROTOS = {
                                  C.c_int]),
     "bch_split_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                   C.c_char_p, C.c_int]),
+    "bch_walk_fastq": (C.c_int, [C.c_char_p, C.c_uint, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_char_p, C.c_int]),
     "bch_count_fastq_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_uint, C.c_uint32,
                                         C.POINTER(C.c_uint64), C.c_char_p, C.c_int]),
     "bch_counters_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_uint64)]),
@@ -493,9 +505,9 @@ class Counter:
 
     def ingest_stats(self):
         """phases of the last count_fastq on the ingest thread (seconds) and its batch counts"""
-        sec, cnt = (C.c_double * 5)(), (C.c_uint64 * 3)()
+        sec, cnt = (C.c_double * 6)(), (C.c_uint64 * 3)()
         lib().bch_ingest_stats(self.run.h, sec, cnt)
-        return dict(split_s=sec[0], pack_s=sec[1], submit_s=sec[2], wait_s=sec[3], total_s=sec[4], batches=int(cnt[0]),
+        return dict(split_s=sec[0], pack_s=sec[1], submit_s=sec[2], wait_s=sec[3], total_s=sec[4], map_s=sec[5], batches=int(cnt[0]),
                     batches_qual8=int(cnt[1]), batches_dense_n=int(cnt[2]))
 
     def write_counts(self, outdir, prefix, merge=False, enrich=False):

@@ -356,7 +356,7 @@ struct IngestBuffers {
 };
 
 struct IngestStats {  // wall time of the phases of the last ingest, on the ingest thread (bch_ingest_stats)
-    double split_s = 0, pack_s = 0, submit_s = 0, wait_s = 0, total_s = 0;
+    double split_s = 0, pack_s = 0, submit_s = 0, wait_s = 0, total_s = 0, map_s = 0;
     uint64_t batches = 0, batches_qual8 = 0, batches_dense_n = 0, h2d_bytes = 0;
 };
 
@@ -379,6 +379,8 @@ struct bch_run {
     void* progress_user = nullptr;
     uint64_t lean_rows = 4u << 20;  // tables of at least this many rows go through the lean CSV writer (bch_set_option)
     bool wire_batches = true;       // host batches cross PCIe in their transfer form (bc_submit_wire); 0: as bc_batch
+    bool fused_ingest = true;       // plain files: frame and pack in one pass over the text (FusedWalk); 0: split, then pack
+    int mmap_populate = 0;          // measurement: 1 maps a plain file with MAP_POPULATE, 2 lets every worker populate its chunk
     IngestStats stats;
     int multi_mode = 0;  // after bch_count_fastq_multi: 1 = rows partitioned over the contexts, 2 = all rows on the first
 };
@@ -606,8 +608,19 @@ inline bool pack_planes(const char* seq, uint32_t len, uint32_t W, uint32_t* lo,
     bool other = false;
     uint32_t w = 0, base = 0;
 #if defined(__x86_64__)
-    if (kHaveAvx2)
+    if (kHaveAvx2) {
         for (; base + 32 <= len; base += 32, w++) pack_word_avx2(seq + base, &lo[w], &hi[w], &nm[w], &other);
+        if (base < len) {  // the last, partial word through the same vector code: a padded copy ('A' = 00, never N or other)
+            char tail[32];
+            const uint32_t m = len - base;
+            memset(tail, 'A', sizeof tail);
+            memcpy(tail, seq + base, m);
+            pack_word_avx2(tail, &lo[w], &hi[w], &nm[w], &other);
+            w++;
+        }
+        for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
+        return other;
+    }
 #endif
     for (; base < len; base += 32, w++) pack_word_scalar(seq + base, std::min(32u, len - base), &lo[w], &hi[w], &nm[w], &other);
     for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
@@ -719,34 +732,50 @@ inline bool pack_qual6_scalar(const uint8_t* c, uint32_t n_codes, uint8_t* out) 
     return ok;
 }
 #if defined(__x86_64__)
-__attribute__((target("avx2"))) inline bool pack_qual6_avx2(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
+// 32 characters -> 24 bytes of codes (shared by the full groups and the padded last one)
+__attribute__((target("avx2"))) inline void qual6_group(const __m256i v, __m256i& bad, __m256i& lowest, uint8_t* out24) {
     const __m256i k33 = _mm256_set1_epi8(33), k63 = _mm256_set1_epi8(63), k62 = _mm256_set1_epi8(62), kff = _mm256_set1_epi8((char)0xFF);
     const __m256i mul1 = _mm256_set1_epi16(0x4001), mul2 = _mm256_set1_epi32(0x10000001);
     const __m256i shuf = _mm256_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1, 0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
-    __m256i bad = _mm256_setzero_si256();
+    const __m256i mark = _mm256_cmpeq_epi8(v, kff);
+    lowest = _mm256_min_epu8(lowest, v);
+    __m256i code = _mm256_sub_epi8(v, k33);
+    bad = _mm256_or_si256(bad, _mm256_andnot_si256(mark, _mm256_xor_si256(_mm256_cmpeq_epi8(_mm256_max_epu8(code, k62), k62), kff)));
+    code = _mm256_and_si256(_mm256_blendv_epi8(code, k63, mark), k63);
+    const __m256i m = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code, mul1), mul2), shuf);
+    const __m128i a = _mm256_castsi256_si128(m), b = _mm256_extracti128_si256(m, 1);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out24), a);
+    const uint32_t a2 = (uint32_t)_mm_extract_epi32(a, 2), b2 = (uint32_t)_mm_extract_epi32(b, 2);
+    memcpy(out24 + 8, &a2, 4);
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(out24 + 12), b);
+    memcpy(out24 + 20, &b2, 4);
+}
+// the first n_valid characters come from c, the rest of the n_codes (a multiple of 4) are '!'; *lowest_out = smallest character seen
+__attribute__((target("avx2"))) inline bool pack_qual6_avx2(const uint8_t* c, uint32_t n_valid, uint32_t n_codes, uint8_t* out, uint8_t* lowest_out) {
+    __m256i bad = _mm256_setzero_si256(), lowest = _mm256_set1_epi8((char)0xFF);
     uint32_t i = 0;
-    for (; i + 32 <= n_codes; i += 32, out += 24) {
-        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(c + i));
-        const __m256i mark = _mm256_cmpeq_epi8(v, kff);
-        __m256i code = _mm256_sub_epi8(v, k33);
-        bad = _mm256_or_si256(bad, _mm256_andnot_si256(mark, _mm256_xor_si256(_mm256_cmpeq_epi8(_mm256_max_epu8(code, k62), k62), kff)));
-        code = _mm256_and_si256(_mm256_blendv_epi8(code, k63, mark), k63);
-        const __m256i m = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(code, mul1), mul2), shuf);
-        const __m128i a = _mm256_castsi256_si128(m), b = _mm256_extracti128_si256(m, 1);
-        _mm_storel_epi64(reinterpret_cast<__m128i*>(out), a);
-        const uint32_t a2 = (uint32_t)_mm_extract_epi32(a, 2), b2 = (uint32_t)_mm_extract_epi32(b, 2);
-        memcpy(out + 8, &a2, 4);
-        _mm_storel_epi64(reinterpret_cast<__m128i*>(out + 12), b);
-        memcpy(out + 20, &b2, 4);
+    for (; i + 32 <= n_valid; i += 32, out += 24) qual6_group(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(c + i)), bad, lowest, out);
+    for (; i < n_codes; i += 32, out += 24) {  // padded groups ('!' = code 0), stored as far as the record goes
+        uint8_t tail[32], packed[24];
+        memset(tail, '!', sizeof tail);
+        if (i < n_valid) memcpy(tail, c + i, n_valid - i);
+        qual6_group(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(tail)), bad, lowest, packed);
+        memcpy(out, packed, (size_t)std::min(32u, n_codes - i) / 4 * 3);
     }
-    bool ok = _mm256_testz_si256(bad, bad) != 0;
-    if (i < n_codes) ok = pack_qual6_scalar(c + i, n_codes - i, out) && ok;
-    return ok;
+    if (lowest_out) {
+        __m128i m = _mm_min_epu8(_mm256_castsi256_si128(lowest), _mm256_extracti128_si256(lowest, 1));
+        m = _mm_min_epu8(m, _mm_srli_si128(m, 8));
+        m = _mm_min_epu8(m, _mm_srli_si128(m, 4));
+        m = _mm_min_epu8(m, _mm_srli_si128(m, 2));
+        m = _mm_min_epu8(m, _mm_srli_si128(m, 1));
+        *lowest_out = (uint8_t)_mm_extract_epi8(m, 0);
+    }
+    return _mm256_testz_si256(bad, bad) != 0;
 }
 #endif
 inline bool pack_qual6(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
 #if defined(__x86_64__)
-    if (kHaveAvx2) return pack_qual6_avx2(c, n_codes, out);
+    if (kHaveAvx2) return pack_qual6_avx2(c, n_codes, n_codes, out, nullptr);
 #endif
     return pack_qual6_scalar(c, n_codes, out);
 }
@@ -806,6 +835,21 @@ bool pack_range_wire(uint32_t mrl, const WireLayout& L, unsigned char* arena, co
             continue;
         }
         bool other = pack_planes(r.seq, r.len, W, lo, lo + W, nm + row * W);
+#if defined(__x86_64__)
+        if (bits == 6 && kHaveAvx2 && r.qlen >= r.len) {  // the usual read: codes straight from the text, one pass
+            uint8_t lowest = 255;
+            const bool ok = pack_qual6_avx2(reinterpret_cast<const uint8_t*>(r.qual), r.len, L.n_codes, q + row * qs, &lowest);
+            if (r.len && lowest < 33) {  // Q13, as pack_one: flagged, never decoded — any representable characters do
+                other = true;
+                memset(chars, '!', L.n_codes);
+                pack_qual6(chars, L.n_codes, q + row * qs);
+            } else {
+                fits = ok && fits;
+            }
+            rl[row] = (uint16_t)(r.len | (other ? BC_READ_UNSUPPORTED : 0u));
+            continue;
+        }
+#endif
         if (bits) {
             const uint32_t n = std::min(r.qlen, r.len);
             unsigned char lowest = 255;
@@ -932,15 +976,54 @@ const char* find_record_start(const char* p, const char* end) {
     return end;
 }
 
+// Line ends of [p, end) one after the other.  32 bytes per step: a record's four line ends come out of about ten compares
+// instead of four memchr calls (whose set-up dominates on lines this short).
+struct NewlineScan {
+    const char* next_block;  // first byte not yet compared
+    const char* end;
+    const char* cur = nullptr;  // block the pending mask belongs to
+    uint32_t mask = 0;
+    NewlineScan(const char* p, const char* e) : next_block(p), end(e) {}
+#if defined(__x86_64__)
+    __attribute__((target("avx2"))) const char* next_avx2() {
+        while (mask == 0) {
+            if (next_block + 32 > end) {  // the last bytes of the range: no load past its end
+                if (next_block >= end) return nullptr;
+                const char* nl = (const char*)memchr(next_block, '\n', (size_t)(end - next_block));
+                next_block = nl ? nl + 1 : end;
+                return nl;
+            }
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(next_block));
+            mask = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('\n')));
+            cur = next_block;
+            next_block += 32;
+        }
+        const char* at = cur + __builtin_ctz(mask);
+        mask &= mask - 1;
+        return at;
+    }
+#endif
+    const char* next() {
+#if defined(__x86_64__)
+        if (kHaveAvx2) return next_avx2();
+#endif
+        if (next_block >= end) return nullptr;
+        const char* nl = (const char*)memchr(next_block, '\n', (size_t)(end - next_block));
+        next_block = nl ? nl + 1 : end;
+        return nl;
+    }
+};
+
 // whole records of [p, end) -> out; returns the position after the last whole record.  at_eof: the last line may lack '\n'.
 const char* split_records(const char* p, const char* end, bool at_eof, std::vector<ReadRef>& out) {
+    NewlineScan scan(p, end);
     for (;;) {
         const char* line[4];
         uint32_t len[4];
         const char* q = p;
         int k = 0;
         for (; k < 4; k++) {
-            const char* nl = q < end ? (const char*)memchr(q, '\n', (size_t)(end - q)) : nullptr;
+            const char* nl = q < end ? scan.next() : nullptr;
             const char* stop;
             if (nl) stop = nl;
             else if (at_eof && k == 3 && q < end) stop = end;
@@ -965,12 +1048,12 @@ struct MappedFile {
         if (data && size) munmap(const_cast<char*>(data), size);
         if (fd >= 0) close(fd);
     }
-    bool open_plain(const char* path) {  // false: not a plain regular file we can map (gzip, pipe, empty...)
+    bool open_plain(const char* path, int populate = 0) {  // false: not a plain regular file we can map (gzip, pipe, empty...)
         fd = open(path, O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 2) return false;
-        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | (populate == 1 ? MAP_POPULATE : 0), fd, 0);
         if (m == MAP_FAILED) return false;
         data = static_cast<const char*>(m);
         size = (size_t)st.st_size;
@@ -1155,6 +1238,118 @@ const char* split_block(Pool& pool, const char* pos, const char* blk_end, bool l
     seq.longest = longest;
     return consumed;
 }
+
+// ---- plain FASTQ in ONE pass over the text ------------------------------------------------------------------------------
+// split_block + pack read every byte of the file twice (the split leaves the text in DRAM again before the pack comes back
+// to it), and on the ingest host both passes run at memory speed.  Here a host thread takes a chunk of the mapping that
+// fits its cache (a few hundred records), frames its records, reserves that many rows of the batch with one atomic and packs
+// them at once.  A chunk that does not fit the rows left in the batch is packed as far as it goes; its remainder (a text
+// range that starts at a record) is the first work of the next batch.  Rows of a batch are therefore in no particular order,
+// which the counts do not depend on.
+struct TextRange {
+    const char* b;
+    const char* e;
+};
+struct PackedRange {  // records of [b, e) went to rows [base, base + n)
+    const char* b;
+    const char* e;
+    size_t base, n;
+};
+inline const char* after_record(const ReadRef& r, const char* end) {
+    const char* p = r.qual + r.qlen;
+    if (p < end && *p == '\r') p++;
+    if (p < end && *p == '\n') p++;
+    return p;
+}
+
+class FusedWalk {
+  public:
+    FusedWalk(Pool& pool, const char* data, size_t size, size_t chunk_bytes)
+        : pool_(pool), data_(data), eof_(data + size), chunk_(std::max<size_t>(chunk_bytes, 64)), n_chunks_((size + chunk_ - 1) / chunk_),
+          refs_(pool.size()), done_(pool.size()) {}
+    bool more() const { return !carried_.empty() || next_chunk_.load() < n_chunks_; }
+    const std::vector<std::vector<PackedRange>>& done() const { return done_; }
+    // One batch of up to `cap` rows: pack(t, refs, base, n, first_text, end_text) is called on the pool's threads (t = worker slot).
+    // Returns the rows filled.
+    template <class Pack>
+    size_t batch(size_t cap, Pack pack) {
+        std::atomic<size_t> cursor{0}, carried_next{0};
+        std::vector<TextRange> deferred;
+        std::mutex mu;
+        std::string error;
+        for (auto& d : done_) d.clear();
+        pool_.run(pool_.size(), [&](size_t t) {
+            std::vector<ReadRef>& R = refs_[t];
+            for (;;) {
+                if (cursor.load(std::memory_order_relaxed) >= cap) return;
+                TextRange it;
+                const size_t ci = carried_next.fetch_add(1);
+                if (ci < carried_.size()) {
+                    it = carried_[ci];
+                } else {
+                    const size_t c = next_chunk_.fetch_add(1);
+                    if (c >= n_chunks_) return;
+                    it = TextRange{bound(c), bound(c + 1)};
+#ifdef MADV_POPULATE_READ
+                    if (populate_ && it.b < it.e) {
+                        const uintptr_t a = (uintptr_t)it.b & ~(uintptr_t)4095, z = ((uintptr_t)it.e + 4095) & ~(uintptr_t)4095;
+                        madvise((void*)a, z - a, MADV_POPULATE_READ);
+                    }
+#endif
+                }
+                if (it.b >= it.e) continue;
+                R.clear();
+                const char* stop = split_records(it.b, it.e, it.e == eof_, R);
+                if (stop != it.e && it.e != eof_) {  // (at the end of the file a trailing partial record is dropped: the reference never posts it)
+                    std::lock_guard<std::mutex> lk(mu);
+                    error = "malformed FASTQ: a record near byte offset " + std::to_string((size_t)(stop - data_)) + " does not have four lines";
+                    cursor.store(cap);
+                    return;
+                }
+                if (R.empty()) continue;
+                const size_t n = R.size(), base = cursor.fetch_add(n), take = base >= cap ? 0 : std::min(n, cap - base);
+                const char* cut = take == n ? it.e : (take ? after_record(R[take - 1], it.e) : it.b);
+                if (take) {
+                    pack(t, R.data(), base, take);
+                    done_[t].push_back(PackedRange{it.b, cut, base, take});
+                }
+                if (take < n) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    deferred.push_back(TextRange{cut, it.e});
+                    return;
+                }
+            }
+        });
+        if (!error.empty()) throw Error(error);
+        const size_t used = std::min(carried_next.load(), carried_.size());
+        carried_.erase(carried_.begin(), carried_.begin() + (std::ptrdiff_t)used);
+        carried_.insert(carried_.end(), deferred.begin(), deferred.end());
+        return std::min(cursor.load(), cap);
+    }
+
+  private:
+    // chunk c owns the records that START in [bound(c), bound(c + 1)): a boundary is the first record start after the first
+    // line end at or after the nominal position, so both neighbours compute the same one
+    const char* bound(size_t c) const {
+        if (c == 0) return data_;
+        if (c >= n_chunks_) return eof_;
+        const char* nominal = data_ + c * chunk_;
+        const char* nl = (const char*)memchr(nominal, '\n', (size_t)(eof_ - nominal));
+        return nl ? find_record_start(nl + 1, eof_) : eof_;
+    }
+  public:
+    bool populate_ = false;
+
+  private:
+    Pool& pool_;
+    const char* data_;
+    const char* eof_;
+    size_t chunk_, n_chunks_;
+    std::atomic<size_t> next_chunk_{0};
+    std::vector<TextRange> carried_;
+    std::vector<std::vector<ReadRef>> refs_;
+    std::vector<std::vector<PackedRange>> done_;
+};
 
 // ---- one ingest: blocks of records -> pinned batches -> bc_submit, round-robin over the contexts ----------------------
 struct Ingest {
@@ -1361,6 +1556,111 @@ struct Ingest {
         return n;
     }
 
+    // a mapped plain FASTQ file in one pass over its text (FusedWalk): rows packed straight into the transfer form.  A batch
+    // that meets what the fast form does not hold — a read longer than the run's geometry, a quality character beyond '_' — is
+    // framed again from its text ranges and goes through submit(), which packs wider / plainer.
+    void run_fused(const char* data, size_t size) {
+        const WireLayout L(batch_reads, mrl0, with_qual);
+        const size_t est_record = 2 * (size_t)mrl0 + 32;
+        const size_t chunk = std::min<size_t>(256u << 10, std::max<size_t>(4096, (size_t)batch_reads * est_record / 64));
+        FusedWalk walk(*pool, data, size, chunk);
+        walk.populate_ = run->mmap_populate == 2;
+        const size_t T = pool->size();
+        std::vector<std::vector<uint32_t>> creads(T);
+        std::vector<std::vector<uint16_t>> cpos(T);
+        std::vector<std::vector<ReadRef>> parts;
+        RecSeq seq;
+        const uint32_t bits = with_qual ? 6u : 0u;
+        while (walk.more()) {
+            const int d = (int)(n_batches % (uint64_t)n_ctx);
+            Lane& ln = *run->ingest.lanes[d];
+            bc_ctx* ctx = ctxs[d];
+            if (ln.in_flight == 2) {
+                const auto t0 = Clock::now();
+                if (bc_wait_copies(ctx) != BC_OK) throw Error(bc_last_error(ctx));
+                st.wait_s += since(t0);
+                ln.in_flight = 0;
+            }
+            PinnedBatch& p = ln.pinned[ln.cur];
+            const uint32_t* nm = reinterpret_cast<const uint32_t*>(p.arena + L.o_nm);
+            std::atomic<int> anomaly{0};
+            for (size_t t = 0; t < T; t++) {
+                creads[t].clear();
+                cpos[t].clear();
+            }
+            auto t0 = Clock::now();
+            const size_t n = walk.batch(batch_reads, [&](size_t t, const ReadRef* r, size_t base, size_t take) {
+                for (size_t i = 0; i < take; i++)
+                    if (r[i].len > mrl0) anomaly = 1;
+                if (!pack_range_wire(mrl0, L, p.arena, r, base, take, bits)) anomaly = 1;
+                list_ncalls(nm, L.W, base, take, creads[t], cpos[t]);
+            });
+            st.pack_s += since(t0);
+            if (n == 0) continue;
+            if (anomaly) {
+                t0 = Clock::now();
+                size_t k = 0;
+                for (const auto& list : walk.done()) k += list.size();
+                if (parts.size() < k) parts.resize(k);
+                k = 0;
+                for (const auto& list : walk.done())
+                    for (const PackedRange& pr : list) {
+                        parts[k].clear();
+                        split_records(pr.b, pr.e, pr.e == data + size, parts[k]);
+                        if (parts[k].size() != pr.n) throw Error("internal: a text range framed differently the second time");
+                        k++;
+                    }
+                seq.index(parts, k);
+                for (size_t i = 0; i < k; i++) {
+                    uint32_t m = 0;
+                    for (const ReadRef& r : parts[i]) m = std::max(m, r.len);
+                    seq.longest[i] = m;
+                }
+                st.split_s += since(t0);
+                submit(seq);
+                continue;
+            }
+            t0 = Clock::now();
+            size_t n_calls = 0;
+            for (size_t t = 0; t < T; t++) n_calls += creads[t].size();
+            const bool list = n_calls <= WireLayout(n, mrl0, with_qual).list_cap && n_calls <= L.list_cap;
+            if (list && n_calls) {
+                uint32_t* nr = reinterpret_cast<uint32_t*>(p.arena + L.o_nr);
+                uint16_t* np = reinterpret_cast<uint16_t*>(p.arena + L.o_np);
+                size_t at = 0;
+                for (size_t t = 0; t < T; t++) {
+                    if (creads[t].empty()) continue;
+                    memcpy(nr + at, creads[t].data(), creads[t].size() * 4);
+                    memcpy(np + at, cpos[t].data(), cpos[t].size() * 2);
+                    at += creads[t].size();
+                }
+            }
+            if (!list) st.batches_dense_n++;
+            st.pack_s += since(t0);
+            bc_wire_batch wb{};
+            wb.n_reads = (uint32_t)n;
+            wb.max_read_len = mrl0;
+            wb.qual_bits = bits;
+            wb.qual_stride = bits ? bc_wire_qual_stride(mrl0, bits) : 0;
+            wb.n_calls = list ? (uint32_t)n_calls : 0;
+            wb.lohi = reinterpret_cast<const uint32_t*>(p.arena + L.o_lohi);
+            wb.read_len = reinterpret_cast<const uint16_t*>(p.arena + L.o_len);
+            wb.nmask = list ? nullptr : nm;
+            wb.n_read = reinterpret_cast<const uint32_t*>(p.arena + L.o_nr);
+            wb.n_pos = reinterpret_cast<const uint16_t*>(p.arena + L.o_np);
+            wb.qual = bits ? p.arena + L.o_q : nullptr;
+            t0 = Clock::now();
+            if (bc_submit_wire(ctx, &wb) != BC_OK) throw Error(bc_last_error(ctx));
+            st.submit_s += since(t0);
+            st.batches++;
+            total += n;
+            n_batches++;
+            ln.cur ^= 1;
+            ln.in_flight++;
+            if (run->progress) run->progress(total, run->progress_user);
+        }
+    }
+
     void finish() {
         const auto t0 = Clock::now();
         for (int d = 0; d < n_ctx; d++)
@@ -1388,7 +1688,15 @@ uint64_t ingest_fastq(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const char* 
     Ingest ing(run, ctxs, n_ctx, threads, batch_reads);
     IngestBuffers& I = run->ingest;
     MappedFile mf;
-    if (mf.open_plain(fastq_path)) {
+    const auto t_map = Ingest::Clock::now();
+    const bool plain = mf.open_plain(fastq_path, run->mmap_populate);
+    ing.st.map_s = Ingest::since(t_map);
+    if (plain && run->wire_batches && run->fused_ingest) {
+        ing.run_fused(mf.data, mf.size);
+        ing.finish();
+        return ing.total;
+    }
+    if (plain) {
         // plain file: no read() copy at all; every host thread splits and packs its own slice of each block of the mapping
         const size_t block_bytes = I.blocks[0].buf.size();
         const char* pos = mf.data;
@@ -1551,6 +1859,14 @@ int bch_set_option(bch_run* run, const char* name, long long value) {
         run->wire_batches = value != 0;
         return BC_OK;
     }
+    if (!strcmp(name, "mmap_populate")) {
+        run->mmap_populate = (int)value;
+        return BC_OK;
+    }
+    if (!strcmp(name, "fused_ingest")) {
+        run->fused_ingest = value != 0;
+        return BC_OK;
+    }
     if (!strcmp(name, "lean_writer_min_rows") && value >= 0) run->lean_rows = (uint64_t)value;
     else return BC_EINVAL;
     return BC_OK;
@@ -1700,6 +2016,7 @@ int bch_ingest_stats(const bch_run* run, double* seconds, uint64_t* counts) {
     if (!run || !seconds || !counts) return BC_EINVAL;
     const IngestStats& s = run->stats;
     seconds[0] = s.split_s; seconds[1] = s.pack_s; seconds[2] = s.submit_s; seconds[3] = s.wait_s; seconds[4] = s.total_s;
+    seconds[5] = s.map_s;
     counts[0] = s.batches; counts[1] = s.batches_qual8; counts[2] = s.batches_dense_n;
     return BC_OK;
 }
@@ -1767,6 +2084,55 @@ int bch_split_fastq(const char* fastq_path, unsigned threads, size_t block_bytes
         if (n_records) *n_records = recs;
         if (n_bases) *n_bases = bases;
         if (crc) *crc = (uint32_t)c;
+        return BC_OK;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());
+        return BC_EINVAL;
+    }
+}
+
+// host-only test hook of the one-pass walker: batches of `batch_rows` rows, chunks of chunk_bytes; every record must land on
+// exactly one row of exactly one batch.  digest = sum over records of crc32(sequence, quality) (the order is not defined).
+int bch_walk_fastq(const char* fastq_path, unsigned threads, size_t chunk_bytes, uint32_t batch_rows, uint64_t* n_records, uint64_t* n_bases,
+                   uint64_t* digest, uint64_t* n_batches, char* err, int errlen) {
+    if (!fastq_path || batch_rows == 0) return BC_EINVAL;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    try {
+        MappedFile mf;
+        if (!mf.open_plain(fastq_path)) throw Error("not a plain, mappable FASTQ file");
+        Pool pool(threads);
+        FusedWalk walk(pool, mf.data, mf.size, chunk_bytes ? chunk_bytes : (256u << 10));
+        uint64_t recs = 0, batches = 0;
+        std::atomic<uint64_t> bases{0}, dig{0};
+        std::vector<uint8_t> hit(batch_rows);
+        while (walk.more()) {
+            std::fill(hit.begin(), hit.end(), 0);
+            const size_t n = walk.batch(batch_rows, [&](size_t, const ReadRef* r, size_t base, size_t take) {
+                uint64_t b = 0, d = 0;
+                for (size_t i = 0; i < take; i++) {
+                    uLong c = crc32(0L, Z_NULL, 0);
+                    c = crc32(c, reinterpret_cast<const unsigned char*>(r[i].seq), r[i].len);
+                    c = crc32(c, reinterpret_cast<const unsigned char*>(r[i].qual), r[i].qlen);
+                    d += (uint64_t)c;
+                    b += r[i].len;
+                    hit[base + i]++;
+                }
+                bases += b;
+                dig += d;
+            });
+            for (size_t i = 0; i < batch_rows; i++)
+                if (hit[i] != (i < n ? 1 : 0)) throw Error("row " + std::to_string(i) + " of a batch of " + std::to_string(n) + " was packed " + std::to_string((int)hit[i]) + " times");
+            size_t ranged = 0;
+            for (const auto& list : walk.done())
+                for (const PackedRange& pr : list) ranged += pr.n;
+            if (ranged != n) throw Error("the packed ranges do not add up to the batch");
+            recs += n;
+            batches += n ? 1 : 0;
+        }
+        if (n_records) *n_records = recs;
+        if (n_bases) *n_bases = bases.load();
+        if (digest) *digest = dig.load();
+        if (n_batches) *n_batches = batches;
         return BC_OK;
     } catch (const std::exception& e) {
         if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", e.what());

@@ -879,9 +879,14 @@ def test_exchange_between_contexts_on_one_gpu(case, n_ranks, bulk):
         if rep == 2:
             need = exchange_plan(matrix, 0)[2]
             assert need > batch.n // (4 * n_ranks)
-            if not bulk:
-                with pytest.raises(bc.BcError):
-                    ranks[0].exchange_scatter(exchange_plan(matrix, 0)[0])
+            if not bulk:  # the rank(s) whose run passed the end of an owner's buffer refuse to go on
+                refused = 0
+                for r, c in enumerate(ranks):
+                    try:
+                        c.exchange_scatter(exchange_plan(matrix, r)[0])
+                    except bc.BcError:
+                        refused += 1
+                assert refused >= 1
             for c in ranks:
                 c.exchange_disconnect()
             for r, c in enumerate(ranks):

@@ -142,3 +142,63 @@ def test_mapped_splitter_reports_malformed_records(tmp_path):
     with pytest.raises(bc.BcError):
         for threads in (4, 16):
             bc.split_fastq(str(p), threads=threads, block_bytes=50_000, min_slice=1000)
+
+
+# ---- the one-pass walker behind bch_count_fastq on plain files (frame + pack a cache-sized chunk at a time) ------------------
+def digest_of(data):
+    """what bch_walk_fastq reports for a well-formed FASTQ text"""
+    lines = data.decode().replace("\r\n", "\n").split("\n")
+    n = bases = dig = 0
+    for i in range(0, len(lines) - 3, 4):
+        seq, qual = lines[i + 1], lines[i + 3]
+        dig += zlib.crc32(qual.encode(), zlib.crc32(seq.encode(), zlib.crc32(b"")))
+        bases += len(seq)
+        n += 1
+    return n, bases, dig & ((1 << 64) - 1)
+
+
+@pytest.mark.parametrize("crlf,last_newline", [(False, True), (True, True), (False, False), (True, False)])
+def test_walker_fills_every_row_once(tmp_path, crlf, last_newline):
+    data, want = make_fastq(40000, 33, crlf=crlf, last_newline=last_newline)
+    p = tmp_path / "r.fastq"
+    p.write_bytes(data)
+    n, bases, dig = digest_of(data)
+    assert (n, bases) == want[:2]
+    for threads, chunk, rows in ((1, 0, 1 << 16), (7, 4096, 5000), (16, 700, 37), (64, 100_000, 1000), (3, 64, 3), (16, 300, 1)):
+        got = bc.walk_fastq(str(p), threads=threads, chunk_bytes=chunk, batch_rows=rows)
+        assert got[:3] == (n, bases, dig), (threads, chunk, rows)
+        assert got[3] >= (n + rows - 1) // rows  # batches: full ones, except that an empty tail range may end one early
+
+
+@pytest.mark.parametrize("n_records", [1, 2, 3, 5, 20, 700])
+@pytest.mark.parametrize("last_newline", [True, False])
+def test_walker_small_files_many_threads(tmp_path, n_records, last_newline):
+    data, _ = make_fastq(n_records, 200 + n_records, last_newline=last_newline)
+    p = tmp_path / "r.fastq"
+    p.write_bytes(data)
+    want = digest_of(data)
+    for threads in (1, 2, 16, 64):
+        for chunk, rows in ((0, 1 << 16), (64, 4), (200, 1), (1000, 3)):
+            assert bc.walk_fastq(str(p), threads=threads, chunk_bytes=chunk, batch_rows=rows)[:3] == want, (threads, chunk, rows)
+
+
+def test_walker_quality_lines_starting_with_at_and_malformed_records(tmp_path):
+    rng = random.Random(4)
+    recs = []
+    for i in range(5000):
+        n = rng.randint(20, 60)
+        seq = "".join(rng.choice("ACGT") for _ in range(n))
+        qual = "@" + "".join(rng.choice("@+IF") for _ in range(n - 1))
+        recs.append(f"@r{i}\n{seq}\n+\n{qual}\n")
+    data = "".join(recs).encode()
+    p = tmp_path / "at.fastq"
+    p.write_bytes(data)
+    for threads in (1, 5, 32):
+        assert bc.walk_fastq(str(p), threads=threads, chunk_bytes=1000, batch_rows=777)[:3] == digest_of(data)
+    good, _ = make_fastq(3000, 8)
+    lines = good.decode().split("\n")
+    del lines[4001]  # a record in the middle loses its sequence line
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes("\n".join(lines).encode())
+    with pytest.raises(bc.BcError):
+        bc.walk_fastq(str(bad), threads=4, chunk_bytes=5000, batch_rows=500)
