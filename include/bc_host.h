@@ -63,6 +63,10 @@ int bch_pack(uint32_t max_read_len, uint32_t n, const char *const *seqs, const c
 int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char *seq_lines, const char *qual_lines, uint32_t *planes_out,
                    uint16_t *read_len_out, uint8_t *qual_out, unsigned threads);
 
+/* The packers and the line-end scanner exist in scalar, AVX2 and AVX-512 (BW + VBMI) form and use the best the CPU has.
+ * Test hook: cap them at level 0 (scalar), 1 (AVX2) or 2 (AVX-512); returns the level now in use.  Process-wide. */
+int bch_set_simd_level(int level);
+
 /* The transfer form of a host batch (bc_wire_batch, bc_submit_wire): bch_wire_from_batch converts a host bc_batch of
  * geometry max_read_len into arrays laid out in `buf` (at least bch_wire_bound bytes; pinned memory for full-rate copies)
  * and fills *out with pointers into it.  qual_bits = 0 picks the narrowest quality form that holds every character of the

@@ -202,6 +202,7 @@ _PROTOS = {
     "bch_pack": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_uint]),
     "bch_pack_lines": (C.c_int, [C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "bch_set_simd_level": (C.c_int, [C.c_int]),
     "bch_wire_bound": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_int]),
     "bch_wire_from_batch": (C.c_int, [C.POINTER(bc_batch), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(bc_wire_batch)]),
     "bch_ingest_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -597,17 +597,53 @@ __attribute__((target("avx2"))) inline void pack_word_avx2(const char* seq, uint
     const uint32_t isN = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('N')));
     *other |= (*nm & ~isN) != 0;
 }
-const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+const bool kCpuAvx2 = __builtin_cpu_supports("avx2");
+// 64 characters per step, compares straight into mask registers, byte permutes across the whole vector (VBMI)
+const bool kCpuAvx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512vbmi");
+bool kHaveAvx2 = kCpuAvx2, kHaveAvx512 = kCpuAvx512;  // what the packers use: the CPU's best, unless bch_set_simd_level caps it (tests)
+#define BC_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi")))
 #else
-const bool kHaveAvx2 = false;
+const bool kCpuAvx2 = false, kCpuAvx512 = false;
+bool kHaveAvx2 = false, kHaveAvx512 = false;
 #endif
 
 // one read -> three bit planes + length word (+ quality bytes)
+#if defined(__x86_64__)
+// 64 bases per step; a masked load takes the last, partial block without touching a byte beyond the read
+BC_AVX512 inline bool pack_planes_avx512(const char* seq, uint32_t len, uint32_t W, uint32_t* lo, uint32_t* hi, uint32_t* nm) {
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T'),
+                  cN = _mm512_set1_epi8('N');
+    uint64_t other = 0;
+    uint32_t w = 0;
+    for (uint32_t base = 0; base < len; base += 64, w += 2) {
+        const uint32_t m = len - base;
+        const __mmask64 k = m >= 64 ? ~0ULL : ((1ULL << m) - 1ULL);
+        const __m512i v = _mm512_maskz_loadu_epi8(k, seq + base);
+        const uint64_t isA = _mm512_mask_cmpeq_epi8_mask(k, v, cA), isC = _mm512_mask_cmpeq_epi8_mask(k, v, cC),
+                       isG = _mm512_mask_cmpeq_epi8_mask(k, v, cG), isT = _mm512_mask_cmpeq_epi8_mask(k, v, cT),
+                       isN = _mm512_mask_cmpeq_epi8_mask(k, v, cN);
+        const uint64_t l = isC | isT, h = isG | isT, x = (uint64_t)k & ~(isA | isC | isG | isT);
+        other |= x & ~isN;
+        lo[w] = (uint32_t)l;
+        hi[w] = (uint32_t)h;
+        nm[w] = (uint32_t)x;
+        if (w + 1 < W) {
+            lo[w + 1] = (uint32_t)(l >> 32);
+            hi[w + 1] = (uint32_t)(h >> 32);
+            nm[w + 1] = (uint32_t)(x >> 32);
+        }
+    }
+    for (; w < W; w++) lo[w] = hi[w] = nm[w] = 0;
+    return other != 0;
+}
+#endif
+
 // the bases of one read -> W words of each plane; true when the read holds a character outside ACGTN
 inline bool pack_planes(const char* seq, uint32_t len, uint32_t W, uint32_t* lo, uint32_t* hi, uint32_t* nm) {
     bool other = false;
     uint32_t w = 0, base = 0;
 #if defined(__x86_64__)
+    if (kHaveAvx512) return pack_planes_avx512(seq, len, W, lo, hi, nm);
     if (kHaveAvx2) {
         for (; base + 32 <= len; base += 32, w++) pack_word_avx2(seq + base, &lo[w], &hi[w], &nm[w], &other);
         if (base < len) {  // the last, partial word through the same vector code: a padded copy ('A' = 00, never N or other)
@@ -773,8 +809,47 @@ __attribute__((target("avx2"))) inline bool pack_qual6_avx2(const uint8_t* c, ui
     return _mm256_testz_si256(bad, bad) != 0;
 }
 #endif
+#if defined(__x86_64__)
+// 64 characters -> 48 bytes per step: masked load ('!' where the line has ended), two multiply-adds that merge four codes
+// into 24 bits, one byte permute across the vector that drops every fourth byte, masked store of exactly the bytes due
+BC_AVX512 inline bool pack_qual6_avx512(const uint8_t* c, uint32_t n_valid, uint32_t n_codes, uint8_t* out, uint8_t* lowest_out) {
+    const __m512i bang = _mm512_set1_epi8('!'), k33 = _mm512_set1_epi8(33), k63 = _mm512_set1_epi8(63), k62 = _mm512_set1_epi8(62),
+                  kff = _mm512_set1_epi8((char)0xFF), mul1 = _mm512_set1_epi16(0x4001), mul2 = _mm512_set1_epi32(0x10000001);
+    alignas(64) static const uint8_t kIdx[64] = {0,  1,  2,  4,  5,  6,  8,  9,  10, 12, 13, 14, 16, 17, 18, 20, 21, 22, 24, 25, 26, 28,
+                                                 29, 30, 32, 33, 34, 36, 37, 38, 40, 41, 42, 44, 45, 46, 48, 49, 50, 52, 53, 54, 56, 57,
+                                                 58, 60, 61, 62, 0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0};
+    const __m512i idx = _mm512_load_si512(kIdx);
+    __m512i lowest = kff;
+    uint64_t bad = 0;
+    for (uint32_t i = 0; i < n_codes; i += 64, out += 48) {
+        const uint32_t have = i < n_valid ? std::min(64u, n_valid - i) : 0u, due = std::min(64u, n_codes - i);
+        const __mmask64 k = have >= 64 ? ~0ULL : ((1ULL << have) - 1ULL);
+        const __m512i v = _mm512_mask_loadu_epi8(bang, k, c + i);
+        const uint64_t mark = _mm512_cmpeq_epi8_mask(v, kff);
+        lowest = _mm512_min_epu8(lowest, v);
+        __m512i code = _mm512_sub_epi8(v, k33);
+        bad |= _mm512_cmpgt_epu8_mask(code, k62) & ~mark;
+        code = _mm512_and_si512(_mm512_mask_mov_epi8(code, mark, k63), k63);
+        const __m512i m = _mm512_madd_epi16(_mm512_maddubs_epi16(code, mul1), mul2);
+        const __m512i packed = _mm512_permutexvar_epi8(idx, m);
+        const uint32_t bytes = due / 4 * 3;
+        _mm512_mask_storeu_epi8(out, bytes >= 64 ? ~0ULL : ((1ULL << bytes) - 1ULL), packed);
+    }
+    if (lowest_out) {
+        __m256i h = _mm256_min_epu8(_mm512_castsi512_si256(lowest), _mm512_extracti64x4_epi64(lowest, 1));
+        __m128i q = _mm_min_epu8(_mm256_castsi256_si128(h), _mm256_extracti128_si256(h, 1));
+        q = _mm_min_epu8(q, _mm_srli_si128(q, 8));
+        q = _mm_min_epu8(q, _mm_srli_si128(q, 4));
+        q = _mm_min_epu8(q, _mm_srli_si128(q, 2));
+        q = _mm_min_epu8(q, _mm_srli_si128(q, 1));
+        *lowest_out = (uint8_t)_mm_extract_epi8(q, 0);
+    }
+    return bad == 0;
+}
+#endif
 inline bool pack_qual6(const uint8_t* c, uint32_t n_codes, uint8_t* out) {
 #if defined(__x86_64__)
+    if (kHaveAvx512) return pack_qual6_avx512(c, n_codes, n_codes, out, nullptr);
     if (kHaveAvx2) return pack_qual6_avx2(c, n_codes, n_codes, out, nullptr);
 #endif
     return pack_qual6_scalar(c, n_codes, out);
@@ -838,7 +913,8 @@ bool pack_range_wire(uint32_t mrl, const WireLayout& L, unsigned char* arena, co
 #if defined(__x86_64__)
         if (bits == 6 && kHaveAvx2 && r.qlen >= r.len) {  // the usual read: codes straight from the text, one pass
             uint8_t lowest = 255;
-            const bool ok = pack_qual6_avx2(reinterpret_cast<const uint8_t*>(r.qual), r.len, L.n_codes, q + row * qs, &lowest);
+            const bool ok = kHaveAvx512 ? pack_qual6_avx512(reinterpret_cast<const uint8_t*>(r.qual), r.len, L.n_codes, q + row * qs, &lowest)
+                                        : pack_qual6_avx2(reinterpret_cast<const uint8_t*>(r.qual), r.len, L.n_codes, q + row * qs, &lowest);
             if (r.len && lowest < 33) {  // Q13, as pack_one: flagged, never decoded — any representable characters do
                 other = true;
                 memset(chars, '!', L.n_codes);
@@ -1003,8 +1079,26 @@ struct NewlineScan {
         return at;
     }
 #endif
+#if defined(__x86_64__)
+    uint64_t mask64 = 0;
+    BC_AVX512 const char* next_avx512() {
+        while (mask64 == 0) {
+            if (next_block >= end) return nullptr;
+            const size_t rem = (size_t)(end - next_block);
+            const __mmask64 k = rem >= 64 ? ~0ULL : ((1ULL << rem) - 1ULL);  // the masked load never touches a byte beyond the range
+            const __m512i v = _mm512_maskz_loadu_epi8(k, next_block);
+            mask64 = _mm512_mask_cmpeq_epi8_mask(k, v, _mm512_set1_epi8('\n'));
+            cur = next_block;
+            next_block += rem >= 64 ? 64 : rem;
+        }
+        const char* at = cur + __builtin_ctzll(mask64);
+        mask64 &= mask64 - 1;
+        return at;
+    }
+#endif
     const char* next() {
 #if defined(__x86_64__)
+        if (kHaveAvx512) return next_avx512();
         if (kHaveAvx2) return next_avx2();
 #endif
         if (next_block >= end) return nullptr;
@@ -1918,6 +2012,12 @@ int bch_pack_lines(uint32_t max_read_len, uint32_t n, const char* seq_lines, con
         s = se ? se + 1 : s + sl;
     }
     return pack_refs(max_read_len, refs, 0, n, planes_out, read_len_out, qual_lines ? qual_out : nullptr, threads);
+}
+
+int bch_set_simd_level(int level) {
+    kHaveAvx2 = kCpuAvx2 && level >= 1;
+    kHaveAvx512 = kCpuAvx512 && level >= 2;
+    return kHaveAvx512 ? 2 : kHaveAvx2 ? 1 : 0;
 }
 
 size_t bch_wire_bound(uint32_t n_reads, uint32_t max_read_len, int with_qual) {

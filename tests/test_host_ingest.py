@@ -202,3 +202,20 @@ def test_walker_quality_lines_starting_with_at_and_malformed_records(tmp_path):
     bad.write_bytes("\n".join(lines).encode())
     with pytest.raises(bc.BcError):
         bc.walk_fastq(str(bad), threads=4, chunk_bytes=5000, batch_rows=500)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_line_end_scanner_simd_levels(tmp_path, level):
+    """scalar / AVX2 / AVX-512 line-end scanners frame the same records (CRLF, no final newline, tiny chunks)"""
+    lib = bc.lib()
+    try:
+        lib.bch_set_simd_level(level)
+        for crlf, last_newline in ((False, True), (True, False)):
+            data, want = make_fastq(6000, 77, crlf=crlf, last_newline=last_newline)
+            p = tmp_path / f"r{int(crlf)}.fastq"
+            p.write_bytes(data)
+            assert bc.split_fastq(str(p), threads=5, block_bytes=200_000, min_slice=500) == want
+            for chunk, rows in ((0, 1 << 16), (333, 50), (64, 7)):
+                assert bc.walk_fastq(str(p), threads=6, chunk_bytes=chunk, batch_rows=rows)[:3] == digest_of(data)
+    finally:
+        lib.bch_set_simd_level(2)

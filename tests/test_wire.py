@@ -131,3 +131,29 @@ def test_wire_strides():
             assert qs % 4 == 0 and qs * 8 >= codes * bits and (qs - 4) * 8 < codes * bits
     # DEL geometry: 150-nt reads cross PCIe in 40 + 2 + 116 bytes (+ the N list) instead of 60 + 2 + 156
     assert lib.bc_wire_qual_stride(150, 6) == 116
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_packers_agree_across_simd_levels(level):
+    """The scalar, AVX2 and AVX-512 forms of the base packer, the 6-bit quality packer and the line-end scanner give the
+    same bytes (the level is capped by what the CPU has)."""
+    lib = bc.lib()
+    _, p = load_golden("example_q20")
+    rng = random.Random(11)
+    try:
+        outs = []
+        for lv in (0, level):
+            lib.bch_set_simd_level(lv)
+            res = []
+            for max_len in (1, 31, 32, 33, 63, 64, 65, 100, 127, 128, 150, 151, 250):
+                run = bc.Run(p["fmt"], p["samples"], p["counted"], min_quality=20.0, max_read_len=max(max_len, 100))
+                r2 = random.Random(max_len)
+                seqs, quals = random_reads(r2, 200, max_len, ALPHABETS[6])
+                batch = run.pack(seqs, quals)
+                wb = bc.WireBatch(batch, run.max_read_len, qual_bits=6)
+                res.append((batch.planes.copy(), batch.read_len.copy(), batch.qual.copy(), bytes(wb.buf[:wb.bound(batch.n, run.max_read_len, True)])))
+            outs.append(res)
+        for a, b in zip(*outs):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    finally:
+        lib.bch_set_simd_level(2)
