@@ -197,6 +197,10 @@ int bc_sync(bc_ctx *ctx);
 /* Blocks until the host->device copies of every submitted host batch are done (their memory may then be
  * rewritten) without waiting for the kernels. */
 int bc_wait_copies(bc_ctx *ctx);
+/* For a host that alternates between two batch buffers: blocks until the copies of every submitted host batch EXCEPT the
+ * most recent one are done, i.e. until the buffer handed over two submits ago may be rewritten, while the copy just queued
+ * keeps running.  (Batches of one form only — all bc_submit or all bc_submit_wire — between two calls.) */
+int bc_wait_older_copies(bc_ctx *ctx);
 
 /* Test / measurement switches of the counting step (results never change): "flush_global" = 1 sends the flush through
  * the global-memory hash tables (the fallback of oversized partitions), "flush_two_stage" = 1 always partitions by

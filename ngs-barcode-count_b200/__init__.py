@@ -161,6 +161,7 @@ _PROTOS = {
     "bc_submit_wire": (C.c_int, [C.c_void_p, C.POINTER(bc_wire_batch)]),
     "bc_sync": (C.c_int, [C.c_void_p]),
     "bc_wait_copies": (C.c_int, [C.c_void_p]),
+    "bc_wait_older_copies": (C.c_int, [C.c_void_p]),
     "bc_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bc_locate_only": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.POINTER(bc_locate_out)]),
     "bc_decode_only": (C.c_int, [C.c_void_p, C.POINTER(bc_batch), C.POINTER(bc_decode_out)]),

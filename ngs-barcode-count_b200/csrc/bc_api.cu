@@ -1338,6 +1338,17 @@ int bc_wait_copies(bc_ctx* ctx) {
     return BC_OK;
 }
 
+// Double buffering on the caller's side: before it rewrites the batch it handed over two submits ago it only has to wait
+// for THAT copy, not for the one just queued.  The staging slots alternate, so the slot the next submit will use is the one
+// whose copy must be over.
+int bc_wait_older_copies(bc_ctx* ctx) {
+    if (!ctx) return BC_EINVAL;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->staging[ctx->cur].copied_ev) CK(ctx, cudaEventSynchronize(ctx->staging[ctx->cur].copied_ev));
+    if (ctx->wire[ctx->wire_cur].copied_ev) CK(ctx, cudaEventSynchronize(ctx->wire[ctx->wire_cur].copied_ev));
+    return BC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- deferred counting
 // The whole record buffer -> final rows (ctx row buffers) and the matched / duplicates split.  A pure function of the
 // buffer (plus the imported rows), so it may run any number of times as more batches arrive.
