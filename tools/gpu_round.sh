@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k_decode -s 4 -c 1 -f -o gpurun_out/r2_decode_del3 $CMD > gpurun_out/ncu_decode.log 2>&1
 echo "decode rc=$?"
-# the step's flush: first big histogram/scatter/reduce launches of the timed step (the warm-up step has the same 9 launches before)
-ncu --set full --clock-control none --import-source on -k "regex:k_reduce|k_split_scatter|k_split_hist" -s 9 -c 5 -f -o gpurun_out/r2_flush_del3 $CMD > gpurun_out/ncu_flush.log 2>&1
+# the step's flush: first big histogram/scatter/reduce launches of the timed step (the warm-up step has the same 12 matching launches before)
+ncu --set full --clock-control none --import-source on -k "regex:k_reduce|k_split_scatter|k_split_hist" -s 12 -c 5 -f -o gpurun_out/r2_flush_del3 $CMD > gpurun_out/ncu_flush.log 2>&1
 echo "flush rc=$?"
