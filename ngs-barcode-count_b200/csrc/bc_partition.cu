@@ -113,11 +113,32 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
 // the same data); per-item stores straight to the output (partial-sector writes: the L2 reads each sector before
 // merging 8 bytes into it — 2x the DRAM reads, 60 G stores/s); re-reading the tile from L2 for every sweep instead of
 // keeping it in registers (latency-bound at 25-50 % occupancy: 280-550 us for 33 M items).
+#ifndef BC_PART_HASH32
+#define BC_PART_HASH32 0
+#endif
+// 64 (or 128) key bits -> 32 well-mixed bits in a dozen 32-bit instructions: one multiply per key word, then the two-round
+// xorshift-multiply finaliser.  The partition hash is evaluated four times per record by the flush (histogram and scatter
+// of two levels) and was a third of those kernels' instructions as a full 64-bit mix.
+__device__ __forceinline__ uint32_t part_hash32(Key k) {
+    uint32_t x = (uint32_t)k.lo * 0x85EBCA6Bu ^ (uint32_t)(k.lo >> 32) * 0xC2B2AE35u ^ (uint32_t)k.hi * 0x27D4EB2Fu ^
+                 (uint32_t)(k.hi >> 32) * 0x165667B1u;
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
 __device__ __forceinline__ uint32_t split_digit(unsigned long long lo, unsigned long long hi, const SplitLevel& lv) {
     // drop_bits > 0: partition by the record without its random barcode, so that a partition holds whole keys
     Key k = lv.drop_bits ? key_shr(Key{lo, hi}, lv.drop_bits) : Key{lo, hi};
     k.lo ^= lv.salt;  // the hot partitions set aside by a by-key pass share their hash bits: re-partition them with another hash
+#if BC_PART_HASH32
+    const uint32_t p = __umulhi(part_hash32(k), (uint32_t)lv.P);  // P < 2^32 (partition_items)
+#else
     const uint32_t p = (uint32_t)__umul64hi(hash_key(k), lv.P);
+#endif
     return (p >> lv.shift) & lv.mask;
 }
 
