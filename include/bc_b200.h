@@ -312,9 +312,9 @@ int bc_exchange_count(bc_ctx *ctx, uint64_t *sent);
 int bc_exchange_scatter(bc_ctx *ctx, const uint64_t *first);
 int bc_exchange_finish(bc_ctx *ctx, uint64_t n_received);
 /* The partitioned form of the exchange (schemes with a random barcode): the first radix level of the flush runs on the
- * SENDER over bins that are owner-major, what crosses NVLink is one contiguous range per (sender, owner) moved by the copy
- * engines to the place the gathered histograms assign it, and the owner's flush starts at its second level — for the SMs
- * one pass over the records fewer than scattering by owner first and partitioning what arrived.  Nothing may have been streamed:
+ * SENDER over bins that are owner-major, what crosses NVLink is contiguous pieces moved by a plain copy kernel into the
+ * place the gathered histograms assign them, and the owner's flush starts at its second level — one pass over the records
+ * fewer than scattering by owner first and partitioning what arrived.  Nothing may have been streamed:
  * bc_set_option(ctx, "exchange_mode", 2) before the job's first batch (the exchange is opened and connected as above).
  *    bc_px_local(&valid)        this rank's records that are not holes (synchronises)
  *    caller: all-reduce (sum) of `valid` over the ranks -> total

@@ -102,7 +102,7 @@ struct bc_ctx {
     uint32_t px_l2 = 0, px_F1 = 0;         // second-level bits, first-level bins per owner
     bool px_ready = false;                 // level 1 done for the records of this job
     std::vector<uint32_t> px_hist;         // this rank's level-1 histogram (n_ranks * px_F1)
-    uint32_t* d_px_tab = nullptr;          // an owner's piece tables on the device: begin | end | group, kPxMaxPieces each
+    uint32_t* d_px_tab = nullptr;          // piece table on the device: src_off | cnt | dst_rank | dst_off, kPxMaxPieces each
     uint32_t* h_px_tab = nullptr;          // its pinned host copy
     // options (bc_set_option): measurement / test switches of the flush
     bool opt_flush_global = false, opt_flush_two_stage = false;
@@ -1364,15 +1364,13 @@ int bc_wait_older_copies(bc_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------- deferred counting
 // The whole record buffer -> final rows (ctx row buffers) and the matched / duplicates split.  A pure function of the
 // buffer (plus the imported rows), so it may run any number of times as more batches arrive.
-static const int kPxMaxPieces = 1 << 11;  // pieces of a partitioned exchange: n_ranks * first-level bins per owner
-
 struct FlushSrc {  // what a flush reads: the record buffer, or (multi-GPU) what the exchange delivered
     ItemView v;
     unsigned long long n, n_valid;
     // partitioned exchange: the input already is the output of a first radix level — pre_F1 segments whose starts are in
     // ctx->d_l1 (starts1), no holes; the flush goes straight to the second level (pre_P global partitions, pre_l2 bits)
     unsigned long long pre_P = 0;
-    uint32_t pre_F1 = 0, pre_l2 = 0, pre_senders = 0;  // pre_senders * pre_F1 pieces (tables in ctx->d_px_tab), pre_F1 groups
+    uint32_t pre_F1 = 0, pre_l2 = 0;
 };
 static int flush_global(bc_ctx* ctx, const FlushSrc& in);
 
@@ -1473,7 +1471,7 @@ static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned 
 // already cut into F1 segments [starts1[s], starts1[s + 1]) — starts1 in ctx->d_l1 as partition_items leaves it.  Same
 // verdicts as partition_items.
 static int partition_second_level(bc_ctx* ctx, const ItemView& in, bool wide, unsigned long long n, unsigned long long n_valid,
-                                  const ItemView& out, unsigned long long P_global, uint32_t F1, uint32_t l2, uint32_t senders, uint32_t drop_bits,
+                                  const ItemView& out, unsigned long long P_global, uint32_t F1, uint32_t l2, uint32_t drop_bits,
                                   uint32_t max_part, unsigned long long* n_parts, unsigned long long* big_items) {
     const uint32_t mb = split_max_bits();
     const unsigned long long P = (unsigned long long)F1 << l2;
@@ -1485,10 +1483,7 @@ static int partition_second_level(bc_ctx* ctx, const ItemView& in, bool wide, un
     const SplitLevel lv2{P_global, 0u, (1u << l2) - 1u, 1u << l2, drop_bits, 0ULL};
     int verdict = BC_OK;
     CK(ctx, cudaMemsetAsync(ctx->d_hist, 0, (P + 1) * sizeof(uint32_t), ctx->stream));
-    // input segments: the pieces (sender, first-level bin), each adding to the bins of its group = its first-level bin
-    const uint32_t n_seg = senders * F1;
-    const uint32_t *seg_begin = ctx->d_px_tab, *seg_end = seg_begin + kPxMaxPieces, *seg_group = seg_end + kPxMaxPieces;
-    CK(ctx, launch_split(false, wide, in, out, seg_begin, n_seg, n, lv2, ctx->d_hist, ctx->d_flush, false, ctx->stream, seg_end, seg_group));
+    CK(ctx, launch_split(false, wide, in, out, starts1, F1, n, lv2, ctx->d_hist, ctx->d_flush, false, ctx->stream));
     CK(ctx, launch_seg_scan(ctx->d_hist, F1, 1u << l2, starts1, ctx->d_starts, ctx->d_cursor, max_part ? ctx->d_flush : nullptr, max_part, ctx->stream));
     if (max_part) {
         FlushStats st{};
@@ -1498,7 +1493,7 @@ static int partition_second_level(bc_ctx* ctx, const ItemView& in, bool wide, un
         if (big_items) *big_items = st.big_items;
         if (st.big_items * 5 > n_valid) return 2;
     }
-    CK(ctx, launch_split(true, wide, in, out, seg_begin, n_seg, n, lv2, ctx->d_cursor, ctx->d_flush, false, ctx->stream, seg_end, seg_group));
+    CK(ctx, launch_split(true, wide, in, out, starts1, F1, n, lv2, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
     return verdict;
 }
 
@@ -1547,8 +1542,7 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
         const uint32_t cap = reduce_capacity(wide_in);
         if (in.pre_F1) {  // level 1 ran on the senders; every record is valid
             CK(ctx, cudaMemcpyAsync(&ctx->d_flush->valid, &in.n_valid, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-            rc = partition_second_level(ctx, src, wide_in, n_rec, n_valid, part_v, in.pre_P, in.pre_F1, in.pre_l2, in.pre_senders, ctx->cfg.umi_bits, cap,
-                                        &n_parts, &big);
+            rc = partition_second_level(ctx, src, wide_in, n_rec, n_valid, part_v, in.pre_P, in.pre_F1, in.pre_l2, ctx->cfg.umi_bits, cap, &n_parts, &big);
         } else
         rc = partition_items(ctx, src, wide_in, n_rec, n_valid, false, part_v, true, ctx->cfg.umi_bits, cap, &n_parts, &big);
         if (rc == 1) return go_global(ctx, in, 2, 0);
@@ -2411,10 +2405,10 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
 // ---- partitioned exchange ------------------------------------------------------------------------------------------------
 // The flush's first radix level runs on every rank over ITS records, with bins that are owner-major: global partition
 // p = mulhi(hash(key), N * F1 << l2), owner = p / (F1 << l2), first-level bin = p >> l2.  A rank's records for one owner are
-// then ONE contiguous range of its level-1 output; it is copied by the copy engines (one device-to-device copy per owner, no
-// SM involved) behind the ranges of the ranks before it in the owner's receive buffer, and the owner's flush starts at the
-// second level over N * F1 pieces (piece (sender, bin b) adds to the bins of group b).  Against the streamed / bulk exchange,
-// which scatter by owner with a kernel first and partition what arrived afterwards, the SMs make one pass over the records fewer.
+// then F1 contiguous pieces; they are copied (k_px_copy: no hashing, a few instructions per record) to the place the
+// all-gathered histograms assign them in the owner's receive buffer — bin-major, so that an owner's buffer is exactly what
+// its own first level would have produced — and the owner's flush starts at the second level.  Against the streamed / bulk
+// exchange, which scatter by owner first and partition what arrived afterwards, this saves one whole pass over the records.
 //   bc_px_local      -> this rank's valid records (synchronises)
 //   caller: all-reduce (sum) -> total
 //   bc_px_partition(total) -> level 1 here; hist_out[n_ranks * F1] = this rank's histogram, *n_bins = n_ranks * F1
@@ -2422,6 +2416,7 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
 //   bc_px_send(all)  -> the copies, asynchronous on the ctx stream
 //   caller: a barrier ordered after every rank's copies
 //   bc_px_finish(all)
+static const int kPxMaxPieces = 1 << 11;
 
 int bc_px_local(bc_ctx* ctx, uint64_t* local_valid) {
     if (!ctx || !local_valid) return BC_EINVAL;
@@ -2519,26 +2514,31 @@ int bc_px_send(bc_ctx* ctx, const uint32_t* all) {
         peers.lo[o] = xbuf_lo(ctx, ctx->x_peer[o], parity);
         peers.hi[o] = wide ? peers.lo[o] + ctx->xcap : nullptr;
     }
-    // This rank's records for owner o are ONE contiguous range of its level-1 output (bins o * F1 .. + F1); in o's buffer the
-    // senders' ranges follow one another in rank order.  One device-to-device copy per owner, on the copy engines: no SM
-    // touches a record between the two radix levels.  Owners in rotated order, so that the ranks do not all start on rank 0.
-    std::vector<unsigned long long> src_start(N + 1, 0), before_me(N, 0);
+    // the piece table: owner-major, bin-minor — the order of this rank's level-1 output; per (owner, bin) running offsets
+    uint32_t *src_off = ctx->h_px_tab, *cnt = src_off + kPxMaxPieces, *dst_rank = cnt + kPxMaxPieces, *dst_off = dst_rank + kPxMaxPieces;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned table of the last job has been consumed
+    std::vector<unsigned long long> col(bins, 0);  // records of the ranks before this one per (owner, bin)
+    for (uint32_t q = 0; q < me; q++)
+        for (uint32_t k = 0; k < bins; k++) col[k] += all[(size_t)q * bins + k];
+    unsigned long long at = 0;
     for (uint32_t o = 0; o < N; o++) {
-        unsigned long long mine = 0;
-        for (uint32_t b2 = 0; b2 < F1; b2++) mine += ctx->px_hist[o * F1 + b2];
-        src_start[o + 1] = src_start[o] + mine;
-        for (uint32_t q = 0; q < me; q++)
-            for (uint32_t b2 = 0; b2 < F1; b2++) before_me[o] += all[(size_t)q * bins + (size_t)o * F1 + b2];
+        unsigned long long bin_start = 0;  // start of bin b in owner o's buffer
+        for (uint32_t b = 0; b < F1; b++) {
+            const uint32_t k = o * F1 + b;
+            src_off[k] = (uint32_t)at;
+            cnt[k] = ctx->px_hist[k];
+            dst_rank[k] = o;
+            dst_off[k] = (uint32_t)(bin_start + col[k]);
+            at += ctx->px_hist[k];
+            for (uint32_t q = 0; q < N; q++) bin_start += all[(size_t)q * bins + k];
+        }
     }
+    CK(ctx, cudaMemcpyAsync(ctx->d_px_tab, ctx->h_px_tab, 4 * kPxMaxPieces * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     {
         ProfScope p(ctx, BC_K_EXCHANGE);
-        for (uint32_t step = 1; step <= N; step++) {
-            const uint32_t o = (me + step) % N;
-            const unsigned long long cnt = src_start[o + 1] - src_start[o];
-            if (cnt == 0) continue;
-            CK(ctx, cudaMemcpyAsync(peers.lo[o] + before_me[o], ctx->tmp.lo + src_start[o], cnt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            if (wide) CK(ctx, cudaMemcpyAsync(peers.hi[o] + before_me[o], ctx->tmp.hi + src_start[o], cnt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        }
+        const uint32_t* d = ctx->d_px_tab;
+        CK(ctx, launch_px_copy(wide, ItemView{ctx->tmp.lo, wide ? ctx->tmp.hi : nullptr, nullptr}, peers, d, d + kPxMaxPieces, d + 2 * kPxMaxPieces,
+                               d + 3 * kPxMaxPieces, bins, ctx->stream));
     }
     ctx->x_state = 2;
     return BC_OK;
@@ -2550,32 +2550,22 @@ int bc_px_finish(bc_ctx* ctx, const uint32_t* all) {
     CK(ctx, cudaSetDevice(ctx->device));
     const bool wide = ctx->cfg.wide != 0;
     const uint32_t N = ctx->x_ranks, F1 = ctx->px_F1, bins = N * F1, me = ctx->x_rank, parity = ctx->x_epoch & 1u, mb = split_max_bits();
-    // this owner's buffer: the senders' ranges in rank order, each cut into its F1 first-level bins -> N * F1 segments; segment
-    // (q, b) belongs to group b, and the second level's output puts group after group (group_starts in starts1)
-    uint32_t *seg_begin = ctx->h_px_tab, *seg_end = seg_begin + kPxMaxPieces, *seg_group = seg_end + kPxMaxPieces;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned table of the last job has been consumed
+    // this owner's buffer: F1 segments, segment b = the ranks' pieces of bin b one after the other
     std::vector<uint32_t> starts(F1 + 1, 0);
     unsigned long long n_received = 0;
-    for (uint32_t q = 0; q < N; q++)
-        for (uint32_t b2 = 0; b2 < F1; b2++) {
-            const uint32_t c = all[(size_t)q * bins + (size_t)me * F1 + b2];
-            seg_begin[q * F1 + b2] = (uint32_t)n_received;
-            seg_end[q * F1 + b2] = (uint32_t)(n_received + c);
-            seg_group[q * F1 + b2] = b2;
-            starts[b2 + 1] += c;
-            n_received += c;
-        }
-    for (uint32_t b2 = 0; b2 < F1; b2++) starts[b2 + 1] += starts[b2];
+    for (uint32_t b = 0; b < F1; b++) {
+        starts[b] = (uint32_t)n_received;
+        for (uint32_t q = 0; q < N; q++) n_received += all[(size_t)q * bins + (size_t)me * F1 + b];
+    }
+    starts[F1] = (uint32_t)n_received;
     if (n_received > ctx->xcap) return fail(ctx, BC_EINVAL, "bc_px_finish: %llu records exceed the receive capacity", n_received);
     uint32_t* starts1 = ctx->d_l1 + (1u << mb) + 1;
-    CK(ctx, cudaMemcpyAsync(ctx->d_px_tab, ctx->h_px_tab, 3 * kPxMaxPieces * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpy(starts1, starts.data(), (F1 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
     unsigned long long* recv = xbuf_lo(ctx, ctx->d_xrecv, parity);
     FlushSrc in{ItemView{recv, wide ? recv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
     in.pre_P = ctx->px_P;
     in.pre_F1 = F1;
     in.pre_l2 = ctx->px_l2;
-    in.pre_senders = N;
     ctx->x_epoch++;
     ctx->px_ready = false;
     int rc = flush_core(ctx, in);

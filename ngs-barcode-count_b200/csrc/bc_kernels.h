@@ -132,12 +132,9 @@ struct SplitLevel {
     uint32_t drop_bits;  // hash the key shifted right by this many bits (the random barcode) instead of the whole item
     unsigned long long salt;  // xor-ed into the key before hashing: an independent partitioning of the same keys
 };
-// seg_end / seg_group (device arrays of n_seg entries, both or neither): segment s is [seg_starts[s], seg_end[s]) and adds to
-// the bins of group seg_group[s] (bins + seg_group[s] * F) — the pieces an owner received from every sender of a partitioned
-// exchange, piece (sender, first-level bin b) belonging to group b.
 cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t n_seg,
                          unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, FlushStats* stats, bool count_valid,
-                         cudaStream_t stream, const uint32_t* seg_end = nullptr, const uint32_t* seg_group = nullptr);
+                         cudaStream_t stream);
 uint32_t split_max_bits();
 // One CTA per partition [starts[p], starts[p+1]) — or, with starts == nullptr, per fixed chunk of `chunk` items.
 //   RED_DEDUPE: distinct records of the partition, then their keys (record >> umi_bits) combined: out = (key, pairs)
@@ -156,6 +153,9 @@ cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_
 // multi-GPU exchange: valid items of `in` -> peers.lo/hi[owner] at cursors[owner]++ (see bc_partition.cu)
 cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& peers, unsigned long long n_total, const SplitLevel& lv,
                                  uint32_t* cursors, cudaStream_t stream);
+// partitioned exchange: contiguous pieces of `in` -> peers.lo/hi[dst_rank[k]] + dst_off[k] (device arrays of n_pieces entries)
+cudaError_t launch_px_copy(bool wide, const ItemView& in, const PeerOut& peers, const uint32_t* src_off, const uint32_t* cnt,
+                           const uint32_t* dst_rank, const uint32_t* dst_off, uint32_t n_pieces, cudaStream_t stream);
 // global-table path over the record buffer (oversized partitions, forced by BC_FLUSH_GLOBAL): counts like k_insert
 cudaError_t launch_insert_items(const Tables& tables, const ItemView& in, bool wide, unsigned long long n, FlushStats* stats,
                                 cudaStream_t stream);

@@ -146,17 +146,14 @@ template <bool WIDE>
 __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const ItemView in, const uint32_t* __restrict__ seg_starts,
                                                               const uint32_t workers, const unsigned long long n_total,
                                                               const SplitLevel lv, uint32_t* __restrict__ bins, FlushStats* stats,
-                                                              const bool count_valid, const uint32_t* __restrict__ seg_end,
-                                                              const uint32_t* __restrict__ seg_group) {
+                                                              const bool count_valid) {
     __shared__ uint32_t s_hist[1u << kSplitMaxBits];
     __shared__ unsigned long long s_valid;
     constexpr int U = 4;
     const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
-    // segments: [seg_starts[s], seg_starts[s + 1]) with their own bins each — or, with seg_end / seg_group (the pieces an owner
-    // received from every sender in a partitioned exchange), [seg_starts[s], seg_end[s]) adding to the bins of group seg_group[s]
     const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
-    const unsigned long long e = seg_end ? (unsigned long long)seg_end[seg] : seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
-    uint32_t* my_bins = bins + (unsigned long long)(seg_group ? seg_group[seg] : seg) * lv.F;
+    const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
+    uint32_t* my_bins = bins + (unsigned long long)seg * lv.F;
     const uint32_t tid = threadIdx.x;
     unsigned long long valid = 0;
     if (tid == 0) s_valid = 0;
@@ -198,8 +195,7 @@ template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
 __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const ItemView in, const ItemView out, const PeerOut peers,
                                                                     const uint32_t* __restrict__ seg_starts, const uint32_t workers,
                                                                     const unsigned long long n_total, const SplitLevel lv,
-                                                                    uint32_t* __restrict__ bins, const uint32_t* __restrict__ seg_end,
-                                                                    const uint32_t* __restrict__ seg_group) {
+                                                                    uint32_t* __restrict__ bins) {
     constexpr uint32_t T = kScatterThreads * IPT;
     extern __shared__ __align__(16) unsigned long long split_stage[];  // [lo | hi | w] x T u64, then T u32 positions
     __shared__ uint32_t s_hist[1u << kSplitMaxBits], s_delta[1u << kSplitMaxBits];
@@ -207,9 +203,9 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
     __shared__ uint32_t s_fits;  // PEER, streamed: bit b = this tile's run fits owner b's buffer
     const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
     const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
-    const unsigned long long e = seg_end ? (unsigned long long)seg_end[seg] : seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
+    const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
     const uint32_t F = lv.F;
-    uint32_t* my_bins = bins + (unsigned long long)(seg_group ? seg_group[seg] : seg) * F;
+    uint32_t* my_bins = bins + (unsigned long long)seg * F;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned long long* st_lo = split_stage;
     unsigned long long* st_hi = st_lo + (WIDE ? T : 0);
@@ -926,8 +922,7 @@ cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_
 
 template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
 static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const PeerOut& peers, const uint32_t* seg_starts,
-                                    uint32_t workers, unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream,
-                                    const uint32_t* seg_end = nullptr, const uint32_t* seg_group = nullptr) {
+                                    uint32_t workers, unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream) {
     constexpr size_t T = (size_t)kScatterThreads * IPT;
     const size_t smem = T * 8 * (1 + (WIDE ? 1 : 0) + (WEIGHTED ? 1 : 0)) + T * 4;
     cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -935,14 +930,13 @@ static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const Ite
         e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    k_split_scatter<WIDE, WEIGHTED, IPT, PEER><<<grid, kScatterThreads, smem, stream>>>(in, out, peers, seg_starts, workers, n_total, lv, bins,
-                                                                                        seg_end, seg_group);
+    k_split_scatter<WIDE, WEIGHTED, IPT, PEER><<<grid, kScatterThreads, smem, stream>>>(in, out, peers, seg_starts, workers, n_total, lv, bins);
     return cudaGetLastError();
 }
 
 cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const ItemView& out, const uint32_t* seg_starts, uint32_t n_seg,
                          unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, FlushStats* stats, bool count_valid,
-                         cudaStream_t stream, const uint32_t* seg_end, const uint32_t* seg_group) {
+                         cudaStream_t stream) {
     if (n_total == 0) return cudaSuccess;
     if (lv.F > (1u << kSplitMaxBits) || lv.F == 0) return cudaErrorInvalidValue;
     const bool weighted = in.w != nullptr;
@@ -962,15 +956,15 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
     const unsigned grid = (unsigned)(workers * n_seg);
     const uint32_t w = (uint32_t)workers;
     if (!scatter) {
-        if (wide) k_split_hist<true><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid, seg_end, seg_group);
-        else k_split_hist<false><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid, seg_end, seg_group);
+        if (wide) k_split_hist<true><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
+        else k_split_hist<false><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
         return cudaGetLastError();
     }
     const PeerOut none{};
-    if (wide) return weighted ? launch_scatter_t<true, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream, seg_end, seg_group)
-                              : launch_scatter_t<true, false, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream, seg_end, seg_group);
-    return weighted ? launch_scatter_t<false, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream, seg_end, seg_group)
-                    : launch_scatter_t<false, false, BC_SCATTER_IPT, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream, seg_end, seg_group);
+    if (wide) return weighted ? launch_scatter_t<true, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
+                              : launch_scatter_t<true, false, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
+    return weighted ? launch_scatter_t<false, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
+                    : launch_scatter_t<false, false, BC_SCATTER_IPT, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
 }
 
 // Exchange step of a multi-GPU job: this rank's records -> their owners' receive buffers.  owner = digit of `lv`
@@ -996,6 +990,37 @@ cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& p
         if (e != cudaSuccess) return e;
         k_owner_scatter<false, 16><<<(unsigned)workers, kScatterThreads, smem, stream>>>(in, peers, (uint32_t)workers, n_total, lv, cursors);
     }
+    return cudaGetLastError();
+}
+
+// Partitioned exchange: piece k of this rank's level-1 output (records src_off[k] .. + cnt[k]) -> rank dst_rank[k]'s receive
+// buffer at dst_off[k].  Pieces are hundreds of kilobytes, contiguous on both sides: a plain streaming copy over NVLink with a
+// handful of instructions per record (no hashing, no shared memory).  One CTA walks a piece; grid = pieces x workers.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_px_copy(const ItemView in, const PeerOut peers, const uint32_t* __restrict__ src_off,
+                                                 const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ dst_rank,
+                                                 const uint32_t* __restrict__ dst_off, const uint32_t workers) {
+    const uint32_t k = blockIdx.x / workers, w = blockIdx.x % workers;
+    const uint32_t n = cnt[k];
+    if (n == 0) return;
+    const unsigned long long* s_lo = in.lo + src_off[k];
+    unsigned long long* d_lo = peers.lo[dst_rank[k]] + dst_off[k];
+    for (uint32_t i = w * 256 + threadIdx.x; i < n; i += workers * 256) d_lo[i] = s_lo[i];
+    if (WIDE) {
+        const unsigned long long* s_hi = in.hi + src_off[k];
+        unsigned long long* d_hi = peers.hi[dst_rank[k]] + dst_off[k];
+        for (uint32_t i = w * 256 + threadIdx.x; i < n; i += workers * 256) d_hi[i] = s_hi[i];
+    }
+}
+
+cudaError_t launch_px_copy(bool wide, const ItemView& in, const PeerOut& peers, const uint32_t* src_off, const uint32_t* cnt,
+                           const uint32_t* dst_rank, const uint32_t* dst_off, uint32_t n_pieces, cudaStream_t stream) {
+    if (n_pieces == 0) return cudaSuccess;
+    uint32_t workers = (148u * 8u + n_pieces - 1) / n_pieces;
+    if (workers < 1) workers = 1;
+    if (workers > 64) workers = 64;
+    if (wide) k_px_copy<true><<<n_pieces * workers, 256, 0, stream>>>(in, peers, src_off, cnt, dst_rank, dst_off, workers);
+    else k_px_copy<false><<<n_pieces * workers, 256, 0, stream>>>(in, peers, src_off, cnt, dst_rank, dst_off, workers);
     return cudaGetLastError();
 }
 
