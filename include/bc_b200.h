@@ -296,8 +296,7 @@ int bc_key_decode(const bc_ctx *ctx, uint64_t key_lo, uint64_t key_hi, uint32_t 
  *             bc_exchange_finish(received)
  *    Until bc_exchange_finish, bc_get_counters / bc_finish on a rank of a multi-GPU job fail with BC_ESTATE.  A rank holds
  *    two receive buffers that alternate job by job, so a fast rank may start streaming the next job while a slow one still
- *    counts this one; the ranks must run the same sequence of jobs.  bc_set_option("exchange_mode", 1) forbids streaming
- *    (2: as 1, for the partitioned form below). */
+ *    counts this one; the ranks must run the same sequence of jobs.  bc_set_option("exchange_bulk", 1) forbids streaming. */
 #define BC_IPC_HANDLE_BYTES 64
 int bc_exchange_open(bc_ctx *ctx, uint32_t n_ranks, uint32_t rank, uint64_t capacity);
 int bc_exchange_handle(bc_ctx *ctx, void *ipc_handle_out);
@@ -311,25 +310,6 @@ int bc_exchange_connect_local(bc_ctx *ctx, bc_ctx *const *ranks);
 int bc_exchange_count(bc_ctx *ctx, uint64_t *sent);
 int bc_exchange_scatter(bc_ctx *ctx, const uint64_t *first);
 int bc_exchange_finish(bc_ctx *ctx, uint64_t n_received);
-/* The partitioned form of the exchange (schemes with a random barcode): the first radix level of the flush runs on the
- * SENDER over bins that are owner-major, what crosses NVLink is contiguous pieces moved by a plain copy kernel into the
- * place the gathered histograms assign them, and the owner's flush starts at its second level — one pass over the records
- * fewer than scattering by owner first and partitioning what arrived.  Nothing may have been streamed:
- * bc_set_option(ctx, "exchange_mode", 2) before the job's first batch (the exchange is opened and connected as above).
- *    bc_px_local(&valid)        this rank's records that are not holes (synchronises)
- *    caller: all-reduce (sum) of `valid` over the ranks -> total
- *    bc_px_partition(total, hist, &n_bins)   level 1 on this rank; hist[n_bins] (n_bins <= 2048) = its histogram.
- *                               BC_EUNSUPPORTED: the job needs more than two levels, or the scheme has no random
- *                               barcode — use bc_exchange_count / _scatter / _finish (the bulk exchange)
- *    caller: all-gather the histograms in rank order -> all[n_ranks][n_bins]; owner o receives the sum over ranks q and
- *            bins b of all[q][o * n_bins / n_ranks + b]; above the capacity: disconnect, re-open larger, reconnect
- *    bc_px_send(all)            the copies, asynchronous on the ctx stream
- *    caller: a barrier ordered after every rank's copies
- *    bc_px_finish(all)          counts; afterwards the context is as after bc_exchange_finish */
-int bc_px_local(bc_ctx *ctx, uint64_t *local_valid);
-int bc_px_partition(bc_ctx *ctx, uint64_t total_valid, uint32_t *hist_out, uint32_t *n_bins);
-int bc_px_send(bc_ctx *ctx, const uint32_t *all_hists);
-int bc_px_finish(bc_ctx *ctx, const uint32_t *all_hists);
 /* One process, several contexts: dst += src for the dense count table (BC_ADD_DENSE_COUNTS) or the dense marginals
  * (BC_ADD_MARGINALS); src may be on another GPU.  Both contexts must be idle.  Synchronises dst. */
 enum { BC_ADD_DENSE_COUNTS = 0, BC_ADD_MARGINALS = 1 };

@@ -181,10 +181,6 @@ _PROTOS = {
     "bc_exchange_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bc_exchange_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bc_exchange_finish": (C.c_int, [C.c_void_p, C.c_uint64]),
-    "bc_px_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
-    "bc_px_partition": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]),
-    "bc_px_send": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "bc_px_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_peer_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "bc_export_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_uint64)]),
@@ -555,29 +551,6 @@ class Counter:
 
     def exchange_finish(self, n_received):
         self._ck(lib().bc_exchange_finish(self.h, int(n_received)), "bc_exchange_finish")
-
-    def px_local(self):
-        v = C.c_uint64()
-        self._ck(lib().bc_px_local(self.h, C.byref(v)), "bc_px_local")
-        return int(v.value)
-
-    def px_partition(self, total_valid):
-        """-> this rank's level-1 histogram (uint32 array), or None when the job / scheme needs the bulk exchange"""
-        hist = np.zeros(2048, np.uint32)
-        n = C.c_uint32()
-        rc = lib().bc_px_partition(self.h, int(total_valid), _ptr(hist), C.byref(n))
-        if rc == -4:  # BC_EUNSUPPORTED
-            return None
-        self._ck(rc, "bc_px_partition")
-        return hist[:n.value].copy()
-
-    def px_send(self, all_hists):
-        a = np.ascontiguousarray(all_hists, dtype=np.uint32)
-        self._ck(lib().bc_px_send(self.h, _ptr(a)), "bc_px_send")
-
-    def px_finish(self, all_hists):
-        a = np.ascontiguousarray(all_hists, dtype=np.uint32)
-        self._ck(lib().bc_px_finish(self.h, _ptr(a)), "bc_px_finish")
 
     def peer_add(self, src, what):
         self._ck(lib().bc_peer_add(self.h, src.h, int(what)), "bc_peer_add")

@@ -95,15 +95,6 @@ struct bc_ctx {
     bool x_overflowed = false, x_dirty = false, opt_exchange_bulk = false;
     unsigned long long* d_xsent = nullptr; // kMaxRanks counters: records sent to each owner by the streamed scatters
     unsigned int* d_xoverflow = nullptr;
-    // partitioned exchange (bc_px_*): the first radix level of the flush runs on the SENDER, over bins that are owner-major
-    // (owner = top part of the global partition number), so what crosses NVLink is contiguous pieces moved by a plain copy
-    // kernel and the owner starts its flush at the second level
-    unsigned long long px_P = 0;           // global partitions = n_ranks * px_F1 << px_l2
-    uint32_t px_l2 = 0, px_F1 = 0;         // second-level bits, first-level bins per owner
-    bool px_ready = false;                 // level 1 done for the records of this job
-    std::vector<uint32_t> px_hist;         // this rank's level-1 histogram (n_ranks * px_F1)
-    uint32_t* d_px_tab = nullptr;          // piece table on the device: src_off | cnt | dst_rank | dst_off, kPxMaxPieces each
-    uint32_t* h_px_tab = nullptr;          // its pinned host copy
     // options (bc_set_option): measurement / test switches of the flush
     bool opt_flush_global = false, opt_flush_two_stage = false;
     uint32_t cfg_flags = 0;
@@ -561,8 +552,6 @@ void bc_destroy(bc_ctx* ctx) {
         if (ctx->x_peer_ipc[r] && ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
     if (ctx->d_xrecv) cudaFree(ctx->d_xrecv);
     if (ctx->d_xcursor) cudaFree(ctx->d_xcursor);
-    if (ctx->d_px_tab) cudaFree(ctx->d_px_tab);
-    if (ctx->h_px_tab) cudaFreeHost(ctx->h_px_tab);
     if (ctx->d_xsent) cudaFree(ctx->d_xsent);
     if (ctx->d_xoverflow) cudaFree(ctx->d_xoverflow);
     if (ctx->x_stream) {
@@ -1326,7 +1315,6 @@ int bc_set_option(bc_ctx* ctx, const char* name, int value) {
     if (!strcmp(name, "flush_global")) ctx->opt_flush_global = value != 0;
     else if (!strcmp(name, "flush_two_stage")) ctx->opt_flush_two_stage = value != 0;
     else if (!strcmp(name, "exchange_bulk")) ctx->opt_exchange_bulk = value != 0;
-    else if (!strcmp(name, "exchange_mode")) ctx->opt_exchange_bulk = value != 0;  // 0 streamed; 1 bulk; 2 partitioned (bc_px_*): nothing leaves before the last batch either
     else return fail(ctx, BC_EINVAL, "bc_set_option: unknown option '%s'", name);
     ctx->rows_valid = false;
     return BC_OK;
@@ -1367,10 +1355,6 @@ int bc_wait_older_copies(bc_ctx* ctx) {
 struct FlushSrc {  // what a flush reads: the record buffer, or (multi-GPU) what the exchange delivered
     ItemView v;
     unsigned long long n, n_valid;
-    // partitioned exchange: the input already is the output of a first radix level — pre_F1 segments whose starts are in
-    // ctx->d_l1 (starts1), no holes; the flush goes straight to the second level (pre_P global partitions, pre_l2 bits)
-    unsigned long long pre_P = 0;
-    uint32_t pre_F1 = 0, pre_l2 = 0;
 };
 static int flush_global(bc_ctx* ctx, const FlushSrc& in);
 
@@ -1467,36 +1451,6 @@ static int partition_items(bc_ctx* ctx, const ItemView& in, bool wide, unsigned 
     return verdict;
 }
 
-// The second radix level alone, over an input that a first level (run elsewhere: the senders of a partitioned exchange) has
-// already cut into F1 segments [starts1[s], starts1[s + 1]) — starts1 in ctx->d_l1 as partition_items leaves it.  Same
-// verdicts as partition_items.
-static int partition_second_level(bc_ctx* ctx, const ItemView& in, bool wide, unsigned long long n, unsigned long long n_valid,
-                                  const ItemView& out, unsigned long long P_global, uint32_t F1, uint32_t l2, uint32_t drop_bits,
-                                  uint32_t max_part, unsigned long long* n_parts, unsigned long long* big_items) {
-    const uint32_t mb = split_max_bits();
-    const unsigned long long P = (unsigned long long)F1 << l2;
-    *n_parts = P;
-    int rc = reserve_parts(ctx, P);
-    if (rc != BC_OK) return rc;
-    ProfScope p(ctx, BC_K_FINISH);
-    uint32_t* starts1 = ctx->d_l1 + (1u << mb) + 1;
-    const SplitLevel lv2{P_global, 0u, (1u << l2) - 1u, 1u << l2, drop_bits, 0ULL};
-    int verdict = BC_OK;
-    CK(ctx, cudaMemsetAsync(ctx->d_hist, 0, (P + 1) * sizeof(uint32_t), ctx->stream));
-    CK(ctx, launch_split(false, wide, in, out, starts1, F1, n, lv2, ctx->d_hist, ctx->d_flush, false, ctx->stream));
-    CK(ctx, launch_seg_scan(ctx->d_hist, F1, 1u << l2, starts1, ctx->d_starts, ctx->d_cursor, max_part ? ctx->d_flush : nullptr, max_part, ctx->stream));
-    if (max_part) {
-        FlushStats st{};
-        CK(ctx, cudaMemcpyAsync(&st, ctx->d_flush, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (st.max_bin > max_part) verdict = 3;
-        if (big_items) *big_items = st.big_items;
-        if (st.big_items * 5 > n_valid) return 2;
-    }
-    CK(ctx, launch_split(true, wide, in, out, starts1, F1, n, lv2, ctx->d_cursor, ctx->d_flush, false, ctx->stream));
-    return verdict;
-}
-
 static int go_global(bc_ctx* ctx, const FlushSrc& in, int where, unsigned long long code) {
     (void)where;
     (void)code;
@@ -1540,10 +1494,6 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
         if (rc != BC_OK) return rc;
         const ItemView part_v{ctx->part.lo, wide_in ? ctx->part.hi : nullptr, nullptr};
         const uint32_t cap = reduce_capacity(wide_in);
-        if (in.pre_F1) {  // level 1 ran on the senders; every record is valid
-            CK(ctx, cudaMemcpyAsync(&ctx->d_flush->valid, &in.n_valid, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-            rc = partition_second_level(ctx, src, wide_in, n_rec, n_valid, part_v, in.pre_P, in.pre_F1, in.pre_l2, ctx->cfg.umi_bits, cap, &n_parts, &big);
-        } else
         rc = partition_items(ctx, src, wide_in, n_rec, n_valid, false, part_v, true, ctx->cfg.umi_bits, cap, &n_parts, &big);
         if (rc == 1) return go_global(ctx, in, 2, 0);
         if (rc == BC_OK || rc == 3) {
@@ -2388,188 +2338,6 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
     int rc = flush_core(ctx, in);
     if (rc != BC_OK) return rc;
     // this rank's share of the job's outcome: the records it owns (matched = distinct pairs, duplicates = their repeats)
-    rc = fold_counters(ctx);
-    if (rc == BC_OK) rc = bc_sync(ctx);
-    if (rc != BC_OK) return rc;
-    unsigned long long h[BC_N_COUNTERS];
-    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    h[BC_CNT_MATCHED] = ctx->last_unique;
-    h[BC_CNT_DUPLICATES] = ctx->last_valid - ctx->last_unique;
-    CK(ctx, cudaMemcpy(ctx->d_counters, h, sizeof h, cudaMemcpyHostToDevice));
-    ctx->dup_applied = 0;
-    ctx->x_received = n_received;
-    ctx->x_state = 3;
-    return BC_OK;
-}
-
-// ---- partitioned exchange ------------------------------------------------------------------------------------------------
-// The flush's first radix level runs on every rank over ITS records, with bins that are owner-major: global partition
-// p = mulhi(hash(key), N * F1 << l2), owner = p / (F1 << l2), first-level bin = p >> l2.  A rank's records for one owner are
-// then F1 contiguous pieces; they are copied (k_px_copy: no hashing, a few instructions per record) to the place the
-// all-gathered histograms assign them in the owner's receive buffer — bin-major, so that an owner's buffer is exactly what
-// its own first level would have produced — and the owner's flush starts at the second level.  Against the streamed / bulk
-// exchange, which scatter by owner first and partition what arrived afterwards, this saves one whole pass over the records.
-//   bc_px_local      -> this rank's valid records (synchronises)
-//   caller: all-reduce (sum) -> total
-//   bc_px_partition(total) -> level 1 here; hist_out[n_ranks * F1] = this rank's histogram, *n_bins = n_ranks * F1
-//   caller: all-gather the histograms (rank order); if an owner's total exceeds the capacity: re-open larger, reconnect
-//   bc_px_send(all)  -> the copies, asynchronous on the ctx stream
-//   caller: a barrier ordered after every rank's copies
-//   bc_px_finish(all)
-static const int kPxMaxPieces = 1 << 11;
-
-int bc_px_local(bc_ctx* ctx, uint64_t* local_valid) {
-    if (!ctx || !local_valid) return BC_EINVAL;
-    if (ctx->x_ranks < 2) return fail(ctx, BC_ESTATE, "bc_px_local: the exchange is not open");
-    if (ctx->x_mode == 1) return fail(ctx, BC_ESTATE, "bc_px_local: this job's records were streamed to their owners (set the option "
-                                                      "\"exchange_mode\" to 2 before the job's first batch)");
-    CK(ctx, cudaSetDevice(ctx->device));
-    int rc = fold_counters(ctx);
-    if (rc == BC_OK) rc = bc_sync(ctx);
-    if (rc != BC_OK) return rc;
-    unsigned long long h[BC_N_COUNTERS];
-    CK(ctx, cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    *local_valid = std::min<unsigned long long>(ctx->rec_n, h[BC_CNT_MATCHED] + h[BC_CNT_DUPLICATES]);
-    ctx->px_ready = false;
-    return BC_OK;
-}
-
-int bc_px_partition(bc_ctx* ctx, uint64_t total_valid, uint32_t* hist_out, uint32_t* n_bins) {
-    if (!ctx || !hist_out || !n_bins) return BC_EINVAL;
-    if (ctx->x_ranks < 2) return fail(ctx, BC_ESTATE, "bc_px_partition: the exchange is not open");
-    if (ctx->x_mode == 1) return fail(ctx, BC_ESTATE, "bc_px_partition: this job's records were streamed already");
-    if (!ctx->cfg.has_umi) return fail(ctx, BC_EUNSUPPORTED, "bc_px_partition: schemes without a random barcode pre-aggregate before they partition; use the bulk exchange");
-    CK(ctx, cudaSetDevice(ctx->device));
-    const bool wide = ctx->cfg.wide != 0;
-    const uint32_t N = ctx->x_ranks, mb = split_max_bits();
-    const unsigned long long n_rec = ctx->rec_n;
-    if (n_rec >= 0xFFFFFFF0ULL) return fail(ctx, BC_EUNSUPPORTED, "bc_px_partition: more than 2^32 records on one rank");
-    // geometry, a pure function of (total, N): every rank computes the same
-    const unsigned long long per_owner = (total_valid + N - 1) / N;
-    unsigned long long need = (per_owner + reduce_fill(wide) - 1) / reduce_fill(wide);
-    if (need < 2) need = 2;
-    // as partition_items balances its two levels — about the same number of bins at either, since a scatter's runs shrink
-    // with its bin count — but the first level is shared by N owners: at most 2^mb / N bins each
-    const unsigned long long f1_max = (1ull << mb) / N;
-    uint32_t lg = 1;
-    while ((1ull << lg) < need) lg++;
-    uint32_t l2 = std::max(1u, (lg + 1) / 2);
-    while (l2 < mb && ((need + (1ull << l2) - 1) >> l2) > f1_max) l2++;
-    unsigned long long F1 = (need + (1ull << l2) - 1) >> l2;
-    if (F1 < 1) F1 = 1;
-    if (F1 > f1_max) return fail(ctx, BC_EUNSUPPORTED, "bc_px_partition: %llu records per owner need more than two radix levels; use the bulk exchange",
-                                 per_owner);
-    ctx->px_l2 = l2;
-    ctx->px_F1 = (uint32_t)F1;
-    ctx->px_P = ((unsigned long long)N * F1) << l2;
-    const uint32_t bins = N * (uint32_t)F1;
-    *n_bins = bins;
-    ctx->px_hist.assign(bins, 0u);
-    if (!ctx->d_px_tab) {
-        CK(ctx, cudaMalloc(&ctx->d_px_tab, 4 * kPxMaxPieces * sizeof(uint32_t)));
-        CK(ctx, cudaHostAlloc((void**)&ctx->h_px_tab, 4 * kPxMaxPieces * sizeof(uint32_t), cudaHostAllocDefault));
-    }
-    if (!ctx->d_l1) CK(ctx, cudaMalloc(&ctx->d_l1, 3 * ((1u << mb) + 1) * sizeof(uint32_t)));
-    if (n_rec) {
-        int rc = reserve_items(ctx, ctx->tmp, n_rec, wide, false);
-        if (rc != BC_OK) return rc;
-        uint32_t *hist1 = ctx->d_l1, *starts1 = hist1 + (1u << mb) + 1, *cursor1 = starts1 + (1u << mb) + 1;
-        const ItemView rec{ctx->rec.lo, wide ? ctx->rec.hi : nullptr, nullptr}, tmp{ctx->tmp.lo, wide ? ctx->tmp.hi : nullptr, nullptr};
-        const SplitLevel lv1{ctx->px_P, l2, 0xFFFFFFFFu, bins, ctx->cfg.umi_bits, 0ULL};
-        ProfScope p(ctx, BC_K_EXCHANGE);
-        CK(ctx, cudaMemsetAsync(hist1, 0, (bins + 1) * sizeof(uint32_t), ctx->stream));
-        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-        CK(ctx, launch_split(false, wide, rec, tmp, nullptr, 1, n_rec, lv1, hist1, ctx->d_flush, true, ctx->stream));
-        CK(ctx, launch_seg_scan(hist1, 1, bins, nullptr, starts1, cursor1, nullptr, 0xFFFFFFFFu, ctx->stream));
-        CK(ctx, launch_split(true, wide, rec, tmp, nullptr, 1, n_rec, lv1, cursor1, ctx->d_flush, false, ctx->stream));
-        CK(ctx, cudaMemcpyAsync(ctx->px_hist.data(), hist1, bins * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
-    }
-    memcpy(hist_out, ctx->px_hist.data(), bins * sizeof(uint32_t));
-    unsigned long long sum = 0;
-    for (uint32_t b = 0; b < bins; b++) sum += ctx->px_hist[b];
-    ctx->x_local_valid = sum;
-    ctx->px_ready = true;
-    ctx->x_state = 1;
-    return BC_OK;
-}
-
-int bc_px_send(bc_ctx* ctx, const uint32_t* all) {
-    if (!ctx || !all) return BC_EINVAL;
-    if (!ctx->px_ready) return fail(ctx, BC_ESTATE, "bc_px_send: call bc_px_partition first");
-    CK(ctx, cudaSetDevice(ctx->device));
-    const bool wide = ctx->cfg.wide != 0;
-    const uint32_t N = ctx->x_ranks, F1 = ctx->px_F1, bins = N * F1, me = ctx->x_rank, parity = ctx->x_epoch & 1u;
-    if (memcmp(all + (size_t)me * bins, ctx->px_hist.data(), bins * sizeof(uint32_t)) != 0)
-        return fail(ctx, BC_EINVAL, "bc_px_send: row %u of the gathered histograms is not this rank's histogram", me);
-    PeerOut peers{};
-    for (uint32_t o = 0; o < N; o++) {
-        if (!ctx->x_peer[o]) return fail(ctx, BC_ESTATE, "bc_px_send: rank %u is not connected", o);
-        unsigned long long total = 0;
-        for (uint32_t q = 0; q < N; q++)
-            for (uint32_t b = 0; b < F1; b++) total += all[(size_t)q * bins + (size_t)o * F1 + b];
-        if (total > ctx->xcap)
-            return fail(ctx, BC_EINVAL, "bc_px_send: rank %u would receive %llu records, its capacity is %llu: reopen larger", o, total, ctx->xcap);
-        peers.lo[o] = xbuf_lo(ctx, ctx->x_peer[o], parity);
-        peers.hi[o] = wide ? peers.lo[o] + ctx->xcap : nullptr;
-    }
-    // the piece table: owner-major, bin-minor — the order of this rank's level-1 output; per (owner, bin) running offsets
-    uint32_t *src_off = ctx->h_px_tab, *cnt = src_off + kPxMaxPieces, *dst_rank = cnt + kPxMaxPieces, *dst_off = dst_rank + kPxMaxPieces;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned table of the last job has been consumed
-    std::vector<unsigned long long> col(bins, 0);  // records of the ranks before this one per (owner, bin)
-    for (uint32_t q = 0; q < me; q++)
-        for (uint32_t k = 0; k < bins; k++) col[k] += all[(size_t)q * bins + k];
-    unsigned long long at = 0;
-    for (uint32_t o = 0; o < N; o++) {
-        unsigned long long bin_start = 0;  // start of bin b in owner o's buffer
-        for (uint32_t b = 0; b < F1; b++) {
-            const uint32_t k = o * F1 + b;
-            src_off[k] = (uint32_t)at;
-            cnt[k] = ctx->px_hist[k];
-            dst_rank[k] = o;
-            dst_off[k] = (uint32_t)(bin_start + col[k]);
-            at += ctx->px_hist[k];
-            for (uint32_t q = 0; q < N; q++) bin_start += all[(size_t)q * bins + k];
-        }
-    }
-    CK(ctx, cudaMemcpyAsync(ctx->d_px_tab, ctx->h_px_tab, 4 * kPxMaxPieces * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    {
-        ProfScope p(ctx, BC_K_EXCHANGE);
-        const uint32_t* d = ctx->d_px_tab;
-        CK(ctx, launch_px_copy(wide, ItemView{ctx->tmp.lo, wide ? ctx->tmp.hi : nullptr, nullptr}, peers, d, d + kPxMaxPieces, d + 2 * kPxMaxPieces,
-                               d + 3 * kPxMaxPieces, bins, ctx->stream));
-    }
-    ctx->x_state = 2;
-    return BC_OK;
-}
-
-int bc_px_finish(bc_ctx* ctx, const uint32_t* all) {
-    if (!ctx || !all) return BC_EINVAL;
-    if (!ctx->px_ready || ctx->x_state != 2) return fail(ctx, BC_ESTATE, "bc_px_finish: call bc_px_send first");
-    CK(ctx, cudaSetDevice(ctx->device));
-    const bool wide = ctx->cfg.wide != 0;
-    const uint32_t N = ctx->x_ranks, F1 = ctx->px_F1, bins = N * F1, me = ctx->x_rank, parity = ctx->x_epoch & 1u, mb = split_max_bits();
-    // this owner's buffer: F1 segments, segment b = the ranks' pieces of bin b one after the other
-    std::vector<uint32_t> starts(F1 + 1, 0);
-    unsigned long long n_received = 0;
-    for (uint32_t b = 0; b < F1; b++) {
-        starts[b] = (uint32_t)n_received;
-        for (uint32_t q = 0; q < N; q++) n_received += all[(size_t)q * bins + (size_t)me * F1 + b];
-    }
-    starts[F1] = (uint32_t)n_received;
-    if (n_received > ctx->xcap) return fail(ctx, BC_EINVAL, "bc_px_finish: %llu records exceed the receive capacity", n_received);
-    uint32_t* starts1 = ctx->d_l1 + (1u << mb) + 1;
-    CK(ctx, cudaMemcpy(starts1, starts.data(), (F1 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    unsigned long long* recv = xbuf_lo(ctx, ctx->d_xrecv, parity);
-    FlushSrc in{ItemView{recv, wide ? recv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
-    in.pre_P = ctx->px_P;
-    in.pre_F1 = F1;
-    in.pre_l2 = ctx->px_l2;
-    ctx->x_epoch++;
-    ctx->px_ready = false;
-    int rc = flush_core(ctx, in);
-    if (rc != BC_OK) return rc;
     rc = fold_counters(ctx);
     if (rc == BC_OK) rc = bc_sync(ctx);
     if (rc != BC_OK) return rc;

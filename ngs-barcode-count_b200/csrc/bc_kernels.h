@@ -153,9 +153,6 @@ cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_
 // multi-GPU exchange: valid items of `in` -> peers.lo/hi[owner] at cursors[owner]++ (see bc_partition.cu)
 cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& peers, unsigned long long n_total, const SplitLevel& lv,
                                  uint32_t* cursors, cudaStream_t stream);
-// partitioned exchange: contiguous pieces of `in` -> peers.lo/hi[dst_rank[k]] + dst_off[k] (device arrays of n_pieces entries)
-cudaError_t launch_px_copy(bool wide, const ItemView& in, const PeerOut& peers, const uint32_t* src_off, const uint32_t* cnt,
-                           const uint32_t* dst_rank, const uint32_t* dst_off, uint32_t n_pieces, cudaStream_t stream);
 // global-table path over the record buffer (oversized partitions, forced by BC_FLUSH_GLOBAL): counts like k_insert
 cudaError_t launch_insert_items(const Tables& tables, const ItemView& in, bool wide, unsigned long long n, FlushStats* stats,
                                 cudaStream_t stream);

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
 // 64 (or 128) key bits -> 32 well-mixed bits in a dozen 32-bit instructions: one multiply per key word, then the two-round
 // xorshift-multiply finaliser.  The partition hash is evaluated four times per record by the flush (histogram and scatter
 // of two levels) and was a third of those kernels' instructions as a full 64-bit mix.
-[[maybe_unused]] __device__ __forceinline__ uint32_t part_hash32(Key k) {
+__device__ __forceinline__ uint32_t part_hash32(Key k) {
     uint32_t x = (uint32_t)k.lo * 0x85EBCA6Bu ^ (uint32_t)(k.lo >> 32) * 0xC2B2AE35u ^ (uint32_t)k.hi * 0x27D4EB2Fu ^
                  (uint32_t)(k.hi >> 32) * 0x165667B1u;
     x ^= x >> 16;
@@ -990,37 +990,6 @@ cudaError_t launch_owner_scatter(bool wide, const ItemView& in, const PeerOut& p
         if (e != cudaSuccess) return e;
         k_owner_scatter<false, 16><<<(unsigned)workers, kScatterThreads, smem, stream>>>(in, peers, (uint32_t)workers, n_total, lv, cursors);
     }
-    return cudaGetLastError();
-}
-
-// Partitioned exchange: piece k of this rank's level-1 output (records src_off[k] .. + cnt[k]) -> rank dst_rank[k]'s receive
-// buffer at dst_off[k].  Pieces are hundreds of kilobytes, contiguous on both sides: a plain streaming copy over NVLink with a
-// handful of instructions per record (no hashing, no shared memory).  One CTA walks a piece; grid = pieces x workers.
-template <bool WIDE>
-__global__ void __launch_bounds__(256) k_px_copy(const ItemView in, const PeerOut peers, const uint32_t* __restrict__ src_off,
-                                                 const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ dst_rank,
-                                                 const uint32_t* __restrict__ dst_off, const uint32_t workers) {
-    const uint32_t k = blockIdx.x / workers, w = blockIdx.x % workers;
-    const uint32_t n = cnt[k];
-    if (n == 0) return;
-    const unsigned long long* s_lo = in.lo + src_off[k];
-    unsigned long long* d_lo = peers.lo[dst_rank[k]] + dst_off[k];
-    for (uint32_t i = w * 256 + threadIdx.x; i < n; i += workers * 256) d_lo[i] = s_lo[i];
-    if (WIDE) {
-        const unsigned long long* s_hi = in.hi + src_off[k];
-        unsigned long long* d_hi = peers.hi[dst_rank[k]] + dst_off[k];
-        for (uint32_t i = w * 256 + threadIdx.x; i < n; i += workers * 256) d_hi[i] = s_hi[i];
-    }
-}
-
-cudaError_t launch_px_copy(bool wide, const ItemView& in, const PeerOut& peers, const uint32_t* src_off, const uint32_t* cnt,
-                           const uint32_t* dst_rank, const uint32_t* dst_off, uint32_t n_pieces, cudaStream_t stream) {
-    if (n_pieces == 0) return cudaSuccess;
-    uint32_t workers = (148u * 8u + n_pieces - 1) / n_pieces;
-    if (workers < 1) workers = 1;
-    if (workers > 64) workers = 64;
-    if (wide) k_px_copy<true><<<n_pieces * workers, 256, 0, stream>>>(in, peers, src_off, cnt, dst_rank, dst_off, workers);
-    else k_px_copy<false><<<n_pieces * workers, 256, 0, stream>>>(in, peers, src_off, cnt, dst_rank, dst_off, workers);
     return cudaGetLastError();
 }
 

@@ -99,31 +99,22 @@ class Job:
     """ctr: this rank's Counter (or any object with the same methods: the CPU test drives the host logic with a fake).
     expected_reads: reads per rank, sizes the exchange's receive buffer (it grows when a job needs more)."""
 
-    EXCHANGE_MODES = {"streamed": 0, "bulk": 1, "partitioned": 2}
-
-    def __init__(self, bc, ctr, run, world, rank, device, stream, has_umi, expected_reads, deferred=None, exchange_mode="partitioned"):
+    def __init__(self, bc, ctr, run, world, rank, device, stream, has_umi, expected_reads, deferred=None):
         self.bc, self.ctr, self.run = bc, ctr, run
         self.world, self.rank, self.device, self.stream, self.has_umi = world, rank, device, stream, has_umi
         self.deferred = bool(ctr.profile()["deferred_count"]) if deferred is None else deferred
         self.exchange = world > 1 and self.deferred
-        self.exchange_mode = exchange_mode if self.exchange else None
         if world == 1:
             self.parallelism = "1 GPU"
         elif self.exchange:
-            how = {"partitioned": "every rank runs the flush's first radix level over its own records with owner-major bins, the pieces "
-                                  "are copied into the owner GPUs' memory over NVLink, each owner continues at the second level",
-                   "streamed": "every batch's records leave for their owners right after its decode (scatter kernel on a side stream, runs "
-                               "reserved on the owner's receive cursor over NVLink)",
-                   "bulk": "after the last batch the records are scattered by owner into the owner GPUs' memory over NVLink"}[exchange_mode]
-            self.parallelism = (f"reads sharded over {world} GPUs; (key,UMI) records go to owner = f(hash(key)) of {world}: {how}; each owner "
-                                f"de-duplicates and counts its keys")
+            self.parallelism = (f"reads sharded over {world} GPUs; after the last batch the (key,UMI) records are exchanged once: "
+                                f"owner = hash(key) % {world}, written by the partitioning kernel into the owner GPU's memory over "
+                                f"NVLink; each owner de-duplicates and counts its keys")
         else:
             self.parallelism = (f"reads sharded over {world} GPUs; one in-place all-reduce of the dense count table at the end")
         if self.exchange:
             self.cap = 0
             self._open(int(expected_reads * 1.25) + 4096)
-            if hasattr(ctr, "set_option"):
-                ctr.set_option("exchange_mode", self.EXCHANGE_MODES[exchange_mode])
 
     def _open(self, capacity):
         """(re)allocate the receive buffers and connect every rank to every other (collective)."""
@@ -162,35 +153,8 @@ class Job:
                 n = int(t.item())
             return n
 
-    def _exchange_partitioned(self):
-        """The partitioned exchange (bc_px_*): level 1 of the flush on the sender, pieces copied, level 2 on the owner.
-        False when the library asks for the bulk exchange instead (every rank gets the same answer: it only depends on
-        the total and on the scheme)."""
-        t = torch.tensor([self.ctr.px_local()], dtype=torch.int64, device=self.device)
-        dist.all_reduce(t)
-        hist = self.ctr.px_partition(int(t.item()))
-        if hist is None:
-            return False
-        bins = len(hist)
-        mine = torch.from_numpy(hist.astype(np.int64)).to(self.device)
-        gathered = torch.empty(self.world * bins, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(gathered, mine)
-        all_hists = gathered.view(self.world, bins).cpu().numpy().astype(np.uint32)
-        f1 = bins // self.world
-        totals = [int(all_hists[:, o * f1:(o + 1) * f1].sum()) for o in range(self.world)]
-        if max(totals) > self.cap:  # every rank sees the same histograms and grows together; level 1 is not redone
-            self._open(int(max(totals) * 1.1) + 4096)
-        self.ctr.px_send(all_hists)
-        # orders the owners' flush after every rank's copies (each enters the all-reduce on the stream its copy kernel runs on)
-        dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=self.device))
-        self.ctr.px_finish(all_hists)
-        self.last_matrix = [[int(all_hists[s, o * f1:(o + 1) * f1].sum()) for o in range(self.world)] for s in range(self.world)]
-        return True
-
     def _exchange(self):
-        """The exchange step of a job with hashed keys.  Every rank computes the same plan from the same matrix."""
-        if self.exchange_mode == "partitioned" and self.has_umi and self._exchange_partitioned():
-            return
+        """The one exchange step of a job with hashed keys.  Every rank computes the same plan from the same matrix."""
         sent = self.ctr.exchange_count(self.world)
         mine = torch.tensor(sent, dtype=torch.int64, device=self.device)
         matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=self.device)

@@ -914,87 +914,3 @@ def test_exchange_between_contexts_on_one_gpu(case, n_ranks, bulk):
         assert sorted(got_rows) == want_rows
         keys = [(h, l) for h, l, _ in got_rows]
         assert len(set(keys)) == len(keys)  # owners hold disjoint key sets
-
-
-@pytest.mark.parametrize("n_ranks", [2, 3, 4])
-@pytest.mark.parametrize("case", ["del3_umi", "lineage_raw", "example", "sample_raw_two"])
-def test_partitioned_exchange_between_contexts_on_one_gpu(case, n_ranks):
-    """The partitioned exchange (bc_px_*: the flush's first radix level on the sender with owner-major bins, pieces copied
-    into the owners' buffers, second level on the owner), ranks = contexts on one GPU: union of the owners' rows and sum of
-    their counters equal a single context's.  Three jobs in a row; the last one with receive buffers that are too small."""
-    exp, paths = load_golden(case)
-    run = make_run(paths, exp["flags"])
-    reads = read_fastq(paths["fastq"])
-    batch = run.pack([r[0] for r in reads], [r[1] for r in reads])
-
-    def rows_of(ctr):
-        rows = ctr.finish()
-        return sorted(zip([int(x) for x in rows["key_hi"]], [int(x) for x in rows["key_lo"]], [int(x) for x in rows["count"]]))
-
-    direct = bc.Counter(run)
-    direct.submit(batch)
-    want_rows, want_c = rows_of(direct), direct.counters()
-    if not direct.profile()["deferred_count"]:
-        pytest.skip("dense count table: ranks merge with an all-reduce, not an exchange")
-    ranks = [bc.Counter(run) for _ in range(n_ranks)]
-
-    def open_all(cap):
-        for c in ranks:
-            c.exchange_disconnect()
-        for r, c in enumerate(ranks):
-            c.exchange_open(n_ranks, r, cap)
-        for c in ranks:
-            c.exchange_connect_local(ranks)
-            c.set_option("exchange_mode", 2)
-
-    open_all(batch.n + 16)
-    cuts = [batch.n * r // n_ranks for r in range(n_ranks + 1)]
-    for rep in range(3):
-        if rep == 2:
-            open_all(max(1, batch.n // (4 * n_ranks)))
-        for r, c in enumerate(ranks):
-            c.reset()
-            mid = (cuts[r] + cuts[r + 1]) // 2
-            c.submit(batch.slice(cuts[r], mid))
-            c.submit(batch.slice(mid, cuts[r + 1]))
-        total = sum(c.px_local() for c in ranks)
-        assert total == want_c["matched"] + want_c["duplicates"]
-        hists = [c.px_partition(total) for c in ranks]
-        if hists[0] is None:  # no random barcode: the library asks for the bulk exchange
-            assert all(h is None for h in hists) and not any(chr(run.slot(i).kind) == "R" for i in range(run.n_slots))
-            from ngs_barcode_count_b200.multi import exchange_plan
-            matrix = [c.exchange_count(n_ranks) for c in ranks]
-            if rep == 2:
-                open_all(exchange_plan(matrix, 0)[2])
-                assert [c.exchange_count(n_ranks) for c in ranks] == matrix
-            for r, c in enumerate(ranks):
-                c.exchange_scatter(exchange_plan(matrix, r)[0])
-            for c in ranks:
-                c.sync()
-            for r, c in enumerate(ranks):
-                c.exchange_finish(exchange_plan(matrix, r)[1])
-        else:
-            all_h = np.stack(hists)
-            f1 = all_h.shape[1] // n_ranks
-            assert int(all_h.sum()) == total
-            need = max(int(all_h[:, o * f1:(o + 1) * f1].sum()) for o in range(n_ranks))
-            if rep == 2:
-                assert need > batch.n // (4 * n_ranks)
-                with pytest.raises(bc.BcError):
-                    ranks[0].px_send(all_h)
-                open_all(need)  # level 1 is not redone
-            for c in ranks:
-                c.px_send(all_h)
-            for c in ranks:
-                c.sync()
-            for c in ranks:
-                c.px_finish(all_h)
-        got_rows, got_c = [], {k: 0 for k in want_c}
-        for c in ranks:
-            got_rows += rows_of(c)
-            for k, v in c.counters().items():
-                got_c[k] += v
-        assert got_c == want_c
-        assert sorted(got_rows) == want_rows
-        keys = [(h, l) for h, l, _ in got_rows]
-        assert len(set(keys)) == len(keys)

@@ -53,34 +53,6 @@ class FakeCounter:
         self.calls.append("finish")
         self.received = received
 
-    def set_option(self, name, value):
-        self.calls.append(("option", name, value))
-
-    # partitioned exchange: `sent` per owner is spread over two first-level bins per owner
-    def px_local(self):
-        self.calls.append("px_local")
-        return sum(self.sent)
-
-    def px_partition(self, total):
-        self.calls.append(("px_partition", total))
-        import numpy as np
-        if self.no_px:
-            return None
-        return np.array([x for s in self.sent for x in (s - s // 3, s // 3)], dtype=np.uint32)
-
-    def px_send(self, all_hists):
-        f1 = all_hists.shape[1] // all_hists.shape[0]
-        for o in range(all_hists.shape[0]):
-            assert int(all_hists[:, o * f1:(o + 1) * f1].sum()) <= self.cap, "pieces past the receive capacity"
-        self.calls.append("px_send")
-        self.px_all = all_hists.copy()
-
-    def px_finish(self, all_hists):
-        assert (all_hists == self.px_all).all()
-        self.calls.append("px_finish")
-
-    no_px = False
-
     def finish_view(self):
         return (3, None, None, None)
 
@@ -101,16 +73,15 @@ def _worker(rank, world, port, q):
         assert multi.exchange_plan([[5, 7], [11, 13]], 0) == ([0, 0], 16, 20)
         for sent_by_rank, expected in (([[100, 40], [60, 300]], 1000), ([[5000, 10], [7000, 20]], 1000)):
             ctr = FakeCounter(sent_by_rank[rank])
-            job = multi.Job(None, ctr, None, world, rank, "cpu", None, True, expected, deferred=True, exchange_mode="streamed")
+            job = multi.Job(None, ctr, None, world, rank, "cpu", None, True, expected, deferred=True)
             assert job.exchange and ctr.calls[0] == ("open", int(expected * 1.25) + 4096) and ctr.calls[1] == "connect"
-            assert ctr.calls[2] == ("option", "exchange_mode", 0)
             n_rows = job.step(["b0", "b1", "b2"])
             assert n_rows == 3 * world  # the all-reduced row count
             totals = [sum(sent_by_rank[s][o] for s in range(world)) for o in range(world)]
             grew = max(totals) > int(expected * 1.25) + 4096
             want = ["reset", "submit", "submit", "submit", "count"] + \
                 (["disconnect", ("open", int(max(totals) * 1.1) + 4096), "connect", "count"] if grew else []) + ["scatter", "finish"]
-            assert ctr.calls[3:] == want, ctr.calls
+            assert ctr.calls[2:] == want, ctr.calls
             assert ctr.received == totals[rank]
             # every owner's buffer is tiled by the ranks' runs, in rank order
             plans = [None] * world
@@ -121,26 +92,6 @@ def _worker(rank, world, port, q):
                     assert plans[s][o] == at, (plans, o, s)
                     at += sent_by_rank[s][o]
                 assert at == totals[o]
-        # the partitioned exchange (the default): one all-reduce of the valid counts, one all-gather of the histograms, the
-        # same growth rule; and the bulk calls when the library declines (no random barcode / too many levels)
-        for sent_by_rank, expected, declined in (([[100, 40], [60, 300]], 1000, False), ([[5000, 10], [7000, 20]], 1000, False),
-                                                 ([[100, 40], [60, 300]], 1000, True)):
-            ctr = FakeCounter(sent_by_rank[rank])
-            ctr.no_px = declined
-            job = multi.Job(None, ctr, None, world, rank, "cpu", None, True, expected, deferred=True)
-            assert ctr.calls[2] == ("option", "exchange_mode", 2)
-            assert job.step(["b0"]) == 3 * world
-            totals = [sum(sent_by_rank[s][o] for s in range(world)) for o in range(world)]
-            total = sum(totals)
-            grew = max(totals) > int(expected * 1.25) + 4096
-            if declined:
-                want = ["reset", "submit", "px_local", ("px_partition", total), "count", "scatter", "finish"]
-            else:
-                want = ["reset", "submit", "px_local", ("px_partition", total)] + \
-                    (["disconnect", ("open", int(max(totals) * 1.1) + 4096), "connect"] if grew else []) + ["px_send", "px_finish"]
-                assert ctr.px_all.shape == (world, 2 * world) and [int(x) for x in ctr.px_all[rank]] == [x for s in sent_by_rank[rank] for x in (s - s // 3, s // 3)]
-                assert job.last_matrix == sent_by_rank
-            assert ctr.calls[3:] == want, ctr.calls
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

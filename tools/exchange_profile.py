@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Development aid: the owner scatter of the multi-GPU exchange with the ranks as contexts on ONE GPU (peer stores land in
-local HBM, so what is measured is the SM-side cost of the kernel).  python tools/exchange_profile.py [ranks] [reads per rank] [streamed|bulk|px]"""
+local HBM, so what is measured is the SM-side cost of the kernel).  python tools/exchange_profile.py [ranks] [reads per rank] [bulk]"""
 import json
 import os
 import sys
@@ -16,8 +16,7 @@ from ngs_barcode_count_b200.multi import exchange_plan  # noqa: E402
 def main():
     n_ranks = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     per = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 24
-    mode = sys.argv[3] if len(sys.argv) > 3 else "streamed"
-    bulk = mode == "bulk"
+    bulk = len(sys.argv) > 3 and sys.argv[3] == "bulk"
     wl = synth.Workload("del3", "/tmp/xprof", reads=per * n_ranks)
     run = wl.run(bc)
     ranks = [bc.Counter(run, expected_reads=per) for _ in range(n_ranks)]
@@ -25,7 +24,7 @@ def main():
         c.exchange_open(n_ranks, r, int(per * 1.3))
     for c in ranks:
         c.exchange_connect_local(ranks)
-        c.set_option("exchange_mode", {"streamed": 0, "bulk": 1, "px": 2}[mode])
+        c.set_option("exchange_bulk", int(bulk))
         c.set_profiling(True)
     step = 1 << 23
     batches = [[wl.generate_device(run, r * per + a, min(step, per - a)) for a in range(0, per, step)] for r in range(n_ranks)]
@@ -37,26 +36,15 @@ def main():
         for r, c in enumerate(ranks):
             for b in batches[r]:
                 c.submit(b)
-        if mode == "px":
-            import numpy as np
-            total = sum(c.px_local() for c in ranks)
-            all_h = np.stack([c.px_partition(total) for c in ranks])
-            for c in ranks:
-                c.px_send(all_h)
-            for c in ranks:
-                c.sync()
-            for c in ranks:
-                c.px_finish(all_h)
-        else:
-            matrix = [c.exchange_count(n_ranks) for c in ranks]
-            for r, c in enumerate(ranks):
-                c.exchange_scatter(exchange_plan(matrix, r)[0])
-            for c in ranks:
-                c.sync()
-            for r, c in enumerate(ranks):
-                c.exchange_finish(exchange_plan(matrix, r)[1])
+        matrix = [c.exchange_count(n_ranks) for c in ranks]
+        for r, c in enumerate(ranks):
+            c.exchange_scatter(exchange_plan(matrix, r)[0])
+        for c in ranks:
+            c.sync()
+        for r, c in enumerate(ranks):
+            c.exchange_finish(exchange_plan(matrix, r)[1])
         p = ranks[0].profile()
-        print(json.dumps({"ranks": n_ranks, "per_rank": per, "mode": mode, "ms": p["ms"], "launches": p["launches"]}), flush=True)
+        print(json.dumps({"ranks": n_ranks, "per_rank": per, "bulk": bulk, "ms": p["ms"], "launches": p["launches"]}), flush=True)
 
 
 if __name__ == "__main__":
