@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(512) k_seg_scan(const uint32_t* __restrict__ h
 // 64 (or 128) key bits -> 32 well-mixed bits in a dozen 32-bit instructions: one multiply per key word, then the two-round
 // xorshift-multiply finaliser.  The partition hash is evaluated four times per record by the flush (histogram and scatter
 // of two levels) and was a third of those kernels' instructions as a full 64-bit mix.
-__device__ __forceinline__ uint32_t part_hash32(Key k) {
+[[maybe_unused]] __device__ __forceinline__ uint32_t part_hash32(Key k) {
     uint32_t x = (uint32_t)k.lo * 0x85EBCA6Bu ^ (uint32_t)(k.lo >> 32) * 0xC2B2AE35u ^ (uint32_t)k.hi * 0x27D4EB2Fu ^
                  (uint32_t)(k.hi >> 32) * 0x165667B1u;
     x ^= x >> 16;
