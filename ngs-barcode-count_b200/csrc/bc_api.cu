@@ -120,6 +120,7 @@ struct bc_ctx {
     unsigned long long imp_n = 0;
     uint32_t *d_hist = nullptr, *d_starts = nullptr, *d_cursor = nullptr;
     uint32_t *d_hot = nullptr, *d_hot_n = nullptr;  // partitions the keyed reduce handed to the two-pass kernel
+    uint32_t* d_big = nullptr;            // k_gather_big's list of oversized partitions: {start, size, place} x part_cap
     unsigned long long part_cap = 0;
     FlushStats* d_flush = nullptr;
     unsigned long long last_valid = 0, last_unique = 0;  // of the last flush
@@ -317,10 +318,12 @@ int reserve_parts(bc_ctx* ctx, unsigned long long n_parts) {
     if (ctx->d_starts) cudaFree(ctx->d_starts);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->d_hot) cudaFree(ctx->d_hot);
-    ctx->d_hist = ctx->d_starts = ctx->d_cursor = ctx->d_hot = nullptr;
+    if (ctx->d_big) cudaFree(ctx->d_big);
+    ctx->d_hist = ctx->d_starts = ctx->d_cursor = ctx->d_hot = ctx->d_big = nullptr;
     ctx->part_cap = 0;
     const unsigned long long cap = n_parts + n_parts / 8 + 1024;
     CK(ctx, cudaMalloc(&ctx->d_hot, cap * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&ctx->d_big, cap * 4 * sizeof(uint32_t)));
     if (!ctx->d_hot_n) CK(ctx, cudaMalloc(&ctx->d_hot_n, sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&ctx->d_hist, cap * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&ctx->d_starts, cap * sizeof(uint32_t)));
@@ -522,6 +525,7 @@ void bc_destroy(bc_ctx* ctx) {
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->d_hot) cudaFree(ctx->d_hot);
     if (ctx->d_hot_n) cudaFree(ctx->d_hot_n);
+    if (ctx->d_big) cudaFree(ctx->d_big);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     for (Staging& s : ctx->staging) {
         if (s.planes) cudaFree(s.planes);
@@ -1530,7 +1534,7 @@ static int flush_core(bc_ctx* ctx, const FlushSrc& in) {
             const ItemView left_v{ctx->left.lo, wide_in ? ctx->left.hi : nullptr, nullptr};
             {
                 ProfScope p(ctx, BC_K_FINISH);
-                CK(ctx, launch_gather_big(part_v, ctx->d_starts, n_parts, cap, left_v, ctx->d_flush, ctx->stream));
+                CK(ctx, launch_gather_big(part_v, ctx->d_starts, n_parts, cap, left_v, ctx->d_flush, ctx->d_big, ctx->d_hot_n, ctx->stream));
             }
             CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, sizeof(FlushStats), ctx->stream));
             src = left_v;

@@ -120,7 +120,7 @@ cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_
                             uint32_t limit, cudaStream_t stream);
 // partitions larger than `limit` copied to `out` (stats->n_out counts the items moved)
 cudaError_t launch_gather_big(const ItemView& in, const uint32_t* starts, unsigned long long n_parts, uint32_t limit, const ItemView& out,
-                              FlushStats* stats, cudaStream_t stream);
+                              FlushStats* stats, uint32_t* scratch /* 4 x n_parts u32, 16-byte aligned */, uint32_t* scratch_n, cudaStream_t stream);
 uint32_t reduce_capacity(bool wide);  // items a partition may hold for the staged (single pass) reduce
 // One radix level of the hash partitioning: partition p of an item = mulhi(hash(key), P); the level's bin is
 // (p >> shift) & mask, F bins.  seg_starts == nullptr: one segment [0, n_total); else n_seg segments, each split on its

@@ -1008,27 +1008,44 @@ cudaError_t launch_reduce(int mode, bool wide, const ItemView& in, const uint32_
                 : launch_reduce_t<false, RED_COUNT>(in, starts, n_items, n_ranges, chunk, umi_bits, out, out_cap, stats, skip_over, hot, stream);
 }
 
-// partitions larger than `limit` copied, one warp each, to a contiguous buffer (their total is known from the scan)
-__global__ void k_gather_big(const ItemView in, const uint32_t* __restrict__ starts, const unsigned long long n_parts, const uint32_t limit,
-                             const ItemView out, FlushStats* stats) {
-    const int lane = threadIdx.x & 31;
-    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long p = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5; p < n_parts; p += n_warps) {
+// partitions larger than `limit` copied to a contiguous buffer (their total is known from the scan).  Two steps, because a
+// hot key's partition can hold millions of records: first every big partition reserves its place (one thread per
+// partition, list[i] = {partition, place}), then all CTAs copy the listed partitions chunk by chunk — a single warp per
+// partition took 2.5 ms for 21 MB of Zipf-distributed lineage barcodes.
+__global__ void k_list_big(const uint32_t* __restrict__ starts, const unsigned long long n_parts, const uint32_t limit, uint4* __restrict__ list,
+                           uint32_t* __restrict__ list_n, FlushStats* stats) {
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n_parts; p += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t a = starts[p], e = starts[p + 1];
         if (e - a <= limit) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&stats->n_out, (unsigned long long)(e - a));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        for (uint32_t i = a + lane; i < e; i += 32) {
-            out.lo[base + (i - a)] = in.lo[i];
-            if (in.hi) out.hi[base + (i - a)] = in.hi[i];
+        const unsigned long long base = atomicAdd(&stats->n_out, (unsigned long long)(e - a));
+        list[atomicAdd(list_n, 1u)] = make_uint4(a, e - a, (uint32_t)base, (uint32_t)(base >> 32));
+    }
+}
+__global__ void __launch_bounds__(256) k_copy_big(const ItemView in, const uint4* __restrict__ list, const uint32_t* __restrict__ list_n, const ItemView out) {
+    constexpr uint32_t kChunk = 4096;
+    const uint32_t n = *list_n;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint4 ent = list[i];
+        const unsigned long long base = ((unsigned long long)ent.w << 32) | ent.z;
+        // chunk c of entry i belongs to CTA (i + c) mod grid: thousands of partitions a little over the limit spread over all
+        // CTAs just like the chunks of one huge partition
+        const uint32_t first = (blockIdx.x + gridDim.x - i % gridDim.x) % gridDim.x;
+        for (unsigned long long c0 = (unsigned long long)first * kChunk; c0 < ent.y; c0 += (unsigned long long)gridDim.x * kChunk) {
+            const uint32_t c1 = (uint32_t)min((unsigned long long)ent.y, c0 + kChunk);
+            for (uint32_t j = (uint32_t)c0 + threadIdx.x; j < c1; j += 256) {
+                out.lo[base + j] = in.lo[ent.x + j];
+                if (in.hi) out.hi[base + j] = in.hi[ent.x + j];
+            }
         }
     }
 }
 
 cudaError_t launch_gather_big(const ItemView& in, const uint32_t* starts, unsigned long long n_parts, uint32_t limit, const ItemView& out,
-                              FlushStats* stats, cudaStream_t stream) {
-    k_gather_big<<<148 * 8, 256, 0, stream>>>(in, starts, n_parts, limit, out, stats);
+                              FlushStats* stats, uint32_t* scratch /* 4 x n_parts u32, 16-byte aligned */, uint32_t* scratch_n, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(scratch_n, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    k_list_big<<<stream_grid(n_parts, 256), 256, 0, stream>>>(starts, n_parts, limit, reinterpret_cast<uint4*>(scratch), scratch_n, stats);
+    k_copy_big<<<148 * 8, 256, 0, stream>>>(in, reinterpret_cast<const uint4*>(scratch), scratch_n, out);
     return cudaGetLastError();
 }
 
