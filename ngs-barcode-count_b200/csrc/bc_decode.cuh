@@ -18,6 +18,12 @@ namespace bc {
 
 __device__ __forceinline__ uint32_t lenmask(uint32_t len) { return len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u); }
 
+// BC_DECODE_CHECKED = true builds k_decode with the bounds-checked plane reads (a verification build: tools/check_plane_reads.py
+// runs it against the shipped one; compute-sanitizer is closed on the pool this was developed on)
+#ifndef BC_DECODE_CHECKED
+#define BC_DECODE_CHECKED false
+#endif
+
 // bits [pos, pos+32) of a W-word bit plane.  CHECK = false (k_decode, planes staged in shared memory): every caller
 // has pos < 32 W, so word j exists, and word j + 1 is at worst the first word of the next plane / record / array of
 // the tile — readable, and its bits land beyond the read's last base, where every consumer masks (template constant
@@ -306,9 +312,9 @@ __device__ __forceinline__ int locate_exact(const DevCfg& cfg, const uint32_t* l
             uint32_t e = 0;
 #pragma unroll
             for (int k = 0; k < TW; k++) {
-                const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
-                const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
-                const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
+                const uint32_t wl = plane_bits<BC_DECODE_CHECKED>(lo, W, o + (k << 5));
+                const uint32_t wh = plane_bits<BC_DECODE_CHECKED>(hi, W, o + (k << 5));
+                const uint32_t wn = plane_bits<BC_DECODE_CHECKED>(nm, W, o + (k << 5));
                 e |= (((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k]) | (wn & (cfg.t_cm[k] | cfg.t_fn[k]));
             }
             if (e == 0) return o;  // offsets are visited in increasing order: the leftmost exact window
@@ -400,9 +406,9 @@ __device__ __forceinline__ uint32_t repair_chunk(const DevCfg& cfg, const uint32
         uint32_t d = 0;
 #pragma unroll
         for (int k = 0; k < TW; k++) {
-            const uint32_t wl = plane_bits<false>(lo, W, o + (k << 5));
-            const uint32_t wh = plane_bits<false>(hi, W, o + (k << 5));
-            const uint32_t wn = plane_bits<false>(nm, W, o + (k << 5));
+            const uint32_t wl = plane_bits<BC_DECODE_CHECKED>(lo, W, o + (k << 5));
+            const uint32_t wh = plane_bits<BC_DECODE_CHECKED>(hi, W, o + (k << 5));
+            const uint32_t wn = plane_bits<BC_DECODE_CHECKED>(nm, W, o + (k << 5));
             d += __popc(((wl ^ cfg.t_lo[k]) | (wh ^ cfg.t_hi[k])) & cfg.t_cm[k] & ~wn);
         }
         if (d < best) {
@@ -588,7 +594,7 @@ __device__ __forceinline__ void decode_body(const DevCfg& cfg, const BatchView& 
                 if (cfg.has_fn) {  // the regex is re-run on the repaired window: format-N still needs ACGT
                     uint32_t bad = 0;
 #pragma unroll
-                    for (int k = 0; k < TW; k++) bad |= plane_bits<false>(nm, W, off + (k << 5)) & cfg.t_fn[k];
+                    for (int k = 0; k < TW; k++) bad |= plane_bits<BC_DECODE_CHECKED>(nm, W, off + (k << 5)) & cfg.t_fn[k];
                     if (bad) {
                         off = -1;
                         repaired = false;
@@ -635,7 +641,7 @@ __device__ __forceinline__ void decode_body(const DevCfg& cfg, const BatchView& 
             for (uint32_t oi = 0; oi < cfg.n_slots; oi++) {
                 const uint32_t si = cfg.order[oi];
                 const DevSlot& S = cfg.slots[si];
-                const SlotBits b = slot_bits<false>(lo, hi, nm, W, off + S.offset, S.len);
+                const SlotBits b = slot_bits<BC_DECODE_CHECKED>(lo, hi, nm, W, off + S.offset, S.len);
                 if (S.mode == MODE_RAW) {
                     key_raw(key, S, b, cfg.wide);
                     continue;

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "ngs-barcode-count_b200"))
 import build as b  # noqa: E402
 
 VARIANTS = {
+    "checked": ["-DBC_DECODE_CHECKED=true"],
     "hash32": ["-DBC_PART_HASH32=1"],
     "nobail": ["-DBC_CHAIN_LIMIT=100000000"],
     "slots8k": ["-DBC_TABLE_SLOTS=8192"],
