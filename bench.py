@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--fastq-reads", type=int, default=8_000_000, help="reads of the FASTQ-file leg (e2e_fastq)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-binned", action="store_true", help="skip the binned-quality variant of the e2e leg")
     ap.add_argument("--e2e-form", choices=["wire", "plain"], default="wire",
                     help="host batches of the e2e leg: the transfer form (bc_submit_wire: 6-bit quality codes, N calls as a list) or plain "
                          "bc_batch arrays (bc_submit)")
@@ -525,6 +526,44 @@ def main():
                         "pinned host bc_batch buffers -> bc_submit (H2D inside)") +
                        " [-> one record exchange over NVLink] -> bc_finish rows on the host"}
         del host_batches
+        # ---- the same leg on reads whose qualities are binned the way current Illumina instruments emit them (RTA3: Q2 / Q12 /
+        # Q23 / Q37): four distinct characters travel as 2-bit codes.  Another input (the quality filter sees other scores), so
+        # it is reported beside `e2e`, not as it; N = 1 only.
+        if world == 1 and wl.min_quality > 0 and args.e2e_form == "wire" and not args.no_binned:
+            bn = min(e2e_n, 1 << 26)
+            u8 = lambda v: torch.tensor(v, dtype=torch.uint8, device=dev)
+
+            def bin4(qual):  # Phred+33 characters -> '#' (Q2), '-' (Q12), '8' (Q23), 'F' (Q37)
+                return torch.where(qual < 40, u8(35), torch.where(qual < 51, u8(45), torch.where(qual < 63, u8(56), u8(70))))
+            binned, done = [], 0
+            for b in leg.batches:
+                if done >= bn:
+                    break
+                n = min(b.n, bn - done)
+                sl = b.slice(0, n)
+                qb = bin4(sl.qual)
+                binned.append(job.to_pinned(bc.Batch(n, sl.plane_stride, sl.qual_stride, sl.planes, sl.read_len, qb, device=True), wire=True))
+                del qb
+                done += n
+            ctr4 = bc.Counter(run, device=local, expected_reads=bn)
+            ctr4.set_stream(stream.cuda_stream)
+            job4 = Job(bc, ctr4, run, 1, 0, dev, stream, leg.has_umi, bn)
+            job4.step(binned, to_host=True)
+            ctr4.reset_profile()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                job4.step(binned, to_host=True)
+            torch.cuda.synchronize()
+            dtb = (time.perf_counter() - t0) / 3
+            p4 = ctr4.profile()
+            cb = ctr4.counters()
+            assert sum(cb.values()) == bn, cb
+            ctr4.close()
+            e2e["binned_quality"] = {"value": bn / dtb, "unit": UNIT, "reads": bn, "h2d_bytes_per_read": p4["h2d_bytes"] / 3 / bn,
+                                     "quality_code_bits": binned[0].qual_bits, "counters": cb,
+                                     "what": "the e2e leg on the same reads with their qualities binned to Q2 / Q12 / Q23 / Q37 (four characters -> "
+                                             "2-bit codes in the transfer form)"}
+            del binned
         if old_aff:
             os.sched_setaffinity(0, old_aff)
 
