@@ -107,9 +107,10 @@ class Job:
         if world == 1:
             self.parallelism = "1 GPU"
         elif self.exchange:
-            self.parallelism = (f"reads sharded over {world} GPUs; after the last batch the (key,UMI) records are exchanged once: "
-                                f"owner = hash(key) % {world}, written by the partitioning kernel into the owner GPU's memory over "
-                                f"NVLink; each owner de-duplicates and counts its keys")
+            self.parallelism = (f"reads sharded over {world} GPUs; every batch's (key,UMI) records leave for owner = hash(key) % {world} "
+                                f"right after its decode: a scatter kernel on a side stream writes them into the owner GPU's memory over "
+                                f"NVLink (runs reserved with one atomic on the owner's receive cursor); each owner de-duplicates and "
+                                f"counts its keys; bulk exchange after the last batch when a receive buffer turns out too small")
         else:
             self.parallelism = (f"reads sharded over {world} GPUs; one in-place all-reduce of the dense count table at the end")
         if self.exchange:

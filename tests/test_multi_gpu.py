@@ -66,16 +66,16 @@ def test_cli_devices_on_real_gpus(case, tmp_path):
     got, stdout = run(paths["fastq"], tmp_path / "all", "all", 37)
     assert_same_csv_set(got, exp["files"])
     assert f"Correctly matched sequences: {exp['counters']['matched']:,}" in stdout
-    # the same reads repeated 400 times with their order shuffled: several batches per GPU, real duplicates for the UMI schemes
+    # the same reads repeated 100 times with their order shuffled: several batches per GPU, real duplicates for the UMI schemes
     import random
     lines = open(paths["fastq"]).read().split("\n")
     recs = ["\n".join(lines[i:i + 4]) + "\n" for i in range(0, len(lines) - 3, 4)]
     rng = random.Random(1)
     big = tmp_path / "big.fastq"
     with open(big, "w") as f:
-        for rep in range(400):
+        for rep in range(100):
             rng.shuffle(recs)
             f.write("".join(recs))
-    one, _ = run(big, tmp_path / "one", "0", 20000)
-    many, _ = run(big, tmp_path / "many", "all", 20000)
+    one, _ = run(big, tmp_path / "one", "0", 5000)
+    many, _ = run(big, tmp_path / "many", "all", 5000)
     assert_same_csv_set(many, one)
