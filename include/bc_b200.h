@@ -142,8 +142,8 @@ uint32_t bc_qual_stride(uint32_t max_read_len);
  *   lohi    : n_reads records of 2W words — the lo plane, then the hi plane (both 0 where the read has 'N').
  *   read_len: as in bc_batch (bit 15 = BC_READ_UNSUPPORTED).
  *   N calls : either `nmask`, n_reads records of W words (the N plane), or — nmask == NULL — a list of n_calls
- *             (n_read[i] = read index in the batch, n_pos[i] = base position) pairs; the list pays when N calls are
- *             rarer than one per ~3W/2 reads' worth of plane words, which is every real run.
+ *             (n_read[i] = read index in the batch, n_pos[i] = base position) pairs: 6 bytes per call against 4W bytes
+ *             per read, so the list is the smaller form below about 2W/3 N calls per read — every real run.
  *   qual    : the first bc_wire_qual_codes(max_read_len) quality characters of every read as `qual_bits`-bit codes,
  *             code i at bits [i * qual_bits, (i + 1) * qual_bits) of the record's little-endian bit stream, records of
  *             qual_stride = bc_wire_qual_stride(max_read_len, qual_bits) bytes.  qual_bits 8: the characters themselves;
@@ -271,8 +271,8 @@ int bc_key_decode(const bc_ctx *ctx, uint64_t key_lo, uint64_t key_hi, uint32_t 
  *  dense count table (small index-coded key space without a random barcode, e.g. a CRISPR screen): ranks sum their
  *    tables once — bc_dense_counts + an all-reduce, or bc_peer_add inside one process.
  *
- *  hashed keys (any scheme with a random barcode, raw or large key spaces): ONE exchange of the (key[, UMI]) records.
- *    record -> owner = hash(key without the random barcode) % n_ranks; the partitioning kernel writes each record
+ *  hashed keys (any scheme with a random barcode, raw or large key spaces): every (key[, UMI]) record crosses NVLink once.
+ *    record -> owner = hash(key without the random barcode) % n_ranks; a scatter kernel writes each record
  *    straight into its owner's receive buffer over NVLink peer memory, and every owner then de-duplicates and counts
  *    the keys it owns, so de-duplication is globally exact.  Afterwards a rank's rows are
  *    its owned keys (disjoint across ranks), its matched / duplicates counters are those of the records it owns and
