@@ -2328,13 +2328,14 @@ int bc_exchange_finish(bc_ctx* ctx, uint64_t n_received) {
     CK(ctx, cudaSetDevice(ctx->device));
     const bool wide = ctx->cfg.wide != 0;
     const uint32_t parity = ctx->x_epoch & 1u;
-    if (ctx->x_mode == 1) {  // the senders advanced this buffer's cursor: it must agree with the caller's plan
+    {   // streamed senders advanced this buffer's cursor (also when this rank itself decoded nothing in this job): what arrived
+        // must agree with the caller's plan; a bulk exchange leaves the cursor at 0
         unsigned long long got = 0;
         CK(ctx, cudaMemcpy(&got, xbuf_cursor(ctx, ctx->d_xrecv, parity), sizeof got, cudaMemcpyDeviceToHost));
-        if (got != n_received)
+        if (got != 0 && got != n_received)
             return fail(ctx, BC_ESTATE, "bc_exchange_finish: %llu records arrived, the caller's plan says %llu (was the barrier after the "
                                         "last rank's bc_exchange_count skipped?)", got, (unsigned long long)n_received);
-        CK(ctx, cudaMemset(xbuf_cursor(ctx, ctx->d_xrecv, parity), 0, sizeof got));  // for the job after next
+        if (got) CK(ctx, cudaMemset(xbuf_cursor(ctx, ctx->d_xrecv, parity), 0, sizeof got));  // for the job after next
     }
     unsigned long long* recv = xbuf_lo(ctx, ctx->d_xrecv, parity);
     const FlushSrc in{ItemView{recv, wide ? recv + ctx->xcap : nullptr, nullptr}, n_received, n_received};
