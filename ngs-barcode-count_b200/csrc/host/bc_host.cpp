@@ -2343,6 +2343,15 @@ int bch_count_fastq_multi(bch_run* run, bc_ctx* const* ctxs, int n_ctx, const ch
             if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0) bytes *= 4;
             const uint64_t est_reads = bytes / (2 * (uint64_t)std::max<uint32_t>(run->cfg.template_len, 20) + 16) + 1024;
             cap = est_reads / (uint64_t)n_ctx * 5 / 4 + 4096;
+            // within the exchange's record limit, and at most a quarter of a GPU's free memory for the two receive buffers
+            cap = std::min<uint64_t>(cap, 0xFFFFFFE0ULL);
+            size_t free_b = 0, total_b = 0;
+            if (cudaSetDevice(bc_device_of(ctxs[0])) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b) {
+                const uint64_t per_record = 2 * 8 * (prof.wide_keys ? 2 : 1);
+                cap = std::min<uint64_t>(cap, std::max<uint64_t>(free_b / 4 / per_record, 1u << 16));
+            } else {
+                cudaGetLastError();
+            }
             bool reuse = true;
             for (int r = 0; r < n_ctx; r++) reuse = reuse && bc_exchange_capacity(ctxs[r]) >= cap;
             if (reuse) cap = bc_exchange_capacity(ctxs[0]);
