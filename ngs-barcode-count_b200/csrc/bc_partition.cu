@@ -188,11 +188,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const ItemView in,
     }
 }
 
-// PEER: the bins are owner ranks (F <= kMaxRanks) and bin b's items go to peers.lo/hi[b] — another GPU's receive buffer
-// mapped over NVLink — at the positions the cursors give; a tile's run for one owner is hundreds of consecutive records,
-// so the peer stores leave the SM as full-width transactions.
-template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
-__global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const ItemView in, const ItemView out, const PeerOut peers,
+template <bool WIDE, bool WEIGHTED, int IPT>
+__global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const ItemView in, const ItemView out,
                                                                     const uint32_t* __restrict__ seg_starts, const uint32_t workers,
                                                                     const unsigned long long n_total, const SplitLevel lv,
                                                                     uint32_t* __restrict__ bins) {
@@ -200,7 +197,6 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
     extern __shared__ __align__(16) unsigned long long split_stage[];  // [lo | hi | w] x T u64, then T u32 positions
     __shared__ uint32_t s_hist[1u << kSplitMaxBits], s_delta[1u << kSplitMaxBits];
     __shared__ uint32_t s_warp[kScatterThreads / 32];
-    __shared__ uint32_t s_fits;  // PEER, streamed: bit b = this tile's run fits owner b's buffer
     const uint32_t seg = blockIdx.x / workers, worker = blockIdx.x % workers;
     const unsigned long long a = seg_starts ? (unsigned long long)seg_starts[seg] : 0ULL;
     const unsigned long long e = seg_starts ? (unsigned long long)seg_starts[seg + 1] : n_total;
@@ -222,7 +218,6 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
             w[k] = WEIGHTED ? (i < e ? in.w[i] : 0ULL) : 0ULL;
         }
         for (uint32_t b = tid; b < F; b += kScatterThreads) s_hist[b] = 0;
-        if (PEER && tid == 0) s_fits = 0xFFFFFFFFu;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
@@ -260,20 +255,7 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
         for (int k = 0; k < 8; k++) {
             const uint32_t b = tid * per + k;
             if (k < (int)per && b < F) {
-                uint32_t g = 0u;
-                if (PEER && peers.cursor[b]) {
-                    if (c[k]) {
-                        const unsigned long long at = atomicAdd_system(peers.cursor[b], (unsigned long long)c[k]);
-                        atomicAdd(&peers.sent[b], (unsigned long long)c[k]);
-                        if (at + c[k] > peers.cap) {
-                            atomicAnd(&s_fits, ~(1u << b));
-                            atomicExch(peers.overflow, 1u);
-                        }
-                        g = (uint32_t)at;
-                    }
-                } else if (c[k]) {
-                    g = atomicAdd(&my_bins[b], c[k]);
-                }
+                const uint32_t g = c[k] ? atomicAdd(&my_bins[b], c[k]) : 0u;
                 s_delta[b] = g - off;  // output position = s_delta[bin] + position in the sorted tile
                 s_hist[b] = off;       // becomes the bin's cursor inside the sorted tile
                 off += c[k];
@@ -293,17 +275,9 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
         __syncthreads();
         for (uint32_t j = tid; j < n_tile; j += kScatterThreads) {
             const uint32_t pos = st_pos[j];
-            if (PEER) {  // the sorted tile is in bin order and s_hist[b] is now the end of bin b's run: count the runs that end at or before j
-                uint32_t b = 0;
-                for (uint32_t q = 0; q + 1 < F; q++) b += j >= s_hist[q];
-                if (!((s_fits >> b) & 1u)) continue;
-                peers.lo[b][pos] = st_lo[j];
-                if (WIDE) peers.hi[b][pos] = st_hi[j];
-            } else {
-                out.lo[pos] = st_lo[j];
-                if (WIDE) out.hi[pos] = st_hi[j];
-                if (WEIGHTED) out.w[pos] = st_w[j];
-            }
+            out.lo[pos] = st_lo[j];
+            if (WIDE) out.hi[pos] = st_hi[j];
+            if (WEIGHTED) out.w[pos] = st_w[j];
         }
         __syncthreads();
     }
@@ -314,7 +288,7 @@ __global__ void __launch_bounds__(kScatterThreads, 3) k_split_scatter(const Item
 // item.  Here a thread counts its items per owner in registers (8 x 16-bit fields in two words), a warp scan and one
 // word pair per warp in shared memory turn the counts into every thread's own offsets inside the owner-sorted tile, and
 // a thread places its items with register arithmetic only: no shared-memory atomics, a quarter of the instructions.
-// Runs are reserved as in k_split_scatter<PEER>: streamed, with one system-scope atomic on the owner's receive cursor
+// Runs are reserved like k_split_scatter's, per tile and bin: streamed, with one system-scope atomic on the owner's receive cursor
 // (peers.cursor[b], in the owner's memory); bulk, on the local cursors that the host primed with the plan's positions.
 __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long v, int d) {
     const uint32_t lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)v, d), hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), d);
@@ -920,17 +894,17 @@ cudaError_t launch_seg_scan(const uint32_t* hist, uint32_t n_seg, uint32_t bins_
     return cudaGetLastError();
 }
 
-template <bool WIDE, bool WEIGHTED, int IPT, bool PEER>
-static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const PeerOut& peers, const uint32_t* seg_starts,
+template <bool WIDE, bool WEIGHTED, int IPT>
+static cudaError_t launch_scatter_t(unsigned grid, const ItemView& in, const ItemView& out, const uint32_t* seg_starts,
                                     uint32_t workers, unsigned long long n_total, const SplitLevel& lv, uint32_t* bins, cudaStream_t stream) {
     constexpr size_t T = (size_t)kScatterThreads * IPT;
     const size_t smem = T * 8 * (1 + (WIDE ? 1 : 0) + (WEIGHTED ? 1 : 0)) + T * 4;
-    cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(k_split_scatter<WIDE, WEIGHTED, IPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    k_split_scatter<WIDE, WEIGHTED, IPT, PEER><<<grid, kScatterThreads, smem, stream>>>(in, out, peers, seg_starts, workers, n_total, lv, bins);
+    k_split_scatter<WIDE, WEIGHTED, IPT><<<grid, kScatterThreads, smem, stream>>>(in, out, seg_starts, workers, n_total, lv, bins);
     return cudaGetLastError();
 }
 
@@ -960,11 +934,10 @@ cudaError_t launch_split(bool scatter, bool wide, const ItemView& in, const Item
         else k_split_hist<false><<<grid, kSplitThreads, 0, stream>>>(in, seg_starts, w, n_total, lv, bins, stats, count_valid);
         return cudaGetLastError();
     }
-    const PeerOut none{};
-    if (wide) return weighted ? launch_scatter_t<true, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
-                              : launch_scatter_t<true, false, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
-    return weighted ? launch_scatter_t<false, true, 8, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream)
-                    : launch_scatter_t<false, false, BC_SCATTER_IPT, false>(grid, in, out, none, seg_starts, w, n_total, lv, bins, stream);
+    if (wide) return weighted ? launch_scatter_t<true, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
+                              : launch_scatter_t<true, false, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
+    return weighted ? launch_scatter_t<false, true, 8>(grid, in, out, seg_starts, w, n_total, lv, bins, stream)
+                    : launch_scatter_t<false, false, BC_SCATTER_IPT>(grid, in, out, seg_starts, w, n_total, lv, bins, stream);
 }
 
 // Exchange step of a multi-GPU job: this rank's records -> their owners' receive buffers.  owner = digit of `lv`
