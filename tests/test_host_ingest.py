@@ -219,3 +219,19 @@ def test_line_end_scanner_simd_levels(tmp_path, level):
                 assert bc.walk_fastq(str(p), threads=6, chunk_bytes=chunk, batch_rows=rows)[:3] == digest_of(data)
     finally:
         lib.bch_set_simd_level(2)
+
+
+@pytest.mark.parametrize("tail", [b"\n", b"\n\n", b"\n\n\n", b"@partial\nACGT\n", b"@partial\nACGT\n+\n", b"\n\n\n\n"])
+def test_readers_agree_on_ragged_file_ends(tmp_path, tail):
+    """Blank lines and a partial record after the last whole one: the block reader, the mapped-file splitter and the
+    one-pass walker frame the same records (the reference takes lines four at a time and never posts an incomplete group,
+    input.rs:44-60; four blank lines ARE a group: an empty read)."""
+    data, want = make_fastq(1000, 3)
+    p = tmp_path / "t.fastq"
+    p.write_bytes(data + tail)
+    extra = 1 if tail == b"\n\n\n\n" else 0
+    a = bc.scan_fastq(str(p))
+    b = bc.split_fastq(str(p), threads=4, block_bytes=50_000, min_slice=1000)
+    c = bc.walk_fastq(str(p), threads=4, chunk_bytes=5000, batch_rows=300)
+    assert a[:2] == b[:2] == c[:2] == (want[0] + extra, want[1])
+    assert a[2] == b[2]
