@@ -6,12 +6,15 @@
 
 A step is one pass of the whole job over the workload's reads: reset, decode every batch, de-duplicate + count (the
 flush), extract the (key, count) rows.  `value` has the packed reads resident in HBM when the timed region starts (CUDA
-events); `e2e` runs the same job through the C ABI from pinned HOST batches (H2D of every batch and D2H of the result
-rows inside the timed region, wall clock between device synchronisations).  One process per GPU; reads are sharded
-across ranks (weak scaling).  With hashed keys (any scheme with a random barcode) the records are exchanged ONCE per job,
-after the last batch: the partitioning kernel writes each record into the receive buffer of its owner rank
-hash(key) % N over NVLink peer memory and every owner de-duplicates what it owns, so de-duplication is globally exact;
-dense count tables (CRISPR) merge with one all-reduce.  For N > 1 the line carries `parity_n_ranks`: the N-rank job and
+events); `e2e` runs the same job through the C ABI from pinned HOST batches — in their transfer form (bc_submit_wire:
+159 instead of 218 bytes per read across PCIe) unless --e2e-form plain — with the H2D of every batch and the D2H of the
+result rows inside the timed region, wall clock between device synchronisations; `e2e.binned_quality` repeats it on the
+same reads with binned qualities (2-bit codes); `e2e_fastq` starts from a FASTQ file (host framing + packing included,
+phases of the ingest thread reported).  One process per GPU; reads are sharded across ranks (weak scaling).  With hashed
+keys (any scheme with a random barcode) every batch's records leave for their owner rank hash(key) % N right after its
+decode — a scatter kernel on a side stream writes them into the owner's receive buffer over NVLink peer memory — and
+every owner de-duplicates what it owns, so de-duplication is globally exact; dense count tables (CRISPR) merge with one
+all-reduce.  For N > 1 the line carries `parity_n_ranks`: the N-rank job and
 a single-GPU job over the same reads (a reduced range) must have identical counters and the same row digest.
 """
 import argparse
